@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""Headline benchmark: RAFT-Stereo inference on KITTI-sized pairs (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's B200 path
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU
+
+One "step" = one full stereo forward (feature encoder, correlation pyramid build, 32 GRU iterations
+each with a fused 4-level radius-4 lookup, convex upsampling of every iteration as the reference's
+``forward`` does) over a batch of 8 synthetic 375x1242 pairs per GPU (padded to 384x1248 like the
+reference's ``evaluate.py``), random-init weights of the reference architecture (seed 0).
+
+Prints ONE JSON line (rank 0).  ``value`` = pairs/s with inputs resident in HBM; ``e2e`` = pairs/s
+through ``StereoEngine.infer`` with pinned HOST buffers (H2D + D2H inside the timed region);
+``roofline`` = the per-iteration lookup kernel against measured HBM bandwidth; ``cpu_baseline`` = the
+oracle port (torch CPU ops, all host threads) on a bounded sample.  Multi-GPU: one process per GPU
+(torchrun), batch-sharded, no data-path collective; the only NCCL call gathers the output maps.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PAIRS_PER_GPU = 8
+IMAGE_HW = (375, 1242)
+ITERS = 32
+METRIC = "RAFT-Stereo KITTI 375x1242 32-iter inference throughput"
+UNIT = "pairs/s"
+LOOKUP_BYTES_PER_PIXEL = 308      # 4*(2r+2)*4 window + 4 coords + 36*4 out
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": "BASELINE configs[1]: RAFT-Stereo full inference, KITTI 375x1242 (padded 384x1248), "
+                    "32 GRU iterations, batch 8 synthetic pairs per GPU",
+        "pairs_per_gpu": PAIRS_PER_GPU, "global_pairs": PAIRS_PER_GPU * n_gpus, "image": list(IMAGE_HW),
+        "iters": ITERS, "weights": "random init (seed 0) of the reference BaseRAFTStereo architecture",
+        "parallelism": f"batch-sharded x{n_gpus}, no data-path collective, one all_gather of the disparity maps",
+        "l2": "activations per iteration (>> 126 MB L2) evict the pyramid between lookups; the isolated "
+              "lookup timing flushes L2 (256 MB write) before every timed launch",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    REASONS = {0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nv = None
+
+    def run(self):
+        if self._nv is None:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(self._nv.nvmlDeviceGetClockInfo(self._h, self._nv.NVML_CLOCK_SM))
+                mask = self._nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def physical_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference / baseline leg (oracle port; the only place bench.py executes oracle/)
+# ------------------------------------------------------------------------------------------------
+def cpu_forward_seconds(steps, warmup, pairs=1):
+    """Seconds per step of the reference algorithm on the host: model shell + oracle correlation."""
+    from nndepth_b200.raft_stereo import BaseRAFTStereo
+    from nndepth_b200.engine import Padder
+    from oracle import torch_port
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    model = BaseRAFTStereo(iters=ITERS).eval()
+    model.corr_fn = torch_port.CorrBlock1D
+    gen = torch.Generator().manual_seed(1)
+    left = torch.rand((pairs, 3) + IMAGE_HW, generator=gen) * 2 - 1
+    right = torch.rand((pairs, 3) + IMAGE_HW, generator=gen) * 2 - 1
+    padder = Padder(left.shape, 32)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            lp, rp = padder.pad(left, right)
+            out = padder.unpad(model(lp, rp)[-1]["up_disp"])
+            float(out.sum())
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    return sum(times) / len(times), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sec, threads = cpu_forward_seconds(args.steps, args.warmup, pairs=1)
+    value = 1.0 / sec
+    sample = f"1 pair of {IMAGE_HW[0]}x{IMAGE_HW[1]} per step ({ITERS} iterations), {args.steps} timed steps"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# isolated lookup kernel timing (roofline leg)
+# ------------------------------------------------------------------------------------------------
+def time_lookup_kernel(device, reps=40):
+    import nndepth_b200 as nb
+    B, C, H, W = PAIRS_PER_GPU, 256, 48, 156
+    torch.manual_seed(3)
+    f1 = torch.randn(B, C, H, W, device=device)
+    f2 = torch.randn(B, C, H, W, device=device)
+    blk = nb.CorrBlock1D(f1, f2, 4, 4)
+    coords = (torch.arange(W, device=device).float().view(1, 1, 1, W).repeat(B, 1, H, 1)
+              - torch.rand(B, 1, H, W, device=device) * 40)
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=device)   # 256 MB > L2
+    stream = torch.cuda.current_stream(device)
+    for _ in range(5):
+        blk(coords)
+    cold, warm = [], []
+    for _ in range(reps):
+        flush.fill_(1.0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        blk(coords)
+        e1.record(stream)
+        e1.synchronize()
+        cold.append(e0.elapsed_time(e1))
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        blk(coords)
+        e1.record(stream)
+        e1.synchronize()
+        warm.append(e0.elapsed_time(e1))
+    build = []
+    for _ in range(10):
+        flush.fill_(1.0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        nb.CorrBlock1D(f1, f2, 4, 4)
+        e1.record(stream)
+        e1.synchronize()
+        build.append(e0.elapsed_time(e1))
+    n_pix = B * H * W
+    return {"lookup_ms_l2_flushed": statistics.median(cold), "lookup_ms_l2_warm": statistics.median(warm),
+            "build_ms_l2_flushed": statistics.median(build), "pixels": n_pix,
+            "lookup_bytes": n_pix * LOOKUP_BYTES_PER_PIXEL,
+            "build_bytes": 2 * B * C * H * W * 4 + B * H * W * (156 + 78 + 39 + 19) * 4,
+            "build_flops": 2 * B * H * W * W * C}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """Per-launch DRAM bytes of the lookup kernel from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "lookup_traffic.json")) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------------
+# main arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import nndepth_b200 as nb
+    from nndepth_b200 import _lib
+    from nndepth_b200.engine import StereoEngine, gather_disparities
+    from nndepth_b200.raft_stereo import BaseRAFTStereo
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: nndepth_b200 has no CPU fallback "
+                         "(use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    nb.load_library()
+    if args.volume_precision:
+        nb.set_volume_precision(args.volume_precision)
+
+    torch.manual_seed(0)
+    model = BaseRAFTStereo(iters=ITERS).eval()
+    engine = StereoEngine(model, device=device, use_cuda_graph=not args.no_graph)
+    gen = torch.Generator().manual_seed(1 + rank)
+    host_l = (torch.rand((PAIRS_PER_GPU, 3) + IMAGE_HW, generator=gen) * 2 - 1).pin_memory()
+    host_r = (torch.rand((PAIRS_PER_GPU, 3) + IMAGE_HW, generator=gen) * 2 - 1).pin_memory()
+    dev_l, dev_r = host_l.to(device), host_r.to(device)
+    stream = torch.cuda.current_stream(device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    def step_device():
+        disp = engine.infer_device(dev_l, dev_r)
+        return gather_disparities(disp, world) if world > 1 else disp
+
+    def step_host():
+        return engine.infer(host_l, host_r)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize(device)
+        wall = time.perf_counter() - t0
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1), wall * 1e3], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms[0].item(), ms[1].item()
+
+    # launches of this repo's kernels per forward (counted on an eager forward, same path the graph captured)
+    before = _lib.launch_count()
+    engine.use_cuda_graph, keep = False, engine.use_cuda_graph
+    step_device()
+    engine.use_cuda_graph = keep
+    launches_per_step = _lib.launch_count() - before
+
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        step_device()
+    barrier()
+    sampler.start()
+    dev_ms, _ = timed(step_device, args.steps, 0)
+    clocks = sampler.stop()
+    _, host_wall_ms = timed(step_host, args.steps, 2)
+
+    total_pairs = PAIRS_PER_GPU * world * args.steps
+    value = total_pairs / (dev_ms / 1e3)
+    e2e_value = total_pairs / (host_wall_ms / 1e3)
+
+    line = None
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        kern = time_lookup_kernel(device)
+        achieved = kern["lookup_bytes"] / (kern["lookup_ms_l2_flushed"] * 1e-3) / 1e9
+        cpu = None
+        if world == 1 and not args.skip_cpu_baseline:
+            sec, threads = cpu_forward_seconds(steps=2, warmup=1, pairs=1)
+            cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"1 pair of {IMAGE_HW[0]}x{IMAGE_HW[1]}, {ITERS} iterations, 2 timed forwards "
+                             f"(model shell in torch CPU ops + oracle/torch_port.py correlation)"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": warm, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "f32 (volume operands %s; cuDNN convs allow_tf32=%s)" % (nb.get_volume_precision(),
+                                                                            torch.backends.cudnn.allow_tf32),
+            "data": "synthetic", "config": workload_config(world), "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": 2 * host_l.numel() * 4, "d2h_bytes_per_step": PAIRS_PER_GPU * IMAGE_HW[0] * IMAGE_HW[1] * 4,
+                    "ms_per_step": host_wall_ms / args.steps},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": {"kernel": "pyramid_lookup_kernel<4,9> (nnd_corr1d_lookup)", "bound": "hbm",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic(), "peak_source": peak_src,
+                         "us_per_launch_l2_flushed": kern["lookup_ms_l2_flushed"] * 1e3,
+                         "us_per_launch_l2_warm": kern["lookup_ms_l2_warm"] * 1e3,
+                         "algorithmic_bytes_per_launch": kern["lookup_bytes"]},
+            "build": {"kernel": "nnd_corr1d_build (%s)" % nb.get_volume_precision(),
+                      "us_per_launch_l2_flushed": kern["build_ms_l2_flushed"] * 1e3,
+                      "hbm_gbs": kern["build_bytes"] / (kern["build_ms_l2_flushed"] * 1e-3) / 1e9,
+                      "tflops": kern["build_flops"] / (kern["build_ms_l2_flushed"] * 1e-3) / 1e12},
+            "cuda_graph": engine.use_cuda_graph,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--volume-precision", default=None, choices=["fp32", "tf32"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

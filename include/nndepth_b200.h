@@ -1,0 +1,140 @@
+/*
+ * nndepth_b200.h -- C ABI of the B200-native stereo-correlation hot path.
+ *
+ * The reference (anhtu293/nndepth) is pure Python/PyTorch and has NO plugin / FFI boundary of its
+ * own; the drop-in boundary is the constructor/__call__ of its correlation classes.
+ * Each entry point below therefore cites the reference *function* it replaces (file:line relative to
+ * the reference root) -- the Python mirror classes in nndepth_b200/ are the only callers.
+ *
+ * Conventions
+ *   - plain C types only: device pointers, ints, an opaque stream handle (a cudaStream_t);
+ *   - every tensor is dense fp32 in the layout named per function; "pitch" = row stride in floats;
+ *   - nothing here allocates device memory that outlives the call, except TMA descriptors cached
+ *     per shape inside the library; outputs are caller-allocated; inputs are never written;
+ *   - all work is enqueued on `stream`, no host synchronisation (CUDA-graph capturable);
+ *   - return value: NND_OK or an error code; nnd_last_error_string() describes the last failure of
+ *     the calling thread.  Nothing throws or aborts across this boundary.
+ *   - there is no CPU fallback: on a machine without a CUDA device every compute entry point
+ *     returns NND_ERR_CUDA.
+ */
+#ifndef NNDEPTH_B200_H
+#define NNDEPTH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NND_ABI_VERSION 1
+#define NND_MAX_LEVELS 8
+
+typedef int nnd_status;
+enum {
+  NND_OK = 0,
+  NND_ERR_INVALID_ARGUMENT = 1,
+  NND_ERR_UNSUPPORTED = 2,
+  NND_ERR_CUDA = 3
+};
+
+/* precision of the volume contraction (operands; accumulation is always fp32) */
+enum {
+  NND_PREC_FP32 = 0,  /* CUDA-core FFMA, bit-for-bit fp32 operands (parity mode, 1e-5 bar)        */
+  NND_PREC_TF32 = 1   /* tcgen05 kind::tf32, operands truncated to 10-bit mantissa (1e-3 bar)     */
+};
+
+typedef struct CUstream_st* nnd_stream_t; /* == cudaStream_t */
+
+int nnd_abi_version(void);
+const char* nnd_last_error_string(void);
+
+/* Number of floats the caller must allocate for a pyramid row at level width `w` (16-byte rows). */
+int nnd_row_pitch(int width);
+
+/* ------------------------------------------------------------------------------------------------
+ * RAFT-Stereo 1-D correlation pyramid.
+ * Replaces CorrBlock1D.corr + CorrBlock1D.__init__, nndepth/models/raft_stereo/cost_volume.py:55-61,
+ * :12-34 (torch.matmul / C**0.5, then avg_pool1d(.,2) per level) in ONE pass: the volume is written
+ * once and the pooled levels come out of the same epilogue.
+ *   fmap1 (B,C,H,W1), fmap2 (B,C,H,W2) NCHW contiguous.
+ *   level[l] (l < num_levels): rows = B*H*W1, width w_l = W2 >> l (floor), row pitch pitch[l] floats.
+ *   num_levels in [1, NND_MAX_LEVELS]; every written level must have width >= 1.
+ * ---------------------------------------------------------------------------------------------- */
+nnd_status nnd_corr1d_build(const float* fmap1, const float* fmap2, int B, int C, int H, int W1, int W2,
+                            int num_levels, int precision, float* const* level, const int* pitch,
+                            nnd_stream_t stream);
+
+/* Grouped variant.  Replaces GroupCorrBlock1D.corr / GeometryAwareCostVolume.build_cost_volume,
+ * raft_stereo/cost_volume.py:113-128 and igev_stereo/cost_volume.py:81-98: group g contracts
+ * channels [g*group_size, (g+1)*group_size) and divides by `scale_div` (sqrt(C) resp. sqrt(G)).
+ *   level[l]: rows ordered [b][g][h][w1], width W2 >> l. */
+nnd_status nnd_groupcorr_build(const float* fmap1, const float* fmap2, int B, int C, int H, int W1, int W2,
+                               int num_groups, int group_size, float scale_div, int num_levels,
+                               float* const* level, const int* pitch, nnd_stream_t stream);
+
+/* avg_pool1d(x, 2) of `rows` rows: dst[r][j] = (src[r][2j] + src[r][2j+1]) / 2, j < src_width/2.
+ * Replaces F.avg_pool1d at raft_stereo/cost_volume.py:33 for levels beyond the fused ones. */
+nnd_status nnd_avgpool_pairs(const float* src, int src_width, int src_pitch, float* dst, int dst_pitch,
+                             int64_t rows, nnd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused pyramid lookup: all levels, all 2r+1 taps, NCHW output, one launch.
+ * Replaces CorrBlock1D.__call__ raft_stereo/cost_volume.py:36-53 + linear_sampler
+ * raft_stereo/utils.py:4-27.
+ *   level[l] rows [b][h][w1] (rows = B*H*W1), widths width[l] >= 2, pitches pitch[l].
+ *   coords (B,1,H,W1) -> out (B, num_levels*(2r+1), H, W1), channel = l*(2r+1)+k.
+ * Index contract: t = clamp(x/(w-1),0,1)*(w-1) with IEEE fp32 div and mul; i0=floor(t), i1=ceil(t).
+ * ---------------------------------------------------------------------------------------------- */
+nnd_status nnd_corr1d_lookup(const float* const* level, const int* width, const int* pitch,
+                             const float* coords, int B, int H, int W1, int num_levels, int radius,
+                             float* out, nnd_stream_t stream);
+
+/* Debug/parity twin of the lookup: writes the int32 window indices instead of values.
+ *   idx0, idx1: (num_levels, B*H*W1, 2r+1) int32. */
+nnd_status nnd_corr1d_lookup_indices(const int* width, const float* coords, int B, int H, int W1,
+                                     int num_levels, int radius, int32_t* idx0, int32_t* idx1,
+                                     nnd_stream_t stream);
+
+/* Grouped lookups over rows ordered [b][g][h][w1] (G groups share the pixel's coordinate).
+ *   mode 0: IGEV dual lookup, GeometryAwareCostVolume.forward igev_stereo/cost_volume.py:54-79:
+ *           two pyramids (feat, geo) -> out (B, L*2*G*T, H, W), channel l*(2GT) + src*(GT) + g*T + k.
+ *           `level_b` = geometry pyramid.
+ *   mode 1: GroupCorrBlock1D.__call__ raft_stereo/cost_volume.py:92-111: one pyramid, output is the
+ *           reference's memory reinterpretation of [b][g][h][w][k] as (B,H,W,G*T) per level
+ *           (cost_volume.py:108), then NCHW.  `level_b` ignored (may be NULL). */
+nnd_status nnd_group_lookup(const float* const* level_a, const float* const* level_b, const int* width,
+                            const int* pitch, const float* coords, int B, int G, int H, int W1,
+                            int num_levels, int radius, int mode, float* out, nnd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * IGEV geometry volume: regulariser output (B,G,D,H,W1) -> pyramid rows [b][g][h][w1] x D (+pooled).
+ * Replaces the permute/reshape/avg_pool1d chain at igev_stereo/cost_volume.py:44-52.
+ * ---------------------------------------------------------------------------------------------- */
+nnd_status nnd_geo_transpose_pool(const float* geo, int B, int G, int D, int H, int W1, int num_levels,
+                                  float* const* level, const int* pitch, nnd_stream_t stream);
+
+/* Soft-argmin: out[b,0,h,w] = -sum_d d * softmax_d(z[b,d,h,w]).  Single pass, online softmax.
+ * Replaces F.softmax(dim=1) + regress_disparity, igev_stereo/model.py:145 and :92-95.
+ *   z (B,D,H,W) -> out (B,1,H,W). */
+nnd_status nnd_soft_argmin(const float* z, int B, int D, int H, int W, float* out, nnd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * CREStereo AGCL.  fmap1/fmap2 (N,C,H,W) NCHW, C % 4 == 0; flow (N,2,H,W) (x, y);
+ * out (N, 36, H, W), channel g*9 + k; small_patch: 0 = 1x9 window, 1 = 3x3 window.
+ *   nnd_agcl_offset: AGCL.corr_att_offset nndepth/models/cre_stereo/cost_volume.py:81-154 (the
+ *     optional attention is applied by the caller beforehand); extra_offset (N,18,H,W).
+ *   nnd_agcl_iter:   AGCL.corr_iter :54-79 + get_correlation :28-52 (warp by flow, replicate-padded
+ *     local window).
+ * Samplers follow bilinear_sampler / bilinear_grid_sample cre_stereo/utils.py:5-107 (zero padding,
+ * align_corners=True, fp32 normalise/denormalise round trip kept for bit-exact corner indices).
+ * ---------------------------------------------------------------------------------------------- */
+nnd_status nnd_agcl_offset(const float* fmap1, const float* fmap2, const float* flow,
+                           const float* extra_offset, int N, int C, int H, int W, int small_patch,
+                           float* out, nnd_stream_t stream);
+nnd_status nnd_agcl_iter(const float* fmap1, const float* fmap2, const float* flow, int N, int C, int H,
+                         int W, int small_patch, float* out, nnd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NNDEPTH_B200_H */

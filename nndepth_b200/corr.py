@@ -1,0 +1,297 @@
+"""RAFT-Stereo correlation blocks on the sm_100a kernels -- drop-in for the reference classes.
+
+Mirrors ``nndepth/models/raft_stereo/cost_volume.py`` of the reference: ``CorrBlock1D`` (:7-61),
+``GroupCorrBlock1D`` (:64-128) and ``linear_sampler`` (``raft_stereo/utils.py:4-27``).  Same
+constructor / ``__call__`` signatures, attributes (``num_levels``, ``radius``, ``corr_pyramid``) and
+output layout, so ``model.corr_fn = nndepth_b200.CorrBlock1D`` swaps the reference model onto these
+kernels (``raft_stereo/model.py:58,124,132``).
+
+Differences by design: one launch builds the volume *and* its pooled levels; one launch per GRU
+iteration does the whole 4-level lookup; rows of the pyramid are padded to 16 bytes (``corr_pyramid``
+hides the padding); inference only (no autograd).
+"""
+import math
+
+import torch
+
+from . import _lib
+
+_VOLUME_PRECISION = "fp32"
+
+
+def set_volume_precision(precision):
+    """``"fp32"`` (CUDA-core FFMA, 1e-5 parity bar) or ``"tf32"`` (tcgen05 tensor cores, 1e-3 bar)."""
+    global _VOLUME_PRECISION
+    if precision not in ("fp32", "tf32"):
+        raise ValueError(f"precision must be 'fp32' or 'tf32', got {precision!r}")
+    _VOLUME_PRECISION = precision
+
+
+def get_volume_precision():
+    return _VOLUME_PRECISION
+
+
+def _prec_code(precision):
+    precision = precision or _VOLUME_PRECISION
+    if precision not in ("fp32", "tf32"):
+        raise ValueError(f"precision must be 'fp32' or 'tf32', got {precision!r}")
+    return _lib.PREC_TF32 if precision == "tf32" else _lib.PREC_FP32
+
+
+class PyramidStorage:
+    """``num_levels`` pooled levels of ``rows`` volume rows in ONE device allocation.
+
+    Level ``l`` is a ``(rows, pitch_l)`` fp32 matrix whose first ``width0 >> l`` columns are valid
+    (``pitch_l`` = width rounded up to 4 floats so every row starts 16-byte aligned).
+    """
+
+    def __init__(self, rows, width0, num_levels, device):
+        if not 1 <= num_levels <= _lib.NND_MAX_LEVELS:
+            raise ValueError(f"num_levels must be in [1, {_lib.NND_MAX_LEVELS}], got {num_levels}")
+        self.rows = int(rows)
+        self.widths = [int(width0) >> l for l in range(num_levels)]
+        if self.widths[-1] < 1:
+            raise ValueError(f"a {num_levels}-level pyramid of width {width0} has an empty level")
+        self.pitches = [_lib.row_pitch(w) for w in self.widths]
+        self.buffer = torch.empty(self.rows * sum(self.pitches), dtype=torch.float32, device=device)
+        self.levels = []
+        start = 0
+        for p in self.pitches:
+            self.levels.append(self.buffer[start:start + self.rows * p].view(self.rows, p))
+            start += self.rows * p
+        self._extra = None
+        self._level_ptrs = _lib.ptr_array(self.levels)
+        self._width_arr = _lib.int_array(self.widths)
+        self._pitch_arr = _lib.int_array(self.pitches)
+
+    @property
+    def num_levels(self):
+        return len(self.levels)
+
+    def load(self, levels):
+        """Copy caller-provided levels (``(rows, w_l)`` or ``(rows, 1, w_l)`` tensors) into the padded storage."""
+        for dst, w, src in zip(self.levels, self.widths, levels):
+            src = torch.as_tensor(src).reshape(self.rows, -1)
+            if src.shape[1] != w:
+                raise RuntimeError(f"pyramid level has width {src.shape[1]}, expected {w}")
+            dst[:, :w] = src.to(device=dst.device, dtype=torch.float32)
+        return self
+
+    def reference_view(self):
+        """The reference's list: ``num_levels + 1`` tensors ``(rows, 1, w_l)`` (cost_volume.py:29-34).
+
+        The last level is never read by the reference's ``__call__``; it is pooled on first access.
+        """
+        views = [lv[:, None, :w] for lv, w in zip(self.levels, self.widths)]
+        if self._extra is None:
+            w_last = self.widths[-1]
+            if w_last < 2:
+                raise RuntimeError("avg_pool1d(kernel 2) of a 1-wide level: output size would be 0")
+            pitch = _lib.row_pitch(w_last // 2)
+            extra = torch.empty(self.rows, pitch, dtype=torch.float32, device=self.buffer.device)
+            with torch.cuda.device(self.buffer.device):
+                _lib.check(
+                    _lib.load().nnd_avgpool_pairs(_lib.ptr(self.levels[-1]), w_last, self.pitches[-1], _lib.ptr(extra),
+                                                  pitch, self.rows, _lib.stream_ptr(extra)),
+                    "nnd_avgpool_pairs",
+                )
+            self._extra = extra
+        views.append(self._extra[:, None, :self.widths[-1] // 2])
+        return views
+
+
+def _check_coords(coords, B, H, W1):
+    coords = _lib.as_cuda_f32(coords, "coords")
+    if coords.dim() != 4 or coords.shape[1] != 1:
+        raise RuntimeError(f"coords must be (B, 1, H, W), got {tuple(coords.shape)}")
+    if tuple(coords.shape) != (B, 1, H, W1):
+        raise RuntimeError(f"coords shape {tuple(coords.shape)} does not match the volume's (B,1,H,W1) = {(B, 1, H, W1)}")
+    return coords
+
+
+class CorrBlock1D:
+    """All-pairs 1-D correlation pyramid + fused radius-r lookup (reference cost_volume.py:7-61)."""
+
+    def __init__(self, fmap1, fmap2, num_levels=4, radius=4, precision=None):
+        self.num_levels = num_levels
+        self.radius = radius
+        f1 = _lib.as_cuda_f32(fmap1, "fmap1")
+        f2 = _lib.as_cuda_f32(fmap2, "fmap2")
+        if f1.dim() != 4 or f2.dim() != 4:
+            raise RuntimeError("fmap1 and fmap2 must be (B, C, H, W)")
+        if f1.shape[:3] != f2.shape[:3] or f1.device != f2.device:
+            raise RuntimeError(
+                f"fmap1 {tuple(f1.shape)} and fmap2 {tuple(f2.shape)} must agree in batch, channels and height"
+            )
+        B, C, H, W1 = f1.shape
+        W2 = f2.shape[3]
+        self._shape = (B, H, W1, W2)
+        self._pyr = PyramidStorage(B * H * W1, W2, num_levels, f1.device)
+        with torch.cuda.device(f1.device):
+            _lib.check(
+                _lib.load().nnd_corr1d_build(_lib.ptr(f1), _lib.ptr(f2), B, C, H, W1, W2, num_levels,
+                                             _prec_code(precision), self._pyr._level_ptrs, self._pyr._pitch_arr,
+                                             _lib.stream_ptr(f1)),
+                "nnd_corr1d_build",
+            )
+
+    @classmethod
+    def from_pyramid(cls, levels, batch, height, num_levels=4, radius=4, device="cuda"):
+        """Wrap an existing pyramid (list of ``(B*H*W1, w_l)`` arrays/tensors) -- used by the parity tests."""
+        self = cls.__new__(cls)
+        self.num_levels, self.radius = num_levels, radius
+        first = torch.as_tensor(levels[0])
+        rows, W2 = first.reshape(first.shape[0], -1).shape
+        self._shape = (batch, height, rows // (batch * height), W2)
+        self._pyr = PyramidStorage(rows, W2, num_levels, torch.device(device)).load(levels[:num_levels])
+        return self
+
+    @property
+    def corr_pyramid(self):
+        return self._pyr.reference_view()
+
+    def __call__(self, coords):
+        B, H, W1, _ = self._shape
+        coords = _check_coords(coords, B, H, W1)
+        T = 2 * self.radius + 1
+        out = torch.empty(B, self.num_levels * T, H, W1, dtype=torch.float32, device=coords.device)
+        with torch.cuda.device(coords.device):
+            _lib.check(
+                _lib.load().nnd_corr1d_lookup(self._pyr._level_ptrs, self._pyr._width_arr, self._pyr._pitch_arr,
+                                              _lib.ptr(coords), B, H, W1, self.num_levels, self.radius, _lib.ptr(out),
+                                              _lib.stream_ptr(coords)),
+                "nnd_corr1d_lookup",
+            )
+        return out
+
+    def lookup_indices(self, coords):
+        """Debug/parity helper: the int32 ``(idx0, idx1)`` of every tap, each ``(L, B*H*W1, 2r+1)``."""
+        B, H, W1, _ = self._shape
+        coords = _check_coords(coords, B, H, W1)
+        return lookup_indices(self._pyr.widths, coords, self.num_levels, self.radius)
+
+    @staticmethod
+    def corr(fmap1, fmap2, precision=None):
+        """``(B, H, W1, W2)`` volume only (reference cost_volume.py:55-61)."""
+        f1 = _lib.as_cuda_f32(fmap1, "fmap1")
+        f2 = _lib.as_cuda_f32(fmap2, "fmap2")
+        B, C, H, W1 = f1.shape
+        W2 = f2.shape[3]
+        pyr = PyramidStorage(B * H * W1, W2, 1, f1.device)
+        with torch.cuda.device(f1.device):
+            _lib.check(
+                _lib.load().nnd_corr1d_build(_lib.ptr(f1), _lib.ptr(f2), B, C, H, W1, W2, 1, _prec_code(precision),
+                                             pyr._level_ptrs, pyr._pitch_arr, _lib.stream_ptr(f1)),
+                "nnd_corr1d_build",
+            )
+        return pyr.levels[0][:, :W2].reshape(B, H, W1, W2)
+
+
+def lookup_indices(widths, coords, num_levels=4, radius=4):
+    """Integer window indices of ``linear_sampler`` (raft_stereo/utils.py:16-21) for every level/tap."""
+    coords = _lib.require_cuda_f32(coords, "coords")
+    B, _, H, W1 = coords.shape
+    T = 2 * radius + 1
+    idx0 = torch.empty(num_levels, B * H * W1, T, dtype=torch.int32, device=coords.device)
+    idx1 = torch.empty_like(idx0)
+    with torch.cuda.device(coords.device):
+        _lib.check(
+            _lib.load().nnd_corr1d_lookup_indices(_lib.int_array(list(widths)[:num_levels]), _lib.ptr(coords), B, H, W1,
+                                                  num_levels, radius, _lib.ptr(idx0), _lib.ptr(idx1),
+                                                  _lib.stream_ptr(coords)),
+            "nnd_corr1d_lookup_indices",
+        )
+    return idx0, idx1
+
+
+def linear_sampler(corr, coords_lvl):
+    """``(N, w2)`` rows sampled at ``(N, T)`` positions -> ``(N, T)`` (reference raft_stereo/utils.py:4-27).
+
+    Runs the fused lookup kernel as a one-level, radius-0 lookup per tap column (the reference helper
+    is only ever called through the correlation blocks; this standalone form exists for API parity).
+    """
+    corr = _lib.as_cuda_f32(corr, "corr")
+    coords_lvl = _lib.as_cuda_f32(coords_lvl, "coords_lvl")
+    if corr.dim() != 2 or coords_lvl.dim() != 2 or corr.shape[0] != coords_lvl.shape[0]:
+        raise RuntimeError("linear_sampler expects corr (N, w2) and coords_lvl (N, T)")
+    N, w2 = corr.shape
+    T = coords_lvl.shape[1]
+    pitch = _lib.row_pitch(w2)
+    rows = corr
+    if pitch != w2:
+        rows = torch.zeros(N, pitch, dtype=torch.float32, device=corr.device)
+        rows[:, :w2] = corr
+    out = torch.empty(N, T, dtype=torch.float32, device=corr.device)
+    lib = _lib.load()
+    with torch.cuda.device(corr.device):
+        for t in range(T):
+            col = coords_lvl[:, t].contiguous()
+            res = torch.empty(N, dtype=torch.float32, device=corr.device)
+            _lib.check(
+                lib.nnd_corr1d_lookup(_lib.ptr_array([rows]), _lib.int_array([w2]), _lib.int_array([pitch]),
+                                      _lib.ptr(col), 1, 1, N, 1, 0, _lib.ptr(res), _lib.stream_ptr(corr)),
+                "nnd_corr1d_lookup",
+            )
+            out[:, t] = res
+    return out
+
+
+class GroupCorrBlock1D:
+    """Grouped correlation pyramid of ``Coarse2FineGroupRepViTRAFTStereo`` (reference cost_volume.py:64-128).
+
+    Reproduces the reference's quirks: ``torch.split(fmap, num_groups)`` makes chunks *of size*
+    ``num_groups`` and only the first ``num_groups`` chunks are read (:115-121); the scale is
+    ``1/sqrt(C_total)`` (:125); the looked-up block ``[b][g][h][w][k]`` is reinterpreted as
+    ``(B, H, W, G*(2r+1))`` (:108).
+    """
+
+    def __init__(self, fmap1, fmap2, num_levels=4, radius=4, num_groups=4):
+        self.num_levels = num_levels
+        self.radius = radius
+        self.num_groups = num_groups
+        f1 = _lib.as_cuda_f32(fmap1, "fmap1")
+        f2 = _lib.as_cuda_f32(fmap2, "fmap2")
+        if f1.dim() != 4 or f1.shape[:3] != f2.shape[:3]:
+            raise RuntimeError("fmap1 and fmap2 must be (B, C, H, W) with equal batch, channels and height")
+        B, C, H, W1 = f1.shape
+        W2 = f2.shape[3]
+        G = num_groups
+        if G * G > C:
+            raise IndexError("tuple index out of range")  # the reference indexes chunk i < G of size G
+        self._shape = (B, H, W1, W2)
+        self._pyr = PyramidStorage(B * G * H * W1, W2, num_levels, f1.device)
+        with torch.cuda.device(f1.device):
+            _lib.check(
+                _lib.load().nnd_groupcorr_build(_lib.ptr(f1), _lib.ptr(f2), B, C, H, W1, W2, G, G,
+                                                float(math.sqrt(C)), num_levels, self._pyr._level_ptrs,
+                                                self._pyr._pitch_arr, _lib.stream_ptr(f1)),
+                "nnd_groupcorr_build",
+            )
+
+    @classmethod
+    def from_pyramid(cls, levels, batch, height, num_levels=4, radius=4, num_groups=4, device="cuda"):
+        self = cls.__new__(cls)
+        self.num_levels, self.radius, self.num_groups = num_levels, radius, num_groups
+        first = torch.as_tensor(levels[0])
+        rows, W2 = first.reshape(first.shape[0], -1).shape
+        self._shape = (batch, height, rows // (batch * height * num_groups), W2)
+        self._pyr = PyramidStorage(rows, W2, num_levels, torch.device(device)).load(levels[:num_levels])
+        return self
+
+    @property
+    def corr_pyramid(self):
+        return self._pyr.reference_view()
+
+    def __call__(self, coords):
+        B, H, W1, _ = self._shape
+        coords = _check_coords(coords, B, H, W1)
+        T = 2 * self.radius + 1
+        out = torch.empty(B, self.num_levels * self.num_groups * T, H, W1, dtype=torch.float32, device=coords.device)
+        with torch.cuda.device(coords.device):
+            _lib.check(
+                _lib.load().nnd_group_lookup(self._pyr._level_ptrs, None, self._pyr._width_arr, self._pyr._pitch_arr,
+                                             _lib.ptr(coords), B, self.num_groups, H, W1, self.num_levels, self.radius,
+                                             1, _lib.ptr(out), _lib.stream_ptr(coords)),
+                "nnd_group_lookup",
+            )
+        return out

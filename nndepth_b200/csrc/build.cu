@@ -1,0 +1,325 @@
+// Correlation-volume builds with the pyramid pooled in the epilogue (sm_100a).
+//
+//   nnd_corr1d_build (fp32 path)  CorrBlock1D.corr + __init__      raft_stereo/cost_volume.py:55-61, :12-34
+//   nnd_groupcorr_build           GroupCorrBlock1D.corr            raft_stereo/cost_volume.py:113-128
+//                                 GeometryAwareCostVolume.build_cost_volume igev_stereo/cost_volume.py:81-98
+//   nnd_avgpool_pairs             F.avg_pool1d(., 2)               raft_stereo/cost_volume.py:33
+//
+// The reference writes the volume with a batched SGEMM, re-reads it for the `/ C**0.5` pass and then
+// once more per avg_pool1d level.  Here every output element is produced once in registers, scaled,
+// and levels 0..3 are written straight from the accumulators: each thread owns 4 consecutive w2
+// columns (levels 1 and 2 are in-thread sums, level 3 takes one shuffle with the neighbouring lane).
+// Pooling follows avg_pool1d exactly -- level l+1 is (x[2j] + x[2j+1]) * 0.5 of the *rounded* level l
+// values, odd tails dropped.
+//
+// The fp32 path is the 1e-5 parity mode (plain FFMA, sequential-in-c accumulation per output).  The
+// tensor-core (tcgen05, TF32 operands) path lives in build_tcgen05.cu.
+#include "common.cuh"
+
+namespace nnd {
+
+nnd_status corr1d_build_tf32(const float* fmap1, const float* fmap2, int B, int C, int H, int W1, int W2,
+                             int num_levels, float* const* level, const int* pitch, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------------
+// fp32 all-pairs build: per (b,h) row, out[m][n] = sum_c f1[c][m] * f2[c][n] / scale_div.
+// 64x64 output tile per 128-thread block, 8(m) x 4(n) register tile per thread, BK = 16.
+// Both operands are "k-slow" in NCHW (consecutive w for a fixed channel), which is exactly the
+// [k][m] / [k][n] shared-memory layout an outer-product FFMA kernel wants: no transposes.
+// ------------------------------------------------------------------------------------------------
+constexpr int BM = 64, BN = 64, BK = 16;
+
+__global__ void __launch_bounds__(128)
+corr1d_build_fp32_kernel(const float* __restrict__ f1, const float* __restrict__ f2, int C, int H, int W1, int W2,
+                         float scale_div, int num_levels, Pyramid pyr, int vec_ok) {
+  __shared__ __align__(16) float As[2][BK][BM];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15;   // n direction: columns 4*tx .. 4*tx+3
+  const int ty = tid >> 4;   // m direction: rows   8*ty .. 8*ty+7
+  const int n_tile = blockIdx.x * BN;
+  const int m_tile = blockIdx.y * BM;
+  const long long bh = blockIdx.z;  // b*H + h
+  const long long b = bh / H;
+  const int h = static_cast<int>(bh - b * H);
+  const long long plane1 = static_cast<long long>(H) * W1;
+  const long long plane2 = static_cast<long long>(H) * W2;
+  const float* a_row = f1 + b * C * plane1 + static_cast<long long>(h) * W1;  // + c*plane1 + m
+  const float* b_row = f2 + b * C * plane2 + static_cast<long long>(h) * W2;  // + c*plane2 + n
+
+  // loader role: 16 k-rows x 64 columns per operand = 1024 floats / 128 threads = 8 each
+  const int lcol = tid & 63;
+  const int lk0 = tid >> 6;  // 0..1, rows lk0, lk0+2, ...
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  float ra[8], rb[8];
+  auto fetch = [&](int c0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = lk0 + 2 * i;
+      const int c = c0 + k;
+      const int m = m_tile + lcol, n = n_tile + lcol;
+      ra[i] = (c < C && m < W1) ? __ldg(a_row + c * plane1 + m) : 0.f;
+      rb[i] = (c < C && n < W2) ? __ldg(b_row + c * plane2 + n) : 0.f;
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      As[buf][lk0 + 2 * i][lcol] = ra[i];
+      Bs[buf][lk0 + 2 * i][lcol] = rb[i];
+    }
+  };
+
+  const int k_tiles = (C + BK - 1) / BK;
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  for (int kt = 0; kt < k_tiles; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < k_tiles) fetch((kt + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][8 * ty]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][8 * ty + 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[buf][k][4 * tx]);
+      const float am[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bn[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(am[i], bn[j], acc[i][j]);
+    }
+    if (kt + 1 < k_tiles) {
+      stash(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+  const int n0 = n_tile + 4 * tx;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m_tile + 8 * ty + i;
+    // every lane runs the shuffle inside store_row_quad; rows/columns out of range only skip stores
+    float4 v;
+    v.x = __fdiv_rn(acc[i][0], scale_div);
+    v.y = __fdiv_rn(acc[i][1], scale_div);
+    v.z = __fdiv_rn(acc[i][2], scale_div);
+    v.w = __fdiv_rn(acc[i][3], scale_div);
+    const long long row = bh * W1 + min(m, W1 - 1);
+    store_row_quad(pyr, num_levels, row, n0, v, vec_ok != 0, m < W1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Group-wise build with a tiny contraction (K = group_size, 8 for IGEV / 4 for GroupCorrBlock1D):
+// 2 flop per output byte, i.e. purely write-bandwidth bound.  One block per (b, g, h): the two
+// K x W operand strips are staged once in shared memory; each warp then sweeps volume rows, lane i
+// producing columns 4i..4i+3 (+128, ...) so a warp store covers 512 contiguous bytes.
+// ------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(256)
+groupcorr_build_kernel(const float* __restrict__ f1, const float* __restrict__ f2, int C, int G, int H, int W1,
+                       int W2, float scale_div, int num_levels, Pyramid pyr, int vec_ok) {
+  extern __shared__ __align__(16) float smem[];
+  const int W2p = (W2 + 3) & ~3;
+  float* As = smem;             // [K][W1]
+  float* Bs = smem + K * W1;    // [K][W2p], zero padded
+  const long long bgh = blockIdx.x;  // (b*G + g)*H + h
+  const int h = static_cast<int>(bgh % H);
+  const long long bg = bgh / H;
+  const int g = static_cast<int>(bg % G);
+  const long long b = bg / G;
+  const long long plane1 = static_cast<long long>(H) * W1;
+  const long long plane2 = static_cast<long long>(H) * W2;
+  const float* a_src = f1 + (b * C + static_cast<long long>(g) * K) * plane1 + static_cast<long long>(h) * W1;
+  const float* b_src = f2 + (b * C + static_cast<long long>(g) * K) * plane2 + static_cast<long long>(h) * W2;
+  for (int i = threadIdx.x; i < K * W1; i += blockDim.x) {
+    const int k = i / W1, m = i - k * W1;
+    As[i] = __ldg(a_src + k * plane1 + m);
+  }
+  for (int i = threadIdx.x; i < K * W2p; i += blockDim.x) {
+    const int k = i / W2p, n = i - k * W2p;
+    Bs[i] = n < W2 ? __ldg(b_src + k * plane2 + n) : 0.f;
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int n_warps = blockDim.x >> 5;
+  const int n_chunks = (W2p + 127) / 128;  // 128 columns per warp sweep
+  for (int m = warp; m < W1; m += n_warps) {
+    float a[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) a[k] = As[k * W1 + m];
+    const long long row = bgh * W1 + m;
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      const int n0 = ch * 128 + 4 * lane;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n0 < W2p) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const float4 bv = *reinterpret_cast<const float4*>(Bs + k * W2p + n0);
+          acc.x = fmaf(a[k], bv.x, acc.x);
+          acc.y = fmaf(a[k], bv.y, acc.y);
+          acc.z = fmaf(a[k], bv.z, acc.z);
+          acc.w = fmaf(a[k], bv.w, acc.w);
+        }
+      }
+      float4 v;
+      v.x = __fdiv_rn(acc.x, scale_div);
+      v.y = __fdiv_rn(acc.y, scale_div);
+      v.z = __fdiv_rn(acc.z, scale_div);
+      v.w = __fdiv_rn(acc.w, scale_div);
+      store_row_quad(pyr, num_levels, row, n0, v, vec_ok != 0);
+    }
+  }
+}
+
+// avg_pool1d(x, 2) for pyramid levels beyond the fused four.
+__global__ void avgpool_pairs_kernel(const float* __restrict__ src, int src_pitch, float* __restrict__ dst,
+                                     int dst_width, int dst_pitch, long long rows) {
+  const long long total = rows * dst_width;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / dst_width;
+    const int j = static_cast<int>(i - r * dst_width);
+    const float* s = src + r * src_pitch + 2 * j;
+    dst[r * dst_pitch + j] = pool2(__ldg(s), __ldg(s + 1));
+  }
+}
+
+nnd_status fill_pyramid(Pyramid& pyr, int W2, int num_levels, float* const* level, const int* pitch,
+                               bool& vec_ok, const char* who) {
+  NND_REQUIRE(level && pitch, "%s: null level/pitch array", who);
+  NND_REQUIRE(num_levels >= 1 && num_levels <= NND_MAX_LEVELS, "%s: num_levels %d outside [1, %d]", who, num_levels,
+              NND_MAX_LEVELS);
+  memset(&pyr, 0, sizeof(pyr));
+  vec_ok = true;
+  int w = W2;
+  for (int l = 0; l < num_levels; ++l) {
+    NND_REQUIRE(w >= 1, "%s: level %d would be empty (W2 = %d)", who, l, W2);
+    NND_REQUIRE(level[l], "%s: level %d pointer is null", who, l);
+    NND_REQUIRE(pitch[l] >= w, "%s: level %d pitch %d < width %d", who, l, pitch[l], w);
+    pyr.ptr[l] = level[l];
+    pyr.width[l] = w;
+    pyr.pitch[l] = pitch[l];
+    if (l < 4) vec_ok = vec_ok && (pitch[l] % 4 == 0) && aligned16(level[l]);
+    w >>= 1;
+  }
+  return NND_OK;
+}
+
+// levels 4.. are pooled from their predecessor by a separate pass (the reference never reads them)
+nnd_status pool_tail(const Pyramid& pyr, int num_levels, long long rows, cudaStream_t stream) {
+  for (int l = 4; l < num_levels; ++l) {
+    const long long total = rows * pyr.width[l];
+    const long long want = (total + 255) / 256;
+    const int blocks = static_cast<int>(want < 148LL * 16 ? want : 148LL * 16);
+    avgpool_pairs_kernel<<<blocks, 256, 0, stream>>>(pyr.ptr[l - 1], pyr.pitch[l - 1], pyr.ptr[l], pyr.width[l],
+                                                     pyr.pitch[l], rows);
+    nnd_status st = check_launch("avgpool_pairs_kernel");
+    if (st != NND_OK) return st;
+  }
+  return NND_OK;
+}
+
+}  // namespace nnd
+
+extern "C" {
+
+nnd_status nnd_corr1d_build(const float* fmap1, const float* fmap2, int B, int C, int H, int W1, int W2,
+                            int num_levels, int precision, float* const* level, const int* pitch,
+                            nnd_stream_t stream_) {
+  using namespace nnd;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  NND_REQUIRE(fmap1 && fmap2, "corr1d_build: null feature map");
+  NND_REQUIRE(B > 0 && C > 0 && H > 0 && W1 > 0 && W2 > 0, "corr1d_build: B, C, H, W1, W2 must be positive");
+  NND_REQUIRE(static_cast<long long>(B) * H <= 65535 * 1024LL, "corr1d_build: too many epipolar rows");
+  Pyramid pyr;
+  bool vec_ok;
+  nnd_status st = fill_pyramid(pyr, W2, num_levels, level, pitch, vec_ok, "corr1d_build");
+  if (st != NND_OK) return st;
+  if (precision == NND_PREC_TF32) {
+    st = corr1d_build_tf32(fmap1, fmap2, B, C, H, W1, W2, num_levels < 4 ? num_levels : 4, level, pitch, stream);
+    if (st != NND_OK) return st;
+    return pool_tail(pyr, num_levels, static_cast<long long>(B) * H * W1, stream);
+  }
+  NND_REQUIRE(precision == NND_PREC_FP32, "corr1d_build: unknown precision %d", precision);
+  const float scale_div = static_cast<float>(sqrt(static_cast<double>(C)));
+  const long long bh = static_cast<long long>(B) * H;
+  NND_REQUIRE(bh <= 65535, "corr1d_build: B*H = %lld exceeds the fp32 path's grid limit (65535)", bh);
+  dim3 grid((W2 + BN - 1) / BN, (W1 + BM - 1) / BM, static_cast<unsigned>(bh));
+  corr1d_build_fp32_kernel<<<grid, 128, 0, stream>>>(fmap1, fmap2, C, H, W1, W2, scale_div, num_levels, pyr,
+                                                     vec_ok ? 1 : 0);
+  st = check_launch("corr1d_build_fp32_kernel");
+  if (st != NND_OK) return st;
+  return pool_tail(pyr, num_levels, bh * W1, stream);
+}
+
+nnd_status nnd_groupcorr_build(const float* fmap1, const float* fmap2, int B, int C, int H, int W1, int W2,
+                               int num_groups, int group_size, float scale_div, int num_levels,
+                               float* const* level, const int* pitch, nnd_stream_t stream_) {
+  using namespace nnd;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  NND_REQUIRE(fmap1 && fmap2, "groupcorr_build: null feature map");
+  NND_REQUIRE(B > 0 && C > 0 && H > 0 && W1 > 0 && W2 > 0, "groupcorr_build: B, C, H, W1, W2 must be positive");
+  NND_REQUIRE(num_groups > 0 && group_size > 0, "groupcorr_build: num_groups and group_size must be positive");
+  // the reference indexes chunk i (of size group_size) for i < num_groups: IndexError beyond C
+  NND_REQUIRE(static_cast<long long>(num_groups) * group_size <= C,
+              "groupcorr_build: num_groups * group_size = %d exceeds C = %d", num_groups * group_size, C);
+  NND_REQUIRE(scale_div > 0.f, "groupcorr_build: scale_div must be positive");
+  Pyramid pyr;
+  bool vec_ok;
+  nnd_status st = fill_pyramid(pyr, W2, num_levels, level, pitch, vec_ok, "groupcorr_build");
+  if (st != NND_OK) return st;
+  const long long blocks = static_cast<long long>(B) * num_groups * H;
+  NND_REQUIRE(blocks <= 0x7fffffffLL, "groupcorr_build: too many rows");
+  const int W2p = (W2 + 3) & ~3;
+  const size_t smem = static_cast<size_t>(group_size) * (W1 + W2p) * sizeof(float);
+  NND_REQUIRE(smem <= 200 * 1024, "groupcorr_build: strips of %zu bytes do not fit shared memory", smem);
+#define NND_LAUNCH_GROUP(KK)                                                                                      \
+  do {                                                                                                            \
+    if (smem > 48 * 1024)                                                                                         \
+      cudaFuncSetAttribute(groupcorr_build_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
+                           static_cast<int>(smem));                                                               \
+    groupcorr_build_kernel<KK><<<static_cast<unsigned>(blocks), 256, smem, stream>>>(                             \
+        fmap1, fmap2, C, num_groups, H, W1, W2, scale_div, num_levels, pyr, vec_ok ? 1 : 0);                      \
+  } while (0)
+  switch (group_size) {
+    case 1: NND_LAUNCH_GROUP(1); break;
+    case 2: NND_LAUNCH_GROUP(2); break;
+    case 4: NND_LAUNCH_GROUP(4); break;
+    case 8: NND_LAUNCH_GROUP(8); break;
+    case 16: NND_LAUNCH_GROUP(16); break;
+    case 32: NND_LAUNCH_GROUP(32); break;
+    default:
+      set_error("groupcorr_build: group_size %d unsupported (1, 2, 4, 8, 16, 32)", group_size);
+      return NND_ERR_UNSUPPORTED;
+  }
+#undef NND_LAUNCH_GROUP
+  st = check_launch("groupcorr_build_kernel");
+  if (st != NND_OK) return st;
+  return pool_tail(pyr, num_levels, blocks * W1, stream);
+}
+
+nnd_status nnd_avgpool_pairs(const float* src, int src_width, int src_pitch, float* dst, int dst_pitch,
+                             int64_t rows, nnd_stream_t stream) {
+  using namespace nnd;
+  NND_REQUIRE(src && dst, "avgpool_pairs: null pointer");
+  NND_REQUIRE(src_width >= 2 && rows > 0, "avgpool_pairs: needs src_width >= 2 and rows > 0");
+  const int dst_width = src_width / 2;
+  NND_REQUIRE(src_pitch >= src_width && dst_pitch >= dst_width, "avgpool_pairs: pitch smaller than width");
+  const long long total = rows * dst_width;
+  const long long want = (total + 255) / 256;
+  const int blocks = static_cast<int>(want < 148LL * 16 ? want : 148LL * 16);
+  avgpool_pairs_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, src_pitch, dst, dst_width,
+                                                                                   dst_pitch, rows);
+  return check_launch("avgpool_pairs_kernel");
+}
+
+}  // extern "C"

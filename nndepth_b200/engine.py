@@ -1,0 +1,105 @@
+"""Inference engine: host pairs in, disparity maps out -- the call a user of the reference's
+``evaluate.py`` / ``inference.py`` makes, minus the dataset plumbing.
+
+Reference recipe (``nndepth/models/raft_stereo/scripts/evaluate.py:146-156``): ``Padder(divis_by=32)``
+-> ``model(left, right)`` -> ``unpad(m_outputs[-1]["up_disp"])``.  ``Padder`` arithmetic follows
+``nndepth/data/dataloaders/utils.py:5-21``: ``pad = (((d // k) + 1) * k - d) % k``, width split
+``[pad//2, pad - pad//2]``, height all at the bottom, replicate mode.
+
+One process drives one GPU.  Multi-GPU inference shards the batch of pairs (or, for the correlation
+path alone, epipolar row bands) across ranks with no collective in the data path; ``gather_disparities``
+is the single NCCL call, collecting the output maps.
+"""
+import torch
+import torch.nn.functional as F
+
+
+class Padder:
+    """Pads images so both sides are divisible by ``divis_by`` (reference dataloaders/utils.py:5-21)."""
+
+    def __init__(self, dims, divis_by=32):
+        self.ht, self.wd = int(dims[-2]), int(dims[-1])
+        # the reference's (((d // k) + 1) * k - d) % k is the distance to the next multiple of k: -d mod k
+        extra_h, extra_w = -self.ht % divis_by, -self.wd % divis_by
+        self.left, self.right = extra_w // 2, extra_w - extra_w // 2
+        self.top, self.bottom = 0, extra_h
+
+    @property
+    def padded_size(self):
+        return self.ht + self.top + self.bottom, self.wd + self.left + self.right
+
+    def pad(self, *inputs):
+        return [F.pad(x, (self.left, self.right, self.top, self.bottom), mode="replicate") for x in inputs]
+
+    def unpad(self, x):
+        return x[..., self.top:x.shape[-2] - self.bottom, self.left:x.shape[-1] - self.right]
+
+
+def shard_range(total, rank, world_size):
+    """Contiguous ``[begin, end)`` slice of ``total`` units for ``rank`` (remainder to the low ranks)."""
+    base, extra = divmod(int(total), int(world_size))
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def gather_disparities(local, world_size=None, group=None):
+    """All-gather per-rank disparity maps ``(b_r, 1, H, W)`` along the batch axis (equal ``b_r``)."""
+    import torch.distributed as dist
+    if world_size is None:
+        world_size = dist.get_world_size(group)
+    if world_size == 1:
+        return local
+    out = torch.empty((world_size * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype,
+                      device=local.device)
+    dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+    return out
+
+
+class StereoEngine:
+    """Host-to-host stereo inference on one GPU with CUDA-graph replay.
+
+    ``infer(left, right)`` takes host (ideally pinned) or device ``(B,3,H,W)`` float32 image batches,
+    normalised like the reference datasets (``(x - 127.5) / 127.5``), and returns the final disparity
+    ``(B,1,H,W)`` on the host (pinned) -- H2D copy, pad, forward, unpad and D2H all on the current stream.
+    """
+
+    def __init__(self, model, device=None, use_cuda_graph=True, divis_by=32, final_only=False):
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.model = model.to(self.device).eval()
+        # final_only=False keeps the reference forward's behaviour (an upsampled map per iteration);
+        # True upsamples only the last iteration, which is all evaluate.py:155 reads.
+        self.model.final_only = final_only
+        gru = getattr(getattr(self.model, "update_block", None), "gru", None)
+        if hasattr(gru, "fuse_gates"):
+            gru.fuse_gates()
+        self.use_cuda_graph = use_cuda_graph
+        self.divis_by = divis_by
+        self._dev_in = {}
+        self._host_out = {}
+
+    @torch.no_grad()
+    def infer_device(self, left, right):
+        """Device tensors in, device disparity out (padded internally, un-padded on return)."""
+        padder = Padder(left.shape, self.divis_by)
+        left_p, right_p = padder.pad(left, right)
+        if self.use_cuda_graph:
+            outputs = self.model.forward_graphed(left_p, right_p)
+        else:
+            outputs = self.model(left_p, right_p)
+        return padder.unpad(outputs[-1]["up_disp"])
+
+    @torch.no_grad()
+    def infer(self, left, right):
+        key = tuple(left.shape)
+        if key not in self._dev_in:
+            self._dev_in[key] = (torch.empty(key, dtype=torch.float32, device=self.device),
+                                 torch.empty(key, dtype=torch.float32, device=self.device))
+            self._host_out[key] = torch.empty((key[0], 1, key[2], key[3]), dtype=torch.float32).pin_memory()
+        dl, dr = self._dev_in[key]
+        dl.copy_(left, non_blocking=True)
+        dr.copy_(right, non_blocking=True)
+        disp = self.infer_device(dl, dr)
+        host = self._host_out[key]
+        host.copy_(disp, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return host

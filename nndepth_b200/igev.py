@@ -1,0 +1,132 @@
+"""IGEV-Stereo geometry-aware cost volume and soft-argmin on the sm_100a kernels.
+
+Mirrors ``nndepth/models/igev_stereo/cost_volume.py:9-98`` (``GeometryAwareCostVolume``) and the
+regression at ``nndepth/models/igev_stereo/model.py:92-95,144-146`` of the reference.
+``model.corr_fn = nndepth_b200.GeometryAwareCostVolume`` swaps the reference model onto these kernels
+(``igev_stereo/model.py:64,133-141``).  The 3-D regulariser stays the caller's PyTorch module.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .corr import PyramidStorage, _check_coords
+
+
+class GeometryAwareCostVolume(nn.Module):
+    """Group-wise all-pairs volume + regularised geometry volume, pooled, with a fused dual lookup."""
+
+    def __init__(self, fmap1, fmap2, features, regularizer_3d, num_levels=4, radius=4, num_groups=8):
+        super().__init__()
+        self.num_groups = num_groups
+        self.num_levels = num_levels
+        self.radius = radius
+        f1 = _lib.as_cuda_f32(fmap1, "fmap1")
+        f2 = _lib.as_cuda_f32(fmap2, "fmap2")
+        if f1.dim() != 4 or f1.shape[:3] != f2.shape[:3]:
+            raise RuntimeError("fmap1 and fmap2 must be (B, C, H, W) with equal batch, channels and height")
+        B, C, H, W1 = f1.shape
+        W2 = f2.shape[3]
+        G = num_groups
+        self._shape = (B, H, W1, W2)
+        self._feat = PyramidStorage(B * G * H * W1, W2, num_levels, f1.device)
+        self._build_feature_volume(f1, f2, self._feat)
+        # regulariser input: (B, G, W2, H, W1) view of the level-0 volume (cost_volume.py:37); level 0 is
+        # dense whenever W2 % 4 == 0, otherwise the padding columns are sliced off.
+        feat0 = self._feat.levels[0][:, :W2].reshape(B, G, H, W1, W2)
+        geo = regularizer_3d(feat0.clone().permute(0, 1, 4, 2, 3), features)
+        if geo.dim() != 5 or geo.shape[1] != G:
+            raise AssertionError("N must be equal to num_groups")
+        geo = _lib.as_cuda_f32(geo, "regularizer_3d output")
+        Bg, _, D, Hg, Wg = geo.shape
+        if (Bg, Hg, Wg, D) != (B, H, W1, W2):
+            raise RuntimeError(
+                f"regularizer_3d returned {tuple(geo.shape)}; expected (B, G, W2, H, W1) = {(B, G, W2, H, W1)}")
+        self._geo = PyramidStorage(B * G * H * W1, D, num_levels, f1.device)
+        with torch.cuda.device(f1.device):
+            _lib.check(
+                _lib.load().nnd_geo_transpose_pool(_lib.ptr(geo), B, G, D, H, W1, num_levels, self._geo._level_ptrs,
+                                                   self._geo._pitch_arr, _lib.stream_ptr(geo)),
+                "nnd_geo_transpose_pool",
+            )
+
+    @classmethod
+    def from_pyramids(cls, feat_levels, geo_levels, batch, height, num_levels=4, radius=4, num_groups=8,
+                      device="cuda"):
+        """Wrap two existing pyramids (lists of ``(B*G*H*W1, w_l)`` arrays) -- used by the parity tests."""
+        self = cls.__new__(cls)
+        nn.Module.__init__(self)
+        self.num_groups, self.num_levels, self.radius = num_groups, num_levels, radius
+        first = torch.as_tensor(feat_levels[0])
+        rows, W2 = first.reshape(first.shape[0], -1).shape
+        self._shape = (batch, height, rows // (batch * height * num_groups), W2)
+        dev = torch.device(device)
+        self._feat = PyramidStorage(rows, W2, num_levels, dev).load(feat_levels[:num_levels])
+        self._geo = PyramidStorage(rows, W2, num_levels, dev).load(geo_levels[:num_levels])
+        return self
+
+    def _build_feature_volume(self, f1, f2, pyr):
+        B, C, H, W1 = f1.shape
+        W2 = f2.shape[3]
+        G = self.num_groups
+        assert C % G == 0 and f2.shape[1] % G == 0, \
+            "Number of channels of fmap1 and fmap2 must be the factor of num_groups"
+        if G * G > C:
+            raise IndexError("tuple index out of range")  # reference reads chunk i < G of size G (:90)
+        with torch.cuda.device(f1.device):
+            _lib.check(
+                _lib.load().nnd_groupcorr_build(_lib.ptr(f1), _lib.ptr(f2), B, C, H, W1, W2, G, G,
+                                                float(math.sqrt(G)), pyr.num_levels, pyr._level_ptrs, pyr._pitch_arr,
+                                                _lib.stream_ptr(f1)),
+                "nnd_groupcorr_build",
+            )
+
+    @property
+    def feat_corr_cv(self):
+        return self._feat.reference_view()
+
+    @property
+    def geo_aware_cv(self):
+        return self._geo.reference_view()
+
+    def build_cost_volume(self, fmap1, fmap2):
+        """``(B, G, H, W1, W2)`` group-wise volume (reference cost_volume.py:81-98)."""
+        f1 = _lib.as_cuda_f32(fmap1, "fmap1")
+        f2 = _lib.as_cuda_f32(fmap2, "fmap2")
+        B, _, H, W1 = f1.shape
+        W2 = f2.shape[3]
+        pyr = PyramidStorage(B * self.num_groups * H * W1, W2, 1, f1.device)
+        self._build_feature_volume(f1, f2, pyr)
+        return pyr.levels[0][:, :W2].reshape(B, self.num_groups, H, W1, W2)
+
+    def forward(self, coords):
+        B, H, W1, _ = self._shape
+        coords = _check_coords(coords, B, H, W1)
+        T = 2 * self.radius + 1
+        out = torch.empty(B, self.num_levels * 2 * self.num_groups * T, H, W1, dtype=torch.float32,
+                          device=coords.device)
+        with torch.cuda.device(coords.device):
+            _lib.check(
+                _lib.load().nnd_group_lookup(self._feat._level_ptrs, self._geo._level_ptrs, self._feat._width_arr,
+                                             self._feat._pitch_arr, _lib.ptr(coords), B, self.num_groups, H, W1,
+                                             self.num_levels, self.radius, 0, _lib.ptr(out), _lib.stream_ptr(coords)),
+                "nnd_group_lookup",
+            )
+        return out
+
+
+def soft_argmin(cost):
+    """``-sum_d d * softmax_d(cost)``: ``(B, D, H, W)`` -> ``(B, 1, H, W)`` in one pass.
+
+    Fuses ``F.softmax(dim=1)`` (igev_stereo/model.py:145) with ``regress_disparity`` (:92-95).
+    """
+    cost = _lib.as_cuda_f32(cost, "cost")
+    if cost.dim() != 4:
+        raise RuntimeError(f"cost must be (B, D, H, W), got {tuple(cost.shape)}")
+    B, D, H, W = cost.shape
+    out = torch.empty(B, 1, H, W, dtype=torch.float32, device=cost.device)
+    with torch.cuda.device(cost.device):
+        _lib.check(_lib.load().nnd_soft_argmin(_lib.ptr(cost), B, D, H, W, _lib.ptr(out), _lib.stream_ptr(cost)),
+                   "nnd_soft_argmin")
+    return out

@@ -1,0 +1,301 @@
+"""RAFT-Stereo model shell around the sm_100a correlation kernels.
+
+The dense layers (feature encoder, motion encoder, separable ConvGRU, flow / mask heads) are OUT OF
+SCOPE of the B200 hot path: they are cuDNN convolutions and stay
+plain ``torch.nn`` modules.  This file only re-states their module tree so that
+
+* parameter names / shapes equal the reference's ``BaseRAFTStereo`` (``nndepth/models/raft_stereo/
+  model.py:17-163``, ``encoders/basic_encoder.py``, ``blocks/update_block.py``, ``blocks/gru.py``,
+  ``blocks/residual_block.py``) -- reference checkpoints load with ``load_state_dict`` unchanged and a
+  seeded construction draws the same random weights;
+* ``forward(frame1, frame2) -> List[{"up_disp": (B,1,H,W)}]`` keeps the reference signature
+  (model.py:111-139) while the correlation pyramid, the per-iteration lookup and the convex upsampling
+  run on the kernels of this package, and the whole forward can be replayed as one CUDA graph.
+
+``corr_fn`` is a class-valued attribute exactly as in the reference (model.py:58), so the same shell
+runs the CPU oracle in tests / the CPU baseline (``model.corr_fn = <oracle class>``).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .corr import CorrBlock1D
+
+
+def _norm(kind, planes):
+    if kind == "batch":
+        return nn.BatchNorm2d(planes)
+    if kind == "instance":
+        return nn.InstanceNorm2d(planes, affine=False)
+    if kind == "group":
+        return nn.GroupNorm(num_groups=planes // 8, num_channels=planes)
+    if kind == "none":
+        return nn.Sequential()
+    raise AssertionError(f"norm_fn must be in group, batch, instance, or none, found {kind}")
+
+
+class ResidualBlock(nn.Module):
+    """Two 3x3 convs + always-on 1x1 projection shortcut (reference blocks/residual_block.py:6-63)."""
+
+    def __init__(self, in_planes, planes, norm_fn="group", stride=1):
+        super().__init__()
+        self.conv1 = nn.Conv2d(in_planes, planes, 3, stride=stride, padding=1)
+        self.conv2 = nn.Conv2d(planes, planes, 3, padding=1)
+        self.relu = nn.ReLU(inplace=True)
+        self.norm1, self.norm2, self.norm3 = (_norm(norm_fn, planes) for _ in range(3))
+        self.downsample = nn.Sequential(nn.Conv2d(in_planes, planes, 1, stride=stride), self.norm3)
+
+    def forward(self, x):
+        y = self.relu(self.norm1(self.conv1(x)))
+        y = self.relu(self.norm2(self.conv2(y)))
+        return self.relu(self.downsample(x) + y)
+
+
+class BasicEncoder(nn.Module):
+    """Stride-8 residual feature encoder (reference encoders/basic_encoder.py:8-93)."""
+
+    def __init__(self, output_dim=128, norm_fn="batch", dropout=0.0):
+        super().__init__()
+        self.norm_fn = norm_fn
+        self.norm1 = nn.GroupNorm(8, 64) if norm_fn == "group" else _norm(norm_fn, 64)
+        self.conv1 = nn.Conv2d(3, 64, 7, stride=2, padding=3)
+        self.relu1 = nn.ReLU(inplace=True)
+        widths, strides, planes = (64, 96, 128), (1, 2, 2), 64
+        for i, (w, s) in enumerate(zip(widths, strides), start=1):
+            setattr(self, f"layer{i}", nn.Sequential(ResidualBlock(planes, w, norm_fn, s),
+                                                     ResidualBlock(w, w, norm_fn, 1)))
+            planes = w
+        self.conv2 = nn.Conv2d(128, output_dim, 1)
+        self.dropout = nn.Dropout2d(dropout) if dropout > 0 else None
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            elif isinstance(m, (nn.BatchNorm2d, nn.InstanceNorm2d, nn.GroupNorm)):
+                if m.weight is not None:
+                    nn.init.constant_(m.weight, 1)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+
+    def forward(self, x):
+        pair = isinstance(x, (tuple, list))
+        if pair:
+            x = torch.cat(x, dim=0)
+        x = self.relu1(self.norm1(self.conv1(x)))
+        x = self.layer3(self.layer2(self.layer1(x)))
+        x = self.conv2(x)
+        if self.dropout is not None:
+            x = self.dropout(x)
+        return torch.split(x, x.shape[0] // 2, dim=0) if pair else x
+
+
+class SepConvGRU(nn.Module):
+    """Horizontal (1x5) then vertical (5x1) conv GRU (reference blocks/gru.py:5-37).
+
+    Inference fusion: the z and r gates read the same input, so their two convolutions run as one
+    conv with concatenated output channels (weights concatenated on the fly -- no new parameters).
+    """
+
+    def __init__(self, hidden_dim=128, input_dim=192 + 128):
+        super().__init__()
+        cin = hidden_dim + input_dim
+        for tag, k, p in (("1", (1, 5), (0, 2)), ("2", (5, 1), (2, 0))):
+            for gate in "zrq":
+                setattr(self, f"conv{gate}{tag}", nn.Conv2d(cin, hidden_dim, k, padding=p))
+        self._fused = {}
+
+    def fuse_gates(self):
+        """Pre-concatenate the z|r gate weights (call after loading weights, in eval mode)."""
+        self._fused = {}
+        for tag in "12":
+            cz, cr = getattr(self, f"convz{tag}"), getattr(self, f"convr{tag}")
+            self._fused[tag] = (torch.cat([cz.weight, cr.weight], 0).detach().contiguous(),
+                                torch.cat([cz.bias, cr.bias], 0).detach().contiguous(), cz.padding)
+
+    def _half_step(self, h, x, tag):
+        hx = torch.cat([h, x], dim=1)
+        if tag in self._fused:
+            w, b, pad = self._fused[tag]
+            z, r = torch.sigmoid(F.conv2d(hx, w, b, padding=pad)).chunk(2, dim=1)
+        else:
+            z = torch.sigmoid(getattr(self, f"convz{tag}")(hx))
+            r = torch.sigmoid(getattr(self, f"convr{tag}")(hx))
+        q = torch.tanh(getattr(self, f"convq{tag}")(torch.cat([r * h, x], dim=1)))
+        return (1 - z) * h + z * q
+
+    def forward(self, h, x):
+        return self._half_step(self._half_step(h, x, "1"), x, "2")
+
+
+class BasicMotionEncoder(nn.Module):
+    """Consumer of the lookup output (reference blocks/update_block.py:39-65)."""
+
+    def __init__(self, cor_planes, hidden_dim=128, flow_channel=2):
+        super().__init__()
+        self.convc1 = nn.Conv2d(cor_planes, 256, 1)
+        self.convc2 = nn.Conv2d(256, 192, 3, padding=1)
+        self.convf1 = nn.Conv2d(flow_channel, 128, 7, padding=3)
+        self.convf2 = nn.Conv2d(128, 64, 3, padding=1)
+        self.conv = nn.Conv2d(64 + 192, hidden_dim - flow_channel, 3, padding=1)
+
+    def forward(self, flow, corr):
+        cor = F.relu(self.convc2(F.relu(self.convc1(corr))))
+        flo = F.relu(self.convf2(F.relu(self.convf1(flow))))
+        out = F.relu(self.conv(torch.cat([cor, flo], dim=1)))
+        return torch.cat([out, flow], dim=1)
+
+
+class FlowHead(nn.Module):
+    def __init__(self, input_dim=128, hidden_dim=256, flow_channel=2):
+        super().__init__()
+        self.conv1 = nn.Conv2d(input_dim, hidden_dim, 3, padding=1)
+        self.conv2 = nn.Conv2d(hidden_dim, flow_channel, 3, padding=1)
+        self.relu = nn.ReLU(inplace=True)
+
+    def forward(self, x):
+        return self.conv2(self.relu(self.conv1(x)))
+
+
+class BasicUpdateBlock(nn.Module):
+    """Motion encoder -> GRU -> flow head + 0.25 * mask head (reference blocks/update_block.py:68-112)."""
+
+    def __init__(self, hidden_dim, cor_planes, context_dim=128, gru="sep_conv", flow_channel=2, spatial_scale=8):
+        super().__init__()
+        if gru != "sep_conv":
+            raise NotImplementedError("only the separable ConvGRU of BaseRAFTStereo is provided")
+        self.encoder = BasicMotionEncoder(cor_planes, hidden_dim=hidden_dim, flow_channel=flow_channel)
+        self.gru = SepConvGRU(hidden_dim=hidden_dim, input_dim=context_dim + hidden_dim)
+        self.flow_head = FlowHead(hidden_dim, hidden_dim=hidden_dim, flow_channel=flow_channel)
+        sps = spatial_scale ** 2 if isinstance(spatial_scale, int) else spatial_scale[0] * spatial_scale[1]
+        self.mask = nn.Sequential(nn.Conv2d(hidden_dim, hidden_dim * 2, 3, padding=1), nn.ReLU(inplace=True),
+                                  nn.Conv2d(hidden_dim * 2, sps * 9, 1))
+
+    def forward(self, net, inp, corr, flow):
+        motion = self.encoder(flow, corr)
+        net = self.gru(net, torch.cat((inp, motion), dim=1))
+        return net, 0.25 * self.mask(net), self.flow_head(net)
+
+
+def convex_upsample(flow, mask, rate=8):
+    """Convex combination of the 3x3 coarse neighbourhood (reference raft_stereo/model.py:93-105)."""
+    N, _, H, W = flow.shape
+    mask = torch.softmax(mask.view(N, 1, 9, rate, rate, H, W), dim=2)
+    up = F.unfold(rate * flow, (3, 3), padding=1).view(N, 1, 9, 1, 1, H, W)
+    up = torch.sum(mask * up, dim=2).permute(0, 1, 4, 2, 5, 3)
+    return up.reshape(N, 1, rate * H, rate * W)
+
+
+class RAFTStereo(nn.Module):
+    """Reference ``RAFTStereo`` API (model.py:17-139) with the correlation path on B200 kernels."""
+
+    def __init__(self, iters=12, fnet_dim=256, hidden_dim=128, context_dim=128, corr_levels=4, corr_radius=4,
+                 tracing=False, include_preprocessing=False, weights=None, strict_load=True, **kwargs):
+        super().__init__()
+        self.iters = iters
+        self.fnet_dim = fnet_dim
+        self.hidden_dim = hidden_dim
+        self.context_dim = context_dim
+        self.corr_levels = corr_levels
+        self.corr_radius = corr_radius
+        self.fnet = self._init_fnet(**kwargs)
+        self.cnet_proj = nn.Sequential(nn.Conv2d(fnet_dim, context_dim + hidden_dim, 3, padding=1), nn.ReLU(False))
+        self.update_block = self._init_update_block()
+        self.corr_fn = CorrBlock1D
+        self.tracing = tracing
+        self.include_preprocessing = include_preprocessing
+        self.weights = weights
+        self.strict_load = strict_load
+        self.final_only = False     # True: upsample only the last iteration (what evaluate.py:155 consumes)
+        self._graphs = {}
+        if weights is not None:
+            state = torch.load(weights, map_location="cpu") if not str(weights).endswith(".safetensors") else None
+            if state is None:
+                from safetensors.torch import load_file
+                state = load_file(weights)
+            self.load_state_dict(state.get("model", state), strict=strict_load)
+
+    def _init_fnet(self):
+        raise NotImplementedError("Must be implemented in child class")
+
+    def _init_update_block(self):
+        raise NotImplementedError("Must be implemented in child class")
+
+    def forward_fnet(self, frame1, frame2):
+        raise NotImplementedError("Must be implemented in child class")
+
+    def freeze_bn(self):
+        for m in self.modules():
+            if isinstance(m, nn.BatchNorm2d):
+                m.eval()
+
+    def initialize_coords(self, fmap1):
+        B, _, H, W = fmap1.shape
+        return torch.arange(W, device=fmap1.device).float()[None, None, None, :].repeat(B, 1, H, 1)
+
+    convex_upsample = staticmethod(convex_upsample)
+
+    def forward(self, frame1, frame2, **kwargs):
+        fmap1, fmap2, cnet1 = self.forward_fnet(frame1, frame2)
+        fnet_ds = frame1.shape[-1] // fmap1.shape[-1]
+        fmap1, fmap2 = fmap1.float(), fmap2.float()
+        net, inp = torch.split(cnet1, [self.hidden_dim, self.context_dim], dim=1)
+        net, inp = torch.tanh(net), F.relu(inp)
+
+        corr = self.corr_fn(fmap1, fmap2, self.corr_levels, self.corr_radius)
+        org_coords = self.initialize_coords(fmap1)
+        coords1 = org_coords.clone()
+        outputs = []
+        for it in range(self.iters):
+            coords1 = coords1.detach()
+            sampled = corr(coords1)
+            net, mask, delta = self.update_block(net, inp, sampled, coords1 - org_coords)
+            coords1 = coords1 + delta
+            if not self.final_only or it == self.iters - 1:
+                outputs.append({"up_disp": self.convex_upsample(coords1 - org_coords, mask, rate=fnet_ds)})
+        return outputs
+
+    # ---- CUDA-graph replay of the whole forward (inference) ---------------------------------------
+    @torch.no_grad()
+    def forward_graphed(self, frame1, frame2):
+        """Replay ``forward`` as one CUDA graph per input shape; returns the static output list.
+
+        Every kernel of the path (cuDNN convs and this package's launches) is stream-ordered with no
+        host synchronisation, so the 32-iteration loop captures cleanly.  Outputs are overwritten by
+        the next replay of the same shape.
+        """
+        key = (tuple(frame1.shape), frame1.device.index, self.iters, self.final_only)
+        entry = self._graphs.get(key)
+        if entry is None:
+            static1, static2 = torch.empty_like(frame1), torch.empty_like(frame2)
+            static1.copy_(frame1)
+            static2.copy_(frame2)
+            side = torch.cuda.Stream(device=frame1.device)
+            side.wait_stream(torch.cuda.current_stream(frame1.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):      # warm-up outside capture: cuDNN autotune, lazy module init
+                    self.forward(static1, static2)
+            torch.cuda.current_stream(frame1.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = self.forward(static1, static2)
+            entry = (graph, static1, static2, static_out)
+            self._graphs[key] = entry
+        graph, static1, static2, static_out = entry
+        static1.copy_(frame1, non_blocking=True)
+        static2.copy_(frame2, non_blocking=True)
+        graph.replay()
+        return static_out
+
+
+class BaseRAFTStereo(RAFTStereo):
+    """The paper's configuration (reference model.py:142-163)."""
+
+    def _init_fnet(self):
+        return BasicEncoder(output_dim=self.fnet_dim)
+
+    def _init_update_block(self):
+        return BasicUpdateBlock(hidden_dim=self.hidden_dim, cor_planes=self.corr_levels * (self.corr_radius * 2 + 1),
+                                flow_channel=1, context_dim=self.context_dim, spatial_scale=8)
+
+    def forward_fnet(self, frame1, frame2):
+        fmap1, fmap2 = self.fnet([frame1, frame2])
+        return fmap1, fmap2, self.cnet_proj(fmap1)

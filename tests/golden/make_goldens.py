@@ -195,7 +195,53 @@ def agcl_case():
     save("agcl", **arrays)
 
 
+def state_fingerprint(model):
+    """Order-sensitive fingerprint of a state dict: (sum |w|, sum w * ramp) in float64."""
+    acc_abs, acc_ramp, count = 0.0, 0.0, 0
+    for name, t in model.state_dict().items():
+        t = t.detach().double().reshape(-1)
+        acc_abs += float(t.abs().sum())
+        acc_ramp += float((t * torch.linspace(-1, 1, t.numel(), dtype=torch.float64)).sum())
+        count += t.numel()
+    return np.float64([acc_abs, acc_ramp, count])
+
+
+def raft_model_cases():
+    """Full-model goldens: the reference BaseRAFTStereo (random init, seed 0) on seeded synthetic pairs.
+
+    The shell model of this repo (nndepth_b200/raft_stereo.py) draws the SAME weights from seed 0 --
+    checked here against the reference's state dict, bit for bit -- so only inputs' seeds, the weight
+    fingerprint and the reference outputs need to be committed.
+    """
+    from nndepth.models.raft_stereo.model import BaseRAFTStereo as RefModel
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from nndepth_b200.raft_stereo import BaseRAFTStereo as OurModel
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    for name, iters, shape in (("raft_small", 6, (1, 3, 96, 160)), ("raft_kitti", 32, (1, 3, 384, 1248))):
+        torch.manual_seed(0)
+        ref = RefModel(iters=iters).eval()
+        torch.manual_seed(0)
+        ours = OurModel(iters=iters).eval()
+        rs, os_ = ref.state_dict(), ours.state_dict()
+        assert list(rs.keys()) == list(os_.keys()), "state-dict keys differ from the reference"
+        for k in rs:
+            assert torch.equal(rs[k], os_[k]), f"seeded init differs at {k}"
+        gen = torch.Generator().manual_seed(1)
+        left = torch.rand(shape, generator=gen) * 2 - 1
+        right = torch.rand(shape, generator=gen) * 2 - 1
+        outs = ref(left, right)
+        arrays = {"iters": np.int64(iters), "shape": np.int64(shape), "fingerprint": state_fingerprint(ref),
+                  "final_up_disp": outs[-1]["up_disp"]}
+        if name == "raft_small":
+            arrays["all_up_disp"] = torch.stack([o["up_disp"] for o in outs])
+        save(name, **arrays)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "raft":
+        raft_model_cases()
+        sys.exit(0)
     sampler_kats()
     corr1d_case("corr1d_small", B=2, C=32, H=3, W=40, seed=11)
     corr1d_case("corr1d_odd", B=1, C=16, H=2, W=39, seed=12)
@@ -204,3 +250,4 @@ if __name__ == "__main__":
     group_corr_case()
     igev_case()
     agcl_case()
+    raft_model_cases()

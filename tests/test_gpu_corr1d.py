@@ -1,0 +1,246 @@
+"""GPU parity: RAFT-Stereo correlation pyramid + lookup through the C ABI vs the oracle / goldens.
+
+Bars (BASELINE.json): window indices bit-exact vs the CPU reference; lookups on an identical
+pyramid bit-exact (same IEEE operation order); fp32 volume within 1e-5 relative (of the volume's
+scale -- values cross zero); pooled levels bit-exact given level 0.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import corr1d as oc
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["corr1d_small", "corr1d_odd", "corr1d_kitti_row", "corr1d_r3l3"]
+REGIMES = ["int", "sub", "oob"]
+VOLUME_RTOL = 1e-5      # fp32 bar of BASELINE.json
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).cuda()
+
+
+def shape_of(g):
+    B, _, H, W = g["coords_int"].shape
+    return B, H, W
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("regime", REGIMES)
+def test_lookup_bit_exact_on_reference_pyramid(golden, case, regime):
+    import nndepth_b200 as nb
+    g = golden(case)
+    L, r = int(g["num_levels"]), int(g["radius"])
+    B, H, W = shape_of(g)
+    blk = nb.CorrBlock1D.from_pyramid([g[f"pyr{l}"] for l in range(L)], B, H, L, r)
+    out = blk(dev(g[f"coords_{regime}"])).cpu().numpy()
+    assert out.dtype == np.float32 and out.shape == g[f"out_{regime}"].shape
+    np.testing.assert_array_equal(out, g[f"out_{regime}"])
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("regime", REGIMES)
+def test_window_indices_bit_exact(golden, case, regime):
+    import nndepth_b200 as nb
+    g = golden(case)
+    L, r = int(g["num_levels"]), int(g["radius"])
+    widths = [g[f"pyr{l}"].shape[1] for l in range(L)]
+    i0, i1 = nb.lookup_indices(widths, dev(g[f"coords_{regime}"]), L, r)
+    for l in range(L):
+        np.testing.assert_array_equal(i0[l].cpu().numpy(), g[f"aten_i0_{regime}_{l}"])
+        np.testing.assert_array_equal(i1[l].cpu().numpy(), g[f"aten_i1_{regime}_{l}"])
+
+
+@pytest.mark.parametrize("w2", [240, 160, 156, 120, 80, 78, 60, 40, 39, 30, 20, 19, 9, 5, 2])
+def test_integer_round_trip_table(golden, w2):
+    """x/(w2-1)*(w2-1) does not round-trip integers; floor/ceil must match ATen's."""
+    import nndepth_b200 as nb
+    g = golden("sampler_kats")
+    coords = torch.arange(w2, dtype=torch.float32, device="cuda").view(1, 1, 1, w2)
+    i0, i1 = nb.lookup_indices([w2], coords, 1, 0)
+    np.testing.assert_array_equal(i0.view(-1).cpu().numpy(), g[f"aten_rt_floor_{w2}"])
+    np.testing.assert_array_equal(i1.view(-1).cpu().numpy(), g[f"aten_rt_ceil_{w2}"])
+    ramp = torch.arange(w2, dtype=torch.float32, device="cuda")[None] * 1.5 - 3
+    out = nb.linear_sampler(ramp, coords.view(1, w2))
+    np.testing.assert_array_equal(out[0].cpu().numpy(), g[f"rt_out_{w2}"])
+
+
+def test_linear_sampler_known_answers(golden):
+    import nndepth_b200 as nb
+    g = golden("sampler_kats")
+    out = nb.linear_sampler(dev(g["kat_row"]), dev(g["kat_x"]))
+    np.testing.assert_array_equal(out.cpu().numpy(), g["kat_out"])
+    np.testing.assert_array_equal(out[0].cpu().numpy(), np.float32([0, 0, 0, 0.25, 8.75, 9, 9, 9]))
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_build_fp32_vs_reference(golden, case):
+    import nndepth_b200 as nb
+    g = golden(case)
+    L, r = int(g["num_levels"]), int(g["radius"])
+    blk = nb.CorrBlock1D(dev(g["fmap1"]), dev(g["fmap2"]), L, r, precision="fp32")
+    pyr = blk.corr_pyramid
+    assert len(pyr) == L + 1
+    scale = np.abs(g["pyr0"]).max()
+    for l in range(L + 1):
+        got = pyr[l].reshape(pyr[l].shape[0], -1).cpu().numpy()
+        assert got.shape == g[f"pyr{l}"].shape
+        np.testing.assert_allclose(got, g[f"pyr{l}"], rtol=VOLUME_RTOL, atol=VOLUME_RTOL * scale)
+    # pooling is exact arithmetic on our own level 0: bit-exact against avg_pool1d's (a+b)/2
+    lvl = pyr[0].reshape(pyr[0].shape[0], -1).cpu().numpy()
+    for l in range(1, L + 1):
+        lvl = oc.avg_pool_pairs(lvl)
+        np.testing.assert_array_equal(pyr[l].reshape(pyr[l].shape[0], -1).cpu().numpy(), lvl)
+    vol = nb.CorrBlock1D.corr(dev(g["fmap1"]), dev(g["fmap2"]), precision="fp32")
+    B, H, W = shape_of(g)
+    assert tuple(vol.shape) == (B, H, W, W)
+    np.testing.assert_array_equal(vol.reshape(-1, W).cpu().numpy(), pyr[0].reshape(-1, W).cpu().numpy())
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("regime", REGIMES)
+def test_build_and_lookup_end_to_end(golden, case, regime):
+    """Own volume + own lookup vs the reference's output: only the fp32 contraction order differs."""
+    import nndepth_b200 as nb
+    g = golden(case)
+    L, r = int(g["num_levels"]), int(g["radius"])
+    blk = nb.CorrBlock1D(dev(g["fmap1"]), dev(g["fmap2"]), L, r, precision="fp32")
+    out = blk(dev(g[f"coords_{regime}"])).cpu().numpy()
+    scale = np.abs(g["pyr0"]).max()
+    np.testing.assert_allclose(out, g[f"out_{regime}"], rtol=VOLUME_RTOL, atol=VOLUME_RTOL * scale)
+
+
+def test_config1_against_oracle():
+    """BASELINE config 1: 256-ch 80x160 features, 4 levels, radius 4 -- oracle (numpy) vs CUDA."""
+    import nndepth_b200 as nb
+    rng = np.random.default_rng(1)
+    B, C, H, W = 1, 256, 80, 160
+    f1 = rng.standard_normal((B, C, H, W), dtype=np.float32)
+    f2 = rng.standard_normal((B, C, H, W), dtype=np.float32)
+    grid = np.broadcast_to(np.arange(W, dtype=np.float32), (B, 1, H, W)).copy()
+    sub = grid - rng.uniform(0, 40, size=grid.shape).astype(np.float32)
+    sub.reshape(-1)[::97] = -7.5
+    sub.reshape(-1)[5::101] = W + 3.25
+    ora = oc.CorrBlock1D(f1, f2, 4, 4)
+    blk = nb.CorrBlock1D(dev(f1), dev(f2), 4, 4, precision="fp32")
+    scale = np.abs(ora.corr_pyramid[0]).max()
+    for l in range(4):
+        got = blk.corr_pyramid[l].reshape(B * H * W, -1).cpu().numpy()
+        np.testing.assert_allclose(got, ora.corr_pyramid[l], rtol=VOLUME_RTOL, atol=VOLUME_RTOL * scale)
+    for coords in (grid, sub):
+        got = blk(dev(coords)).cpu().numpy()
+        np.testing.assert_allclose(got, ora(coords), rtol=VOLUME_RTOL, atol=VOLUME_RTOL * scale)
+        # identical pyramid -> identical lookup bits
+        same = nb.CorrBlock1D.from_pyramid(ora.corr_pyramid, B, H, 4, 4)
+        np.testing.assert_array_equal(same(dev(coords)).cpu().numpy(), ora(coords))
+        i0, i1 = blk.lookup_indices(dev(coords))
+        for l, (o0, o1) in enumerate(oc.lookup_indices([160, 80, 40, 20], coords, 4, 4)):
+            np.testing.assert_array_equal(i0[l].cpu().numpy(), o0)
+            np.testing.assert_array_equal(i1[l].cpu().numpy(), o1)
+
+
+def test_config2_full_size_properties():
+    """BASELINE config 2 shapes (B8, 256 ch, 48x156): size-independent properties at full size."""
+    import nndepth_b200 as nb
+    torch.manual_seed(2)
+    B, C, H, W = 8, 256, 48, 156
+    f1 = torch.randn(B, C, H, W, device="cuda")
+    f2 = torch.randn(B, C, H, W, device="cuda")
+    blk = nb.CorrBlock1D(f1, f2, 4, 4, precision="fp32")
+    pyr = blk.corr_pyramid
+    assert [p.shape[-1] for p in pyr] == [156, 78, 39, 19, 9]
+    # (1) the volume against an fp64 contraction on the device
+    ref = torch.einsum("bchi,bchj->bhij", f1.double(), f2.double()).float() / 16.0
+    scale = ref.abs().max().item()
+    err = (pyr[0].reshape(B, H, W, W) - ref).abs().max().item()
+    assert err <= VOLUME_RTOL * scale, (err, scale)
+    # (2) every pooled level is exactly (x[2j] + x[2j+1]) * 0.5 of the level below, odd tails dropped
+    for l in range(4):
+        lo = pyr[l][:, 0]
+        half = lo.shape[1] // 2
+        expect = (lo[:, 0:2 * half:2] + lo[:, 1:2 * half:2]) * 0.5
+        assert torch.equal(pyr[l + 1][:, 0], expect)
+    # (3) linearity in fmap1: corr(a*f1 + g1, f2) == a*corr(f1,f2) + corr(g1,f2) up to fp32 rounding
+    g1 = torch.randn_like(f1)
+    lhs = nb.CorrBlock1D.corr(2.0 * f1 + g1, f2)
+    rhs = 2.0 * pyr[0].reshape(B, H, W, W) + nb.CorrBlock1D.corr(g1, f2)
+    assert (lhs - rhs).abs().max().item() <= 4 * VOLUME_RTOL * scale
+    # (4) lookup at far out-of-range coordinates returns the clamped border columns of every level
+    far = torch.full((B, 1, H, W), 1e6, device="cuda")
+    out = blk(far)
+    for l in range(4):
+        last = pyr[l][:, 0, -1].reshape(B, H, W)
+        for k in range(9):
+            assert torch.equal(out[:, l * 9 + k], last)
+    out = blk(-far)
+    for l in range(4):
+        first = pyr[l][:, 0, 0].reshape(B, H, W)
+        assert torch.equal(out[:, l * 9 + 4], first)
+    # (5) lookup vs a straightforward torch restatement on the device (same IEEE op order)
+    coords = torch.arange(W, device="cuda").float().view(1, 1, 1, W).repeat(B, 1, H, 1) - torch.rand(B, 1, H, W, device="cuda") * 40
+    got = blk(coords)
+    chunks = []
+    for l in range(4):
+        rows = pyr[l][:, 0]
+        w2 = rows.shape[1]
+        x = torch.linspace(-4, 4, 9, device="cuda").view(1, 9) + coords.reshape(-1, 1) / 2 ** l
+        t = torch.clamp(x / (w2 - 1), 0, 1) * (w2 - 1)
+        i0, i1 = t.floor().long(), t.ceil().long()
+        coef = i1 - t
+        chunks.append((coef * rows.gather(1, i0) + (1 - coef) * rows.gather(1, i1)).view(B, H, W, 9))
+    ref_out = torch.cat(chunks, -1).permute(0, 3, 1, 2)
+    # ATen's CUDA division may use a reciprocal: compare values (continuous), not bits
+    assert (got - ref_out).abs().max().item() <= 1e-5 * scale
+
+
+def test_group_corr_block_matches_reference(golden):
+    import nndepth_b200 as nb
+    g = golden("group_corr1d")
+    G = int(g["num_groups"])
+    B, H, W = shape_of(g)
+    blk = nb.GroupCorrBlock1D(dev(g["fmap1"]), dev(g["fmap2"]), 4, 4, G)
+    scale = np.abs(g["pyr0"]).max()
+    for l in range(5):
+        got = blk.corr_pyramid[l].reshape(-1, g[f"pyr{l}"].shape[1]).cpu().numpy()
+        np.testing.assert_allclose(got, g[f"pyr{l}"], rtol=VOLUME_RTOL, atol=VOLUME_RTOL * scale)
+    same = nb.GroupCorrBlock1D.from_pyramid([g[f"pyr{l}"] for l in range(4)], B, H, 4, 4, G)
+    for regime in REGIMES:
+        out = same(dev(g[f"coords_{regime}"])).cpu().numpy()
+        np.testing.assert_array_equal(out, g[f"out_{regime}"])
+        out = blk(dev(g[f"coords_{regime}"])).cpu().numpy()
+        np.testing.assert_allclose(out, g[f"out_{regime}"], rtol=VOLUME_RTOL, atol=VOLUME_RTOL * scale)
+
+
+def test_edge_cases_and_errors():
+    import nndepth_b200 as nb
+    f = torch.randn(1, 8, 2, 12, device="cuda")
+    # level 3 of a 12-wide volume has width 1: linear_sampler would divide by zero -> refused
+    blk = nb.CorrBlock1D(f, f, 4, 4)
+    with pytest.raises(nb.NNDepthError, match="width"):
+        blk(torch.zeros(1, 1, 2, 12, device="cuda"))
+    # a 5-level pyramid of width 12 has an empty level
+    with pytest.raises(ValueError):
+        nb.CorrBlock1D(f, f, 5, 4)
+    # mismatched coords
+    ok = nb.CorrBlock1D(f, f, 2, 4)
+    with pytest.raises(RuntimeError, match="coords"):
+        ok(torch.zeros(1, 1, 3, 12, device="cuda"))
+    # W1 != W2 is legal (rectangular volume)
+    f2 = torch.randn(1, 8, 2, 20, device="cuda")
+    rect = nb.CorrBlock1D(f, f2, 2, 2)
+    assert rect.corr_pyramid[0].shape == (24, 1, 20)
+    ref = torch.einsum("bchi,bchj->bhij", f, f2) / 8 ** 0.5
+    assert torch.allclose(rect.corr_pyramid[0].reshape(1, 2, 12, 20), ref, rtol=1e-5, atol=1e-5)
+    assert rect(torch.zeros(1, 1, 2, 12, device="cuda")).shape == (1, 10, 2, 12)
+    # non-contiguous and half inputs are densified/cast like the reference's .float()
+    nc = torch.randn(1, 2, 12, 8, device="cuda").permute(0, 3, 1, 2)
+    a = nb.CorrBlock1D(nc, nc.half().float(), 2, 4)
+    assert a.corr_pyramid[0].shape == (24, 1, 12)
+    # NaN coordinates read index 0 instead of faulting
+    out = ok(torch.full((1, 1, 2, 12), float("nan"), device="cuda"))
+    assert out.shape == (1, 18, 2, 12)
+    torch.cuda.synchronize()
+    # gradients are refused, not silently dropped
+    with pytest.raises(RuntimeError, match="inference-only"):
+        nb.CorrBlock1D(f.clone().requires_grad_(True), f)

@@ -1,0 +1,142 @@
+"""GPU parity: IGEV group-wise volume, geometry re-layout + pooling, dual lookup, soft-argmin."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import igev as oi
+
+pytestmark = pytest.mark.gpu
+
+REGIMES = ["int", "sub", "oob"]
+VOLUME_RTOL = 1e-5          # fp32 bar of BASELINE.json
+SOFTARGMIN_ATOL = 2e-4      # px; far inside the 0.01 px end-point budget of BASELINE.json
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).cuda()
+
+
+def toy_regularizer(vol, feats):
+    """Same stand-in as tests/golden/make_goldens.py (the 3-D hourglass is out of scope)."""
+    return torch.tanh(vol) * 0.5 + torch.roll(vol, 1, dims=2) * 0.25 + feats[0].mean() * 0.0
+
+
+def test_groupwise_volume_matches_reference(golden):
+    import nndepth_b200 as nb
+    g = golden("igev")
+    G = int(g["num_groups"])
+    f1, f2 = dev(g["fmap1"]), dev(g["fmap2"])
+    cv = nb.GeometryAwareCostVolume(f1, f2, [dev(np.zeros((2, 4, 3, 24), np.float32))], toy_regularizer, 4, 4, G)
+    vol = cv.build_cost_volume(f1, f2)
+    ref = g["feat_volume"]
+    assert tuple(vol.shape) == ref.shape
+    np.testing.assert_allclose(vol.cpu().numpy(), ref, rtol=VOLUME_RTOL, atol=VOLUME_RTOL * np.abs(ref).max())
+    # only the first G*G channels enter the volume
+    f1z = f1.clone()
+    f1z[:, G * G:] = 7.0
+    assert torch.equal(cv.build_cost_volume(f1z, f2), vol)
+    # pyramids of the constructor: feature side within tolerance, pooling exact on own level 0
+    scale = np.abs(ref).max()
+    for l in range(5):
+        got = cv.feat_corr_cv[l].reshape(-1, g[f"feat_pyr{l}"].shape[1]).cpu().numpy()
+        np.testing.assert_allclose(got, g[f"feat_pyr{l}"], rtol=VOLUME_RTOL, atol=VOLUME_RTOL * scale)
+    # geometry side: regulariser is elementwise-ish on our volume -> tolerance, and pooling exact
+    for l in range(5):
+        got = cv.geo_aware_cv[l].reshape(-1, g[f"geo_pyr{l}"].shape[1]).cpu().numpy()
+        np.testing.assert_allclose(got, g[f"geo_pyr{l}"], rtol=1e-4, atol=1e-5 * scale)
+    # model.py:144 reads geo_aware_cv[0] and reshapes it
+    B, H, W = 2, 3, 24
+    assert cv.geo_aware_cv[0].reshape(B, G, H, W, W).permute(0, 1, 4, 2, 3).shape == (B, G, W, H, W)
+
+
+def test_geo_transpose_pool_bit_exact(golden):
+    """Pure data movement + avg_pool1d arithmetic: bit-exact against the reference pyramid."""
+    import nndepth_b200 as nb
+    g = golden("igev")
+    G = int(g["num_groups"])
+    geo = dev(g["geo_volume"])
+
+    def regulariser(vol, feats):
+        return geo
+
+    cv = nb.GeometryAwareCostVolume(dev(g["fmap1"]), dev(g["fmap2"]), [], regulariser, 4, 4, G)
+    for l in range(5):
+        got = cv.geo_aware_cv[l].reshape(-1, g[f"geo_pyr{l}"].shape[1]).cpu().numpy()
+        np.testing.assert_array_equal(got, g[f"geo_pyr{l}"])
+
+
+@pytest.mark.parametrize("regime", REGIMES)
+def test_dual_lookup_bit_exact(golden, regime):
+    import nndepth_b200 as nb
+    g = golden("igev")
+    G = int(g["num_groups"])
+    cv = nb.GeometryAwareCostVolume.from_pyramids([g[f"feat_pyr{l}"] for l in range(4)],
+                                                  [g[f"geo_pyr{l}"] for l in range(4)], 2, 3, 4, 4, G)
+    out = cv(dev(g[f"coords_{regime}"])).cpu().numpy()
+    assert out.shape == g[f"out_{regime}"].shape == (2, 4 * 2 * G * 9, 3, 24)
+    np.testing.assert_array_equal(out, g[f"out_{regime}"])
+
+
+def test_soft_argmin_golden(golden):
+    import nndepth_b200 as nb
+    g = golden("igev")
+    out = nb.soft_argmin(dev(g["sa_logits"])).cpu().numpy()
+    assert out.shape == g["sa_disp"].shape
+    np.testing.assert_allclose(out, g["sa_disp"], rtol=1e-5, atol=SOFTARGMIN_ATOL)
+    assert out[0, 0, 0, 1] == -5.0                                   # one-hot row
+    np.testing.assert_allclose(out[0, 0, 0, 0], -11.5, rtol=1e-6)    # uniform row: mean of 0..23
+    np.testing.assert_allclose(out[1, 0, 4, 6], -11.5, rtol=1e-6)    # large negative constant row
+
+
+@pytest.mark.parametrize("shape", [(2, 160, 30, 40), (1, 7, 3, 5), (3, 33, 1, 70), (1, 1, 2, 2)])
+def test_soft_argmin_vs_oracle(shape):
+    import nndepth_b200 as nb
+    rng = np.random.default_rng(5)
+    z = (rng.standard_normal(shape) * 4).astype(np.float32)
+    out = nb.soft_argmin(dev(z)).cpu().numpy()
+    np.testing.assert_allclose(out, oi.soft_argmin(z), rtol=1e-5, atol=SOFTARGMIN_ATOL)
+
+
+def test_config4_shapes_properties():
+    """BASELINE config 4 geometry at reduced batch (B=2 of 16; rows are independent): 120x160, G=8, D=160."""
+    import nndepth_b200 as nb
+    torch.manual_seed(4)
+    B, C, H, W, G = 2, 256, 120, 160, 8
+    f1 = torch.randn(B, C, H, W, device="cuda")
+    f2 = torch.randn(B, C, H, W, device="cuda")
+
+    def regulariser(vol, feats):
+        return torch.tanh(vol) * 0.5 + 0.125
+
+    cv = nb.GeometryAwareCostVolume(f1, f2, [], regulariser, 4, 4, G)
+    feat, geo = cv.feat_corr_cv, cv.geo_aware_cv
+    # volume vs fp64 contraction over the first 64 channels
+    a = f1[:, :G * G].reshape(B, G, G, H, W).double()
+    b = f2[:, :G * G].reshape(B, G, G, H, W).double()
+    ref = (torch.einsum("bgchi,bgchj->bghij", a, b) / G ** 0.5).float()
+    scale = ref.abs().max().item()
+    assert (feat[0].reshape(B, G, H, W, W) - ref).abs().max().item() <= VOLUME_RTOL * scale
+    # geometry level 0 == regulariser(vol permuted) permuted back, bit for bit
+    expect = regulariser(feat[0].reshape(B, G, H, W, W).permute(0, 1, 4, 2, 3), []).permute(0, 1, 3, 4, 2)
+    assert torch.equal(geo[0].reshape(B, G, H, W, W), expect)
+    for pyr in (feat, geo):
+        assert [p.shape[-1] for p in pyr] == [160, 80, 40, 20, 10]
+        for l in range(4):
+            lo = pyr[l][:, 0]
+            assert torch.equal(pyr[l + 1][:, 0], (lo[:, 0::2] + lo[:, 1::2]) * 0.5)
+    # dual lookup vs the single-pyramid kernel applied per (source, group) plane
+    coords = torch.arange(W, device="cuda").float().view(1, 1, 1, W).repeat(B, 1, H, 1) - torch.rand(B, 1, H, W, device="cuda") * 40
+    out = cv(coords)
+    assert out.shape == (B, 576, H, W)
+    for src, pyr in enumerate((feat, geo)):
+        for g in (0, 3, 7):
+            levels = [p[:, 0].reshape(B, G, H * W, -1)[:, g].reshape(B * H * W, -1) for p in pyr[:4]]
+            single = nb.CorrBlock1D.from_pyramid(levels, B, H, 4, 4)(coords)
+            for l in range(4):
+                ch = l * 144 + src * 72 + g * 9
+                assert torch.equal(out[:, ch:ch + 9], single[:, l * 9:(l + 1) * 9])
+    # soft-argmin at the config's (D,H,W) vs torch on the device
+    z = torch.randn(B, W, H, W, device="cuda") * 3
+    d = torch.arange(W, device="cuda").float().view(1, -1, 1, 1)
+    ref_sa = -(torch.softmax(z.double(), 1) * d).sum(1, keepdim=True).float()
+    assert (nb.soft_argmin(z) - ref_sa).abs().max().item() <= SOFTARGMIN_ATOL

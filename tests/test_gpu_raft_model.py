@@ -1,0 +1,66 @@
+"""GPU parity of the full RAFT-Stereo forward on the B200 kernels vs the reference model's outputs.
+
+Bar (BASELINE.json): final disparity end-point error within 0.01 px of the reference.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import epe, seeded_pair, state_fingerprint
+
+pytestmark = pytest.mark.gpu
+EPE_BAR = 0.01
+
+
+def build(golden_case, final_only=False):
+    from nndepth_b200.raft_stereo import BaseRAFTStereo
+    torch.manual_seed(0)
+    model = BaseRAFTStereo(iters=int(golden_case["iters"])).eval()
+    np.testing.assert_allclose(state_fingerprint(model), golden_case["fingerprint"], rtol=1e-12)
+    model = model.cuda()
+    model.final_only = final_only
+    return model
+
+
+@pytest.mark.parametrize("tf32_convs", [False, True])
+def test_small_all_iterations(golden, tf32_convs):
+    g = golden("raft_small")
+    model = build(g)
+    left, right = (t.cuda() for t in seeded_pair(g["shape"]))
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = tf32_convs
+    try:
+        with torch.no_grad():
+            outs = model(left, right)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    ref = torch.from_numpy(g["all_up_disp"]).cuda()
+    assert len(outs) == int(g["iters"])
+    for i, o in enumerate(outs):
+        assert o["up_disp"].shape == ref[i].shape
+        assert epe(o["up_disp"], ref[i]) < EPE_BAR, (i, epe(o["up_disp"], ref[i]))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_kitti_32_iterations(golden, precision):
+    """BASELINE config 2 geometry (384x1248 padded KITTI, 32 iterations), one pair."""
+    import nndepth_b200 as nb
+    g = golden("raft_kitti")
+    model = build(g, final_only=True)
+    model.update_block.gru.fuse_gates()
+    left, right = (t.cuda() for t in seeded_pair(g["shape"]))
+    old_prec = nb.get_volume_precision()
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    nb.set_volume_precision(precision)
+    try:
+        with torch.no_grad():
+            out = model(left, right)[-1]["up_disp"]
+            graphed = model.forward_graphed(left, right)[-1]["up_disp"].clone()
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+        nb.set_volume_precision(old_prec)
+    ref = torch.from_numpy(g["final_up_disp"]).cuda()
+    assert out.shape == ref.shape == (1, 1, 384, 1248)
+    assert epe(out, ref) < EPE_BAR, epe(out, ref)
+    assert epe(graphed, ref) < EPE_BAR, epe(graphed, ref)
