@@ -174,6 +174,8 @@ def time_lookup_kernel(device, reps=40):
         e1.synchronize()
         cold.append(e0.elapsed_time(e1))
     for _ in range(reps):
+        # keep the GPU busy (~100 us spin) while the host enqueues, so the events bracket the kernel only
+        torch.cuda._sleep(200000)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         blk(coords)

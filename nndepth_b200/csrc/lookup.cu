@@ -5,19 +5,20 @@
 //                     mode 1   GroupCorrBlock1D.__call__       raft_stereo/cost_volume.py:92-111
 //   nnd_corr1d_lookup_indices  the integer half of linear_sampler, raft_stereo/utils.py:16-21
 //
-// Work decomposition: one warp = 32 consecutive pixels x one pyramid level (x a chunk of planes:
-// plane = (source pyramid, group)).  A pixel's window at a level is <= 2r+3 consecutive floats of
-// its own volume row, so neighbouring pixels never share data and a thread-per-pixel gather would
+// Work decomposition: one warp = 32 consecutive pixels of one image x one pyramid level (x a chunk of
+// planes: plane = (source pyramid, group)).  A pixel's window at a level is <= 2r+3 consecutive floats
+// of its own volume row, so neighbouring pixels never share data and a thread-per-pixel gather would
 // cost one L1 wavefront per lane per tap.  Instead the warp loads the 32 windows cooperatively --
 // WINQ lanes per pixel, one 16-byte load each, 32/WINQ rows per instruction -- parks them in a
-// bank-swizzled shared-memory tile and then every lane interpolates its own pixel's taps from
-// shared memory.  That is the minimum number of L1 wavefronts (one per touched row segment), the
-// loads of a warp are all independent (WINQ in flight per lane), and the stores are 128-byte
-// coalesced channel planes.
+// padded shared-memory tile and then every lane interpolates its own pixel's taps from shared
+// memory.  That is the minimum number of L1 wavefronts (one per touched row segment), the loads of
+// a warp are all independent (WINQ in flight per lane), and the stores are 128-byte coalesced
+// channel planes.  The kernel is instruction-issue sensitive (a launch moves only ~18 MB at the
+// KITTI shape), so the per-tap arithmetic is kept minimal: no 64-bit index math in the loops and an
+// exact 3-instruction division (sampler_quotient) instead of the generic IEEE division routine.
 //
-// Bit-exactness: tap positions follow the reference's fp32 operation order exactly
-// (common.cuh:sampler_position); integer indices therefore equal the CPU reference's, and the lerp
-// is evaluated without FMA contraction.
+// Bit-exactness: tap positions follow the reference's fp32 operation order exactly; integer indices
+// therefore equal the CPU reference's, and the lerp is evaluated without FMA contraction.
 #include "common.cuh"
 
 namespace nnd {
@@ -26,8 +27,7 @@ struct LookupArgs {
   ConstPyramid src[2];  // [0] = feature correlation, [1] = geometry volume (IGEV only)
   const float* coords;
   float* out;
-  long long hw;     // H * W1
-  long long n_pix;  // B * H * W1
+  int hw;           // H * W1 (pixels per image)
   int G;            // planes (groups) per pixel and source
   int n_src;        // 1 or 2
   int num_levels;
@@ -37,23 +37,59 @@ struct LookupArgs {
   int vec;               // 1: pitches % 4 == 0 and bases 16-byte aligned -> float4 loads
 };
 
-// Window bookkeeping for one (pixel, level): [lo, hi] is the index range the taps can touch.
-struct TapRange {
-  int lo, hi;
+// One tap of linear_sampler: position t (fp32, reference op order), neighbours i0 <= i1, lerp weights.
+struct Tap {
+  int i0, i1;
+  float coef, one_minus;
 };
 
-__device__ __forceinline__ float tap_x(int k, int r, float centre) {
-  // dx + coords / 2**i  (cost_volume.py:44-46): dx = k - r is an exact small integer.
-  return __fadd_rn(static_cast<float>(k - r), centre);
+struct LevelScale {
+  float span;      // w2 - 1
+  float inv_span;  // RN(1 / span)
+  float inv_pow2;  // 1 / 2**level (exact)
+};
+
+// x / span, correctly rounded, for x in [-1, span + 1]:  q = RN(x*y), r = x - q*span (exact, FMA),
+// q' = RN(q + r*y) with y = RN(1/span) is the IEEE quotient (Markstein's theorem; span is a small
+// positive integer, so y is never the all-ones-significand exception).  Inputs outside [-1, span+1]
+// are clamped first, which cannot change clamp(x/span, 0, 1); NaN becomes -1 (-> t = 0).
+// The theorem needs the residual r free of underflow, i.e. |x| >= ~2^-100.  For smaller non-zero |x|
+// the interpolated VALUE is unaffected (t is then 0 or a denormal: either way the result is row[0]
+// exactly), but ceil(t) could differ; EXACT_TINY (the index-reporting kernel) therefore routes those
+// inputs through the generic IEEE division.
+template <bool EXACT_TINY>
+__device__ __forceinline__ float sampler_quotient(float x, const LevelScale& s) {
+  x = fminf(fmaxf(x, -1.0f), s.span + 1.0f);
+  if (EXACT_TINY && fabsf(x) < 1e-30f) return __fdiv_rn(x, s.span);
+  const float q = __fmul_rn(x, s.inv_span);
+  const float r = __fmaf_rn(-q, s.span, x);
+  return __fmaf_rn(r, s.inv_span, q);
 }
 
-__device__ __forceinline__ TapRange tap_range(float centre, int r, float span) {
-  const float t_lo = sampler_position(tap_x(0, r, centre), span);
-  const float t_hi = sampler_position(tap_x(2 * r, r, centre), span);
-  TapRange tr;
-  tr.lo = static_cast<int>(floorf(t_lo));
-  tr.hi = static_cast<int>(ceilf(t_hi));
-  return tr;
+__device__ __forceinline__ LevelScale level_scale(int width, int lvl, float centre) {
+  LevelScale s;
+  s.span = static_cast<float>(width - 1);
+  s.inv_span = __frcp_rn(s.span);
+  s.inv_pow2 = 1.0f / static_cast<float>(1 << lvl);
+  (void)centre;
+  return s;
+}
+
+template <bool EXACT_TINY = false>
+__device__ __forceinline__ Tap make_tap(int k, int r, float centre, const LevelScale& s) {
+  // dx + coords / 2**i (cost_volume.py:44-46): dx = k - r is an exact small integer
+  const float x = __fadd_rn(static_cast<float>(k - r), centre);
+  // clamp(x / (w2-1), 0, 1) * (w2-1)   (utils.py:16-18); __saturatef maps NaN to 0
+  const float t = __fmul_rn(__saturatef(sampler_quotient<EXACT_TINY>(x, s)), s.span);
+  const float f0 = floorf(t);
+  Tap tap;
+  tap.i0 = static_cast<int>(f0);
+  const bool whole = (t == f0);
+  tap.i1 = tap.i0 + (whole ? 0 : 1);                        // ceil(t)
+  const float f1 = whole ? f0 : __fadd_rn(f0, 1.0f);        // float(idx1), exact
+  tap.coef = __fsub_rn(f1, t);                              // coef = idx1 - t      (utils.py:26)
+  tap.one_minus = __fsub_rn(1.0f, tap.coef);                // (1 - coef)           (utils.py:27)
+  return tap;
 }
 
 // WINQ : 16-byte quads per staged window (window = 4*WINQ floats >= 2r+6)
@@ -62,136 +98,140 @@ template <int WINQ, int TAPS>
 __global__ void __launch_bounds__(32 * NND_MAX_LEVELS)
 pyramid_lookup_kernel(const LookupArgs a) {
   constexpr int COLS = 4 * WINQ;
-  constexpr int PPL = 32 / WINQ;  // pixels per cooperative load instruction
+  constexpr int STRIDE = COLS + 1;  // odd word stride: lanes reading the same column hit 32 banks
+  constexpr int PPL = 32 / WINQ;    // pixels per cooperative load instruction
+  constexpr int NT = TAPS > 0 ? TAPS : 1;
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ float smem[];
 
   const int lane = threadIdx.x;
   const int lvl = threadIdx.y;
-  float* win = smem + lvl * (COLS * 32);
+  float* win = smem + lvl * (STRIDE * 32);
 
-  const long long pix0 = static_cast<long long>(blockIdx.x) * 32;
-  const long long pix = pix0 + lane;
-  const bool valid = pix < a.n_pix;
+  const int b = blockIdx.z;
+  const int rem0 = blockIdx.x * 32;   // first pixel (within the image) of this warp
+  const int rem = rem0 + lane;
+  const bool valid = rem < a.hw;
   const int r = a.radius;
   const int T = TAPS > 0 ? TAPS : 2 * r + 1;
   const int w = a.src[0].width[lvl];
   const int pitch = a.src[0].pitch[lvl];
-  const float span = static_cast<float>(w - 1);
 
-  const float c = valid ? __ldg(a.coords + pix) : 0.0f;
-  // coords / 2**lvl: scaling by a power of two is exact, so the product equals the IEEE quotient.
+  const float c = valid ? __ldg(a.coords + static_cast<long long>(b) * a.hw + rem) : 0.0f;
+  // coords / 2**lvl: scaling by a power of two is exact, so the product equals the IEEE quotient
   const float centre = __fmul_rn(c, 1.0f / static_cast<float>(1 << lvl));
-  const TapRange tr = tap_range(centre, r, span);
-  const int s = tr.lo & ~3;  // window start, quad aligned (rows are 16-byte aligned in vec mode)
+  const LevelScale sc = level_scale(w, lvl, centre);
 
-  // per-tap state: shared-memory word offsets of the two neighbours and the lerp weights
-  int o0[TAPS > 0 ? TAPS : 1], o1[TAPS > 0 ? TAPS : 1];
-  float cf[TAPS > 0 ? TAPS : 1], omc[TAPS > 0 ? TAPS : 1];
-  auto tap_setup = [&](int k, int& off0, int& off1, float& coef, float& one_minus) {
-    const float t = sampler_position(tap_x(k, r, centre), span);
-    const float f0 = floorf(t), f1 = ceilf(t);
-    int i0 = static_cast<int>(f0) - s, i1 = static_cast<int>(f1) - s;
-    i0 = min(max(i0, 0), COLS - 1);
-    i1 = min(max(i1, 0), COLS - 1);
-    off0 = i0 * 32 + ((lane + PPL * (i0 >> 2)) & 31);
-    off1 = i1 * 32 + ((lane + PPL * (i1 >> 2)) & 31);
-    coef = __fsub_rn(f1, t);               // coef = idx1 - t            (utils.py:26)
-    one_minus = __fsub_rn(1.0f, coef);     // (1 - coef)                 (utils.py:27)
-  };
+  // window range [lo, hi]: taps are monotone in k, so the extremes come from the first / last tap
+  int o0[NT], o1[NT];
+  float cf[NT], omc[NT];
+  int lo, hi;
   if (TAPS > 0) {
+    Tap tp[NT];
 #pragma unroll
-    for (int k = 0; k < TAPS; ++k) tap_setup(k, o0[k], o1[k], cf[k], omc[k]);
+    for (int k = 0; k < NT; ++k) tp[k] = make_tap(k, r, centre, sc);
+    lo = tp[0].i0;
+    hi = tp[NT - 1].i1;
+    const int base = lane * STRIDE - (lo & ~3);
+#pragma unroll
+    for (int k = 0; k < NT; ++k) {
+      o0[k] = base + tp[k].i0;
+      o1[k] = base + tp[k].i1;
+      cf[k] = tp[k].coef;
+      omc[k] = tp[k].one_minus;
+    }
+  } else {
+    lo = make_tap(0, r, centre, sc).i0;
+    hi = make_tap(2 * r, r, centre, sc).i1;
   }
+  const int s = lo & ~3;  // window start, quad aligned (rows are 16-byte aligned in vec mode)
 
   // cooperative loader role: this lane fetches quad q of pixel (j*PPL + lane/WINQ), j < WINQ
   const int q = lane % WINQ;
-  long long row0[WINQ];  // volume row of (pixel, group 0)
-  int col0[WINQ];        // first column of my quad, or -1 when the quad is not needed
-  int slot[WINQ];        // swizzled position of that pixel inside a column of the tile
+  int goff[WINQ];  // float offset of my quad relative to the warp's first volume row, or -1
+  int left[WINQ];  // valid columns from the start of my quad (scalar path)
 #pragma unroll
   for (int j = 0; j < WINQ; ++j) {
     const int p = j * PPL + lane / WINQ;
     const int sp = __shfl_sync(FULL, s, p);
-    const int hp = __shfl_sync(FULL, tr.hi, p);
-    const long long ppix = pix0 + p;
+    const int hp = __shfl_sync(FULL, hi, p);
     const int cq = sp + 4 * q;
-    const bool need = ppix < a.n_pix && cq <= hp && cq < w;
-    const long long pb = ppix / a.hw;
-    row0[j] = pb * a.G * a.hw + (ppix - pb * a.hw);
-    col0[j] = need ? cq : -1;
-    slot[j] = (p + PPL * q) & 31;
+    const bool need = (rem0 + p < a.hw) && cq <= hp && cq < w;
+    goff[j] = need ? p * pitch + cq : -1;
+    left[j] = w - cq;
   }
+  float* const my_quad = win + (lane / WINQ) * STRIDE + 4 * q;  // + j*PPL*STRIDE
 
-  const long long b = pix / a.hw;
-  const long long rem = pix - b * a.hw;
   const int GT = a.G * T;
-  const long long c_total = static_cast<long long>(a.num_levels) * a.n_src * GT;
   const int n_planes = a.n_src * a.G;
   const int plane_begin = blockIdx.y * a.planes_per_block;
   const int plane_end = min(plane_begin + a.planes_per_block, n_planes);
+  const long long c_total = static_cast<long long>(a.num_levels) * a.n_src * GT;
+  float* const out_img = a.out + static_cast<long long>(b) * c_total * a.hw;
 
   for (int plane = plane_begin; plane < plane_end; ++plane) {
-    const int sidx = plane / a.G;
+    const int sidx = plane >= a.G ? 1 : 0;
     const int g = plane - sidx * a.G;
-    const float* __restrict__ base = a.src[sidx].ptr[lvl];
+    // first volume row of this warp: ((b*G + g) * hw + rem0)
+    const float* __restrict__ rows =
+        a.src[sidx].ptr[lvl] + ((static_cast<long long>(b) * a.G + g) * a.hw + rem0) * pitch;
 
     float4 v[WINQ];
 #pragma unroll
     for (int j = 0; j < WINQ; ++j) {
       v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (col0[j] >= 0) {
-        const float* p = base + (row0[j] + g * a.hw) * pitch + col0[j];
+      if (goff[j] >= 0) {
+        const float* p = rows + goff[j];
         if (a.vec) {
           v[j] = ldg_f4(p);
         } else {
-          const int left = w - col0[j];
           v[j].x = __ldg(p);
-          if (left > 1) v[j].y = __ldg(p + 1);
-          if (left > 2) v[j].z = __ldg(p + 2);
-          if (left > 3) v[j].w = __ldg(p + 3);
+          if (left[j] > 1) v[j].y = __ldg(p + 1);
+          if (left[j] > 2) v[j].z = __ldg(p + 2);
+          if (left[j] > 3) v[j].w = __ldg(p + 3);
         }
       }
     }
 #pragma unroll
     for (int j = 0; j < WINQ; ++j) {
-      float* dst = win + (4 * q) * 32 + slot[j];
+      float* dst = my_quad + j * (PPL * STRIDE);
       dst[0] = v[j].x;
-      dst[32] = v[j].y;
-      dst[64] = v[j].z;
-      dst[96] = v[j].w;
+      dst[1] = v[j].y;
+      dst[2] = v[j].z;
+      dst[3] = v[j].w;
     }
     __syncwarp();
 
     if (valid) {
-      long long out_base;
       if (a.mode == 0) {
-        const long long ch0 = static_cast<long long>(lvl) * a.n_src * GT + static_cast<long long>(sidx) * GT + g * T;
-        out_base = (b * c_total + ch0) * a.hw + rem;
-      } else {
-        out_base = (b * c_total + static_cast<long long>(lvl) * GT) * a.hw;
-      }
-      for (int k = 0; k < T; ++k) {
-        int off0, off1;
-        float coef, one_minus;
+        float* op = out_img + (static_cast<long long>(lvl) * a.n_src * GT + sidx * GT + g * T) * a.hw + rem;
         if (TAPS > 0) {
-          off0 = o0[k]; off1 = o1[k]; coef = cf[k]; one_minus = omc[k];
+#pragma unroll
+          for (int k = 0; k < NT; ++k) {
+            // coef * val0 + (1 - coef) * val1, each operation rounded (utils.py:27)
+            op[static_cast<long long>(k) * a.hw] = __fadd_rn(__fmul_rn(cf[k], win[o0[k]]), __fmul_rn(omc[k], win[o1[k]]));
+          }
         } else {
-          tap_setup(k, off0, off1, coef, one_minus);
+          const int base = lane * STRIDE - s;
+          for (int k = 0; k < T; ++k) {
+            const Tap tp = make_tap(k, r, centre, sc);
+            const int i0 = min(max(base + tp.i0, lane * STRIDE), lane * STRIDE + COLS - 1);
+            const int i1 = min(max(base + tp.i1, lane * STRIDE), lane * STRIDE + COLS - 1);
+            op[static_cast<long long>(k) * a.hw] = __fadd_rn(__fmul_rn(tp.coef, win[i0]), __fmul_rn(tp.one_minus, win[i1]));
+          }
         }
-        const float v0 = win[off0];
-        const float v1 = win[off1];
-        // coef * val0 + (1 - coef) * val1, each operation rounded (utils.py:27)
-        const float res = __fadd_rn(__fmul_rn(coef, v0), __fmul_rn(one_minus, v1));
-        if (a.mode == 0) {
-          a.out[out_base + static_cast<long long>(k) * a.hw] = res;
-        } else {
-          // reference memory order is [b][g][h][w][k]; it is *viewed* as (B, H, W, G*T)
-          // (raft_stereo/cost_volume.py:108) and then permuted to NCHW.
+      } else {
+        // GroupCorrBlock1D: the sampled block, in memory order [b][g][h][w][k], is *viewed* as
+        // (B, H, W, G*T) (raft_stereo/cost_volume.py:108) and then permuted to NCHW.
+        float* op = out_img + static_cast<long long>(lvl) * GT * a.hw;
+        const int base = lane * STRIDE - s;
+        for (int k = 0; k < T; ++k) {
+          const Tap tp = make_tap(k, r, centre, sc);
+          const int i0 = min(max(base + tp.i0, lane * STRIDE), lane * STRIDE + COLS - 1);
+          const int i1 = min(max(base + tp.i1, lane * STRIDE), lane * STRIDE + COLS - 1);
+          const float res = __fadd_rn(__fmul_rn(tp.coef, win[i0]), __fmul_rn(tp.one_minus, win[i1]));
           const long long f = (static_cast<long long>(g) * a.hw + rem) * T + k;
-          const long long cprime = f % GT;
-          const long long pos = f / GT;
-          a.out[out_base + cprime * a.hw + pos] = res;
+          op[(f % GT) * a.hw + f / GT] = res;
         }
       }
     }
@@ -199,11 +239,9 @@ pyramid_lookup_kernel(const LookupArgs a) {
   }
 }
 
-__global__ void lookup_indices_kernel(const int* __restrict__ width_dev, const float* __restrict__ coords,
-                                      long long n_pix, int num_levels, int radius, int w0, int w1, int w2, int w3,
-                                      int w4, int w5, int w6, int w7, int32_t* __restrict__ idx0,
-                                      int32_t* __restrict__ idx1) {
-  (void)width_dev;
+__global__ void lookup_indices_kernel(const float* __restrict__ coords, long long n_pix, int num_levels, int radius,
+                                      int w0, int w1, int w2, int w3, int w4, int w5, int w6, int w7,
+                                      int32_t* __restrict__ idx0, int32_t* __restrict__ idx1) {
   const int T = 2 * radius + 1;
   const long long total = n_pix * T * num_levels;
   const int widths[NND_MAX_LEVELS] = {w0, w1, w2, w3, w4, w5, w6, w7};
@@ -213,11 +251,10 @@ __global__ void lookup_indices_kernel(const int* __restrict__ width_dev, const f
     const long long pl = i / T;
     const long long pix = pl % n_pix;
     const int lvl = static_cast<int>(pl / n_pix);
-    const float span = static_cast<float>(widths[lvl] - 1);
     const float centre = __fmul_rn(__ldg(coords + pix), 1.0f / static_cast<float>(1 << lvl));
-    const float t = sampler_position(tap_x(k, radius, centre), span);
-    idx0[i] = static_cast<int32_t>(floorf(t));
-    idx1[i] = static_cast<int32_t>(ceilf(t));
+    const Tap tp = make_tap<true>(k, radius, centre, level_scale(widths[lvl], lvl, centre));
+    idx0[i] = tp.i0;
+    idx1[i] = tp.i1;
   }
 }
 
@@ -226,6 +263,8 @@ static nnd_status launch_lookup(const float* const* level_a, const float* const*
                                 int radius, int n_src, int mode, float* out, cudaStream_t stream) {
   NND_REQUIRE(level_a && width && pitch && coords && out, "lookup: null pointer argument");
   NND_REQUIRE(B > 0 && G > 0 && H > 0 && W1 > 0, "lookup: B, G, H, W1 must be positive (got %d %d %d %d)", B, G, H, W1);
+  NND_REQUIRE(B <= 65535, "lookup: batch %d exceeds the grid limit (65535)", B);
+  NND_REQUIRE(static_cast<long long>(H) * W1 < (1LL << 30), "lookup: H*W1 too large");
   NND_REQUIRE(num_levels >= 1 && num_levels <= NND_MAX_LEVELS, "lookup: num_levels %d outside [1, %d]", num_levels,
               NND_MAX_LEVELS);
   NND_REQUIRE(radius >= 0 && radius <= 13, "lookup: radius %d outside [0, 13]", radius);
@@ -237,6 +276,7 @@ static nnd_status launch_lookup(const float* const* level_a, const float* const*
   for (int l = 0; l < num_levels; ++l) {
     // linear_sampler divides by (w2 - 1): a 1-wide level is a division by zero in the reference
     NND_REQUIRE(width[l] >= 2, "lookup: level %d has width %d; linear_sampler needs width >= 2", l, width[l]);
+    NND_REQUIRE(width[l] <= (1 << 22), "lookup: level %d width %d too large", l, width[l]);
     NND_REQUIRE(pitch[l] >= width[l], "lookup: level %d pitch %d < width %d", l, pitch[l], width[l]);
     NND_REQUIRE(level_a[l], "lookup: level %d pointer is null", l);
     a.src[0].ptr[l] = level_a[l];
@@ -253,8 +293,7 @@ static nnd_status launch_lookup(const float* const* level_a, const float* const*
   }
   a.coords = coords;
   a.out = out;
-  a.hw = static_cast<long long>(H) * W1;
-  a.n_pix = a.hw * B;
+  a.hw = H * W1;
   a.G = G;
   a.n_src = n_src;
   a.num_levels = num_levels;
@@ -264,18 +303,16 @@ static nnd_status launch_lookup(const float* const* level_a, const float* const*
   const int n_planes = n_src * G;
   a.planes_per_block = n_planes >= 8 ? 4 : n_planes;
 
-  const long long blocks_x = (a.n_pix + 31) / 32;
-  NND_REQUIRE(blocks_x <= 0x7fffffffLL, "lookup: too many pixels");
-  dim3 grid(static_cast<unsigned>(blocks_x), static_cast<unsigned>((n_planes + a.planes_per_block - 1) / a.planes_per_block));
+  dim3 grid((a.hw + 31) / 32, (n_planes + a.planes_per_block - 1) / a.planes_per_block, B);
   dim3 block(32, num_levels);
   if (radius <= 5) {
-    const size_t smem = static_cast<size_t>(num_levels) * 16 * 32 * sizeof(float);
-    if (radius == 4)
+    const size_t smem = static_cast<size_t>(num_levels) * 17 * 32 * sizeof(float);
+    if (radius == 4 && mode == 0)
       pyramid_lookup_kernel<4, 9><<<grid, block, smem, stream>>>(a);
     else
       pyramid_lookup_kernel<4, 0><<<grid, block, smem, stream>>>(a);
   } else {
-    const size_t smem = static_cast<size_t>(num_levels) * 32 * 32 * sizeof(float);
+    const size_t smem = static_cast<size_t>(num_levels) * 33 * 32 * sizeof(float);
     pyramid_lookup_kernel<8, 0><<<grid, block, smem, stream>>>(a);
   }
   return check_launch("pyramid_lookup_kernel");
@@ -311,7 +348,8 @@ nnd_status nnd_corr1d_lookup_indices(const int* width, const float* coords, int 
   NND_REQUIRE(radius >= 0 && radius <= 64, "lookup_indices: radius %d outside [0, 64]", radius);
   int w[NND_MAX_LEVELS] = {2, 2, 2, 2, 2, 2, 2, 2};
   for (int l = 0; l < num_levels; ++l) {
-    NND_REQUIRE(width[l] >= 2, "lookup_indices: level %d has width %d; linear_sampler needs width >= 2", l, width[l]);
+    NND_REQUIRE(width[l] >= 2 && width[l] <= (1 << 22),
+                "lookup_indices: level %d has width %d; linear_sampler needs width >= 2", l, width[l]);
     w[l] = width[l];
   }
   const long long n_pix = static_cast<long long>(B) * H * W1;
@@ -320,7 +358,7 @@ nnd_status nnd_corr1d_lookup_indices(const int* width, const float* coords, int 
   const long long want = (total + threads - 1) / threads;
   const int blocks = static_cast<int>(want < 148LL * 32 ? want : 148LL * 32);
   nnd::lookup_indices_kernel<<<blocks, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      nullptr, coords, n_pix, num_levels, radius, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], idx0, idx1);
+      coords, n_pix, num_levels, radius, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], idx0, idx1);
   return nnd::check_launch("lookup_indices_kernel");
 }
 
