@@ -133,6 +133,62 @@ def test_build_and_lookup_end_to_end(golden, case, regime):
     np.testing.assert_allclose(out, g[f"out_{regime}"], rtol=VOLUME_RTOL, atol=VOLUME_RTOL * scale)
 
 
+TF32_RTOL = 1e-3       # tf32-operand bar of BASELINE.json (relative to the volume's scale)
+
+
+@pytest.mark.parametrize("case", ["corr1d_small", "corr1d_kitti_row", "corr1d_r3l3"])
+def test_build_tf32_vs_reference(golden, case):
+    """tcgen05 path (TF32 operands, fp32 accumulation in TMEM) against the reference pyramid."""
+    import nndepth_b200 as nb
+    g = golden(case)
+    L, r = int(g["num_levels"]), int(g["radius"])
+    blk = nb.CorrBlock1D(dev(g["fmap1"]), dev(g["fmap2"]), L, r, precision="tf32")
+    pyr = blk.corr_pyramid
+    scale = np.abs(g["pyr0"]).max()
+    for l in range(L + 1):
+        got = pyr[l].reshape(pyr[l].shape[0], -1).cpu().numpy()
+        assert got.shape == g[f"pyr{l}"].shape
+        np.testing.assert_allclose(got, g[f"pyr{l}"], rtol=0, atol=TF32_RTOL * scale)
+    lvl = pyr[0].reshape(pyr[0].shape[0], -1).cpu().numpy()
+    for l in range(1, L + 1):                       # pooling stays exact arithmetic on our own level 0
+        lvl = oc.avg_pool_pairs(lvl)
+        np.testing.assert_array_equal(pyr[l].reshape(pyr[l].shape[0], -1).cpu().numpy(), lvl)
+    for regime in REGIMES:
+        out = blk(dev(g[f"coords_{regime}"])).cpu().numpy()
+        np.testing.assert_allclose(out, g[f"out_{regime}"], rtol=0, atol=TF32_RTOL * scale)
+
+
+@pytest.mark.parametrize("shape", [(8, 256, 48, 156, 156), (1, 256, 80, 160, 160), (1, 256, 17, 240, 240),
+                                   (2, 24, 3, 300, 300), (1, 16, 2, 520, 264), (1, 40, 2, 40, 72), (3, 7, 5, 8, 12)])
+def test_build_tf32_shapes(shape):
+    """BASELINE configs 2, 1 and 5 (one row band) at full width, plus multi-tile / ragged shapes."""
+    import nndepth_b200 as nb
+    B, C, H, W1, W2 = shape
+    torch.manual_seed(sum(shape))
+    f1 = torch.randn(B, C, H, W1, device="cuda")
+    f2 = torch.randn(B, C, H, W2, device="cuda")
+    L = 4 if (W2 >> 3) >= 2 else 1
+    blk = nb.CorrBlock1D(f1, f2, L, 4, precision="tf32")
+    pyr = blk.corr_pyramid
+    ref = torch.einsum("bchi,bchj->bhij", f1.double(), f2.double()).float() / C ** 0.5
+    scale = ref.abs().max().item()
+    assert (pyr[0].reshape(B, H, W1, W2) - ref).abs().max().item() <= TF32_RTOL * scale
+    fp32 = nb.CorrBlock1D(f1, f2, L, 4, precision="fp32").corr_pyramid
+    for l in range(L):
+        lo = pyr[l][:, 0]
+        half = lo.shape[1] // 2
+        assert torch.equal(pyr[l + 1][:, 0], (lo[:, 0:2 * half:2] + lo[:, 1:2 * half:2]) * 0.5)
+        assert (pyr[l][:, 0] - fp32[l][:, 0]).abs().max().item() <= TF32_RTOL * scale
+
+
+def test_build_tf32_refuses_unaligned_width():
+    """TMA needs 16-byte row strides: odd widths are refused loudly, never silently re-routed."""
+    import nndepth_b200 as nb
+    f = torch.randn(1, 16, 2, 39, device="cuda")
+    with pytest.raises(nb.NNDepthError, match="multiples of 4"):
+        nb.CorrBlock1D(f, f, 2, 4, precision="tf32")
+
+
 def test_config1_against_oracle():
     """BASELINE config 1: 256-ch 80x160 features, 4 levels, radius 4 -- oracle (numpy) vs CUDA."""
     import nndepth_b200 as nb
