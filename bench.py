@@ -241,6 +241,12 @@ def run_ours(args):
     nb.load_library()
     if args.volume_precision:
         nb.set_volume_precision(args.volume_precision)
+    # Parity first: the reference computes in fp32 (CPU).  With cuDNN's TF32 convolutions the final
+    # disparity drifts 0.015 px from the reference (> the 0.01 px bar, tools/exp_epe.py), with fp32
+    # convolutions 0.0002 px -- so the headline runs the dense layers in strict fp32; --conv-tf32 is the
+    # faster, out-of-tolerance variant, reported separately and never as `value`.
+    torch.backends.cudnn.allow_tf32 = bool(args.conv_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = bool(args.conv_tf32)
 
     torch.manual_seed(0)
     model = BaseRAFTStereo(iters=ITERS).eval()
@@ -353,6 +359,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--volume-precision", default=None, choices=["fp32", "tf32"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--conv-tf32", action="store_true",
+                    help="let cuDNN run the dense layers in TF32 (faster, 0.015 px off the reference: outside the bar)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -16,11 +16,13 @@ import torch
 
 from . import _lib
 
-_VOLUME_PRECISION = "fp32"
+_VOLUME_PRECISION = "tf32"
 
 
 def set_volume_precision(precision):
-    """``"fp32"`` (CUDA-core FFMA, 1e-5 parity bar) or ``"tf32"`` (tcgen05 tensor cores, 1e-3 bar)."""
+    """``"tf32"`` (default: tcgen05 tensor cores, operands rounded to nearest TF32, 1e-3 bar) or
+    ``"fp32"`` (CUDA-core FFMA, 1e-5 parity bar).  Shapes the tensor-core path cannot take (feature
+    widths not divisible by 4) run on the fp32 kernel when the precision is left at its default."""
     global _VOLUME_PRECISION
     if precision not in ("fp32", "tf32"):
         raise ValueError(f"precision must be 'fp32' or 'tf32', got {precision!r}")
@@ -31,8 +33,11 @@ def get_volume_precision():
     return _VOLUME_PRECISION
 
 
-def _prec_code(precision):
-    precision = precision or _VOLUME_PRECISION
+def _prec_code(precision, W1=4, W2=4):
+    if precision is None:
+        precision = _VOLUME_PRECISION
+        if precision == "tf32" and (W1 % 4 or W2 % 4):
+            precision = "fp32"      # 16-byte TMA rows need widths divisible by 4: same result on the fp32 kernel
     if precision not in ("fp32", "tf32"):
         raise ValueError(f"precision must be 'fp32' or 'tf32', got {precision!r}")
     return _lib.PREC_TF32 if precision == "tf32" else _lib.PREC_FP32
@@ -130,7 +135,7 @@ class CorrBlock1D:
         with torch.cuda.device(f1.device):
             _lib.check(
                 _lib.load().nnd_corr1d_build(_lib.ptr(f1), _lib.ptr(f2), B, C, H, W1, W2, num_levels,
-                                             _prec_code(precision), self._pyr._level_ptrs, self._pyr._pitch_arr,
+                                             _prec_code(precision, W1, W2), self._pyr._level_ptrs, self._pyr._pitch_arr,
                                              _lib.stream_ptr(f1)),
                 "nnd_corr1d_build",
             )
@@ -180,7 +185,7 @@ class CorrBlock1D:
         pyr = PyramidStorage(B * H * W1, W2, 1, f1.device)
         with torch.cuda.device(f1.device):
             _lib.check(
-                _lib.load().nnd_corr1d_build(_lib.ptr(f1), _lib.ptr(f2), B, C, H, W1, W2, 1, _prec_code(precision),
+                _lib.load().nnd_corr1d_build(_lib.ptr(f1), _lib.ptr(f2), B, C, H, W1, W2, 1, _prec_code(precision, W1, W2),
                                              pyr._level_ptrs, pyr._pitch_arr, _lib.stream_ptr(f1)),
                 "nnd_corr1d_build",
             )

@@ -1,5 +1,6 @@
-// Tensor-core build of the RAFT-Stereo correlation pyramid: TMA -> shared memory -> tcgen05.mma
-// (kind::tf32, fp32 accumulators in TMEM) -> pooled 4-level epilogue -> TMA stores.  sm_100a only.
+// Tensor-core build of the RAFT-Stereo correlation pyramid: TMA -> shared memory (RN-rounded to
+// TF32 in place) -> tcgen05.mma (kind::tf32, fp32 accumulators in TMEM) -> pooled 4-level epilogue ->
+// TMA stores.  sm_100a only.
 //
 // Replaces CorrBlock1D.corr + CorrBlock1D.__init__ (nndepth/models/raft_stereo/cost_volume.py:55-61,
 // :12-34): torch.matmul(f1^T, f2) / C**0.5 followed by four avg_pool1d passes.
@@ -9,17 +10,27 @@
 // are "MN-major" in UMMA terms -- which tcgen05 supports for TF32, so the features are consumed where
 // they lie (no transposes, no staging pass):
 //
-//   * TMA boxes {32 w, 1 h, KB c, 1 b} with SWIZZLE_128B_ATOM_32B land as [KB rows of c][128 B of w]:
-//     exactly the canonical MN-major "SW128 / 32-byte base" atom (4 rows x 128 B, 32-byte chunks XORed
-//     with row % 4) -- the ONLY shared-memory layout tcgen05 accepts for MN-major 32-bit operands (the
-//     plain 128B swizzle silently yields zeros).  Atoms stack along c (stride byte offset 512); a
-//     128-row M tile is four boxes (leading byte offset = box size), an N<=256 tile up to eight.
-//   * one elected thread issues tcgen05.mma M=128, N=roundup16(W2), K=8 per 8 channels; the whole
-//     W1 x W2 row (W1, W2 <= 256 per job) accumulates in TMEM: two M tiles x <=256 columns = 512.
-//   * four epilogue warps read their TMEM lane quarter 32 columns at a time (tcgen05.ld 32x32b.x32),
-//     scale by 1/sqrt(C), pool in registers (a thread owns one volume row -> 2/4/8-wide poolings are
-//     intra-thread, summed pairwise and halved like avg_pool1d), park the four level tiles in
-//     swizzled shared memory and TMA-store them; the tensor maps clip ragged widths (156/78/39/19).
+//   * shared-memory operand layout = the canonical MN-major "SW128 / 32-byte base" atom: boxes of
+//     [KB rows of c][128 B of w] with the 32-byte chunks of a row XORed with row % 4 -- the ONLY layout
+//     tcgen05 accepts for MN-major 32-bit operands (the plain 128B swizzle silently yields zeros).
+//     Atoms stack along c (stride byte offset 512); a 128-row M tile is four boxes (leading byte
+//     offset = box size), an N<=256 tile up to eight.
+//   * one producer thread feeds a ring of stages with TMA boxes {32 w, 1 h, 32 c, 1 b}
+//     (SWIZZLE_128B_ATOM_32B lands exactly that layout).  Measured on B200: these 4-KB boxes of 32
+//     strided, 16-byte-aligned 128-byte rows stream at ~4 TB/s chip-wide; a cp.async (LSU) loader with
+//     the same footprint was slower (its issue/handshake cost sits in the loader warps' critical path).
+//   * eight rounder warps take each landed stage and round it to TF32 with round-to-nearest IN PLACE
+//     before the tensor core sees it: tcgen05 kind::tf32 TRUNCATES the low 13 mantissa bits, a
+//     systematic shrink of every product that costs 0.0126 px of final EPE at KITTI/32 iterations
+//     against 0.0002 px with RN (tools/exp_epe.py).  full[s] (TMA) -> ready[s] (rounded) -> MMA.
+//   * one elected thread issues tcgen05.mma M=128, N=roundup16(W2), K=8 per 8 channels; both M tiles
+//     of a row share every B stage and accumulate in TMEM (2 x n_cols columns per job, two jobs
+//     double-buffered when that fits 512 columns).
+//   * four epilogue warps, each on its own (no cross-warp barrier), read their TMEM lane quarter 32
+//     columns at a time (tcgen05.ld 32x32b.x32), scale by 1/sqrt(C), pool in registers (a thread owns
+//     one volume row -> 2/4/8-wide poolings are intra-thread, summed pairwise and halved like
+//     avg_pool1d), park the four level tiles in swizzled shared memory and TMA-store them (lanes 0-3
+//     issue one level each); the tensor maps clip ragged widths (156/78/39/19) and ragged row tiles.
 //
 // The volume is written once and never re-read.  At BASELINE shapes the kernel is HBM-bound
 // (K = 256: ~25 flop/B, ridge > 200), so the pipeline is sized for bytes in flight, not MMA issue.
@@ -33,33 +44,45 @@ namespace nnd {
 namespace {
 
 constexpr int KB = 32;            // channels per pipeline stage (4 UMMA k-steps of 8)
-constexpr int BOX_W = 32;         // floats per TMA box row = 128 bytes = one swizzle span
+constexpr int BOX_W = 32;         // floats per box row = 128 bytes = one swizzle span
 constexpr int BOX_BYTES = KB * BOX_W * 4;
 constexpr int TILE_M = 128;
+constexpr int MAX_M = 2 * TILE_M; // volume rows per pass: two M tiles share every B stage
 constexpr int MAX_N = 256;
-constexpr int NUM_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
-constexpr int EPI_THREADS = 128;
+constexpr int EPI_WARPS = 4;      // warps 0-3: epilogue (TMEM lane quarter = warp index)
+constexpr int MMA_WARP = 4;       // warp 4: MMA issuer + TMEM owner
+constexpr int LOADER_WARP0 = 5;   // warps 5-12: round the landed operand tiles to TF32 (RN) in place
+constexpr int LOADER_WARPS = 8;
+constexpr int TMA_WARP = LOADER_WARP0 + LOADER_WARPS;  // warp 13: TMA producer
+constexpr int EPI_THREADS = 32 * EPI_WARPS;
+constexpr int NUM_THREADS = 32 * (TMA_WARP + 1);
 constexpr int TMEM_COLS = 512;
 constexpr int CHUNK = 32;         // volume columns per epilogue step
+constexpr int MAX_STAGES = 6;
 
-// epilogue staging (one buffer set): level 0..3 tiles of 128 rows x {32,16,8,4} floats
-constexpr int EPI_L0 = 128 * 32 * 4, EPI_L1 = 128 * 16 * 4, EPI_L2 = 128 * 8 * 4, EPI_L3 = 128 * 4 * 4;
-constexpr int EPI_SET = EPI_L0 + EPI_L1 + EPI_L2 + EPI_L3;  // 30720 B
+// epilogue staging, per warp and buffer set: level 0..3 tiles of 32 rows x {32,16,8,4} floats (7.5 KB, padded
+// to 8 KB so that every set keeps the 1024-byte alignment the 128B swizzle pattern is anchored to)
+constexpr int EPI_L0 = 32 * 32 * 4, EPI_L1 = 32 * 16 * 4, EPI_L2 = 32 * 8 * 4;  // level 3: 32 * 4 * 4 more
+constexpr int EPI_WARP_SET = 8192;
+constexpr int EPI_SET = EPI_WARPS * EPI_WARP_SET;  // one buffer set of all four epilogue warps
 
 struct BuildParams {
   int C, W1, W2;
-  int rows;         // B * H
+  int rows;            // B * H
   int H;
-  int num_levels;   // 1..4 fused
-  int m_groups;     // ceil(W1 / 256)
-  int n_chunks;     // ceil(W2 / 256)
+  int num_levels;      // 1..4 fused
+  int n_chunks;        // ceil(W2 / 256): column chunks, one job each
+  int m_passes;        // ceil(W1 / 256): passes of <= 2 M tiles per job
+  int a_region_boxes;  // ceil(min(W1, 256) / 32)
+  int b_region_boxes;  // ceil(min(W2, 256) / 32)
   int stages;
-  int stage_bytes;  // (a_boxes_padded + b_boxes) * BOX_BYTES
-  int a_boxes_pad;  // roundup4(max boxes of an m-group)
+  int stage_bytes;     // (a_region_boxes + b_region_boxes) * BOX_BYTES
+  int n_slots;         // accumulator slots in TMEM (2 when two jobs' accumulators fit 512 columns)
+  int slot_cols;
   float scale_div;
   float scale_inv;
   int scale_is_pow2;
-  long long jobs;   // rows * m_groups * n_chunks
+  long long jobs;      // rows * n_chunks
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -69,9 +92,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -97,12 +117,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   } while (!done);
 }
 
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                             int c3) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+__device__ __forceinline__ uint32_t rna_tf32(uint32_t x) {
+  uint32_t y;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(y) : "f"(__uint_as_float(x)));
+  return y;
 }
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
@@ -150,7 +178,6 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
 
 // UMMA shared-memory descriptor, MN-major, SWIZZLE_128B_BASE32B (bit layout of cute::UMMA::SmemDescriptor):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (stride between 32-element MN atoms)
@@ -171,6 +198,34 @@ __device__ __forceinline__ uint32_t umma_idesc_tf32(int n) {
          (static_cast<uint32_t>(TILE_M >> 4) << 24);
 }
 
+// Byte offset, inside an operand region, of 16-byte chunk j (= columns 4j..4j+3 of the region's first
+// column) of channel row r of a stage: box j/8, row r, 32-byte chunks XORed with r % 4.
+__device__ __forceinline__ uint32_t chunk_offset(int j, int r) {
+  const int jj = j & 7;
+  return static_cast<uint32_t>((j >> 3) * BOX_BYTES + r * 128 + ((((jj >> 1) ^ (r & 3)) << 5) | ((jj & 1) << 4)));
+}
+
+// A job = one epipolar row x one chunk of <= 256 volume columns; its M tiles are processed in passes of
+// <= 2 tiles, each pass accumulating over all channels into one TMEM slot.
+struct JobGeom {
+  int row, b, h;
+  int n0, n_ext, n_cols, n_mma, b_boxes;
+};
+
+__device__ __forceinline__ JobGeom job_geom(const BuildParams& p, long long job) {
+  JobGeom g;
+  g.row = static_cast<int>(job / p.n_chunks);
+  const int nc = static_cast<int>(job - static_cast<long long>(g.row) * p.n_chunks);
+  g.b = g.row / p.H;
+  g.h = g.row - g.b * p.H;
+  g.n0 = nc * MAX_N;
+  g.n_ext = min(p.W2 - g.n0, MAX_N);
+  g.b_boxes = (g.n_ext + BOX_W - 1) / BOX_W;
+  g.n_cols = g.b_boxes * BOX_W;  // TMEM columns per M tile
+  g.n_mma = (g.n_ext + 15) & ~15;
+  return g;
+}
+
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
@@ -184,30 +239,34 @@ corr1d_build_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* epi = smem + static_cast<size_t>(p.stages) * p.stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi + 2 * EPI_SET);
-  // bars[0..S) full, [S..2S) empty, [2S] tmem_full, [2S+1] tmem_empty
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 2);
+  // bars: full[s] (TMA landed), ready[s] (rounded to TF32), empty[s] (MMAs retired), tmem_full[slot], tmem_empty[slot]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * p.stages);
-  const uint32_t tmem_empty_bar = bar_base + 8u * (2 * p.stages + 1);
+  auto ready_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + s); };
+  auto tmem_full_bar = [&](uint32_t slot) { return bar_base + 8u * (3 * MAX_STAGES + slot); };
+  auto tmem_empty_bar = [&](uint32_t slot) { return bar_base + 8u * (3 * MAX_STAGES + 2 + slot); };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar(s), 1);
+      mbar_init(ready_bar(s), LOADER_WARPS);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tmem_full_bar, 1);
-    mbar_init(tmem_empty_bar, EPI_THREADS);
+    for (uint32_t slot = 0; slot < 2; ++slot) {
+      mbar_init(tmem_full_bar(slot), 1);
+      mbar_init(tmem_empty_bar(slot), EPI_THREADS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     prefetch_tmap(&map_a);
     prefetch_tmap(&map_b);
     prefetch_tmap(&map_l0);
   }
-  if (warp == 1) {
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "n"(TMEM_COLS)
                  : "memory");
@@ -219,163 +278,212 @@ corr1d_build_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   const uint32_t tmem_base = *tmem_slot;
 
   const int k_blocks = (p.C + KB - 1) / KB;
-  const int jobs_per_row = p.m_groups * p.n_chunks;
+  const uint32_t b_region = static_cast<uint32_t>(p.a_region_boxes) * BOX_BYTES;
 
-  if (warp == 0) {
+  if (warp == TMA_WARP) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (long long job = blockIdx.x; job < p.jobs; job += gridDim.x) {
-        const int row = static_cast<int>(job / jobs_per_row);
-        const int sub = static_cast<int>(job - static_cast<long long>(row) * jobs_per_row);
-        const int mg = sub / p.n_chunks, nc = sub - mg * p.n_chunks;
-        const int b = row / p.H, h = row - b * p.H;
-        const int m0 = mg * 2 * TILE_M, n0 = nc * MAX_N;
-        const int a_boxes = (min(p.W1 - m0, 2 * TILE_M) + BOX_W - 1) / BOX_W;
-        const int b_boxes = (min(p.W2 - n0, MAX_N) + BOX_W - 1) / BOX_W;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
-          const uint32_t sbase = smem_u32(smem + static_cast<size_t>(stage) * p.stage_bytes);
-          mbar_expect_tx(full_bar(stage), static_cast<uint32_t>((a_boxes + b_boxes) * BOX_BYTES));
-          for (int i = 0; i < a_boxes; ++i)
-            tma_load_4d(sbase + i * BOX_BYTES, &map_a, full_bar(stage), m0 + i * BOX_W, h, kb * KB, b);
-          const uint32_t bbase = sbase + p.a_boxes_pad * BOX_BYTES;
-          for (int i = 0; i < b_boxes; ++i)
-            tma_load_4d(bbase + i * BOX_BYTES, &map_b, full_bar(stage), n0 + i * BOX_W, h, kb * KB, b);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        const JobGeom g = job_geom(p, job);
+        for (int pass = 0; pass < p.m_passes; ++pass) {
+          const int m_start = pass * MAX_M;
+          const int a_boxes = (min(p.W1 - m_start, MAX_M) + BOX_W - 1) / BOX_W;
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            const uint32_t sbase = smem_u32(smem + static_cast<size_t>(stage) * p.stage_bytes);
+            mbar_expect_tx(full_bar(stage), static_cast<uint32_t>((a_boxes + g.b_boxes) * BOX_BYTES));
+            for (int i = 0; i < a_boxes; ++i)
+              tma_load_4d(sbase + i * BOX_BYTES, &map_a, full_bar(stage), m_start + i * BOX_W, g.h, kb * KB, g.b);
+            for (int i = 0; i < g.b_boxes; ++i)
+              tma_load_4d(sbase + b_region + i * BOX_BYTES, &map_b, full_bar(stage), g.n0 + i * BOX_W, g.h, kb * KB, g.b);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp >= LOADER_WARP0) {
+    // ===================== rounders: TF32 round-to-nearest of the landed stage, in place =====================
+    // The tensor core truncates fp32 operands to TF32; rounding them to nearest first removes the bias.
+    // Every thread owns a fixed set of 16-byte chunks of a stage (whatever the boxes hold), so no
+    // geometry is needed here; stale chunks of partially filled regions are rounded harmlessly.
+    const int wl = warp - LOADER_WARP0;
+    constexpr int NCH = (KB / LOADER_WARPS) * 4;
+    uint32_t off[NCH];
+#pragma unroll
+    for (int rr = 0; rr < KB / LOADER_WARPS; ++rr) {
+      const int r = wl + LOADER_WARPS * rr;
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int j = lane + 32 * s;
+        off[rr * 4 + s * 2 + 0] = j < p.a_region_boxes * 8 ? chunk_offset(j, r) : 0xffffffffu;
+        off[rr * 4 + s * 2 + 1] = j < p.b_region_boxes * 8 ? b_region + chunk_offset(j, r) : 0xffffffffu;
+      }
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    long long iters = 0;
+    for (long long job = blockIdx.x; job < p.jobs; job += gridDim.x) iters += static_cast<long long>(p.m_passes) * k_blocks;
+    for (long long it = 0; it < iters; ++it) {
+      mbar_wait(full_bar(stage), phase);
+      uint8_t* sbase = smem + static_cast<size_t>(stage) * p.stage_bytes;
+      {
+        uint4 val[NCH];
+        // all loads first, then the conversions, then the stores: independent chunks overlap their latencies
+#pragma unroll
+        for (int i = 0; i < NCH; ++i)
+          val[i] = off[i] != 0xffffffffu ? *reinterpret_cast<const uint4*>(sbase + off[i]) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+          val[i].x = rna_tf32(val[i].x); val[i].y = rna_tf32(val[i].y);
+          val[i].z = rna_tf32(val[i].z); val[i].w = rna_tf32(val[i].w);
+        }
+#pragma unroll
+        for (int i = 0; i < NCH; ++i)
+          if (off[i] != 0xffffffffu) *reinterpret_cast<uint4*>(sbase + off[i]) = val[i];
+      }
+      fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ready_bar(stage));  // one arrival per rounder warp
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == MMA_WARP) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       int stage = 0;
-      uint32_t phase = 0, acc_phase = 0;
+      uint32_t phase = 0;
+      uint32_t acc_count = 0;  // accumulator slot = acc_count % n_slots
       for (long long job = blockIdx.x; job < p.jobs; job += gridDim.x) {
-        const int row = static_cast<int>(job / jobs_per_row);
-        const int sub = static_cast<int>(job - static_cast<long long>(row) * jobs_per_row);
-        const int mg = sub / p.n_chunks, nc = sub - mg * p.n_chunks;
-        const int m_ext = min(p.W1 - mg * 2 * TILE_M, 2 * TILE_M);
-        const int n_ext = min(p.W2 - nc * MAX_N, MAX_N);
-        const int m_tiles = (m_ext + TILE_M - 1) / TILE_M;
-        const int n_mma = (n_ext + 15) & ~15;
-        const int n_cols = ((n_ext + BOX_W - 1) / BOX_W) * BOX_W;  // TMEM columns per M tile
-        const uint32_t idesc = umma_idesc_tf32(n_mma);
-        mbar_wait(tmem_empty_bar, acc_phase ^ 1);  // epilogue has drained the previous job
-        tc_fence_after();
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(full_bar(stage), phase);
+        const JobGeom g = job_geom(p, job);
+        const uint32_t idesc = umma_idesc_tf32(g.n_mma);
+        for (int pass = 0; pass < p.m_passes; ++pass, ++acc_count) {
+          const int m_start = pass * MAX_M;
+          const int tiles = (min(p.W1 - m_start, MAX_M) + TILE_M - 1) / TILE_M;
+          const uint32_t slot = p.n_slots == 2 ? (acc_count & 1) : 0;
+          const uint32_t slot_phase = (p.n_slots == 2 ? (acc_count >> 1) : acc_count) & 1;
+          const uint32_t d_base = tmem_base + slot * p.slot_cols;
+          mbar_wait(tmem_empty_bar(slot), slot_phase ^ 1);  // the epilogue has drained this slot
           tc_fence_after();
-          const uint32_t sbase = smem_u32(smem + static_cast<size_t>(stage) * p.stage_bytes);
-          const uint32_t bbase = sbase + p.a_boxes_pad * BOX_BYTES;
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            mbar_wait(ready_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t sbase = smem_u32(smem + static_cast<size_t>(stage) * p.stage_bytes);
+            const uint32_t bbase = sbase + b_region;
 #pragma unroll
-          for (int ks = 0; ks < KB / 8; ++ks) {
-            const uint64_t bdesc = umma_desc_mn_sw128_32b(bbase + ks * 1024, BOX_BYTES, 512);
-            for (int mt = 0; mt < m_tiles; ++mt) {
-              const uint64_t adesc = umma_desc_mn_sw128_32b(sbase + mt * 4 * BOX_BYTES + ks * 1024, BOX_BYTES, 512);
-              tc_mma_tf32(tmem_base + mt * n_cols, adesc, bdesc, idesc, (kb | ks) != 0 ? 1u : 0u);
+            for (int ks = 0; ks < KB / 8; ++ks) {
+              const uint64_t bdesc = umma_desc_mn_sw128_32b(bbase + ks * 1024, BOX_BYTES, 512);
+              for (int t = 0; t < tiles; ++t) {
+                const uint64_t adesc = umma_desc_mn_sw128_32b(sbase + t * 4 * BOX_BYTES + ks * 1024, BOX_BYTES, 512);
+                tc_mma_tf32(d_base + t * g.n_cols, adesc, bdesc, idesc, (kb | ks) != 0 ? 1u : 0u);
+              }
             }
+            tc_commit(empty_bar(stage));  // frees this smem stage when the MMAs above retire
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
-          tc_commit(empty_bar(stage));  // frees this smem stage when the MMAs above retire
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          tc_commit(tmem_full_bar(slot));  // accumulators of this pass complete
         }
-        tc_commit(tmem_full_bar);  // accumulators complete
-        acc_phase ^= 1;
       }
     }
   } else {
-    // ===================== epilogue warps (TMEM lane quarter = warp % 4) =====================
-    const int quarter = warp & 3;
-    const int trow = quarter * 32 + lane;  // TMEM lane == row of the M tile
-    const int et = threadIdx.x - 64;       // 0..127 among the epilogue threads
-    uint32_t acc_phase = 0;
+    // ===================== epilogue warps (TMEM lane quarter = warp) =====================
+    // Each warp drains its own 32 volume rows independently (no cross-warp barrier): TMEM -> registers ->
+    // scale + pool -> its own swizzled staging tiles -> TMA stores issued by lanes 0..3 (one level each).
+    // A warp whose 32 rows lie past W1 (the ragged second M tile) skips the tile altogether.
+    const int quarter = warp;
+    uint32_t acc_count = 0;
     int chunk_parity = 0;
+    uint8_t* my_sets = epi + quarter * EPI_WARP_SET;  // + chunk_parity * EPI_SET
+    const CUtensorMap* my_map = lane == 0 ? &map_l0 : lane == 1 ? &map_l1 : lane == 2 ? &map_l2 : &map_l3;
+    const uint32_t my_level_off = lane == 0 ? 0u : lane == 1 ? EPI_L0 : lane == 2 ? EPI_L0 + EPI_L1 : EPI_L0 + EPI_L1 + EPI_L2;
+    const bool store_lane = lane < p.num_levels && lane < 4;
     for (long long job = blockIdx.x; job < p.jobs; job += gridDim.x) {
-      const int row = static_cast<int>(job / jobs_per_row);
-      const int sub = static_cast<int>(job - static_cast<long long>(row) * jobs_per_row);
-      const int mg = sub / p.n_chunks, nc = sub - mg * p.n_chunks;
-      const int m0 = mg * 2 * TILE_M, n0 = nc * MAX_N;
-      const int m_ext = min(p.W1 - m0, 2 * TILE_M);
-      const int n_ext = min(p.W2 - n0, MAX_N);
-      const int m_tiles = (m_ext + TILE_M - 1) / TILE_M;
-      const int n_cols = ((n_ext + BOX_W - 1) / BOX_W) * BOX_W;
-      const int n_chunks32 = n_cols / CHUNK;
+      const JobGeom g = job_geom(p, job);
+      const int n_chunks32 = g.n_cols / CHUNK;
+      for (int pass = 0; pass < p.m_passes; ++pass, ++acc_count) {
+        const int m_start = pass * MAX_M;
+        const int tiles = (min(p.W1 - m_start, MAX_M) + TILE_M - 1) / TILE_M;
+        const uint32_t slot = p.n_slots == 2 ? (acc_count & 1) : 0;
+        const uint32_t slot_phase = (p.n_slots == 2 ? (acc_count >> 1) : acc_count) & 1;
+        const uint32_t d_base = tmem_base + slot * p.slot_cols + (static_cast<uint32_t>(quarter * 32) << 16);
+        mbar_wait(tmem_full_bar(slot), slot_phase);
+        tc_fence_after();
+        // the last tile in which this warp owns valid rows: after its last TMEM read the slot is handed back
+        int last_tile = -1;
+        for (int t = 0; t < tiles; ++t)
+          if (m_start + t * TILE_M + quarter * 32 < p.W1) last_tile = t;
+        if (last_tile < 0) {
+          tc_fence_before();
+          mbar_arrive(tmem_empty_bar(slot));
+        }
+        for (int t = 0; t <= last_tile; ++t) {
+          const int mrow = m_start + t * TILE_M + quarter * 32;
+          for (int ch = 0; ch < n_chunks32; ++ch) {
+            float v[32];
+            tc_ld32(d_base + t * g.n_cols + ch * CHUNK, v);
+            if (t == last_tile && ch == n_chunks32 - 1) {
+              tc_fence_before();
+              mbar_arrive(tmem_empty_bar(slot));
+            }
+            if (p.scale_is_pow2) {  // x / 2^k == x * 2^-k exactly
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __fmul_rn(v[i], p.scale_inv);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __fdiv_rn(v[i], p.scale_div);
+            }
 
-      mbar_wait(tmem_full_bar, acc_phase);
-      tc_fence_after();
-      for (int mt = 0; mt < m_tiles; ++mt) {
-        for (int ch = 0; ch < n_chunks32; ++ch) {
-          float v[32];
-          tc_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + mt * n_cols + ch * CHUNK, v);
-          if (mt == m_tiles - 1 && ch == n_chunks32 - 1) {
-            // last TMEM read of this job: hand the accumulators back to the MMA warp
-            tc_fence_before();
-            mbar_arrive(tmem_empty_bar);
+            uint8_t* set = my_sets + chunk_parity * EPI_SET;
+            if (store_lane) tma_store_wait_read<1>();  // my store that last read this buffer set has drained
+            __syncwarp();
+            // level 0: 8 x 16-byte chunks per row, 128B swizzle (chunk ^= row & 7)
+            {
+              float4* dst = reinterpret_cast<float4*>(set + lane * 128);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                dst[j ^ (lane & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            float l1[16], l2[8], l3[4];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) l1[i] = pool2(v[2 * i], v[2 * i + 1]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) l2[i] = pool2(l1[2 * i], l1[2 * i + 1]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) l3[i] = pool2(l2[2 * i], l2[2 * i + 1]);
+            if (p.num_levels > 1) {  // 64 B per row, 64B swizzle (chunk ^= (row >> 1) & 3)
+              float4* dst = reinterpret_cast<float4*>(set + EPI_L0 + lane * 64);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                dst[j ^ ((lane >> 1) & 3)] = make_float4(l1[4 * j], l1[4 * j + 1], l1[4 * j + 2], l1[4 * j + 3]);
+            }
+            if (p.num_levels > 2) {  // 32 B per row, 32B swizzle (chunk ^= (row >> 2) & 1)
+              float4* dst = reinterpret_cast<float4*>(set + EPI_L0 + EPI_L1 + lane * 32);
+#pragma unroll
+              for (int j = 0; j < 2; ++j)
+                dst[j ^ ((lane >> 2) & 1)] = make_float4(l2[4 * j], l2[4 * j + 1], l2[4 * j + 2], l2[4 * j + 3]);
+            }
+            if (p.num_levels > 3) {  // 16 B per row, no swizzle
+              *reinterpret_cast<float4*>(set + EPI_L0 + EPI_L1 + EPI_L2 + lane * 16) =
+                  make_float4(l3[0], l3[1], l3[2], l3[3]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (store_lane) {
+              const int col = (g.n0 + ch * CHUNK) >> lane;  // first column of this chunk at my level
+              if (col < (p.W2 >> lane)) tma_store_3d(my_map, smem_u32(set) + my_level_off, col, mrow, g.row);
+              tma_store_commit();
+            }
+            chunk_parity ^= 1;
           }
-          if (p.scale_is_pow2) {  // x / 2^k == x * 2^-k exactly
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __fmul_rn(v[i], p.scale_inv);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __fdiv_rn(v[i], p.scale_div);
-          }
-
-          uint8_t* set = epi + chunk_parity * EPI_SET;
-          if (et == 0) tma_store_wait_read<1>();  // the store that last read this buffer set has drained
-          epi_bar_sync();
-          // level 0: 8 x 16-byte chunks per row, 128B swizzle (chunk ^= row & 7)
-          {
-            float4* dst = reinterpret_cast<float4*>(set + trow * 128);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j ^ (trow & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-          float l1[16], l2[8], l3[4];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) l1[i] = pool2(v[2 * i], v[2 * i + 1]);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) l2[i] = pool2(l1[2 * i], l1[2 * i + 1]);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) l3[i] = pool2(l2[2 * i], l2[2 * i + 1]);
-          if (p.num_levels > 1) {  // 64 B per row, 64B swizzle (chunk ^= (row >> 1) & 3)
-            float4* dst = reinterpret_cast<float4*>(set + EPI_L0 + trow * 64);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              dst[j ^ ((trow >> 1) & 3)] = make_float4(l1[4 * j], l1[4 * j + 1], l1[4 * j + 2], l1[4 * j + 3]);
-          }
-          if (p.num_levels > 2) {  // 32 B per row, 32B swizzle (chunk ^= (row >> 2) & 1)
-            float4* dst = reinterpret_cast<float4*>(set + EPI_L0 + EPI_L1 + trow * 32);
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-              dst[j ^ ((trow >> 2) & 1)] = make_float4(l2[4 * j], l2[4 * j + 1], l2[4 * j + 2], l2[4 * j + 3]);
-          }
-          if (p.num_levels > 3) {  // 16 B per row, no swizzle
-            *reinterpret_cast<float4*>(set + EPI_L0 + EPI_L1 + EPI_L2 + trow * 16) = make_float4(l3[0], l3[1], l3[2], l3[3]);
-          }
-          fence_proxy_async();
-          epi_bar_sync();
-          if (et == 0) {
-            const int col = n0 + ch * CHUNK;
-            const int mrow = m0 + mt * TILE_M;
-            const uint32_t s0 = smem_u32(set);
-            tma_store_3d(&map_l0, s0, col, mrow, row);
-            if (p.num_levels > 1 && (col >> 1) < (p.W2 >> 1)) tma_store_3d(&map_l1, s0 + EPI_L0, col >> 1, mrow, row);
-            if (p.num_levels > 2 && (col >> 2) < (p.W2 >> 2)) tma_store_3d(&map_l2, s0 + EPI_L0 + EPI_L1, col >> 2, mrow, row);
-            if (p.num_levels > 3 && (col >> 3) < (p.W2 >> 3))
-              tma_store_3d(&map_l3, s0 + EPI_L0 + EPI_L1 + EPI_L2, col >> 3, mrow, row);
-            tma_store_commit();
-          }
-          chunk_parity ^= 1;
         }
       }
-      acc_phase ^= 1;
     }
-    if (et == 0) tma_store_wait_all();
+    if (store_lane) tma_store_wait_all();
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
@@ -426,8 +534,8 @@ nnd_status corr1d_build_tf32(const float* fmap1, const float* fmap2, int B, int 
                              int num_levels, float* const* level, const int* pitch, cudaStream_t stream) {
   // TMA constraints: every global stride a multiple of 16 bytes, bases 16-byte aligned
   if (W1 % 4 != 0 || W2 % 4 != 0 || !aligned16(fmap1) || !aligned16(fmap2)) {
-    set_error("corr1d_build(tf32): TMA needs W1 and W2 to be multiples of 4 and 16-byte aligned feature maps "
-              "(W1=%d, W2=%d); use NND_PREC_FP32 for this shape", W1, W2);
+    set_error("corr1d_build(tf32): TMA needs W1 and W2 to be multiples of 4 and 16-byte aligned "
+              "feature maps (W1=%d, W2=%d); use NND_PREC_FP32 for this shape", W1, W2);
     return NND_ERR_UNSUPPORTED;
   }
   for (int l = 0; l < num_levels; ++l) {
@@ -441,26 +549,32 @@ nnd_status corr1d_build_tf32(const float* fmap1, const float* fmap2, int B, int 
   p.C = C; p.W1 = W1; p.W2 = W2; p.H = H;
   p.rows = B * H;
   p.num_levels = num_levels;
-  p.m_groups = (W1 + 2 * TILE_M - 1) / (2 * TILE_M);
   p.n_chunks = (W2 + MAX_N - 1) / MAX_N;
-  p.jobs = static_cast<long long>(p.rows) * p.m_groups * p.n_chunks;
+  p.m_passes = (W1 + MAX_M - 1) / MAX_M;
+  p.jobs = static_cast<long long>(p.rows) * p.n_chunks;
   p.scale_div = static_cast<float>(sqrt(static_cast<double>(C)));
   p.scale_inv = 1.0f / p.scale_div;
   {
     int e = 0;
     p.scale_is_pow2 = (frexpf(p.scale_div, &e) == 0.5f) ? 1 : 0;
   }
-  const int a_boxes = (min(W1, 2 * TILE_M) + BOX_W - 1) / BOX_W;
-  const int b_boxes = (min(W2, MAX_N) + BOX_W - 1) / BOX_W;
-  p.a_boxes_pad = (a_boxes + 3) & ~3;
-  p.stage_bytes = (p.a_boxes_pad + b_boxes) * BOX_BYTES;
-  const int budget = 227 * 1024 - 1024 /*alignment slack*/ - 2 * EPI_SET - 256 /*barriers*/;
+  p.a_region_boxes = (min(W1, MAX_M) + BOX_W - 1) / BOX_W;
+  p.b_region_boxes = (min(W2, MAX_N) + BOX_W - 1) / BOX_W;
+  // an M tile always reads four boxes: keep the boxes behind a short A region inside the allocation
+  const int a_tiles = (min(W1, MAX_M) + TILE_M - 1) / TILE_M;
+  p.stage_bytes = (p.a_region_boxes + p.b_region_boxes) * BOX_BYTES;
+  const int tail_boxes = 4 * a_tiles - p.a_region_boxes - p.b_region_boxes;  // > 0 only for tiny W2
+  const int budget = 227 * 1024 - 1024 /*alignment slack*/ - 2 * EPI_SET - 256 /*barriers*/ -
+                     (tail_boxes > 0 ? tail_boxes * BOX_BYTES : 0);
   p.stages = budget / p.stage_bytes;
-  if (p.stages > 6) p.stages = 6;
+  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   if (p.stages < 2) {
     set_error("corr1d_build(tf32): a pipeline stage of %d bytes leaves no room for double buffering", p.stage_bytes);
     return NND_ERR_UNSUPPORTED;
   }
+  const int acc_cols = a_tiles * p.b_region_boxes * BOX_W;  // TMEM columns one pass accumulates into
+  p.n_slots = 2 * acc_cols <= TMEM_COLS ? 2 : 1;
+  p.slot_cols = acc_cols;
   const size_t smem_bytes = 1024 + static_cast<size_t>(p.stages) * p.stage_bytes + 2 * EPI_SET + 256;
 
   alignas(64) CUtensorMap map_a, map_b, map_l[4];
@@ -487,7 +601,7 @@ nnd_status corr1d_build_tf32(const float* fmap1, const float* fmap2, int B, int 
     const cuuint64_t dims[3] = {static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(W1),
                                 static_cast<cuuint64_t>(p.rows)};
     const cuuint64_t str[2] = {static_cast<cuuint64_t>(pitch[ll]) * 4, static_cast<cuuint64_t>(W1) * pitch[ll] * 4};
-    const cuuint32_t box[3] = {static_cast<cuuint32_t>(CHUNK >> l), TILE_M, 1};
+    const cuuint32_t box[3] = {static_cast<cuuint32_t>(CHUNK >> l), 32, 1};
     nnd_status st = make_map(&map_l[l], level[ll], 3, dims, str, box, sw[l], "pyramid level");
     if (st != NND_OK) return st;
   }
@@ -497,7 +611,7 @@ nnd_status corr1d_build_tf32(const float* fmap1, const float* fmap2, int B, int 
                                          static_cast<int>(smem_bytes));
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(corr1d_build_tf32_kernel)");
   }
-  const long long sms = sm_count();
+  const long long sms = sm_count();  // persistent: one CTA per SM, rows dealt round-robin
   const unsigned grid = static_cast<unsigned>(p.jobs < sms ? p.jobs : sms);
   corr1d_build_tf32_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(map_a, map_b, map_l[0], map_l[1], map_l[2],
                                                                       map_l[3], p);

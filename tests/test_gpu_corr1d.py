@@ -241,9 +241,13 @@ def test_config2_full_size_properties():
         assert torch.equal(pyr[l + 1][:, 0], expect)
     # (3) linearity in fmap1: corr(a*f1 + g1, f2) == a*corr(f1,f2) + corr(g1,f2) up to fp32 rounding
     g1 = torch.randn_like(f1)
-    lhs = nb.CorrBlock1D.corr(2.0 * f1 + g1, f2)
-    rhs = 2.0 * pyr[0].reshape(B, H, W, W) + nb.CorrBlock1D.corr(g1, f2)
+    lhs = nb.CorrBlock1D.corr(2.0 * f1 + g1, f2, precision="fp32")
+    rhs = 2.0 * pyr[0].reshape(B, H, W, W) + nb.CorrBlock1D.corr(g1, f2, precision="fp32")
     assert (lhs - rhs).abs().max().item() <= 4 * VOLUME_RTOL * scale
+    # ... and on the tensor-core path (operands rounded to TF32) within the 1e-3 bar
+    lhs = nb.CorrBlock1D.corr(2.0 * f1 + g1, f2, precision="tf32")
+    rhs = 2.0 * nb.CorrBlock1D.corr(f1, f2, precision="tf32") + nb.CorrBlock1D.corr(g1, f2, precision="tf32")
+    assert (lhs - rhs).abs().max().item() <= 4 * TF32_RTOL * scale
     # (4) lookup at far out-of-range coordinates returns the clamped border columns of every level
     far = torch.full((B, 1, H, W), 1e6, device="cuda")
     out = blk(far)
@@ -307,7 +311,7 @@ def test_edge_cases_and_errors():
         ok(torch.zeros(1, 1, 3, 12, device="cuda"))
     # W1 != W2 is legal (rectangular volume)
     f2 = torch.randn(1, 8, 2, 20, device="cuda")
-    rect = nb.CorrBlock1D(f, f2, 2, 2)
+    rect = nb.CorrBlock1D(f, f2, 2, 2, precision="fp32")
     assert rect.corr_pyramid[0].shape == (24, 1, 20)
     ref = torch.einsum("bchi,bchj->bhij", f, f2) / 8 ** 0.5
     assert torch.allclose(rect.corr_pyramid[0].reshape(1, 2, 12, 20), ref, rtol=1e-5, atol=1e-5)
