@@ -55,6 +55,42 @@ def gather_disparities(local, world_size=None, group=None):
     return out
 
 
+def row_band(tensor, rank, world_size):
+    """Rows ``[h0, h1)`` of a ``(B, C, H, W)`` tensor owned by ``rank`` (contiguous copy) and the range.
+
+    The correlation path is independent per epipolar row: row ``h`` of the volume depends only on row
+    ``h`` of the two feature maps and a lookup only on row ``h`` of the coordinates (reference
+    ``raft_stereo/cost_volume.py:55-61,36-53``), so a single high-resolution pair is sharded across GPUs
+    by row bands with no halo and no collective in the data path (BASELINE config 5).
+    """
+    h0, h1 = shard_range(tensor.shape[2], rank, world_size)
+    return tensor[:, :, h0:h1].contiguous(), (h0, h1)
+
+
+def gather_row_bands(local, height, world_size=None, group=None):
+    """All-gather per-rank row bands ``(B, C, h_r, W)`` back into ``(B, C, height, W)``.
+
+    Bands differ by at most one row (``shard_range``); short bands are padded to the tallest one for
+    the fixed-size collective and trimmed afterwards.
+    """
+    import torch.distributed as dist
+    if world_size is None:
+        world_size = dist.get_world_size(group)
+    if world_size == 1:
+        return local
+    tallest = -(-int(height) // world_size)
+    B, C, h, W = local.shape
+    padded = local if h == tallest else F.pad(local, (0, 0, 0, tallest - h))
+    out = torch.empty((world_size * B, C, tallest, W), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, padded.contiguous(), group=group)
+    out = out.view(world_size, B, C, tallest, W)
+    bands = []
+    for r in range(world_size):
+        h0, h1 = shard_range(height, r, world_size)
+        bands.append(out[r, :, :, :h1 - h0])
+    return torch.cat(bands, dim=2)
+
+
 class StereoEngine:
     """Host-to-host stereo inference on one GPU with CUDA-graph replay.
 
