@@ -134,6 +134,20 @@ nnd_status nnd_agcl_offset(const float* fmap1, const float* fmap2, const float* 
 nnd_status nnd_agcl_iter(const float* fmap1, const float* fmap2, const float* flow, int N, int C, int H,
                          int W, int small_patch, float* out, nnd_stream_t stream);
 
+/* Channels-last fast path of AGCL (C % 16 == 0, C <= 512).  The maps of an AGCL object are fixed while
+ * it is called 6-12 times per cascade scale (cre_stereo/model.py:198-275), so the caller stages them
+ * once as (N,H,W,C) with nnd_nchw_to_nhwc and every call gathers whole channel vectors (one bilinear
+ * corner = C contiguous floats).  Same semantics, outputs and reference citations as the NCHW entry
+ * points above.  nnd_agcl_iter_nhwc needs a caller-provided workspace of N*H*W*C floats for the
+ * flow-warped right map (the tensor the reference materialises at cost_volume.py:57-59). */
+nnd_status nnd_nchw_to_nhwc(const float* src, int N, int C, int H, int W, float* dst, nnd_stream_t stream);
+nnd_status nnd_agcl_offset_nhwc(const float* fmap1_nhwc, const float* fmap2_nhwc, const float* flow,
+                                const float* extra_offset, int N, int C, int H, int W, int small_patch,
+                                float* out, nnd_stream_t stream);
+nnd_status nnd_agcl_iter_nhwc(const float* fmap1_nhwc, const float* fmap2_nhwc, const float* flow, int N,
+                              int C, int H, int W, int small_patch, float* warped_ws, float* out,
+                              nnd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,10 @@ The reference model names ``AGCL`` directly (``cre_stereo/model.py:198-200``), s
 patching that module attribute.  The optional LoFTR cross-attention (``att``) is dense attention and
 stays the caller's PyTorch module; it is a pure function of the two maps, so its output is computed
 once and cached instead of once per call (reference :91-99).
+
+Layout: the kernels gather whole channel vectors, so for ``C % 16 == 0`` (every model configuration) the
+two maps are staged ONCE per object as channels-last ``(N, H, W, C)`` copies (``nnd_nchw_to_nhwc``) and all
+6-12 calls of a cascade scale run on those; other channel counts take the generic NCHW kernels.
 """
 import torch
 
@@ -20,6 +24,27 @@ class AGCL:
             raise RuntimeError("fmap1 and fmap2 must be (N, C, H, W) of identical shape")
         self.att = att
         self._attended = None
+        self._staged = {}       # id(nchw tensor) -> (nchw tensor kept alive, channels-last copy)
+        self._warp_ws = None    # workspace of the flow-warped right map (iter mode)
+
+    @staticmethod
+    def _fast(C):
+        return C % 16 == 0 and C <= 512
+
+    def _nhwc(self, t):
+        """Channels-last staging copy of an ``(N, C, H, W)`` map, made once per tensor."""
+        hit = self._staged.get(id(t))
+        if hit is not None and hit[0] is t:
+            return hit[1]
+        N, C, H, W = t.shape
+        out = torch.empty(N, H, W, C, dtype=torch.float32, device=t.device)
+        with torch.cuda.device(t.device):
+            _lib.check(_lib.load().nnd_nchw_to_nhwc(_lib.ptr(t), N, C, H, W, _lib.ptr(out), _lib.stream_ptr(t)),
+                       "nnd_nchw_to_nhwc")
+        if len(self._staged) >= 4:          # fmap1, fmap2 and their attended versions; transient maps rotate out
+            self._staged.pop(next(iter(self._staged)))
+        self._staged[id(t)] = (t, out)
+        return out
 
     def __call__(self, flow, extra_offset, small_patch=False, iter_mode=False):
         if iter_mode:
@@ -34,11 +59,22 @@ class AGCL:
         return flow
 
     def corr_iter(self, left_feature, right_feature, flow, small_patch):
-        left = _lib.as_cuda_f32(left_feature, "left_feature")
-        right = _lib.as_cuda_f32(right_feature, "right_feature")
+        left = left_feature if left_feature is self.fmap1 else _lib.as_cuda_f32(left_feature, "left_feature")
+        right = right_feature if right_feature is self.fmap2 else _lib.as_cuda_f32(right_feature, "right_feature")
         N, C, H, W = left.shape
         flow = self._check_flow(flow, N, H, W)
         out = torch.empty(N, 36, H, W, dtype=torch.float32, device=left.device)
+        if self._fast(C) and H >= 2 and W >= 2:
+            if self._warp_ws is None or self._warp_ws.shape != (N, H, W, C) or self._warp_ws.device != left.device:
+                self._warp_ws = torch.empty(N, H, W, C, dtype=torch.float32, device=left.device)
+            with torch.cuda.device(left.device):
+                _lib.check(
+                    _lib.load().nnd_agcl_iter_nhwc(_lib.ptr(self._nhwc(left)), _lib.ptr(self._nhwc(right)),
+                                                   _lib.ptr(flow), N, C, H, W, 1 if small_patch else 0,
+                                                   _lib.ptr(self._warp_ws), _lib.ptr(out), _lib.stream_ptr(left)),
+                    "nnd_agcl_iter_nhwc",
+                )
+            return out
         with torch.cuda.device(left.device):
             _lib.check(
                 _lib.load().nnd_agcl_iter(_lib.ptr(left), _lib.ptr(right), _lib.ptr(flow), N, C, H, W,
@@ -69,6 +105,15 @@ class AGCL:
         if tuple(extra.shape) != (N, 18, H, W):
             raise RuntimeError(f"extra_offset must be (N, 18, H, W) = {(N, 18, H, W)}, got {tuple(extra.shape)}")
         out = torch.empty(N, 36, H, W, dtype=torch.float32, device=left.device)
+        if self._fast(C) and H >= 2 and W >= 2:
+            with torch.cuda.device(left.device):
+                _lib.check(
+                    _lib.load().nnd_agcl_offset_nhwc(_lib.ptr(self._nhwc(left)), _lib.ptr(self._nhwc(right)),
+                                                     _lib.ptr(flow), _lib.ptr(extra), N, C, H, W,
+                                                     1 if small_patch else 0, _lib.ptr(out), _lib.stream_ptr(left)),
+                    "nnd_agcl_offset_nhwc",
+                )
+            return out
         with torch.cuda.device(left.device):
             _lib.check(
                 _lib.load().nnd_agcl_offset(_lib.ptr(left), _lib.ptr(right), _lib.ptr(flow), _lib.ptr(extra), N, C, H,

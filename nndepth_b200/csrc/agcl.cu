@@ -236,6 +236,211 @@ agcl_iter_kernel(const float* __restrict__ L, const float* __restrict__ R, const
   }
 }
 
+// ================================================================================================
+// Channels-last fast path (C % 16 == 0).
+//
+// In NCHW one bilinear corner of one channel is a lone 4-byte gather; with a non-smooth flow a warp
+// of 32 pixels touches 32 sectors per corner per channel.  In channels-last (N,H,W,C) a corner is C
+// contiguous floats, so every fetched sector is fully used and the loads are 16 bytes per lane.
+// The maps are fixed for the life of an AGCL object (one per cascade scale, called 6-12 times), so the
+// caller transposes them once (nnd_nchw_to_nhwc) and every call runs on the staged copies.
+//
+// Work decomposition: one warp per pixel, lanes over channels.  Lane = (group gl = lane / 8, sub-lane
+// sl = lane % 8); the 8 sub-lanes of a group stride over that group's C/4 channels in float4 chunks,
+// so a warp load is four full 128-byte segments and the group dot product is an 8-lane butterfly.
+// A block is 8 warps x 4 pixels = 32 consecutive pixels; the 36 outputs per pixel are parked in
+// shared memory and leave as 128-byte coalesced channel-plane stores.
+// ================================================================================================
+constexpr int CL_WARPS = 8;
+constexpr int CL_PIX = 32;           // pixels per block
+constexpr int CL_MAX_CHUNKS = 4;     // float4 chunks per lane: C/4 groups of <= 8*4*4 = 128 channels -> C <= 512
+
+// (N,C,H,W) -> (N,H,W,C): 32(c) x 32(hw) tiles through padded shared memory, both sides coalesced.
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_kernel(const float* __restrict__ src, int C, long long hw, float* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const long long n = blockIdx.z;
+  const long long p0 = static_cast<long long>(blockIdx.x) * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i;
+    const long long p = p0 + tx;
+    tile[ty + 8 * i][tx] = (c < C && p < hw) ? __ldg(src + (n * C + c) * hw + p) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long p = p0 + ty + 8 * i;
+    const int c = c0 + tx;
+    if (c < C && p < hw) dst[(n * hw + p) * C + c] = tile[tx][ty + 8 * i];
+  }
+}
+
+struct WarpFootprint {  // one tap's bilinear footprint, broadcast to the warp through shared memory
+  int off[4];
+  float wt[4];
+};
+
+__device__ __forceinline__ float4 ld4_or_zero(const float* __restrict__ base, int pix_off, int C, int ch) {
+  // pix_off: pixel index inside the image (y*W + x) or -1 for an out-of-image corner
+  return pix_off >= 0 ? ldg_f4(base + static_cast<long long>(pix_off) * C + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// wa*a + wb*b + wc*c + wd*d per component (utils.py:107)
+__device__ __forceinline__ float4 blend4(const float4 v[4], const float w[4]) {
+  float4 r;
+  r.x = fmaf(v[3].x, w[3], fmaf(v[2].x, w[2], fmaf(v[1].x, w[1], v[0].x * w[0])));
+  r.y = fmaf(v[3].y, w[3], fmaf(v[2].y, w[2], fmaf(v[1].y, w[1], v[0].y * w[0])));
+  r.z = fmaf(v[3].z, w[3], fmaf(v[2].z, w[2], fmaf(v[1].z, w[1], v[0].z * w[0])));
+  r.w = fmaf(v[3].w, w[3], fmaf(v[2].w, w[2], fmaf(v[1].w, w[1], v[0].w * w[0])));
+  return r;
+}
+
+__device__ __forceinline__ float dot4(float4 a, float4 b, float acc) {
+  return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, fmaf(a.x, b.x, acc))));
+}
+
+__device__ __forceinline__ float group_reduce8(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
+}
+
+// coalesced write-out of the block's [36][CL_PIX] result tile
+__device__ __forceinline__ void store_result_tile(const float (*res)[CL_PIX + 1], long long pix0, long long n_pix,
+                                                  long long hw, float* __restrict__ out) {
+  const int px = threadIdx.x & 31;
+  const long long pix = pix0 + px;
+  if (pix >= n_pix) return;
+  const long long n = pix / hw, p = pix - n * hw;
+  float* op = out + n * AGCL_GROUPS * AGCL_TAPS * hw + p;
+  for (int ch = threadIdx.x >> 5; ch < AGCL_GROUPS * AGCL_TAPS; ch += CL_WARPS) op[ch * hw] = res[ch][px];
+}
+
+// MODE 0: offset mode (deformable taps, zero-padded bilinear on R)
+// MODE 1: iter-mode pass 2 (R = flow-warped map; integer taps, replicate clamp)
+template <int MODE>
+__global__ void __launch_bounds__(32 * CL_WARPS)
+agcl_cl_kernel(const float* __restrict__ L, const float* __restrict__ R, const float* __restrict__ flow,
+               const float* __restrict__ extra, int C, int H, int W, long long n_pix, int small_patch,
+               float* __restrict__ out) {
+  __shared__ WarpFootprint fp[CL_WARPS][AGCL_TAPS];
+  __shared__ float res[AGCL_GROUPS * AGCL_TAPS][CL_PIX + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gl = lane >> 3, sl = lane & 7;
+  const int cg = C / AGCL_GROUPS;
+  const int n_chunks = (cg / 4 + 7) / 8;  // float4 chunks per lane
+  const long long hw = static_cast<long long>(H) * W;
+  const long long pix0 = static_cast<long long>(blockIdx.x) * CL_PIX;
+  const float inv_cnt_div = static_cast<float>(cg);
+
+  for (int i = 0; i < CL_PIX / CL_WARPS; ++i) {
+    const int slot = warp * (CL_PIX / CL_WARPS) + i;
+    const long long pix = pix0 + slot;
+    if (pix >= n_pix) break;  // warp-uniform
+    const long long n = pix / hw;
+    const int p = static_cast<int>(pix - n * hw);
+    const int y = p / W, x = p - y * W;
+
+    // taps: lane k < 9 prepares tap k, then everybody reads it back
+    if (lane < AGCL_TAPS) {
+      int dx, dy;
+      tap_delta(lane, small_patch != 0, dx, dy);
+      WarpFootprint f;
+      if (MODE == 0) {
+        const float* fl = flow + n * 2 * hw + p;
+        const float* ex = extra + (n * 2 * AGCL_TAPS + 2 * lane) * hw + p;
+        // (grid + flow) + (d_k + extra_k), in that association order (cost_volume.py:133-137)
+        const float px = __fadd_rn(__fadd_rn(static_cast<float>(x), __ldg(fl)),
+                                   __fadd_rn(static_cast<float>(dx), __ldg(ex)));
+        const float py = __fadd_rn(__fadd_rn(static_cast<float>(y), __ldg(fl + hw)),
+                                   __fadd_rn(static_cast<float>(dy), __ldg(ex + hw)));
+        const Footprint ff = make_footprint(px, py, H, W);
+        // an out-of-image corner contributes exactly zero (zero padding): give it weight 0 and point it at
+        // pixel 0, so the channel loop is predicate-free (float offsets from the image base)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          f.off[q] = ff.off[q] >= 0 ? ff.off[q] * C : 0;
+          f.wt[q] = ff.off[q] >= 0 ? ff.wt[q] : 0.f;
+        }
+      } else {
+        // replicate padding of the warped map (cost_volume.py:40, utils.py:29-31): clamp the tap into the image
+        const int xx = min(max(x + dx, 0), W - 1), yy = min(max(y + dy, 0), H - 1);
+        f.off[0] = (yy * W + xx) * C;
+        f.off[1] = f.off[2] = f.off[3] = 0;
+        f.wt[0] = 1.f;
+        f.wt[1] = f.wt[2] = f.wt[3] = 0.f;
+      }
+      fp[warp][lane] = f;
+    }
+    __syncwarp();
+
+    const float* lp = L + (n * hw + p) * C + gl * cg + 4 * sl;
+    const float* rb = R + n * hw * C + gl * cg + 4 * sl;
+    float4 lv[CL_MAX_CHUNKS];
+#pragma unroll
+    for (int j = 0; j < CL_MAX_CHUNKS; ++j)
+      lv[j] = (j < n_chunks && 4 * (sl + 8 * j) < cg) ? ldg_f4(lp + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+
+#pragma unroll 3
+    for (int k = 0; k < AGCL_TAPS; ++k) {
+      const WarpFootprint f = fp[warp][k];
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < CL_MAX_CHUNKS; ++j) {
+        if (j < n_chunks && 4 * (sl + 8 * j) < cg) {
+          if (MODE == 0) {
+            float4 v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] = ldg_f4(rb + f.off[q] + 32 * j);
+            acc = dot4(lv[j], blend4(v, f.wt), acc);
+          } else {
+            acc = dot4(lv[j], ldg_f4(rb + f.off[0] + 32 * j), acc);
+          }
+        }
+      }
+      acc = group_reduce8(acc);
+      if (sl == 0) res[gl * AGCL_TAPS + k][slot] = __fdiv_rn(acc, inv_cnt_div);  // torch.mean over C/4
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  store_result_tile(res, pix0, n_pix, hw, out);
+}
+
+// iter-mode pass 1: Rw[n,p,:] = zero-padded bilinear sample of R at p + flow(p), channels-last in and out
+__global__ void __launch_bounds__(32 * CL_WARPS)
+agcl_warp_cl_kernel(const float* __restrict__ R, const float* __restrict__ flow, int C, int H, int W, long long n_pix,
+                    float* __restrict__ Rw) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long hw = static_cast<long long>(H) * W;
+  const long long pix = static_cast<long long>(blockIdx.x) * CL_WARPS + warp;
+  if (pix >= n_pix) return;
+  const long long n = pix / hw;
+  const int p = static_cast<int>(pix - n * hw);
+  const int y = p / W, x = p - y * W;
+  const float* fl = flow + n * 2 * hw + p;
+  const Footprint f = make_footprint(__fadd_rn(static_cast<float>(x), __ldg(fl)),
+                                     __fadd_rn(static_cast<float>(y), __ldg(fl + hw)), H, W);
+  const float* rb = R + n * hw * C;
+  float* dst = Rw + pix * C;
+  for (int ch = 4 * lane; ch < C; ch += 128) {
+    float4 v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = ld4_or_zero(rb, f.off[q], C, ch);
+    // Ia*wa + Ib*wb + Ic*wc + Id*wd, left to right, every step rounded (utils.py:107): the warped map is
+    // an intermediate the reference materialises, so it is reproduced bit for bit
+    float4 r;
+    const float vx[4] = {v[0].x, v[1].x, v[2].x, v[3].x}, vy[4] = {v[0].y, v[1].y, v[2].y, v[3].y};
+    const float vz[4] = {v[0].z, v[1].z, v[2].z, v[3].z}, vw[4] = {v[0].w, v[1].w, v[2].w, v[3].w};
+    r.x = blend(vx, f.wt); r.y = blend(vy, f.wt); r.z = blend(vz, f.wt); r.w = blend(vw, f.wt);
+    *reinterpret_cast<float4*>(dst + ch) = r;
+  }
+}
+
 static nnd_status check_agcl(const float* f1, const float* f2, const float* flow, const float* out, int N, int C,
                              int H, int W, const char* who) {
   NND_REQUIRE(f1 && f2 && flow && out, "%s: null pointer argument", who);
@@ -283,6 +488,68 @@ nnd_status nnd_agcl_iter(const float* fmap1, const float* fmap2, const float* fl
     agcl_iter_kernel<false><<<grid, 256, 0, stream>>>(fmap1, fmap2, flow, C, H, W, out);
   }
   return check_launch("agcl_iter_kernel");
+}
+
+nnd_status nnd_nchw_to_nhwc(const float* src, int N, int C, int H, int W, float* dst, nnd_stream_t stream) {
+  using namespace nnd;
+  NND_REQUIRE(src && dst, "nchw_to_nhwc: null pointer");
+  NND_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0, "nchw_to_nhwc: N, C, H, W must be positive");
+  NND_REQUIRE(N <= 65535 && (C + 31) / 32 <= 65535, "nchw_to_nhwc: N or C exceeds the grid limit");
+  const long long hw = static_cast<long long>(H) * W;
+  dim3 grid(static_cast<unsigned>((hw + 31) / 32), (C + 31) / 32, N);
+  nchw_to_nhwc_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, C, hw, dst);
+  return check_launch("nchw_to_nhwc_kernel");
+}
+
+static nnd_status check_agcl_cl(int C, int H, int W, const char* who) {
+  using namespace nnd;
+  NND_REQUIRE(C % 16 == 0, "%s: the channels-last path needs C %% 16 == 0 (got %d); use the NCHW entry point", who, C);
+  NND_REQUIRE(C <= 4 * 8 * 4 * CL_MAX_CHUNKS, "%s: C = %d exceeds the channels-last path's limit (%d)", who, C,
+              4 * 8 * 4 * CL_MAX_CHUNKS);
+  NND_REQUIRE(static_cast<long long>(H) * W * C < (1LL << 31), "%s: one image of the map exceeds 2^31 floats", who);
+  return NND_OK;
+}
+
+nnd_status nnd_agcl_offset_nhwc(const float* fmap1_nhwc, const float* fmap2_nhwc, const float* flow,
+                                const float* extra_offset, int N, int C, int H, int W, int small_patch, float* out,
+                                nnd_stream_t stream) {
+  using namespace nnd;
+  nnd_status st = check_agcl(fmap1_nhwc, fmap2_nhwc, flow, out, N, C, H, W, "agcl_offset_nhwc");
+  if (st != NND_OK) return st;
+  st = check_agcl_cl(C, H, W, "agcl_offset_nhwc");
+  if (st != NND_OK) return st;
+  NND_REQUIRE(extra_offset, "agcl_offset_nhwc: extra_offset is null");
+  NND_REQUIRE(aligned16(fmap1_nhwc) && aligned16(fmap2_nhwc), "agcl_offset_nhwc: maps must be 16-byte aligned");
+  const long long n_pix = static_cast<long long>(N) * H * W;
+  const long long blocks = (n_pix + CL_PIX - 1) / CL_PIX;
+  NND_REQUIRE(blocks <= 0x7fffffffLL, "agcl_offset_nhwc: too many pixels");
+  agcl_cl_kernel<0><<<static_cast<unsigned>(blocks), 32 * CL_WARPS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      fmap1_nhwc, fmap2_nhwc, flow, extra_offset, C, H, W, n_pix, small_patch ? 1 : 0, out);
+  return check_launch("agcl_cl_kernel<offset>");
+}
+
+nnd_status nnd_agcl_iter_nhwc(const float* fmap1_nhwc, const float* fmap2_nhwc, const float* flow, int N, int C,
+                              int H, int W, int small_patch, float* warped_ws, float* out, nnd_stream_t stream_) {
+  using namespace nnd;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  nnd_status st = check_agcl(fmap1_nhwc, fmap2_nhwc, flow, out, N, C, H, W, "agcl_iter_nhwc");
+  if (st != NND_OK) return st;
+  st = check_agcl_cl(C, H, W, "agcl_iter_nhwc");
+  if (st != NND_OK) return st;
+  NND_REQUIRE(warped_ws, "agcl_iter_nhwc: the N*H*W*C workspace for the warped right map is null");
+  NND_REQUIRE(aligned16(fmap1_nhwc) && aligned16(fmap2_nhwc) && aligned16(warped_ws),
+              "agcl_iter_nhwc: maps and workspace must be 16-byte aligned");
+  const long long n_pix = static_cast<long long>(N) * H * W;
+  const long long wblocks = (n_pix + CL_WARPS - 1) / CL_WARPS;
+  const long long blocks = (n_pix + CL_PIX - 1) / CL_PIX;
+  NND_REQUIRE(wblocks <= 0x7fffffffLL, "agcl_iter_nhwc: too many pixels");
+  agcl_warp_cl_kernel<<<static_cast<unsigned>(wblocks), 32 * CL_WARPS, 0, stream>>>(fmap2_nhwc, flow, C, H, W, n_pix,
+                                                                                    warped_ws);
+  st = check_launch("agcl_warp_cl_kernel");
+  if (st != NND_OK) return st;
+  agcl_cl_kernel<1><<<static_cast<unsigned>(blocks), 32 * CL_WARPS, 0, stream>>>(fmap1_nhwc, warped_ws, flow, nullptr, C,
+                                                                                H, W, n_pix, small_patch ? 1 : 0, out);
+  return check_launch("agcl_cl_kernel<iter>");
 }
 
 }  // extern "C"

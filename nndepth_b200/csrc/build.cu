@@ -117,14 +117,22 @@ corr1d_build_fp32_kernel(const float* __restrict__ f1, const float* __restrict__
 
 // ------------------------------------------------------------------------------------------------
 // Group-wise build with a tiny contraction (K = group_size, 8 for IGEV / 4 for GroupCorrBlock1D):
-// 2 flop per output byte, i.e. purely write-bandwidth bound.  One block per (b, g, h): the two
-// K x W operand strips are staged once in shared memory; each warp then sweeps volume rows, lane i
-// producing columns 4i..4i+3 (+128, ...) so a warp store covers 512 contiguous bytes.
+// 2 flop per output byte, i.e. purely write-bandwidth bound -- provided the instruction stream keeps
+// up (at 22 B/clk/SM of stores the budget is ~60 instructions per 16 output bytes).  One block per
+// (b, g, h): the two K x W operand strips are staged once in shared memory.  A warp is 4 row-lanes x
+// 8 column-lanes and owns groups of 16 volume rows: a thread keeps a[4 rows][K] in registers for the
+// whole group and sweeps the row in 32-column steps, so every B value is loaded once per four outputs
+// and a warp store covers four full 128-byte row segments.  The pooled levels come out of the same
+// registers (levels 1-2 in-thread, level 3 with one shuffle).
 // ------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int gc_rows_per_thread(int k) { return k <= 8 ? 4 : k == 16 ? 2 : 1; }  // a[TR][K] must stay in registers
+
 template <int K>
 __global__ void __launch_bounds__(256)
 groupcorr_build_kernel(const float* __restrict__ f1, const float* __restrict__ f2, int C, int G, int H, int W1,
-                       int W2, float scale_div, int num_levels, Pyramid pyr, int vec_ok) {
+                       int W2, float scale_div, float scale_rcp, int num_levels, Pyramid pyr, int vec_ok) {
+  constexpr int GC_TR = gc_rows_per_thread(K);
+  constexpr int GC_ROWS = 4 * GC_TR;  // rows per warp group
   extern __shared__ __align__(16) float smem[];
   const int W2p = (W2 + 3) & ~3;
   float* As = smem;             // [K][W1]
@@ -151,31 +159,69 @@ groupcorr_build_kernel(const float* __restrict__ f1, const float* __restrict__ f
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int n_warps = blockDim.x >> 5;
-  const int n_chunks = (W2p + 127) / 128;  // 128 columns per warp sweep
-  for (int m = warp; m < W1; m += n_warps) {
-    float a[K];
+  const int rl = lane >> 3;   // row-lane 0..3
+  const int cl = lane & 7;    // column-lane 0..7: columns 4*cl .. 4*cl+3 of a 32-column sweep
+  const int n_groups = (W1 + GC_ROWS - 1) / GC_ROWS;
+  const int n_sweeps = (W2p + 31) / 32;
+  const bool fast = vec_ok != 0 && (W2 & 7) == 0 && num_levels <= 4;  // every level's quad lies fully inside its row
+
+  for (int grp = warp; grp < n_groups; grp += n_warps) {
+    float a[GC_TR][K];
+    int row_m[GC_TR];
 #pragma unroll
-    for (int k = 0; k < K; ++k) a[k] = As[k * W1 + m];
-    const long long row = bgh * W1 + m;
-    for (int ch = 0; ch < n_chunks; ++ch) {
-      const int n0 = ch * 128 + 4 * lane;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < GC_TR; ++i) {
+      row_m[i] = grp * GC_ROWS + rl + 4 * i;
+      const int mm = min(row_m[i], W1 - 1);
+#pragma unroll
+      for (int k = 0; k < K; ++k) a[i][k] = As[k * W1 + mm];
+    }
+    for (int sw = 0; sw < n_sweeps; ++sw) {
+      const int n0 = sw * 32 + 4 * cl;
+      float4 acc[GC_TR];
+#pragma unroll
+      for (int i = 0; i < GC_TR; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (n0 < W2p) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
           const float4 bv = *reinterpret_cast<const float4*>(Bs + k * W2p + n0);
-          acc.x = fmaf(a[k], bv.x, acc.x);
-          acc.y = fmaf(a[k], bv.y, acc.y);
-          acc.z = fmaf(a[k], bv.z, acc.z);
-          acc.w = fmaf(a[k], bv.w, acc.w);
+#pragma unroll
+          for (int i = 0; i < GC_TR; ++i) {
+            acc[i].x = fmaf(a[i][k], bv.x, acc[i].x);
+            acc[i].y = fmaf(a[i][k], bv.y, acc[i].y);
+            acc[i].z = fmaf(a[i][k], bv.z, acc[i].z);
+            acc[i].w = fmaf(a[i][k], bv.w, acc[i].w);
+          }
         }
       }
-      float4 v;
-      v.x = __fdiv_rn(acc.x, scale_div);
-      v.y = __fdiv_rn(acc.y, scale_div);
-      v.z = __fdiv_rn(acc.z, scale_div);
-      v.w = __fdiv_rn(acc.w, scale_div);
-      store_row_quad(pyr, num_levels, row, n0, v, vec_ok != 0);
+#pragma unroll
+      for (int i = 0; i < GC_TR; ++i) {
+        float4 v;
+        v.x = div_rn_fast(acc[i].x, scale_div, scale_rcp);
+        v.y = div_rn_fast(acc[i].y, scale_div, scale_rcp);
+        v.z = div_rn_fast(acc[i].z, scale_div, scale_rcp);
+        v.w = div_rn_fast(acc[i].w, scale_div, scale_rcp);
+        const bool row_ok = row_m[i] < W1;
+        const long long row = bgh * W1 + min(row_m[i], W1 - 1);
+        if (fast) {
+          // W2 % 8 == 0: a quad inside level 0 has its pooled pair / single / shuffle partner inside too
+          const bool ok = row_ok && n0 < W2;
+          if (ok) *reinterpret_cast<float4*>(pyr.ptr[0] + row * pyr.pitch[0] + n0) = v;
+          if (num_levels > 1) {
+            const float l1a = pool2(v.x, v.y), l1b = pool2(v.z, v.w);
+            if (ok) *reinterpret_cast<float2*>(pyr.ptr[1] + row * pyr.pitch[1] + (n0 >> 1)) = make_float2(l1a, l1b);
+            if (num_levels > 2) {
+              const float l2 = pool2(l1a, l1b);
+              if (ok) pyr.ptr[2][row * pyr.pitch[2] + (n0 >> 2)] = l2;
+              if (num_levels > 3) {
+                const float other = __shfl_xor_sync(0xffffffffu, l2, 1);
+                if (ok && (cl & 1) == 0) pyr.ptr[3][row * pyr.pitch[3] + (n0 >> 3)] = pool2(l2, other);
+              }
+            }
+          }
+        } else {
+          store_row_quad(pyr, num_levels, row, n0, v, vec_ok != 0, row_ok);
+        }
+      }
     }
   }
 }
@@ -282,13 +328,25 @@ nnd_status nnd_groupcorr_build(const float* fmap1, const float* fmap2, int B, in
   const int W2p = (W2 + 3) & ~3;
   const size_t smem = static_cast<size_t>(group_size) * (W1 + W2p) * sizeof(float);
   NND_REQUIRE(smem <= 200 * 1024, "groupcorr_build: strips of %zu bytes do not fit shared memory", smem);
+  // warps per block: the count in [4, 8] that divides the 16-row groups of a volume slab most evenly
+  int gc_warps = 8;
+  {
+    const int group_rows = 4 * gc_rows_per_thread(group_size);
+    const int n_groups = (W1 + group_rows - 1) / group_rows;
+    double best = -1.0;
+    for (int w = 8; w >= 4; --w) {
+      const int rounds = (n_groups + w - 1) / w;
+      const double eff = static_cast<double>(n_groups) / (rounds * w);
+      if (eff > best + 1e-9) { best = eff; gc_warps = w; }
+    }
+  }
 #define NND_LAUNCH_GROUP(KK)                                                                                      \
   do {                                                                                                            \
     if (smem > 48 * 1024)                                                                                         \
       cudaFuncSetAttribute(groupcorr_build_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
                            static_cast<int>(smem));                                                               \
-    groupcorr_build_kernel<KK><<<static_cast<unsigned>(blocks), 256, smem, stream>>>(                             \
-        fmap1, fmap2, C, num_groups, H, W1, W2, scale_div, num_levels, pyr, vec_ok ? 1 : 0);                      \
+    groupcorr_build_kernel<KK><<<static_cast<unsigned>(blocks), 32 * gc_warps, smem, stream>>>(                   \
+        fmap1, fmap2, C, num_groups, H, W1, W2, scale_div, 1.0f / scale_div, num_levels, pyr, vec_ok ? 1 : 0);    \
   } while (0)
   switch (group_size) {
     case 1: NND_LAUNCH_GROUP(1); break;

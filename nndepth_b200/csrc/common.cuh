@@ -60,6 +60,16 @@ __device__ __forceinline__ float sampler_lerp(float t, float i1f, float v0, floa
 // (a + b) / 2 as avg_pool1d(.,2) computes it (sum, then divide by the window size).
 __device__ __forceinline__ float pool2(float a, float b) { return __fmul_rn(__fadd_rn(a, b), 0.5f); }
 
+// x / d, correctly rounded, in three instructions (Markstein): q = RN(x*r), e = x - q*d (exact, FMA),
+// q' = RN(q + e*r) with r = RN(1/d).  Exact whenever the residual neither under- nor overflows and r is
+// not the all-ones-significand exception -- true for the scale divisors (sqrt of small integers) and the
+// volume magnitudes here; differs from IEEE division by at most 1 ulp otherwise.
+__device__ __forceinline__ float div_rn_fast(float x, float d, float r) {
+  const float q = __fmul_rn(x, r);
+  const float e = __fmaf_rn(-q, d, x);
+  return __fmaf_rn(e, r, q);
+}
+
 __device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 // ---- shared epilogue: 4 consecutive columns n0..n0+3 of one volume row -> levels 0..min(L,4)-1 ----

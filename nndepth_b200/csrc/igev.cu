@@ -58,28 +58,41 @@ geo_transpose_pool_kernel(const float* __restrict__ geo, int D, int H, int W1, i
 // ------------------------------------------------------------------------------------------------
 // Soft-argmin: out[b,0,h,w] = -sum_d d * softmax_d(z[b,d,h,w]) in ONE pass over z (online softmax).
 // z is (B,D,H,W): the softmax axis is strided by H*W, consecutive pixels are contiguous.  A block is
-// 32 pixels x SA_SLICES disparity slices: each warp streams its slice with 128-byte loads (4 in
-// flight per lane), keeping a running (max, sum, weighted sum); the slices are merged through shared
-// memory.  197.8 MB in, 1.2 MB out at the IGEV configuration -- pure HBM streaming.
+// 32 lanes x S disparity slices; a lane owns VEC consecutive pixels (one 16-byte load per disparity
+// when H*W % 4 == 0), warp `s` streams disparities s, s+S, ... with eight loads in flight per lane and
+// keeps a running (max, sum, weighted sum) per pixel; the slices are merged through shared memory.
+// 197.8 MB in, 1.2 MB out at the IGEV configuration -- pure HBM streaming.  With enough pixels S = 1:
+// every warp is its own block, all of them are resident at once and do equal work, so there is no wave
+// quantisation and no merge; small problems slice the disparity axis to fill the machine.
 // ------------------------------------------------------------------------------------------------
-constexpr int SA_SLICES = 8;
+constexpr int SA_MAX_SLICES = 8;
 constexpr float LOG2E = 1.4426950408889634f;
 
 struct SoftState {
-  float m, s, ws;  // running max, sum of exp(z - m), sum of d * exp(z - m)
+  float m, s, ws;  // running max (times log2e), sum of exp(z - max), sum of d * exp(z - max)
 };
 
-__device__ __forceinline__ void soft_push4(SoftState& st, const float z[4], int d0, int step, int n_valid) {
+__device__ __forceinline__ float ex2_fast(float x) {  // 2**x, MUFU.EX2 (2 ulp), flushes denormal results to zero
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Online softmax-expectation over NV more disparities d0, d0+step, ...: one rescale of the running sums
+// per call, then exp2(z*log2e - max*log2e) as a single FFMA + MUFU per element.  st.m is kept in the
+// log2 domain (max(z) * log2e) so the subtraction folds into the FFMA.
+template <int NV>
+__device__ __forceinline__ void soft_push(SoftState& st, const float (&z)[NV], int d0, int step, int n_valid) {
   float mx = st.m;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-    if (i < n_valid) mx = fmaxf(mx, z[i]);
-  const float resc = exp2f((st.m - mx) * LOG2E);
+  for (int i = 0; i < NV; ++i)
+    if (i < n_valid) mx = fmaxf(mx, z[i] * LOG2E);
+  const float resc = ex2_fast(st.m - mx);
   float s = st.s * resc, ws = st.ws * resc;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < NV; ++i) {
     if (i < n_valid) {
-      const float e = exp2f((z[i] - mx) * LOG2E);
+      const float e = ex2_fast(fmaf(z[i], LOG2E, -mx));
       s += e;
       ws = fmaf(static_cast<float>(d0 + i * step), e, ws);
     }
@@ -89,49 +102,88 @@ __device__ __forceinline__ void soft_push4(SoftState& st, const float z[4], int 
   st.ws = ws;
 }
 
-__global__ void __launch_bounds__(32 * SA_SLICES)
-soft_argmin_kernel(const float* __restrict__ z, int D, long long hw, float* __restrict__ out) {
-  __shared__ SoftState part[SA_SLICES][32];
-  const int lane = threadIdx.x, slice = threadIdx.y;
+template <int VEC>
+struct SoftVec;
+template <>
+struct SoftVec<1> {
+  using type = float;
+  static __device__ __forceinline__ void unpack(float v, float (&o)[1]) { o[0] = v; }
+  static __device__ __forceinline__ float pack(const float (&o)[1]) { return o[0]; }
+};
+template <>
+struct SoftVec<4> {
+  using type = float4;
+  static __device__ __forceinline__ void unpack(float4 v, float (&o)[4]) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+  static __device__ __forceinline__ float4 pack(const float (&o)[4]) { return make_float4(o[0], o[1], o[2], o[3]); }
+};
+
+// hwv = H*W / VEC pixel groups per image; blockDim = (32, S)
+template <int VEC>
+__global__ void __launch_bounds__(32 * SA_MAX_SLICES)
+soft_argmin_kernel(const float* __restrict__ z, int D, long long hwv, float* __restrict__ out) {
+  using V = typename SoftVec<VEC>::type;
+  extern __shared__ SoftState part[];  // [S][32][VEC]
+  const int lane = threadIdx.x, slice = threadIdx.y, S = blockDim.y;
   const long long p = static_cast<long long>(blockIdx.x) * 32 + lane;
   const long long b = blockIdx.y;
-  const bool valid = p < hw;
-  const float* src = z + b * D * hw + (valid ? p : 0);
+  const bool valid = p < hwv;
+  const V* src = reinterpret_cast<const V*>(z) + b * D * hwv + (valid ? p : 0);
 
-  SoftState st;
-  st.m = -FLT_MAX;
-  st.s = 0.f;
-  st.ws = 0.f;
-  // disparities slice, slice + S, slice + 2S, ... ; four loads in flight per lane
-  for (int d = slice; d < D; d += 4 * SA_SLICES) {
-    float v[4];
+  SoftState st[VEC];
+#pragma unroll
+  for (int c = 0; c < VEC; ++c) {
+    st[c].m = -FLT_MAX;
+    st[c].s = 0.f;
+    st[c].ws = 0.f;
+  }
+  // disparities slice, slice + S, slice + 2S, ... ; eight loads in flight per lane
+  for (int d = slice; d < D; d += 8 * S) {
+    float v[8][VEC];
     int n_valid = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int di = d + i * SA_SLICES;
-      v[i] = 0.f;
-      if (di < D) {
-        v[i] = __ldcs(src + di * hw);
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) v[i][c] = 0.f;
+      if (d + i * S < D) {
+        SoftVec<VEC>::unpack(__ldcs(src + (d + i * S) * hwv), v[i]);
         n_valid = i + 1;
       }
     }
-    soft_push4(st, v, d, SA_SLICES, n_valid);
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) {
+      const float zc[8] = {v[0][c], v[1][c], v[2][c], v[3][c], v[4][c], v[5][c], v[6][c], v[7][c]};
+      soft_push<8>(st[c], zc, d, S, n_valid);
+    }
   }
-  part[slice][lane] = st;
+#pragma unroll
+  for (int c = 0; c < VEC; ++c) part[(slice * 32 + lane) * VEC + c] = st[c];
   __syncthreads();
   if (slice == 0 && valid) {
-    float mx = part[0][lane].m;
+    float res[VEC];
 #pragma unroll
-    for (int i = 1; i < SA_SLICES; ++i) mx = fmaxf(mx, part[i][lane].m);
-    float s = 0.f, ws = 0.f;
-#pragma unroll
-    for (int i = 0; i < SA_SLICES; ++i) {
-      const float resc = exp2f((part[i][lane].m - mx) * LOG2E);
-      s = fmaf(part[i][lane].s, resc, s);
-      ws = fmaf(part[i][lane].ws, resc, ws);
+    for (int c = 0; c < VEC; ++c) {
+      float mx = -FLT_MAX;
+      for (int i = 0; i < S; ++i) mx = fmaxf(mx, part[(i * 32 + lane) * VEC + c].m);
+      float s = 0.f, ws = 0.f;
+      for (int i = 0; i < S; ++i) {
+        const SoftState q = part[(i * 32 + lane) * VEC + c];
+        const float resc = ex2_fast(q.m - mx);  // m is already in the log2 domain
+        s = fmaf(q.s, resc, s);
+        ws = fmaf(q.ws, resc, ws);
+      }
+      res[c] = -(ws / s);
     }
-    out[b * hw + p] = -(ws / s);
+    reinterpret_cast<V*>(out)[b * hwv + p] = SoftVec<VEC>::pack(res);
   }
+}
+
+// slices per block: 1 when one warp per 32 pixel groups already fills the machine (>= 12 warps per SM),
+// otherwise enough disparity slices to get there (merge cost grows with S, so at most 8).
+static int soft_argmin_slices(long long units, int D) {
+  const long long want = static_cast<long long>(sm_count()) * 12;
+  int S = 1;
+  while (S < 8 && units * S < want && 2 * S <= D) S *= 2;
+  return S;
 }
 
 }  // namespace nnd
@@ -166,9 +218,20 @@ nnd_status nnd_soft_argmin(const float* z, int B, int D, int H, int W, float* ou
   NND_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "soft_argmin: B, D, H, W must be positive");
   NND_REQUIRE(B <= 65535, "soft_argmin: batch %d exceeds grid limit", B);
   const long long hw = static_cast<long long>(H) * W;
-  dim3 grid(static_cast<unsigned>((hw + 31) / 32), B);
-  dim3 block(32, SA_SLICES);
-  soft_argmin_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(z, D, hw, out);
+  const bool vec4 = hw % 4 == 0 && aligned16(z) && aligned16(out);
+  const long long hwv = vec4 ? hw / 4 : hw;
+  const long long gx = (hwv + 31) / 32;
+  NND_REQUIRE(gx <= 0x7fffffffLL, "soft_argmin: H*W too large");
+  const int S = soft_argmin_slices(gx * B, D);
+  dim3 grid(static_cast<unsigned>(gx), B);
+  dim3 block(32, S);
+  const size_t smem = static_cast<size_t>(S) * 32 * (vec4 ? 4 : 1) * sizeof(SoftState);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (vec4) {
+    soft_argmin_kernel<4><<<grid, block, smem, st>>>(z, D, hwv, out);
+  } else {
+    soft_argmin_kernel<1><<<grid, block, smem, st>>>(z, D, hwv, out);
+  }
   return check_launch("soft_argmin_kernel");
 }
 

@@ -68,7 +68,18 @@ def main():
         f2 = torch.randn(B, C, H, W, device="cuda")
         cv = nb.GeometryAwareCostVolume(f1, f2, [], lambda vol, feats: vol, 4, 4, G)
         vol_bytes = B * G * H * W * W * 4
-        report("igev groupcorr build B16", timed(lambda: cv.build_cost_volume(f1, f2), reps=10, flush=flush), 2 * B * 64 * H * W * 4 + vol_bytes)
+        fpyr = cv._feat
+        report("igev groupcorr build B16 (4 levels)", timed(lambda: cv._build_feature_volume(f1, f2, fpyr), reps=10, flush=flush),
+               2 * B * 64 * H * W * 4 + B * G * H * W * (160 + 80 + 40 + 20) * 4)
+        from nndepth_b200 import _lib
+        from nndepth_b200.corr import PyramidStorage
+        geo = torch.randn(B, G, W, H, W, device="cuda")
+        pyr = PyramidStorage(B * G * H * W, W, 4, geo.device)
+        report("igev geo transpose+pool B16",
+               timed(lambda: _lib.check(_lib.load().nnd_geo_transpose_pool(_lib.ptr(geo), B, G, W, H, W, 4, pyr._level_ptrs, pyr._pitch_arr,
+                                                                           _lib.stream_ptr(geo)), "geo"), reps=10, flush=flush),
+               vol_bytes + B * G * H * W * (160 + 80 + 40 + 20) * 4)
+        del geo, pyr
         coords = torch.arange(W, device="cuda").float().view(1, 1, 1, W).repeat(B, 1, H, 1) - torch.rand(B, 1, H, W, device="cuda") * 40
         report("igev dual lookup B16", timed(lambda: cv(coords), reps=10, flush=flush), B * H * W * 4868)
         del cv
@@ -83,6 +94,7 @@ def main():
             offs = torch.rand(N, 18, H, W, device="cuda") * 2 - 1
             a = nb.AGCL(f1, f2)
             px = N * H * W
+            report(f"agcl nchw->nhwc staging (one map) N4 {H}x{W}", timed(lambda: nb.AGCL(f1, f2)._nhwc(f1), reps=10, flush=flush), 2 * px * C * 4)
             for small in (False, True):
                 tag = "3x3" if small else "1x9"
                 report(f"agcl offset {tag} N4 {H}x{W}", timed(lambda: a(flow, offs, small, False), reps=10, flush=flush), px * 2272)
