@@ -113,6 +113,21 @@ nnd_status nnd_group_lookup(const float* const* level_a, const float* const* lev
 nnd_status nnd_geo_transpose_pool(const float* geo, int B, int G, int D, int H, int W1, int num_levels,
                                   float* const* level, const int* pitch, nnd_stream_t stream);
 
+/* Interleaved ("group innermost") IGEV pyramids -- the fast path for G == 8, D % 8 == 0, levels <= 4.
+ * level[l] holds [b][h][w1][d_l][g] (one pixel = (D >> l) * 8 contiguous floats), so the eight radius-4
+ * windows of a pixel are one contiguous run instead of eight scattered 40-byte pieces.
+ *   nnd_gev_interleave_pool: one pass from either source layout to levels 0..num_levels-1, pooled exactly
+ *     like avg_pool1d(., 2).  layout 0: reference-layout volume, rows [b][g][h][w1] of D floats with row
+ *     pitch src_pitch (the output of nnd_groupcorr_build; igev_stereo/cost_volume.py:43-51).  layout 1:
+ *     regulariser output (B, 8, D, H, W1) contiguous (igev_stereo/cost_volume.py:44-52); W1 % 4 == 0.
+ *   nnd_gev_lookup: GeometryAwareCostVolume.forward igev_stereo/cost_volume.py:54-79 on those pyramids;
+ *     coords (B,1,H,W1) -> out (B, L*2*8*9, H, W1), channel l*144 + src*72 + g*9 + k, radius 4. */
+nnd_status nnd_gev_interleave_pool(const float* vol, int layout, int src_pitch, int B, int G, int D, int H,
+                                   int W1, int num_levels, float* const* level, nnd_stream_t stream);
+nnd_status nnd_gev_lookup(const float* const* level_feat, const float* const* level_geo, const float* coords,
+                          int B, int G, int D, int H, int W1, int num_levels, int radius, float* out,
+                          nnd_stream_t stream);
+
 /* Soft-argmin: out[b,0,h,w] = -sum_d d * softmax_d(z[b,d,h,w]).  Single pass, online softmax.
  * Replaces F.softmax(dim=1) + regress_disparity, igev_stereo/model.py:145 and :92-95.
  *   z (B,D,H,W) -> out (B,1,H,W). */

@@ -146,13 +146,44 @@ groupcorr_build_kernel(const float* __restrict__ f1, const float* __restrict__ f
   const long long plane2 = static_cast<long long>(H) * W2;
   const float* a_src = f1 + (b * C + static_cast<long long>(g) * K) * plane1 + static_cast<long long>(h) * W1;
   const float* b_src = f2 + (b * C + static_cast<long long>(g) * K) * plane2 + static_cast<long long>(h) * W2;
-  for (int i = threadIdx.x; i < K * W1; i += blockDim.x) {
-    const int k = i / W1, m = i - k * W1;
-    As[i] = __ldg(a_src + k * plane1 + m);
-  }
-  for (int i = threadIdx.x; i < K * W2p; i += blockDim.x) {
-    const int k = i / W2p, n = i - k * W2p;
-    Bs[i] = n < W2 ? __ldg(b_src + k * plane2 + n) : 0.f;
+  // stage the two K x W strips: 16-byte loads, all of a thread's loads issued before the first store
+  // (a dependent load->store loop here costs one memory latency per iteration and dominated the kernel)
+  if (vec_ok != 0 && (W1 & 3) == 0 && (W2 & 3) == 0 && aligned16(f1) && aligned16(f2)) {
+    const int qa = W1 >> 2, qb = W2 >> 2;           // float4 per row
+    const int total = K * (qa + qb);
+    constexpr int MAXQ = 8;
+    for (int base = threadIdx.x; base < total; base += MAXQ * blockDim.x) {
+      float4 v[MAXQ];
+#pragma unroll
+      for (int j = 0; j < MAXQ; ++j) {
+        const int i = base + j * blockDim.x;
+        if (i < total) {
+          const bool is_a = i < K * qa;
+          const int ii = is_a ? i : i - K * qa;
+          const int q = is_a ? qa : qb;
+          const int k = ii / q, c = ii - k * q;
+          v[j] = ldg_f4((is_a ? a_src + k * plane1 : b_src + k * plane2) + 4 * c);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < MAXQ; ++j) {
+        const int i = base + j * blockDim.x;
+        if (i < total) {
+          const bool is_a = i < K * qa;
+          const int ii = is_a ? i : i - K * qa;
+          *reinterpret_cast<float4*>((is_a ? As : Bs) + 4 * ii) = v[j];  // W2p == W2 here: rows stay dense
+        }
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < K * W1; i += blockDim.x) {
+      const int k = i / W1, m = i - k * W1;
+      As[i] = __ldg(a_src + k * plane1 + m);
+    }
+    for (int i = threadIdx.x; i < K * W2p; i += blockDim.x) {
+      const int k = i / W2p, n = i - k * W2p;
+      Bs[i] = n < W2 ? __ldg(b_src + k * plane2 + n) : 0.f;
+    }
   }
   __syncthreads();
 

@@ -42,7 +42,7 @@ nnd_status fill_pyramid(Pyramid& pyr, int W2, int num_levels, float* const* leve
                         const char* who);
 nnd_status pool_tail(const Pyramid& pyr, int num_levels, long long rows, cudaStream_t stream);
 
-inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+__host__ __device__ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---- the bit-exact sampler contract (raft_stereo/utils.py:15-21 of the reference) ------------
 // t = clamp(x / (w-1), 0, 1) * (w-1), both as separately rounded IEEE fp32 operations.

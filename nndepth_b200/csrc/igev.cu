@@ -56,6 +56,128 @@ geo_transpose_pool_kernel(const float* __restrict__ geo, int D, int H, int W1, i
 }
 
 // ------------------------------------------------------------------------------------------------
+// Interleaved ("g innermost") IGEV pyramids.
+//
+// In the reference layout ([b][g][h][w1] rows of D floats) the radius-4 window of one pixel is 8 groups
+// x 40 bytes scattered over 8 rows: with 32-byte sectors and 64-byte DRAM granules the dual lookup
+// drags 2.66 GB through HBM per iteration for 0.79 GB of useful window data (ncu, BASELINE config 4).
+// The lookup-side pyramids are therefore stored pixel-major with the group index innermost:
+//     level l:  [b][h][w1][d_l][g]   (row of one pixel = (D >> l) * G floats, 32-byte aligned)
+// so the 8 windows of a pixel are ONE contiguous run of <= 11 * 32 bytes.  The layout is private to the
+// cost-volume object; the reference-layout views (feat_corr_cv / geo_aware_cv) are synthesised on demand.
+//
+// Both producers below read the volume once and write levels 0..3 from registers.  A thread owns
+// (pixel(s), 4 consecutive d, 4 consecutive g): levels 1 and 2 pool inside the thread, level 3 takes one
+// shuffle with the thread holding the neighbouring d-quad (lane ^ 2).  Lane bit 0 selects the g-half, so
+// the two lanes of a pair complete every 32-byte sector they touch in the same store instruction.
+// Requires G == 8 and D % 8 == 0 (num_levels <= 4).
+// ------------------------------------------------------------------------------------------------
+struct InterleavedLevels {
+  float* ptr[4];
+  int num_levels;
+};
+
+// v[gi] = 4 consecutive d of group 4*gh + gi for ONE pixel; writes this thread's share of levels 0..3.
+__device__ __forceinline__ void store_interleaved_quad(const InterleavedLevels& lv, long long pixrow, int D, int dq,
+                                                       int gh, const float (&v)[4][4], bool ok) {
+  // level 0: d = 4*dq + j  ->  floats (pixrow*D + d) * 8 + 4*gh
+  if (ok) {
+    float* p0 = lv.ptr[0] + (pixrow * D + 4 * dq) * 8 + 4 * gh;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(p0 + 8 * j) = make_float4(v[0][j], v[1][j], v[2][j], v[3][j]);
+  }
+  if (lv.num_levels < 2) return;
+  float l1[4][2];
+#pragma unroll
+  for (int gi = 0; gi < 4; ++gi) {
+    l1[gi][0] = pool2(v[gi][0], v[gi][1]);
+    l1[gi][1] = pool2(v[gi][2], v[gi][3]);
+  }
+  if (ok) {
+    float* p1 = lv.ptr[1] + (pixrow * (D >> 1) + 2 * dq) * 8 + 4 * gh;
+    *reinterpret_cast<float4*>(p1) = make_float4(l1[0][0], l1[1][0], l1[2][0], l1[3][0]);
+    *reinterpret_cast<float4*>(p1 + 8) = make_float4(l1[0][1], l1[1][1], l1[2][1], l1[3][1]);
+  }
+  if (lv.num_levels < 3) return;
+  float l2[4];
+#pragma unroll
+  for (int gi = 0; gi < 4; ++gi) l2[gi] = pool2(l1[gi][0], l1[gi][1]);
+  if (ok) *reinterpret_cast<float4*>(lv.ptr[2] + (pixrow * (D >> 2) + dq) * 8 + 4 * gh) = make_float4(l2[0], l2[1], l2[2], l2[3]);
+  if (lv.num_levels < 4) return;
+  float o[4];
+#pragma unroll
+  for (int gi = 0; gi < 4; ++gi) o[gi] = __shfl_xor_sync(0xffffffffu, l2[gi], 2);  // the d-quad dq ^ 1
+  if (ok && (dq & 1) == 0)
+    *reinterpret_cast<float4*>(lv.ptr[3] + (pixrow * (D >> 3) + (dq >> 1)) * 8 + 4 * gh) =
+        make_float4(pool2(l2[0], o[0]), pool2(l2[1], o[1]), pool2(l2[2], o[2]), pool2(l2[3], o[3]));
+}
+
+// source = reference-layout volume: rows [b][g][h][w1] of D floats (d contiguous, row pitch `pitch`).
+// lane = gh | (item_in_warp << 1); items = (pixel, d-quad) pairs, d-quad fastest.
+__global__ void __launch_bounds__(256)
+gev_interleave_dmajor_kernel(const float* __restrict__ vol, long long pitch, int D, long long hw, long long n_items,
+                             InterleavedLevels lv) {
+  const int gh = threadIdx.x & 1;
+  const long long item = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 1;
+  const bool ok = item < n_items;
+  const int dqs = D >> 2;
+  const long long it = ok ? item : 0;
+  const long long pixrow = it / dqs;            // (b*H + h)*W1 + w1
+  const int dq = static_cast<int>(it - pixrow * dqs);
+  const long long b = pixrow / hw;
+  const long long p = pixrow - b * hw;
+  float v[4][4];
+#pragma unroll
+  for (int gi = 0; gi < 4; ++gi) {
+    const long long row = (b * 8 + 4 * gh + gi) * hw + p;
+    const float4 t = ok ? __ldcs(reinterpret_cast<const float4*>(vol + row * pitch + 4 * dq)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    v[gi][0] = t.x; v[gi][1] = t.y; v[gi][2] = t.z; v[gi][3] = t.w;
+  }
+  store_interleaved_quad(lv, pixrow, D, dq, gh, v, ok);
+}
+
+// source = regulariser output (B, 8, D, H, W1), w1 contiguous.
+// lane = gh | (dq parity << 1) | (w-quad in a group of 8 << 2); warp item = (b, h, w-group of 32 px, d-octet).
+__global__ void __launch_bounds__(256)
+gev_interleave_wmajor_kernel(const float* __restrict__ geo, int D, int H, int W1, int w_groups, long long n_warp_items,
+                             InterleavedLevels lv) {
+  const int lane = threadIdx.x & 31;
+  const long long witem = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (witem >= n_warp_items) return;  // warp-uniform
+  const int gh = lane & 1, dqp = (lane >> 1) & 1, wql = lane >> 2;
+  const int d_octs = D >> 3;
+  long long t = witem;
+  const int doct = static_cast<int>(t % d_octs);
+  t /= d_octs;
+  const int wg = static_cast<int>(t % w_groups);
+  const long long bh = t / w_groups;
+  const long long b = bh / H;
+  const int h = static_cast<int>(bh - b * H);
+  const int w0 = (wg * 8 + wql) * 4;
+  const bool ok = w0 < W1;  // W1 % 4 == 0: a quad is inside or outside as a whole
+  const int dq = doct * 2 + dqp;
+  const long long plane = static_cast<long long>(H) * W1;
+  float4 raw[4][4];  // [gi][j]: 4 pixels of (g = 4*gh + gi, d = 4*dq + j)
+#pragma unroll
+  for (int gi = 0; gi < 4; ++gi)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      raw[gi][j] = ok ? __ldcs(reinterpret_cast<const float4*>(
+                            geo + ((b * 8 + 4 * gh + gi) * D + 4 * dq + j) * plane + static_cast<long long>(h) * W1 + w0))
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float v[4][4];
+#pragma unroll
+    for (int gi = 0; gi < 4; ++gi)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        v[gi][j] = e == 0 ? raw[gi][j].x : e == 1 ? raw[gi][j].y : e == 2 ? raw[gi][j].z : raw[gi][j].w;
+    store_interleaved_quad(lv, bh * W1 + w0 + e, D, dq, gh, v, ok);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Soft-argmin: out[b,0,h,w] = -sum_d d * softmax_d(z[b,d,h,w]) in ONE pass over z (online softmax).
 // z is (B,D,H,W): the softmax axis is strided by H*W, consecutive pixels are contiguous.  A block is
 // 32 lanes x S disparity slices; a lane owns VEC consecutive pixels (one 16-byte load per disparity
@@ -233,6 +355,43 @@ nnd_status nnd_soft_argmin(const float* z, int B, int D, int H, int W, float* ou
     soft_argmin_kernel<1><<<grid, block, smem, st>>>(z, D, hwv, out);
   }
   return check_launch("soft_argmin_kernel");
+}
+
+nnd_status nnd_gev_interleave_pool(const float* vol, int layout, int src_pitch, int B, int G, int D, int H, int W1,
+                                   int num_levels, float* const* level, nnd_stream_t stream_) {
+  using namespace nnd;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  NND_REQUIRE(vol && level, "gev_interleave_pool: null pointer");
+  NND_REQUIRE(B > 0 && D > 0 && H > 0 && W1 > 0, "gev_interleave_pool: B, D, H, W1 must be positive");
+  NND_REQUIRE(G == 8, "gev_interleave_pool: the interleaved layout is built for 8 groups (got %d)", G);
+  NND_REQUIRE(D % 8 == 0, "gev_interleave_pool: D = %d must be a multiple of 8", D);
+  NND_REQUIRE(num_levels >= 1 && num_levels <= 4, "gev_interleave_pool: num_levels %d outside [1, 4]", num_levels);
+  NND_REQUIRE(layout == 0 || layout == 1, "gev_interleave_pool: layout %d is not 0 (rows of D) or 1 (B,G,D,H,W)", layout);
+  NND_REQUIRE(aligned16(vol), "gev_interleave_pool: source must be 16-byte aligned");
+  InterleavedLevels lv;
+  memset(&lv, 0, sizeof(lv));
+  lv.num_levels = num_levels;
+  for (int l = 0; l < num_levels; ++l) {
+    NND_REQUIRE(level[l] && aligned16(level[l]), "gev_interleave_pool: level %d pointer is null or unaligned", l);
+    lv.ptr[l] = level[l];
+  }
+  const long long hw = static_cast<long long>(H) * W1;
+  if (layout == 0) {
+    NND_REQUIRE(src_pitch >= D && src_pitch % 4 == 0, "gev_interleave_pool: row pitch %d must be >= D and a multiple of 4",
+                src_pitch);
+    const long long n_items = static_cast<long long>(B) * hw * (D / 4);
+    const long long blocks = (2 * n_items + 255) / 256;
+    NND_REQUIRE(blocks <= 0x7fffffffLL, "gev_interleave_pool: volume too large for one launch");
+    gev_interleave_dmajor_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(vol, src_pitch, D, hw, n_items, lv);
+    return check_launch("gev_interleave_dmajor_kernel");
+  }
+  NND_REQUIRE(W1 % 4 == 0, "gev_interleave_pool: layout 1 needs W1 %% 4 == 0 (got %d)", W1);
+  const int w_groups = (W1 + 31) / 32;
+  const long long n_warp_items = static_cast<long long>(B) * H * w_groups * (D / 8);
+  const long long blocks = (n_warp_items + 7) / 8;
+  NND_REQUIRE(blocks <= 0x7fffffffLL, "gev_interleave_pool: volume too large for one launch");
+  gev_interleave_wmajor_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(vol, D, H, W1, w_groups, n_warp_items, lv);
+  return check_launch("gev_interleave_wmajor_kernel");
 }
 
 }  // extern "C"

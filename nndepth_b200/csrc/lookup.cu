@@ -239,6 +239,112 @@ pyramid_lookup_kernel(const LookupArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// IGEV dual lookup over the interleaved pyramids ([b][h][w1][d][g], igev.cu): the eight windows of a
+// pixel are one contiguous run of (hi - lo + 1) * 32 bytes <= 352 bytes, so every fetched sector is used.
+// Warp = 32 consecutive pixels x one level; for each of the two sources the warp copies the 32 runs into a
+// padded shared-memory tile with 16-byte loads (8 lanes per pixel, 4 pixels per instruction), then every
+// lane interpolates its own pixel: per tap two 32-byte reads give the 8 groups of idx0 and idx1.
+// Output layout and arithmetic are those of the reference (channel = l*144 + src*72 + g*9 + k).
+// ------------------------------------------------------------------------------------------------
+struct GevLookupArgs {
+  const float* src[2][4];  // [source][level]
+  int width[4];            // D >> l
+  const float* coords;
+  float* out;
+  int hw;
+  int num_levels;
+};
+
+constexpr int GEV_G = 8;
+constexpr int GEV_T = 9;           // radius 4
+constexpr int GEV_RUN = 11 * GEV_G;   // floats in the longest run
+constexpr int GEV_STRIDE = GEV_RUN + 4;  // 92 floats: 16-byte aligned rows, 28-bank skew -> conflict-free LDS.128
+
+__global__ void __launch_bounds__(128)
+gev_lookup_kernel(const __grid_constant__ GevLookupArgs a) {
+  constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ __align__(16) float gsm[];
+  const int lane = threadIdx.x;
+  const int lvl = threadIdx.y;
+  float* win = gsm + lvl * (32 * GEV_STRIDE);
+  const int b = blockIdx.y;
+  const int rem0 = blockIdx.x * 32;
+  const int rem = rem0 + lane;
+  const bool valid = rem < a.hw;
+  const int w = a.width[lvl];
+
+  const float c = valid ? __ldg(a.coords + static_cast<long long>(b) * a.hw + rem) : 0.0f;
+  const float centre = __fmul_rn(c, 1.0f / static_cast<float>(1 << lvl));
+  const LevelScale sc = level_scale(w, lvl, centre);
+  int o0[GEV_T], o1[GEV_T];
+  float cf[GEV_T], omc[GEV_T];
+  int lo, hi;
+  {
+    Tap tp[GEV_T];
+#pragma unroll
+    for (int k = 0; k < GEV_T; ++k) tp[k] = make_tap(k, 4, centre, sc);
+    lo = tp[0].i0;
+    hi = tp[GEV_T - 1].i1;
+    const int base = lane * GEV_STRIDE - lo * GEV_G;
+#pragma unroll
+    for (int k = 0; k < GEV_T; ++k) {
+      o0[k] = base + tp[k].i0 * GEV_G;
+      o1[k] = base + tp[k].i1 * GEV_G;
+      cf[k] = tp[k].coef;
+      omc[k] = tp[k].one_minus;
+    }
+  }
+  const int nq = valid ? 2 * (hi - lo + 1) : 0;  // 16-byte quads in my run (<= 22)
+
+  // loader role: round r serves pixels 4r .. 4r+3, eight lanes each, three quads per lane
+  const int sub = lane & 7;
+  const long long rowlen = static_cast<long long>(w) * GEV_G;
+  const long long pix_base = static_cast<long long>(b) * a.hw + rem0;
+  const long long c_total = static_cast<long long>(a.num_levels) * 2 * GEV_G * GEV_T;
+  float* const out_px = a.out + static_cast<long long>(b) * c_total * a.hw + rem;
+
+  for (int s = 0; s < 2; ++s) {
+    const float* __restrict__ rows = a.src[s][lvl] + pix_base * rowlen;
+#pragma unroll 4
+    for (int r = 0; r < 8; ++r) {
+      const int p = 4 * r + (lane >> 3);
+      const int lo_p = __shfl_sync(FULL, lo, p);
+      const int nq_p = __shfl_sync(FULL, nq, p);
+      const float* src = rows + static_cast<long long>(p) * rowlen + lo_p * GEV_G;
+      float4 v[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int q = sub + 8 * j;
+        v[j] = q < nq_p ? ldg_f4(src + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int q = sub + 8 * j;
+        if (q < 23) *reinterpret_cast<float4*>(win + p * GEV_STRIDE + 4 * q) = v[j];
+      }
+    }
+    __syncwarp();
+    if (valid) {
+      float* op = out_px + (static_cast<long long>(lvl) * 2 * GEV_G * GEV_T + s * GEV_G * GEV_T) * a.hw;
+#pragma unroll
+      for (int k = 0; k < GEV_T; ++k) {
+        const float4 a0 = *reinterpret_cast<const float4*>(win + o0[k]);
+        const float4 a1 = *reinterpret_cast<const float4*>(win + o0[k] + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(win + o1[k]);
+        const float4 b1 = *reinterpret_cast<const float4*>(win + o1[k] + 4);
+        const float v0[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float v1[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int g = 0; g < GEV_G; ++g)
+          // coef * val0 + (1 - coef) * val1, each operation rounded (utils.py:27)
+          op[static_cast<long long>(g * GEV_T + k) * a.hw] = __fadd_rn(__fmul_rn(cf[k], v0[g]), __fmul_rn(omc[k], v1[g]));
+      }
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void lookup_indices_kernel(const float* __restrict__ coords, long long n_pix, int num_levels, int radius,
                                       int w0, int w1, int w2, int w3, int w4, int w5, int w6, int w7,
                                       int32_t* __restrict__ idx0, int32_t* __restrict__ idx1) {
@@ -360,6 +466,40 @@ nnd_status nnd_corr1d_lookup_indices(const int* width, const float* coords, int 
   nnd::lookup_indices_kernel<<<blocks, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       coords, n_pix, num_levels, radius, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], idx0, idx1);
   return nnd::check_launch("lookup_indices_kernel");
+}
+
+nnd_status nnd_gev_lookup(const float* const* level_feat, const float* const* level_geo, const float* coords, int B,
+                          int G, int D, int H, int W1, int num_levels, int radius, float* out, nnd_stream_t stream) {
+  using namespace nnd;
+  NND_REQUIRE(level_feat && level_geo && coords && out, "gev_lookup: null pointer argument");
+  NND_REQUIRE(B > 0 && H > 0 && W1 > 0, "gev_lookup: B, H, W1 must be positive");
+  NND_REQUIRE(B <= 65535, "gev_lookup: batch %d exceeds the grid limit (65535)", B);
+  NND_REQUIRE(G == GEV_G && radius == 4, "gev_lookup: built for 8 groups and radius 4 (got G=%d, radius=%d)", G, radius);
+  NND_REQUIRE(num_levels >= 1 && num_levels <= 4, "gev_lookup: num_levels %d outside [1, 4]", num_levels);
+  NND_REQUIRE(D % 8 == 0, "gev_lookup: D = %d must be a multiple of 8", D);
+  NND_REQUIRE(static_cast<long long>(H) * W1 < (1LL << 30), "gev_lookup: H*W1 too large");
+  GevLookupArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int l = 0; l < num_levels; ++l) {
+    // linear_sampler divides by (w2 - 1): a 1-wide level is a division by zero in the reference
+    NND_REQUIRE((D >> l) >= 2, "gev_lookup: level %d has width %d; linear_sampler needs width >= 2", l, D >> l);
+    NND_REQUIRE(level_feat[l] && level_geo[l] && aligned16(level_feat[l]) && aligned16(level_geo[l]),
+                "gev_lookup: level %d pointer is null or unaligned", l);
+    a.src[0][l] = level_feat[l];
+    a.src[1][l] = level_geo[l];
+    a.width[l] = D >> l;
+  }
+  a.coords = coords;
+  a.out = out;
+  a.hw = H * W1;
+  a.num_levels = num_levels;
+  dim3 grid((a.hw + 31) / 32, B);
+  dim3 block(32, num_levels);
+  const size_t smem = static_cast<size_t>(num_levels) * 32 * GEV_STRIDE * sizeof(float);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(gev_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  gev_lookup_kernel<<<grid, block, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  return check_launch("gev_lookup_kernel");
 }
 
 }  // extern "C"

@@ -4,6 +4,11 @@ Mirrors ``nndepth/models/igev_stereo/cost_volume.py:9-98`` (``GeometryAwareCostV
 regression at ``nndepth/models/igev_stereo/model.py:92-95,144-146`` of the reference.
 ``model.corr_fn = nndepth_b200.GeometryAwareCostVolume`` swaps the reference model onto these kernels
 (``igev_stereo/model.py:64,133-141``).  The 3-D regulariser stays the caller's PyTorch module.
+
+Layout: for the model's configuration (8 groups, ``W2 % 8 == 0``, <= 4 levels, radius 4) the two lookup
+pyramids are stored pixel-major with the group innermost (``[b][h][w1][d][g]``, see csrc/igev.cu), which
+makes the eight windows of a pixel one contiguous run; the reference-layout lists ``feat_corr_cv`` /
+``geo_aware_cv`` are synthesised on demand.  Other configurations use the reference row layout.
 """
 import math
 
@@ -12,6 +17,42 @@ import torch.nn as nn
 
 from . import _lib
 from .corr import PyramidStorage, _check_coords
+
+
+class InterleavedPyramid:
+    """Levels ``[b][h][w1][d_l][g]`` of a grouped volume in ONE allocation (G = 8, D % 8 == 0)."""
+
+    def __init__(self, pixels, depth, num_levels, device):
+        self.pixels, self.depth = int(pixels), int(depth)
+        self.widths = [self.depth >> l for l in range(num_levels)]
+        sizes = [self.pixels * w * 8 for w in self.widths]
+        self.buffer = torch.empty(sum(sizes), dtype=torch.float32, device=device)
+        self.levels, start = [], 0
+        for n in sizes:
+            self.levels.append(self.buffer[start:start + n])
+            start += n
+        self._level_ptrs = _lib.ptr_array(self.levels)
+
+    def fill(self, src, layout, src_pitch, B, D, H, W1):
+        with torch.cuda.device(src.device):
+            _lib.check(
+                _lib.load().nnd_gev_interleave_pool(_lib.ptr(src), layout, src_pitch, B, 8, D, H, W1, len(self.levels),
+                                                    self._level_ptrs, _lib.stream_ptr(src)),
+                "nnd_gev_interleave_pool",
+            )
+        return self
+
+    def load_reference(self, levels, B, H, W1):
+        """From reference-layout levels ``(B*8*H*W1, w_l)`` (parity tests)."""
+        for dst, w, src in zip(self.levels, self.widths, levels):
+            src = torch.as_tensor(src).to(device=dst.device, dtype=torch.float32).reshape(B, 8, H, W1, w)
+            dst.copy_(src.permute(0, 2, 3, 4, 1).reshape(-1))
+        return self
+
+    def reference_level(self, l, B, H, W1):
+        """Level ``l`` back in the reference layout ``(B*8*H*W1, 1, w_l)``."""
+        w = self.widths[l]
+        return self.levels[l].view(B, H, W1, w, 8).permute(0, 4, 1, 2, 3).reshape(B * 8 * H * W1, 1, w)
 
 
 class GeometryAwareCostVolume(nn.Module):
@@ -30,7 +71,10 @@ class GeometryAwareCostVolume(nn.Module):
         W2 = f2.shape[3]
         G = num_groups
         self._shape = (B, H, W1, W2)
-        self._feat = PyramidStorage(B * G * H * W1, W2, num_levels, f1.device)
+        self._interleaved = (G == 8 and W2 % 8 == 0 and W1 % 4 == 0 and num_levels <= 4 and radius == 4)
+        # feature volume in the reference row layout: level 0 only on the interleaved path (it feeds the
+        # regulariser), all levels otherwise
+        self._feat = PyramidStorage(B * G * H * W1, W2, 1 if self._interleaved else num_levels, f1.device)
         self._build_feature_volume(f1, f2, self._feat)
         # regulariser input: (B, G, W2, H, W1) view of the level-0 volume (cost_volume.py:37); level 0 is
         # dense whenever W2 % 4 == 0, otherwise the padding columns are sliced off.
@@ -43,6 +87,12 @@ class GeometryAwareCostVolume(nn.Module):
         if (Bg, Hg, Wg, D) != (B, H, W1, W2):
             raise RuntimeError(
                 f"regularizer_3d returned {tuple(geo.shape)}; expected (B, G, W2, H, W1) = {(B, G, W2, H, W1)}")
+        if self._interleaved:
+            self._feat_il = InterleavedPyramid(B * H * W1, W2, num_levels, f1.device).fill(
+                self._feat.levels[0], 0, self._feat.pitches[0], B, W2, H, W1)
+            self._geo_il = InterleavedPyramid(B * H * W1, D, num_levels, f1.device).fill(geo, 1, 0, B, D, H, W1)
+            self._geo = None
+            return
         self._geo = PyramidStorage(B * G * H * W1, D, num_levels, f1.device)
         with torch.cuda.device(f1.device):
             _lib.check(
@@ -62,8 +112,18 @@ class GeometryAwareCostVolume(nn.Module):
         rows, W2 = first.reshape(first.shape[0], -1).shape
         self._shape = (batch, height, rows // (batch * height * num_groups), W2)
         dev = torch.device(device)
-        self._feat = PyramidStorage(rows, W2, num_levels, dev).load(feat_levels[:num_levels])
-        self._geo = PyramidStorage(rows, W2, num_levels, dev).load(geo_levels[:num_levels])
+        W1 = self._shape[2]
+        self._interleaved = (num_groups == 8 and W2 % 8 == 0 and W1 % 4 == 0 and num_levels <= 4 and radius == 4)
+        if self._interleaved:
+            self._feat = PyramidStorage(rows, W2, 1, dev).load(feat_levels[:1])
+            self._geo = None
+            self._feat_il = InterleavedPyramid(batch * height * W1, W2, num_levels, dev).load_reference(
+                feat_levels[:num_levels], batch, height, W1)
+            self._geo_il = InterleavedPyramid(batch * height * W1, W2, num_levels, dev).load_reference(
+                geo_levels[:num_levels], batch, height, W1)
+        else:
+            self._feat = PyramidStorage(rows, W2, num_levels, dev).load(feat_levels[:num_levels])
+            self._geo = PyramidStorage(rows, W2, num_levels, dev).load(geo_levels[:num_levels])
         return self
 
     def _build_feature_volume(self, f1, f2, pyr):
@@ -82,13 +142,20 @@ class GeometryAwareCostVolume(nn.Module):
                 "nnd_groupcorr_build",
             )
 
+    def _reference_list(self, il):
+        """The reference's ``num_levels + 1`` list from an interleaved pyramid (de-interleaved copies)."""
+        B, H, W1, _ = self._shape
+        views = [il.reference_level(l, B, H, W1) for l in range(len(il.levels))]
+        views.append(torch.nn.functional.avg_pool1d(views[-1], 2))      # the level the reference never reads
+        return views
+
     @property
     def feat_corr_cv(self):
-        return self._feat.reference_view()
+        return self._reference_list(self._feat_il) if self._interleaved else self._feat.reference_view()
 
     @property
     def geo_aware_cv(self):
-        return self._geo.reference_view()
+        return self._reference_list(self._geo_il) if self._interleaved else self._geo.reference_view()
 
     def build_cost_volume(self, fmap1, fmap2):
         """``(B, G, H, W1, W2)`` group-wise volume (reference cost_volume.py:81-98)."""
@@ -106,6 +173,15 @@ class GeometryAwareCostVolume(nn.Module):
         T = 2 * self.radius + 1
         out = torch.empty(B, self.num_levels * 2 * self.num_groups * T, H, W1, dtype=torch.float32,
                           device=coords.device)
+        if self._interleaved:
+            with torch.cuda.device(coords.device):
+                _lib.check(
+                    _lib.load().nnd_gev_lookup(self._feat_il._level_ptrs, self._geo_il._level_ptrs, _lib.ptr(coords), B,
+                                               self.num_groups, self._shape[3], H, W1, self.num_levels, self.radius,
+                                               _lib.ptr(out), _lib.stream_ptr(coords)),
+                    "nnd_gev_lookup",
+                )
+            return out
         with torch.cuda.device(coords.device):
             _lib.check(
                 _lib.load().nnd_group_lookup(self._feat._level_ptrs, self._geo._level_ptrs, self._feat._width_arr,

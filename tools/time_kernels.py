@@ -62,26 +62,27 @@ def main():
             report(f"lookup B{B} {H}x{W} (L2 flushed)", timed(lambda: blk(coords), flush=flush), lb)
             report(f"lookup B{B} {H}x{W} (L2 warm)", timed(lambda: blk(coords), flush=None), lb)
     if args.what in ("igev", "all"):
+        from nndepth_b200 import _lib
+        from nndepth_b200.igev import InterleavedPyramid
         B, C, H, W, G = 16, 256, 120, 160, 8
         torch.manual_seed(0)
         f1 = torch.randn(B, C, H, W, device="cuda")
         f2 = torch.randn(B, C, H, W, device="cuda")
         cv = nb.GeometryAwareCostVolume(f1, f2, [], lambda vol, feats: vol, 4, 4, G)
         vol_bytes = B * G * H * W * W * 4
+        pyr_bytes = B * G * H * W * (160 + 80 + 40 + 20) * 4
         fpyr = cv._feat
-        report("igev groupcorr build B16 (4 levels)", timed(lambda: cv._build_feature_volume(f1, f2, fpyr), reps=10, flush=flush),
-               2 * B * 64 * H * W * 4 + B * G * H * W * (160 + 80 + 40 + 20) * 4)
-        from nndepth_b200 import _lib
-        from nndepth_b200.corr import PyramidStorage
+        report("igev groupcorr build B16 (level 0, reference layout)",
+               timed(lambda: cv._build_feature_volume(f1, f2, fpyr), reps=10, flush=flush), 2 * B * 64 * H * W * 4 + vol_bytes)
+        il = InterleavedPyramid(B * H * W, W, 4, f1.device)
+        report("igev interleave+pool from rows (feat) B16",
+               timed(lambda: il.fill(fpyr.levels[0], 0, fpyr.pitches[0], B, W, H, W), reps=10, flush=flush), vol_bytes + pyr_bytes)
         geo = torch.randn(B, G, W, H, W, device="cuda")
-        pyr = PyramidStorage(B * G * H * W, W, 4, geo.device)
-        report("igev geo transpose+pool B16",
-               timed(lambda: _lib.check(_lib.load().nnd_geo_transpose_pool(_lib.ptr(geo), B, G, W, H, W, 4, pyr._level_ptrs, pyr._pitch_arr,
-                                                                           _lib.stream_ptr(geo)), "geo"), reps=10, flush=flush),
-               vol_bytes + B * G * H * W * (160 + 80 + 40 + 20) * 4)
-        del geo, pyr
+        report("igev interleave+pool from (B,G,D,H,W) (geo) B16",
+               timed(lambda: il.fill(geo, 1, 0, B, W, H, W), reps=10, flush=flush), vol_bytes + pyr_bytes)
+        del geo, il
         coords = torch.arange(W, device="cuda").float().view(1, 1, 1, W).repeat(B, 1, H, 1) - torch.rand(B, 1, H, W, device="cuda") * 40
-        report("igev dual lookup B16", timed(lambda: cv(coords), reps=10, flush=flush), B * H * W * 4868)
+        report("igev dual lookup B16 (interleaved pyramids)", timed(lambda: cv(coords), reps=10, flush=flush), B * H * W * 4868)
         del cv
         z = torch.randn(B, W, H, W, device="cuda")
         report("soft-argmin B16 D160 120x160", timed(lambda: nb.soft_argmin(z), reps=10, flush=flush), z.numel() * 4 + B * H * W * 4)
