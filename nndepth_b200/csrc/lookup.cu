@@ -306,24 +306,24 @@ gev_lookup_kernel(const __grid_constant__ GevLookupArgs a) {
 
   for (int s = 0; s < 2; ++s) {
     const float* __restrict__ rows = a.src[s][lvl] + pix_base * rowlen;
-#pragma unroll 4
+    // 16-byte cp.async copies straight into the tile: all 24 of a lane are in flight at once and cost no
+    // registers (through registers ptxas interleaves "load round r / store round r-1" and keeps ~3 in flight)
+#pragma unroll
     for (int r = 0; r < 8; ++r) {
       const int p = 4 * r + (lane >> 3);
       const int lo_p = __shfl_sync(FULL, lo, p);
       const int nq_p = __shfl_sync(FULL, nq, p);
       const float* src = rows + static_cast<long long>(p) * rowlen + lo_p * GEV_G;
-      float4 v[3];
+      const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(win + p * GEV_STRIDE));
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         const int q = sub + 8 * j;
-        v[j] = q < nq_p ? ldg_f4(src + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const int q = sub + 8 * j;
-        if (q < 23) *reinterpret_cast<float4*>(win + p * GEV_STRIDE + 4 * q) = v[j];
+        if (q < nq_p)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * q), "l"(src + 4 * q) : "memory");
       }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
     if (valid) {
       float* op = out_px + (static_cast<long long>(lvl) * 2 * GEV_G * GEV_T + s * GEV_G * GEV_T) * a.hw;
