@@ -240,6 +240,80 @@ pyramid_lookup_kernel(const LookupArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// RAFT-Stereo fast path (one source, one plane): warp = 32 consecutive pixels x one level, like the
+// generic kernel, but lean in registers.  A launch at the KITTI shape moves only ~18 MB, so its
+// duration is a latency chain (coords -> window bounds -> window fetch -> interpolate -> store), and the
+// generic kernel's 74 registers (per-tap state of 9 taps kept across the plane loop) leave room for only
+// half of the 7 488 warps at once: the second wave pays the whole chain again.  Here only the window
+// bounds are computed before the fetch and the taps are re-derived afterwards (11 instead of 9 tap
+// evaluations), which fits 40 registers -> the whole grid is resident in one wave.
+// ------------------------------------------------------------------------------------------------
+template <int TAPS>
+__global__ void __launch_bounds__(32 * NND_MAX_LEVELS, 6)
+corr1d_lookup_lean_kernel(const __grid_constant__ LookupArgs a) {
+  constexpr int WINQ = 4, COLS = 4 * WINQ, STRIDE = COLS + 1;
+  constexpr int R = (TAPS - 1) / 2;
+  constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x, lvl = threadIdx.y;
+  float* win = smem + lvl * (32 * STRIDE);
+
+  const int b = blockIdx.y;
+  const int rem0 = blockIdx.x * 32;
+  const int rem = rem0 + lane;
+  const bool valid = rem < a.hw;
+  const int w = a.src[0].width[lvl];
+  const int pitch = a.src[0].pitch[lvl];
+  const float c = valid ? __ldg(a.coords + static_cast<long long>(b) * a.hw + rem) : 0.0f;
+  const float centre = __fmul_rn(c, 1.0f / static_cast<float>(1 << lvl));
+  const LevelScale sc = level_scale(w, lvl, centre);
+  const int s = make_tap(0, R, centre, sc).i0 & ~3;
+  const int hi = make_tap(TAPS - 1, R, centre, sc).i1;
+
+  const int q = lane & 3;
+  const float* __restrict__ rows = a.src[0].ptr[lvl] + (static_cast<long long>(b) * a.hw + rem0) * pitch;
+  float4 v[WINQ];
+#pragma unroll
+  for (int j = 0; j < WINQ; ++j) {
+    const int p = j * 8 + (lane >> 2);
+    const int sp = __shfl_sync(FULL, s, p);
+    const int hp = __shfl_sync(FULL, hi, p);
+    const int cq = sp + 4 * q;
+    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((rem0 + p < a.hw) && cq <= hp && cq < w) {
+      const float* src = rows + static_cast<long long>(p) * pitch + cq;
+      if (a.vec) {
+        v[j] = ldg_f4(src);
+      } else {
+        const int left = w - cq;
+        v[j].x = __ldg(src);
+        if (left > 1) v[j].y = __ldg(src + 1);
+        if (left > 2) v[j].z = __ldg(src + 2);
+        if (left > 3) v[j].w = __ldg(src + 3);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < WINQ; ++j) {
+    float* dst = win + (j * 8 + (lane >> 2)) * STRIDE + 4 * q;
+    dst[0] = v[j].x;
+    dst[1] = v[j].y;
+    dst[2] = v[j].z;
+    dst[3] = v[j].w;
+  }
+  __syncwarp();
+  if (!valid) return;
+  const float* mine = win + lane * STRIDE - s;
+  float* op = a.out + (static_cast<long long>(b) * a.num_levels + lvl) * TAPS * a.hw + rem;
+#pragma unroll
+  for (int k = 0; k < TAPS; ++k) {
+    const Tap tp = make_tap(k, R, centre, sc);
+    // coef * val0 + (1 - coef) * val1, each operation rounded (utils.py:27)
+    op[static_cast<long long>(k) * a.hw] = __fadd_rn(__fmul_rn(tp.coef, mine[tp.i0]), __fmul_rn(tp.one_minus, mine[tp.i1]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // IGEV dual lookup over the interleaved pyramids ([b][h][w1][d][g], igev.cu): the eight windows of a
 // pixel are one contiguous run of (hi - lo + 1) * 32 bytes <= 352 bytes, so every fetched sector is used.
 // Warp = 32 consecutive pixels x one level; for each of the two sources the warp copies the 32 runs into a
@@ -409,6 +483,14 @@ static nnd_status launch_lookup(const float* const* level_a, const float* const*
   const int n_planes = n_src * G;
   a.planes_per_block = n_planes >= 8 ? 4 : n_planes;
 
+  if (n_src == 1 && G == 1 && mode == 0 && radius == 4) {
+    // RAFT-Stereo: register-lean variant, whole grid resident in one wave (see corr1d_lookup_lean_kernel)
+    dim3 grid((a.hw + 31) / 32, B);
+    dim3 block(32, num_levels);
+    const size_t smem = static_cast<size_t>(num_levels) * 32 * 17 * sizeof(float);
+    corr1d_lookup_lean_kernel<9><<<grid, block, smem, stream>>>(a);
+    return check_launch("corr1d_lookup_lean_kernel");
+  }
   dim3 grid((a.hw + 31) / 32, (n_planes + a.planes_per_block - 1) / a.planes_per_block, B);
   dim3 block(32, num_levels);
   if (radius <= 5) {

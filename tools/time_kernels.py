@@ -45,6 +45,17 @@ def main():
     ap.add_argument("what", nargs="?", default="raft")
     args = ap.parse_args()
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
+    if args.what in ("floor", "raft", "all"):
+        # reference points for latency-bound launches: what does the same harness report for a trivial kernel and
+        # for a plain copy moving the lookup's 18.4 MB?
+        one = torch.zeros(32, device="cuda")
+        report("floor: 1-block fill kernel", timed(lambda: one.fill_(1.0), flush=flush), 128)
+        src = torch.randn(2300000, device="cuda"); dst = torch.empty_like(src)
+        report("floor: copy 9.2 MB -> 9.2 MB (L2 flushed)", timed(lambda: dst.copy_(src), flush=flush), 2 * src.numel() * 4)
+        report("floor: copy 9.2 MB -> 9.2 MB (L2 warm)", timed(lambda: dst.copy_(src), flush=None), 2 * src.numel() * 4)
+        big = torch.randn(8 * 1024 * 1024, device="cuda"); idx = torch.randint(0, big.numel() // 16, (59904 * 4,), device="cuda") * 16
+        gat = torch.empty(59904 * 4, 16, device="cuda")
+        report("floor: gather 240k x 64 B rows from 32 MB (flushed)", timed(lambda: torch.index_select(big.view(-1, 16), 0, idx // 16, out=gat), flush=flush), 2 * gat.numel() * 4)
     if args.what in ("raft", "all"):
         for (B, C, H, W) in ((8, 256, 48, 156), (1, 256, 80, 160), (1, 256, 136, 240)):
             torch.manual_seed(0)
