@@ -9,6 +9,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from nndepth_b200.engine import StereoEngine  # noqa: E402
 from nndepth_b200.raft_stereo import BaseRAFTStereo  # noqa: E402
 
+torch.backends.cudnn.allow_tf32 = "--conv-tf32" in sys.argv
+torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32
 torch.manual_seed(0)
 channels_last = "--channels-last" in sys.argv
 model = BaseRAFTStereo(iters=32).eval()
@@ -23,4 +25,4 @@ torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     engine.infer_device(left, right)
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=90))
+print(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=45, max_name_column_width=100))
