@@ -327,3 +327,25 @@ def test_edge_cases_and_errors():
     # gradients are refused, not silently dropped
     with pytest.raises(RuntimeError, match="inference-only"):
         nb.CorrBlock1D(f.clone().requires_grad_(True), f)
+
+
+def test_config5_row_bands_equal_full_volume():
+    """BASELINE config 5 (1080x1920 -> features 136x240): 8 row bands, built and looked up independently
+    (one per GPU in the sharded run), reproduce the unsharded pyramid and lookup bit for bit."""
+    import nndepth_b200 as nb
+    from nndepth_b200.engine import shard_range
+    torch.manual_seed(5)
+    B, C, H, W = 1, 256, 136, 240
+    f1 = torch.randn(B, C, H, W, device="cuda")
+    f2 = torch.randn(B, C, H, W, device="cuda")
+    coords = (torch.arange(W, device="cuda").float().view(1, 1, 1, W).repeat(B, 1, H, 1)
+              - torch.rand(B, 1, H, W, device="cuda") * 60)
+    full = nb.CorrBlock1D(f1, f2, 4, 4)
+    full_out = full(coords)
+    full_pyr = [p.reshape(B, H, W, -1) for p in full.corr_pyramid[:4]]
+    for rank in range(8):
+        h0, h1 = shard_range(H, rank, 8)
+        band = nb.CorrBlock1D(f1[:, :, h0:h1].contiguous(), f2[:, :, h0:h1].contiguous(), 4, 4)
+        for l, p in enumerate(band.corr_pyramid[:4]):
+            assert torch.equal(p.reshape(B, h1 - h0, W, -1), full_pyr[l][:, h0:h1])
+        assert torch.equal(band(coords[:, :, h0:h1].contiguous()), full_out[:, :, h0:h1])
