@@ -385,7 +385,7 @@ agcl_cl_kernel(const float* __restrict__ L, const float* __restrict__ R, const f
     for (int j = 0; j < CL_MAX_CHUNKS; ++j)
       lv[j] = (j < n_chunks && 4 * (sl + 8 * j) < cg) ? ldg_f4(lp + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
 
-#pragma unroll 3
+#pragma unroll(MODE == 1 ? 9 : 3)
     for (int k = 0; k < AGCL_TAPS; ++k) {
       const WarpFootprint f = fp[warp][k];
       float acc = 0.f;
