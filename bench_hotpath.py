@@ -125,6 +125,14 @@ def cfg3(skip_cpu):
             out["gpu_us"][f"offset_{tag}_{H}x{W}"] = gpu_us(lambda: a(flow, offs, small, False), reps=8)
             out["gpu_us"][f"iter_{tag}_{H}x{W}"] = gpu_us(lambda: a(flow, None, small, True), reps=8)
         out["gpu_us"][f"staging_nhwc_one_map_{H}x{W}"] = gpu_us(lambda: nb.AGCL(f1, f2)._nhwc(f1), reps=8)
+        if (H, W) == (90, 160):
+            # a disparity-like field (smooth in x and y) instead of white noise: neighbouring pixels then
+            # gather neighbouring corner vectors, which is what the cascade actually feeds the layer
+            yy, xx = torch.meshgrid(torch.arange(H, device="cuda").float(), torch.arange(W, device="cuda").float(), indexing="ij")
+            smooth = torch.stack([-(8 + 6 * torch.sin(xx / 23) * torch.cos(yy / 17)), 0.3 * torch.sin(yy / 9)], 0)
+            smooth = smooth[None].repeat(N, 1, 1, 1).contiguous()
+            out["gpu_us"]["offset_1x9_90x160_smooth_flow"] = gpu_us(lambda: a(smooth, offs, False, False), reps=8)
+            out["gpu_us"]["iter_1x9_90x160_smooth_flow"] = gpu_us(lambda: a(smooth, None, False, True), reps=8)
     us = out["gpu_us"]["offset_1x9_90x160"]
     out["value"] = 1e6 / us
     out["roofline"] = roof("agcl_cl_kernel<0> (offset mode, 90x160)", N * 90 * 160 * 2272, us)

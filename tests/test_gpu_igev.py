@@ -140,3 +140,34 @@ def test_config4_shapes_properties():
     d = torch.arange(W, device="cuda").float().view(1, -1, 1, 1)
     ref_sa = -(torch.softmax(z.double(), 1) * d).sum(1, keepdim=True).float()
     assert (nb.soft_argmin(z) - ref_sa).abs().max().item() <= SOFTARGMIN_ATOL
+
+
+@pytest.mark.parametrize("shape,levels", [((1, 64, 3, 20), 2), ((1, 64, 2, 24), 2), ((2, 64, 2, 32), 3), ((1, 64, 2, 12), 1)])
+def test_constructor_and_lookup_vs_oracle(shape, levels):
+    """Both storage layouts against the oracle: W2 = 20 / 12 are not multiples of 8 -> reference row layout and
+    the generic kernels; W2 = 24 / 32 -> interleaved pyramids with fewer than four levels."""
+    import nndepth_b200 as nb
+    rng = np.random.default_rng(11)
+    B, C, H, W = shape
+    G = 8
+    f1 = rng.standard_normal(shape, dtype=np.float32)
+    f2 = rng.standard_normal(shape, dtype=np.float32)
+
+    def reg_np(vol):
+        return np.tanh(vol) * 0.5 + 0.25
+
+    cv = nb.GeometryAwareCostVolume(dev(f1), dev(f2), [], lambda vol, feats: torch.tanh(vol) * 0.5 + 0.25, levels, 4, G)
+    assert cv._interleaved == (W % 8 == 0)
+    vol = oi.groupwise_volume(f1, f2, G)
+    feat_pyr, geo_pyr = oi.volume_pyramids(vol, reg_np(vol.transpose(0, 1, 4, 2, 3)), levels)
+    scale = np.abs(vol).max()
+    for l in range(levels + 1):
+        np.testing.assert_allclose(cv.feat_corr_cv[l].reshape(feat_pyr[l].shape).cpu().numpy(), feat_pyr[l],
+                                   rtol=VOLUME_RTOL, atol=VOLUME_RTOL * scale)
+        np.testing.assert_allclose(cv.geo_aware_cv[l].reshape(geo_pyr[l].shape).cpu().numpy(), geo_pyr[l],
+                                   rtol=1e-4, atol=1e-5 * scale)
+    coords = (np.broadcast_to(np.arange(W, dtype=np.float32), (B, 1, H, W)) - rng.uniform(-3, 9, (B, 1, H, W))).astype(np.float32)
+    same = nb.GeometryAwareCostVolume.from_pyramids(feat_pyr[:levels], geo_pyr[:levels], B, H, levels, 4, G)
+    np.testing.assert_array_equal(same(dev(coords)).cpu().numpy(), oi.gev_lookup(feat_pyr, geo_pyr, coords, levels, 4, G))
+    got = cv(dev(coords)).cpu().numpy()
+    np.testing.assert_allclose(got, oi.gev_lookup(feat_pyr, geo_pyr, coords, levels, 4, G), rtol=1e-4, atol=1e-4 * scale)
