@@ -163,6 +163,18 @@ nnd_status nnd_agcl_iter_nhwc(const float* fmap1_nhwc, const float* fmap2_nhwc, 
                               int C, int H, int W, int small_patch, float* warped_ws, float* out,
                               nnd_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Convex upsampling of the coarse disparity by the learned 9-neighbour mask, one pass.
+ * Replaces RAFTStereo.convex_upsample nndepth/models/raft_stereo/model.py:93-105 (identical code in
+ * cre_stereo/model.py:110-122 and igev_stereo/model.py:103-115): softmax over the 9 neighbours,
+ * F.unfold(rate * flow, 3x3, padding 1), multiply, sum, pixel shuffle.
+ *   flow (N,1,H,W), mask (N, 9*rate*rate, H, W) -> out (N, 1, rate*H, rate*W); rate in {2, 4, 8}.
+ *   mask_scale multiplies the mask logits first: pass 0.25 to fold the update block's `0.25 * mask`
+ *   (blocks/update_block.py:110) into this pass, 1.0 for an already scaled mask.
+ * ---------------------------------------------------------------------------------------------- */
+nnd_status nnd_convex_upsample(const float* flow, const float* mask, int N, int H, int W, int rate,
+                               float mask_scale, float* out, nnd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,9 +8,10 @@ from .corr import (CorrBlock1D, GroupCorrBlock1D, linear_sampler, lookup_indices
                    set_volume_precision, get_volume_precision)
 from .igev import GeometryAwareCostVolume, soft_argmin  # noqa: F401
 from .agcl import AGCL  # noqa: F401
+from .upsample import convex_upsample  # noqa: F401
 
 __all__ = [
     "CorrBlock1D", "GroupCorrBlock1D", "linear_sampler", "lookup_indices", "set_volume_precision",
-    "get_volume_precision", "GeometryAwareCostVolume", "soft_argmin", "AGCL", "NNDepthError", "build_library",
+    "get_volume_precision", "GeometryAwareCostVolume", "soft_argmin", "AGCL", "convex_upsample", "NNDepthError", "build_library",
     "load_library",
 ]

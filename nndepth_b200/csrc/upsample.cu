@@ -1,0 +1,93 @@
+// Convex upsampling of the disparity field (sm_100a).
+//
+//   nnd_convex_upsample   RAFTStereo.convex_upsample   nndepth/models/raft_stereo/model.py:93-105
+//                         (same code: cre_stereo/model.py:110-122, igev_stereo/model.py:103-115)
+//
+// Reference chain per GRU iteration: view -> softmax over the 9 neighbours -> F.unfold(rate * flow, 3x3,
+// padding 1) -> multiply -> sum -> permute -> reshape, i.e. five passes over a (N, 9*rate^2, H, W) tensor
+// (138 MB at KITTI, batch 8) plus the update block's separate `0.25 *` pass.  Here: one pass.
+//   out[n, 0, rate*h + i, rate*w + j] = sum_k softmax_k(s * mask[n, k*rate^2 + i*rate + j, h, w])
+//                                              * rate * flow[n, 0, h + k/3 - 1, w + k%3 - 1]   (zero padded)
+// Thread = (coarse pixel, sub-row i): 9*rate coalesced mask loads (lanes run along w, every load is a full
+// 128-byte row segment of one channel plane), a 9-way softmax per output, `rate` consecutive outputs written
+// as 16-byte stores.  Pure streaming: 153 MB per launch at the bench shape.
+#include <float.h>
+
+#include "common.cuh"
+
+namespace nnd {
+
+template <int RATE>
+__global__ void __launch_bounds__(32 * RATE)
+convex_upsample_kernel(const float* __restrict__ flow, const float* __restrict__ mask, int H, int W, float mask_scale,
+                       float* __restrict__ out) {
+  const int lane = threadIdx.x, i = threadIdx.y;
+  const long long hw = static_cast<long long>(H) * W;
+  const long long p = static_cast<long long>(blockIdx.x) * 32 + lane;
+  const long long n = blockIdx.y;
+  if (p >= hw) return;
+  const int h = static_cast<int>(p / W), w = static_cast<int>(p - static_cast<long long>(h) * W);
+
+  // the 3x3 neighbourhood of rate * flow, zero padded (F.unfold(..., padding=1))
+  float nb[9];
+  const float* fl = flow + n * hw;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const int hh = h + k / 3 - 1, ww = w + k % 3 - 1;
+    nb[k] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __fmul_rn(static_cast<float>(RATE), __ldg(fl + static_cast<long long>(hh) * W + ww)) : 0.f;
+  }
+  const float* mp = mask + (n * 9 * RATE * RATE + i * RATE) * hw + p;
+  float res[RATE];
+#pragma unroll
+  for (int j = 0; j < RATE; ++j) {
+    float x[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) x[k] = __ldcs(mp + (static_cast<long long>(k) * RATE * RATE + j) * hw) * mask_scale;
+    float m = x[0];
+#pragma unroll
+    for (int k = 1; k < 9; ++k) m = fmaxf(m, x[k]);
+    float s = 0.f, acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const float e = __expf(x[k] - m);
+      s += e;
+      acc = fmaf(e, nb[k], acc);
+    }
+    res[j] = acc / s;
+  }
+  float* op = out + (n * RATE * H + static_cast<long long>(RATE) * h + i) * (static_cast<long long>(RATE) * W) + static_cast<long long>(RATE) * w;
+  if (RATE % 4 == 0) {
+#pragma unroll
+    for (int j = 0; j < RATE; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(res[j], res[j + 1], res[j + 2], res[j + 3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < RATE; ++j) op[j] = res[j];
+  }
+}
+
+}  // namespace nnd
+
+extern "C" {
+
+nnd_status nnd_convex_upsample(const float* flow, const float* mask, int N, int H, int W, int rate, float mask_scale,
+                               float* out, nnd_stream_t stream_) {
+  using namespace nnd;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  NND_REQUIRE(flow && mask && out, "convex_upsample: null pointer");
+  NND_REQUIRE(N > 0 && H > 0 && W > 0, "convex_upsample: N, H, W must be positive");
+  NND_REQUIRE(N <= 65535, "convex_upsample: batch %d exceeds the grid limit", N);
+  NND_REQUIRE(rate == 2 || rate == 4 || rate == 8, "convex_upsample: rate %d unsupported (2, 4, 8)", rate);
+  NND_REQUIRE(rate % 4 != 0 || aligned16(out), "convex_upsample: output must be 16-byte aligned");
+  const long long hw = static_cast<long long>(H) * W;
+  dim3 grid(static_cast<unsigned>((hw + 31) / 32), N);
+  if (rate == 8) {
+    convex_upsample_kernel<8><<<grid, dim3(32, 8), 0, stream>>>(flow, mask, H, W, mask_scale, out);
+  } else if (rate == 4) {
+    convex_upsample_kernel<4><<<grid, dim3(32, 4), 0, stream>>>(flow, mask, H, W, mask_scale, out);
+  } else {
+    convex_upsample_kernel<2><<<grid, dim3(32, 2), 0, stream>>>(flow, mask, H, W, mask_scale, out);
+  }
+  return check_launch("convex_upsample_kernel");
+}
+
+}  // extern "C"

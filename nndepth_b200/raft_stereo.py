@@ -20,6 +20,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .corr import CorrBlock1D
+from .upsample import convex_upsample as fused_convex_upsample
 
 
 def _norm(kind, planes):
@@ -169,10 +170,13 @@ class BasicUpdateBlock(nn.Module):
         self.mask = nn.Sequential(nn.Conv2d(hidden_dim, hidden_dim * 2, 3, padding=1), nn.ReLU(inplace=True),
                                   nn.Conv2d(hidden_dim * 2, sps * 9, 1))
 
-    def forward(self, net, inp, corr, flow):
+    def forward(self, net, inp, corr, flow, raw_mask=False):
+        """``raw_mask=True`` returns the mask logits without the reference's ``0.25 *`` (update_block.py:110):
+        the fused upsampling kernel applies that scale itself, saving a pass over the (N,576,H,W) tensor."""
         motion = self.encoder(flow, corr)
         net = self.gru(net, torch.cat((inp, motion), dim=1))
-        return net, 0.25 * self.mask(net), self.flow_head(net)
+        mask = self.mask(net)
+        return net, (mask if raw_mask else 0.25 * mask), self.flow_head(net)
 
 
 def convex_upsample(flow, mask, rate=8):
@@ -247,10 +251,18 @@ class RAFTStereo(nn.Module):
         for it in range(self.iters):
             coords1 = coords1.detach()
             sampled = corr(coords1)
-            net, mask, delta = self.update_block(net, inp, sampled, coords1 - org_coords)
+            # on the GPU the convex upsampling is one fused kernel (softmax + unfold + weighted sum + pixel
+            # shuffle, with the update block's 0.25 mask scale folded in); the torch chain below is the
+            # reference's own, kept for the CPU baseline leg (corr_fn = oracle) only
+            fused = coords1.is_cuda and fnet_ds in (2, 4, 8) and not torch.is_grad_enabled()
+            net, mask, delta = self.update_block(net, inp, sampled, coords1 - org_coords, raw_mask=fused)
             coords1 = coords1 + delta
             if not self.final_only or it == self.iters - 1:
-                outputs.append({"up_disp": self.convex_upsample(coords1 - org_coords, mask, rate=fnet_ds)})
+                if fused:
+                    up = fused_convex_upsample(coords1 - org_coords, mask, rate=fnet_ds, mask_scale=0.25)
+                else:
+                    up = self.convex_upsample(coords1 - org_coords, mask, rate=fnet_ds)
+                outputs.append({"up_disp": up})
         return outputs
 
     # ---- CUDA-graph replay of the whole forward (inference) ---------------------------------------

@@ -1,0 +1,30 @@
+"""Convex upsampling of the coarse disparity on the sm_100a kernel -- one pass instead of the reference's
+softmax / unfold / multiply / sum / permute chain (``nndepth/models/raft_stereo/model.py:93-105``; the same
+code serves CREStereo ``cre_stereo/model.py:110-122`` and IGEV ``igev_stereo/model.py:103-115``).
+"""
+import torch
+
+from . import _lib
+
+
+def convex_upsample(flow, mask, rate=8, mask_scale=1.0):
+    """``flow (N,1,H,W)``, ``mask (N, 9*rate*rate, H, W)`` -> ``(N, 1, rate*H, rate*W)``.
+
+    ``mask_scale`` multiplies the mask logits inside the kernel: ``0.25`` folds the update block's
+    ``0.25 * mask`` (``blocks/update_block.py:110``) into the same pass (exact: a power of two).
+    """
+    flow = _lib.as_cuda_f32(flow, "flow")
+    mask = _lib.as_cuda_f32(mask, "mask")
+    if flow.dim() != 4 or flow.shape[1] != 1:
+        raise RuntimeError(f"flow must be (N, 1, H, W), got {tuple(flow.shape)}")
+    N, _, H, W = flow.shape
+    if tuple(mask.shape) != (N, 9 * rate * rate, H, W):
+        raise RuntimeError(f"mask must be (N, 9*rate*rate, H, W) = {(N, 9 * rate * rate, H, W)}, got {tuple(mask.shape)}")
+    out = torch.empty(N, 1, rate * H, rate * W, dtype=torch.float32, device=flow.device)
+    with torch.cuda.device(flow.device):
+        _lib.check(
+            _lib.load().nnd_convex_upsample(_lib.ptr(flow), _lib.ptr(mask), N, H, W, int(rate), float(mask_scale),
+                                            _lib.ptr(out), _lib.stream_ptr(flow)),
+            "nnd_convex_upsample",
+        )
+    return out

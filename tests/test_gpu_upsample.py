@@ -1,0 +1,53 @@
+"""GPU parity of the fused convex upsampling vs the reference's torch chain (raft_stereo/model.py:93-105)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def reference_chain(flow, mask, rate):
+    """Verbatim op chain of the reference (softmax / unfold / mul / sum / permute / reshape), on the device."""
+    import torch.nn.functional as F
+    N, _, H, W = flow.shape
+    mask = mask.view(N, 1, 9, rate, rate, H, W)
+    mask = torch.softmax(mask, dim=2)
+    up = F.unfold(rate * flow, (3, 3), padding=1).view(N, 1, 9, 1, 1, H, W)
+    up = torch.sum(mask * up, dim=2).permute(0, 1, 4, 2, 5, 3)
+    return up.reshape(N, 1, rate * H, rate * W)
+
+
+@pytest.mark.parametrize("shape,rate", [((2, 6, 10), 8), ((1, 48, 156), 8), ((3, 5, 33), 4), ((1, 1, 1), 8), ((2, 7, 9), 2)])
+def test_matches_reference_chain(shape, rate):
+    import nndepth_b200 as nb
+    N, H, W = shape
+    torch.manual_seed(N * H + W)
+    flow = torch.randn(N, 1, H, W, device="cuda") * 20
+    mask = torch.randn(N, 9 * rate * rate, H, W, device="cuda") * 3
+    got = nb.convex_upsample(flow, mask, rate)
+    ref = reference_chain(flow.double(), mask.double(), rate).float()
+    assert got.shape == ref.shape == (N, 1, rate * H, rate * W)
+    assert (got - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item())
+    # the folded 0.25 scale is exact (power of two): identical bits to scaling the mask first
+    assert torch.equal(nb.convex_upsample(flow, mask, rate, mask_scale=0.25), nb.convex_upsample(flow, 0.25 * mask, rate))
+
+
+def test_convexity_and_constant_field():
+    """A convex combination of a constant field is that constant (times rate), whatever the mask."""
+    import nndepth_b200 as nb
+    flow = torch.full((1, 1, 9, 11), -3.5, device="cuda")
+    mask = torch.randn(1, 576, 9, 11, device="cuda") * 5
+    out = nb.convex_upsample(flow, mask, 8)
+    inner = out[..., 8:-8, 8:-8]                      # away from the zero-padded border
+    assert (inner + 28.0).abs().max().item() <= 1e-5 * 28
+    assert out.min().item() >= -28.0 - 1e-4 and out.max().item() <= 1e-6     # border mixes in zeros, never overshoots
+
+
+def test_errors():
+    import nndepth_b200 as nb
+    flow = torch.zeros(1, 1, 4, 4, device="cuda")
+    with pytest.raises(RuntimeError, match="mask"):
+        nb.convex_upsample(flow, torch.zeros(1, 9 * 64, 4, 5, device="cuda"), 8)
+    with pytest.raises(nb.NNDepthError, match="rate"):
+        nb.convex_upsample(flow, torch.zeros(1, 81, 4, 4, device="cuda"), 3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        nb.convex_upsample(flow.cpu(), torch.zeros(1, 576, 4, 4), 8)
