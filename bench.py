@@ -241,15 +241,16 @@ def run_ours(args):
     nb.load_library()
     if args.volume_precision:
         nb.set_volume_precision(args.volume_precision)
-    # Parity first: the reference computes in fp32 (CPU).  With cuDNN's TF32 convolutions the final
-    # disparity drifts 0.015 px from the reference (> the 0.01 px bar, tools/exp_epe.py), with fp32
-    # convolutions 0.0002 px -- so the headline runs the dense layers in strict fp32; --conv-tf32 is the
-    # faster, out-of-tolerance variant, reported separately and never as `value`.
-    torch.backends.cudnn.allow_tf32 = bool(args.conv_tf32)
-    torch.backends.cuda.matmul.allow_tf32 = bool(args.conv_tf32)
+    # Parity first: the reference computes in fp32 (CPU) and the bar is 0.01 px of final end-point error.
+    # Measured on the KITTI / 32-iteration golden (tools/exp_epe_modules.py, tests/test_gpu_raft_model.py):
+    # all cuDNN convolutions in TF32 drift 0.0147 px (outside the bar); the drift comes from the ConvGRU
+    # recurrence.  "mixed" keeps the ConvGRU in fp32 and lets the encoder, motion encoder, flow and mask heads
+    # use TF32 tensor cores: 0.0035 px.  "fp32" (0.0002 px) and "tf32" are selectable; `value` is never
+    # measured in the out-of-tolerance "tf32" mode unless asked for explicitly.
 
     torch.manual_seed(0)
     model = BaseRAFTStereo(iters=ITERS).eval()
+    model.dense_precision = args.dense_precision
     engine = StereoEngine(model, device=device, use_cuda_graph=not args.no_graph)
     gen = torch.Generator().manual_seed(1 + rank)
     host_l = (torch.rand((PAIRS_PER_GPU, 3) + IMAGE_HW, generator=gen) * 2 - 1).pin_memory()
@@ -342,8 +343,11 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": warm, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None,
-            "dtype": "f32 (volume operands %s; cuDNN convs allow_tf32=%s)" % (nb.get_volume_precision(),
-                                                                            torch.backends.cudnn.allow_tf32),
+            "dtype": "f32 (correlation volume: %s operands rounded to nearest, fp32 accumulate; dense layers: %s)" % (
+                nb.get_volume_precision(), {"fp32": "cuDNN fp32", "tf32": "cuDNN TF32",
+                                            "mixed": "ConvGRU cuDNN fp32, other convolutions cuDNN TF32"}[args.dense_precision]),
+            "parity": {"final_epe_px_vs_reference": {"fp32": 0.00016, "mixed": 0.0035, "tf32": 0.0147}[args.dense_precision],
+                       "bar_px": 0.01, "source": "tests/test_gpu_raft_model.py::test_kitti_32_iterations, tools/exp_epe_modules.py"},
             "data": "synthetic", "config": workload_config(world), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": 2 * host_l.numel() * 4, "d2h_bytes_per_step": PAIRS_PER_GPU * IMAGE_HW[0] * IMAGE_HW[1] * 4,
@@ -384,8 +388,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--volume-precision", default=None, choices=["fp32", "tf32"])
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--conv-tf32", action="store_true",
-                    help="let cuDNN run the dense layers in TF32 (faster, 0.015 px off the reference: outside the bar)")
+    ap.add_argument("--dense-precision", default="mixed", choices=["fp32", "mixed", "tf32"],
+                    help="cuDNN layers: fp32 everywhere, fp32 ConvGRU + TF32 elsewhere (default, 0.0035 px EPE), or TF32 "
+                         "everywhere (0.0147 px: outside the 0.01 px bar)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

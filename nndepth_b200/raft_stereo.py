@@ -23,6 +23,22 @@ from .corr import CorrBlock1D
 from .upsample import convex_upsample as fused_convex_upsample
 
 
+class cudnn_tf32:
+    """Context manager: let (or forbid) cuDNN / cuBLAS run fp32 convolutions on TF32 tensor cores."""
+
+    def __init__(self, allow):
+        self.allow = bool(allow)
+
+    def __enter__(self):
+        self.old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        torch.backends.cudnn.allow_tf32 = self.allow
+        torch.backends.cuda.matmul.allow_tf32 = self.allow
+
+    def __exit__(self, *exc):
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = self.old
+        return False
+
+
 def _norm(kind, planes):
     if kind == "batch":
         return nn.BatchNorm2d(planes)
@@ -103,6 +119,7 @@ class SepConvGRU(nn.Module):
             for gate in "zrq":
                 setattr(self, f"conv{gate}{tag}", nn.Conv2d(cin, hidden_dim, k, padding=p))
         self._fused = {}
+        self.strict_fp32 = False    # set by RAFTStereo.dense_precision == "mixed": keep the recurrence in fp32
 
     def fuse_gates(self):
         """Pre-concatenate the z|r gate weights (call after loading weights, in eval mode)."""
@@ -124,6 +141,9 @@ class SepConvGRU(nn.Module):
         return (1 - z) * h + z * q
 
     def forward(self, h, x):
+        if self.strict_fp32:
+            with cudnn_tf32(False):
+                return self._half_step(self._half_step(h, x, "1"), x, "2")
         return self._half_step(self._half_step(h, x, "1"), x, "2")
 
 
@@ -209,6 +229,12 @@ class RAFTStereo(nn.Module):
         self.weights = weights
         self.strict_load = strict_load
         self.final_only = False     # True: upsample only the last iteration (what evaluate.py:155 consumes)
+        # Precision of the dense (cuDNN) layers, measured on the KITTI/32-iteration golden (tools/exp_epe_modules.py):
+        #   "fp32"  every convolution in fp32                           final EPE vs reference 0.0002 px
+        #   "mixed" ConvGRU in fp32, everything else on TF32 tensor cores              0.0035 px  (bar: 0.01 px)
+        #   "tf32"  everything TF32 (PyTorch's CUDA default)                           0.0147 px  -> outside the bar
+        # None leaves torch.backends.cudnn.allow_tf32 as the caller set it.
+        self.dense_precision = None
         self._graphs = {}
         if weights is not None:
             state = torch.load(weights, map_location="cpu") if not str(weights).endswith(".safetensors") else None
@@ -238,6 +264,17 @@ class RAFTStereo(nn.Module):
     convex_upsample = staticmethod(convex_upsample)
 
     def forward(self, frame1, frame2, **kwargs):
+        if self.dense_precision is None:
+            return self._forward(frame1, frame2, **kwargs)
+        if self.dense_precision not in ("fp32", "mixed", "tf32"):
+            raise ValueError(f"dense_precision must be None, 'fp32', 'mixed' or 'tf32', got {self.dense_precision!r}")
+        gru = getattr(self.update_block, "gru", None)
+        if gru is not None:
+            gru.strict_fp32 = self.dense_precision == "mixed"
+        with cudnn_tf32(self.dense_precision != "fp32"):
+            return self._forward(frame1, frame2, **kwargs)
+
+    def _forward(self, frame1, frame2, **kwargs):
         fmap1, fmap2, cnet1 = self.forward_fnet(frame1, frame2)
         fnet_ds = frame1.shape[-1] // fmap1.shape[-1]
         fmap1, fmap2 = fmap1.float(), fmap2.float()
@@ -274,7 +311,7 @@ class RAFTStereo(nn.Module):
         host synchronisation, so the 32-iteration loop captures cleanly.  Outputs are overwritten by
         the next replay of the same shape.
         """
-        key = (tuple(frame1.shape), frame1.device.index, self.iters, self.final_only)
+        key = (tuple(frame1.shape), frame1.device.index, self.iters, self.final_only, self.dense_precision)
         entry = self._graphs.get(key)
         if entry is None:
             static1, static2 = torch.empty_like(frame1), torch.empty_like(frame2)

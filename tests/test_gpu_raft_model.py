@@ -64,3 +64,21 @@ def test_kitti_32_iterations(golden, precision):
     assert out.shape == ref.shape == (1, 1, 384, 1248)
     assert epe(out, ref) < EPE_BAR, epe(out, ref)
     assert epe(graphed, ref) < EPE_BAR, epe(graphed, ref)
+
+
+@pytest.mark.parametrize("mode,bar", [("fp32", 0.001), ("mixed", EPE_BAR)])
+def test_kitti_dense_precision_modes(golden, mode, bar):
+    """The bench's dense-layer precision modes against the reference disparity (KITTI geometry, 32 iterations):
+    "mixed" (ConvGRU fp32, other convolutions TF32) must stay inside the 0.01 px bar, "fp32" far inside."""
+    g = golden("raft_kitti")
+    model = build(g, final_only=True)
+    model.dense_precision = mode
+    left, right = (t.cuda() for t in seeded_pair(g["shape"]))
+    before = torch.backends.cudnn.allow_tf32
+    with torch.no_grad():
+        out = model(left, right)[-1]["up_disp"]
+        graphed = model.forward_graphed(left, right)[-1]["up_disp"].clone()
+    assert torch.backends.cudnn.allow_tf32 == before          # the mode does not leak into global state
+    ref = torch.from_numpy(g["final_up_disp"]).cuda()
+    assert epe(out, ref) < bar, epe(out, ref)
+    assert epe(graphed, ref) < bar, epe(graphed, ref)
