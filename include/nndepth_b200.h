@@ -175,6 +175,14 @@ nnd_status nnd_agcl_iter_nhwc(const float* fmap1_nhwc, const float* fmap2_nhwc, 
 nnd_status nnd_convex_upsample(const float* flow, const float* mask, int N, int H, int W, int rate,
                                float mask_scale, float* out, nnd_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Error-compensated TF32 operand split for the ConvGRU convolutions (nndepth/blocks/gru.py:5-37), the
+ * one dense block whose TF32 rounding leaves the 0.01 px parity bar: x = hi + lo with hi = RN_tf32(x).
+ *   x (N, C, H*W) -> out (N, 3C, H*W) = [hi ; lo ; hi]; convolved against weights [w_hi ; w_hi ; w_lo]
+ *   on TF32 tensor cores this equals the fp32 convolution to O(2^-22).
+ * ---------------------------------------------------------------------------------------------- */
+nnd_status nnd_split_tf32(const float* x, int N, int C, long long hw, float* out, nnd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -119,7 +119,10 @@ class SepConvGRU(nn.Module):
             for gate in "zrq":
                 setattr(self, f"conv{gate}{tag}", nn.Conv2d(cin, hidden_dim, k, padding=p))
         self._fused = {}
-        self.strict_fp32 = False    # set by RAFTStereo.dense_precision == "mixed": keep the recurrence in fp32
+        # set by RAFTStereo.dense_precision: "fp32" = cuDNN fp32 convolutions for the recurrence ("mixed"),
+        # "3xtf32" = error-compensated TF32 on tensor cores ("mixed3x"), None = whatever the caller's flags say
+        self.recurrence = None
+        self._split_w = {}
 
     def fuse_gates(self):
         """Pre-concatenate the z|r gate weights (call after loading weights, in eval mode)."""
@@ -140,8 +143,46 @@ class SepConvGRU(nn.Module):
         q = torch.tanh(getattr(self, f"convq{tag}")(torch.cat([r * h, x], dim=1)))
         return (1 - z) * h + z * q
 
+    # ---- error-compensated TF32 ("3xTF32"): conv(x, w) = conv([hi; lo; hi], [w_hi; w_hi; w_lo]) --------------
+    @staticmethod
+    def _rn_tf32(t):
+        return ((t.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+    def _split_weights(self, tag):
+        """[w_hi ; w_hi ; w_lo] along the input-channel axis for the (z|r) and q convolutions of one half-step."""
+        if tag not in self._split_w:
+            cz, cr, cq = (getattr(self, f"conv{g}{tag}") for g in "zrq")
+            out = []
+            for w, b in ((torch.cat([cz.weight, cr.weight], 0), torch.cat([cz.bias, cr.bias], 0)), (cq.weight, cq.bias)):
+                w = w.detach().float()
+                hi = self._rn_tf32(w)
+                out.append((torch.cat([hi, hi, w - hi], 1).contiguous(), b.detach().contiguous()))
+            self._split_w[tag] = (out[0], out[1], cz.padding)
+        return self._split_w[tag]
+
+    @staticmethod
+    def _split_act(t):
+        """(N, C, H, W) -> (N, 3C, H, W) = [hi ; lo ; hi] in one pass (nnd_split_tf32)."""
+        from . import _lib
+        t = t.contiguous()
+        N, C, H, W = t.shape
+        out = torch.empty(N, 3 * C, H, W, dtype=torch.float32, device=t.device)
+        with torch.cuda.device(t.device):
+            _lib.check(_lib.load().nnd_split_tf32(_lib.ptr(t), N, C, H * W, _lib.ptr(out), _lib.stream_ptr(t)),
+                       "nnd_split_tf32")
+        return out
+
+    def _half_step_3x(self, h, x, tag):
+        (wzr, bzr), (wq, bq), pad = self._split_weights(tag)
+        z, r = torch.sigmoid(F.conv2d(self._split_act(torch.cat([h, x], dim=1)), wzr, bzr, padding=pad)).chunk(2, dim=1)
+        q = torch.tanh(F.conv2d(self._split_act(torch.cat([r * h, x], dim=1)), wq, bq, padding=pad))
+        return (1 - z) * h + z * q
+
     def forward(self, h, x):
-        if self.strict_fp32:
+        if self.recurrence == "3xtf32" and h.is_cuda:
+            with cudnn_tf32(True):
+                return self._half_step_3x(self._half_step_3x(h, x, "1"), x, "2")
+        if self.recurrence == "fp32":
             with cudnn_tf32(False):
                 return self._half_step(self._half_step(h, x, "1"), x, "2")
         return self._half_step(self._half_step(h, x, "1"), x, "2")
@@ -231,7 +272,8 @@ class RAFTStereo(nn.Module):
         self.final_only = False     # True: upsample only the last iteration (what evaluate.py:155 consumes)
         # Precision of the dense (cuDNN) layers, measured on the KITTI/32-iteration golden (tools/exp_epe_modules.py):
         #   "fp32"  every convolution in fp32                           final EPE vs reference 0.0002 px
-        #   "mixed" ConvGRU in fp32, everything else on TF32 tensor cores              0.0035 px  (bar: 0.01 px)
+        #   "mixed" ConvGRU in fp32, everything else on TF32 tensor cores              0.0021 px  (bar: 0.01 px)
+        #   "mixed3x" as "mixed", the ConvGRU as error-compensated 3xTF32 on tensor cores 0.0020 px, 2x faster
         #   "tf32"  everything TF32 (PyTorch's CUDA default)                           0.0147 px  -> outside the bar
         # None leaves torch.backends.cudnn.allow_tf32 as the caller set it.
         self.dense_precision = None
@@ -266,11 +308,12 @@ class RAFTStereo(nn.Module):
     def forward(self, frame1, frame2, **kwargs):
         if self.dense_precision is None:
             return self._forward(frame1, frame2, **kwargs)
-        if self.dense_precision not in ("fp32", "mixed", "tf32"):
-            raise ValueError(f"dense_precision must be None, 'fp32', 'mixed' or 'tf32', got {self.dense_precision!r}")
+        if self.dense_precision not in ("fp32", "mixed", "mixed3x", "tf32"):
+            raise ValueError("dense_precision must be None, 'fp32', 'mixed', 'mixed3x' or 'tf32', "
+                             f"got {self.dense_precision!r}")
         gru = getattr(self.update_block, "gru", None)
         if gru is not None:
-            gru.strict_fp32 = self.dense_precision == "mixed"
+            gru.recurrence = {"mixed": "fp32", "mixed3x": "3xtf32"}.get(self.dense_precision)
         with cudnn_tf32(self.dense_precision != "fp32"):
             return self._forward(frame1, frame2, **kwargs)
 

@@ -66,7 +66,7 @@ def test_kitti_32_iterations(golden, precision):
     assert epe(graphed, ref) < EPE_BAR, epe(graphed, ref)
 
 
-@pytest.mark.parametrize("mode,bar", [("fp32", 0.001), ("mixed", EPE_BAR)])
+@pytest.mark.parametrize("mode,bar", [("fp32", 0.001), ("mixed", EPE_BAR), ("mixed3x", EPE_BAR)])
 def test_kitti_dense_precision_modes(golden, mode, bar):
     """The bench's dense-layer precision modes against the reference disparity (KITTI geometry, 32 iterations):
     "mixed" (ConvGRU fp32, other convolutions TF32) must stay inside the 0.01 px bar, "fp32" far inside."""
