@@ -89,6 +89,17 @@ nnd_status nnd_corr1d_lookup(const float* const* level, const int* width, const 
                              const float* coords, int B, int H, int W1, int num_levels, int radius,
                              float* out, nnd_stream_t stream);
 
+/* The same lookup fused with the motion encoder's first layer, `F.relu(convc1(corr))` with convc1 a 1x1
+ * convolution (nndepth/blocks/update_block.py:51,58): the (B, L*9, H, W) lookup tensor stays on chip.
+ *   weight (L*9, c_out) row-major (= convc1.weight[:, :, 0, 0] transposed), bias (c_out) or NULL, relu 0/1;
+ *   out (B, c_out, H, W).  radius 4, 4 levels.  precision NND_PREC_FP32: fp32 FFMA; NND_PREC_TF32
+ *   (c_out <= 256): mma.sync TF32 with both operands rounded to nearest, weights resident in registers --
+ *   the precision class cuDNN gives this layer under allow_tf32. */
+nnd_status nnd_corr1d_lookup_conv1x1(const float* const* level, const int* width, const int* pitch,
+                                     const float* coords, int B, int H, int W1, int num_levels, int radius,
+                                     const float* weight, const float* bias, int c_out, int relu, int precision,
+                                     float* out, nnd_stream_t stream);
+
 /* Debug/parity twin of the lookup: writes the int32 window indices instead of values.
  *   idx0, idx1: (num_levels, B*H*W1, 2r+1) int32. */
 nnd_status nnd_corr1d_lookup_indices(const int* width, const float* coords, int B, int H, int W1,

@@ -169,6 +169,48 @@ class CorrBlock1D:
             )
         return out
 
+    @staticmethod
+    def prepare_conv1x1_weight(weight):
+        """``(c_out, K[, 1, 1])`` conv weight -> the ``(K, c_out)`` k-major copy ``lookup_conv1x1`` consumes."""
+        weight = _lib.as_cuda_f32(weight, "weight")
+        return weight.reshape(weight.shape[0], -1).t().contiguous()
+
+    def lookup_conv1x1(self, coords, weight, bias=None, relu=True, weight_t=None, precision="fp32"):
+        """``relu(conv1x1(self(coords)))`` in one launch; the ``(B, L*(2r+1), H, W)`` lookup never reaches HBM.
+
+        Fuses the lookup with the motion encoder's first layer (reference ``blocks/update_block.py:51,58``:
+        ``cor = F.relu(self.convc1(corr))``).  ``weight`` is ``(c_out, L*(2r+1))`` or the conv's
+        ``(c_out, L*(2r+1), 1, 1)``; returns ``(B, c_out, H, W)``.  Radius 4, 4 levels.  The kernel wants the
+        weights k-major: pass ``weight_t=prepare_conv1x1_weight(weight)`` to transpose once per forward
+        instead of once per call.  ``precision``: ``"fp32"`` (FFMA) or ``"tf32"`` (tensor cores, operands rounded
+        to nearest TF32 -- what cuDNN does to this layer under ``allow_tf32``).
+        """
+        if precision not in ("fp32", "tf32"):
+            raise ValueError(f"precision must be 'fp32' or 'tf32', got {precision!r}")
+        B, H, W1, _ = self._shape
+        coords = _check_coords(coords, B, H, W1)
+        T = 2 * self.radius + 1
+        if weight_t is None:
+            weight_t = self.prepare_conv1x1_weight(weight)
+        weight = _lib.require_cuda_f32(weight_t, "weight_t")
+        if weight.dim() != 2 or weight.shape[0] != self.num_levels * T:
+            raise RuntimeError(f"weight must have {self.num_levels * T} input channels, got {tuple(weight.shape)}")
+        if bias is not None:
+            bias = _lib.as_cuda_f32(bias, "bias")
+        c_out = weight.shape[1]
+        out = torch.empty(B, c_out, H, W1, dtype=torch.float32, device=coords.device)
+        with torch.cuda.device(coords.device):
+            _lib.check(
+                _lib.load().nnd_corr1d_lookup_conv1x1(self._pyr._level_ptrs, self._pyr._width_arr, self._pyr._pitch_arr,
+                                                      _lib.ptr(coords), B, H, W1, self.num_levels, self.radius,
+                                                      _lib.ptr(weight), _lib.ptr(bias) if bias is not None else None,
+                                                      c_out, 1 if relu else 0,
+                                                      _lib.PREC_TF32 if precision == "tf32" else _lib.PREC_FP32,
+                                                      _lib.ptr(out), _lib.stream_ptr(coords)),
+                "nnd_corr1d_lookup_conv1x1",
+            )
+        return out
+
     def lookup_indices(self, coords):
         """Debug/parity helper: the int32 ``(idx0, idx1)`` of every tap, each ``(L, B*H*W1, 2r+1)``."""
         B, H, W1, _ = self._shape

@@ -314,6 +314,320 @@ corr1d_lookup_lean_kernel(const __grid_constant__ LookupArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Lookup fused with the motion encoder's first layer: out = relu(W . lookup(coords) + b), W = convc1's 1x1
+// weights (blocks/update_block.py:51,58: `cor = F.relu(self.convc1(corr))`).  The (B, 36, H, W) lookup
+// tensor never reaches HBM: a block computes the 36 taps of 32 pixels into shared memory (one warp per
+// level, same arithmetic as the stand-alone kernel), then its four warps turn them into Cout channels in
+// fp32 FFMA -- thread = one pixel x Cout/4 output channels, weights read as 16-byte shared-memory
+// broadcasts -- and store 128-byte coalesced channel-plane segments.  At the KITTI shape one launch is
+// 552 MFMA and a 61 MB write: ~15 us of FFMA, hidden behind nothing else the GPU has to do here.
+// Requires num_levels * TAPS % 4 == 0 (36 for RAFT-Stereo) and num_levels == blockDim.y.
+// ------------------------------------------------------------------------------------------------
+template <int TAPS>
+__global__ void __launch_bounds__(128)
+corr1d_lookup_conv1x1_kernel(const __grid_constant__ LookupArgs a, const float* __restrict__ weight,
+                             const float* __restrict__ bias, int c_out, int relu, long long n_groups) {
+  constexpr int WINQ = 4, COLS = 4 * WINQ, STRIDE = COLS + 1;
+  constexpr int R = (TAPS - 1) / 2;
+  constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ __align__(16) float smem[];
+  const int L = blockDim.y;
+  const int K = L * TAPS;                       // lookup channels (36)
+  const int c_pad = (c_out + 3) & ~3;
+  float* wsm = smem;                            // [K][c_pad]   k-major: four output channels of one k are 16 bytes
+  float* bsm = wsm + K * c_pad;                 // [c_pad]
+  float* corr = bsm + c_pad;                    // [K][32]
+  float* wins = corr + K * 32;                  // [L][32][STRIDE]
+  const int lane = threadIdx.x, lvl = threadIdx.y;
+  const int tid = lvl * 32 + lane, nthreads = 32 * L;
+  if (c_pad == c_out && (reinterpret_cast<uintptr_t>(weight) & 15u) == 0) {
+    // 16-byte copies, eight in flight per thread (a load->store loop would serialise one L2 latency per element)
+    const int n4 = K * c_out / 4;
+    for (int base = tid; base < n4; base += 8 * nthreads) {
+      float4 t[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (base + j * nthreads < n4) t[j] = __ldg(reinterpret_cast<const float4*>(weight) + base + j * nthreads);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (base + j * nthreads < n4) reinterpret_cast<float4*>(wsm)[base + j * nthreads] = t[j];
+    }
+  } else {
+    for (int i = tid; i < K * c_pad; i += nthreads) {
+      const int k = i / c_pad, co = i - k * c_pad;
+      wsm[i] = co < c_out ? __ldg(weight + static_cast<long long>(k) * c_out + co) : 0.f;
+    }
+  }
+  for (int i = tid; i < c_pad; i += nthreads) bsm[i] = (bias && i < c_out) ? __ldg(bias + i) : 0.f;
+
+  float* win = wins + lvl * (32 * STRIDE);
+  // persistent blocks: the weights are staged once, pixel groups are dealt round-robin
+  const int groups_per_image = (a.hw + 31) / 32;
+  for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+  const int b = static_cast<int>(grp / groups_per_image);
+  const int rem0 = static_cast<int>(grp - static_cast<long long>(b) * groups_per_image) * 32;
+  const int rem = rem0 + lane;
+  const bool valid = rem < a.hw;
+  const int w = a.src[0].width[lvl];
+  const int pitch = a.src[0].pitch[lvl];
+  const float c = valid ? __ldg(a.coords + static_cast<long long>(b) * a.hw + rem) : 0.0f;
+  const float centre = __fmul_rn(c, 1.0f / static_cast<float>(1 << lvl));
+  const LevelScale sc = level_scale(w, lvl, centre);
+  const int s = make_tap(0, R, centre, sc).i0 & ~3;
+  const int hi = make_tap(TAPS - 1, R, centre, sc).i1;
+  const int q = lane & 3;
+  const float* __restrict__ rows = a.src[0].ptr[lvl] + (static_cast<long long>(b) * a.hw + rem0) * pitch;
+  float4 v[WINQ];
+#pragma unroll
+  for (int j = 0; j < WINQ; ++j) {
+    const int p = j * 8 + (lane >> 2);
+    const int sp = __shfl_sync(FULL, s, p);
+    const int hp = __shfl_sync(FULL, hi, p);
+    const int cq = sp + 4 * q;
+    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((rem0 + p < a.hw) && cq <= hp && cq < w) {
+      const float* src = rows + static_cast<long long>(p) * pitch + cq;
+      if (a.vec) {
+        v[j] = ldg_f4(src);
+      } else {
+        const int left = w - cq;
+        v[j].x = __ldg(src);
+        if (left > 1) v[j].y = __ldg(src + 1);
+        if (left > 2) v[j].z = __ldg(src + 2);
+        if (left > 3) v[j].w = __ldg(src + 3);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < WINQ; ++j) {
+    float* dst = win + (j * 8 + (lane >> 2)) * STRIDE + 4 * q;
+    dst[0] = v[j].x;
+    dst[1] = v[j].y;
+    dst[2] = v[j].z;
+    dst[3] = v[j].w;
+  }
+  __syncwarp();
+  {
+    const float* mine = win + lane * STRIDE - s;
+#pragma unroll
+    for (int k = 0; k < TAPS; ++k) {
+      const Tap tp = make_tap(k, R, centre, sc);
+      // coef * val0 + (1 - coef) * val1, each operation rounded (utils.py:27); invalid pixels read zeros
+      corr[(lvl * TAPS + k) * 32 + lane] = __fadd_rn(__fmul_rn(tp.coef, mine[tp.i0]), __fmul_rn(tp.one_minus, mine[tp.i1]));
+    }
+  }
+  __syncthreads();  // also orders the weight staging before the first use
+
+  // 1x1 convolution, register tile 4 output channels x 4 pixels per thread: lane = (pixel quad pq = lane & 7,
+  // channel quad cq = lane >> 3), warp `lvl` owns channel quads 4*lvl + cq of every 64-channel pass.  Per k:
+  // one 16-byte read of W[k][4 channels] (broadcast inside the 8 lanes of a channel quad), one of
+  // corr[k][4 pixels], 16 independent FFMA.  Stores: per channel eight lanes write 128 contiguous bytes.
+  constexpr int KMAX = 4 * TAPS;  // this kernel is launched with L == 4
+  const int pq = lane & 7, cq = lane >> 3;
+  const bool vec_out = (a.hw & 3) == 0;
+  for (int pass = 0; pass < c_out; pass += 64) {
+    const int co0 = pass + 16 * lvl + 4 * cq;   // first of my four output channels
+    float acc[4][4];                             // [channel][pixel]
+    {
+      const float4 bv = co0 < c_out ? *reinterpret_cast<const float4*>(bsm + co0) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = bb[i];
+    }
+    if (co0 < c_out) {
+#pragma unroll 12
+      for (int k = 0; k < KMAX; ++k) {
+        const float4 wv = *reinterpret_cast<const float4*>(wsm + k * c_pad + co0);
+        const float4 xv = *reinterpret_cast<const float4*>(corr + k * 32 + 4 * pq);
+        const float ww[4] = {wv.x, wv.y, wv.z, wv.w}, xx[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ww[i], xx[j], acc[i][j]);
+      }
+      float* op = a.out + (static_cast<long long>(b) * c_out + co0) * a.hw + rem0 + 4 * pq;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (co0 + i >= c_out) break;
+        float r[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r[j] = relu ? fmaxf(acc[i][j], 0.f) : acc[i][j];
+        float* o = op + static_cast<long long>(i) * a.hw;
+        if (vec_out && rem0 + 4 * pq + 3 < a.hw) {
+          *reinterpret_cast<float4*>(o) = make_float4(r[0], r[1], r[2], r[3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (rem0 + 4 * pq + j < a.hw) o[j] = r[j];
+        }
+      }
+    }
+  }
+  __syncthreads();  // corr[] is rewritten by the next group
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tensor-core variant of the fused lookup + 1x1 convolution (operands rounded to nearest TF32, fp32
+// accumulation): the same precision class cuDNN gives this layer when TF32 convolutions are allowed.
+// Each warp keeps its share of the weight matrix -- 64 output channels x 40 (36 padded) inputs -- as
+// mma.sync m16n8k8 A-fragments in 80 REGISTERS for the whole (persistent) kernel, so the per-group work is
+// the lookup itself, 80 MMAs per warp fed from the 36 x 32 tile the lookup left in shared memory, and the
+// output stores.  The GEMM all but vanishes; the kernel costs a lookup plus a 61 MB write.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t y;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int TAPS>
+__global__ void __launch_bounds__(128)
+corr1d_lookup_conv1x1_tc_kernel(const __grid_constant__ LookupArgs a, const float* __restrict__ weight,
+                                const float* __restrict__ bias, int c_out, int relu, long long n_groups) {
+  constexpr int WINQ = 4, COLS = 4 * WINQ, STRIDE = COLS + 1;
+  constexpr int R = (TAPS - 1) / 2;
+  constexpr int K = 4 * TAPS;        // 36 lookup channels (4 levels)
+  constexpr int KSTEPS = (K + 7) / 8;  // 5 k-steps of 8, the last one half empty
+  constexpr int CS = 40;             // corr tile: [32 px][CS] floats -> B-fragment reads hit 32 distinct banks
+  constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ __align__(16) float smem[];
+  float* corr = smem;                     // [32][CS]
+  float* wins = corr + 32 * CS;           // [4][32][STRIDE]
+  const int lane = threadIdx.x, lvl = threadIdx.y;
+  const int gid = lane >> 2, tig = lane & 3;
+
+  // A fragments: warp `lvl` owns output channels [64*lvl, 64*lvl + 64): 4 m-tiles x 5 k-steps x 4 registers.
+  // weight is k-major (K, c_out).  a0:(row gid, col tig) a1:(gid+8, tig) a2:(gid, tig+4) a3:(gid+8, tig+4)
+  uint32_t af[4][KSTEPS][4];
+  float bv[4][2];
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt) {
+    const int r0 = 64 * lvl + 16 * mt + gid, r1 = r0 + 8;
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks) {
+      const int k0 = 8 * ks + tig, k1 = k0 + 4;
+      af[mt][ks][0] = (r0 < c_out && k0 < K) ? to_tf32(__ldg(weight + static_cast<long long>(k0) * c_out + r0)) : 0u;
+      af[mt][ks][1] = (r1 < c_out && k0 < K) ? to_tf32(__ldg(weight + static_cast<long long>(k0) * c_out + r1)) : 0u;
+      af[mt][ks][2] = (r0 < c_out && k1 < K) ? to_tf32(__ldg(weight + static_cast<long long>(k1) * c_out + r0)) : 0u;
+      af[mt][ks][3] = (r1 < c_out && k1 < K) ? to_tf32(__ldg(weight + static_cast<long long>(k1) * c_out + r1)) : 0u;
+    }
+    bv[mt][0] = (bias && r0 < c_out) ? __ldg(bias + r0) : 0.f;
+    bv[mt][1] = (bias && r1 < c_out) ? __ldg(bias + r1) : 0.f;
+  }
+  // zero the padding columns of the corr tile once (k = 36..39 feed the last k-step)
+  for (int i = lvl * 32 + lane; i < 32 * (CS - K); i += 128) corr[(i / (CS - K)) * CS + K + i % (CS - K)] = 0.f;
+
+  float* win = wins + lvl * (32 * STRIDE);
+  const int groups_per_image = (a.hw + 31) / 32;
+  const int w = a.src[0].width[lvl];
+  const int pitch = a.src[0].pitch[lvl];
+  const LevelScale sc = level_scale(w, lvl, 0.f);
+  for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    const int b = static_cast<int>(grp / groups_per_image);
+    const int rem0 = static_cast<int>(grp - static_cast<long long>(b) * groups_per_image) * 32;
+    const int rem = rem0 + lane;
+    const bool valid = rem < a.hw;
+    const float c = valid ? __ldg(a.coords + static_cast<long long>(b) * a.hw + rem) : 0.0f;
+    const float centre = __fmul_rn(c, 1.0f / static_cast<float>(1 << lvl));
+    const int s = make_tap(0, R, centre, sc).i0 & ~3;
+    const int hi = make_tap(TAPS - 1, R, centre, sc).i1;
+    const int q = lane & 3;
+    const float* __restrict__ rows = a.src[0].ptr[lvl] + (static_cast<long long>(b) * a.hw + rem0) * pitch;
+    float4 v[WINQ];
+#pragma unroll
+    for (int j = 0; j < WINQ; ++j) {
+      const int p = j * 8 + (lane >> 2);
+      const int sp = __shfl_sync(FULL, s, p);
+      const int hp = __shfl_sync(FULL, hi, p);
+      const int cq = sp + 4 * q;
+      v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if ((rem0 + p < a.hw) && cq <= hp && cq < w) {
+        const float* src = rows + static_cast<long long>(p) * pitch + cq;
+        if (a.vec) {
+          v[j] = ldg_f4(src);
+        } else {
+          const int left = w - cq;
+          v[j].x = __ldg(src);
+          if (left > 1) v[j].y = __ldg(src + 1);
+          if (left > 2) v[j].z = __ldg(src + 2);
+          if (left > 3) v[j].w = __ldg(src + 3);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < WINQ; ++j) {
+      float* dst = win + (j * 8 + (lane >> 2)) * STRIDE + 4 * q;
+      dst[0] = v[j].x;
+      dst[1] = v[j].y;
+      dst[2] = v[j].z;
+      dst[3] = v[j].w;
+    }
+    __syncwarp();
+    {
+      const float* mine = win + lane * STRIDE - s;
+#pragma unroll
+      for (int k = 0; k < TAPS; ++k) {
+        const Tap tp = make_tap(k, R, centre, sc);
+        // coef * val0 + (1 - coef) * val1, each operation rounded (utils.py:27); then RN to TF32 for the MMA
+        const float val = __fadd_rn(__fmul_rn(tp.coef, mine[tp.i0]), __fmul_rn(tp.one_minus, mine[tp.i1]));
+        corr[lane * CS + lvl * TAPS + k] = __uint_as_float(to_tf32(val));
+      }
+    }
+    __syncthreads();
+
+    // D[co][px] = sum_k W[co][k] * corr[px][k]: 4 m-tiles x 4 n-tiles (8 pixels each) per warp
+    float* out_img = a.out + static_cast<long long>(b) * c_out * a.hw + rem0;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      uint32_t bf[KSTEPS][2];   // b0:(k = tig, n = gid)  b1:(k = tig + 4, n = gid)
+      const float* cp = corr + (8 * nt + gid) * CS + tig;
+#pragma unroll
+      for (int ks = 0; ks < KSTEPS; ++ks) {
+        bf[ks][0] = __float_as_uint(cp[8 * ks]);
+        bf[ks][1] = __float_as_uint(cp[8 * ks + 4]);
+      }
+      const int px = 8 * nt + 2 * tig;   // my two output pixels (c0/c1 and c2/c3 columns)
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        float d[4] = {bv[mt][0], bv[mt][0], bv[mt][1], bv[mt][1]};
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) mma_tf32_16x8x8(d, af[mt][ks], bf[ks][0], bf[ks][1]);
+        if (relu) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) d[i] = fmaxf(d[i], 0.f);
+        }
+        const int r0 = 64 * lvl + 16 * mt + gid, r1 = r0 + 8;
+        float* o0 = out_img + static_cast<long long>(r0) * a.hw + px;
+        float* o1 = out_img + static_cast<long long>(r1) * a.hw + px;
+        if (rem0 + px + 1 < a.hw && (a.hw & 1) == 0) {
+          if (r0 < c_out) *reinterpret_cast<float2*>(o0) = make_float2(d[0], d[1]);
+          if (r1 < c_out) *reinterpret_cast<float2*>(o1) = make_float2(d[2], d[3]);
+        } else {
+          if (rem0 + px < a.hw) {
+            if (r0 < c_out) o0[0] = d[0];
+            if (r1 < c_out) o1[0] = d[2];
+          }
+          if (rem0 + px + 1 < a.hw) {
+            if (r0 < c_out) o0[1] = d[1];
+            if (r1 < c_out) o1[1] = d[3];
+          }
+        }
+      }
+    }
+    __syncthreads();  // corr[] is rewritten by the next group
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // IGEV dual lookup over the interleaved pyramids ([b][h][w1][d][g], igev.cu): the eight windows of a
 // pixel are one contiguous run of (hi - lo + 1) * 32 bytes <= 352 bytes, so every fetched sector is used.
 // Warp = 32 consecutive pixels x one level; for each of the two sources the warp copies the 32 runs into a
@@ -582,6 +896,63 @@ nnd_status nnd_gev_lookup(const float* const* level_feat, const float* const* le
     cudaFuncSetAttribute(gev_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   gev_lookup_kernel<<<grid, block, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
   return check_launch("gev_lookup_kernel");
+}
+
+nnd_status nnd_corr1d_lookup_conv1x1(const float* const* level, const int* width, const int* pitch, const float* coords,
+                                     int B, int H, int W1, int num_levels, int radius, const float* weight,
+                                     const float* bias, int c_out, int relu, int precision, float* out,
+                                     nnd_stream_t stream) {
+  using namespace nnd;
+  NND_REQUIRE(level && width && pitch && coords && weight && out, "lookup_conv1x1: null pointer argument");
+  NND_REQUIRE(B > 0 && H > 0 && W1 > 0 && c_out > 0, "lookup_conv1x1: B, H, W1, c_out must be positive");
+  NND_REQUIRE(B <= 65535, "lookup_conv1x1: batch %d exceeds the grid limit (65535)", B);
+  NND_REQUIRE(radius == 4, "lookup_conv1x1: built for radius 4 (got %d)", radius);
+  NND_REQUIRE(num_levels == 4, "lookup_conv1x1: built for the 4-level pyramid (got %d levels)", num_levels);
+  NND_REQUIRE(static_cast<long long>(H) * W1 < (1LL << 30), "lookup_conv1x1: H*W1 too large");
+  LookupArgs a;
+  memset(&a, 0, sizeof(a));
+  bool vec = true;
+  for (int l = 0; l < num_levels; ++l) {
+    NND_REQUIRE(width[l] >= 2, "lookup_conv1x1: level %d has width %d; linear_sampler needs width >= 2", l, width[l]);
+    NND_REQUIRE(pitch[l] >= width[l] && level[l], "lookup_conv1x1: level %d pointer/pitch invalid", l);
+    a.src[0].ptr[l] = level[l];
+    a.src[0].width[l] = width[l];
+    a.src[0].pitch[l] = pitch[l];
+    vec = vec && (pitch[l] % 4 == 0) && aligned16(level[l]);
+  }
+  a.coords = coords;
+  a.out = out;
+  a.hw = H * W1;
+  a.G = 1;
+  a.n_src = 1;
+  a.num_levels = num_levels;
+  a.radius = radius;
+  a.vec = vec ? 1 : 0;
+  NND_REQUIRE(precision == NND_PREC_FP32 || precision == NND_PREC_TF32, "lookup_conv1x1: unknown precision %d", precision);
+  const long long n_groups_all = static_cast<long long>(B) * ((a.hw + 31) / 32);
+  if (precision == NND_PREC_TF32 && c_out <= 256) {
+    // tensor-core path: weights live in registers, shared memory holds only the lookup tiles
+    const size_t smem_tc = (32 * 40 + static_cast<size_t>(4) * 32 * 17) * sizeof(float);
+    const long long resident = static_cast<long long>(sm_count()) * 3;   // 128 threads x ~150 registers
+    dim3 grid_tc(static_cast<unsigned>(n_groups_all < resident ? n_groups_all : resident));
+    corr1d_lookup_conv1x1_tc_kernel<9><<<grid_tc, dim3(32, 4), smem_tc, reinterpret_cast<cudaStream_t>(stream)>>>(
+        a, weight, bias, c_out, relu ? 1 : 0, n_groups_all);
+    return check_launch("corr1d_lookup_conv1x1_tc_kernel");
+  }
+  const int K = num_levels * 9;
+  const size_t c_pad = (static_cast<size_t>(c_out) + 3) & ~static_cast<size_t>(3);
+  const size_t smem = (c_pad * K + c_pad + static_cast<size_t>(K) * 32 + static_cast<size_t>(num_levels) * 32 * 17) *
+                      sizeof(float);
+  NND_REQUIRE(smem <= 200 * 1024, "lookup_conv1x1: c_out = %d needs %zu bytes of shared memory", c_out, smem);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(corr1d_lookup_conv1x1_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  const long long n_groups = static_cast<long long>(B) * ((a.hw + 31) / 32);
+  const long long resident = static_cast<long long>(sm_count()) * (smem > 100 * 1024 ? 1 : smem > 70 * 1024 ? 2 : smem > 52 * 1024 ? 3 : 4);
+  dim3 grid(static_cast<unsigned>(n_groups < resident ? n_groups : resident));
+  dim3 block(32, num_levels);
+  corr1d_lookup_conv1x1_kernel<9><<<grid, block, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a, weight, bias, c_out,
+                                                                                                 relu ? 1 : 0, n_groups);
+  return check_launch("corr1d_lookup_conv1x1_kernel");
 }
 
 }  // extern "C"

@@ -199,8 +199,9 @@ class BasicMotionEncoder(nn.Module):
         self.convf2 = nn.Conv2d(128, 64, 3, padding=1)
         self.conv = nn.Conv2d(64 + 192, hidden_dim - flow_channel, 3, padding=1)
 
-    def forward(self, flow, corr):
-        cor = F.relu(self.convc2(F.relu(self.convc1(corr))))
+    def forward(self, flow, corr, cor1=None):
+        """``cor1``: ``relu(convc1(corr))`` already computed by the fused lookup kernel (then ``corr`` is unused)."""
+        cor = F.relu(self.convc2(cor1 if cor1 is not None else F.relu(self.convc1(corr))))
         flo = F.relu(self.convf2(F.relu(self.convf1(flow))))
         out = F.relu(self.conv(torch.cat([cor, flo], dim=1)))
         return torch.cat([out, flow], dim=1)
@@ -231,10 +232,10 @@ class BasicUpdateBlock(nn.Module):
         self.mask = nn.Sequential(nn.Conv2d(hidden_dim, hidden_dim * 2, 3, padding=1), nn.ReLU(inplace=True),
                                   nn.Conv2d(hidden_dim * 2, sps * 9, 1))
 
-    def forward(self, net, inp, corr, flow, raw_mask=False):
+    def forward(self, net, inp, corr, flow, raw_mask=False, cor1=None):
         """``raw_mask=True`` returns the mask logits without the reference's ``0.25 *`` (update_block.py:110):
         the fused upsampling kernel applies that scale itself, saving a pass over the (N,576,H,W) tensor."""
-        motion = self.encoder(flow, corr)
+        motion = self.encoder(flow, corr, cor1=cor1)
         net = self.gru(net, torch.cat((inp, motion), dim=1))
         mask = self.mask(net)
         return net, (mask if raw_mask else 0.25 * mask), self.flow_head(net)
@@ -270,6 +271,7 @@ class RAFTStereo(nn.Module):
         self.weights = weights
         self.strict_load = strict_load
         self.final_only = False     # True: upsample only the last iteration (what evaluate.py:155 consumes)
+        self.fuse_motion_front = True   # lookup + convc1 + ReLU as one kernel when corr_fn provides it
         # Precision of the dense (cuDNN) layers, measured on the KITTI/32-iteration golden (tools/exp_epe_modules.py):
         #   "fp32"  every convolution in fp32                           final EPE vs reference 0.0002 px
         #   "mixed" ConvGRU in fp32, everything else on TF32 tensor cores              0.0021 px  (bar: 0.01 px)
@@ -330,12 +332,22 @@ class RAFTStereo(nn.Module):
         outputs = []
         for it in range(self.iters):
             coords1 = coords1.detach()
-            sampled = corr(coords1)
+            fuse_front = (self.fuse_motion_front and coords1.is_cuda and not torch.is_grad_enabled()
+                          and hasattr(corr, "lookup_conv1x1") and self.corr_levels == 4 and self.corr_radius == 4)
+            if fuse_front:
+                # lookup + convc1 (1x1) + ReLU in one kernel: the motion encoder's input is written directly
+                conv1 = self.update_block.encoder.convc1
+                if it == 0:
+                    conv1_wt = corr.prepare_conv1x1_weight(conv1.weight)    # k-major copy, once per forward
+                sampled, cor1 = None, corr.lookup_conv1x1(coords1, None, conv1.bias, relu=True, weight_t=conv1_wt,
+                                                          precision="tf32" if torch.backends.cudnn.allow_tf32 else "fp32")
+            else:
+                sampled, cor1 = corr(coords1), None
             # on the GPU the convex upsampling is one fused kernel (softmax + unfold + weighted sum + pixel
             # shuffle, with the update block's 0.25 mask scale folded in); the torch chain below is the
             # reference's own, kept for the CPU baseline leg (corr_fn = oracle) only
             fused = coords1.is_cuda and fnet_ds in (2, 4, 8) and not torch.is_grad_enabled()
-            net, mask, delta = self.update_block(net, inp, sampled, coords1 - org_coords, raw_mask=fused)
+            net, mask, delta = self.update_block(net, inp, sampled, coords1 - org_coords, raw_mask=fused, cor1=cor1)
             coords1 = coords1 + delta
             if not self.final_only or it == self.iters - 1:
                 if fused:

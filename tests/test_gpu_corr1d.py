@@ -349,3 +349,36 @@ def test_config5_row_bands_equal_full_volume():
         for l, p in enumerate(band.corr_pyramid[:4]):
             assert torch.equal(p.reshape(B, h1 - h0, W, -1), full_pyr[l][:, h0:h1])
         assert torch.equal(band(coords[:, :, h0:h1].contiguous()), full_out[:, :, h0:h1])
+
+
+@pytest.mark.parametrize("shape,c_out", [((8, 48, 156), 256), ((1, 5, 52), 64), ((2, 3, 40), 7)])
+def test_lookup_conv1x1_fusion(shape, c_out):
+    """Lookup fused with the motion encoder's 1x1 convolution + ReLU vs the two-step path on the device."""
+    import nndepth_b200 as nb
+    B, H, W = shape
+    torch.manual_seed(B + H + W)
+    f1 = torch.randn(B, 32, H, W, device="cuda")
+    f2 = torch.randn(B, 32, H, W, device="cuda")
+    blk = nb.CorrBlock1D(f1, f2, 4, 4)
+    coords = torch.arange(W, device="cuda").float().view(1, 1, 1, W).repeat(B, 1, H, 1) - torch.rand(B, 1, H, W, device="cuda") * 20
+    conv = torch.nn.Conv2d(36, c_out, 1).cuda()
+    looked = blk(coords)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            ref = torch.relu(torch.einsum("ok,bkhw->bohw", conv.weight.view(c_out, 36).double(), looked.double())
+                             + conv.bias.double().view(1, -1, 1, 1)).float()
+            got = blk.lookup_conv1x1(coords, conv.weight, conv.bias, relu=True)
+            lin = blk.lookup_conv1x1(coords, conv.weight, None, relu=False)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    scale = ref.abs().max().item()
+    assert got.shape == (B, c_out, H, W)
+    assert (got - ref).abs().max().item() <= 1e-5 * scale
+    ref_lin = torch.einsum("ok,bkhw->bohw", conv.weight.view(c_out, 36).double(), looked.double()).float()
+    assert (lin - ref_lin).abs().max().item() <= 1e-5 * scale
+    # tensor-core variant: operands rounded to nearest TF32 -> the 1e-3 bar
+    with torch.no_grad():
+        tc = blk.lookup_conv1x1(coords, conv.weight, conv.bias, relu=True, precision="tf32")
+    assert (tc - ref).abs().max().item() <= 1e-3 * scale

@@ -9,11 +9,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from nndepth_b200.engine import StereoEngine  # noqa: E402
 from nndepth_b200.raft_stereo import BaseRAFTStereo  # noqa: E402
 
-torch.backends.cudnn.allow_tf32 = "--conv-tf32" in sys.argv
-torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32
 torch.manual_seed(0)
 channels_last = "--channels-last" in sys.argv
 model = BaseRAFTStereo(iters=32).eval()
+model.dense_precision = next((a.split("=")[1] for a in sys.argv if a.startswith("--mode=")), "mixed3x")
 engine = StereoEngine(model, use_cuda_graph=False)
 if channels_last:
     engine.model = engine.model.to(memory_format=torch.channels_last)
