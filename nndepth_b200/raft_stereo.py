@@ -178,6 +178,26 @@ class SepConvGRU(nn.Module):
         q = torch.tanh(F.conv2d(self._split_act(torch.cat([r * h, x], dim=1)), wq, bq, padding=pad))
         return (1 - z) * h + z * q
 
+    # ---- fused channels-last runner of the 3xTF32 recurrence (csrc/gru_fused.cu) ------------------------------
+    def _split_weights_cl(self, tag, ch):
+        """Channels-last 3x weights matching the staging row [h_hi|h_lo|h_hi|x_hi|x_lo|x_hi] of FusedGRURun."""
+        key = ("cl", tag)
+        if key not in self._split_w:
+            cz, cr, cq = (getattr(self, f"conv{g}{tag}") for g in "zrq")
+            packed = []
+            for w, b in ((torch.cat([cz.weight, cr.weight], 0), torch.cat([cz.bias, cr.bias], 0)), (cq.weight, cq.bias)):
+                w = w.detach().float()
+                hi = self._rn_tf32(w)
+                lo = w - hi
+                w3 = torch.cat([hi[:, :ch], hi[:, :ch], lo[:, :ch], hi[:, ch:], hi[:, ch:], lo[:, ch:]], 1)
+                packed.append((w3.contiguous(memory_format=torch.channels_last), b.detach().float().contiguous()))
+            self._split_w[key] = (packed[0], packed[1], cz.padding)
+        return self._split_w[key]
+
+    def start(self, h0, inp):
+        """Begin a forward: returns the per-forward runner holding the hidden state and the staging buffer."""
+        return FusedGRURun(self, h0, inp)
+
     def forward(self, h, x):
         if self.recurrence == "3xtf32" and h.is_cuda:
             with cudnn_tf32(True):
@@ -186,6 +206,65 @@ class SepConvGRU(nn.Module):
             with cudnn_tf32(False):
                 return self._half_step(self._half_step(h, x, "1"), x, "2")
         return self._half_step(self._half_step(h, x, "1"), x, "2")
+
+
+class FusedGRURun:
+    """One forward's worth of the 3xTF32 ConvGRU on the fused channels-last kernels.
+
+    Holds the hidden state ``h`` (channels-last) and the staging buffer ``S`` whose rows are
+    ``[h_hi|h_lo|h_hi|x_hi|x_lo|x_hi]``; ``S`` is the NHWC input of all four convolutions of an iteration, so
+    cuDNN's tensor-core kernels run without layout conversions and every elementwise step between two
+    convolutions is ONE kernel (``nnd_gru_gate_r`` / ``nnd_gru_gate_h``).  The context half of ``x`` is staged
+    once per forward, the motion half once per iteration.
+    """
+
+    def __init__(self, gru, h0, inp):
+        from . import _lib
+        self._lib = _lib
+        self.gru = gru
+        h0 = h0.float().contiguous()
+        inp = inp.float().contiguous()
+        N, ch, H, W = h0.shape
+        self.N, self.ch, self.H, self.W = N, ch, H, W
+        self.c_inp = inp.shape[1]
+        self.cx = gru.convz1.weight.shape[1] - ch
+        self.ctot = 3 * (ch + self.cx)
+        cl = torch.channels_last
+        self.S = torch.empty(N, self.ctot, H, W, dtype=torch.float32, device=h0.device).contiguous(memory_format=cl)
+        self.h = torch.empty(N, ch, H, W, dtype=torch.float32, device=h0.device).contiguous(memory_format=cl)
+        self.z = torch.empty_like(self.h)
+        self.h.copy_(h0)
+        self._stage(h0, 0, ch, 2 * ch)
+        x0 = 3 * ch
+        self._stage(inp, x0, x0 + self.cx, x0 + 2 * self.cx)
+
+    def _stage(self, src, off_hi0, off_lo, off_hi1):
+        lib = self._lib
+        N, C = src.shape[0], src.shape[1]
+        with torch.cuda.device(src.device):
+            lib.check(lib.load().nnd_gru_stage(lib.ptr(src), N, C, self.H * self.W, lib.ptr(self.S), self.ctot, off_hi0, off_lo,
+                                               off_hi1, lib.stream_ptr(src)), "nnd_gru_stage")
+
+    def step(self, motion):
+        """One GRU update with ``x = cat[inp, motion]``; returns the new hidden state (channels-last view)."""
+        lib = self._lib
+        motion = motion.float().contiguous()
+        if motion.shape[1] != self.cx - self.c_inp:
+            raise RuntimeError(f"motion features must have {self.cx - self.c_inp} channels, got {motion.shape[1]}")
+        x0 = 3 * self.ch + self.c_inp
+        self._stage(motion, x0, x0 + self.cx, x0 + 2 * self.cx)
+        pixels = self.N * self.H * self.W
+        cl = torch.channels_last
+        with cudnn_tf32(True), torch.cuda.device(self.S.device):
+            for tag in "12":
+                (wzr, bzr), (wq, bq), pad = self.gru._split_weights_cl(tag, self.ch)
+                zr = F.conv2d(self.S, wzr, None, padding=pad).contiguous(memory_format=cl)
+                lib.check(lib.load().nnd_gru_gate_r(lib.ptr(zr), lib.ptr(bzr), lib.ptr(self.h), pixels, self.ch, lib.ptr(self.z),
+                                                    lib.ptr(self.S), self.ctot, lib.stream_ptr(zr)), "nnd_gru_gate_r")
+                q = F.conv2d(self.S, wq, None, padding=pad).contiguous(memory_format=cl)
+                lib.check(lib.load().nnd_gru_gate_h(lib.ptr(q), lib.ptr(bq), lib.ptr(self.z), pixels, self.ch, lib.ptr(self.h),
+                                                    lib.ptr(self.S), self.ctot, lib.stream_ptr(q)), "nnd_gru_gate_h")
+        return self.h
 
 
 class BasicMotionEncoder(nn.Module):
@@ -232,11 +311,14 @@ class BasicUpdateBlock(nn.Module):
         self.mask = nn.Sequential(nn.Conv2d(hidden_dim, hidden_dim * 2, 3, padding=1), nn.ReLU(inplace=True),
                                   nn.Conv2d(hidden_dim * 2, sps * 9, 1))
 
-    def forward(self, net, inp, corr, flow, raw_mask=False, cor1=None):
+    def forward(self, net, inp, corr, flow, raw_mask=False, cor1=None, gru_run=None):
         """``raw_mask=True`` returns the mask logits without the reference's ``0.25 *`` (update_block.py:110):
         the fused upsampling kernel applies that scale itself, saving a pass over the (N,576,H,W) tensor."""
         motion = self.encoder(flow, corr, cor1=cor1)
-        net = self.gru(net, torch.cat((inp, motion), dim=1))
+        if gru_run is not None:
+            net = gru_run.step(motion)          # fused channels-last 3xTF32 recurrence; `net` lives in the runner
+        else:
+            net = self.gru(net, torch.cat((inp, motion), dim=1))
         mask = self.mask(net)
         return net, (mask if raw_mask else 0.25 * mask), self.flow_head(net)
 
@@ -272,6 +354,7 @@ class RAFTStereo(nn.Module):
         self.strict_load = strict_load
         self.final_only = False     # True: upsample only the last iteration (what evaluate.py:155 consumes)
         self.fuse_motion_front = True   # lookup + convc1 + ReLU as one kernel when corr_fn provides it
+        self.fuse_gru = True            # 3xTF32 ConvGRU on the fused channels-last kernels (mode "mixed3x")
         # Precision of the dense (cuDNN) layers, measured on the KITTI/32-iteration golden (tools/exp_epe_modules.py):
         #   "fp32"  every convolution in fp32                           final EPE vs reference 0.0002 px
         #   "mixed" ConvGRU in fp32, everything else on TF32 tensor cores              0.0021 px  (bar: 0.01 px)
@@ -327,6 +410,11 @@ class RAFTStereo(nn.Module):
         net, inp = torch.tanh(net), F.relu(inp)
 
         corr = self.corr_fn(fmap1, fmap2, self.corr_levels, self.corr_radius)
+        gru = getattr(self.update_block, "gru", None)
+        gru_run = None
+        if (self.fuse_gru and gru is not None and getattr(gru, "recurrence", None) == "3xtf32" and net.is_cuda
+                and not torch.is_grad_enabled()):
+            gru_run = gru.start(net, inp)
         org_coords = self.initialize_coords(fmap1)
         coords1 = org_coords.clone()
         outputs = []
@@ -347,7 +435,8 @@ class RAFTStereo(nn.Module):
             # shuffle, with the update block's 0.25 mask scale folded in); the torch chain below is the
             # reference's own, kept for the CPU baseline leg (corr_fn = oracle) only
             fused = coords1.is_cuda and fnet_ds in (2, 4, 8) and not torch.is_grad_enabled()
-            net, mask, delta = self.update_block(net, inp, sampled, coords1 - org_coords, raw_mask=fused, cor1=cor1)
+            net, mask, delta = self.update_block(net, inp, sampled, coords1 - org_coords, raw_mask=fused, cor1=cor1,
+                                                 gru_run=gru_run)
             coords1 = coords1 + delta
             if not self.final_only or it == self.iters - 1:
                 if fused:

@@ -82,3 +82,27 @@ def test_kitti_dense_precision_modes(golden, mode, bar):
     ref = torch.from_numpy(g["final_up_disp"]).cuda()
     assert epe(out, ref) < bar, epe(out, ref)
     assert epe(graphed, ref) < bar, epe(graphed, ref)
+
+
+def test_fused_gru_matches_unfused_3xtf32():
+    """The fused channels-last ConvGRU runner vs the same 3xTF32 recurrence written with torch ops, and vs fp32."""
+    from nndepth_b200.raft_stereo import SepConvGRU, cudnn_tf32
+    torch.manual_seed(7)
+    gru = SepConvGRU(hidden_dim=128, input_dim=256).cuda().eval()
+    N, H, W = 2, 12, 20
+    h0 = torch.tanh(torch.randn(N, 128, H, W, device="cuda"))
+    inp = torch.relu(torch.randn(N, 128, H, W, device="cuda"))
+    motions = [torch.randn(N, 128, H, W, device="cuda") for _ in range(3)]
+    with torch.no_grad():
+        gru.recurrence = "3xtf32"
+        run = gru.start(h0, inp)
+        h_ref, h_fp32 = h0, h0
+        for m in motions:
+            fused = run.step(m)
+            h_ref = gru(h_ref, torch.cat([inp, m], 1))
+            gru.recurrence = "fp32"
+            h_fp32 = gru(h_fp32, torch.cat([inp, m], 1))
+            gru.recurrence = "3xtf32"
+            assert fused.shape == h_ref.shape
+            assert (fused - h_ref).abs().max().item() < 2e-5
+            assert (fused - h_fp32).abs().max().item() < 2e-5
