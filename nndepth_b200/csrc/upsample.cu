@@ -65,12 +65,61 @@ convex_upsample_kernel(const float* __restrict__ flow, const float* __restrict__
   }
 }
 
+// Channels-last mask (N, H, W, 9*RATE*RATE) -- what cuDNN hands back when the hidden state is channels-last.
+// One warp per coarse pixel: the pixel's 9*64 logits are 2304 contiguous bytes; lane = (sub-row i, column pair)
+// reads 8 bytes per neighbour k (a warp load covers 256 contiguous bytes) and writes two outputs.
+__global__ void __launch_bounds__(256)
+convex_upsample_nhwc8_kernel(const float* __restrict__ flow, const float* __restrict__ mask, int H, int W, long long n_pix,
+                             float mask_scale, float* __restrict__ out) {
+  constexpr int RATE = 8;
+  const int lane = threadIdx.x & 31;
+  const int i = lane >> 2, jp = lane & 3;
+  const long long hw = static_cast<long long>(H) * W;
+  const long long warp0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long pix = warp0; pix < n_pix; pix += n_warps) {
+    const long long n = pix / hw;
+    const long long p = pix - n * hw;
+    const int h = static_cast<int>(p / W), w = static_cast<int>(p - static_cast<long long>(h) * W);
+    const float* fl = flow + n * hw;
+    const float2* mp = reinterpret_cast<const float2*>(mask + pix * (9 * RATE * RATE) + i * RATE + 2 * jp);
+    float2 x[9];
+    float nb[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      x[k] = __ldcs(mp + k * (RATE * RATE / 2));
+      const int hh = h + k / 3 - 1, ww = w + k % 3 - 1;
+      nb[k] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __fmul_rn(8.0f, __ldg(fl + static_cast<long long>(hh) * W + ww)) : 0.f;
+    }
+    float m0 = x[0].x * mask_scale, m1 = x[0].y * mask_scale;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      x[k].x *= mask_scale;
+      x[k].y *= mask_scale;
+      m0 = fmaxf(m0, x[k].x);
+      m1 = fmaxf(m1, x[k].y);
+    }
+    float s0 = 0.f, s1 = 0.f, a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const float e0 = __expf(x[k].x - m0), e1 = __expf(x[k].y - m1);
+      s0 += e0;
+      s1 += e1;
+      a0 = fmaf(e0, nb[k], a0);
+      a1 = fmaf(e1, nb[k], a1);
+    }
+    float* op = out + (n * RATE * H + static_cast<long long>(RATE) * h + i) * (static_cast<long long>(RATE) * W) +
+                static_cast<long long>(RATE) * w + 2 * jp;
+    *reinterpret_cast<float2*>(op) = make_float2(a0 / s0, a1 / s1);
+  }
+}
+
 }  // namespace nnd
 
 extern "C" {
 
 nnd_status nnd_convex_upsample(const float* flow, const float* mask, int N, int H, int W, int rate, float mask_scale,
-                               float* out, nnd_stream_t stream_) {
+                               int mask_channels_last, float* out, nnd_stream_t stream_) {
   using namespace nnd;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   NND_REQUIRE(flow && mask && out, "convex_upsample: null pointer");
@@ -79,6 +128,16 @@ nnd_status nnd_convex_upsample(const float* flow, const float* mask, int N, int 
   NND_REQUIRE(rate == 2 || rate == 4 || rate == 8, "convex_upsample: rate %d unsupported (2, 4, 8)", rate);
   NND_REQUIRE(rate % 4 != 0 || aligned16(out), "convex_upsample: output must be 16-byte aligned");
   const long long hw = static_cast<long long>(H) * W;
+  if (mask_channels_last) {
+    NND_REQUIRE(rate == 8, "convex_upsample: the channels-last mask path is built for rate 8 (got %d)", rate);
+    NND_REQUIRE((reinterpret_cast<uintptr_t>(mask) & 7u) == 0 && (reinterpret_cast<uintptr_t>(out) & 7u) == 0,
+                "convex_upsample: mask and output must be 8-byte aligned");
+    const long long n_pix = hw * N;
+    const long long want = (n_pix + 7) / 8, cap = static_cast<long long>(sm_count()) * 8;
+    convex_upsample_nhwc8_kernel<<<static_cast<unsigned>(want < cap ? want : cap), 256, 0, stream>>>(flow, mask, H, W, n_pix,
+                                                                                              mask_scale, out);
+    return check_launch("convex_upsample_nhwc8_kernel");
+  }
   dim3 grid(static_cast<unsigned>((hw + 31) / 32), N);
   if (rate == 8) {
     convex_upsample_kernel<8><<<grid, dim3(32, 8), 0, stream>>>(flow, mask, H, W, mask_scale, out);

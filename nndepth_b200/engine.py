@@ -105,9 +105,16 @@ class StereoEngine:
         # final_only=False keeps the reference forward's behaviour (an upsampled map per iteration);
         # True upsamples only the last iteration, which is all evaluate.py:155 reads.
         self.model.final_only = final_only
-        gru = getattr(getattr(self.model, "update_block", None), "gru", None)
+        ub = getattr(self.model, "update_block", None)
+        gru = getattr(ub, "gru", None)
         if hasattr(gru, "fuse_gates"):
             gru.fuse_gates()
+        # the fused ConvGRU keeps the hidden state channels-last: give the heads that read it channels-last
+        # weights once, instead of letting cuDNN convert them on every call
+        for name in ("flow_head", "mask"):
+            head = getattr(ub, name, None)
+            if head is not None:
+                head.to(memory_format=torch.channels_last)
         self.use_cuda_graph = use_cuda_graph
         self.divis_by = divis_by
         self._dev_in = {}

@@ -39,6 +39,15 @@ class cudnn_tf32:
         return False
 
 
+def conv_relu(conv, x):
+    """``relu(conv(x))``: on the GPU, inference, as cuDNN's fused convolution + bias + ReLU -- one kernel where
+    ``F.relu(conv(x))`` costs three (convolution, bias add, clamp).  Same arithmetic, same TF32 policy."""
+    if (x.is_cuda and not torch.is_grad_enabled() and conv.bias is not None and conv.padding_mode == "zeros"
+            and isinstance(conv.padding, tuple) and hasattr(torch, "cudnn_convolution_relu")):
+        return torch.cudnn_convolution_relu(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups)
+    return F.relu(conv(x))
+
+
 def _norm(kind, planes):
     if kind == "batch":
         return nn.BatchNorm2d(planes)
@@ -280,9 +289,9 @@ class BasicMotionEncoder(nn.Module):
 
     def forward(self, flow, corr, cor1=None):
         """``cor1``: ``relu(convc1(corr))`` already computed by the fused lookup kernel (then ``corr`` is unused)."""
-        cor = F.relu(self.convc2(cor1 if cor1 is not None else F.relu(self.convc1(corr))))
-        flo = F.relu(self.convf2(F.relu(self.convf1(flow))))
-        out = F.relu(self.conv(torch.cat([cor, flo], dim=1)))
+        cor = conv_relu(self.convc2, cor1 if cor1 is not None else conv_relu(self.convc1, corr))
+        flo = conv_relu(self.convf2, conv_relu(self.convf1, flow))
+        out = conv_relu(self.conv, torch.cat([cor, flo], dim=1))
         return torch.cat([out, flow], dim=1)
 
 
@@ -294,7 +303,7 @@ class FlowHead(nn.Module):
         self.relu = nn.ReLU(inplace=True)
 
     def forward(self, x):
-        return self.conv2(self.relu(self.conv1(x)))
+        return self.conv2(conv_relu(self.conv1, x))
 
 
 class BasicUpdateBlock(nn.Module):
@@ -319,7 +328,7 @@ class BasicUpdateBlock(nn.Module):
             net = gru_run.step(motion)          # fused channels-last 3xTF32 recurrence; `net` lives in the runner
         else:
             net = self.gru(net, torch.cat((inp, motion), dim=1))
-        mask = self.mask(net)
+        mask = self.mask[2](conv_relu(self.mask[0], net))
         return net, (mask if raw_mask else 0.25 * mask), self.flow_head(net)
 
 

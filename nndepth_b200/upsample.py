@@ -14,7 +14,11 @@ def convex_upsample(flow, mask, rate=8, mask_scale=1.0):
     ``0.25 * mask`` (``blocks/update_block.py:110``) into the same pass (exact: a power of two).
     """
     flow = _lib.as_cuda_f32(flow, "flow")
-    mask = _lib.as_cuda_f32(mask, "mask")
+    # a channels-last mask (what cuDNN returns for a channels-last hidden state) is consumed as it lies
+    nhwc = (rate == 8 and isinstance(mask, torch.Tensor) and mask.is_cuda and mask.dtype == torch.float32 and mask.dim() == 4
+            and mask.shape[1] > 1 and not mask.is_contiguous() and mask.is_contiguous(memory_format=torch.channels_last)
+            and not (torch.is_grad_enabled() and mask.requires_grad))
+    mask = mask.detach() if nhwc else _lib.as_cuda_f32(mask, "mask")
     if flow.dim() != 4 or flow.shape[1] != 1:
         raise RuntimeError(f"flow must be (N, 1, H, W), got {tuple(flow.shape)}")
     N, _, H, W = flow.shape
@@ -24,7 +28,7 @@ def convex_upsample(flow, mask, rate=8, mask_scale=1.0):
     with torch.cuda.device(flow.device):
         _lib.check(
             _lib.load().nnd_convex_upsample(_lib.ptr(flow), _lib.ptr(mask), N, H, W, int(rate), float(mask_scale),
-                                            _lib.ptr(out), _lib.stream_ptr(flow)),
+                                            1 if nhwc else 0, _lib.ptr(out), _lib.stream_ptr(flow)),
             "nnd_convex_upsample",
         )
     return out

@@ -27,6 +27,10 @@ def test_matches_reference_chain(shape, rate):
     ref = reference_chain(flow.double(), mask.double(), rate).float()
     assert got.shape == ref.shape == (N, 1, rate * H, rate * W)
     assert (got - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item())
+    if rate == 8:   # channels-last mask: same numbers, consumed without a layout copy
+        cl = mask.contiguous(memory_format=torch.channels_last)
+        got_cl = nb.convex_upsample(flow, cl, rate)
+        assert (got_cl - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item())
     # the folded 0.25 scale is exact (power of two): identical bits to scaling the mask first
     assert torch.equal(nb.convex_upsample(flow, mask, rate, mask_scale=0.25), nb.convex_upsample(flow, 0.25 * mask, rate))
 
