@@ -182,11 +182,13 @@ nnd_status nnd_agcl_iter_nhwc(const float* fmap1_nhwc, const float* fmap2_nhwc, 
  *   flow (N,1,H,W), mask (N, 9*rate*rate, H, W) -> out (N, 1, rate*H, rate*W); rate in {2, 4, 8}.
  *   mask_scale multiplies the mask logits first: pass 0.25 to fold the update block's `0.25 * mask`
  *   (blocks/update_block.py:110) into this pass, 1.0 for an already scaled mask.
+ *   mask_bias (9*rate*rate) or NULL is added to the logits before the scale: the bias of the mask head's last
+ *   1x1 convolution, so that convolution can run bias-free (one pass over the mask less).
  *   mask_channels_last != 0: the mask is stored (N, H, W, 9*rate*rate) (rate 8 only) -- the memory format
  *   cuDNN returns when the hidden state feeding the mask head is channels-last.
  * ---------------------------------------------------------------------------------------------- */
-nnd_status nnd_convex_upsample(const float* flow, const float* mask, int N, int H, int W, int rate,
-                               float mask_scale, int mask_channels_last, float* out, nnd_stream_t stream);
+nnd_status nnd_convex_upsample(const float* flow, const float* mask, const float* mask_bias, int N, int H, int W,
+                               int rate, float mask_scale, int mask_channels_last, float* out, nnd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Error-compensated TF32 operand split for the ConvGRU convolutions (nndepth/blocks/gru.py:5-37), the

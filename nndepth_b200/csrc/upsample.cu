@@ -6,7 +6,7 @@
 // Reference chain per GRU iteration: view -> softmax over the 9 neighbours -> F.unfold(rate * flow, 3x3,
 // padding 1) -> multiply -> sum -> permute -> reshape, i.e. five passes over a (N, 9*rate^2, H, W) tensor
 // (138 MB at KITTI, batch 8) plus the update block's separate `0.25 *` pass.  Here: one pass.
-//   out[n, 0, rate*h + i, rate*w + j] = sum_k softmax_k(s * mask[n, k*rate^2 + i*rate + j, h, w])
+//   out[n, 0, rate*h + i, rate*w + j] = sum_k softmax_k(s * (mask[n, k*rate^2 + i*rate + j, h, w] + bias[..]))
 //                                              * rate * flow[n, 0, h + k/3 - 1, w + k%3 - 1]   (zero padded)
 // Thread = (coarse pixel, sub-row i): 9*rate coalesced mask loads (lanes run along w, every load is a full
 // 128-byte row segment of one channel plane), a 9-way softmax per output, `rate` consecutive outputs written
@@ -19,8 +19,8 @@ namespace nnd {
 
 template <int RATE>
 __global__ void __launch_bounds__(32 * RATE)
-convex_upsample_kernel(const float* __restrict__ flow, const float* __restrict__ mask, int H, int W, float mask_scale,
-                       float* __restrict__ out) {
+convex_upsample_kernel(const float* __restrict__ flow, const float* __restrict__ mask, const float* __restrict__ mask_bias,
+                       int H, int W, float mask_scale, float* __restrict__ out) {
   const int lane = threadIdx.x, i = threadIdx.y;
   const long long hw = static_cast<long long>(H) * W;
   const long long p = static_cast<long long>(blockIdx.x) * 32 + lane;
@@ -42,7 +42,10 @@ convex_upsample_kernel(const float* __restrict__ flow, const float* __restrict__
   for (int j = 0; j < RATE; ++j) {
     float x[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) x[k] = __ldcs(mp + (static_cast<long long>(k) * RATE * RATE + j) * hw) * mask_scale;
+    for (int k = 0; k < 9; ++k) {
+      const float bk = mask_bias ? __ldg(mask_bias + k * RATE * RATE + i * RATE + j) : 0.f;
+      x[k] = (__ldcs(mp + (static_cast<long long>(k) * RATE * RATE + j) * hw) + bk) * mask_scale;
+    }
     float m = x[0];
 #pragma unroll
     for (int k = 1; k < 9; ++k) m = fmaxf(m, x[k]);
@@ -69,14 +72,18 @@ convex_upsample_kernel(const float* __restrict__ flow, const float* __restrict__
 // One warp per coarse pixel: the pixel's 9*64 logits are 2304 contiguous bytes; lane = (sub-row i, column pair)
 // reads 8 bytes per neighbour k (a warp load covers 256 contiguous bytes) and writes two outputs.
 __global__ void __launch_bounds__(256)
-convex_upsample_nhwc8_kernel(const float* __restrict__ flow, const float* __restrict__ mask, int H, int W, long long n_pix,
-                             float mask_scale, float* __restrict__ out) {
+convex_upsample_nhwc8_kernel(const float* __restrict__ flow, const float* __restrict__ mask, const float* __restrict__ mask_bias,
+                             int H, int W, long long n_pix, float mask_scale, float* __restrict__ out) {
   constexpr int RATE = 8;
   const int lane = threadIdx.x & 31;
   const int i = lane >> 2, jp = lane & 3;
   const long long hw = static_cast<long long>(H) * W;
   const long long warp0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  float2 bias[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+    bias[k] = mask_bias ? __ldg(reinterpret_cast<const float2*>(mask_bias + k * RATE * RATE + i * RATE + 2 * jp)) : make_float2(0.f, 0.f);
   for (long long pix = warp0; pix < n_pix; pix += n_warps) {
     const long long n = pix / hw;
     const long long p = pix - n * hw;
@@ -91,11 +98,11 @@ convex_upsample_nhwc8_kernel(const float* __restrict__ flow, const float* __rest
       const int hh = h + k / 3 - 1, ww = w + k % 3 - 1;
       nb[k] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __fmul_rn(8.0f, __ldg(fl + static_cast<long long>(hh) * W + ww)) : 0.f;
     }
-    float m0 = x[0].x * mask_scale, m1 = x[0].y * mask_scale;
+    float m0 = (x[0].x + bias[0].x) * mask_scale, m1 = (x[0].y + bias[0].y) * mask_scale;
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-      x[k].x *= mask_scale;
-      x[k].y *= mask_scale;
+      x[k].x = (x[k].x + bias[k].x) * mask_scale;
+      x[k].y = (x[k].y + bias[k].y) * mask_scale;
       m0 = fmaxf(m0, x[k].x);
       m1 = fmaxf(m1, x[k].y);
     }
@@ -118,8 +125,8 @@ convex_upsample_nhwc8_kernel(const float* __restrict__ flow, const float* __rest
 
 extern "C" {
 
-nnd_status nnd_convex_upsample(const float* flow, const float* mask, int N, int H, int W, int rate, float mask_scale,
-                               int mask_channels_last, float* out, nnd_stream_t stream_) {
+nnd_status nnd_convex_upsample(const float* flow, const float* mask, const float* mask_bias, int N, int H, int W, int rate,
+                               float mask_scale, int mask_channels_last, float* out, nnd_stream_t stream_) {
   using namespace nnd;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   NND_REQUIRE(flow && mask && out, "convex_upsample: null pointer");
@@ -134,17 +141,17 @@ nnd_status nnd_convex_upsample(const float* flow, const float* mask, int N, int 
                 "convex_upsample: mask and output must be 8-byte aligned");
     const long long n_pix = hw * N;
     const long long want = (n_pix + 7) / 8, cap = static_cast<long long>(sm_count()) * 8;
-    convex_upsample_nhwc8_kernel<<<static_cast<unsigned>(want < cap ? want : cap), 256, 0, stream>>>(flow, mask, H, W, n_pix,
-                                                                                              mask_scale, out);
+    convex_upsample_nhwc8_kernel<<<static_cast<unsigned>(want < cap ? want : cap), 256, 0, stream>>>(flow, mask, mask_bias, H, W,
+                                                                                              n_pix, mask_scale, out);
     return check_launch("convex_upsample_nhwc8_kernel");
   }
   dim3 grid(static_cast<unsigned>((hw + 31) / 32), N);
   if (rate == 8) {
-    convex_upsample_kernel<8><<<grid, dim3(32, 8), 0, stream>>>(flow, mask, H, W, mask_scale, out);
+    convex_upsample_kernel<8><<<grid, dim3(32, 8), 0, stream>>>(flow, mask, mask_bias, H, W, mask_scale, out);
   } else if (rate == 4) {
-    convex_upsample_kernel<4><<<grid, dim3(32, 4), 0, stream>>>(flow, mask, H, W, mask_scale, out);
+    convex_upsample_kernel<4><<<grid, dim3(32, 4), 0, stream>>>(flow, mask, mask_bias, H, W, mask_scale, out);
   } else {
-    convex_upsample_kernel<2><<<grid, dim3(32, 2), 0, stream>>>(flow, mask, H, W, mask_scale, out);
+    convex_upsample_kernel<2><<<grid, dim3(32, 2), 0, stream>>>(flow, mask, mask_bias, H, W, mask_scale, out);
   }
   return check_launch("convex_upsample_kernel");
 }

@@ -321,15 +321,22 @@ class BasicUpdateBlock(nn.Module):
                                   nn.Conv2d(hidden_dim * 2, sps * 9, 1))
 
     def forward(self, net, inp, corr, flow, raw_mask=False, cor1=None, gru_run=None):
-        """``raw_mask=True`` returns the mask logits without the reference's ``0.25 *`` (update_block.py:110):
-        the fused upsampling kernel applies that scale itself, saving a pass over the (N,576,H,W) tensor."""
+        """``raw_mask=True`` returns the mask logits without the last convolution's bias and without the reference's
+        ``0.25 *`` (update_block.py:110): the fused upsampling kernel applies both, saving two passes over the
+        (N,576,H,W) tensor."""
         motion = self.encoder(flow, corr, cor1=cor1)
         if gru_run is not None:
             net = gru_run.step(motion)          # fused channels-last 3xTF32 recurrence; `net` lives in the runner
         else:
             net = self.gru(net, torch.cat((inp, motion), dim=1))
-        mask = self.mask[2](conv_relu(self.mask[0], net))
-        return net, (mask if raw_mask else 0.25 * mask), self.flow_head(net)
+        hidden = conv_relu(self.mask[0], net)
+        if raw_mask:
+            # bias-free logits: the fused upsampling kernel adds self.mask[2].bias and applies the 0.25 itself
+            last = self.mask[2]
+            mask = F.conv2d(hidden, last.weight, None, last.stride, last.padding)
+        else:
+            mask = 0.25 * self.mask[2](hidden)
+        return net, mask, self.flow_head(net)
 
 
 def convex_upsample(flow, mask, rate=8):
@@ -449,7 +456,8 @@ class RAFTStereo(nn.Module):
             coords1 = coords1 + delta
             if not self.final_only or it == self.iters - 1:
                 if fused:
-                    up = fused_convex_upsample(coords1 - org_coords, mask, rate=fnet_ds, mask_scale=0.25)
+                    up = fused_convex_upsample(coords1 - org_coords, mask, rate=fnet_ds, mask_scale=0.25,
+                                               mask_bias=self.update_block.mask[2].bias)
                 else:
                     up = self.convex_upsample(coords1 - org_coords, mask, rate=fnet_ds)
                 outputs.append({"up_disp": up})

@@ -7,11 +7,13 @@ import torch
 from . import _lib
 
 
-def convex_upsample(flow, mask, rate=8, mask_scale=1.0):
+def convex_upsample(flow, mask, rate=8, mask_scale=1.0, mask_bias=None):
     """``flow (N,1,H,W)``, ``mask (N, 9*rate*rate, H, W)`` -> ``(N, 1, rate*H, rate*W)``.
 
     ``mask_scale`` multiplies the mask logits inside the kernel: ``0.25`` folds the update block's
     ``0.25 * mask`` (``blocks/update_block.py:110``) into the same pass (exact: a power of two).
+    ``mask_bias`` ``(9*rate*rate,)`` is added to the logits first -- the bias of the mask head's last 1x1
+    convolution, which can then run bias-free.
     """
     flow = _lib.as_cuda_f32(flow, "flow")
     # a channels-last mask (what cuDNN returns for a channels-last hidden state) is consumed as it lies
@@ -24,10 +26,15 @@ def convex_upsample(flow, mask, rate=8, mask_scale=1.0):
     N, _, H, W = flow.shape
     if tuple(mask.shape) != (N, 9 * rate * rate, H, W):
         raise RuntimeError(f"mask must be (N, 9*rate*rate, H, W) = {(N, 9 * rate * rate, H, W)}, got {tuple(mask.shape)}")
+    if mask_bias is not None:
+        mask_bias = _lib.as_cuda_f32(mask_bias, "mask_bias")
+        if mask_bias.numel() != 9 * rate * rate:
+            raise RuntimeError(f"mask_bias must have {9 * rate * rate} elements, got {mask_bias.numel()}")
     out = torch.empty(N, 1, rate * H, rate * W, dtype=torch.float32, device=flow.device)
     with torch.cuda.device(flow.device):
         _lib.check(
-            _lib.load().nnd_convex_upsample(_lib.ptr(flow), _lib.ptr(mask), N, H, W, int(rate), float(mask_scale),
+            _lib.load().nnd_convex_upsample(_lib.ptr(flow), _lib.ptr(mask), _lib.ptr(mask_bias) if mask_bias is not None else None,
+                                            N, H, W, int(rate), float(mask_scale),
                                             1 if nhwc else 0, _lib.ptr(out), _lib.stream_ptr(flow)),
             "nnd_convex_upsample",
         )

@@ -31,6 +31,14 @@ def test_matches_reference_chain(shape, rate):
         cl = mask.contiguous(memory_format=torch.channels_last)
         got_cl = nb.convex_upsample(flow, cl, rate)
         assert (got_cl - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item())
+    # a per-channel bias folded into the kernel == adding it to the mask first
+    bias = torch.randn(9 * rate * rate, device="cuda")
+    with_bias = nb.convex_upsample(flow, mask, rate, mask_bias=bias)
+    ref_b = reference_chain(flow.double(), (mask + bias.view(1, -1, 1, 1)).double(), rate).float()
+    assert (with_bias - ref_b).abs().max().item() <= 1e-5 * max(1.0, ref_b.abs().max().item())
+    if rate == 8:
+        with_bias_cl = nb.convex_upsample(flow, mask.contiguous(memory_format=torch.channels_last), rate, mask_bias=bias)
+        assert (with_bias_cl - ref_b).abs().max().item() <= 1e-5 * max(1.0, ref_b.abs().max().item())
     # the folded 0.25 scale is exact (power of two): identical bits to scaling the mask first
     assert torch.equal(nb.convex_upsample(flow, mask, rate, mask_scale=0.25), nb.convex_upsample(flow, 0.25 * mask, rate))
 
