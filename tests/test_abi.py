@@ -64,6 +64,24 @@ def test_invalid_arguments_are_reported_not_crashed(lib):
     # unknown precision
     st = lib.nnd_corr1d_build(dummy, dummy, 1, 8, 1, 8, 8, 1, 7, lv, _lib.int_array([8]), None)
     assert st != 0
+    # interleaved IGEV pyramids are an 8-group layout
+    st = lib.nnd_gev_interleave_pool(dummy, 0, 16, 1, 4, 16, 2, 8, 1, lv, None)
+    assert st == 1 and b"8 groups" in lib.nnd_last_error_string()
+    st = lib.nnd_gev_lookup(lv, lv, dummy, 1, 8, 12, 2, 8, 1, 4, dummy, None)
+    assert st == 1 and b"multiple of 8" in lib.nnd_last_error_string()
+    # channels-last AGCL needs C % 16 == 0
+    st = lib.nnd_agcl_offset_nhwc(dummy, dummy, dummy, dummy, 1, 24, 4, 4, 0, dummy, None)
+    assert st == 1 and b"16" in lib.nnd_last_error_string()
+    # upsampling rates are 2, 4, 8
+    st = lib.nnd_convex_upsample(dummy, dummy, None, 1, 4, 4, 3, 1.0, 0, dummy, None)
+    assert st == 1 and b"rate" in lib.nnd_last_error_string()
+    # fused lookup + 1x1 convolution is the 4-level, radius-4 configuration
+    st = lib.nnd_corr1d_lookup_conv1x1(lv, _lib.int_array([8]), _lib.int_array([8]), dummy, 1, 1, 8, 1, 4, dummy, None, 16, 1, 0,
+                                       dummy, None)
+    assert st == 1 and b"4-level" in lib.nnd_last_error_string()
+    # GRU glue: channel counts in quads
+    st = lib.nnd_gru_gate_r(dummy, dummy, dummy, 8, 6, dummy, dummy, 36, None)
+    assert st == 1 and b"ch % 4" in lib.nnd_last_error_string()
 
 
 def test_python_layer_refuses_cpu_tensors():
