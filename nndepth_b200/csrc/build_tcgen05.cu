@@ -24,8 +24,10 @@
 //     systematic shrink of every product that costs 0.0126 px of final EPE at KITTI/32 iterations
 //     against 0.0002 px with RN (tools/exp_epe.py).  full[s] (TMA) -> ready[s] (rounded) -> MMA.
 //   * one elected thread issues tcgen05.mma M=128, N=roundup16(W2), K=8 per 8 channels; both M tiles
-//     of a row share every B stage and accumulate in TMEM (2 x n_cols columns per job, two jobs
-//     double-buffered when that fits 512 columns).
+//     of a row share every B stage.  TMEM is a ring of 512 / n_cols tile slots, one M tile of fp32
+//     accumulators each: with 160-column tiles (KITTI) that is three slots, so the next row's first tile
+//     starts accumulating while the epilogue still drains the previous row, and its second tile as soon
+//     as the previous row's first tile has been read; narrower volumes double-buffer whole rows.
 //   * four epilogue warps, each on its own (no cross-warp barrier), read their TMEM lane quarter 32
 //     columns at a time (tcgen05.ld 32x32b.x32), scale by 1/sqrt(C), pool in registers (a thread owns
 //     one volume row -> 2/4/8-wide poolings are intra-thread, summed pairwise and halved like
@@ -59,6 +61,8 @@ constexpr int NUM_THREADS = 32 * (TMA_WARP + 1);
 constexpr int TMEM_COLS = 512;
 constexpr int CHUNK = 32;         // volume columns per epilogue step
 constexpr int MAX_STAGES = 6;
+constexpr int MAX_TSLOTS = 16;     // 512 TMEM columns / 32
+constexpr int BAR_BYTES = 512;     // 3 * MAX_STAGES + 2 * MAX_TSLOTS mbarriers + the TMEM base word
 
 // epilogue staging, per warp and buffer set: level 0..3 tiles of 32 rows x {32,16,8,4} floats (7.5 KB, padded
 // to 8 KB so that every set keeps the 1024-byte alignment the 128B swizzle pattern is anchored to)
@@ -77,8 +81,8 @@ struct BuildParams {
   int b_region_boxes;  // ceil(min(W2, 256) / 32)
   int stages;
   int stage_bytes;     // (a_region_boxes + b_region_boxes) * BOX_BYTES
-  int n_slots;         // accumulator slots in TMEM (2 when two jobs' accumulators fit 512 columns)
-  int slot_cols;
+  int n_tslots;        // tile slots in TMEM: 512 / slot_cols (one 128-row M tile of accumulators each)
+  int slot_cols;       // b_region_boxes * 32
   float scale_div;
   float scale_inv;
   int scale_is_pow2;
@@ -240,7 +244,7 @@ corr1d_build_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   uint8_t* epi = smem + static_cast<size_t>(p.stages) * p.stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi + 2 * EPI_SET);
   // bars: full[s] (TMA landed), ready[s] (rounded to TF32), empty[s] (MMAs retired), tmem_full[slot], tmem_empty[slot]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 2 * MAX_TSLOTS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -249,7 +253,7 @@ corr1d_build_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   auto ready_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
   auto empty_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + s); };
   auto tmem_full_bar = [&](uint32_t slot) { return bar_base + 8u * (3 * MAX_STAGES + slot); };
-  auto tmem_empty_bar = [&](uint32_t slot) { return bar_base + 8u * (3 * MAX_STAGES + 2 + slot); };
+  auto tmem_empty_bar = [&](uint32_t slot) { return bar_base + 8u * (3 * MAX_STAGES + MAX_TSLOTS + slot); };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -257,7 +261,7 @@ corr1d_build_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       mbar_init(ready_bar(s), LOADER_WARPS);
       mbar_init(empty_bar(s), 1);
     }
-    for (uint32_t slot = 0; slot < 2; ++slot) {
+    for (uint32_t slot = 0; slot < static_cast<uint32_t>(p.n_tslots); ++slot) {
       mbar_init(tmem_full_bar(slot), 1);
       mbar_init(tmem_empty_bar(slot), EPI_THREADS);
     }
@@ -353,18 +357,18 @@ corr1d_build_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t acc_count = 0;  // accumulator slot = acc_count % n_slots
+      uint32_t tile_seq = 0;  // every M tile takes the next TMEM tile slot of the ring
       for (long long job = blockIdx.x; job < p.jobs; job += gridDim.x) {
         const JobGeom g = job_geom(p, job);
         const uint32_t idesc = umma_idesc_tf32(g.n_mma);
-        for (int pass = 0; pass < p.m_passes; ++pass, ++acc_count) {
+        for (int pass = 0; pass < p.m_passes; ++pass) {
           const int m_start = pass * MAX_M;
           const int tiles = (min(p.W1 - m_start, MAX_M) + TILE_M - 1) / TILE_M;
-          const uint32_t slot = p.n_slots == 2 ? (acc_count & 1) : 0;
-          const uint32_t slot_phase = (p.n_slots == 2 ? (acc_count >> 1) : acc_count) & 1;
-          const uint32_t d_base = tmem_base + slot * p.slot_cols;
-          mbar_wait(tmem_empty_bar(slot), slot_phase ^ 1);  // the epilogue has drained this slot
-          tc_fence_after();
+          uint32_t slot[2], d_base[2];
+          for (int t = 0; t < tiles; ++t) {
+            slot[t] = (tile_seq + t) % p.n_tslots;
+            d_base[t] = tmem_base + slot[t] * p.slot_cols;
+          }
           for (int kb = 0; kb < k_blocks; ++kb) {
             mbar_wait(ready_bar(stage), phase);
             tc_fence_after();
@@ -374,14 +378,20 @@ corr1d_build_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             for (int ks = 0; ks < KB / 8; ++ks) {
               const uint64_t bdesc = umma_desc_mn_sw128_32b(bbase + ks * 1024, BOX_BYTES, 512);
               for (int t = 0; t < tiles; ++t) {
+                if ((kb | ks) == 0) {
+                  // first write into this tile slot: the epilogue must have drained its previous tenant
+                  mbar_wait(tmem_empty_bar(slot[t]), (((tile_seq + t) / p.n_tslots) & 1) ^ 1);
+                  tc_fence_after();
+                }
                 const uint64_t adesc = umma_desc_mn_sw128_32b(sbase + t * 4 * BOX_BYTES + ks * 1024, BOX_BYTES, 512);
-                tc_mma_tf32(d_base + t * g.n_cols, adesc, bdesc, idesc, (kb | ks) != 0 ? 1u : 0u);
+                tc_mma_tf32(d_base[t], adesc, bdesc, idesc, (kb | ks) != 0 ? 1u : 0u);
               }
             }
             tc_commit(empty_bar(stage));  // frees this smem stage when the MMAs above retire
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
-          tc_commit(tmem_full_bar(slot));  // accumulators of this pass complete
+          for (int t = 0; t < tiles; ++t) tc_commit(tmem_full_bar(slot[t]));  // accumulators of this pass complete
+          tile_seq += tiles;
         }
       }
     }
@@ -391,7 +401,7 @@ corr1d_build_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     // scale + pool -> its own swizzled staging tiles -> TMA stores issued by lanes 0..3 (one level each).
     // A warp whose 32 rows lie past W1 (the ragged second M tile) skips the tile altogether.
     const int quarter = warp;
-    uint32_t acc_count = 0;
+    uint32_t tile_seq = 0;
     int chunk_parity = 0;
     uint8_t* my_sets = epi + quarter * EPI_WARP_SET;  // + chunk_parity * EPI_SET
     const CUtensorMap* my_map = lane == 0 ? &map_l0 : lane == 1 ? &map_l1 : lane == 2 ? &map_l2 : &map_l3;
@@ -400,28 +410,26 @@ corr1d_build_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     for (long long job = blockIdx.x; job < p.jobs; job += gridDim.x) {
       const JobGeom g = job_geom(p, job);
       const int n_chunks32 = g.n_cols / CHUNK;
-      for (int pass = 0; pass < p.m_passes; ++pass, ++acc_count) {
+      for (int pass = 0; pass < p.m_passes; ++pass) {
         const int m_start = pass * MAX_M;
         const int tiles = (min(p.W1 - m_start, MAX_M) + TILE_M - 1) / TILE_M;
-        const uint32_t slot = p.n_slots == 2 ? (acc_count & 1) : 0;
-        const uint32_t slot_phase = (p.n_slots == 2 ? (acc_count >> 1) : acc_count) & 1;
-        const uint32_t d_base = tmem_base + slot * p.slot_cols + (static_cast<uint32_t>(quarter * 32) << 16);
-        mbar_wait(tmem_full_bar(slot), slot_phase);
-        tc_fence_after();
-        // the last tile in which this warp owns valid rows: after its last TMEM read the slot is handed back
-        int last_tile = -1;
-        for (int t = 0; t < tiles; ++t)
-          if (m_start + t * TILE_M + quarter * 32 < p.W1) last_tile = t;
-        if (last_tile < 0) {
-          tc_fence_before();
-          mbar_arrive(tmem_empty_bar(slot));
-        }
-        for (int t = 0; t <= last_tile; ++t) {
+        const int last_tile = tiles - 1;
+        for (int t = 0; t <= last_tile; ++t, ++tile_seq) {
+          const uint32_t slot = tile_seq % p.n_tslots;
+          const uint32_t d_base = tmem_base + slot * p.slot_cols + (static_cast<uint32_t>(quarter * 32) << 16);
+          mbar_wait(tmem_full_bar(slot), (tile_seq / p.n_tslots) & 1);
+          tc_fence_after();
           const int mrow = m_start + t * TILE_M + quarter * 32;
+          if (mrow >= p.W1) {  // no valid rows of this tile in my lane quarter: hand the slot back at once
+            tc_fence_before();
+            mbar_arrive(tmem_empty_bar(slot));
+            continue;
+          }
           for (int ch = 0; ch < n_chunks32; ++ch) {
             float v[32];
-            tc_ld32(d_base + t * g.n_cols + ch * CHUNK, v);
-            if (t == last_tile && ch == n_chunks32 - 1) {
+            tc_ld32(d_base + ch * CHUNK, v);
+            if (ch == n_chunks32 - 1) {
+              // my last TMEM read of this tile: the slot goes back to the MMA warp while I finish the stores
               tc_fence_before();
               mbar_arrive(tmem_empty_bar(slot));
             }
@@ -564,7 +572,7 @@ nnd_status corr1d_build_tf32(const float* fmap1, const float* fmap2, int B, int 
   const int a_tiles = (min(W1, MAX_M) + TILE_M - 1) / TILE_M;
   p.stage_bytes = (p.a_region_boxes + p.b_region_boxes) * BOX_BYTES;
   const int tail_boxes = 4 * a_tiles - p.a_region_boxes - p.b_region_boxes;  // > 0 only for tiny W2
-  const int budget = 227 * 1024 - 1024 /*alignment slack*/ - 2 * EPI_SET - 256 /*barriers*/ -
+  const int budget = 227 * 1024 - 1024 /*alignment slack*/ - 2 * EPI_SET - BAR_BYTES /*barriers*/ -
                      (tail_boxes > 0 ? tail_boxes * BOX_BYTES : 0);
   p.stages = budget / p.stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
@@ -572,10 +580,9 @@ nnd_status corr1d_build_tf32(const float* fmap1, const float* fmap2, int B, int 
     set_error("corr1d_build(tf32): a pipeline stage of %d bytes leaves no room for double buffering", p.stage_bytes);
     return NND_ERR_UNSUPPORTED;
   }
-  const int acc_cols = a_tiles * p.b_region_boxes * BOX_W;  // TMEM columns one pass accumulates into
-  p.n_slots = 2 * acc_cols <= TMEM_COLS ? 2 : 1;
-  p.slot_cols = acc_cols;
-  const size_t smem_bytes = 1024 + static_cast<size_t>(p.stages) * p.stage_bytes + 2 * EPI_SET + 256;
+  p.slot_cols = p.b_region_boxes * BOX_W;         // TMEM columns of one M tile
+  p.n_tslots = TMEM_COLS / p.slot_cols;            // >= 2 (slot_cols <= 256): a ring of tile slots
+  const size_t smem_bytes = 1024 + static_cast<size_t>(p.stages) * p.stage_bytes + 2 * EPI_SET + BAR_BYTES;
 
   alignas(64) CUtensorMap map_a, map_b, map_l[4];
   {
