@@ -411,6 +411,98 @@ agcl_cl_kernel(const float* __restrict__ L, const float* __restrict__ R, const f
   store_result_tile(res, pix0, n_pix, hw, out);
 }
 
+// Four pixels per warp (C = 128 or 256): lane = (pixel = lane / 8, sub-lane sl = lane % 8).  The per-tap
+// bookkeeping (footprint fetch, corner addresses, reduction, result store) is the same number of warp
+// instructions as in the one-pixel-per-warp kernel above but now serves four pixels, and it was two thirds
+// of that kernel's instruction stream (ncu: 1 280 warp instructions per pixel, IPC 2.0, issue-bound -- a
+// smooth flow field instead of white noise did not change its time).  The 8 sub-lanes of a pixel read one
+// full 128-byte line per chunk; chunk j covers channels 32j .. 32j+31, so it belongs to group j / (CH/4)
+// at compile time and each lane keeps four group accumulators.
+template <int MODE, int CH>   // CH = C / 32 chunks per lane (4 or 8)
+__global__ void __launch_bounds__(32 * CL_WARPS, 2)
+agcl_cl4_kernel(const float* __restrict__ L, const float* __restrict__ R, const float* __restrict__ flow,
+                const float* __restrict__ extra, int H, int W, long long n_pix, int small_patch, float* __restrict__ out) {
+  constexpr int C = 32 * CH;
+  constexpr int CPG = CH / AGCL_GROUPS;   // chunks per group
+  __shared__ WarpFootprint fp[CL_WARPS][4][AGCL_TAPS];
+  __shared__ float res[AGCL_GROUPS * AGCL_TAPS][CL_PIX + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int px = lane >> 3, sl = lane & 7;
+  const long long hw = static_cast<long long>(H) * W;
+  const long long pix0 = static_cast<long long>(blockIdx.x) * CL_PIX;
+  const float inv_cnt_div = static_cast<float>(C / AGCL_GROUPS);
+
+  // footprints of this warp's 4 pixels x 9 taps: 36 (pixel, tap) pairs over 32 lanes, two rounds
+  for (int pair = lane; pair < 4 * AGCL_TAPS; pair += 32) {
+    const int pp = pair / AGCL_TAPS, k = pair - pp * AGCL_TAPS;
+    const long long pix = pix0 + warp * 4 + pp;
+    WarpFootprint f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { f.off[q] = 0; f.wt[q] = 0.f; }
+    if (pix < n_pix) {
+      const long long n = pix / hw;
+      const int p = static_cast<int>(pix - n * hw);
+      const int y = p / W, x = p - y * W;
+      int dx, dy;
+      tap_delta(k, small_patch != 0, dx, dy);
+      if (MODE == 0) {
+        const float* fl = flow + n * 2 * hw + p;
+        const float* ex = extra + (n * 2 * AGCL_TAPS + 2 * k) * hw + p;
+        // (grid + flow) + (d_k + extra_k), in that association order (cost_volume.py:133-137)
+        const float pxf = __fadd_rn(__fadd_rn(static_cast<float>(x), __ldg(fl)), __fadd_rn(static_cast<float>(dx), __ldg(ex)));
+        const float pyf = __fadd_rn(__fadd_rn(static_cast<float>(y), __ldg(fl + hw)), __fadd_rn(static_cast<float>(dy), __ldg(ex + hw)));
+        const Footprint ff = make_footprint(pxf, pyf, H, W);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          f.off[q] = ff.off[q] >= 0 ? ff.off[q] * C : 0;     // out-of-image corner: weight 0, any valid address
+          f.wt[q] = ff.off[q] >= 0 ? ff.wt[q] : 0.f;
+        }
+      } else {
+        const int xx = min(max(x + dx, 0), W - 1), yy = min(max(y + dy, 0), H - 1);
+        f.off[0] = (yy * W + xx) * C;
+        f.wt[0] = 1.f;
+      }
+    }
+    fp[warp][pp][k] = f;
+  }
+  __syncwarp();
+
+  const int slot = warp * 4 + px;
+  const long long pix = pix0 + slot;
+  const bool valid = pix < n_pix;
+  const long long n = valid ? pix / hw : 0;
+  const long long p = valid ? pix - n * hw : 0;
+  const float* lp = L + (n * hw + p) * C + 4 * sl;
+  const float* rb = R + n * hw * C + 4 * sl;
+  float4 lv[CH];
+#pragma unroll
+  for (int j = 0; j < CH; ++j) lv[j] = valid ? ldg_f4(lp + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+
+#pragma unroll 1
+  for (int k = 0; k < AGCL_TAPS; ++k) {
+    const WarpFootprint f = fp[warp][px][k];
+    float acc[AGCL_GROUPS] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      if (MODE == 0) {
+        float4 v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = ldg_f4(rb + f.off[q] + 32 * j);
+        acc[j / CPG] = dot4(lv[j], blend4(v, f.wt), acc[j / CPG]);
+      } else {
+        acc[j / CPG] = dot4(lv[j], ldg_f4(rb + f.off[0] + 32 * j), acc[j / CPG]);
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < AGCL_GROUPS; ++g) {
+      const float r = group_reduce8(acc[g]);
+      if (sl == 0) res[g * AGCL_TAPS + k][slot] = __fdiv_rn(r, inv_cnt_div);  // torch.mean over C/4
+    }
+  }
+  __syncthreads();
+  store_result_tile(res, pix0, n_pix, hw, out);
+}
+
 // iter-mode pass 1: Rw[n,p,:] = zero-padded bilinear sample of R at p + flow(p), channels-last in and out
 __global__ void __launch_bounds__(32 * CL_WARPS)
 agcl_warp_cl_kernel(const float* __restrict__ R, const float* __restrict__ flow, int C, int H, int W, long long n_pix,
@@ -523,8 +615,17 @@ nnd_status nnd_agcl_offset_nhwc(const float* fmap1_nhwc, const float* fmap2_nhwc
   const long long n_pix = static_cast<long long>(N) * H * W;
   const long long blocks = (n_pix + CL_PIX - 1) / CL_PIX;
   NND_REQUIRE(blocks <= 0x7fffffffLL, "agcl_offset_nhwc: too many pixels");
-  agcl_cl_kernel<0><<<static_cast<unsigned>(blocks), 32 * CL_WARPS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      fmap1_nhwc, fmap2_nhwc, flow, extra_offset, C, H, W, n_pix, small_patch ? 1 : 0, out);
+  cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream);
+  if (C == 256) {
+    agcl_cl4_kernel<0, 8><<<static_cast<unsigned>(blocks), 32 * CL_WARPS, 0, st_>>>(fmap1_nhwc, fmap2_nhwc, flow, extra_offset, H, W,
+                                                                                n_pix, small_patch ? 1 : 0, out);
+  } else if (C == 128) {
+    agcl_cl4_kernel<0, 4><<<static_cast<unsigned>(blocks), 32 * CL_WARPS, 0, st_>>>(fmap1_nhwc, fmap2_nhwc, flow, extra_offset, H, W,
+                                                                                n_pix, small_patch ? 1 : 0, out);
+  } else {
+    agcl_cl_kernel<0><<<static_cast<unsigned>(blocks), 32 * CL_WARPS, 0, st_>>>(fmap1_nhwc, fmap2_nhwc, flow, extra_offset, C, H, W,
+                                                                            n_pix, small_patch ? 1 : 0, out);
+  }
   return check_launch("agcl_cl_kernel<offset>");
 }
 
@@ -547,8 +648,16 @@ nnd_status nnd_agcl_iter_nhwc(const float* fmap1_nhwc, const float* fmap2_nhwc, 
                                                                                     warped_ws);
   st = check_launch("agcl_warp_cl_kernel");
   if (st != NND_OK) return st;
-  agcl_cl_kernel<1><<<static_cast<unsigned>(blocks), 32 * CL_WARPS, 0, stream>>>(fmap1_nhwc, warped_ws, flow, nullptr, C,
-                                                                                H, W, n_pix, small_patch ? 1 : 0, out);
+  if (C == 256) {
+    agcl_cl4_kernel<1, 8><<<static_cast<unsigned>(blocks), 32 * CL_WARPS, 0, stream>>>(fmap1_nhwc, warped_ws, flow, nullptr, H, W,
+                                                                                   n_pix, small_patch ? 1 : 0, out);
+  } else if (C == 128) {
+    agcl_cl4_kernel<1, 4><<<static_cast<unsigned>(blocks), 32 * CL_WARPS, 0, stream>>>(fmap1_nhwc, warped_ws, flow, nullptr, H, W,
+                                                                                   n_pix, small_patch ? 1 : 0, out);
+  } else {
+    agcl_cl_kernel<1><<<static_cast<unsigned>(blocks), 32 * CL_WARPS, 0, stream>>>(fmap1_nhwc, warped_ws, flow, nullptr, C, H, W,
+                                                                               n_pix, small_patch ? 1 : 0, out);
+  }
   return check_launch("agcl_cl_kernel<iter>");
 }
 

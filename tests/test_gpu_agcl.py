@@ -53,13 +53,14 @@ def test_offset_mode_with_attention_hook(golden):
 
 
 @pytest.mark.parametrize("shape", [(2, 64, 22, 40), (1, 32, 45, 80), (1, 8, 7, 61), (1, 4, 2, 2),
-                                   (1, 16, 4, 6), (1, 48, 5, 9), (1, 512, 3, 4), (1, 528, 2, 3)])
+                                   (1, 16, 4, 6), (1, 48, 5, 9), (1, 512, 3, 4), (1, 528, 2, 3), (2, 256, 5, 7), (1, 128, 3, 11)])
 @pytest.mark.parametrize("small", [False, True])
 def test_against_oracle(shape, small):
     """Scales of BASELINE config 3 (1/32 and 1/16 of 720x1280, reduced channels) + ragged shapes.
 
     C % 16 == 0 and C <= 512 take the channels-last kernels (1, 2, 3 and 4 chunks per lane; idle sub-lanes
-    at C = 16 / 48), the others (C = 8, 4, 528) the generic NCHW kernels."""
+    at C = 16 / 48; C = 128 and 256 the four-pixels-per-warp variant), the others (C = 8, 4, 528) the generic
+    NCHW kernels."""
     import nndepth_b200 as nb
     rng = np.random.default_rng(7)
     N, C, H, W = shape
