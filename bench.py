@@ -246,7 +246,7 @@ def run_ours(args):
     # all cuDNN convolutions in TF32 drift 0.0147 px (outside the bar); the drift comes from the ConvGRU
     # recurrence.  "mixed" keeps the ConvGRU in fp32 and lets the encoder, motion encoder, flow and mask heads
     # use TF32 tensor cores: 0.0021 px.  "mixed3x" (default) runs the ConvGRU as error-compensated 3xTF32
-    # (operands split hi + lo by nnd_split_tf32, fp32-equivalent to 2^-22): 0.0020 px at 2x the speed of
+    # (operands split hi + lo, fp32-equivalent to 2^-22, fused channels-last glue kernels): 0.0031 px at 3.5x the speed of
     # "mixed".  "fp32" (0.0002 px) and "tf32" are selectable; `value` is never measured in the
     # out-of-tolerance "tf32" mode unless asked for explicitly.
 
@@ -359,7 +359,7 @@ def run_ours(args):
                                             "mixed": "ConvGRU cuDNN fp32, other convolutions cuDNN TF32",
                                             "mixed3x": "ConvGRU error-compensated 3xTF32 (fp32-equivalent), other "
                                                        "convolutions cuDNN TF32"}[args.dense_precision]),
-            "parity": {"final_epe_px_vs_reference": {"fp32": 0.00016, "mixed": 0.0021, "mixed3x": 0.0020, "tf32": 0.0147}[args.dense_precision],
+            "parity": {"final_epe_px_vs_reference": {"fp32": 0.00016, "mixed": 0.0021, "mixed3x": 0.0031, "tf32": 0.0147}[args.dense_precision],
                        "bar_px": 0.01, "source": "tests/test_gpu_raft_model.py::test_kitti_32_iterations, tools/exp_epe_modules.py"},
             "data": "synthetic", "config": workload_config(world), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT,
@@ -407,7 +407,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--dense-precision", default="mixed3x", choices=["fp32", "mixed", "mixed3x", "tf32"],
                     help="cuDNN layers: fp32 everywhere (0.0002 px EPE); ConvGRU fp32 + TF32 elsewhere (0.0021 px); "
-                         "ConvGRU error-compensated 3xTF32 + TF32 elsewhere (default, 0.0020 px); TF32 everywhere "
+                         "ConvGRU error-compensated 3xTF32 + TF32 elsewhere (default, 0.0031 px); TF32 everywhere "
                          "(0.0147 px: outside the 0.01 px bar)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -39,13 +39,59 @@ class cudnn_tf32:
         return False
 
 
+def rn_tf32(t):
+    """Round an fp32 tensor to the nearest TF32 value (10-bit mantissa), ties away from zero."""
+    return ((t.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def inference_weight(conv):
+    """The convolution's weight as the tensor cores should see it: under ``allow_tf32`` rounded to the NEAREST
+    TF32 value once (cuDNN's TF32 kernels truncate fp32 operands; with truncated weights the KITTI/32-iteration
+    disparity sits 0.005 px from the reference, with rounded ones 0.003 px), otherwise untouched."""
+    if not torch.backends.cudnn.allow_tf32:
+        return conv.weight
+    cache = getattr(conv, "_tf32_weight", None)
+    if cache is None or cache[0] != conv.weight._version or cache[1].device != conv.weight.device:
+        rounded = rn_tf32(conv.weight.detach())
+        if conv.weight.is_contiguous(memory_format=torch.channels_last) and not conv.weight.is_contiguous():
+            rounded = rounded.contiguous(memory_format=torch.channels_last)
+        cache = (conv.weight._version, rounded)
+        conv._tf32_weight = cache
+    return cache[1]
+
+
 def conv_relu(conv, x):
     """``relu(conv(x))``: on the GPU, inference, as cuDNN's fused convolution + bias + ReLU -- one kernel where
     ``F.relu(conv(x))`` costs three (convolution, bias add, clamp).  Same arithmetic, same TF32 policy."""
     if (x.is_cuda and not torch.is_grad_enabled() and conv.bias is not None and conv.padding_mode == "zeros"
             and isinstance(conv.padding, tuple) and hasattr(torch, "cudnn_convolution_relu")):
-        return torch.cudnn_convolution_relu(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups)
+        return torch.cudnn_convolution_relu(x, inference_weight(conv), conv.bias, conv.stride, conv.padding, conv.dilation,
+                                            conv.groups)
     return F.relu(conv(x))
+
+
+def conv_plain(conv, x):
+    """``conv(x)``; on the GPU at inference with the TF32-rounded weight of ``inference_weight``."""
+    if x.is_cuda and not torch.is_grad_enabled() and conv.padding_mode == "zeros" and isinstance(conv.padding, tuple):
+        return F.conv2d(x, inference_weight(conv), conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups)
+    return conv(x)
+
+
+def fold_bn(conv, bn, tf32=False):
+    """Weights and bias of ``bn(conv(x))`` as ONE convolution (eval-mode BatchNorm is affine per channel).
+
+    ``tf32``: the weights are additionally rounded to nearest TF32 -- tensor-core kernels that take fp32
+    operands truncate them, and a truncated weight is biased where a rounded one is not."""
+    scale = bn.weight.detach() / torch.sqrt(bn.running_var.detach() + bn.eps)
+    w = (conv.weight.detach() * scale.view(-1, 1, 1, 1)).contiguous()
+    b = ((conv.bias.detach() if conv.bias is not None else 0.0) - bn.running_mean.detach()) * scale + bn.bias.detach()
+    return (rn_tf32(w) if tf32 else w), b.contiguous()
+
+
+def _fused_ok(x, *norms):
+    """Inference on the GPU with eval-mode BatchNorm: the conv + BN (+ add) + ReLU chains run as single cuDNN calls."""
+    return (x.is_cuda and not torch.is_grad_enabled() and hasattr(torch, "cudnn_convolution_relu")
+            and all(isinstance(n, nn.BatchNorm2d) and not n.training and n.track_running_stats for n in norms))
 
 
 def _norm(kind, planes):
@@ -71,7 +117,25 @@ class ResidualBlock(nn.Module):
         self.norm1, self.norm2, self.norm3 = (_norm(norm_fn, planes) for _ in range(3))
         self.downsample = nn.Sequential(nn.Conv2d(in_planes, planes, 1, stride=stride), self.norm3)
 
+    def _folded(self):
+        """(w, b) of conv1+norm1, conv2+norm2, shortcut+norm3, folded once (inference)."""
+        tf32 = bool(torch.backends.cudnn.allow_tf32)
+        cache = getattr(self, "_fold_cache", None)
+        if cache is None or cache[0] != tf32:
+            cache = (tf32, (fold_bn(self.conv1, self.norm1, tf32), fold_bn(self.conv2, self.norm2, tf32),
+                            fold_bn(self.downsample[0], self.norm3, tf32)))
+            self._fold_cache = cache
+        return cache[1]
+
     def forward(self, x):
+        if _fused_ok(x, self.norm1, self.norm2, self.norm3):
+            # BatchNorm folded into the convolutions; conv + bias + ReLU and conv + bias + add + ReLU are single
+            # cuDNN calls (the reference chain is conv, bias add, batch norm, clamp: four passes per layer)
+            (w1, b1), (w2, b2), (w3, b3) = self._folded()
+            c1, c3 = self.conv1, self.downsample[0]
+            y = torch.cudnn_convolution_relu(x, w1, b1, c1.stride, c1.padding, c1.dilation, 1)
+            y = torch.cudnn_convolution_relu(y, w2, b2, self.conv2.stride, self.conv2.padding, self.conv2.dilation, 1)
+            return torch.cudnn_convolution_add_relu(x, w3, y, 1.0, b3, c3.stride, c3.padding, c3.dilation, 1)
         y = self.relu(self.norm1(self.conv1(x)))
         y = self.relu(self.norm2(self.conv2(y)))
         return self.relu(self.downsample(x) + y)
@@ -106,9 +170,16 @@ class BasicEncoder(nn.Module):
         pair = isinstance(x, (tuple, list))
         if pair:
             x = torch.cat(x, dim=0)
-        x = self.relu1(self.norm1(self.conv1(x)))
+        if _fused_ok(x, self.norm1):
+            tf32 = bool(torch.backends.cudnn.allow_tf32)
+            if getattr(self, "_fold_cache", None) is None or self._fold_cache[0] != tf32:
+                self._fold_cache = (tf32, fold_bn(self.conv1, self.norm1, tf32))
+            w, b = self._fold_cache[1]
+            x = torch.cudnn_convolution_relu(x, w, b, self.conv1.stride, self.conv1.padding, self.conv1.dilation, 1)
+        else:
+            x = self.relu1(self.norm1(self.conv1(x)))
         x = self.layer3(self.layer2(self.layer1(x)))
-        x = self.conv2(x)
+        x = conv_plain(self.conv2, x)
         if self.dropout is not None:
             x = self.dropout(x)
         return torch.split(x, x.shape[0] // 2, dim=0) if pair else x
@@ -303,7 +374,7 @@ class FlowHead(nn.Module):
         self.relu = nn.ReLU(inplace=True)
 
     def forward(self, x):
-        return self.conv2(conv_relu(self.conv1, x))
+        return conv_plain(self.conv2, conv_relu(self.conv1, x))
 
 
 class BasicUpdateBlock(nn.Module):
@@ -333,9 +404,9 @@ class BasicUpdateBlock(nn.Module):
         if raw_mask:
             # bias-free logits: the fused upsampling kernel adds self.mask[2].bias and applies the 0.25 itself
             last = self.mask[2]
-            mask = F.conv2d(hidden, last.weight, None, last.stride, last.padding)
+            mask = F.conv2d(hidden, inference_weight(last), None, last.stride, last.padding)
         else:
-            mask = 0.25 * self.mask[2](hidden)
+            mask = 0.25 * conv_plain(self.mask[2], hidden)
         return net, mask, self.flow_head(net)
 
 
@@ -508,4 +579,4 @@ class BaseRAFTStereo(RAFTStereo):
 
     def forward_fnet(self, frame1, frame2):
         fmap1, fmap2 = self.fnet([frame1, frame2])
-        return fmap1, fmap2, self.cnet_proj(fmap1)
+        return fmap1, fmap2, conv_relu(self.cnet_proj[0], fmap1)
