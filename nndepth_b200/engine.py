@@ -99,7 +99,7 @@ class StereoEngine:
     ``(B,1,H,W)`` on the host (pinned) -- H2D copy, pad, forward, unpad and D2H all on the current stream.
     """
 
-    def __init__(self, model, device=None, use_cuda_graph=True, divis_by=32, final_only=False):
+    def __init__(self, model, device=None, use_cuda_graph=True, divis_by=32, final_only=False, channels_last_encoder=True):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.model = model.to(self.device).eval()
         # final_only=False keeps the reference forward's behaviour (an upsampled map per iteration);
@@ -115,6 +115,11 @@ class StereoEngine:
             head = getattr(ub, name, None)
             if head is not None:
                 head.to(memory_format=torch.channels_last)
+        # the feature encoder runs on cuDNN's tensor-core kernels, which are NHWC inside: channels-last weights and
+        # a channels-last input image spare it a layout conversion around every convolution
+        self.channels_last_encoder = channels_last_encoder
+        if channels_last_encoder and hasattr(self.model, "fnet"):
+            self.model.fnet.to(memory_format=torch.channels_last)
         self.use_cuda_graph = use_cuda_graph
         self.divis_by = divis_by
         self._dev_in = {}
@@ -125,6 +130,9 @@ class StereoEngine:
         """Device tensors in, device disparity out (padded internally, un-padded on return)."""
         padder = Padder(left.shape, self.divis_by)
         left_p, right_p = padder.pad(left, right)
+        if self.channels_last_encoder:
+            left_p = left_p.contiguous(memory_format=torch.channels_last)
+            right_p = right_p.contiguous(memory_format=torch.channels_last)
         if self.use_cuda_graph:
             outputs = self.model.forward_graphed(left_p, right_p)
         else:

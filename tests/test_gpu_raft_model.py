@@ -106,3 +106,23 @@ def test_fused_gru_matches_unfused_3xtf32():
             assert fused.shape == h_ref.shape
             assert (fused - h_ref).abs().max().item() < 2e-5
             assert (fused - h_fp32).abs().max().item() < 2e-5
+
+
+def test_engine_bench_configuration_stays_inside_the_bar(golden):
+    """The exact configuration bench.py times -- StereoEngine (channels-last encoder, CUDA graph, fused GRU glue,
+    fused lookup / upsampling), dense_precision = "mixed3x" -- against the reference disparity."""
+    from nndepth_b200.engine import StereoEngine
+    from nndepth_b200.raft_stereo import BaseRAFTStereo
+    g = golden("raft_kitti")
+    torch.manual_seed(0)
+    model = BaseRAFTStereo(iters=int(g["iters"])).eval()
+    model.dense_precision = "mixed3x"
+    engine = StereoEngine(model, device="cuda", use_cuda_graph=True)
+    left, right = (t.cuda() for t in seeded_pair(g["shape"]))
+    ref = torch.from_numpy(g["final_up_disp"]).cuda()
+    for _ in range(2):                                  # second call replays the captured graph
+        out = engine.infer_device(left, right)
+        assert out.shape == ref.shape
+        assert epe(out, ref) < EPE_BAR, epe(out, ref)
+    host = engine.infer(left.cpu().pin_memory(), right.cpu().pin_memory())
+    assert epe(host.cuda(), ref) < EPE_BAR
