@@ -202,13 +202,14 @@ nnd_status nnd_split_tf32(const float* x, int N, int C, long long hw, float* out
  * convolutions.  One staging buffer S (N, H*W, ctot) with row layout
  *     [ h_hi(ch) | h_lo(ch) | h_hi(ch) | x_hi(cx) | x_lo(cx) | x_hi(cx) ],  ctot = 3*(ch + cx),
  * is the NHWC input of all four convolutions of an iteration (weights [w_hi ; w_hi ; w_lo] per part).
- *   nnd_gru_stage:  src (N, C, H*W) NCHW -> [hi | lo | hi] at channel offsets off_hi0 / off_lo / off_hi1.
+ *   nnd_gru_stage:  src (N, C, H*W) NCHW, or (N, H*W, C) when src_channels_last != 0 -> [hi | lo | hi] at channel
+ *                   offsets off_hi0 / off_lo / off_hi1.
  *   nnd_gru_gate_r: zr_pre (pixels, 2ch) NHWC conv output, bias_zr (2ch), h (pixels, ch) ->
  *                   z = sigmoid(z_pre + b) (pixels, ch);  S.h <- split(sigmoid(r_pre + b) * h).
  *   nnd_gru_gate_h: q_pre (pixels, ch), bias_q (ch), z, h -> h <- (1 - z) * h + z * tanh(q_pre + b) in place;
  *                   S.h <- split(h). */
-nnd_status nnd_gru_stage(const float* src, int N, int C, long long hw, float* S, int ctot, int off_hi0, int off_lo,
-                         int off_hi1, nnd_stream_t stream);
+nnd_status nnd_gru_stage(const float* src, int src_channels_last, int N, int C, long long hw, float* S, int ctot,
+                         int off_hi0, int off_lo, int off_hi1, nnd_stream_t stream);
 nnd_status nnd_gru_gate_r(const float* zr_pre, const float* bias_zr, const float* h, long long pixels, int ch,
                           float* z, float* S, int ctot, nnd_stream_t stream);
 nnd_status nnd_gru_gate_h(const float* q_pre, const float* bias_q, const float* z, long long pixels, int ch,

@@ -63,6 +63,23 @@ gru_stage_kernel(const float* __restrict__ src, int C, long long hw, float* __re
   }
 }
 
+// channels-last source (N, HW, C): no transpose, one thread = 4 consecutive channels of one pixel
+__global__ void __launch_bounds__(256)
+gru_stage_cl_kernel(const float4* __restrict__ src, int c4n, long long total4, float* __restrict__ S, int ctot, int off_hi0,
+                    int off_lo, int off_hi1) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = i / c4n;
+    const int c4 = static_cast<int>(i - p * c4n);
+    float4 hi, lo;
+    split4(__ldg(src + i), hi, lo);
+    float* row = S + p * ctot + 4 * c4;
+    *reinterpret_cast<float4*>(row + off_hi0) = hi;
+    *reinterpret_cast<float4*>(row + off_lo) = lo;
+    *reinterpret_cast<float4*>(row + off_hi1) = hi;
+  }
+}
+
 // one thread = 4 consecutive channels of one pixel; everything channels-last
 __global__ void __launch_bounds__(256)
 gru_gate_r_kernel(const float4* __restrict__ zr_pre, const float4* __restrict__ bias_zr, const float4* __restrict__ h, int ch4,
@@ -120,14 +137,23 @@ static unsigned grid_for(long long items) {
 
 extern "C" {
 
-nnd_status nnd_gru_stage(const float* src, int N, int C, long long hw, float* S, int ctot, int off_hi0, int off_lo,
-                         int off_hi1, nnd_stream_t stream) {
+nnd_status nnd_gru_stage(const float* src, int src_channels_last, int N, int C, long long hw, float* S, int ctot, int off_hi0,
+                         int off_lo, int off_hi1, nnd_stream_t stream) {
   using namespace nnd;
   NND_REQUIRE(src && S, "gru_stage: null pointer");
   NND_REQUIRE(N > 0 && C > 0 && hw > 0 && ctot > 0, "gru_stage: N, C, H*W, ctot must be positive");
   NND_REQUIRE(N <= 65535 && (C + 31) / 32 <= 65535, "gru_stage: N or C exceeds the grid limit");
   NND_REQUIRE(off_hi0 >= 0 && off_lo >= 0 && off_hi1 >= 0 && off_hi0 + C <= ctot && off_lo + C <= ctot && off_hi1 + C <= ctot,
               "gru_stage: channel offsets outside the staging row");
+  if (src_channels_last) {
+    NND_REQUIRE(C % 4 == 0 && ctot % 4 == 0 && off_hi0 % 4 == 0 && off_lo % 4 == 0 && off_hi1 % 4 == 0 && aligned16(src) &&
+                    aligned16(S),
+                "gru_stage: the channels-last source path needs channel counts / offsets in quads and 16-byte alignment");
+    const long long total4 = static_cast<long long>(N) * hw * (C / 4);
+    gru_stage_cl_kernel<<<grid_for(total4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(src), C / 4, total4, S, ctot, off_hi0, off_lo, off_hi1);
+    return check_launch("gru_stage_cl_kernel");
+  }
   dim3 grid(static_cast<unsigned>((hw + 31) / 32), (C + 31) / 32, N);
   gru_stage_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, C, hw, S, ctot, off_hi0, off_lo, off_hi1);
   return check_launch("gru_stage_kernel");

@@ -111,10 +111,12 @@ class StereoEngine:
             gru.fuse_gates()
         # the fused ConvGRU keeps the hidden state channels-last: give the heads that read it channels-last
         # weights once, instead of letting cuDNN convert them on every call
-        for name in ("flow_head", "mask"):
+        for name in ("flow_head", "mask", "encoder"):
             head = getattr(ub, name, None)
             if head is not None:
                 head.to(memory_format=torch.channels_last)
+        if hasattr(getattr(ub, "encoder", None), "channels_last"):
+            ub.encoder.channels_last = True
         # the feature encoder runs on cuDNN's tensor-core kernels, which are NHWC inside: channels-last weights and
         # a channels-last input image spare it a layout conversion around every convolution
         self.channels_last_encoder = channels_last_encoder

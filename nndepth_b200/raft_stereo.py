@@ -302,8 +302,7 @@ class FusedGRURun:
         from . import _lib
         self._lib = _lib
         self.gru = gru
-        h0 = h0.float().contiguous()
-        inp = inp.float().contiguous()
+        h0, inp = h0.float(), inp.float()
         N, ch, H, W = h0.shape
         self.N, self.ch, self.H, self.W = N, ch, H, W
         self.c_inp = inp.shape[1]
@@ -319,16 +318,20 @@ class FusedGRURun:
         self._stage(inp, x0, x0 + self.cx, x0 + 2 * self.cx)
 
     def _stage(self, src, off_hi0, off_lo, off_hi1):
+        """Write ``[hi | lo | hi]`` of ``src`` into the staging rows; a channels-last ``src`` is read as it lies."""
         lib = self._lib
         N, C = src.shape[0], src.shape[1]
+        src = src.float()
+        cl = (not src.is_contiguous()) and src.is_contiguous(memory_format=torch.channels_last) and C % 4 == 0
+        if not cl:
+            src = src.contiguous()
         with torch.cuda.device(src.device):
-            lib.check(lib.load().nnd_gru_stage(lib.ptr(src), N, C, self.H * self.W, lib.ptr(self.S), self.ctot, off_hi0, off_lo,
-                                               off_hi1, lib.stream_ptr(src)), "nnd_gru_stage")
+            lib.check(lib.load().nnd_gru_stage(lib.ptr(src), 1 if cl else 0, N, C, self.H * self.W, lib.ptr(self.S), self.ctot,
+                                               off_hi0, off_lo, off_hi1, lib.stream_ptr(src)), "nnd_gru_stage")
 
     def step(self, motion):
         """One GRU update with ``x = cat[inp, motion]``; returns the new hidden state (channels-last view)."""
         lib = self._lib
-        motion = motion.float().contiguous()
         if motion.shape[1] != self.cx - self.c_inp:
             raise RuntimeError(f"motion features must have {self.cx - self.c_inp} channels, got {motion.shape[1]}")
         x0 = 3 * self.ch + self.c_inp
@@ -357,9 +360,13 @@ class BasicMotionEncoder(nn.Module):
         self.convf1 = nn.Conv2d(flow_channel, 128, 7, padding=3)
         self.convf2 = nn.Conv2d(128, 64, 3, padding=1)
         self.conv = nn.Conv2d(64 + 192, hidden_dim - flow_channel, 3, padding=1)
+        self.channels_last = False      # set by the engine together with channels-last weights
 
     def forward(self, flow, corr, cor1=None):
         """``cor1``: ``relu(convc1(corr))`` already computed by the fused lookup kernel (then ``corr`` is unused)."""
+        if cor1 is not None and self.channels_last:
+            # the rest of the encoder then stays channels-last: cuDNN's tensor-core kernels need no layout conversion
+            cor1 = cor1.contiguous(memory_format=torch.channels_last)
         cor = conv_relu(self.convc2, cor1 if cor1 is not None else conv_relu(self.convc1, corr))
         flo = conv_relu(self.convf2, conv_relu(self.convf1, flow))
         out = conv_relu(self.conv, torch.cat([cor, flo], dim=1))
