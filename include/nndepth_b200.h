@@ -100,6 +100,19 @@ nnd_status nnd_corr1d_lookup_conv1x1(const float* const* level, const int* width
                                      const float* weight, const float* bias, int c_out, int relu, int precision,
                                      float* out, nnd_stream_t stream);
 
+/* Backward passes for training (the reference path is differentiable; trainers: raft_trainer.py:242-259).
+ *   nnd_corr1d_lookup_backward: gradient of the lookup w.r.t. the pyramid.  grad_out (B, L*(2r+1), H, W1);
+ *     d_level[l] (rows = B*H*W1, pitch[l]) must be zero-initialised: each row receives its <= 2r+3 window
+ *     entries, deterministic (a row belongs to one pixel).  The coordinates carry no gradient: the reference
+ *     detaches them before every lookup (raft_stereo/model.py:131).
+ *   nnd_avgpool_pairs_backward: backward of avg_pool1d(., 2) (raft_stereo/cost_volume.py:33), accumulating:
+ *     d_src[r][2j] += d_dst[r][j] / 2, d_src[r][2j+1] += d_dst[r][j] / 2. */
+nnd_status nnd_corr1d_lookup_backward(const float* grad_out, const float* coords, const int* width, const int* pitch,
+                                      int B, int H, int W1, int num_levels, int radius, float* const* d_level,
+                                      nnd_stream_t stream);
+nnd_status nnd_avgpool_pairs_backward(const float* d_dst, int dst_width, int dst_pitch, float* d_src, int src_pitch,
+                                      int64_t rows, nnd_stream_t stream);
+
 /* Debug/parity twin of the lookup: writes the int32 window indices instead of values.
  *   idx0, idx1: (num_levels, B*H*W1, 2r+1) int32. */
 nnd_status nnd_corr1d_lookup_indices(const int* width, const float* coords, int B, int H, int W1,

@@ -32,6 +32,8 @@ SIGNATURES = {
     "nnd_avgpool_pairs": (_I, [_P, _I, _I, _P, _I, ctypes.c_int64, _P]),
     "nnd_corr1d_lookup": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "nnd_corr1d_lookup_conv1x1": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _I, _P, _P]),
+    "nnd_corr1d_lookup_backward": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "nnd_avgpool_pairs_backward": (_I, [_P, _I, _I, _P, _I, ctypes.c_int64, _P]),
     "nnd_corr1d_lookup_indices": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "nnd_group_lookup": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "nnd_geo_transpose_pool": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
@@ -125,13 +127,13 @@ def require_cuda_f32(t, name):
     return t
 
 
-def as_cuda_f32(t, name):
+def as_cuda_f32(t, name, allow_grad=False):
     """Reference call sites hand over whatever the encoder produced: make it dense fp32 on its device."""
     if not isinstance(t, torch.Tensor):
         raise TypeError(f"{name} must be a torch.Tensor, got {type(t).__name__}")
     if not t.is_cuda:
         raise RuntimeError(f"{name} must be a CUDA tensor: nndepth_b200 has no CPU path (got device {t.device})")
-    if torch.is_grad_enabled() and t.requires_grad:
+    if torch.is_grad_enabled() and t.requires_grad and not allow_grad:
         raise RuntimeError(
             f"{name} requires grad: the B200 correlation path is inference-only (wrap the call in torch.no_grad())"
         )

@@ -8,7 +8,10 @@ kernels (``raft_stereo/model.py:58,124,132``).
 
 Differences by design: one launch builds the volume *and* its pooled levels; one launch per GRU
 iteration does the whole 4-level lookup; rows of the pyramid are padded to 16 bytes (``corr_pyramid``
-hides the padding); inference only (no autograd).
+hides the padding).  ``CorrBlock1D`` is differentiable with respect to the feature maps (the coordinates are
+detached by the reference before every lookup, ``raft_stereo/model.py:131``): the lookup backward and the pooling
+backward are kernels of this package, the two volume-gradient contractions are cuBLAS GEMMs.  The grouped blocks,
+AGCL and the IGEV volume are inference only.
 """
 import math
 
@@ -50,7 +53,7 @@ class PyramidStorage:
     (``pitch_l`` = width rounded up to 4 floats so every row starts 16-byte aligned).
     """
 
-    def __init__(self, rows, width0, num_levels, device):
+    def __init__(self, rows, width0, num_levels, device, buffer=None):
         if not 1 <= num_levels <= _lib.NND_MAX_LEVELS:
             raise ValueError(f"num_levels must be in [1, {_lib.NND_MAX_LEVELS}], got {num_levels}")
         self.rows = int(rows)
@@ -58,7 +61,8 @@ class PyramidStorage:
         if self.widths[-1] < 1:
             raise ValueError(f"a {num_levels}-level pyramid of width {width0} has an empty level")
         self.pitches = [_lib.row_pitch(w) for w in self.widths]
-        self.buffer = torch.empty(self.rows * sum(self.pitches), dtype=torch.float32, device=device)
+        self.buffer = (torch.empty(self.rows * sum(self.pitches), dtype=torch.float32, device=device)
+                       if buffer is None else buffer)
         self.levels = []
         start = 0
         for p in self.pitches:
@@ -105,6 +109,71 @@ class PyramidStorage:
         return views
 
 
+class _BuildPyramid(torch.autograd.Function):
+    """Differentiable pyramid build: forward = ``nnd_corr1d_build``; backward = un-pool the level gradients
+    (``nnd_avgpool_pairs_backward``) and contract ``d_volume`` with the other feature map (cuBLAS)."""
+
+    @staticmethod
+    def forward(ctx, f1, f2, num_levels, prec_code):
+        B, C, H, W1 = f1.shape
+        W2 = f2.shape[3]
+        pyr = PyramidStorage(B * H * W1, W2, num_levels, f1.device)
+        with torch.cuda.device(f1.device):
+            _lib.check(
+                _lib.load().nnd_corr1d_build(_lib.ptr(f1), _lib.ptr(f2), B, C, H, W1, W2, num_levels, prec_code,
+                                             pyr._level_ptrs, pyr._pitch_arr, _lib.stream_ptr(f1)),
+                "nnd_corr1d_build",
+            )
+        ctx.save_for_backward(f1, f2)
+        ctx.geom = (B, C, H, W1, W2, num_levels)
+        return pyr.buffer
+
+    @staticmethod
+    def backward(ctx, d_buffer):
+        f1, f2 = ctx.saved_tensors
+        B, C, H, W1, W2, L = ctx.geom
+        d = PyramidStorage(B * H * W1, W2, L, f1.device, buffer=d_buffer.contiguous().clone())
+        with torch.cuda.device(f1.device):
+            for l in range(L - 1, 0, -1):       # avg_pool1d backward, coarsest level first
+                _lib.check(
+                    _lib.load().nnd_avgpool_pairs_backward(_lib.ptr(d.levels[l]), d.widths[l], d.pitches[l],
+                                                           _lib.ptr(d.levels[l - 1]), d.pitches[l - 1], d.rows,
+                                                           _lib.stream_ptr(f1)),
+                    "nnd_avgpool_pairs_backward",
+                )
+        d_vol = d.levels[0][:, :W2].reshape(B, H, W1, W2) / math.sqrt(C)
+        d_f1 = torch.einsum("bhij,bchj->bchi", d_vol, f2) if ctx.needs_input_grad[0] else None
+        d_f2 = torch.einsum("bhij,bchi->bchj", d_vol, f1) if ctx.needs_input_grad[1] else None
+        return d_f1, d_f2, None, None
+
+
+class _LookupPyramid(torch.autograd.Function):
+    """Differentiable lookup: the gradient flows to the pyramid only (``nnd_corr1d_lookup_backward``)."""
+
+    @staticmethod
+    def forward(ctx, buffer, coords, block):
+        ctx.block = block
+        ctx.save_for_backward(coords)
+        return block._lookup_raw(coords)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (coords,) = ctx.saved_tensors
+        block = ctx.block
+        B, H, W1, W2 = block._shape
+        d = PyramidStorage(B * H * W1, W2, block.num_levels, coords.device,
+                           buffer=torch.zeros_like(block._pyr.buffer))
+        grad_out = grad_out.contiguous().float()
+        with torch.cuda.device(coords.device):
+            _lib.check(
+                _lib.load().nnd_corr1d_lookup_backward(_lib.ptr(grad_out), _lib.ptr(coords), d._width_arr, d._pitch_arr, B, H,
+                                                       W1, block.num_levels, block.radius, d._level_ptrs,
+                                                       _lib.stream_ptr(coords)),
+                "nnd_corr1d_lookup_backward",
+            )
+        return d.buffer, None, None
+
+
 def _check_coords(coords, B, H, W1):
     coords = _lib.as_cuda_f32(coords, "coords")
     if coords.dim() != 4 or coords.shape[1] != 1:
@@ -120,8 +189,17 @@ class CorrBlock1D:
     def __init__(self, fmap1, fmap2, num_levels=4, radius=4, precision=None):
         self.num_levels = num_levels
         self.radius = radius
-        f1 = _lib.as_cuda_f32(fmap1, "fmap1")
-        f2 = _lib.as_cuda_f32(fmap2, "fmap2")
+        self._graph_buffer = None
+        train = torch.is_grad_enabled() and (getattr(fmap1, "requires_grad", False) or getattr(fmap2, "requires_grad", False))
+        if train:
+            # training: keep the autograd graph (the feature maps stay attached)
+            for t, name in ((fmap1, "fmap1"), (fmap2, "fmap2")):
+                if not (isinstance(t, torch.Tensor) and t.is_cuda):
+                    raise RuntimeError(f"{name} must be a CUDA tensor: nndepth_b200 has no CPU path")
+            f1, f2 = fmap1.float().contiguous(), fmap2.float().contiguous()
+        else:
+            f1 = _lib.as_cuda_f32(fmap1, "fmap1")
+            f2 = _lib.as_cuda_f32(fmap2, "fmap2")
         if f1.dim() != 4 or f2.dim() != 4:
             raise RuntimeError("fmap1 and fmap2 must be (B, C, H, W)")
         if f1.shape[:3] != f2.shape[:3] or f1.device != f2.device:
@@ -131,6 +209,10 @@ class CorrBlock1D:
         B, C, H, W1 = f1.shape
         W2 = f2.shape[3]
         self._shape = (B, H, W1, W2)
+        if train:
+            self._graph_buffer = _BuildPyramid.apply(f1, f2, num_levels, _prec_code(precision, W1, W2))
+            self._pyr = PyramidStorage(B * H * W1, W2, num_levels, f1.device, buffer=self._graph_buffer.detach())
+            return
         self._pyr = PyramidStorage(B * H * W1, W2, num_levels, f1.device)
         with torch.cuda.device(f1.device):
             _lib.check(
@@ -145,6 +227,7 @@ class CorrBlock1D:
         """Wrap an existing pyramid (list of ``(B*H*W1, w_l)`` arrays/tensors) -- used by the parity tests."""
         self = cls.__new__(cls)
         self.num_levels, self.radius = num_levels, radius
+        self._graph_buffer = None
         first = torch.as_tensor(levels[0])
         rows, W2 = first.reshape(first.shape[0], -1).shape
         self._shape = (batch, height, rows // (batch * height), W2)
@@ -157,7 +240,13 @@ class CorrBlock1D:
 
     def __call__(self, coords):
         B, H, W1, _ = self._shape
-        coords = _check_coords(coords, B, H, W1)
+        if self._graph_buffer is not None and torch.is_grad_enabled():
+            coords = _check_coords(coords.detach(), B, H, W1)     # the reference detaches them too (model.py:131)
+            return _LookupPyramid.apply(self._graph_buffer, coords, self)
+        return self._lookup_raw(_check_coords(coords, B, H, W1))
+
+    def _lookup_raw(self, coords):
+        B, H, W1, _ = self._shape
         T = 2 * self.radius + 1
         out = torch.empty(B, self.num_levels * T, H, W1, dtype=torch.float32, device=coords.device)
         with torch.cuda.device(coords.device):

@@ -733,6 +733,78 @@ gev_lookup_kernel(const __grid_constant__ GevLookupArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward of the pyramid lookup with respect to the pyramid (training; the coordinates are detached by the
+// reference before every lookup, raft_stereo/model.py:131).  out = coef * row[i0] + (1 - coef) * row[i1] per tap,
+// so d_row[i0] += coef * g and d_row[i1] += (1 - coef) * g.  A pyramid row belongs to exactly one pixel, so the
+// thread that owns (pixel, level) sums its <= 2r+3 window entries in registers and writes them with plain stores:
+// no atomics, deterministic.  The caller hands in zero-initialised gradient levels (entries outside the windows
+// stay zero).
+// ------------------------------------------------------------------------------------------------
+struct LookupBwdArgs {
+  float* d_level[NND_MAX_LEVELS];
+  int width[NND_MAX_LEVELS];
+  int pitch[NND_MAX_LEVELS];
+  const float* coords;
+  const float* grad_out;
+  long long n_pix;   // B * H * W1
+  int hw;
+  int num_levels;
+  int radius;
+};
+
+__global__ void __launch_bounds__(256)
+corr1d_lookup_backward_kernel(const __grid_constant__ LookupBwdArgs a) {
+  constexpr int MAXWIN = 32;  // 2r + 3 <= 29 for r <= 13
+  const int T = 2 * a.radius + 1;
+  const long long total = a.n_pix * a.num_levels;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int lvl = static_cast<int>(i / a.n_pix);
+    const long long pix = i - static_cast<long long>(lvl) * a.n_pix;
+    const long long b = pix / a.hw;
+    const int rem = static_cast<int>(pix - b * a.hw);
+    const int w = a.width[lvl];
+    const float centre = __fmul_rn(__ldg(a.coords + pix), 1.0f / static_cast<float>(1 << lvl));
+    const LevelScale sc = level_scale(w, lvl, centre);
+    const int lo = make_tap(0, a.radius, centre, sc).i0;
+    float acc[MAXWIN];
+#pragma unroll
+    for (int j = 0; j < MAXWIN; ++j) acc[j] = 0.f;
+    const float* g = a.grad_out + (b * a.num_levels + lvl) * T * a.hw + rem;
+    for (int k = 0; k < T; ++k) {
+      const Tap tp = make_tap(k, a.radius, centre, sc);
+      const float gk = __ldg(g + static_cast<long long>(k) * a.hw);
+      const int j0 = tp.i0 - lo, j1 = tp.i1 - lo;
+#pragma unroll
+      for (int j = 0; j < MAXWIN; ++j) {   // register array: select instead of dynamic indexing
+        if (j == j0) acc[j] = fmaf(tp.coef, gk, acc[j]);
+        if (j == j1) acc[j] = fmaf(tp.one_minus, gk, acc[j]);
+      }
+    }
+    float* row = a.d_level[lvl] + pix * a.pitch[lvl] + lo;
+    const int n = min(w - lo, MAXWIN);
+#pragma unroll
+    for (int j = 0; j < MAXWIN; ++j)
+      if (j < n && j <= 2 * a.radius + 2) row[j] = acc[j];
+  }
+}
+
+// backward of avg_pool1d(., 2): d_src[r][2j] += d_dst[r][j] / 2, d_src[r][2j+1] += d_dst[r][j] / 2
+__global__ void avgpool_pairs_backward_kernel(const float* __restrict__ d_dst, int dst_width, int dst_pitch,
+                                              float* __restrict__ d_src, int src_pitch, long long rows) {
+  const long long total = rows * dst_width;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / dst_width;
+    const int j = static_cast<int>(i - r * dst_width);
+    const float h = 0.5f * __ldg(d_dst + r * dst_pitch + j);
+    float* s = d_src + r * src_pitch + 2 * j;
+    s[0] += h;
+    s[1] += h;
+  }
+}
+
 __global__ void lookup_indices_kernel(const float* __restrict__ coords, long long n_pix, int num_levels, int radius,
                                       int w0, int w1, int w2, int w3, int w4, int w5, int w6, int w7,
                                       int32_t* __restrict__ idx0, int32_t* __restrict__ idx1) {
@@ -953,6 +1025,49 @@ nnd_status nnd_corr1d_lookup_conv1x1(const float* const* level, const int* width
   corr1d_lookup_conv1x1_kernel<9><<<grid, block, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a, weight, bias, c_out,
                                                                                                  relu ? 1 : 0, n_groups);
   return check_launch("corr1d_lookup_conv1x1_kernel");
+}
+
+nnd_status nnd_corr1d_lookup_backward(const float* grad_out, const float* coords, const int* width, const int* pitch, int B,
+                                      int H, int W1, int num_levels, int radius, float* const* d_level,
+                                      nnd_stream_t stream) {
+  using namespace nnd;
+  NND_REQUIRE(grad_out && coords && width && pitch && d_level, "lookup_backward: null pointer argument");
+  NND_REQUIRE(B > 0 && H > 0 && W1 > 0, "lookup_backward: B, H, W1 must be positive");
+  NND_REQUIRE(num_levels >= 1 && num_levels <= NND_MAX_LEVELS, "lookup_backward: num_levels %d outside [1, %d]", num_levels,
+              NND_MAX_LEVELS);
+  NND_REQUIRE(radius >= 0 && radius <= 13, "lookup_backward: radius %d outside [0, 13]", radius);
+  NND_REQUIRE(static_cast<long long>(H) * W1 < (1LL << 30), "lookup_backward: H*W1 too large");
+  LookupBwdArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int l = 0; l < num_levels; ++l) {
+    NND_REQUIRE(width[l] >= 2 && pitch[l] >= width[l] && d_level[l], "lookup_backward: level %d invalid", l);
+    a.d_level[l] = d_level[l];
+    a.width[l] = width[l];
+    a.pitch[l] = pitch[l];
+  }
+  a.coords = coords;
+  a.grad_out = grad_out;
+  a.hw = H * W1;
+  a.n_pix = static_cast<long long>(B) * a.hw;
+  a.num_levels = num_levels;
+  a.radius = radius;
+  const long long total = a.n_pix * num_levels;
+  const long long want = (total + 255) / 256, cap = static_cast<long long>(sm_count()) * 8;
+  corr1d_lookup_backward_kernel<<<static_cast<unsigned>(want < cap ? want : cap), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  return check_launch("corr1d_lookup_backward_kernel");
+}
+
+nnd_status nnd_avgpool_pairs_backward(const float* d_dst, int dst_width, int dst_pitch, float* d_src, int src_pitch,
+                                      int64_t rows, nnd_stream_t stream) {
+  using namespace nnd;
+  NND_REQUIRE(d_dst && d_src, "avgpool_pairs_backward: null pointer");
+  NND_REQUIRE(dst_width >= 1 && rows > 0 && dst_pitch >= dst_width && src_pitch >= 2 * dst_width,
+              "avgpool_pairs_backward: widths / pitches inconsistent");
+  const long long total = rows * dst_width;
+  const long long want = (total + 255) / 256, cap = static_cast<long long>(sm_count()) * 16;
+  avgpool_pairs_backward_kernel<<<static_cast<unsigned>(want < cap ? want : cap), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      d_dst, dst_width, dst_pitch, d_src, src_pitch, rows);
+  return check_launch("avgpool_pairs_backward_kernel");
 }
 
 }  // extern "C"

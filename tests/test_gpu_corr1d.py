@@ -324,9 +324,10 @@ def test_edge_cases_and_errors():
     out = ok(torch.full((1, 1, 2, 12), float("nan"), device="cuda"))
     assert out.shape == (1, 18, 2, 12)
     torch.cuda.synchronize()
-    # gradients are refused, not silently dropped
+    # CorrBlock1D is differentiable (tests/test_gpu_backward.py); the grouped block refuses gradients loudly
+    # instead of silently dropping them
     with pytest.raises(RuntimeError, match="inference-only"):
-        nb.CorrBlock1D(f.clone().requires_grad_(True), f)
+        nb.GroupCorrBlock1D(f.clone().requires_grad_(True), f, 2, 4, 2)
 
 
 def test_config5_row_bands_equal_full_volume():
