@@ -43,8 +43,9 @@ def workload_config(n_gpus):
         "pairs_per_gpu": PAIRS_PER_GPU, "global_pairs": PAIRS_PER_GPU * n_gpus, "image": list(IMAGE_HW),
         "iters": ITERS, "weights": "random init (seed 0) of the reference BaseRAFTStereo architecture",
         "parallelism": f"batch-sharded x{n_gpus}, no data-path collective, one all_gather of the disparity maps",
-        "l2": "activations per iteration (>> 126 MB L2) evict the pyramid between lookups; the isolated "
-              "lookup timing flushes L2 (256 MB write) before every timed launch",
+        "l2": "inputs larger than L2: one GRU iteration streams > 2 GB of activations (126 MB L2), so the 70 MB pyramid "
+              "and every tensor are cold again at the next iteration; isolated kernel timings flush L2 (256 MB write) "
+              "before every timed launch",
     }
 
 
@@ -197,6 +198,65 @@ def time_lookup_kernel(device, reps=40):
             "lookup_bytes": n_pix * LOOKUP_BYTES_PER_PIXEL,
             "build_bytes": 2 * B * C * H * W * 4 + B * H * W * (156 + 78 + 39 + 19) * 4,
             "build_flops": 2 * B * H * W * W * C}
+
+
+def time_step_kernels(device, peak):
+    """Isolated CUDA-event timings (L2 flushed) of this repo's other kernels at the bench shape, with their
+    algorithmic bytes: the per-step launch mix is 1 build, 32 fused lookups, 32 upsamplings, 34 stagings, 64 + 64 gates."""
+    import nndepth_b200 as nb
+    from nndepth_b200 import _lib
+    B, H, W, ch, cx = PAIRS_PER_GPU, 48, 156, 128, 256
+    px = B * H * W
+    ctot = 3 * (ch + cx)
+    cl = torch.channels_last
+    torch.manual_seed(4)
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=device)
+    stream = torch.cuda.current_stream(device)
+
+    def timed(fn, reps=12):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(reps):
+            torch.cuda._sleep(1000000)
+            flush.fill_(1.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        return statistics.median(ts)
+
+    lib = _lib.load()
+    sp = _lib.stream_ptr(flush)
+    S = torch.empty(B, ctot, H, W, device=device).contiguous(memory_format=cl)
+    h = torch.randn(B, ch, H, W, device=device).contiguous(memory_format=cl)
+    z = torch.empty_like(h)
+    zr = torch.randn(B, 2 * ch, H, W, device=device).contiguous(memory_format=cl)
+    q = torch.randn(B, ch, H, W, device=device).contiguous(memory_format=cl)
+    bias = torch.randn(2 * ch, device=device)
+    motion = torch.randn(B, ch, H, W, device=device).contiguous(memory_format=cl)
+    flow = torch.randn(B, 1, H, W, device=device)
+    mask = torch.randn(B, 576, H, W, device=device).contiguous(memory_format=cl)
+    mbias = torch.randn(576, device=device)
+    rows = []
+
+    def add(name, per_step, nbytes, fn):
+        us = timed(fn)
+        rows.append({"kernel": name, "launches_per_step": per_step, "us_per_launch_l2_flushed": us,
+                     "algorithmic_bytes_per_launch": nbytes, "achieved_gbs": nbytes / us / 1e3, "frac_of_hbm_peak": nbytes / us / 1e3 / peak})
+
+    add("gru_gate_r_kernel", 64, px * (2 * ch + ch + ch + 3 * ch) * 4,
+        lambda: _lib.check(lib.nnd_gru_gate_r(_lib.ptr(zr), _lib.ptr(bias), _lib.ptr(h), px, ch, _lib.ptr(z), _lib.ptr(S), ctot, sp), "gate_r"))
+    add("gru_gate_h_kernel", 64, px * (ch + ch + ch + ch + 3 * ch) * 4,
+        lambda: _lib.check(lib.nnd_gru_gate_h(_lib.ptr(q), _lib.ptr(bias), _lib.ptr(z), px, ch, _lib.ptr(h), _lib.ptr(S), ctot, sp), "gate_h"))
+    add("gru_stage_cl_kernel (motion features)", 32, px * (ch + 3 * ch) * 4,
+        lambda: _lib.check(lib.nnd_gru_stage(_lib.ptr(motion), 1, B, ch, H * W, _lib.ptr(S), ctot, 3 * ch + ch, 3 * ch + cx + ch,
+                                             3 * ch + 2 * cx + ch, sp), "stage"))
+    add("convex_upsample_nhwc8_kernel", 32, px * 576 * 4 + px * 64 * 4 + px * 4,
+        lambda: nb.convex_upsample(flow, mask, 8, 0.25, mbias))
+    return rows
 
 
 def measured_peak():
@@ -386,6 +446,7 @@ def run_ours(args):
                       "us_per_launch_l2_flushed": kern["build_ms_l2_flushed"] * 1e3,
                       "hbm_gbs": kern["build_bytes"] / (kern["build_ms_l2_flushed"] * 1e-3) / 1e9,
                       "tflops": kern["build_flops"] / (kern["build_ms_l2_flushed"] * 1e-3) / 1e12},
+            "other_kernels": time_step_kernels(device, peak),
             "cuda_graph": engine.use_cuda_graph,
         }
         if cpu is not None:
