@@ -38,6 +38,7 @@
 // (K = 256: ~25 flop/B, ridge > 200), so the pipeline is sized for bytes in flight, not MMA issue.
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -81,6 +82,8 @@ struct BuildParams {
   int b_region_boxes;  // ceil(min(W2, 256) / 32)
   int stages;
   int stage_bytes;     // (a_region_boxes + b_region_boxes) * BOX_BYTES
+  int lt_mode;         // 1: "leftover transposed" layout (128 < W1 <= 160): see the kernel comment
+  int lt_cols;         // TMEM columns of one job in lt_mode: n_cols + 64
   int n_tslots;        // tile slots in TMEM: 512 / slot_cols (one 128-row M tile of accumulators each)
   int slot_cols;       // b_region_boxes * 32
   float scale_div;
@@ -357,8 +360,49 @@ corr1d_build_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if (p.lt_mode) {
+        // Leftover-transposed layout (one job = one row, 128 < W1 <= 160, one pass):
+        //   D0  [cols 0, n_cols)             rows m = 0..127        x all n        (A = f1 boxes 0-3, B = f2)
+        //   DLa [n_cols, n_cols + 32)        rows n = 0..127        x m' = 128+..  (A = f2 boxes 0-3, B = f1 box 4)
+        //   DLb [n_cols + 32, n_cols + 64)   rows n = 128..255      x m'           (A = f2 boxes 4-7, B = f1 box 4)
+        // The ragged second M tile (28 valid rows at KITTI) would otherwise occupy n_cols more columns; this way a
+        // job needs n_cols + 64 columns and TWO jobs fit in TMEM: the epilogue of one row fully overlaps the
+        // MMAs of the next.  Both operands are MN-major atoms of the same shape, so f2 boxes serve as the A operand
+        // and the f1 box as B without any other change.
+        const uint32_t idesc32 = umma_idesc_tf32(32);
+        uint32_t job_seq = 0;
+        for (long long job = blockIdx.x; job < p.jobs; job += gridDim.x, ++job_seq) {
+          const JobGeom g = job_geom(p, job);
+          const uint32_t idesc = umma_idesc_tf32(g.n_mma);
+          const uint32_t slot = job_seq & 1;
+          const uint32_t d0 = tmem_base + slot * p.lt_cols, dla = d0 + g.n_cols, dlb = dla + 32;
+          const bool has_b = g.n_ext > TILE_M;
+          mbar_wait(tmem_empty_bar(slot), ((job_seq >> 1) & 1) ^ 1);
+          tc_fence_after();
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            mbar_wait(ready_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t sbase = smem_u32(smem + static_cast<size_t>(stage) * p.stage_bytes);
+            const uint32_t bbase = sbase + b_region;
+#pragma unroll
+            for (int ks = 0; ks < KB / 8; ++ks) {
+              const uint32_t acc = (kb | ks) != 0 ? 1u : 0u;
+              const uint64_t f1_t0 = umma_desc_mn_sw128_32b(sbase + ks * 1024, BOX_BYTES, 512);
+              const uint64_t f1_b4 = umma_desc_mn_sw128_32b(sbase + 4 * BOX_BYTES + ks * 1024, BOX_BYTES, 512);
+              const uint64_t f2_t0 = umma_desc_mn_sw128_32b(bbase + ks * 1024, BOX_BYTES, 512);
+              const uint64_t f2_t1 = umma_desc_mn_sw128_32b(bbase + 4 * BOX_BYTES + ks * 1024, BOX_BYTES, 512);
+              tc_mma_tf32(d0, f1_t0, f2_t0, idesc, acc);
+              tc_mma_tf32(dla, f2_t0, f1_b4, idesc32, acc);
+              if (has_b) tc_mma_tf32(dlb, f2_t1, f1_b4, idesc32, acc);
+            }
+            tc_commit(empty_bar(stage));
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+          tc_commit(tmem_full_bar(slot));
+        }
+      }
       uint32_t tile_seq = 0;  // every M tile takes the next TMEM tile slot of the ring
-      for (long long job = blockIdx.x; job < p.jobs; job += gridDim.x) {
+      for (long long job = p.lt_mode ? p.jobs : blockIdx.x; job < p.jobs; job += gridDim.x) {
         const JobGeom g = job_geom(p, job);
         const uint32_t idesc = umma_idesc_tf32(g.n_mma);
         for (int pass = 0; pass < p.m_passes; ++pass) {
@@ -407,7 +451,126 @@ corr1d_build_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     const CUtensorMap* my_map = lane == 0 ? &map_l0 : lane == 1 ? &map_l1 : lane == 2 ? &map_l2 : &map_l3;
     const uint32_t my_level_off = lane == 0 ? 0u : lane == 1 ? EPI_L0 : lane == 2 ? EPI_L0 + EPI_L1 : EPI_L0 + EPI_L1 + EPI_L2;
     const bool store_lane = lane < p.num_levels && lane < 4;
-    for (long long job = blockIdx.x; job < p.jobs; job += gridDim.x) {
+    // stage one 32-row x 32-column chunk (rows = my lanes) and TMA-store its four level tiles
+    auto stage_and_store = [&](float (&v)[32], int col0, int mrow, int vol_row) {
+      uint8_t* set = my_sets + chunk_parity * EPI_SET;
+      if (store_lane) tma_store_wait_read<1>();  // my store that last read this buffer set has drained
+      __syncwarp();
+      {
+        float4* dst = reinterpret_cast<float4*>(set + lane * 128);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dst[j ^ (lane & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      float l1[16], l2[8], l3[4];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) l1[i] = pool2(v[2 * i], v[2 * i + 1]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) l2[i] = pool2(l1[2 * i], l1[2 * i + 1]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) l3[i] = pool2(l2[2 * i], l2[2 * i + 1]);
+      if (p.num_levels > 1) {
+        float4* dst = reinterpret_cast<float4*>(set + EPI_L0 + lane * 64);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          dst[j ^ ((lane >> 1) & 3)] = make_float4(l1[4 * j], l1[4 * j + 1], l1[4 * j + 2], l1[4 * j + 3]);
+      }
+      if (p.num_levels > 2) {
+        float4* dst = reinterpret_cast<float4*>(set + EPI_L0 + EPI_L1 + lane * 32);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          dst[j ^ ((lane >> 2) & 1)] = make_float4(l2[4 * j], l2[4 * j + 1], l2[4 * j + 2], l2[4 * j + 3]);
+      }
+      if (p.num_levels > 3)
+        *reinterpret_cast<float4*>(set + EPI_L0 + EPI_L1 + EPI_L2 + lane * 16) = make_float4(l3[0], l3[1], l3[2], l3[3]);
+      fence_proxy_async();
+      __syncwarp();
+      if (store_lane) {
+        const int col = col0 >> lane;  // first column of this chunk at my level
+        if (col < (p.W2 >> lane)) tma_store_3d(my_map, smem_u32(set) + my_level_off, col, mrow, vol_row);
+        tma_store_commit();
+      }
+      chunk_parity ^= 1;
+    };
+    // the same for a TRANSPOSED chunk: my lanes are 32 consecutive volume COLUMNS n0 + lane, v[j] is volume row
+    // mrow + j.  Level 0 goes to shared memory column-wise; the pooled levels pair neighbouring lanes.
+    auto stage_and_store_transposed = [&](float (&v)[32], int n0, int mrow, int vol_row) {
+      constexpr unsigned FULL = 0xffffffffu;
+      uint8_t* set = my_sets + chunk_parity * EPI_SET;
+      if (store_lane) tma_store_wait_read<1>();
+      __syncwarp();
+      float* t0 = reinterpret_cast<float*>(set);
+      float* t1 = reinterpret_cast<float*>(set + EPI_L0);
+      float* t2 = reinterpret_cast<float*>(set + EPI_L0 + EPI_L1);
+      float* t3 = reinterpret_cast<float*>(set + EPI_L0 + EPI_L1 + EPI_L2);
+      const int c1 = lane >> 1, c2 = lane >> 2, c3 = lane >> 3;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {   // j = tile row (volume row mrow + j), lane = tile column
+        const float x0 = v[j];
+        t0[j * 32 + ((((lane >> 2) ^ (j & 7)) << 2) | (lane & 3))] = x0;
+        const float x1 = pool2(x0, __shfl_xor_sync(FULL, x0, 1));       // valid on even lanes: columns (lane, lane+1)
+        const float x2 = pool2(x1, __shfl_xor_sync(FULL, x1, 2));       // valid on lanes % 4 == 0
+        const float x3 = pool2(x2, __shfl_xor_sync(FULL, x2, 4));       // valid on lanes % 8 == 0
+        if (p.num_levels > 1 && (lane & 1) == 0) t1[j * 16 + ((((c1 >> 2) ^ ((j >> 1) & 3)) << 2) | (c1 & 3))] = x1;
+        if (p.num_levels > 2 && (lane & 3) == 0) t2[j * 8 + ((((c2 >> 2) ^ ((j >> 2) & 1)) << 2) | (c2 & 3))] = x2;
+        if (p.num_levels > 3 && (lane & 7) == 0) t3[j * 4 + c3] = x3;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (store_lane) {
+        const int col = n0 >> lane;
+        if (col < (p.W2 >> lane)) tma_store_3d(my_map, smem_u32(set) + my_level_off, col, mrow, vol_row);
+        tma_store_commit();
+      }
+      chunk_parity ^= 1;
+    };
+    auto scale32 = [&](float (&v)[32]) {
+      if (p.scale_is_pow2) {  // x / 2^k == x * 2^-k exactly
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __fmul_rn(v[i], p.scale_inv);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __fdiv_rn(v[i], p.scale_div);
+      }
+    };
+    if (p.lt_mode) {
+      uint32_t job_seq = 0;
+      for (long long job = blockIdx.x; job < p.jobs; job += gridDim.x, ++job_seq) {
+        const JobGeom g = job_geom(p, job);
+        const int n_chunks32 = g.n_cols / CHUNK;
+        const uint32_t slot = job_seq & 1;
+        const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
+        const uint32_t d0 = tmem_base + slot * p.lt_cols + lane_sel, dla = d0 + g.n_cols, dlb = dla + 32;
+        const bool has_b = 128 + quarter * 32 < g.n_ext;   // my lane quarter holds valid columns n >= 128
+        mbar_wait(tmem_full_bar(slot), (job_seq >> 1) & 1);
+        tc_fence_after();
+        for (int ch = 0; ch < n_chunks32; ++ch) {             // rows m = 32*quarter + lane of the first 128
+          float v[32];
+          tc_ld32(d0 + ch * CHUNK, v);
+          scale32(v);
+          stage_and_store(v, g.n0 + ch * CHUNK, quarter * 32, g.row);
+        }
+        {
+          float v[32];                                          // volume rows 128 + j, columns n = 32*quarter + lane
+          tc_ld32(dla, v);
+          if (!has_b) {
+            tc_fence_before();
+            mbar_arrive(tmem_empty_bar(slot));                 // my last TMEM read of this job
+          }
+          scale32(v);
+          stage_and_store_transposed(v, g.n0 + quarter * 32, TILE_M, g.row);
+        }
+        if (has_b) {
+          float v[32];                                          // columns n = 128 + 32*quarter + lane
+          tc_ld32(dlb, v);
+          tc_fence_before();
+          mbar_arrive(tmem_empty_bar(slot));
+          scale32(v);
+          stage_and_store_transposed(v, g.n0 + TILE_M + quarter * 32, TILE_M, g.row);
+        }
+      }
+    }
+    for (long long job = p.lt_mode ? p.jobs : blockIdx.x; job < p.jobs; job += gridDim.x) {
       const JobGeom g = job_geom(p, job);
       const int n_chunks32 = g.n_cols / CHUNK;
       for (int pass = 0; pass < p.m_passes; ++pass) {
@@ -582,6 +745,10 @@ nnd_status corr1d_build_tf32(const float* fmap1, const float* fmap2, int B, int 
   }
   p.slot_cols = p.b_region_boxes * BOX_W;         // TMEM columns of one M tile
   p.n_tslots = TMEM_COLS / p.slot_cols;            // >= 2 (slot_cols <= 256): a ring of tile slots
+  // leftover-transposed layout: a ragged second M tile of <= 32 rows, one column chunk, and room for two jobs
+  p.lt_cols = p.slot_cols + 64;
+  p.lt_mode = (W1 > TILE_M && W1 <= TILE_M + BOX_W && p.n_chunks == 1 && 2 * p.lt_cols <= TMEM_COLS) ? 1 : 0;
+  { const char* e = getenv("NND_NO_LT"); if (e && e[0] == '1') p.lt_mode = 0; }
   const size_t smem_bytes = 1024 + static_cast<size_t>(p.stages) * p.stage_bytes + 2 * EPI_SET + BAR_BYTES;
 
   alignas(64) CUtensorMap map_a, map_b, map_l[4];
