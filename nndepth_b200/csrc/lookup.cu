@@ -493,7 +493,7 @@ template <int TAPS>
 __global__ void __launch_bounds__(128)
 corr1d_lookup_conv1x1_tc_kernel(const __grid_constant__ LookupArgs a, const float* __restrict__ weight,
                                 const float* __restrict__ bias, int c_out, int relu, long long n_groups) {
-  constexpr int WINQ = 4, COLS = 4 * WINQ, STRIDE = COLS + 1;
+  constexpr int WINQ = 4, COLS = 4 * WINQ, STRIDE = COLS + 4;  // 16-byte aligned rows for the 16-byte cp.async copies
   constexpr int R = (TAPS - 1) / 2;
   constexpr int K = 4 * TAPS;        // 36 lookup channels (4 levels)
   constexpr int KSTEPS = (K + 7) / 8;  // 5 k-steps of 8, the last one half empty
@@ -501,7 +501,7 @@ corr1d_lookup_conv1x1_tc_kernel(const __grid_constant__ LookupArgs a, const floa
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ __align__(16) float smem[];
   float* corr = smem;                     // [32][CS]
-  float* wins = corr + 32 * CS;           // [4][32][STRIDE]
+  float* wins = corr + 32 * CS;           // [2 buffers][4 levels][32][STRIDE]
   const int lane = threadIdx.x, lvl = threadIdx.y;
   const int gid = lane >> 2, tig = lane & 3;
 
@@ -515,62 +515,80 @@ corr1d_lookup_conv1x1_tc_kernel(const __grid_constant__ LookupArgs a, const floa
 #pragma unroll
     for (int ks = 0; ks < KSTEPS; ++ks) {
       const int k0 = 8 * ks + tig, k1 = k0 + 4;
-      af[mt][ks][0] = (r0 < c_out && k0 < K) ? to_tf32(__ldg(weight + static_cast<long long>(k0) * c_out + r0)) : 0u;
-      af[mt][ks][1] = (r1 < c_out && k0 < K) ? to_tf32(__ldg(weight + static_cast<long long>(k0) * c_out + r1)) : 0u;
-      af[mt][ks][2] = (r0 < c_out && k1 < K) ? to_tf32(__ldg(weight + static_cast<long long>(k1) * c_out + r0)) : 0u;
-      af[mt][ks][3] = (r1 < c_out && k1 < K) ? to_tf32(__ldg(weight + static_cast<long long>(k1) * c_out + r1)) : 0u;
+      // raw loads first (all 80 in flight together), rounding to TF32 in a second sweep below
+      af[mt][ks][0] = (r0 < c_out && k0 < K) ? __float_as_uint(__ldg(weight + static_cast<long long>(k0) * c_out + r0)) : 0u;
+      af[mt][ks][1] = (r1 < c_out && k0 < K) ? __float_as_uint(__ldg(weight + static_cast<long long>(k0) * c_out + r1)) : 0u;
+      af[mt][ks][2] = (r0 < c_out && k1 < K) ? __float_as_uint(__ldg(weight + static_cast<long long>(k1) * c_out + r0)) : 0u;
+      af[mt][ks][3] = (r1 < c_out && k1 < K) ? __float_as_uint(__ldg(weight + static_cast<long long>(k1) * c_out + r1)) : 0u;
     }
     bv[mt][0] = (bias && r0 < c_out) ? __ldg(bias + r0) : 0.f;
     bv[mt][1] = (bias && r1 < c_out) ? __ldg(bias + r1) : 0.f;
   }
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) af[mt][ks][e] = to_tf32(__uint_as_float(af[mt][ks][e]));
   // zero the padding columns of the corr tile once (k = 36..39 feed the last k-step)
   for (int i = lvl * 32 + lane; i < 32 * (CS - K); i += 128) corr[(i / (CS - K)) * CS + K + i % (CS - K)] = 0.f;
 
-  float* win = wins + lvl * (32 * STRIDE);
   const int groups_per_image = (a.hw + 31) / 32;
   const int w = a.src[0].width[lvl];
   const int pitch = a.src[0].pitch[lvl];
   const LevelScale sc = level_scale(w, lvl, 0.f);
-  for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-    const int b = static_cast<int>(grp / groups_per_image);
-    const int rem0 = static_cast<int>(grp - static_cast<long long>(b) * groups_per_image) * 32;
+  const int q = lane & 3;
+
+  // Software pipeline over the block's pixel groups: coordinates are fetched two groups ahead, windows one
+  // group ahead (cp.async into the other half of the double-buffered window tile, issued right before the MMA
+  // phase of the current group), so neither DRAM latency sits on the per-group critical path.
+  auto group_coord = [&](long long grp, int& b, int& rem0) -> float {
+    if (grp >= n_groups) { b = 0; rem0 = 0; return 0.0f; }
+    b = static_cast<int>(grp / groups_per_image);
+    rem0 = static_cast<int>(grp - static_cast<long long>(b) * groups_per_image) * 32;
     const int rem = rem0 + lane;
-    const bool valid = rem < a.hw;
-    const float c = valid ? __ldg(a.coords + static_cast<long long>(b) * a.hw + rem) : 0.0f;
+    return rem < a.hw ? __ldg(a.coords + static_cast<long long>(b) * a.hw + rem) : 0.0f;
+  };
+  auto issue_windows = [&](float c, int b, int rem0, float* win) {
     const float centre = __fmul_rn(c, 1.0f / static_cast<float>(1 << lvl));
     const int s = make_tap(0, R, centre, sc).i0 & ~3;
     const int hi = make_tap(TAPS - 1, R, centre, sc).i1;
-    const int q = lane & 3;
     const float* __restrict__ rows = a.src[0].ptr[lvl] + (static_cast<long long>(b) * a.hw + rem0) * pitch;
-    float4 v[WINQ];
 #pragma unroll
     for (int j = 0; j < WINQ; ++j) {
       const int p = j * 8 + (lane >> 2);
       const int sp = __shfl_sync(FULL, s, p);
       const int hp = __shfl_sync(FULL, hi, p);
       const int cq = sp + 4 * q;
-      v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       if ((rem0 + p < a.hw) && cq <= hp && cq < w) {
         const float* src = rows + static_cast<long long>(p) * pitch + cq;
+        const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(win + p * STRIDE + 4 * q));
         if (a.vec) {
-          v[j] = ldg_f4(src);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
         } else {
           const int left = w - cq;
-          v[j].x = __ldg(src);
-          if (left > 1) v[j].y = __ldg(src + 1);
-          if (left > 2) v[j].z = __ldg(src + 2);
-          if (left > 3) v[j].w = __ldg(src + 3);
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (e < left) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * e), "l"(src + e) : "memory");
         }
       }
     }
-#pragma unroll
-    for (int j = 0; j < WINQ; ++j) {
-      float* dst = win + (j * 8 + (lane >> 2)) * STRIDE + 4 * q;
-      dst[0] = v[j].x;
-      dst[1] = v[j].y;
-      dst[2] = v[j].z;
-      dst[3] = v[j].w;
-    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  const long long stride = gridDim.x;
+  long long grp = blockIdx.x;
+  int b, rem0, b1, rem01, b2, rem02;
+  float c = group_coord(grp, b, rem0);
+  float c1 = group_coord(grp + stride, b1, rem01);
+  int buf = 0;
+  if (grp < n_groups) issue_windows(c, b, rem0, wins + (buf * 4 + lvl) * (32 * STRIDE));
+  for (; grp < n_groups; grp += stride) {
+    const float c2 = group_coord(grp + 2 * stride, b2, rem02);   // in flight during this whole iteration
+    const float* win = wins + (buf * 4 + lvl) * (32 * STRIDE);
+    const float centre = __fmul_rn(c, 1.0f / static_cast<float>(1 << lvl));
+    const int s = make_tap(0, R, centre, sc).i0 & ~3;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
     {
       const float* mine = win + lane * STRIDE - s;
@@ -583,6 +601,7 @@ corr1d_lookup_conv1x1_tc_kernel(const __grid_constant__ LookupArgs a, const floa
       }
     }
     __syncthreads();
+    if (grp + stride < n_groups) issue_windows(c1, b1, rem01, wins + ((buf ^ 1) * 4 + lvl) * (32 * STRIDE));
 
     // D[co][px] = sum_k W[co][k] * corr[px][k]: 4 m-tiles x 4 n-tiles (8 pixels each) per warp
     float* out_img = a.out + static_cast<long long>(b) * c_out * a.hw + rem0;
@@ -624,6 +643,9 @@ corr1d_lookup_conv1x1_tc_kernel(const __grid_constant__ LookupArgs a, const floa
       }
     }
     __syncthreads();  // corr[] is rewritten by the next group
+    c = c1; b = b1; rem0 = rem01;
+    c1 = c2; b1 = b2; rem01 = rem02;
+    buf ^= 1;
   }
 }
 
@@ -1004,7 +1026,7 @@ nnd_status nnd_corr1d_lookup_conv1x1(const float* const* level, const int* width
   const long long n_groups_all = static_cast<long long>(B) * ((a.hw + 31) / 32);
   if (precision == NND_PREC_TF32 && c_out <= 256) {
     // tensor-core path: weights live in registers, shared memory holds only the lookup tiles
-    const size_t smem_tc = (32 * 40 + static_cast<size_t>(4) * 32 * 17) * sizeof(float);
+    const size_t smem_tc = (32 * 40 + static_cast<size_t>(2) * 4 * 32 * 20) * sizeof(float);
     const long long resident = static_cast<long long>(sm_count()) * 3;   // 128 threads x ~150 registers
     dim3 grid_tc(static_cast<unsigned>(n_groups_all < resident ? n_groups_all : resident));
     corr1d_lookup_conv1x1_tc_kernel<9><<<grid_tc, dim3(32, 4), smem_tc, reinterpret_cast<cudaStream_t>(stream)>>>(
