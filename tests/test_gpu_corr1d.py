@@ -383,3 +383,38 @@ def test_lookup_conv1x1_fusion(shape, c_out):
     with torch.no_grad():
         tc = blk.lookup_conv1x1(coords, conv.weight, conv.bias, relu=True, precision="tf32")
     assert (tc - ref).abs().max().item() <= 1e-3 * scale
+
+
+def test_randomised_lookup_sweep_bit_exact():
+    """40 random (shape, levels, radius, coordinate regime) draws: lookup on an identical pyramid and the integer
+    window indices must equal the oracle bit for bit -- covers the generic kernel (radius != 4, ragged widths,
+    unaligned pitches) as well as the RAFT fast path."""
+    import nndepth_b200 as nb
+    rng = np.random.default_rng(2026)
+    for trial in range(40):
+        B, H = int(rng.integers(1, 3)), int(rng.integers(1, 4))
+        W1 = int(rng.integers(2, 70))
+        L = int(rng.integers(1, 5))
+        W2 = int(rng.integers(2 << (L - 1), 90))          # the last used level keeps width >= 2
+        r = int(rng.choice([0, 1, 2, 3, 4, 4, 4, 5, 7]))
+        vol = rng.standard_normal((B * H * W1, W2)).astype(np.float32)
+        pyr = oc.build_pyramid(vol, L)
+        regime = trial % 4
+        base = np.broadcast_to(np.arange(W1, dtype=np.float32), (B, 1, H, W1))
+        if regime == 0:
+            coords = base.copy()                                              # exact integers
+        elif regime == 1:
+            coords = base - rng.uniform(0, W2, size=base.shape).astype(np.float32)
+        elif regime == 2:
+            coords = rng.uniform(-3 * W2, 4 * W2, size=base.shape).astype(np.float32)   # mostly out of range
+        else:
+            coords = (rng.integers(0, W2, size=base.shape) + rng.choice([0.0, 0.5, 1e-7, -1e-7], size=base.shape)).astype(np.float32)
+        coords = np.ascontiguousarray(coords, dtype=np.float32)
+        blk = nb.CorrBlock1D.from_pyramid(pyr, B, H, L, r)
+        got = blk(dev(coords)).cpu().numpy()
+        want = oc.lookup(pyr, coords, L, r)
+        np.testing.assert_array_equal(got, want, err_msg=f"trial {trial}: B{B} H{H} W1={W1} W2={W2} L{L} r{r} regime {regime}")
+        i0, i1 = blk.lookup_indices(dev(coords))
+        for lvl, (o0, o1) in enumerate(oc.lookup_indices([W2 >> l for l in range(L)], coords, L, r)):
+            np.testing.assert_array_equal(i0[lvl].cpu().numpy(), o0)
+            np.testing.assert_array_equal(i1[lvl].cpu().numpy(), o1)
