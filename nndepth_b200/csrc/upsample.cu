@@ -69,55 +69,63 @@ convex_upsample_kernel(const float* __restrict__ flow, const float* __restrict__
 }
 
 // Channels-last mask (N, H, W, 9*RATE*RATE) -- what cuDNN hands back when the hidden state is channels-last.
-// One warp per coarse pixel: the pixel's 9*64 logits are 2304 contiguous bytes; lane = (sub-row i, column pair)
-// reads 8 bytes per neighbour k (a warp load covers 256 contiguous bytes) and writes two outputs.
+// Half a warp per coarse pixel: the pixel's 9*64 logits are 2304 contiguous bytes; lane = (pixel of the pair,
+// sub-row i, column quad) reads 16 bytes per neighbour k (a warp load covers 2 x 256 contiguous bytes) and
+// writes four outputs as one 16-byte store.
 __global__ void __launch_bounds__(256)
 convex_upsample_nhwc8_kernel(const float* __restrict__ flow, const float* __restrict__ mask, const float* __restrict__ mask_bias,
                              int H, int W, long long n_pix, float mask_scale, float* __restrict__ out) {
   constexpr int RATE = 8;
   const int lane = threadIdx.x & 31;
-  const int i = lane >> 2, jp = lane & 3;
+  const int half = lane >> 4, i = (lane >> 1) & 7, jq = lane & 1;
   const long long hw = static_cast<long long>(H) * W;
   const long long warp0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-  float2 bias[9];
-#pragma unroll
-  for (int k = 0; k < 9; ++k)
-    bias[k] = mask_bias ? __ldg(reinterpret_cast<const float2*>(mask_bias + k * RATE * RATE + i * RATE + 2 * jp)) : make_float2(0.f, 0.f);
-  for (long long pix = warp0; pix < n_pix; pix += n_warps) {
+  const float4* bp = mask_bias ? reinterpret_cast<const float4*>(mask_bias + i * RATE + 4 * jq) : nullptr;  // L1-resident
+  for (long long pair = warp0; 2 * pair < n_pix; pair += n_warps) {
+    const long long pix = 2 * pair + half;
+    if (pix >= n_pix) continue;
     const long long n = pix / hw;
     const long long p = pix - n * hw;
     const int h = static_cast<int>(p / W), w = static_cast<int>(p - static_cast<long long>(h) * W);
     const float* fl = flow + n * hw;
-    const float2* mp = reinterpret_cast<const float2*>(mask + pix * (9 * RATE * RATE) + i * RATE + 2 * jp);
-    float2 x[9];
+    const float4* mp = reinterpret_cast<const float4*>(mask + pix * (9 * RATE * RATE) + i * RATE + 4 * jq);
+    float4 x[9];
     float nb[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-      x[k] = __ldcs(mp + k * (RATE * RATE / 2));
+      x[k] = __ldcs(mp + k * (RATE * RATE / 4));
       const int hh = h + k / 3 - 1, ww = w + k % 3 - 1;
       nb[k] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __fmul_rn(8.0f, __ldg(fl + static_cast<long long>(hh) * W + ww)) : 0.f;
     }
-    float m0 = (x[0].x + bias[0].x) * mask_scale, m1 = (x[0].y + bias[0].y) * mask_scale;
+    if (bp) {
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      x[k].x = (x[k].x + bias[k].x) * mask_scale;
-      x[k].y = (x[k].y + bias[k].y) * mask_scale;
-      m0 = fmaxf(m0, x[k].x);
-      m1 = fmaxf(m1, x[k].y);
+      for (int k = 0; k < 9; ++k) {
+        const float4 bk = __ldg(bp + k * (RATE * RATE / 4));
+        x[k].x += bk.x; x[k].y += bk.y; x[k].z += bk.z; x[k].w += bk.w;
+      }
     }
-    float s0 = 0.f, s1 = 0.f, a0 = 0.f, a1 = 0.f;
+    float res[4];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      const float e0 = __expf(x[k].x - m0), e1 = __expf(x[k].y - m1);
-      s0 += e0;
-      s1 += e1;
-      a0 = fmaf(e0, nb[k], a0);
-      a1 = fmaf(e1, nb[k], a1);
+    for (int e = 0; e < 4; ++e) {
+      float v[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) v[k] = (e == 0 ? x[k].x : e == 1 ? x[k].y : e == 2 ? x[k].z : x[k].w) * mask_scale;
+      float m = v[0];
+#pragma unroll
+      for (int k = 1; k < 9; ++k) m = fmaxf(m, v[k]);
+      float s = 0.f, a = 0.f;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const float ex = __expf(v[k] - m);
+        s += ex;
+        a = fmaf(ex, nb[k], a);
+      }
+      res[e] = a / s;
     }
     float* op = out + (n * RATE * H + static_cast<long long>(RATE) * h + i) * (static_cast<long long>(RATE) * W) +
-                static_cast<long long>(RATE) * w + 2 * jp;
-    *reinterpret_cast<float2*>(op) = make_float2(a0 / s0, a1 / s1);
+                static_cast<long long>(RATE) * w + 4 * jq;
+    *reinterpret_cast<float4*>(op) = make_float4(res[0], res[1], res[2], res[3]);
   }
 }
 
@@ -137,10 +145,10 @@ nnd_status nnd_convex_upsample(const float* flow, const float* mask, const float
   const long long hw = static_cast<long long>(H) * W;
   if (mask_channels_last) {
     NND_REQUIRE(rate == 8, "convex_upsample: the channels-last mask path is built for rate 8 (got %d)", rate);
-    NND_REQUIRE((reinterpret_cast<uintptr_t>(mask) & 7u) == 0 && (reinterpret_cast<uintptr_t>(out) & 7u) == 0,
-                "convex_upsample: mask and output must be 8-byte aligned");
+    NND_REQUIRE(aligned16(mask) && aligned16(out) && (!mask_bias || aligned16(mask_bias)),
+                "convex_upsample: mask, bias and output must be 16-byte aligned");
     const long long n_pix = hw * N;
-    const long long want = (n_pix + 7) / 8, cap = static_cast<long long>(sm_count()) * 8;
+    const long long want = (n_pix + 15) / 16, cap = static_cast<long long>(sm_count()) * 8;
     convex_upsample_nhwc8_kernel<<<static_cast<unsigned>(want < cap ? want : cap), 256, 0, stream>>>(flow, mask, mask_bias, H, W,
                                                                                               n_pix, mask_scale, out);
     return check_launch("convex_upsample_nhwc8_kernel");
