@@ -126,3 +126,24 @@ def test_engine_bench_configuration_stays_inside_the_bar(golden):
         assert epe(out, ref) < EPE_BAR, epe(out, ref)
     host = engine.infer(left.cpu().pin_memory(), right.cpu().pin_memory())
     assert epe(host.cuda(), ref) < EPE_BAR
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_small_all_iterations_bench_mode(golden, graph):
+    """The bench's mode (mixed3x, every fusion on) at the small golden shape: every iteration's upsampled map
+    against the reference, eager and as a CUDA graph (few pixel groups, ragged tiles, 12 iterations)."""
+    from nndepth_b200.engine import StereoEngine
+    from nndepth_b200.raft_stereo import BaseRAFTStereo
+    g = golden("raft_small")
+    torch.manual_seed(0)
+    model = BaseRAFTStereo(iters=int(g["iters"])).eval()
+    model.dense_precision = "mixed3x"
+    engine = StereoEngine(model, device="cuda", use_cuda_graph=graph)
+    left, right = (t.cuda() for t in seeded_pair(g["shape"]))
+    ref = torch.from_numpy(g["all_up_disp"]).cuda()
+    with torch.no_grad():
+        outs = engine.model.forward_graphed(left, right) if graph else engine.model(left, right)
+    assert len(outs) == int(g["iters"])
+    for i, o in enumerate(outs):
+        assert o["up_disp"].shape == ref[i].shape
+        assert epe(o["up_disp"], ref[i]) < EPE_BAR, (i, epe(o["up_disp"], ref[i]))
