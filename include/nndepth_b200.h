@@ -203,26 +203,19 @@ nnd_status nnd_agcl_iter_nhwc(const float* fmap1_nhwc, const float* fmap2_nhwc, 
 nnd_status nnd_convex_upsample(const float* flow, const float* mask, const float* mask_bias, int N, int H, int W,
                                int rate, float mask_scale, int mask_channels_last, float* out, nnd_stream_t stream);
 
-/* ------------------------------------------------------------------------------------------------
- * Error-compensated TF32 operand split for the ConvGRU convolutions (nndepth/blocks/gru.py:5-37), the
- * one dense block whose TF32 rounding leaves the 0.01 px parity bar: x = hi + lo with hi = RN_tf32(x).
- *   x (N, C, H*W) -> out (N, 3C, H*W) = [hi ; lo ; hi]; convolved against weights [w_hi ; w_hi ; w_lo]
- *   on TF32 tensor cores this equals the fp32 convolution to O(2^-22).
- * ---------------------------------------------------------------------------------------------- */
-nnd_status nnd_split_tf32(const float* x, int N, int C, long long hw, float* out, nnd_stream_t stream);
-
-/* Fused, channels-last glue of the separable ConvGRU (nndepth/blocks/gru.py:5-37) around its 3xTF32
- * convolutions.  One staging buffer S (N, H*W, ctot) with row layout
- *     [ h_hi(ch) | h_lo(ch) | h_hi(ch) | x_hi(cx) | x_lo(cx) | x_hi(cx) ],  ctot = 3*(ch + cx),
- * is the NHWC input of all four convolutions of an iteration (weights [w_hi ; w_hi ; w_lo] per part).
- *   nnd_gru_stage:  src (N, C, H*W) NCHW, or (N, H*W, C) when src_channels_last != 0 -> [hi | lo | hi] at channel
- *                   offsets off_hi0 / off_lo / off_hi1.
- *   nnd_gru_gate_r: zr_pre (pixels, 2ch) NHWC conv output, bias_zr (2ch), h (pixels, ch) ->
- *                   z = sigmoid(z_pre + b) (pixels, ch);  S.h <- split(sigmoid(r_pre + b) * h).
+/* Fused, channels-last glue of the separable ConvGRU (nndepth/blocks/gru.py:5-37) around its weight-split
+ * TF32 convolutions: conv([RN_tf32(x) ; RN_tf32(x)], [w_hi ; w_lo]) -- fp32-exact weights on the tensor cores;
+ * plain TF32 weights leave the 0.01 px parity bar.  One staging buffer S (N, H*W, ctot), rows
+ * [ RN(h) (ch) | RN(x) (cx) | RN(h) | RN(x) ], ctot = 2*(ch + cx), is the NHWC input of all four convolutions of
+ * an iteration.
+ *   nnd_gru_stage:  src (N, C, H*W) NCHW, or (N, H*W, C) when src_channels_last != 0 -> RN_tf32(src) at channel
+ *                   offsets `off` and `off + ctot/2` of S.
+ *   nnd_gru_gate_r: zr_pre (pixels, 2ch) NHWC conv output [z | r], bias_zr (2ch), h (pixels, ch)
+ *                   -> z = sigmoid(z_pre + b) (pixels, ch);  S.h <- RN(sigmoid(r_pre + b) * h) (both copies).
  *   nnd_gru_gate_h: q_pre (pixels, ch), bias_q (ch), z, h -> h <- (1 - z) * h + z * tanh(q_pre + b) in place;
- *                   S.h <- split(h). */
+ *                   S.h <- RN(h) (both copies). */
 nnd_status nnd_gru_stage(const float* src, int src_channels_last, int N, int C, long long hw, float* S, int ctot,
-                         int off_hi0, int off_lo, int off_hi1, nnd_stream_t stream);
+                         int off, nnd_stream_t stream);
 nnd_status nnd_gru_gate_r(const float* zr_pre, const float* bias_zr, const float* h, long long pixels, int ch,
                           float* z, float* S, int ctot, nnd_stream_t stream);
 nnd_status nnd_gru_gate_h(const float* q_pre, const float* bias_q, const float* z, long long pixels, int ch,

@@ -40,10 +40,9 @@ SIGNATURES = {
     "nnd_soft_argmin": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "nnd_agcl_offset": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "nnd_agcl_iter": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
-    "nnd_gru_stage": (_I, [_P, _I, _I, _I, ctypes.c_longlong, _P, _I, _I, _I, _I, _P]),
+    "nnd_gru_stage": (_I, [_P, _I, _I, _I, ctypes.c_longlong, _P, _I, _I, _P]),
     "nnd_gru_gate_r": (_I, [_P, _P, _P, ctypes.c_longlong, _I, _P, _P, _I, _P]),
     "nnd_gru_gate_h": (_I, [_P, _P, _P, ctypes.c_longlong, _I, _P, _P, _I, _P]),
-    "nnd_split_tf32": (_I, [_P, _I, _I, ctypes.c_longlong, _P, _P]),
     "nnd_convex_upsample": (_I, [_P, _P, _P, _I, _I, _I, _I, ctypes.c_float, _I, _P, _P]),
     "nnd_gev_interleave_pool": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "nnd_gev_lookup": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),

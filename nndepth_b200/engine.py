@@ -99,7 +99,8 @@ class StereoEngine:
     ``(B,1,H,W)`` on the host (pinned) -- H2D copy, pad, forward, unpad and D2H all on the current stream.
     """
 
-    def __init__(self, model, device=None, use_cuda_graph=True, divis_by=32, final_only=False, channels_last_encoder=True):
+    def __init__(self, model, device=None, use_cuda_graph=True, divis_by=32, final_only=False, channels_last_encoder=True,
+                 cudnn_benchmark=True):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.model = model.to(self.device).eval()
         # final_only=False keeps the reference forward's behaviour (an upsampled map per iteration);
@@ -122,6 +123,10 @@ class StereoEngine:
         self.channels_last_encoder = channels_last_encoder
         if channels_last_encoder and hasattr(self.model, "fnet"):
             self.model.fnet.to(memory_format=torch.channels_last)
+        # fixed shapes, replayed many times: let cuDNN time its candidates once per convolution shape (its heuristic
+        # picks a 4x slower pre-Blackwell kernel for the ConvGRU's doubled-output convolutions otherwise)
+        if cudnn_benchmark:
+            torch.backends.cudnn.benchmark = True
         self.use_cuda_graph = use_cuda_graph
         self.divis_by = divis_by
         self._dev_in = {}

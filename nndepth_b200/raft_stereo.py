@@ -200,7 +200,7 @@ class SepConvGRU(nn.Module):
                 setattr(self, f"conv{gate}{tag}", nn.Conv2d(cin, hidden_dim, k, padding=p))
         self._fused = {}
         # set by RAFTStereo.dense_precision: "fp32" = cuDNN fp32 convolutions for the recurrence ("mixed"),
-        # "3xtf32" = error-compensated TF32 on tensor cores ("mixed3x"), None = whatever the caller's flags say
+        # "wsplit" = TF32 activations x split fp32 weights on tensor cores ("mixed2x"), None = the caller's flags
         self.recurrence = None
         self._split_w = {}
 
@@ -223,65 +223,48 @@ class SepConvGRU(nn.Module):
         q = torch.tanh(getattr(self, f"convq{tag}")(torch.cat([r * h, x], dim=1)))
         return (1 - z) * h + z * q
 
-    # ---- error-compensated TF32 ("3xTF32"): conv(x, w) = conv([hi; lo; hi], [w_hi; w_hi; w_lo]) --------------
+    # ---- weight-split TF32: conv(x, w) ~ conv(RN(x), w_hi) + conv(RN(x), w_lo) as ONE conv with doubled outputs ----
+    # The recurrence tolerates TF32-rounded ACTIVATIONS (fresh rounding noise every iteration) but not TF32
+    # WEIGHTS (the same perturbation 32 times): tools/exp_epe_2term.py, csrc/gru_fused.cu.
     @staticmethod
     def _rn_tf32(t):
         return ((t.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
 
-    def _split_weights(self, tag):
-        """[w_hi ; w_hi ; w_lo] along the input-channel axis for the (z|r) and q convolutions of one half-step."""
-        if tag not in self._split_w:
-            cz, cr, cq = (getattr(self, f"conv{g}{tag}") for g in "zrq")
-            out = []
-            for w, b in ((torch.cat([cz.weight, cr.weight], 0), torch.cat([cz.bias, cr.bias], 0)), (cq.weight, cq.bias)):
-                w = w.detach().float()
-                hi = self._rn_tf32(w)
-                out.append((torch.cat([hi, hi, w - hi], 1).contiguous(), b.detach().contiguous()))
-            self._split_w[tag] = (out[0], out[1], cz.padding)
-        return self._split_w[tag]
-
-    @staticmethod
-    def _split_act(t):
-        """(N, C, H, W) -> (N, 3C, H, W) = [hi ; lo ; hi] in one pass (nnd_split_tf32)."""
-        from . import _lib
-        t = t.contiguous()
-        N, C, H, W = t.shape
-        out = torch.empty(N, 3 * C, H, W, dtype=torch.float32, device=t.device)
-        with torch.cuda.device(t.device):
-            _lib.check(_lib.load().nnd_split_tf32(_lib.ptr(t), N, C, H * W, _lib.ptr(out), _lib.stream_ptr(t)),
-                       "nnd_split_tf32")
-        return out
-
-    def _half_step_3x(self, h, x, tag):
-        (wzr, bzr), (wq, bq), pad = self._split_weights(tag)
-        z, r = torch.sigmoid(F.conv2d(self._split_act(torch.cat([h, x], dim=1)), wzr, bzr, padding=pad)).chunk(2, dim=1)
-        q = torch.tanh(F.conv2d(self._split_act(torch.cat([r * h, x], dim=1)), wq, bq, padding=pad))
-        return (1 - z) * h + z * q
-
-    # ---- fused channels-last runner of the 3xTF32 recurrence (csrc/gru_fused.cu) ------------------------------
-    def _split_weights_cl(self, tag, ch):
-        """Channels-last 3x weights matching the staging row [h_hi|h_lo|h_hi|x_hi|x_lo|x_hi] of FusedGRURun."""
-        key = ("cl", tag)
+    def _split_weights(self, tag, channels_last=False):
+        """``[w_hi ; w_lo]`` along the INPUT-channel axis for the (z|r) and q convolutions of one half-step (the
+        activations are presented twice, ``[RN(x) ; RN(x)]``)."""
+        key = (tag, channels_last)
         if key not in self._split_w:
             cz, cr, cq = (getattr(self, f"conv{g}{tag}") for g in "zrq")
             packed = []
             for w, b in ((torch.cat([cz.weight, cr.weight], 0), torch.cat([cz.bias, cr.bias], 0)), (cq.weight, cq.bias)):
                 w = w.detach().float()
                 hi = self._rn_tf32(w)
-                lo = w - hi
-                w3 = torch.cat([hi[:, :ch], hi[:, :ch], lo[:, :ch], hi[:, ch:], hi[:, ch:], lo[:, ch:]], 1)
-                packed.append((w3.contiguous(memory_format=torch.channels_last), b.detach().float().contiguous()))
+                w2 = torch.cat([hi, w - hi], 1).contiguous()
+                if channels_last:
+                    w2 = w2.contiguous(memory_format=torch.channels_last)
+                packed.append((w2, b.detach().float().contiguous()))
             self._split_w[key] = (packed[0], packed[1], cz.padding)
         return self._split_w[key]
 
+    def _half_step_wsplit(self, h, x, tag):
+        """The same recurrence through torch ops (the fused runner's reference and its fallback)."""
+        (wzr, bzr), (wq, bq), pad = self._split_weights(tag)
+        hx = self._rn_tf32(torch.cat([h, x], dim=1))
+        z, r = torch.sigmoid(F.conv2d(torch.cat([hx, hx], 1), wzr, bzr, padding=pad)).chunk(2, dim=1)
+        rhx = self._rn_tf32(torch.cat([r * h, x], dim=1))
+        q = torch.tanh(F.conv2d(torch.cat([rhx, rhx], 1), wq, bq, padding=pad))
+        return (1 - z) * h + z * q
+
+    # ---- fused channels-last runner of the weight-split recurrence (csrc/gru_fused.cu) -------------------------
     def start(self, h0, inp):
         """Begin a forward: returns the per-forward runner holding the hidden state and the staging buffer."""
         return FusedGRURun(self, h0, inp)
 
     def forward(self, h, x):
-        if self.recurrence == "3xtf32" and h.is_cuda:
+        if self.recurrence == "wsplit" and h.is_cuda:
             with cudnn_tf32(True):
-                return self._half_step_3x(self._half_step_3x(h, x, "1"), x, "2")
+                return self._half_step_wsplit(self._half_step_wsplit(h, x, "1"), x, "2")
         if self.recurrence == "fp32":
             with cudnn_tf32(False):
                 return self._half_step(self._half_step(h, x, "1"), x, "2")
@@ -289,13 +272,13 @@ class SepConvGRU(nn.Module):
 
 
 class FusedGRURun:
-    """One forward's worth of the 3xTF32 ConvGRU on the fused channels-last kernels.
+    """One forward's worth of the weight-split TF32 ConvGRU on the fused channels-last kernels.
 
     Holds the hidden state ``h`` (channels-last) and the staging buffer ``S`` whose rows are
-    ``[h_hi|h_lo|h_hi|x_hi|x_lo|x_hi]``; ``S`` is the NHWC input of all four convolutions of an iteration, so
-    cuDNN's tensor-core kernels run without layout conversions and every elementwise step between two
-    convolutions is ONE kernel (``nnd_gru_gate_r`` / ``nnd_gru_gate_h``).  The context half of ``x`` is staged
-    once per forward, the motion half once per iteration.
+    ``[RN(h) | RN(x) | RN(h) | RN(x)]``; ``S`` is the NHWC input of all four convolutions of an iteration (weights
+    ``[w_hi ; w_lo]`` along the input channels), so cuDNN's tensor-core kernels run without layout conversions
+    and every elementwise step between two convolutions is ONE kernel (``nnd_gru_gate_r`` / ``nnd_gru_gate_h``).  The context half of ``x`` is staged once
+    per forward, the motion half once per iteration.
     """
 
     def __init__(self, gru, h0, inp):
@@ -307,18 +290,17 @@ class FusedGRURun:
         self.N, self.ch, self.H, self.W = N, ch, H, W
         self.c_inp = inp.shape[1]
         self.cx = gru.convz1.weight.shape[1] - ch
-        self.ctot = 3 * (ch + self.cx)
+        self.ctot = 2 * (ch + self.cx)
         cl = torch.channels_last
         self.S = torch.empty(N, self.ctot, H, W, dtype=torch.float32, device=h0.device).contiguous(memory_format=cl)
         self.h = torch.empty(N, ch, H, W, dtype=torch.float32, device=h0.device).contiguous(memory_format=cl)
         self.z = torch.empty_like(self.h)
         self.h.copy_(h0)
-        self._stage(h0, 0, ch, 2 * ch)
-        x0 = 3 * ch
-        self._stage(inp, x0, x0 + self.cx, x0 + 2 * self.cx)
+        self._stage(h0, 0)
+        self._stage(inp, ch)
 
-    def _stage(self, src, off_hi0, off_lo, off_hi1):
-        """Write ``[hi | lo | hi]`` of ``src`` into the staging rows; a channels-last ``src`` is read as it lies."""
+    def _stage(self, src, off):
+        """Write ``RN_tf32(src)`` at channel offset ``off`` of the staging rows; a channels-last ``src`` is read as it lies."""
         lib = self._lib
         N, C = src.shape[0], src.shape[1]
         src = src.float()
@@ -327,20 +309,19 @@ class FusedGRURun:
             src = src.contiguous()
         with torch.cuda.device(src.device):
             lib.check(lib.load().nnd_gru_stage(lib.ptr(src), 1 if cl else 0, N, C, self.H * self.W, lib.ptr(self.S), self.ctot,
-                                               off_hi0, off_lo, off_hi1, lib.stream_ptr(src)), "nnd_gru_stage")
+                                               off, lib.stream_ptr(src)), "nnd_gru_stage")
 
     def step(self, motion):
         """One GRU update with ``x = cat[inp, motion]``; returns the new hidden state (channels-last view)."""
         lib = self._lib
         if motion.shape[1] != self.cx - self.c_inp:
             raise RuntimeError(f"motion features must have {self.cx - self.c_inp} channels, got {motion.shape[1]}")
-        x0 = 3 * self.ch + self.c_inp
-        self._stage(motion, x0, x0 + self.cx, x0 + 2 * self.cx)
+        self._stage(motion, self.ch + self.c_inp)
         pixels = self.N * self.H * self.W
         cl = torch.channels_last
         with cudnn_tf32(True), torch.cuda.device(self.S.device):
             for tag in "12":
-                (wzr, bzr), (wq, bq), pad = self.gru._split_weights_cl(tag, self.ch)
+                (wzr, bzr), (wq, bq), pad = self.gru._split_weights(tag, channels_last=True)
                 zr = F.conv2d(self.S, wzr, None, padding=pad).contiguous(memory_format=cl)
                 lib.check(lib.load().nnd_gru_gate_r(lib.ptr(zr), lib.ptr(bzr), lib.ptr(self.h), pixels, self.ch, lib.ptr(self.z),
                                                     lib.ptr(self.S), self.ctot, lib.stream_ptr(zr)), "nnd_gru_gate_r")
@@ -404,7 +385,7 @@ class BasicUpdateBlock(nn.Module):
         (N,576,H,W) tensor."""
         motion = self.encoder(flow, corr, cor1=cor1)
         if gru_run is not None:
-            net = gru_run.step(motion)          # fused channels-last 3xTF32 recurrence; `net` lives in the runner
+            net = gru_run.step(motion)          # fused channels-last weight-split recurrence; `net` lives in the runner
         else:
             net = self.gru(net, torch.cat((inp, motion), dim=1))
         hidden = conv_relu(self.mask[0], net)
@@ -448,11 +429,12 @@ class RAFTStereo(nn.Module):
         self.strict_load = strict_load
         self.final_only = False     # True: upsample only the last iteration (what evaluate.py:155 consumes)
         self.fuse_motion_front = True   # lookup + convc1 + ReLU as one kernel when corr_fn provides it
-        self.fuse_gru = True            # 3xTF32 ConvGRU on the fused channels-last kernels (mode "mixed3x")
+        self.fuse_gru = True            # weight-split ConvGRU on the fused channels-last kernels (mode "mixed2x")
         # Precision of the dense (cuDNN) layers, measured on the KITTI/32-iteration golden (tools/exp_epe_modules.py):
         #   "fp32"  every convolution in fp32                           final EPE vs reference 0.0002 px
         #   "mixed" ConvGRU in fp32, everything else on TF32 tensor cores              0.0021 px  (bar: 0.01 px)
-        #   "mixed3x" as "mixed", the ConvGRU as error-compensated 3xTF32 on tensor cores 0.0020 px, 2x faster
+        #   "mixed2x" as "mixed", the ConvGRU with TF32 activations x split fp32 weights [w_hi; w_lo] on tensor
+        #           cores (the recurrence is sensitive to weight rounding only)          0.0031 px, 3x faster
         #   "tf32"  everything TF32 (PyTorch's CUDA default)                           0.0147 px  -> outside the bar
         # None leaves torch.backends.cudnn.allow_tf32 as the caller set it.
         self.dense_precision = None
@@ -487,12 +469,12 @@ class RAFTStereo(nn.Module):
     def forward(self, frame1, frame2, **kwargs):
         if self.dense_precision is None:
             return self._forward(frame1, frame2, **kwargs)
-        if self.dense_precision not in ("fp32", "mixed", "mixed3x", "tf32"):
-            raise ValueError("dense_precision must be None, 'fp32', 'mixed', 'mixed3x' or 'tf32', "
+        if self.dense_precision not in ("fp32", "mixed", "mixed2x", "tf32"):
+            raise ValueError("dense_precision must be None, 'fp32', 'mixed', 'mixed2x' or 'tf32', "
                              f"got {self.dense_precision!r}")
         gru = getattr(self.update_block, "gru", None)
         if gru is not None:
-            gru.recurrence = {"mixed": "fp32", "mixed3x": "3xtf32"}.get(self.dense_precision)
+            gru.recurrence = {"mixed": "fp32", "mixed2x": "wsplit"}.get(self.dense_precision)
         with cudnn_tf32(self.dense_precision != "fp32"):
             return self._forward(frame1, frame2, **kwargs)
 
@@ -506,7 +488,7 @@ class RAFTStereo(nn.Module):
         corr = self.corr_fn(fmap1, fmap2, self.corr_levels, self.corr_radius)
         gru = getattr(self.update_block, "gru", None)
         gru_run = None
-        if (self.fuse_gru and gru is not None and getattr(gru, "recurrence", None) == "3xtf32" and net.is_cuda
+        if (self.fuse_gru and gru is not None and getattr(gru, "recurrence", None) == "wsplit" and net.is_cuda
                 and not torch.is_grad_enabled()):
             gru_run = gru.start(net, inp)
         org_coords = self.initialize_coords(fmap1)

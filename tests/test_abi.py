@@ -80,7 +80,7 @@ def test_invalid_arguments_are_reported_not_crashed(lib):
                                        dummy, None)
     assert st == 1 and b"4-level" in lib.nnd_last_error_string()
     # GRU glue: channel counts in quads
-    st = lib.nnd_gru_gate_r(dummy, dummy, dummy, 8, 6, dummy, dummy, 36, None)
+    st = lib.nnd_gru_gate_r(dummy, dummy, dummy, 8, 6, dummy, dummy, 40, None)
     assert st == 1 and b"ch % 4" in lib.nnd_last_error_string()
 
 

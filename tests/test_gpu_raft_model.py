@@ -66,7 +66,7 @@ def test_kitti_32_iterations(golden, precision):
     assert epe(graphed, ref) < EPE_BAR, epe(graphed, ref)
 
 
-@pytest.mark.parametrize("mode,bar", [("fp32", 0.001), ("mixed", EPE_BAR), ("mixed3x", EPE_BAR)])
+@pytest.mark.parametrize("mode,bar", [("fp32", 0.001), ("mixed", EPE_BAR), ("mixed2x", EPE_BAR)])
 def test_kitti_dense_precision_modes(golden, mode, bar):
     """The bench's dense-layer precision modes against the reference disparity (KITTI geometry, 32 iterations):
     "mixed" (ConvGRU fp32, other convolutions TF32) must stay inside the 0.01 px bar, "fp32" far inside."""
@@ -84,8 +84,8 @@ def test_kitti_dense_precision_modes(golden, mode, bar):
     assert epe(graphed, ref) < bar, epe(graphed, ref)
 
 
-def test_fused_gru_matches_unfused_3xtf32():
-    """The fused channels-last ConvGRU runner vs the same 3xTF32 recurrence written with torch ops, and vs fp32."""
+def test_fused_gru_matches_unfused_weight_split():
+    """The fused channels-last ConvGRU runner vs the same weight-split TF32 recurrence written with torch ops, and vs fp32."""
     from nndepth_b200.raft_stereo import SepConvGRU, cudnn_tf32
     torch.manual_seed(7)
     gru = SepConvGRU(hidden_dim=128, input_dim=256).cuda().eval()
@@ -94,7 +94,7 @@ def test_fused_gru_matches_unfused_3xtf32():
     inp = torch.relu(torch.randn(N, 128, H, W, device="cuda"))
     motions = [torch.randn(N, 128, H, W, device="cuda") for _ in range(3)]
     with torch.no_grad():
-        gru.recurrence = "3xtf32"
+        gru.recurrence = "wsplit"
         run = gru.start(h0, inp)
         h_ref, h_fp32 = h0, h0
         for m in motions:
@@ -102,21 +102,21 @@ def test_fused_gru_matches_unfused_3xtf32():
             h_ref = gru(h_ref, torch.cat([inp, m], 1))
             gru.recurrence = "fp32"
             h_fp32 = gru(h_fp32, torch.cat([inp, m], 1))
-            gru.recurrence = "3xtf32"
+            gru.recurrence = "wsplit"
             assert fused.shape == h_ref.shape
-            assert (fused - h_ref).abs().max().item() < 2e-5
-            assert (fused - h_fp32).abs().max().item() < 2e-5
+            assert (fused - h_ref).abs().max().item() < 2e-5        # same arithmetic, fused vs torch ops
+            assert (fused - h_fp32).abs().max().item() < 1e-3       # activations are rounded to TF32 (2^-11 relative)
 
 
 def test_engine_bench_configuration_stays_inside_the_bar(golden):
     """The exact configuration bench.py times -- StereoEngine (channels-last encoder, CUDA graph, fused GRU glue,
-    fused lookup / upsampling), dense_precision = "mixed3x" -- against the reference disparity."""
+    fused lookup / upsampling), dense_precision = "mixed2x" -- against the reference disparity."""
     from nndepth_b200.engine import StereoEngine
     from nndepth_b200.raft_stereo import BaseRAFTStereo
     g = golden("raft_kitti")
     torch.manual_seed(0)
     model = BaseRAFTStereo(iters=int(g["iters"])).eval()
-    model.dense_precision = "mixed3x"
+    model.dense_precision = "mixed2x"
     engine = StereoEngine(model, device="cuda", use_cuda_graph=True)
     left, right = (t.cuda() for t in seeded_pair(g["shape"]))
     ref = torch.from_numpy(g["final_up_disp"]).cuda()
@@ -130,14 +130,14 @@ def test_engine_bench_configuration_stays_inside_the_bar(golden):
 
 @pytest.mark.parametrize("graph", [False, True])
 def test_small_all_iterations_bench_mode(golden, graph):
-    """The bench's mode (mixed3x, every fusion on) at the small golden shape: every iteration's upsampled map
+    """The bench's mode (mixed2x, every fusion on) at the small golden shape: every iteration's upsampled map
     against the reference, eager and as a CUDA graph (few pixel groups, ragged tiles, 12 iterations)."""
     from nndepth_b200.engine import StereoEngine
     from nndepth_b200.raft_stereo import BaseRAFTStereo
     g = golden("raft_small")
     torch.manual_seed(0)
     model = BaseRAFTStereo(iters=int(g["iters"])).eval()
-    model.dense_precision = "mixed3x"
+    model.dense_precision = "mixed2x"
     engine = StereoEngine(model, device="cuda", use_cuda_graph=graph)
     left, right = (t.cuda() for t in seeded_pair(g["shape"]))
     ref = torch.from_numpy(g["all_up_disp"]).cuda()

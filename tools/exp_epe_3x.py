@@ -11,7 +11,7 @@ ref = torch.from_numpy(g["final_up_disp"]).cuda()
 torch.manual_seed(0)
 model = BaseRAFTStereo(iters=32).eval().cuda()
 model.final_only = True
-for mode in ("fp32", "mixed", "mixed3x", "tf32"):
+for mode in ("fp32", "mixed", "mixed2x", "tf32"):
     model.dense_precision = mode
     with torch.no_grad():
         out = model(left, right)[-1]["up_disp"]
@@ -19,7 +19,7 @@ for mode in ("fp32", "mixed", "mixed3x", "tf32"):
     print(f"{mode:8s} EPE={d.mean().item():.5f} px  max={d.max().item():.4f}", flush=True)
 # only the GRU in 3xTF32, everything else fp32: isolates the split's own error
 model.dense_precision = None
-model.update_block.gru.recurrence = "3xtf32"
+model.update_block.gru.recurrence = "wsplit"
 torch.backends.cudnn.allow_tf32 = False
 with torch.no_grad():
     out = model(left, right)[-1]["up_disp"]

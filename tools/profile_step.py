@@ -12,7 +12,7 @@ from nndepth_b200.raft_stereo import BaseRAFTStereo  # noqa: E402
 torch.manual_seed(0)
 channels_last = "--channels-last" in sys.argv
 model = BaseRAFTStereo(iters=32).eval()
-model.dense_precision = next((a.split("=")[1] for a in sys.argv if a.startswith("--mode=")), "mixed3x")
+model.dense_precision = next((a.split("=")[1] for a in sys.argv if a.startswith("--mode=")), "mixed2x")
 engine = StereoEngine(model, use_cuda_graph=False)
 if channels_last:
     engine.model = engine.model.to(memory_format=torch.channels_last)
