@@ -1,0 +1,76 @@
+"""CPU tests of the host-side helpers around the kernels (no GPU needed): TF32 rounding, BatchNorm folding, the
+weight split of the ConvGRU, the model shell's state-dict compatibility with the reference layout."""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from nndepth_b200 import raft_stereo as rs
+
+
+def test_rn_tf32_is_round_to_nearest_on_10_mantissa_bits():
+    x = torch.tensor([1.0, 1.0 + 2 ** -11, 1.0 + 2 ** -11 + 2 ** -20, 1.0 + 2 ** -10, -3.1415927, 1e-30, 65504.0, 0.0])
+    y = rs.rn_tf32(x)
+    bits = y.view(torch.int32)
+    assert torch.all((bits & 0x1FFF) == 0)                       # low 13 mantissa bits cleared
+    assert torch.all((y - x).abs() <= x.abs() * 2.0 ** -11)       # half an ulp of a 10-bit mantissa
+    assert y[0] == 1.0 and y[2] == 1.0 + 2 ** -10 and y[3] == 1.0 + 2 ** -10
+    # ties round away from zero (cvt.rna), like the device kernels
+    assert y[1] == 1.0 + 2 ** -10
+
+
+def test_fold_bn_matches_conv_followed_by_eval_batchnorm():
+    torch.manual_seed(0)
+    conv = nn.Conv2d(5, 7, 3, padding=1)
+    bn = nn.BatchNorm2d(7).eval()
+    with torch.no_grad():
+        bn.running_mean.uniform_(-1, 1)
+        bn.running_var.uniform_(0.5, 2)
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.uniform_(-1, 1)
+    x = torch.randn(2, 5, 6, 8)
+    w, b = rs.fold_bn(conv, bn)
+    with torch.no_grad():
+        ref = bn(conv(x))
+        got = F.conv2d(x, w, b, padding=1)
+    assert torch.allclose(got, ref, rtol=1e-5, atol=1e-5)
+    w32, _ = rs.fold_bn(conv, bn, tf32=True)
+    assert torch.equal(w32, rs.rn_tf32(w))
+
+
+def test_gru_weight_split_reconstructs_the_weights_exactly():
+    torch.manual_seed(1)
+    gru = rs.SepConvGRU(hidden_dim=8, input_dim=12)
+    (wzr, bzr), (wq, bq), pad = gru._split_weights("1")
+    cin = 8 + 12
+    assert wzr.shape == (16, 2 * cin, 1, 5) and wq.shape == (8, 2 * cin, 1, 5) and pad == (0, 2)
+    full = torch.cat([gru.convz1.weight, gru.convr1.weight], 0)
+    assert torch.equal(wzr[:, :cin] + wzr[:, cin:], full)            # w_hi + w_lo == w, exactly
+    assert torch.equal(wzr[:, :cin], rs.rn_tf32(full.detach()))
+    assert torch.equal(bzr, torch.cat([gru.convz1.bias, gru.convr1.bias], 0))
+    # the torch-op form of the weight-split recurrence equals the plain recurrence up to TF32 rounding of the activations
+    h, x = torch.tanh(torch.randn(1, 8, 4, 6)), torch.randn(1, 12, 4, 6)
+    with torch.no_grad():
+        ref = gru._half_step(h, x, "1")
+        got = gru._half_step_wsplit(h, x, "1")
+    assert (got - ref).abs().max().item() < 5e-3
+
+
+def test_model_shell_parameter_names_follow_the_reference_layout():
+    torch.manual_seed(0)
+    model = rs.BaseRAFTStereo(iters=2)
+    names = set(model.state_dict().keys())
+    for expected in ("fnet.conv1.weight", "fnet.layer1.0.conv1.weight", "fnet.layer3.1.downsample.0.weight", "fnet.conv2.bias",
+                     "cnet_proj.0.weight", "update_block.encoder.convc1.weight", "update_block.gru.convz1.weight",
+                     "update_block.gru.convq2.bias", "update_block.flow_head.conv2.weight", "update_block.mask.2.weight"):
+        assert expected in names, expected
+    assert model.update_block.encoder.convc1.weight.shape == (256, 36, 1, 1)
+    assert model.update_block.mask[2].weight.shape == (576, 256, 1, 1)
+    # CPU forward of the shell with the oracle correlation block (the path bench.py --impl reference times)
+    from oracle import torch_port
+    model.corr_fn = torch_port.CorrBlock1D
+    model.eval()
+    with torch.no_grad():
+        outs = model(torch.rand(1, 3, 64, 160) * 2 - 1, torch.rand(1, 3, 64, 160) * 2 - 1)
+    assert len(outs) == 2 and outs[-1]["up_disp"].shape == (1, 1, 64, 160) and torch.isfinite(outs[-1]["up_disp"]).all()
+    assert np.isfinite(outs[0]["up_disp"].numpy()).all()
