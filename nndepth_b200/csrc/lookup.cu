@@ -492,7 +492,7 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&
 template <int TAPS>
 __global__ void __launch_bounds__(128)
 corr1d_lookup_conv1x1_tc_kernel(const __grid_constant__ LookupArgs a, const float* __restrict__ weight,
-                                const float* __restrict__ bias, int c_out, int relu, long long n_groups) {
+                                const float* __restrict__ bias, int c_out, int relu, int out_nhwc, long long n_groups) {
   constexpr int WINQ = 4, COLS = 4 * WINQ, STRIDE = COLS + 4;  // 16-byte aligned rows for the 16-byte cp.async copies
   constexpr int R = (TAPS - 1) / 2;
   constexpr int K = 4 * TAPS;        // 36 lookup channels (4 levels)
@@ -625,6 +625,19 @@ corr1d_lookup_conv1x1_tc_kernel(const __grid_constant__ LookupArgs a, const floa
           for (int i = 0; i < 4; ++i) d[i] = fmaxf(d[i], 0.f);
         }
         const int r0 = 64 * lvl + 16 * mt + gid, r1 = r0 + 8;
+        if (out_nhwc) {
+          // channels-last output (B, H*W, c_out): eight lanes (gid) write 32 contiguous bytes of one pixel
+          float* o = a.out + (static_cast<long long>(b) * a.hw + rem0 + px) * c_out;
+          if (rem0 + px < a.hw) {
+            if (r0 < c_out) o[r0] = d[0];
+            if (r1 < c_out) o[r1] = d[2];
+          }
+          if (rem0 + px + 1 < a.hw) {
+            if (r0 < c_out) o[c_out + r0] = d[1];
+            if (r1 < c_out) o[c_out + r1] = d[3];
+          }
+          continue;
+        }
         float* o0 = out_img + static_cast<long long>(r0) * a.hw + px;
         float* o1 = out_img + static_cast<long long>(r1) * a.hw + px;
         if (rem0 + px + 1 < a.hw && (a.hw & 1) == 0) {
@@ -994,8 +1007,8 @@ nnd_status nnd_gev_lookup(const float* const* level_feat, const float* const* le
 
 nnd_status nnd_corr1d_lookup_conv1x1(const float* const* level, const int* width, const int* pitch, const float* coords,
                                      int B, int H, int W1, int num_levels, int radius, const float* weight,
-                                     const float* bias, int c_out, int relu, int precision, float* out,
-                                     nnd_stream_t stream) {
+                                     const float* bias, int c_out, int relu, int precision, int out_channels_last,
+                                     float* out, nnd_stream_t stream) {
   using namespace nnd;
   NND_REQUIRE(level && width && pitch && coords && weight && out, "lookup_conv1x1: null pointer argument");
   NND_REQUIRE(B > 0 && H > 0 && W1 > 0 && c_out > 0, "lookup_conv1x1: B, H, W1, c_out must be positive");
@@ -1030,9 +1043,10 @@ nnd_status nnd_corr1d_lookup_conv1x1(const float* const* level, const int* width
     const long long resident = static_cast<long long>(sm_count()) * 3;   // 128 threads x ~150 registers
     dim3 grid_tc(static_cast<unsigned>(n_groups_all < resident ? n_groups_all : resident));
     corr1d_lookup_conv1x1_tc_kernel<9><<<grid_tc, dim3(32, 4), smem_tc, reinterpret_cast<cudaStream_t>(stream)>>>(
-        a, weight, bias, c_out, relu ? 1 : 0, n_groups_all);
+        a, weight, bias, c_out, relu ? 1 : 0, out_channels_last ? 1 : 0, n_groups_all);
     return check_launch("corr1d_lookup_conv1x1_tc_kernel");
   }
+  NND_REQUIRE(!out_channels_last, "lookup_conv1x1: the channels-last output is provided by the tensor-core path only");
   const int K = num_levels * 9;
   const size_t c_pad = (static_cast<size_t>(c_out) + 3) & ~static_cast<size_t>(3);
   const size_t smem = (c_pad * K + c_pad + static_cast<size_t>(K) * 32 + static_cast<size_t>(num_levels) * 32 * 17) *

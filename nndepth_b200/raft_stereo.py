@@ -503,8 +503,10 @@ class RAFTStereo(nn.Module):
                 conv1 = self.update_block.encoder.convc1
                 if it == 0:
                     conv1_wt = corr.prepare_conv1x1_weight(conv1.weight)    # k-major copy, once per forward
+                tf32 = bool(torch.backends.cudnn.allow_tf32)
                 sampled, cor1 = None, corr.lookup_conv1x1(coords1, None, conv1.bias, relu=True, weight_t=conv1_wt,
-                                                          precision="tf32" if torch.backends.cudnn.allow_tf32 else "fp32")
+                                                          precision="tf32" if tf32 else "fp32",
+                                                          channels_last=tf32 and self.update_block.encoder.channels_last)
             else:
                 sampled, cor1 = corr(coords1), None
             # on the GPU the convex upsampling is one fused kernel (softmax + unfold + weighted sum + pixel

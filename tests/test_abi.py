@@ -76,7 +76,7 @@ def test_invalid_arguments_are_reported_not_crashed(lib):
     st = lib.nnd_convex_upsample(dummy, dummy, None, 1, 4, 4, 3, 1.0, 0, dummy, None)
     assert st == 1 and b"rate" in lib.nnd_last_error_string()
     # fused lookup + 1x1 convolution is the 4-level, radius-4 configuration
-    st = lib.nnd_corr1d_lookup_conv1x1(lv, _lib.int_array([8]), _lib.int_array([8]), dummy, 1, 1, 8, 1, 4, dummy, None, 16, 1, 0,
+    st = lib.nnd_corr1d_lookup_conv1x1(lv, _lib.int_array([8]), _lib.int_array([8]), dummy, 1, 1, 8, 1, 4, dummy, None, 16, 1, 0, 0,
                                        dummy, None)
     assert st == 1 and b"4-level" in lib.nnd_last_error_string()
     # GRU glue: channel counts in quads

@@ -382,7 +382,10 @@ def test_lookup_conv1x1_fusion(shape, c_out):
     # tensor-core variant: operands rounded to nearest TF32 -> the 1e-3 bar
     with torch.no_grad():
         tc = blk.lookup_conv1x1(coords, conv.weight, conv.bias, relu=True, precision="tf32")
+        tc_cl = blk.lookup_conv1x1(coords, conv.weight, conv.bias, relu=True, precision="tf32", channels_last=True)
     assert (tc - ref).abs().max().item() <= 1e-3 * scale
+    assert tc_cl.shape == tc.shape and tc_cl.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(tc_cl, tc)                       # same numbers, channels-last memory
 
 
 def test_randomised_lookup_sweep_bit_exact():
