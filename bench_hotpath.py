@@ -169,6 +169,26 @@ def cfg4(skip_cpu):
     del geo, il
     coords = torch.arange(W, device="cuda").float().view(1, 1, 1, W).repeat(B, 1, H, 1) - torch.rand(B, 1, H, W, device="cuda") * 40
     us["dual_lookup"] = gpu_us(lambda: cv(coords), reps=6)
+    # initial disparity: cv_squeezer Conv3d(8->1) + softmax + regress_disparity (igev_stereo/model.py:143-146)
+    torch.manual_seed(1)
+    squeezer = torch.nn.Conv3d(G, 1, 3, 1, 1).cuda()
+    with torch.no_grad():
+        us["squeeze_soft_argmin_fused"] = gpu_us(lambda: cv.init_disparity(squeezer), reps=6)
+
+        def unfused():
+            g0 = cv._geo_il.reference_level(0, B, H, W).reshape(B, G, H, W, W).permute(0, 1, 4, 2, 3)
+            return nb.soft_argmin(squeezer(g0).squeeze(1))
+
+        def torch_chain(g0):
+            p = torch.softmax(squeezer(g0).squeeze(1), dim=1)
+            return -(torch.arange(W, device="cuda").float().view(1, -1, 1, 1) * p).sum(1, keepdim=True)
+
+        g0 = cv._geo_il.reference_level(0, B, H, W).reshape(B, G, H, W, W).permute(0, 1, 4, 2, 3)
+        us["squeeze_cudnn_conv3d_tf32_plus_torch_softmax"] = gpu_us(lambda: torch_chain(g0), reps=3)
+        with torch.backends.cudnn.flags(allow_tf32=False):
+            us["squeeze_cudnn_conv3d_fp32_plus_torch_softmax"] = gpu_us(lambda: torch_chain(g0), reps=3)
+            diff = (cv.init_disparity(squeezer) - torch_chain(g0)).abs().max().item()
+        del g0
     del cv
     z = torch.randn(B, W, H, W, device="cuda")
     us["soft_argmin"] = gpu_us(lambda: nb.soft_argmin(z), reps=6)
@@ -179,7 +199,11 @@ def cfg4(skip_cpu):
            "other_rooflines": [roof("groupcorr_build_kernel<8>", 2 * B * 64 * H * W * 4 + vol_bytes, us["groupcorr_build_level0"]),
                                roof("gev_interleave_dmajor_kernel", vol_bytes + pyr_bytes, us["interleave_pool_feat"]),
                                roof("gev_interleave_wmajor_kernel", vol_bytes + pyr_bytes, us["interleave_pool_geo"]),
-                               roof("soft_argmin_kernel<4>", B * W * H * W * 4 + B * H * W * 4, us["soft_argmin"])]}
+                               roof("soft_argmin_kernel<4>", B * W * H * W * 4 + B * H * W * 4, us["soft_argmin"]),
+                               dict(roof("gev_squeeze_soft_argmin_kernel", vol_bytes + B * H * W * 4, us["squeeze_soft_argmin_fused"]),
+                                    fp32_gflop=2 * 216 * B * W * H * W / 1e9,
+                                    ffma_tflops=2 * 216 * B * W * H * W / us["squeeze_soft_argmin_fused"] / 1e6,
+                                    max_abs_diff_vs_torch_fp32_px=diff)]}
     if not skip_cpu:
         rng = np.random.default_rng(0)
         b, h = 1, 8

@@ -158,6 +158,18 @@ nnd_status nnd_gev_lookup(const float* const* level_feat, const float* const* le
  *   z (B,D,H,W) -> out (B,1,H,W). */
 nnd_status nnd_soft_argmin(const float* z, int B, int D, int H, int W, float* out, nnd_stream_t stream);
 
+/* cv_squeezer + soft-argmin in one pass over the interleaved level-0 geometry volume:
+ *   cost[b,d,h,w] = bias + sum_{g,kd,kh,kw} weight[0,g,kd,kh,kw] * geo[b,g,d+kd-1,h+kh-1,w+kw-1]  (zero padded)
+ *   out[b,0,h,w]  = -sum_d d * softmax_d(cost[b,:,h,w])
+ * Replaces nn.Conv3d(8, 1, 3, 1, 1) on geo_aware_cv[0].reshape(...).permute(0,1,4,2,3), squeeze, F.softmax and
+ * regress_disparity: igev_stereo/model.py:65, 143-146, 92-95.
+ *   geo_level0: level 0 written by nnd_gev_interleave_pool ([b][h][w1][d][g], G = 8); weight: the Conv3d
+ *   weight (1,8,3,3,3) contiguous, device memory; bias: 1 float in device memory or NULL; D <= 512;
+ *   out (B,1,H,W1); cost_out: optional (B,D,H,W1) copy of the squeezed cost (parity tests), or NULL. */
+nnd_status nnd_gev_squeeze_soft_argmin(const float* geo_level0, const float* weight, const float* bias, int B,
+                                       int G, int D, int H, int W1, float* out, float* cost_out,
+                                       nnd_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * CREStereo AGCL.  fmap1/fmap2 (N,C,H,W) NCHW, C % 4 == 0; flow (N,2,H,W) (x, y);
  * out (N, 36, H, W), channel g*9 + k; small_patch: 0 = 1x9 window, 1 = 3x3 window.

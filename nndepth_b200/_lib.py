@@ -38,6 +38,7 @@ SIGNATURES = {
     "nnd_group_lookup": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "nnd_geo_transpose_pool": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "nnd_soft_argmin": (_I, [_P, _I, _I, _I, _I, _P, _P]),
+    "nnd_gev_squeeze_soft_argmin": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "nnd_agcl_offset": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "nnd_agcl_iter": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "nnd_gru_stage": (_I, [_P, _I, _I, _I, ctypes.c_longlong, _P, _I, _I, _P]),

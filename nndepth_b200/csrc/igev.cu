@@ -308,6 +308,134 @@ static int soft_argmin_slices(long long units, int D) {
   return S;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// cv_squeezer (Conv3d(8 -> 1, 3x3x3, padding 1), igev_stereo/model.py:65,144-145) fused with the soft-argmin
+// (model.py:92-95,146) on the interleaved level-0 geometry volume [b][h][w][d][g].
+//
+// Thread = one input disparity plane d' with its 8 groups in registers (two 16-byte loads per neighbour
+// pixel, lanes run along d' = contiguous memory).  Instead of gathering the three d-taps of an output, every
+// thread SCATTERS: it accumulates, per output pixel of its SQ_TH x SQ_TW register tile, the three partial
+// sums A_kd[d'] = sum_{g,kh,kw} W[g,kd,kh,kw] * x[g,d',h+kh-1,w+kw-1]; the 216 weights are immediate
+// constant-bank operands of the FFMAs (static indices after unrolling), so a neighbour pixel costs 2 loads
+// for up to 96 FFMAs.  out[d] = bias + A_0[d-1] + A_1[d] + A_2[d+1] is assembled through shared memory in
+// a fixed order (deterministic) and one warp per pixel runs the online softmax-expectation over d.
+// ---------------------------------------------------------------------------------------------------
+constexpr int SQ_TH = 2, SQ_TW = 4, SQ_PX = SQ_TH * SQ_TW;
+// Conv3d weight (1, 8, 3, 3, 3) repacked [kd][kh][kw][g] (the eight group weights of a tap = two uniform
+// 16-byte constant loads), bias in [54].x.  Filled stream-ordered from g_squeeze_stage by the ABI call.
+__constant__ float4 c_squeeze[56];
+__device__ float g_squeeze_stage[224];
+
+__global__ void squeeze_pack_kernel(const float* __restrict__ weight, const float* __restrict__ bias) {
+  const int i = threadIdx.x;  // destination index ((kd*3 + kh)*3 + kw)*8 + g
+  if (i < 216) g_squeeze_stage[i] = weight[(i & 7) * 27 + (i >> 3)];
+  if (i >= 216 && i < 224) g_squeeze_stage[i] = (i == 216 && bias) ? bias[0] : 0.f;
+}
+
+template <int MAX_THREADS>
+__global__ void __launch_bounds__(MAX_THREADS)
+gev_squeeze_soft_argmin_kernel(const float* __restrict__ geo, int D, int H, int W, float* __restrict__ out,
+                               float* __restrict__ cost_out) {
+  extern __shared__ float sq_part[];  // [3][SQ_PX][D + 2], index d' + 1; [0] and [D + 1] stay zero
+  const int Dp = D + 2;
+  const int w0 = blockIdx.x * SQ_TW, h0 = blockIdx.y * SQ_TH, b = blockIdx.z;
+  const int dq = threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+
+  float acc[SQ_PX][3];
+#pragma unroll
+  for (int p = 0; p < SQ_PX; ++p) acc[p][0] = acc[p][1] = acc[p][2] = 0.f;
+
+  if (dq < D) {
+#pragma unroll
+    for (int nh = 0; nh < SQ_TH + 2; ++nh) {
+      // one row of neighbour pixels in registers: every weight vector then feeds SQ_TW output pixels
+      const int hh = h0 + nh - 1;
+      const bool row_ok = hh >= 0 && hh < H;
+      const float4* row = reinterpret_cast<const float4*>(
+          geo + (((static_cast<long long>(b) * H + (row_ok ? hh : 0)) * W) * D + dq) * 8);
+      float4 v0[SQ_TW + 2], v1[SQ_TW + 2];
+#pragma unroll
+      for (int nw = 0; nw < SQ_TW + 2; ++nw) {
+        const int ww = w0 + nw - 1;
+        v0[nw] = v1[nw] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row_ok && ww >= 0 && ww < W) {
+          const float4* src = row + static_cast<long long>(ww) * D * 2;
+          v0[nw] = __ldg(src);
+          v1[nw] = __ldg(src + 1);
+        }
+      }
+#pragma unroll
+      for (int oh = 0; oh < SQ_TH; ++oh) {
+        const int kh = nh - oh;
+        if (kh < 0 || kh > 2) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+          for (int kd = 0; kd < 3; ++kd) {
+            const float4 wa = c_squeeze[((kd * 3 + kh) * 3 + kw) * 2], wb = c_squeeze[((kd * 3 + kh) * 3 + kw) * 2 + 1];
+#pragma unroll
+            for (int ow = 0; ow < SQ_TW; ++ow) {
+              const int nw = ow + kw;
+              float a = acc[oh * SQ_TW + ow][kd];
+              a = fmaf(v0[nw].x, wa.x, a);
+              a = fmaf(v0[nw].y, wa.y, a);
+              a = fmaf(v0[nw].z, wa.z, a);
+              a = fmaf(v0[nw].w, wa.w, a);
+              a = fmaf(v1[nw].x, wb.x, a);
+              a = fmaf(v1[nw].y, wb.y, a);
+              a = fmaf(v1[nw].z, wb.z, a);
+              a = fmaf(v1[nw].w, wb.w, a);
+              acc[oh * SQ_TW + ow][kd] = a;
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < SQ_PX; ++p) {
+#pragma unroll
+      for (int kd = 0; kd < 3; ++kd) sq_part[(kd * SQ_PX + p) * Dp + dq + 1] = acc[p][kd];
+    }
+  }
+  if (threadIdx.x < 3 * SQ_PX) {
+    sq_part[threadIdx.x * Dp] = 0.f;
+    sq_part[threadIdx.x * Dp + D + 1] = 0.f;
+  }
+  __syncthreads();
+
+  const float bias = c_squeeze[54].x;
+  for (int p = warp; p < SQ_PX; p += n_warps) {
+    const int hh = h0 + p / SQ_TW, ww = w0 + p % SQ_TW;
+    if (hh >= H || ww >= W) continue;  // warp-uniform
+    const float* a0 = sq_part + (0 * SQ_PX + p) * Dp;
+    const float* a1 = sq_part + (1 * SQ_PX + p) * Dp;
+    const float* a2 = sq_part + (2 * SQ_PX + p) * Dp;
+    // out[d] = bias + A_0[d' = d - 1] + A_1[d' = d] + A_2[d' = d + 1]  (kd = 0 reads d - 1, ... as Conv3d does)
+    float mx = -FLT_MAX;
+    for (int d = lane; d < D; d += 32) {
+      const float c = ((bias + a0[d]) + a1[d + 1]) + a2[d + 2];
+      if (cost_out) cost_out[((static_cast<long long>(b) * D + d) * H + hh) * W + ww] = c;
+      mx = fmaxf(mx, c * LOG2E);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float s = 0.f, ws = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      const float c = ((bias + a0[d]) + a1[d + 1]) + a2[d + 2];
+      const float e = ex2_fast(fmaf(c, LOG2E, -mx));
+      s += e;
+      ws = fmaf(static_cast<float>(d), e, ws);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      ws += __shfl_xor_sync(0xffffffffu, ws, o);
+    }
+    if (lane == 0) out[(static_cast<long long>(b) * H + hh) * W + ww] = -(ws / s);
+  }
+}
+
 }  // namespace nnd
 
 extern "C" {
@@ -392,6 +520,37 @@ nnd_status nnd_gev_interleave_pool(const float* vol, int layout, int src_pitch, 
   NND_REQUIRE(blocks <= 0x7fffffffLL, "gev_interleave_pool: volume too large for one launch");
   gev_interleave_wmajor_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(vol, D, H, W1, w_groups, n_warp_items, lv);
   return check_launch("gev_interleave_wmajor_kernel");
+}
+
+nnd_status nnd_gev_squeeze_soft_argmin(const float* geo_level0, const float* weight, const float* bias, int B, int G,
+                                       int D, int H, int W1, float* out, float* cost_out, nnd_stream_t stream_) {
+  using namespace nnd;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  NND_REQUIRE(geo_level0 && weight && out, "gev_squeeze_soft_argmin: null pointer");
+  NND_REQUIRE(G == 8, "gev_squeeze_soft_argmin: the interleaved layout holds 8 groups (got %d)", G);
+  NND_REQUIRE(B > 0 && D > 0 && H > 0 && W1 > 0, "gev_squeeze_soft_argmin: B, D, H, W1 must be positive");
+  NND_REQUIRE(B <= 65535 && (H + SQ_TH - 1) / SQ_TH <= 65535, "gev_squeeze_soft_argmin: B or H exceeds the grid limit");
+  NND_REQUIRE(D <= 512, "gev_squeeze_soft_argmin: D = %d exceeds 512 (one thread per disparity plane)", D);
+  NND_REQUIRE(aligned16(geo_level0), "gev_squeeze_soft_argmin: volume must be 16-byte aligned");
+  // weights -> constant bank, stream-ordered (no host synchronisation; capturable).  Launches on different
+  // streams with DIFFERENT weights would race on the symbol; one model per process uses one squeezer.
+  squeeze_pack_kernel<<<1, 224, 0, stream>>>(weight, bias);
+  nnd_status ps = check_launch("squeeze_pack_kernel");
+  if (ps != NND_OK) return ps;
+  void* stage = nullptr;
+  cudaError_t e = cudaGetSymbolAddress(&stage, g_squeeze_stage);
+  if (e != cudaSuccess) return cuda_fail(e, "gev_squeeze_soft_argmin: staging symbol");
+  e = cudaMemcpyToSymbolAsync(c_squeeze, stage, 224 * sizeof(float), 0, cudaMemcpyDeviceToDevice, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "gev_squeeze_soft_argmin: weight upload");
+  const int threads = ((D + 31) / 32) * 32;
+  const size_t smem = static_cast<size_t>(3) * SQ_PX * (D + 2) * sizeof(float);
+  dim3 grid((W1 + SQ_TW - 1) / SQ_TW, (H + SQ_TH - 1) / SQ_TH, B);
+  if (threads <= 256) {
+    gev_squeeze_soft_argmin_kernel<256><<<grid, threads, smem, stream>>>(geo_level0, D, H, W1, out, cost_out);
+  } else {
+    gev_squeeze_soft_argmin_kernel<512><<<grid, threads, smem, stream>>>(geo_level0, D, H, W1, out, cost_out);
+  }
+  return check_launch("gev_squeeze_soft_argmin_kernel");
 }
 
 }  // extern "C"

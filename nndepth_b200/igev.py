@@ -167,6 +167,41 @@ class GeometryAwareCostVolume(nn.Module):
         self._build_feature_volume(f1, f2, pyr)
         return pyr.levels[0][:, :W2].reshape(B, self.num_groups, H, W1, W2)
 
+    def init_disparity(self, cv_squeezer, return_cost=False):
+        """``regress_disparity(softmax(cv_squeezer(geo).squeeze(1)), W)`` -> ``(B, 1, H, W1)`` in one kernel.
+
+        Fuses the ``nn.Conv3d(8, 1, 3, 1, 1)`` squeeze of the level-0 geometry volume with the soft-argmin
+        (igev_stereo/model.py:65, 143-146): the volume is read once instead of permute-copied, convolved,
+        soft-maxed and reduced.  ``cv_squeezer`` is the model's ``nn.Conv3d`` (weight ``(1, 8, 3, 3, 3)``).
+        ``return_cost=True`` also returns the squeezed ``(B, D, H, W1)`` cost (parity tests).
+        """
+        B, H, W1, D = self._shape
+        weight = _lib.as_cuda_f32(cv_squeezer.weight.detach(), "cv_squeezer.weight")
+        bias = None if cv_squeezer.bias is None else _lib.as_cuda_f32(cv_squeezer.bias.detach(), "cv_squeezer.bias")
+        if tuple(weight.shape) != (1, self.num_groups, 3, 3, 3):
+            raise RuntimeError(f"cv_squeezer.weight must be (1, {self.num_groups}, 3, 3, 3), got {tuple(weight.shape)}")
+        if tuple(cv_squeezer.padding) != (1, 1, 1) or tuple(cv_squeezer.stride) != (1, 1, 1) \
+                or tuple(cv_squeezer.dilation) != (1, 1, 1):
+            raise RuntimeError("cv_squeezer must be Conv3d(kernel 3, stride 1, padding 1, dilation 1)")
+        if not self._interleaved or D > 512:
+            # reference-layout volume: cuDNN Conv3d on the permuted view, then the fused soft-argmin kernel
+            geo = self.geo_aware_cv[0].reshape(B, self.num_groups, H, W1, D).permute(0, 1, 4, 2, 3)
+            cost = torch.nn.functional.conv3d(geo, weight, bias, 1, 1).squeeze(1).contiguous()
+            disp = soft_argmin(cost)
+            return (disp, cost) if return_cost else disp
+        out = torch.empty(B, 1, H, W1, dtype=torch.float32, device=weight.device)
+        cost = torch.empty(B, D, H, W1, dtype=torch.float32, device=weight.device) if return_cost else None
+        with torch.cuda.device(weight.device):
+            _lib.check(
+                _lib.load().nnd_gev_squeeze_soft_argmin(_lib.ptr(self._geo_il.levels[0]), _lib.ptr(weight),
+                                                        _lib.ptr(bias) if bias is not None else None, B,
+                                                        self.num_groups, D, H, W1, _lib.ptr(out),
+                                                        _lib.ptr(cost) if cost is not None else None,
+                                                        _lib.stream_ptr(weight)),
+                "nnd_gev_squeeze_soft_argmin",
+            )
+        return (out, cost) if return_cost else out
+
     def forward(self, coords):
         B, H, W1, _ = self._shape
         coords = _check_coords(coords, B, H, W1)

@@ -100,6 +100,34 @@ def soft_argmin(z, accumulate="f64"):
     return (-(d * e).sum(axis=1, keepdims=True) / e.sum(axis=1, keepdims=True)).astype(F32)
 
 
+def squeeze_cost(geo_level0, shape, weight, bias=None, accumulate="f64"):
+    """``cv_squeezer`` = ``nn.Conv3d(G, 1, 3, 1, 1)`` on the level-0 geometry volume as the model feeds it.
+
+    Reference: igev_stereo/model.py:65 (the layer) and :143-145 (``geo_aware_cv[0].reshape(B, G, H, W1, W2)
+    .permute(0, 1, 4, 2, 3)`` -> conv -> ``squeeze(1)``).  ``geo_level0`` is the ``(B*G*H*W1, W2)`` level;
+    ``shape = (B, G, H, W1, W2)``; ``weight`` ``(1, G, 3, 3, 3)`` over (d, h, w), zero padding.  -> ``(B, D, H, W1)``.
+    """
+    B, G, H, W1, W2 = (int(v) for v in shape)
+    acc_t = np.float64 if accumulate == "f64" else F32
+    x = np.asarray(geo_level0, dtype=F32).reshape(B, G, H, W1, W2).transpose(0, 1, 4, 2, 3).astype(acc_t)
+    w = np.asarray(weight, dtype=F32).reshape(G, 3, 3, 3).astype(acc_t)
+    xp = np.pad(x, ((0, 0), (0, 0), (1, 1), (1, 1), (1, 1)))
+    out = np.zeros((B, W2, H, W1), dtype=acc_t)
+    for kd in range(3):
+        for kh in range(3):
+            for kw in range(3):
+                win = xp[:, :, kd:kd + W2, kh:kh + H, kw:kw + W1]
+                out += np.einsum("bgdhw,g->bdhw", win, w[:, kd, kh, kw])
+    if bias is not None:
+        out += acc_t(np.asarray(bias, dtype=F32).reshape(-1)[0])
+    return out.astype(F32)
+
+
+def squeeze_soft_argmin(geo_level0, shape, weight, bias=None, accumulate="f64"):
+    """Initial disparity of IGEV-Stereo: ``regress_disparity(softmax(cv_squeezer(geo)))``, model.py:143-146."""
+    return soft_argmin(squeeze_cost(geo_level0, shape, weight, bias, accumulate), accumulate)
+
+
 class GeometryAwareCostVolume:
     """Oracle twin of igev_stereo/cost_volume.py:9-79.  ``regularizer_3d`` maps numpy -> numpy."""
 

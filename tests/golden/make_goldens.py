@@ -168,6 +168,26 @@ def igev_case():
     save("igev", **arrays)
 
 
+def igev_squeeze_case():
+    """cv_squeezer + softmax + regress_disparity exactly as IGEVStereoBase.forward runs them
+    (igev_stereo/model.py:65, 143-146) on the reference GeometryAwareCostVolume's geo_aware_cv[0]."""
+    gen = torch.Generator().manual_seed(37)
+    B, C, H, W, G = 2, 64, 5, 24, 8
+    f1 = torch.randn(B, C, H, W, generator=gen)
+    f2 = torch.randn(B, C, H, W, generator=gen)
+    feats = [torch.randn(B, 4, H, W, generator=gen)]
+    cv = GeometryAwareCostVolume(f1, f2, feats, toy_regularizer, 4, 4, G)
+    torch.manual_seed(38)
+    squeezer = torch.nn.Conv3d(G, 1, 3, 1, 1)
+    squeezer.weight.data.mul_(4.0)      # sharper softmax than the default init gives
+    geo = cv.geo_aware_cv[0].reshape(B, G, H, W, W).permute(0, 1, 4, 2, 3)
+    cost = squeezer(geo).squeeze(1)
+    dist = F.softmax(cost, dim=1)
+    disp = IGEVStereoBase.regress_disparity(None, dist, W)
+    save("igev_squeeze", geo_pyr0=cv.geo_aware_cv[0].reshape(-1, W), weight=squeezer.weight, bias=squeezer.bias,
+         cost=cost, disp=disp, shape=np.int64([B, G, H, W, W]))
+
+
 def agcl_case():
     gen = torch.Generator().manual_seed(41)
     N, C, H, W = 2, 32, 6, 10
@@ -242,6 +262,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "raft":
         raft_model_cases()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "igev_squeeze":
+        igev_squeeze_case()
+        sys.exit(0)
     sampler_kats()
     corr1d_case("corr1d_small", B=2, C=32, H=3, W=40, seed=11)
     corr1d_case("corr1d_odd", B=1, C=16, H=2, W=39, seed=12)
@@ -249,5 +272,6 @@ if __name__ == "__main__":
     corr1d_case("corr1d_r3l3", B=1, C=8, H=2, W=32, seed=14, levels=3, radius=3)
     group_corr_case()
     igev_case()
+    igev_squeeze_case()
     agcl_case()
     raft_model_cases()

@@ -171,3 +171,77 @@ def test_constructor_and_lookup_vs_oracle(shape, levels):
     np.testing.assert_array_equal(same(dev(coords)).cpu().numpy(), oi.gev_lookup(feat_pyr, geo_pyr, coords, levels, 4, G))
     got = cv(dev(coords)).cpu().numpy()
     np.testing.assert_allclose(got, oi.gev_lookup(feat_pyr, geo_pyr, coords, levels, 4, G), rtol=1e-4, atol=1e-4 * scale)
+
+
+def test_squeeze_soft_argmin_golden(golden):
+    """Fused cv_squeezer + soft-argmin against the reference model's own Conv3d / softmax / regress chain."""
+    import nndepth_b200 as nb
+    g = golden("igev_squeeze")
+    B, G, H, W1, W2 = (int(v) for v in g["shape"])
+    geo0 = g["geo_pyr0"]
+    pyr = oi.volume_pyramids(geo0.reshape(B, G, H, W1, W2), geo0.reshape(B, G, H, W1, W2).transpose(0, 1, 4, 2, 3), 4)[1]
+    cv = nb.GeometryAwareCostVolume.from_pyramids(pyr[:4], pyr[:4], B, H, 4, 4, G)
+    assert cv._interleaved
+    sq = torch.nn.Conv3d(G, 1, 3, 1, 1).cuda()
+    sq.weight.data.copy_(dev(g["weight"]))
+    sq.bias.data.copy_(dev(g["bias"]))
+    disp, cost = cv.init_disparity(sq, return_cost=True)
+    scale = np.abs(g["cost"]).max()
+    np.testing.assert_allclose(cost.cpu().numpy(), g["cost"], rtol=VOLUME_RTOL, atol=VOLUME_RTOL * scale)
+    np.testing.assert_allclose(disp.cpu().numpy(), g["disp"], rtol=0, atol=SOFTARGMIN_ATOL)
+    np.testing.assert_array_equal(cv.init_disparity(sq).cpu().numpy(), disp.cpu().numpy())
+
+
+@pytest.mark.parametrize("shape", [(1, 3, 5, 40), (2, 4, 12, 64), (1, 7, 9, 168), (1, 2, 6, 264), (3, 1, 1, 8)])
+def test_squeeze_soft_argmin_vs_oracle(shape):
+    """Through the C ABI on a hand-interleaved volume: ragged tiles in both directions (H odd, W1 % 4 != 0),
+    D not a multiple of 32, the 512-thread variant (D = 264), a single-pixel image, no bias (D = 64)."""
+    from nndepth_b200 import _lib
+    rng = np.random.default_rng(5)
+    B, H, W1, D = shape
+    G = 8
+    geo = rng.standard_normal((B, G, H, W1, D), dtype=np.float32)
+    weight = (rng.standard_normal((1, G, 3, 3, 3)) * 0.3).astype(np.float32)
+    bias = None if D == 64 else np.float32([0.37])
+    il = dev(geo.transpose(0, 2, 3, 4, 1))                     # [b][h][w1][d][g]
+    w_d = dev(weight)
+    b_d = dev(bias) if bias is not None else None
+    disp = torch.empty(B, 1, H, W1, device="cuda")
+    cost = torch.empty(B, D, H, W1, device="cuda")
+    _lib.check(_lib.load().nnd_gev_squeeze_soft_argmin(_lib.ptr(il), _lib.ptr(w_d), _lib.ptr(b_d) if bias is not None else None,
+                                                       B, G, D, H, W1, _lib.ptr(disp), _lib.ptr(cost), _lib.stream_ptr(il)),
+               "nnd_gev_squeeze_soft_argmin")
+    ref_cost = oi.squeeze_cost(geo.reshape(-1, D), (B, G, H, W1, D), weight, bias)
+    scale = np.abs(ref_cost).max()
+    np.testing.assert_allclose(cost.cpu().numpy(), ref_cost, rtol=VOLUME_RTOL, atol=VOLUME_RTOL * scale)
+    ref = oi.squeeze_soft_argmin(geo.reshape(-1, D), (B, G, H, W1, D), weight, bias)
+    np.testing.assert_allclose(disp.cpu().numpy(), ref, rtol=0, atol=SOFTARGMIN_ATOL * max(1.0, D / 160))
+
+
+def test_squeeze_soft_argmin_reference_layout_fallback():
+    """W2 % 8 != 0 keeps the reference row layout: cuDNN Conv3d + the soft-argmin kernel, same result."""
+    import nndepth_b200 as nb
+    rng = np.random.default_rng(6)
+    B, G, H, W1, D = 1, 8, 3, 8, 20
+    geo = rng.standard_normal((B, G, H, W1, D), dtype=np.float32)
+    weight = (rng.standard_normal((1, G, 3, 3, 3)) * 0.3).astype(np.float32)
+    pyr = oi.volume_pyramids(geo, geo.transpose(0, 1, 4, 2, 3), 2)[1]
+    cv = nb.GeometryAwareCostVolume.from_pyramids(pyr[:2], pyr[:2], B, H, 2, 4, G)
+    assert not cv._interleaved
+    sq = torch.nn.Conv3d(G, 1, 3, 1, 1).cuda()
+    sq.weight.data.copy_(dev(weight))
+    with torch.backends.cudnn.flags(allow_tf32=False):
+        disp = cv.init_disparity(sq)
+    ref = oi.squeeze_soft_argmin(pyr[0], (B, G, H, W1, D), weight, sq.bias.detach().cpu().numpy())
+    np.testing.assert_allclose(disp.cpu().numpy(), ref, rtol=0, atol=SOFTARGMIN_ATOL)
+
+
+def test_squeeze_rejects_other_convolutions():
+    import nndepth_b200 as nb
+    geo = np.zeros((1, 8, 2, 8, 16), dtype=np.float32)
+    pyr = oi.volume_pyramids(geo, geo.transpose(0, 1, 4, 2, 3), 1)[1]
+    cv = nb.GeometryAwareCostVolume.from_pyramids(pyr[:1], pyr[:1], 1, 2, 1, 4, 8)
+    with pytest.raises(RuntimeError):
+        cv.init_disparity(torch.nn.Conv3d(8, 2, 3, 1, 1).cuda())
+    with pytest.raises(RuntimeError):
+        cv.init_disparity(torch.nn.Conv3d(8, 1, 3, 1, 0).cuda())

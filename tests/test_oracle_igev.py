@@ -48,3 +48,18 @@ def test_soft_argmin(golden):
     np.testing.assert_allclose(fused, g["sa_disp"], rtol=1e-5, atol=1e-5)
     assert fused[0, 0, 0, 1] == -5.0                     # one-hot row
     np.testing.assert_allclose(fused[0, 0, 0, 0], -11.5, rtol=1e-6)   # uniform row: mean of 0..23
+
+
+def test_squeeze_soft_argmin(golden):
+    """cv_squeezer (Conv3d) + softmax + regress_disparity against the reference model's own op chain."""
+    g = golden("igev_squeeze")
+    cost = oi.squeeze_cost(g["geo_pyr0"], g["shape"], g["weight"], g["bias"])
+    assert cost.shape == g["cost"].shape
+    np.testing.assert_allclose(cost, g["cost"], rtol=1e-5, atol=1e-5 * np.abs(g["cost"]).max())
+    disp = oi.squeeze_soft_argmin(g["geo_pyr0"], g["shape"], g["weight"], g["bias"])
+    np.testing.assert_allclose(disp, g["disp"], rtol=1e-4, atol=1e-4)
+    # the padding is zero padding: a constant volume gives smaller sums on the faces than inside
+    B, G, H, W1, W2 = (int(v) for v in g["shape"])
+    ones = np.ones((B * G * H * W1, W2), dtype=np.float32)
+    c1 = oi.squeeze_cost(ones, g["shape"], np.ones((1, G, 3, 3, 3), np.float32))
+    assert c1[0, 1, 1, 1] == 27 * G and c1[0, 0, 0, 0] == 8 * G and c1[0, 0, 1, 1] == 18 * G
