@@ -216,6 +216,19 @@ nnd_status nnd_agcl_iter_nhwc(const float* fmap1_nhwc, const float* fmap2_nhwc, 
 nnd_status nnd_convex_upsample(const float* flow, const float* mask, const float* mask_bias, int N, int H, int W,
                                int rate, float mask_scale, int mask_channels_last, float* out, nnd_stream_t stream);
 
+/* Single-flow-channel convolutions of the update block (stereo: flow_channel = 1), fp32 FFMA.
+ *   nnd_flow_conv7x7_relu: relu(convf1(flow)), BasicMotionEncoder blocks/update_block.py:53,60.
+ *     flow (N,1,H,W); weight (c_out,1,7,7); bias (c_out); out channels-last (N,H,W,c_out); padding 3.
+ *   nnd_flow_head_tail: FlowHead.conv2 blocks/update_block.py:23,36 on a channels-last x (N,H,W,C), C in
+ *     {256, 512}; weight (1,C,3,3); bias 1 float or NULL; delta (N,1,H,W) or NULL.  With coords_in the
+ *     refinement-loop update raft_stereo/model.py:132-134 is fused: coords_out = coords_in + delta and, if
+ *     flow_out, flow_out = coords_out - org (all (N,1,H,W); coords_out may alias coords_in). */
+nnd_status nnd_flow_conv7x7_relu(const float* flow, const float* weight, const float* bias, int N, int H, int W,
+                                 int c_out, float* out, nnd_stream_t stream);
+nnd_status nnd_flow_head_tail(const float* x, const float* weight, const float* bias, int N, int C, int H, int W,
+                              float* delta, const float* coords_in, const float* org, float* coords_out,
+                              float* flow_out, nnd_stream_t stream);
+
 /* Fused, channels-last glue of the separable ConvGRU (nndepth/blocks/gru.py:5-37) around its weight-split
  * TF32 convolutions: conv([RN_tf32(x) ; RN_tf32(x)], [w_hi ; w_lo]) -- fp32-exact weights on the tensor cores;
  * plain TF32 weights leave the 0.01 px parity bar.  One staging buffer S (N, H*W, ctot), rows

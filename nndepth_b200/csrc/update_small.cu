@@ -1,0 +1,203 @@
+// The two single-flow-channel convolutions of the RAFT-Stereo update block (sm_100a).  With one flow channel
+// (stereo) neither is GEMM-shaped: cuDNN pads the channel to its tile width, runs a tensor-core kernel that is
+// >97 % padding and converts layouts around it (3 + 49 + 6 us and 42 us per iteration at KITTI shapes).
+//
+//   nnd_flow_conv7x7_relu   relu(convf1(flow)):  (N,1,H,W) -> channels-last (N,H,W,Cout), 7x7, padding 3
+//                           reference blocks/update_block.py:53,60
+//   nnd_flow_head_tail      FlowHead.conv2 (3x3, C -> 1) on a channels-last map, fused with the coordinate update
+//                           of the refinement loop: delta = conv2(x); coords += delta; flow = coords - org
+//                           reference blocks/update_block.py:23,36 and raft_stereo/model.py:132-134
+//
+// Both accumulate in fp32 FFMA (cuDNN's TF32 kernels would round the operands; the reference is fp32).
+#include "common.cuh"
+
+namespace nnd {
+
+constexpr int F7_PX = 8;  // consecutive x positions per thread (share every weight load)
+
+// block = (Cout/4 lanes-of-4-channels, rows of 8-pixel strips); weights [tap][Cout] in shared memory
+__global__ void __launch_bounds__(256)
+flow_conv7x7_relu_kernel(const float* __restrict__ flow, const float* __restrict__ weight, const float* __restrict__ bias,
+                         int H, int W, int cout, long long n_strips, int strips_per_row, float* __restrict__ out) {
+  extern __shared__ float4 w_sm[];  // [49][cout / 4]
+  const int c4n = cout >> 2;
+  for (int i = threadIdx.x; i < 49 * c4n; i += blockDim.x) {
+    const int tap = i / c4n, c4 = i - tap * c4n;
+    // weight (Cout, 1, 7, 7): element (c, tap)
+    w_sm[i] = make_float4(__ldg(weight + (4 * c4 + 0) * 49 + tap), __ldg(weight + (4 * c4 + 1) * 49 + tap),
+                          __ldg(weight + (4 * c4 + 2) * 49 + tap), __ldg(weight + (4 * c4 + 3) * 49 + tap));
+  }
+  __syncthreads();
+  const int c4 = threadIdx.x % c4n;
+  const int sub = threadIdx.x / c4n, subs = blockDim.x / c4n;
+  const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+  for (long long s = static_cast<long long>(blockIdx.x) * subs + sub; s < n_strips;
+       s += static_cast<long long>(gridDim.x) * subs) {
+    const long long row = s / strips_per_row;  // n * H + y
+    const int x0 = static_cast<int>(s - row * strips_per_row) * F7_PX;
+    const int y = static_cast<int>(row % H);
+    const float* img = flow + (row - y) * W;   // image n
+    float4 acc[F7_PX];
+#pragma unroll
+    for (int p = 0; p < F7_PX; ++p) acc[p] = b4;
+#pragma unroll
+    for (int ky = 0; ky < 7; ++ky) {
+      const int yy = y + ky - 3;
+      if (yy < 0 || yy >= H) continue;
+      float f[F7_PX + 6];
+#pragma unroll
+      for (int i = 0; i < F7_PX + 6; ++i) {
+        const int xx = x0 + i - 3;
+        f[i] = (xx >= 0 && xx < W) ? __ldg(img + static_cast<long long>(yy) * W + xx) : 0.f;
+      }
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) {
+        const float4 w4 = w_sm[(ky * 7 + kx) * c4n + c4];
+#pragma unroll
+        for (int p = 0; p < F7_PX; ++p) {
+          acc[p].x = fmaf(w4.x, f[p + kx], acc[p].x);
+          acc[p].y = fmaf(w4.y, f[p + kx], acc[p].y);
+          acc[p].z = fmaf(w4.z, f[p + kx], acc[p].z);
+          acc[p].w = fmaf(w4.w, f[p + kx], acc[p].w);
+        }
+      }
+    }
+    float4* dst = reinterpret_cast<float4*>(out) + (row * W + x0) * c4n + c4;
+#pragma unroll
+    for (int p = 0; p < F7_PX; ++p) {
+      if (x0 + p < W) {
+        dst[static_cast<long long>(p) * c4n] = make_float4(fmaxf(acc[p].x, 0.f), fmaxf(acc[p].y, 0.f),
+                                                           fmaxf(acc[p].z, 0.f), fmaxf(acc[p].w, 0.f));
+      }
+    }
+  }
+}
+
+constexpr int FH_PX = 8;  // output pixels per warp (a strip along x); lane = 8 channels per 256-channel slab
+
+// x (N,H,W,C) channels-last, C % 256 == 0 handled in slabs of 256 (lane owns channels slab*256 + 8*lane .. +7).
+// weight (1, C, 3, 3).  One warp per strip of FH_PX output pixels: 3 x (FH_PX + 2) input pixels are read once each.
+template <int SLABS>
+__global__ void __launch_bounds__(256)
+flow_head_tail_kernel(const float* __restrict__ x, const float* __restrict__ weight, const float* __restrict__ bias,
+                      int H, int W, long long n_strips, int strips_per_row, float* __restrict__ delta,
+                      const float* __restrict__ coords_in, const float* __restrict__ org, float* __restrict__ coords_out,
+                      float* __restrict__ flow_out) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  constexpr int C = SLABS * 256;
+  // this lane's 8 * SLABS channels x 9 taps
+  float w[SLABS][9][8];
+#pragma unroll
+  for (int sl = 0; sl < SLABS; ++sl)
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[sl][t][j] = __ldg(weight + (sl * 256 + lane * 8 + j) * 9 + t);
+  const float b = bias ? __ldg(bias) : 0.f;
+  for (long long s = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); s < n_strips;
+       s += static_cast<long long>(gridDim.x) * warps_per_block) {
+    const long long row = s / strips_per_row;  // n * H + y
+    const int x0 = static_cast<int>(s - row * strips_per_row) * FH_PX;
+    const int y = static_cast<int>(row % H);
+    float acc[FH_PX];
+#pragma unroll
+    for (int p = 0; p < FH_PX; ++p) acc[p] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y + ky - 1;
+      if (yy < 0 || yy >= H) continue;  // warp-uniform
+      const float* line = x + ((row - y + yy) * W) * C;
+#pragma unroll
+      for (int i = 0; i < FH_PX + 2; ++i) {
+        const int xx = x0 + i - 1;
+        if (xx < 0 || xx >= W) continue;  // warp-uniform
+#pragma unroll
+        for (int sl = 0; sl < SLABS; ++sl) {
+          const float4* src = reinterpret_cast<const float4*>(line + static_cast<long long>(xx) * C + sl * 256 + lane * 8);
+          const float4 a = __ldg(src), c = __ldg(src + 1);
+          const float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const int p = i - kx;  // output pixel that sees input i through tap kx
+            if (p < 0 || p >= FH_PX) continue;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[p] = fmaf(v[j], w[sl][ky * 3 + kx][j], acc[p]);
+          }
+        }
+      }
+    }
+    // 8 butterfly reductions; lane p keeps pixel p
+    float mine = 0.f;
+#pragma unroll
+    for (int p = 0; p < FH_PX; ++p) {
+      float v = acc[p];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == p) mine = v;
+    }
+    if (lane < FH_PX && x0 + lane < W) {
+      const long long idx = row * W + x0 + lane;
+      const float d = mine + b;
+      if (delta) delta[idx] = d;
+      if (coords_in) {
+        const float c1 = coords_in[idx] + d;
+        coords_out[idx] = c1;
+        if (flow_out) flow_out[idx] = c1 - org[idx];
+      }
+    }
+  }
+}
+
+}  // namespace nnd
+
+extern "C" {
+
+nnd_status nnd_flow_conv7x7_relu(const float* flow, const float* weight, const float* bias, int N, int H, int W,
+                                 int c_out, float* out, nnd_stream_t stream) {
+  using namespace nnd;
+  NND_REQUIRE(flow && weight && bias && out, "flow_conv7x7_relu: null pointer");
+  NND_REQUIRE(N > 0 && H > 0 && W > 0, "flow_conv7x7_relu: N, H, W must be positive");
+  NND_REQUIRE(c_out > 0 && c_out % 4 == 0 && c_out <= 1024 && 256 % (c_out / 4) == 0,
+              "flow_conv7x7_relu: c_out = %d must be a multiple of 4 with c_out/4 dividing 256", c_out);
+  NND_REQUIRE(aligned16(out) && aligned16(bias), "flow_conv7x7_relu: out and bias must be 16-byte aligned");
+  const int strips_per_row = (W + F7_PX - 1) / F7_PX;
+  const long long n_strips = static_cast<long long>(N) * H * strips_per_row;
+  const int subs = 256 / (c_out / 4);
+  const long long want = (n_strips + subs - 1) / subs;
+  const long long cap = static_cast<long long>(sm_count()) * 8;
+  const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
+  const size_t smem = static_cast<size_t>(49) * c_out * sizeof(float);
+  flow_conv7x7_relu_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(flow, weight, bias, H, W, c_out,
+                                                                                        n_strips, strips_per_row, out);
+  return check_launch("flow_conv7x7_relu_kernel");
+}
+
+nnd_status nnd_flow_head_tail(const float* x, const float* weight, const float* bias, int N, int C, int H, int W,
+                              float* delta, const float* coords_in, const float* org, float* coords_out,
+                              float* flow_out, nnd_stream_t stream) {
+  using namespace nnd;
+  NND_REQUIRE(x && weight, "flow_head_tail: null pointer");
+  NND_REQUIRE(N > 0 && H > 0 && W > 0, "flow_head_tail: N, H, W must be positive");
+  NND_REQUIRE(C == 256 || C == 512, "flow_head_tail: C = %d (supported: 256, 512)", C);
+  NND_REQUIRE(aligned16(x), "flow_head_tail: x must be 16-byte aligned");
+  NND_REQUIRE(delta || coords_in, "flow_head_tail: nothing to write (delta and coords_in are both null)");
+  NND_REQUIRE(!coords_in || coords_out, "flow_head_tail: coords_in needs coords_out");
+  NND_REQUIRE(!flow_out || (coords_in && org), "flow_head_tail: flow_out needs coords_in and org");
+  const int strips_per_row = (W + FH_PX - 1) / FH_PX;
+  const long long n_strips = static_cast<long long>(N) * H * strips_per_row;
+  const long long want = (n_strips + 7) / 8;
+  const long long cap = static_cast<long long>(sm_count()) * 4;
+  const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (C == 256) {
+    flow_head_tail_kernel<1><<<grid, 256, 0, st>>>(x, weight, bias, H, W, n_strips, strips_per_row, delta, coords_in, org,
+                                                   coords_out, flow_out);
+  } else {
+    flow_head_tail_kernel<2><<<grid, 256, 0, st>>>(x, weight, bias, H, W, n_strips, strips_per_row, delta, coords_in, org,
+                                                   coords_out, flow_out);
+  }
+  return check_launch("flow_head_tail_kernel");
+}
+
+}  // extern "C"

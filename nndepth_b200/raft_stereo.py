@@ -77,6 +77,66 @@ def conv_plain(conv, x):
     return conv(x)
 
 
+def _is_nhwc(t):
+    return t.dim() == 4 and t.permute(0, 2, 3, 1).is_contiguous()
+
+
+def _small_kernels_ok(t):
+    return t.is_cuda and t.dtype == torch.float32 and not torch.is_grad_enabled()
+
+
+def flow_conv7x7_relu(conv, flow):
+    """``relu(conv(flow))`` for the one-channel 7x7 ``convf1`` (reference blocks/update_block.py:53,60) as one fp32
+    kernel writing channels-last; anything else goes to cuDNN."""
+    if not (_small_kernels_ok(flow) and flow.shape[1] == 1 and conv.kernel_size == (7, 7) and conv.padding == (3, 3)
+            and conv.stride == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1 and conv.bias is not None
+            and conv.out_channels % 4 == 0 and 256 % (conv.out_channels // 4) == 0):
+        return conv_relu(conv, flow)
+    from . import _lib
+    N, _, H, W = flow.shape
+    flow = flow.contiguous()
+    weight = conv.weight.detach().contiguous()       # (Cout,1,7,7): dense in either memory format
+    out = torch.empty(N, H, W, conv.out_channels, dtype=torch.float32, device=flow.device)
+    with torch.cuda.device(flow.device):
+        _lib.check(_lib.load().nnd_flow_conv7x7_relu(_lib.ptr(flow), _lib.ptr(weight), _lib.ptr(conv.bias.detach()), N, H, W,
+                                                     conv.out_channels, _lib.ptr(out), _lib.stream_ptr(flow)),
+                   "nnd_flow_conv7x7_relu")
+    return out.permute(0, 3, 1, 2)
+
+
+def flow_head_tail(conv, x, coords=None, org=None):
+    """``conv(x)`` for the flow head's 3x3 ``C -> 1`` convolution (reference blocks/update_block.py:23,36) on a
+    channels-last ``x``, as one fp32 kernel.  With ``coords`` / ``org`` it also performs the loop's update
+    (raft_stereo/model.py:132-134) and returns ``(coords + delta, coords + delta - org)``; otherwise ``delta``.
+    Returns ``None`` when the shape is not the kernel's (the caller then uses cuDNN)."""
+    if not (_small_kernels_ok(x) and conv.out_channels == 1 and conv.in_channels in (256, 512) and _is_nhwc(x)
+            and conv.kernel_size == (3, 3) and conv.padding == (1, 1) and conv.stride == (1, 1)
+            and conv.dilation == (1, 1) and conv.groups == 1):
+        return None
+    from . import _lib
+    N, C, H, W = x.shape
+    cache = getattr(conv, "_nchw_weight", None)
+    if cache is None or cache[0] != conv.weight._version or cache[1].device != x.device:
+        cache = (conv.weight._version, conv.weight.detach().contiguous(memory_format=torch.contiguous_format).clone())
+        conv._nchw_weight = cache
+    weight = cache[1]
+    bias = None if conv.bias is None else conv.bias.detach()
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        if coords is None:
+            delta = torch.empty(N, 1, H, W, dtype=torch.float32, device=x.device)
+            _lib.check(lib.nnd_flow_head_tail(_lib.ptr(x), _lib.ptr(weight), _lib.ptr(bias) if bias is not None else None, N, C,
+                                              H, W, _lib.ptr(delta), None, None, None, None, _lib.stream_ptr(x)),
+                       "nnd_flow_head_tail")
+            return delta
+        coords, org = coords.contiguous(), org.contiguous()
+        new_coords, new_flow = torch.empty_like(coords), torch.empty_like(coords)
+        _lib.check(lib.nnd_flow_head_tail(_lib.ptr(x), _lib.ptr(weight), _lib.ptr(bias) if bias is not None else None, N, C, H,
+                                          W, None, _lib.ptr(coords), _lib.ptr(org), _lib.ptr(new_coords), _lib.ptr(new_flow),
+                                          _lib.stream_ptr(x)), "nnd_flow_head_tail")
+    return new_coords, new_flow
+
+
 def fold_bn(conv, bn, tf32=False):
     """Weights and bias of ``bn(conv(x))`` as ONE convolution (eval-mode BatchNorm is affine per channel).
 
@@ -311,12 +371,17 @@ class FusedGRURun:
             lib.check(lib.load().nnd_gru_stage(lib.ptr(src), 1 if cl else 0, N, C, self.H * self.W, lib.ptr(self.S), self.ctot,
                                                off, lib.stream_ptr(src)), "nnd_gru_stage")
 
-    def step(self, motion):
-        """One GRU update with ``x = cat[inp, motion]``; returns the new hidden state (channels-last view)."""
+    def step(self, motion, flow=None):
+        """One GRU update with ``x = cat[inp, motion]``; returns the new hidden state (channels-last view).
+
+        With ``flow`` given, the last ``flow.shape[1]`` channels of ``motion`` are placeholders and the flow is
+        staged over them (``motion = cat[features, flow]`` of the reference, update_block.py:65, without the cat)."""
         lib = self._lib
         if motion.shape[1] != self.cx - self.c_inp:
             raise RuntimeError(f"motion features must have {self.cx - self.c_inp} channels, got {motion.shape[1]}")
         self._stage(motion, self.ch + self.c_inp)
+        if flow is not None:
+            self._stage(flow, self.ch + self.cx - flow.shape[1])
         pixels = self.N * self.H * self.W
         cl = torch.channels_last
         with cudnn_tf32(True), torch.cuda.device(self.S.device):
@@ -343,15 +408,37 @@ class BasicMotionEncoder(nn.Module):
         self.conv = nn.Conv2d(64 + 192, hidden_dim - flow_channel, 3, padding=1)
         self.channels_last = False      # set by the engine together with channels-last weights
 
-    def forward(self, flow, corr, cor1=None):
+    def forward(self, flow, corr, cor1=None, split_flow=False):
         """``cor1``: ``relu(convc1(corr))`` already computed by the fused lookup kernel (then ``corr`` is unused)."""
         if cor1 is not None and self.channels_last:
             # the rest of the encoder then stays channels-last: cuDNN's tensor-core kernels need no layout conversion
             cor1 = cor1.contiguous(memory_format=torch.channels_last)
         cor = conv_relu(self.convc2, cor1 if cor1 is not None else conv_relu(self.convc1, corr))
-        flo = conv_relu(self.convf2, conv_relu(self.convf1, flow))
-        out = conv_relu(self.conv, torch.cat([cor, flo], dim=1))
+        flo = conv_relu(self.convf2, flow_conv7x7_relu(self.convf1, flow) if self.channels_last
+                        else conv_relu(self.convf1, flow))
+        x = torch.cat([cor, flo], dim=1)
+        if split_flow:
+            # (motion features with one zero channel appended, flow): the caller writes the flow into that channel
+            # of its staging buffer itself, so neither cuDNN's padding of the odd channel count (127) nor the
+            # concatenation pass over the result is needed.  Same arithmetic: the extra filter is all zeros.
+            w, b = self._padded_conv()
+            return torch.cudnn_convolution_relu(x, w, b, self.conv.stride, self.conv.padding, self.conv.dilation, 1), flow
+        out = conv_relu(self.conv, x)
         return torch.cat([out, flow], dim=1)
+
+    def _padded_conv(self):
+        """``self.conv`` with zero filters appended up to ``hidden_dim`` output channels (cached per weight version)."""
+        conv = self.conv
+        key = (conv.weight._version, conv.bias._version, conv.weight.device, torch.backends.cudnn.allow_tf32)
+        cache = getattr(self, "_pad_cache", None)
+        if cache is None or cache[0] != key:
+            w = inference_weight(conv).detach()
+            extra = self.convf1.weight.shape[1]          # the flow channels the reference concatenates
+            w = torch.cat([w, w.new_zeros(extra, *w.shape[1:])], 0).contiguous(memory_format=torch.channels_last)
+            b = torch.cat([conv.bias.detach(), conv.bias.new_zeros(extra)], 0).contiguous()
+            cache = (key, (w, b))
+            self._pad_cache = cache
+        return cache[1]
 
 
 class FlowHead(nn.Module):
@@ -361,8 +448,14 @@ class FlowHead(nn.Module):
         self.conv2 = nn.Conv2d(hidden_dim, flow_channel, 3, padding=1)
         self.relu = nn.ReLU(inplace=True)
 
-    def forward(self, x):
-        return conv_plain(self.conv2, conv_relu(self.conv1, x))
+    def forward(self, x, coords=None, org=None):
+        """``delta``; with ``coords`` / ``org`` and the fused tail available: ``(coords + delta, coords + delta - org)``."""
+        hidden = conv_relu(self.conv1, x)
+        fused = flow_head_tail(self.conv2, hidden, coords, org)
+        if fused is not None:
+            return fused
+        delta = conv_plain(self.conv2, hidden)
+        return delta if coords is None else (coords + delta, coords + delta - org)
 
 
 class BasicUpdateBlock(nn.Module):
@@ -379,14 +472,18 @@ class BasicUpdateBlock(nn.Module):
         self.mask = nn.Sequential(nn.Conv2d(hidden_dim, hidden_dim * 2, 3, padding=1), nn.ReLU(inplace=True),
                                   nn.Conv2d(hidden_dim * 2, sps * 9, 1))
 
-    def forward(self, net, inp, corr, flow, raw_mask=False, cor1=None, gru_run=None):
+    def forward(self, net, inp, corr, flow, raw_mask=False, cor1=None, gru_run=None, coords=None, org=None):
         """``raw_mask=True`` returns the mask logits without the last convolution's bias and without the reference's
         ``0.25 *`` (update_block.py:110): the fused upsampling kernel applies both, saving two passes over the
-        (N,576,H,W) tensor."""
-        motion = self.encoder(flow, corr, cor1=cor1)
+        (N,576,H,W) tensor.  With ``coords`` / ``org`` the third result is ``(coords + delta, coords + delta - org)``
+        (the loop's update, fused into the flow head's last convolution) instead of ``delta``."""
         if gru_run is not None:
-            net = gru_run.step(motion)          # fused channels-last weight-split recurrence; `net` lives in the runner
+            split = flow.is_cuda and not torch.is_grad_enabled() and hasattr(torch, "cudnn_convolution_relu")
+            motion = self.encoder(flow, corr, cor1=cor1, split_flow=split)
+            # fused channels-last weight-split recurrence; `net` lives in the runner
+            net = gru_run.step(*motion) if split else gru_run.step(motion)
         else:
+            motion = self.encoder(flow, corr, cor1=cor1)
             net = self.gru(net, torch.cat((inp, motion), dim=1))
         hidden = conv_relu(self.mask[0], net)
         if raw_mask:
@@ -395,7 +492,7 @@ class BasicUpdateBlock(nn.Module):
             mask = F.conv2d(hidden, inference_weight(last), None, last.stride, last.padding)
         else:
             mask = 0.25 * conv_plain(self.mask[2], hidden)
-        return net, mask, self.flow_head(net)
+        return net, mask, self.flow_head(net, coords, org)
 
 
 def convex_upsample(flow, mask, rate=8):
@@ -513,15 +610,22 @@ class RAFTStereo(nn.Module):
             # shuffle, with the update block's 0.25 mask scale folded in); the torch chain below is the
             # reference's own, kept for the CPU baseline leg (corr_fn = oracle) only
             fused = coords1.is_cuda and fnet_ds in (2, 4, 8) and not torch.is_grad_enabled()
-            net, mask, delta = self.update_block(net, inp, sampled, coords1 - org_coords, raw_mask=fused, cor1=cor1,
-                                                 gru_run=gru_run)
-            coords1 = coords1 + delta
+            if it == 0:
+                flow = coords1 - org_coords
+            if fused:
+                # the flow head's last convolution also writes the new coordinates and the new flow
+                net, mask, (coords1, flow) = self.update_block(net, inp, sampled, flow, raw_mask=True, cor1=cor1,
+                                                               gru_run=gru_run, coords=coords1, org=org_coords)
+            else:
+                net, mask, delta = self.update_block(net, inp, sampled, flow, raw_mask=False, cor1=cor1, gru_run=gru_run)
+                coords1 = coords1 + delta
+                flow = coords1 - org_coords
             if not self.final_only or it == self.iters - 1:
                 if fused:
-                    up = fused_convex_upsample(coords1 - org_coords, mask, rate=fnet_ds, mask_scale=0.25,
+                    up = fused_convex_upsample(flow, mask, rate=fnet_ds, mask_scale=0.25,
                                                mask_bias=self.update_block.mask[2].bias)
                 else:
-                    up = self.convex_upsample(coords1 - org_coords, mask, rate=fnet_ds)
+                    up = self.convex_upsample(flow, mask, rate=fnet_ds)
                 outputs.append({"up_disp": up})
         return outputs
 

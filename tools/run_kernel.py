@@ -33,6 +33,17 @@ elif what in ("igev_lookup", "igev_build", "igev_geo"):
             cv._build_feature_volume(f1, f2, cv._feat)
         else:
             nb.GeometryAwareCostVolume(f1, f2, [], lambda vol, feats: vol, 4, 4, G)
+elif what == "squeeze":
+    B, H, W, G = 16, 120, 160, 8
+    from nndepth_b200.igev import InterleavedPyramid
+    cv = nb.GeometryAwareCostVolume.__new__(nb.GeometryAwareCostVolume)
+    torch.nn.Module.__init__(cv)
+    cv.num_groups, cv.num_levels, cv.radius, cv._shape, cv._interleaved = G, 1, 4, (B, H, W, W), True
+    cv._geo_il = InterleavedPyramid(B * H * W, W, 1, torch.device("cuda"))
+    cv._geo_il.levels[0].normal_()
+    sq = torch.nn.Conv3d(G, 1, 3, 1, 1).cuda()
+    for _ in range(reps):
+        cv.init_disparity(sq)
 elif what in ("raft_lookup", "raft_build"):
     B, C, H, W = 8, 256, 48, 156
     f1 = torch.randn(B, C, H, W, device="cuda"); f2 = torch.randn(B, C, H, W, device="cuda")
