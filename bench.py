@@ -417,8 +417,10 @@ def run_ours(args):
                 nb.get_volume_precision(), {"fp32": "cuDNN fp32", "tf32": "cuDNN TF32",
                                             "mixed": "ConvGRU cuDNN fp32, other convolutions cuDNN TF32",
                                             "mixed2x": "ConvGRU TF32 activations x split fp32 weights [w_hi; w_lo] on tensor cores, "
-                                                       "other convolutions cuDNN TF32"}[args.dense_precision]),
-            "parity": {"final_epe_px_vs_reference": {"fp32": 0.00016, "mixed": 0.0021, "mixed2x": 0.0031, "tf32": 0.0147}[args.dense_precision],
+                                                       "other convolutions cuDNN TF32",
+                                            "mixed16": "ConvGRU fp16 activations x split weights [w_hi16; w_lo16] on tensor cores "
+                                                       "(fp32 accumulate, fp32 gates and state), other convolutions cuDNN TF32"}[args.dense_precision]),
+            "parity": {"final_epe_px_vs_reference": {"fp32": 0.00016, "mixed": 0.0021, "mixed2x": 0.0031, "mixed16": 0.0031, "tf32": 0.0147}[args.dense_precision],
                        "bar_px": 0.01, "source": "tests/test_gpu_raft_model.py::test_kitti_32_iterations, tools/exp_epe_modules.py"},
             "data": "synthetic", "config": workload_config(world), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT,
@@ -465,7 +467,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--volume-precision", default=None, choices=["fp32", "tf32"])
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--dense-precision", default="mixed2x", choices=["fp32", "mixed", "mixed2x", "tf32"],
+    ap.add_argument("--dense-precision", default="mixed16", choices=["fp32", "mixed", "mixed2x", "mixed16", "tf32"],
                     help="cuDNN layers: fp32 everywhere (0.0002 px EPE); ConvGRU fp32 + TF32 elsewhere (0.0021 px); "
                          "ConvGRU with split fp32 weights on tensor cores + TF32 elsewhere (default, 0.0031 px); TF32 everywhere "
                          "(0.0147 px: outside the 0.01 px bar)")

@@ -218,12 +218,13 @@ nnd_status nnd_convex_upsample(const float* flow, const float* mask, const float
 
 /* Single-flow-channel convolutions of the update block (stereo: flow_channel = 1), fp32 FFMA.
  *   nnd_flow_conv7x7_relu: relu(convf1(flow)), BasicMotionEncoder blocks/update_block.py:53,60.
- *     flow (N,1,H,W); weight (c_out,1,7,7); bias (c_out); out channels-last (N,H,W,c_out); padding 3.
+ *     flow (N,1,H,W); weight_t (49, c_out) = the (c_out,1,7,7) filter bank transposed (tap-major); bias (c_out);
+ *     out channels-last (N,H,W,c_out); padding 3.
  *   nnd_flow_head_tail: FlowHead.conv2 blocks/update_block.py:23,36 on a channels-last x (N,H,W,C), C in
- *     {256, 512}; weight (1,C,3,3); bias 1 float or NULL; delta (N,1,H,W) or NULL.  With coords_in the
+ *     {128, 256, 512}; weight (1,C,3,3); bias 1 float or NULL; delta (N,1,H,W) or NULL.  With coords_in the
  *     refinement-loop update raft_stereo/model.py:132-134 is fused: coords_out = coords_in + delta and, if
  *     flow_out, flow_out = coords_out - org (all (N,1,H,W); coords_out may alias coords_in). */
-nnd_status nnd_flow_conv7x7_relu(const float* flow, const float* weight, const float* bias, int N, int H, int W,
+nnd_status nnd_flow_conv7x7_relu(const float* flow, const float* weight_t, const float* bias, int N, int H, int W,
                                  int c_out, float* out, nnd_stream_t stream);
 nnd_status nnd_flow_head_tail(const float* x, const float* weight, const float* bias, int N, int C, int H, int W,
                               float* delta, const float* coords_in, const float* org, float* coords_out,
@@ -246,6 +247,18 @@ nnd_status nnd_gru_gate_r(const float* zr_pre, const float* bias_zr, const float
                           float* z, float* S, int ctot, nnd_stream_t stream);
 nnd_status nnd_gru_gate_h(const float* q_pre, const float* bias_q, const float* z, long long pixels, int ch,
                           float* h, float* S, int ctot, nnd_stream_t stream);
+
+/* The same glue for the fp16 form of the recurrence (kind::f16 tensor-core products at twice the TF32 rate, same
+ * 10-bit operand mantissa): staging buffer S16, split weights and the convolutions' pre-activations are IEEE
+ * fp16 (passed as void*), h / z / biases stay fp32; conversions round to nearest and saturate.
+ *   nnd_gru_stage_f16: src_kind 0 = fp32 (N,C,HW), 1 = fp32 channels-last, 2 = fp16 channels-last.
+ *   nnd_gru_gate_h_f16: h16, when not NULL, also receives the new hidden state as dense channels-last fp16. */
+nnd_status nnd_gru_stage_f16(const void* src, int src_kind, int N, int C, long long hw, void* S16, int ctot, int off,
+                             nnd_stream_t stream);
+nnd_status nnd_gru_gate_r_f16(const void* zr_pre16, const float* bias_zr, const float* h, long long pixels, int ch,
+                              float* z, void* S16, int ctot, nnd_stream_t stream);
+nnd_status nnd_gru_gate_h_f16(const void* q_pre16, const float* bias_q, const float* z, long long pixels, int ch,
+                              float* h, void* S16, int ctot, void* h16, nnd_stream_t stream);
 
 #ifdef __cplusplus
 }

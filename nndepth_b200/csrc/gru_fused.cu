@@ -126,6 +126,113 @@ gru_gate_h_kernel(const float4* __restrict__ q_pre, const float4* __restrict__ b
   }
 }
 
+// ---- fp16 staging variant ------------------------------------------------------------------------------------
+// fp16 has TF32's 10-bit mantissa, so RN_fp16(x) == RN_tf32(x) for every |x| in fp16's normal range (the GRU's
+// activations: h in [-1, 1], x = ReLU features of a few units) and kind::f16 tensor-core products run at twice
+// the TF32 rate.  The staging buffer, the split weights [RN16(w) ; RN16(w - RN16(w))] and the pre-activations
+// cuDNN returns are fp16; accumulation is fp32 inside the convolution; h, z and all gate arithmetic stay fp32.
+// Conversions saturate (cvt.rn.satfinite) instead of producing inf.  Measured (tools/exp_epe_fp16.py): final
+// disparity 0.00312 px from the reference vs 0.00311 px for the TF32 split.
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint2 pack_h4(const float4 v) { return make_uint2(pack_h2(v.x, v.y), pack_h2(v.z, v.w)); }
+__device__ __forceinline__ float2 unpack_h2(uint32_t v) {
+  float2 r;
+  asm("{.reg .f16 l, h; mov.b32 {l, h}, %2; cvt.f32.f16 %0, l; cvt.f32.f16 %1, h;}" : "=f"(r.x), "=f"(r.y) : "r"(v));
+  return r;
+}
+__device__ __forceinline__ float4 unpack_h4(const uint2 v) {
+  const float2 a = unpack_h2(v.x), b = unpack_h2(v.y);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void store_both_h4(uint16_t* S, long long p, int ctot, int c, const uint2 v) {
+  *reinterpret_cast<uint2*>(S + p * ctot + c) = v;
+  *reinterpret_cast<uint2*>(S + p * ctot + ctot / 2 + c) = v;
+}
+
+// fp32 NCHW source -> fp16 staging rows (transpose through shared memory, as gru_stage_kernel)
+__global__ void __launch_bounds__(256)
+gru_stage_f16_kernel(const float* __restrict__ src, int C, long long hw, uint16_t* __restrict__ S, int ctot, int off) {
+  __shared__ float tile[32][33];
+  const long long n = blockIdx.z;
+  const long long p0 = static_cast<long long>(blockIdx.x) * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i;
+    const long long p = p0 + tx;
+    tile[ty + 8 * i][tx] = (c < C && p < hw) ? __ldg(src + (n * C + c) * hw + p) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long p = p0 + ty + 8 * i;
+    const int c = c0 + tx;
+    if (c < C && p < hw) {
+      const uint16_t v = static_cast<uint16_t>(pack_h2(tile[tx][ty + 8 * i], 0.f) & 0xffffu);
+      uint16_t* row = S + (n * hw + p) * ctot + off + c;
+      row[0] = v;
+      row[ctot / 2] = v;
+    }
+  }
+}
+
+// channels-last source, fp32 (SRC_HALF = 0) or fp16 (1): one thread = 4 consecutive channels of one pixel
+template <int SRC_HALF>
+__global__ void __launch_bounds__(256)
+gru_stage_cl_f16_kernel(const void* __restrict__ src, int c4n, long long total4, uint16_t* __restrict__ S, int ctot, int off) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = i / c4n;
+    const int c4 = static_cast<int>(i - p * c4n);
+    const uint2 v = SRC_HALF ? __ldg(reinterpret_cast<const uint2*>(src) + i)
+                             : pack_h4(__ldg(reinterpret_cast<const float4*>(src) + i));
+    store_both_h4(S, p, ctot, off + 4 * c4, v);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gru_gate_r_f16_kernel(const uint2* __restrict__ zr_pre, const float4* __restrict__ bias_zr, const float4* __restrict__ h,
+                      int ch4, long long total4, float4* __restrict__ z_out, uint16_t* __restrict__ S, int ctot) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = i / ch4;
+    const int c4 = static_cast<int>(i - p * ch4);
+    const uint2* row = zr_pre + p * 2 * ch4;   // [z | r]
+    const float4 zp = add4(unpack_h4(__ldg(row + c4)), __ldg(bias_zr + c4));
+    const float4 rp = add4(unpack_h4(__ldg(row + ch4 + c4)), __ldg(bias_zr + ch4 + c4));
+    const float4 hv = __ldg(h + i);
+    z_out[i] = make_float4(sigmoidf_(zp.x), sigmoidf_(zp.y), sigmoidf_(zp.z), sigmoidf_(zp.w));
+    const float4 rh = make_float4(sigmoidf_(rp.x) * hv.x, sigmoidf_(rp.y) * hv.y, sigmoidf_(rp.z) * hv.z, sigmoidf_(rp.w) * hv.w);
+    store_both_h4(S, p, ctot, 4 * c4, pack_h4(rh));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gru_gate_h_f16_kernel(const uint2* __restrict__ q_pre, const float4* __restrict__ bias_q, const float4* __restrict__ z, int ch4,
+                      long long total4, float4* __restrict__ h, uint16_t* __restrict__ S, int ctot, uint2* __restrict__ h16) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = i / ch4;
+    const int c4 = static_cast<int>(i - p * ch4);
+    const float4 qp = add4(unpack_h4(__ldg(q_pre + i)), __ldg(bias_q + c4));
+    const float4 zv = __ldg(z + i), hv = h[i];
+    float4 hn;
+    hn.x = (1.0f - zv.x) * hv.x + zv.x * tanhf(qp.x);
+    hn.y = (1.0f - zv.y) * hv.y + zv.y * tanhf(qp.y);
+    hn.z = (1.0f - zv.z) * hv.z + zv.z * tanhf(qp.z);
+    hn.w = (1.0f - zv.w) * hv.w + zv.w * tanhf(qp.w);
+    h[i] = hn;
+    const uint2 hq = pack_h4(hn);
+    store_both_h4(S, p, ctot, 4 * c4, hq);
+    if (h16) h16[i] = hq;
+  }
+}
+
 static unsigned grid_for(long long items) {
   const long long want = (items + 255) / 256, cap = static_cast<long long>(sm_count()) * 16;
   return static_cast<unsigned>(want < cap ? want : cap);
@@ -183,6 +290,63 @@ nnd_status nnd_gru_gate_h(const float* q_pre, const float* bias_q, const float* 
       reinterpret_cast<const float4*>(q_pre), reinterpret_cast<const float4*>(bias_q), reinterpret_cast<const float4*>(z), ch / 4,
       total4, reinterpret_cast<float4*>(h), S, ctot);
   return check_launch("gru_gate_h_kernel");
+}
+
+nnd_status nnd_gru_stage_f16(const void* src, int src_kind, int N, int C, long long hw, void* S16, int ctot, int off,
+                             nnd_stream_t stream) {
+  using namespace nnd;
+  NND_REQUIRE(src && S16, "gru_stage_f16: null pointer");
+  NND_REQUIRE(src_kind >= 0 && src_kind <= 2, "gru_stage_f16: src_kind %d is not 0 (fp32 NCHW), 1 (fp32 NHWC) or 2 (fp16 NHWC)",
+              src_kind);
+  NND_REQUIRE(N > 0 && C > 0 && hw > 0 && ctot > 0, "gru_stage_f16: N, C, H*W, ctot must be positive");
+  NND_REQUIRE(N <= 65535 && (C + 31) / 32 <= 65535, "gru_stage_f16: N or C exceeds the grid limit");
+  NND_REQUIRE(ctot % 2 == 0 && off >= 0 && off + C <= ctot / 2, "gru_stage_f16: channel offset outside the staging half-row");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint16_t* S = reinterpret_cast<uint16_t*>(S16);
+  if (src_kind != 0) {
+    NND_REQUIRE(C % 4 == 0 && ctot % 8 == 0 && off % 4 == 0 && aligned16(src) && aligned16(S16),
+                "gru_stage_f16: the channels-last source path needs channel counts / offsets in quads and 16-byte alignment");
+    const long long total4 = static_cast<long long>(N) * hw * (C / 4);
+    if (src_kind == 1) {
+      gru_stage_cl_f16_kernel<0><<<grid_for(total4), 256, 0, st>>>(src, C / 4, total4, S, ctot, off);
+    } else {
+      gru_stage_cl_f16_kernel<1><<<grid_for(total4), 256, 0, st>>>(src, C / 4, total4, S, ctot, off);
+    }
+    return check_launch("gru_stage_cl_f16_kernel");
+  }
+  dim3 grid(static_cast<unsigned>((hw + 31) / 32), (C + 31) / 32, N);
+  gru_stage_f16_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(src), C, hw, S, ctot, off);
+  return check_launch("gru_stage_f16_kernel");
+}
+
+nnd_status nnd_gru_gate_r_f16(const void* zr_pre16, const float* bias_zr, const float* h, long long pixels, int ch, float* z,
+                              void* S16, int ctot, nnd_stream_t stream) {
+  using namespace nnd;
+  NND_REQUIRE(zr_pre16 && bias_zr && h && z && S16, "gru_gate_r_f16: null pointer");
+  NND_REQUIRE(pixels > 0 && ch > 0 && ch % 4 == 0 && ctot % 8 == 0 && 2 * ch <= ctot,
+              "gru_gate_r_f16: needs ch %% 4 == 0, ctot %% 8 == 0 and 2*ch <= ctot");
+  NND_REQUIRE(aligned16(zr_pre16) && aligned16(bias_zr) && aligned16(h) && aligned16(z) && aligned16(S16),
+              "gru_gate_r_f16: tensors must be 16-byte aligned");
+  const long long total4 = pixels * (ch / 4);
+  gru_gate_r_f16_kernel<<<grid_for(total4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint2*>(zr_pre16), reinterpret_cast<const float4*>(bias_zr), reinterpret_cast<const float4*>(h),
+      ch / 4, total4, reinterpret_cast<float4*>(z), reinterpret_cast<uint16_t*>(S16), ctot);
+  return check_launch("gru_gate_r_f16_kernel");
+}
+
+nnd_status nnd_gru_gate_h_f16(const void* q_pre16, const float* bias_q, const float* z, long long pixels, int ch, float* h,
+                              void* S16, int ctot, void* h16, nnd_stream_t stream) {
+  using namespace nnd;
+  NND_REQUIRE(q_pre16 && bias_q && z && h && S16, "gru_gate_h_f16: null pointer");
+  NND_REQUIRE(pixels > 0 && ch > 0 && ch % 4 == 0 && ctot % 8 == 0 && 2 * ch <= ctot,
+              "gru_gate_h_f16: needs ch %% 4 == 0, ctot %% 8 == 0 and 2*ch <= ctot");
+  NND_REQUIRE(aligned16(q_pre16) && aligned16(bias_q) && aligned16(z) && aligned16(h) && aligned16(S16) && aligned16(h16),
+              "gru_gate_h_f16: tensors must be 16-byte aligned");
+  const long long total4 = pixels * (ch / 4);
+  gru_gate_h_f16_kernel<<<grid_for(total4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint2*>(q_pre16), reinterpret_cast<const float4*>(bias_q), reinterpret_cast<const float4*>(z), ch / 4,
+      total4, reinterpret_cast<float4*>(h), reinterpret_cast<uint16_t*>(S16), ctot, reinterpret_cast<uint2*>(h16));
+  return check_launch("gru_gate_h_f16_kernel");
 }
 
 }  // extern "C"

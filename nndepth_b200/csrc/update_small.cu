@@ -15,18 +15,13 @@ namespace nnd {
 
 constexpr int F7_PX = 8;  // consecutive x positions per thread (share every weight load)
 
-// block = (Cout/4 lanes-of-4-channels, rows of 8-pixel strips); weights [tap][Cout] in shared memory
+// block = (Cout/4 lanes-of-4-channels, rows of 8-pixel strips); weight_t = the filter bank as [tap][Cout]
 __global__ void __launch_bounds__(256)
-flow_conv7x7_relu_kernel(const float* __restrict__ flow, const float* __restrict__ weight, const float* __restrict__ bias,
+flow_conv7x7_relu_kernel(const float* __restrict__ flow, const float* __restrict__ weight_t, const float* __restrict__ bias,
                          int H, int W, int cout, long long n_strips, int strips_per_row, float* __restrict__ out) {
   extern __shared__ float4 w_sm[];  // [49][cout / 4]
   const int c4n = cout >> 2;
-  for (int i = threadIdx.x; i < 49 * c4n; i += blockDim.x) {
-    const int tap = i / c4n, c4 = i - tap * c4n;
-    // weight (Cout, 1, 7, 7): element (c, tap)
-    w_sm[i] = make_float4(__ldg(weight + (4 * c4 + 0) * 49 + tap), __ldg(weight + (4 * c4 + 1) * 49 + tap),
-                          __ldg(weight + (4 * c4 + 2) * 49 + tap), __ldg(weight + (4 * c4 + 3) * 49 + tap));
-  }
+  for (int i = threadIdx.x; i < 49 * c4n; i += blockDim.x) w_sm[i] = __ldg(reinterpret_cast<const float4*>(weight_t) + i);
   __syncthreads();
   const int c4 = threadIdx.x % c4n;
   const int sub = threadIdx.x / c4n, subs = blockDim.x / c4n;
@@ -73,11 +68,11 @@ flow_conv7x7_relu_kernel(const float* __restrict__ flow, const float* __restrict
   }
 }
 
-constexpr int FH_PX = 8;  // output pixels per warp (a strip along x); lane = 8 channels per 256-channel slab
+constexpr int FH_PX = 8;  // output pixels per warp (a strip along x)
 
-// x (N,H,W,C) channels-last, C % 256 == 0 handled in slabs of 256 (lane owns channels slab*256 + 8*lane .. +7).
-// weight (1, C, 3, 3).  One warp per strip of FH_PX output pixels: 3 x (FH_PX + 2) input pixels are read once each.
-template <int SLABS>
+// x (N,H,W,C) channels-last with C = 32 * CPL: lane owns channels [lane*CPL, lane*CPL + CPL).  weight (1, C, 3, 3).
+// One warp per strip of FH_PX output pixels: the 3 x (FH_PX + 2) input pixels are read once each.
+template <int CPL>
 __global__ void __launch_bounds__(256)
 flow_head_tail_kernel(const float* __restrict__ x, const float* __restrict__ weight, const float* __restrict__ bias,
                       int H, int W, long long n_strips, int strips_per_row, float* __restrict__ delta,
@@ -85,15 +80,12 @@ flow_head_tail_kernel(const float* __restrict__ x, const float* __restrict__ wei
                       float* __restrict__ flow_out) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
-  constexpr int C = SLABS * 256;
-  // this lane's 8 * SLABS channels x 9 taps
-  float w[SLABS][9][8];
+  constexpr int C = 32 * CPL;
+  float w[9][CPL];
 #pragma unroll
-  for (int sl = 0; sl < SLABS; ++sl)
+  for (int t = 0; t < 9; ++t)
 #pragma unroll
-    for (int t = 0; t < 9; ++t)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) w[sl][t][j] = __ldg(weight + (sl * 256 + lane * 8 + j) * 9 + t);
+    for (int j = 0; j < CPL; ++j) w[t][j] = __ldg(weight + (lane * CPL + j) * 9 + t);
   const float b = bias ? __ldg(bias) : 0.f;
   for (long long s = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); s < n_strips;
        s += static_cast<long long>(gridDim.x) * warps_per_block) {
@@ -107,23 +99,26 @@ flow_head_tail_kernel(const float* __restrict__ x, const float* __restrict__ wei
     for (int ky = 0; ky < 3; ++ky) {
       const int yy = y + ky - 1;
       if (yy < 0 || yy >= H) continue;  // warp-uniform
-      const float* line = x + ((row - y + yy) * W) * C;
+      const float* line = x + ((row - y + yy) * W) * C + lane * CPL;
 #pragma unroll
       for (int i = 0; i < FH_PX + 2; ++i) {
         const int xx = x0 + i - 1;
-        if (xx < 0 || xx >= W) continue;  // warp-uniform
+        float v[CPL];
 #pragma unroll
-        for (int sl = 0; sl < SLABS; ++sl) {
-          const float4* src = reinterpret_cast<const float4*>(line + static_cast<long long>(xx) * C + sl * 256 + lane * 8);
-          const float4 a = __ldg(src), c = __ldg(src + 1);
-          const float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+        for (int q = 0; q < CPL / 4; ++q) {
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (xx >= 0 && xx < W) a = __ldg(reinterpret_cast<const float4*>(line + static_cast<long long>(xx) * C) + q);
+          v[4 * q] = a.x;
+          v[4 * q + 1] = a.y;
+          v[4 * q + 2] = a.z;
+          v[4 * q + 3] = a.w;
+        }
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const int p = i - kx;  // output pixel that sees input i through tap kx
-            if (p < 0 || p >= FH_PX) continue;
+        for (int kx = 0; kx < 3; ++kx) {
+          const int p = i - kx;  // output pixel that sees input i through tap kx
+          if (p < 0 || p >= FH_PX) continue;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[p] = fmaf(v[j], w[sl][ky * 3 + kx][j], acc[p]);
-          }
+          for (int j = 0; j < CPL; ++j) acc[p] = fmaf(v[j], w[ky * 3 + kx][j], acc[p]);
         }
       }
     }
@@ -153,22 +148,23 @@ flow_head_tail_kernel(const float* __restrict__ x, const float* __restrict__ wei
 
 extern "C" {
 
-nnd_status nnd_flow_conv7x7_relu(const float* flow, const float* weight, const float* bias, int N, int H, int W,
+nnd_status nnd_flow_conv7x7_relu(const float* flow, const float* weight_t, const float* bias, int N, int H, int W,
                                  int c_out, float* out, nnd_stream_t stream) {
   using namespace nnd;
-  NND_REQUIRE(flow && weight && bias && out, "flow_conv7x7_relu: null pointer");
+  NND_REQUIRE(flow && weight_t && bias && out, "flow_conv7x7_relu: null pointer");
   NND_REQUIRE(N > 0 && H > 0 && W > 0, "flow_conv7x7_relu: N, H, W must be positive");
   NND_REQUIRE(c_out > 0 && c_out % 4 == 0 && c_out <= 1024 && 256 % (c_out / 4) == 0,
               "flow_conv7x7_relu: c_out = %d must be a multiple of 4 with c_out/4 dividing 256", c_out);
-  NND_REQUIRE(aligned16(out) && aligned16(bias), "flow_conv7x7_relu: out and bias must be 16-byte aligned");
+  NND_REQUIRE(aligned16(out) && aligned16(bias) && aligned16(weight_t),
+              "flow_conv7x7_relu: out, bias and weight_t must be 16-byte aligned");
   const int strips_per_row = (W + F7_PX - 1) / F7_PX;
   const long long n_strips = static_cast<long long>(N) * H * strips_per_row;
   const int subs = 256 / (c_out / 4);
   const long long want = (n_strips + subs - 1) / subs;
-  const long long cap = static_cast<long long>(sm_count()) * 8;
+  const long long cap = static_cast<long long>(sm_count()) * 2;  // persistent: the 49 x c_out weights are staged per block
   const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
   const size_t smem = static_cast<size_t>(49) * c_out * sizeof(float);
-  flow_conv7x7_relu_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(flow, weight, bias, H, W, c_out,
+  flow_conv7x7_relu_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(flow, weight_t, bias, H, W, c_out,
                                                                                         n_strips, strips_per_row, out);
   return check_launch("flow_conv7x7_relu_kernel");
 }
@@ -179,7 +175,7 @@ nnd_status nnd_flow_head_tail(const float* x, const float* weight, const float* 
   using namespace nnd;
   NND_REQUIRE(x && weight, "flow_head_tail: null pointer");
   NND_REQUIRE(N > 0 && H > 0 && W > 0, "flow_head_tail: N, H, W must be positive");
-  NND_REQUIRE(C == 256 || C == 512, "flow_head_tail: C = %d (supported: 256, 512)", C);
+  NND_REQUIRE(C == 128 || C == 256 || C == 512, "flow_head_tail: C = %d (supported: 128, 256, 512)", C);
   NND_REQUIRE(aligned16(x), "flow_head_tail: x must be 16-byte aligned");
   NND_REQUIRE(delta || coords_in, "flow_head_tail: nothing to write (delta and coords_in are both null)");
   NND_REQUIRE(!coords_in || coords_out, "flow_head_tail: coords_in needs coords_out");
@@ -187,15 +183,18 @@ nnd_status nnd_flow_head_tail(const float* x, const float* weight, const float* 
   const int strips_per_row = (W + FH_PX - 1) / FH_PX;
   const long long n_strips = static_cast<long long>(N) * H * strips_per_row;
   const long long want = (n_strips + 7) / 8;
-  const long long cap = static_cast<long long>(sm_count()) * 4;
+  const long long cap = static_cast<long long>(sm_count()) * 8;
   const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (C == 256) {
-    flow_head_tail_kernel<1><<<grid, 256, 0, st>>>(x, weight, bias, H, W, n_strips, strips_per_row, delta, coords_in, org,
+  if (C == 128) {
+    flow_head_tail_kernel<4><<<grid, 256, 0, st>>>(x, weight, bias, H, W, n_strips, strips_per_row, delta, coords_in, org,
+                                                   coords_out, flow_out);
+  } else if (C == 256) {
+    flow_head_tail_kernel<8><<<grid, 256, 0, st>>>(x, weight, bias, H, W, n_strips, strips_per_row, delta, coords_in, org,
                                                    coords_out, flow_out);
   } else {
-    flow_head_tail_kernel<2><<<grid, 256, 0, st>>>(x, weight, bias, H, W, n_strips, strips_per_row, delta, coords_in, org,
-                                                   coords_out, flow_out);
+    flow_head_tail_kernel<16><<<grid, 256, 0, st>>>(x, weight, bias, H, W, n_strips, strips_per_row, delta, coords_in, org,
+                                                    coords_out, flow_out);
   }
   return check_launch("flow_head_tail_kernel");
 }

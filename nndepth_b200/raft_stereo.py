@@ -95,7 +95,11 @@ def flow_conv7x7_relu(conv, flow):
     from . import _lib
     N, _, H, W = flow.shape
     flow = flow.contiguous()
-    weight = conv.weight.detach().contiguous()       # (Cout,1,7,7): dense in either memory format
+    cache = getattr(conv, "_tap_major_weight", None)
+    if cache is None or cache[0] != conv.weight._version or cache[1].device != flow.device:
+        cache = (conv.weight._version, conv.weight.detach().reshape(conv.out_channels, 49).t().contiguous())
+        conv._tap_major_weight = cache
+    weight = cache[1]                                # (49, Cout)
     out = torch.empty(N, H, W, conv.out_channels, dtype=torch.float32, device=flow.device)
     with torch.cuda.device(flow.device):
         _lib.check(_lib.load().nnd_flow_conv7x7_relu(_lib.ptr(flow), _lib.ptr(weight), _lib.ptr(conv.bias.detach()), N, H, W,
@@ -109,7 +113,7 @@ def flow_head_tail(conv, x, coords=None, org=None):
     channels-last ``x``, as one fp32 kernel.  With ``coords`` / ``org`` it also performs the loop's update
     (raft_stereo/model.py:132-134) and returns ``(coords + delta, coords + delta - org)``; otherwise ``delta``.
     Returns ``None`` when the shape is not the kernel's (the caller then uses cuDNN)."""
-    if not (_small_kernels_ok(x) and conv.out_channels == 1 and conv.in_channels in (256, 512) and _is_nhwc(x)
+    if not (_small_kernels_ok(x) and conv.out_channels == 1 and conv.in_channels in (128, 256, 512) and _is_nhwc(x)
             and conv.kernel_size == (3, 3) and conv.padding == (1, 1) and conv.stride == (1, 1)
             and conv.dilation == (1, 1) and conv.groups == 1):
         return None
@@ -290,17 +294,22 @@ class SepConvGRU(nn.Module):
     def _rn_tf32(t):
         return ((t.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
 
-    def _split_weights(self, tag, channels_last=False):
+    def _split_weights(self, tag, channels_last=False, half=False):
         """``[w_hi ; w_lo]`` along the INPUT-channel axis for the (z|r) and q convolutions of one half-step (the
-        activations are presented twice, ``[RN(x) ; RN(x)]``)."""
-        key = (tag, channels_last)
+        activations are presented twice, ``[RN(x) ; RN(x)]``).  ``half``: both parts as fp16 (same 10-bit mantissa
+        as TF32; ``w_lo`` keeps ~5 more bits before fp16's subnormal spacing cuts it, i.e. weights good to 2**-17)."""
+        key = (tag, channels_last, half)
         if key not in self._split_w:
             cz, cr, cq = (getattr(self, f"conv{g}{tag}") for g in "zrq")
             packed = []
             for w, b in ((torch.cat([cz.weight, cr.weight], 0), torch.cat([cz.bias, cr.bias], 0)), (cq.weight, cq.bias)):
                 w = w.detach().float()
-                hi = self._rn_tf32(w)
-                w2 = torch.cat([hi, w - hi], 1).contiguous()
+                if half:
+                    hi16 = w.clamp(-65504.0, 65504.0).half()
+                    w2 = torch.cat([hi16, (w - hi16.float()).half()], 1).contiguous()
+                else:
+                    hi = self._rn_tf32(w)
+                    w2 = torch.cat([hi, w - hi], 1).contiguous()
                 if channels_last:
                     w2 = w2.contiguous(memory_format=torch.channels_last)
                 packed.append((w2, b.detach().float().contiguous()))
@@ -316,15 +325,27 @@ class SepConvGRU(nn.Module):
         q = torch.tanh(F.conv2d(torch.cat([rhx, rhx], 1), wq, bq, padding=pad))
         return (1 - z) * h + z * q
 
+    def _half_step_wsplit16(self, h, x, tag):
+        """The fp16 form through torch ops: fp16 operands, fp32 accumulation, fp16 pre-activations (what cuDNN's
+        fp16 convolution returns), fp32 gates."""
+        (wzr, bzr), (wq, bq), pad = self._split_weights(tag, half=True)
+        hx = torch.cat([h, x], dim=1).clamp(-65504.0, 65504.0).half()
+        z, r = torch.sigmoid(F.conv2d(torch.cat([hx, hx], 1), wzr, None, padding=pad).float() + bzr.view(1, -1, 1, 1)).chunk(2, dim=1)
+        rhx = torch.cat([r * h, x], dim=1).clamp(-65504.0, 65504.0).half()
+        q = torch.tanh(F.conv2d(torch.cat([rhx, rhx], 1), wq, None, padding=pad).float() + bq.view(1, -1, 1, 1))
+        return (1 - z) * h + z * q
+
     # ---- fused channels-last runner of the weight-split recurrence (csrc/gru_fused.cu) -------------------------
     def start(self, h0, inp):
         """Begin a forward: returns the per-forward runner holding the hidden state and the staging buffer."""
-        return FusedGRURun(self, h0, inp)
+        return FusedGRURun(self, h0, inp, half=self.recurrence == "wsplit16")
 
     def forward(self, h, x):
         if self.recurrence == "wsplit" and h.is_cuda:
             with cudnn_tf32(True):
                 return self._half_step_wsplit(self._half_step_wsplit(h, x, "1"), x, "2")
+        if self.recurrence == "wsplit16" and h.is_cuda:
+            return self._half_step_wsplit16(self._half_step_wsplit16(h, x, "1"), x, "2")
         if self.recurrence == "fp32":
             with cudnn_tf32(False):
                 return self._half_step(self._half_step(h, x, "1"), x, "2")
@@ -341,10 +362,11 @@ class FusedGRURun:
     per forward, the motion half once per iteration.
     """
 
-    def __init__(self, gru, h0, inp):
+    def __init__(self, gru, h0, inp, half=False):
         from . import _lib
         self._lib = _lib
         self.gru = gru
+        self.half = bool(half)      # fp16 staging buffer / weights / pre-activations (csrc/gru_fused.cu, fp16 variant)
         h0, inp = h0.float(), inp.float()
         N, ch, H, W = h0.shape
         self.N, self.ch, self.H, self.W = N, ch, H, W
@@ -352,7 +374,8 @@ class FusedGRURun:
         self.cx = gru.convz1.weight.shape[1] - ch
         self.ctot = 2 * (ch + self.cx)
         cl = torch.channels_last
-        self.S = torch.empty(N, self.ctot, H, W, dtype=torch.float32, device=h0.device).contiguous(memory_format=cl)
+        self.S = torch.empty(N, self.ctot, H, W, dtype=torch.float16 if self.half else torch.float32,
+                             device=h0.device).contiguous(memory_format=cl)
         self.h = torch.empty(N, ch, H, W, dtype=torch.float32, device=h0.device).contiguous(memory_format=cl)
         self.z = torch.empty_like(self.h)
         self.h.copy_(h0)
@@ -363,11 +386,17 @@ class FusedGRURun:
         """Write ``RN_tf32(src)`` at channel offset ``off`` of the staging rows; a channels-last ``src`` is read as it lies."""
         lib = self._lib
         N, C = src.shape[0], src.shape[1]
-        src = src.float()
+        if not (self.half and src.dtype == torch.float16):
+            src = src.float()
         cl = (not src.is_contiguous()) and src.is_contiguous(memory_format=torch.channels_last) and C % 4 == 0
         if not cl:
-            src = src.contiguous()
+            src = src.float().contiguous()
         with torch.cuda.device(src.device):
+            if self.half:
+                kind = 0 if not cl else (2 if src.dtype == torch.float16 else 1)
+                lib.check(lib.load().nnd_gru_stage_f16(src.data_ptr(), kind, N, C, self.H * self.W, self.S.data_ptr(), self.ctot,
+                                                       off, lib.stream_ptr(src)), "nnd_gru_stage_f16")
+                return
             lib.check(lib.load().nnd_gru_stage(lib.ptr(src), 1 if cl else 0, N, C, self.H * self.W, lib.ptr(self.S), self.ctot,
                                                off, lib.stream_ptr(src)), "nnd_gru_stage")
 
@@ -384,6 +413,8 @@ class FusedGRURun:
             self._stage(flow, self.ch + self.cx - flow.shape[1])
         pixels = self.N * self.H * self.W
         cl = torch.channels_last
+        if self.half:
+            return self._step_f16(pixels)
         with cudnn_tf32(True), torch.cuda.device(self.S.device):
             for tag in "12":
                 (wzr, bzr), (wq, bq), pad = self.gru._split_weights(tag, channels_last=True)
@@ -393,6 +424,22 @@ class FusedGRURun:
                 q = F.conv2d(self.S, wq, None, padding=pad).contiguous(memory_format=cl)
                 lib.check(lib.load().nnd_gru_gate_h(lib.ptr(q), lib.ptr(bq), lib.ptr(self.z), pixels, self.ch, lib.ptr(self.h),
                                                     lib.ptr(self.S), self.ctot, lib.stream_ptr(q)), "nnd_gru_gate_h")
+        return self.h
+
+    def _step_f16(self, pixels):
+        lib = self._lib
+        cl = torch.channels_last
+        st = lib.stream_ptr(self.S)
+        with torch.cuda.device(self.S.device):
+            for tag in "12":
+                (wzr, bzr), (wq, bq), pad = self.gru._split_weights(tag, channels_last=True, half=True)
+                zr = F.conv2d(self.S, wzr, None, padding=pad).contiguous(memory_format=cl)
+                lib.check(lib.load().nnd_gru_gate_r_f16(zr.data_ptr(), lib.ptr(bzr), lib.ptr(self.h), pixels, self.ch,
+                                                        lib.ptr(self.z), self.S.data_ptr(), self.ctot, st), "nnd_gru_gate_r_f16")
+                q = F.conv2d(self.S, wq, None, padding=pad).contiguous(memory_format=cl)
+                lib.check(lib.load().nnd_gru_gate_h_f16(q.data_ptr(), lib.ptr(bq), lib.ptr(self.z), pixels, self.ch,
+                                                        lib.ptr(self.h), self.S.data_ptr(), self.ctot, None, st),
+                          "nnd_gru_gate_h_f16")
         return self.h
 
 
@@ -566,12 +613,12 @@ class RAFTStereo(nn.Module):
     def forward(self, frame1, frame2, **kwargs):
         if self.dense_precision is None:
             return self._forward(frame1, frame2, **kwargs)
-        if self.dense_precision not in ("fp32", "mixed", "mixed2x", "tf32"):
-            raise ValueError("dense_precision must be None, 'fp32', 'mixed', 'mixed2x' or 'tf32', "
+        if self.dense_precision not in ("fp32", "mixed", "mixed2x", "mixed16", "tf32"):
+            raise ValueError("dense_precision must be None, 'fp32', 'mixed', 'mixed2x', 'mixed16' or 'tf32', "
                              f"got {self.dense_precision!r}")
         gru = getattr(self.update_block, "gru", None)
         if gru is not None:
-            gru.recurrence = {"mixed": "fp32", "mixed2x": "wsplit"}.get(self.dense_precision)
+            gru.recurrence = {"mixed": "fp32", "mixed2x": "wsplit", "mixed16": "wsplit16"}.get(self.dense_precision)
         with cudnn_tf32(self.dense_precision != "fp32"):
             return self._forward(frame1, frame2, **kwargs)
 
@@ -585,7 +632,7 @@ class RAFTStereo(nn.Module):
         corr = self.corr_fn(fmap1, fmap2, self.corr_levels, self.corr_radius)
         gru = getattr(self.update_block, "gru", None)
         gru_run = None
-        if (self.fuse_gru and gru is not None and getattr(gru, "recurrence", None) == "wsplit" and net.is_cuda
+        if (self.fuse_gru and gru is not None and getattr(gru, "recurrence", None) in ("wsplit", "wsplit16") and net.is_cuda
                 and not torch.is_grad_enabled()):
             gru_run = gru.start(net, inp)
         org_coords = self.initialize_coords(fmap1)

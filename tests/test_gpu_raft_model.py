@@ -66,7 +66,7 @@ def test_kitti_32_iterations(golden, precision):
     assert epe(graphed, ref) < EPE_BAR, epe(graphed, ref)
 
 
-@pytest.mark.parametrize("mode,bar", [("fp32", 0.001), ("mixed", EPE_BAR), ("mixed2x", EPE_BAR)])
+@pytest.mark.parametrize("mode,bar", [("fp32", 0.001), ("mixed", EPE_BAR), ("mixed2x", EPE_BAR), ("mixed16", EPE_BAR)])
 def test_kitti_dense_precision_modes(golden, mode, bar):
     """The bench's dense-layer precision modes against the reference disparity (KITTI geometry, 32 iterations):
     "mixed" (ConvGRU fp32, other convolutions TF32) must stay inside the 0.01 px bar, "fp32" far inside."""
@@ -108,15 +108,43 @@ def test_fused_gru_matches_unfused_weight_split():
             assert (fused - h_fp32).abs().max().item() < 1e-3       # activations are rounded to TF32 (2^-11 relative)
 
 
+def test_fused_gru_fp16_matches_torch_ops_and_fp32():
+    """The fp16 form of the fused runner (fp16 staging / split weights / pre-activations, fp32 gates) vs the same
+    recurrence in torch ops, and vs fp32: fp16 carries TF32's mantissa, so the distance to fp32 is the same."""
+    from nndepth_b200.raft_stereo import SepConvGRU
+    torch.manual_seed(7)
+    gru = SepConvGRU(hidden_dim=128, input_dim=256).cuda().eval()
+    N, H, W = 2, 12, 20
+    h0 = torch.tanh(torch.randn(N, 128, H, W, device="cuda"))
+    inp = torch.relu(torch.randn(N, 128, H, W, device="cuda"))
+    motions = [torch.randn(N, 128, H, W, device="cuda") for _ in range(3)]
+    with torch.no_grad():
+        gru.recurrence = "wsplit16"
+        run = gru.start(h0, inp)
+        assert run.half and run.S.dtype == torch.float16
+        h_ref, h_fp32 = h0, h0
+        for i, m in enumerate(motions):
+            # channels-last fp32, NCHW fp32 and channels-last fp16 sources all stage to the same rows
+            src = [m.contiguous(memory_format=torch.channels_last), m, m.half().contiguous(memory_format=torch.channels_last)][i]
+            fused = run.step(src)
+            h_ref = gru(h_ref, torch.cat([inp, m], 1))
+            gru.recurrence = "fp32"
+            h_fp32 = gru(h_fp32, torch.cat([inp, m], 1))
+            gru.recurrence = "wsplit16"
+            assert fused.dtype == torch.float32 and fused.shape == h_ref.shape
+            assert (fused - h_ref).abs().max().item() < 2e-3        # fp16 pre-activations: summation order moves a rounding
+            assert (fused - h_fp32).abs().max().item() < 2e-3       # 2^-11 relative on operands and pre-activations
+
+
 def test_engine_bench_configuration_stays_inside_the_bar(golden):
     """The exact configuration bench.py times -- StereoEngine (channels-last encoder, CUDA graph, fused GRU glue,
-    fused lookup / upsampling), dense_precision = "mixed2x" -- against the reference disparity."""
+    fused lookup / upsampling), dense_precision = "mixed16" -- against the reference disparity."""
     from nndepth_b200.engine import StereoEngine
     from nndepth_b200.raft_stereo import BaseRAFTStereo
     g = golden("raft_kitti")
     torch.manual_seed(0)
     model = BaseRAFTStereo(iters=int(g["iters"])).eval()
-    model.dense_precision = "mixed2x"
+    model.dense_precision = "mixed16"
     engine = StereoEngine(model, device="cuda", use_cuda_graph=True)
     left, right = (t.cuda() for t in seeded_pair(g["shape"]))
     ref = torch.from_numpy(g["final_up_disp"]).cuda()
@@ -128,8 +156,9 @@ def test_engine_bench_configuration_stays_inside_the_bar(golden):
     assert epe(host.cuda(), ref) < EPE_BAR
 
 
+@pytest.mark.parametrize("mode", ["mixed2x", "mixed16"])
 @pytest.mark.parametrize("graph", [False, True])
-def test_small_all_iterations_bench_mode(golden, graph):
+def test_small_all_iterations_bench_mode(golden, graph, mode):
     """The bench's mode (mixed2x, every fusion on) at the small golden shape: every iteration's upsampled map
     against the reference, eager and as a CUDA graph (few pixel groups, ragged tiles, 12 iterations)."""
     from nndepth_b200.engine import StereoEngine
@@ -137,7 +166,7 @@ def test_small_all_iterations_bench_mode(golden, graph):
     g = golden("raft_small")
     torch.manual_seed(0)
     model = BaseRAFTStereo(iters=int(g["iters"])).eval()
-    model.dense_precision = "mixed2x"
+    model.dense_precision = mode
     engine = StereoEngine(model, device="cuda", use_cuda_graph=graph)
     left, right = (t.cuda() for t in seeded_pair(g["shape"]))
     ref = torch.from_numpy(g["all_up_disp"]).cuda()

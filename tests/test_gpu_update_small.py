@@ -29,7 +29,7 @@ def test_flow_conv7x7_falls_back_for_two_flow_channels():
         torch.testing.assert_close(flow_conv7x7_relu(conv, flow), F.relu(conv(flow)), rtol=1e-5, atol=1e-5)
 
 
-@pytest.mark.parametrize("shape", [(2, 256, 9, 21), (1, 256, 48, 156), (1, 512, 5, 7), (1, 256, 1, 1)])
+@pytest.mark.parametrize("shape", [(2, 128, 9, 21), (1, 128, 48, 156), (1, 256, 9, 13), (1, 512, 5, 7), (1, 256, 1, 1)])
 @pytest.mark.parametrize("bias", [True, False])
 def test_flow_head_tail(shape, bias):
     from nndepth_b200.raft_stereo import flow_head_tail
@@ -54,7 +54,8 @@ def test_flow_head_tail_declines_other_shapes():
     from nndepth_b200.raft_stereo import flow_head_tail
     x = torch.randn(1, 128, 4, 4, device="cuda").contiguous(memory_format=torch.channels_last)
     with torch.no_grad():
-        assert flow_head_tail(torch.nn.Conv2d(128, 1, 3, padding=1).cuda(), x) is None        # C = 128
+        x64 = torch.randn(1, 64, 4, 4, device="cuda").contiguous(memory_format=torch.channels_last)
+        assert flow_head_tail(torch.nn.Conv2d(64, 1, 3, padding=1).cuda(), x64) is None        # C = 64
         x256 = torch.randn(1, 256, 4, 4, device="cuda")                                       # NCHW, not channels-last
         assert flow_head_tail(torch.nn.Conv2d(256, 1, 3, padding=1).cuda(), x256) is None
         assert flow_head_tail(torch.nn.Conv2d(256, 2, 3, padding=1).cuda(),
