@@ -210,24 +210,26 @@ nnd_status nnd_agcl_iter_nhwc(const float* fmap1_nhwc, const float* fmap2_nhwc, 
  *   (blocks/update_block.py:110) into this pass, 1.0 for an already scaled mask.
  *   mask_bias (9*rate*rate) or NULL is added to the logits before the scale: the bias of the mask head's last
  *   1x1 convolution, so that convolution can run bias-free (one pass over the mask less).
- *   mask_channels_last != 0: the mask is stored (N, H, W, 9*rate*rate) (rate 8 only) -- the memory format
- *   cuDNN returns when the hidden state feeding the mask head is channels-last.
+ *   mask_layout: 0 = fp32 (N, 9*rate*rate, H, W); 1 = fp32 stored (N, H, W, 9*rate*rate) (rate 8 only) -- the
+ *   memory format cuDNN returns when the hidden state feeding the mask head is channels-last; 2 = the same
+ *   channels-last layout in IEEE fp16 (mask head run as fp16 convolutions).
  * ---------------------------------------------------------------------------------------------- */
-nnd_status nnd_convex_upsample(const float* flow, const float* mask, const float* mask_bias, int N, int H, int W,
-                               int rate, float mask_scale, int mask_channels_last, float* out, nnd_stream_t stream);
+nnd_status nnd_convex_upsample(const float* flow, const void* mask, const float* mask_bias, int N, int H, int W,
+                               int rate, float mask_scale, int mask_layout, float* out, nnd_stream_t stream);
 
 /* Single-flow-channel convolutions of the update block (stereo: flow_channel = 1), fp32 FFMA.
  *   nnd_flow_conv7x7_relu: relu(convf1(flow)), BasicMotionEncoder blocks/update_block.py:53,60.
  *     flow (N,1,H,W); weight_t (49, c_out) = the (c_out,1,7,7) filter bank transposed (tap-major); bias (c_out);
  *     out channels-last (N,H,W,c_out); padding 3.
- *   nnd_flow_head_tail: FlowHead.conv2 blocks/update_block.py:23,36 on a channels-last x (N,H,W,C), C in
+ *   nnd_flow_head_tail: FlowHead.conv2 blocks/update_block.py:23,36 on a channels-last x (N,H,W,C) (fp32, or IEEE fp16
+ *     when x_f16), C in
  *     {128, 256, 512}; weight (1,C,3,3); bias 1 float or NULL; delta (N,1,H,W) or NULL.  With coords_in the
  *     refinement-loop update raft_stereo/model.py:132-134 is fused: coords_out = coords_in + delta and, if
  *     flow_out, flow_out = coords_out - org (all (N,1,H,W); coords_out may alias coords_in). */
 nnd_status nnd_flow_conv7x7_relu(const float* flow, const float* weight_t, const float* bias, int N, int H, int W,
                                  int c_out, float* out, nnd_stream_t stream);
-nnd_status nnd_flow_head_tail(const float* x, const float* weight, const float* bias, int N, int C, int H, int W,
-                              float* delta, const float* coords_in, const float* org, float* coords_out,
+nnd_status nnd_flow_head_tail(const void* x, int x_f16, const float* weight, const float* bias, int N, int C, int H,
+                              int W, float* delta, const float* coords_in, const float* org, float* coords_out,
                               float* flow_out, nnd_stream_t stream);
 
 /* Fused, channels-last glue of the separable ConvGRU (nndepth/blocks/gru.py:5-37) around its weight-split

@@ -116,4 +116,21 @@ __device__ __forceinline__ void store_row_quad(const Pyramid& pyr, int num_level
   }
 }
 
+// ---- IEEE fp16 packing (round to nearest, saturating instead of inf) ------------------------------
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint2 pack_h4(const float4 v) { return make_uint2(pack_h2(v.x, v.y), pack_h2(v.z, v.w)); }
+__device__ __forceinline__ float2 unpack_h2(uint32_t v) {
+  float2 r;
+  asm("{.reg .f16 l, h; mov.b32 {l, h}, %2; cvt.f32.f16 %0, l; cvt.f32.f16 %1, h;}" : "=f"(r.x), "=f"(r.y) : "r"(v));
+  return r;
+}
+__device__ __forceinline__ float4 unpack_h4(const uint2 v) {
+  const float2 a = unpack_h2(v.x), b = unpack_h2(v.y);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
 }  // namespace nnd

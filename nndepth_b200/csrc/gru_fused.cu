@@ -133,21 +133,6 @@ gru_gate_h_kernel(const float4* __restrict__ q_pre, const float4* __restrict__ b
 // cuDNN returns are fp16; accumulation is fp32 inside the convolution; h, z and all gate arithmetic stay fp32.
 // Conversions saturate (cvt.rn.satfinite) instead of producing inf.  Measured (tools/exp_epe_fp16.py): final
 // disparity 0.00312 px from the reference vs 0.00311 px for the TF32 split.
-__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-__device__ __forceinline__ uint2 pack_h4(const float4 v) { return make_uint2(pack_h2(v.x, v.y), pack_h2(v.z, v.w)); }
-__device__ __forceinline__ float2 unpack_h2(uint32_t v) {
-  float2 r;
-  asm("{.reg .f16 l, h; mov.b32 {l, h}, %2; cvt.f32.f16 %0, l; cvt.f32.f16 %1, h;}" : "=f"(r.x), "=f"(r.y) : "r"(v));
-  return r;
-}
-__device__ __forceinline__ float4 unpack_h4(const uint2 v) {
-  const float2 a = unpack_h2(v.x), b = unpack_h2(v.y);
-  return make_float4(a.x, a.y, b.x, b.y);
-}
 __device__ __forceinline__ void store_both_h4(uint16_t* S, long long p, int ctot, int c, const uint2 v) {
   *reinterpret_cast<uint2*>(S + p * ctot + c) = v;
   *reinterpret_cast<uint2*>(S + p * ctot + ctot / 2 + c) = v;

@@ -72,9 +72,9 @@ constexpr int FH_PX = 8;  // output pixels per warp (a strip along x)
 
 // x (N,H,W,C) channels-last with C = 32 * CPL: lane owns channels [lane*CPL, lane*CPL + CPL).  weight (1, C, 3, 3).
 // One warp per strip of FH_PX output pixels: the 3 x (FH_PX + 2) input pixels are read once each.
-template <int CPL>
+template <int CPL, int X_F16>
 __global__ void __launch_bounds__(256)
-flow_head_tail_kernel(const float* __restrict__ x, const float* __restrict__ weight, const float* __restrict__ bias,
+flow_head_tail_kernel(const void* __restrict__ x_, const float* __restrict__ weight, const float* __restrict__ bias,
                       int H, int W, long long n_strips, int strips_per_row, float* __restrict__ delta,
                       const float* __restrict__ coords_in, const float* __restrict__ org, float* __restrict__ coords_out,
                       float* __restrict__ flow_out) {
@@ -99,7 +99,7 @@ flow_head_tail_kernel(const float* __restrict__ x, const float* __restrict__ wei
     for (int ky = 0; ky < 3; ++ky) {
       const int yy = y + ky - 1;
       if (yy < 0 || yy >= H) continue;  // warp-uniform
-      const float* line = x + ((row - y + yy) * W) * C + lane * CPL;
+      const long long line = ((row - y + yy) * W) * C + lane * CPL;   // element index of this lane's channels
 #pragma unroll
       for (int i = 0; i < FH_PX + 2; ++i) {
         const int xx = x0 + i - 1;
@@ -107,7 +107,10 @@ flow_head_tail_kernel(const float* __restrict__ x, const float* __restrict__ wei
 #pragma unroll
         for (int q = 0; q < CPL / 4; ++q) {
           float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (xx >= 0 && xx < W) a = __ldg(reinterpret_cast<const float4*>(line + static_cast<long long>(xx) * C) + q);
+          if (xx >= 0 && xx < W) {
+            const long long e4 = (line + static_cast<long long>(xx) * C) / 4 + q;
+            a = X_F16 ? unpack_h4(__ldg(reinterpret_cast<const uint2*>(x_) + e4)) : __ldg(reinterpret_cast<const float4*>(x_) + e4);
+          }
           v[4 * q] = a.x;
           v[4 * q + 1] = a.y;
           v[4 * q + 2] = a.z;
@@ -169,7 +172,7 @@ nnd_status nnd_flow_conv7x7_relu(const float* flow, const float* weight_t, const
   return check_launch("flow_conv7x7_relu_kernel");
 }
 
-nnd_status nnd_flow_head_tail(const float* x, const float* weight, const float* bias, int N, int C, int H, int W,
+nnd_status nnd_flow_head_tail(const void* x, int x_f16, const float* weight, const float* bias, int N, int C, int H, int W,
                               float* delta, const float* coords_in, const float* org, float* coords_out,
                               float* flow_out, nnd_stream_t stream) {
   using namespace nnd;
@@ -186,16 +189,17 @@ nnd_status nnd_flow_head_tail(const float* x, const float* weight, const float* 
   const long long cap = static_cast<long long>(sm_count()) * 8;
   const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define NND_FHT(CPL, F16) \
+  flow_head_tail_kernel<CPL, F16><<<grid, 256, 0, st>>>(x, weight, bias, H, W, n_strips, strips_per_row, delta, coords_in, org, \
+                                                        coords_out, flow_out)
   if (C == 128) {
-    flow_head_tail_kernel<4><<<grid, 256, 0, st>>>(x, weight, bias, H, W, n_strips, strips_per_row, delta, coords_in, org,
-                                                   coords_out, flow_out);
+    if (x_f16) NND_FHT(4, 1); else NND_FHT(4, 0);
   } else if (C == 256) {
-    flow_head_tail_kernel<8><<<grid, 256, 0, st>>>(x, weight, bias, H, W, n_strips, strips_per_row, delta, coords_in, org,
-                                                   coords_out, flow_out);
+    if (x_f16) NND_FHT(8, 1); else NND_FHT(8, 0);
   } else {
-    flow_head_tail_kernel<16><<<grid, 256, 0, st>>>(x, weight, bias, H, W, n_strips, strips_per_row, delta, coords_in, org,
-                                                    coords_out, flow_out);
+    if (x_f16) NND_FHT(16, 1); else NND_FHT(16, 0);
   }
+#undef NND_FHT
   return check_launch("flow_head_tail_kernel");
 }
 

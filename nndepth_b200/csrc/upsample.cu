@@ -72,8 +72,10 @@ convex_upsample_kernel(const float* __restrict__ flow, const float* __restrict__
 // Half a warp per coarse pixel: the pixel's 9*64 logits are 2304 contiguous bytes; lane = (pixel of the pair,
 // sub-row i, column quad) reads 16 bytes per neighbour k (a warp load covers 2 x 256 contiguous bytes) and
 // writes four outputs as one 16-byte store.
+// MASK_F16: the logits are IEEE fp16 (the mask head run as fp16 convolutions); a pixel's row is then 1152 bytes.
+template <int MASK_F16>
 __global__ void __launch_bounds__(256)
-convex_upsample_nhwc8_kernel(const float* __restrict__ flow, const float* __restrict__ mask, const float* __restrict__ mask_bias,
+convex_upsample_nhwc8_kernel(const float* __restrict__ flow, const void* __restrict__ mask_, const float* __restrict__ mask_bias,
                              int H, int W, long long n_pix, float mask_scale, float* __restrict__ out) {
   constexpr int RATE = 8;
   const int lane = threadIdx.x & 31;
@@ -89,12 +91,16 @@ convex_upsample_nhwc8_kernel(const float* __restrict__ flow, const float* __rest
     const long long p = pix - n * hw;
     const int h = static_cast<int>(p / W), w = static_cast<int>(p - static_cast<long long>(h) * W);
     const float* fl = flow + n * hw;
-    const float4* mp = reinterpret_cast<const float4*>(mask + pix * (9 * RATE * RATE) + i * RATE + 4 * jq);
+    const long long quad0 = (pix * (9 * RATE * RATE) + i * RATE + 4 * jq) / 4;   // index in units of 4 logits
     float4 x[9];
     float nb[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-      x[k] = __ldcs(mp + k * (RATE * RATE / 4));
+      if (MASK_F16) {
+        x[k] = unpack_h4(__ldcs(reinterpret_cast<const uint2*>(mask_) + quad0 + k * (RATE * RATE / 4)));
+      } else {
+        x[k] = __ldcs(reinterpret_cast<const float4*>(mask_) + quad0 + k * (RATE * RATE / 4));
+      }
       const int hh = h + k / 3 - 1, ww = w + k % 3 - 1;
       nb[k] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __fmul_rn(8.0f, __ldg(fl + static_cast<long long>(hh) * W + ww)) : 0.f;
     }
@@ -133,8 +139,8 @@ convex_upsample_nhwc8_kernel(const float* __restrict__ flow, const float* __rest
 
 extern "C" {
 
-nnd_status nnd_convex_upsample(const float* flow, const float* mask, const float* mask_bias, int N, int H, int W, int rate,
-                               float mask_scale, int mask_channels_last, float* out, nnd_stream_t stream_) {
+nnd_status nnd_convex_upsample(const float* flow, const void* mask, const float* mask_bias, int N, int H, int W, int rate,
+                               float mask_scale, int mask_layout, float* out, nnd_stream_t stream_) {
   using namespace nnd;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   NND_REQUIRE(flow && mask && out, "convex_upsample: null pointer");
@@ -143,23 +149,30 @@ nnd_status nnd_convex_upsample(const float* flow, const float* mask, const float
   NND_REQUIRE(rate == 2 || rate == 4 || rate == 8, "convex_upsample: rate %d unsupported (2, 4, 8)", rate);
   NND_REQUIRE(rate % 4 != 0 || aligned16(out), "convex_upsample: output must be 16-byte aligned");
   const long long hw = static_cast<long long>(H) * W;
-  if (mask_channels_last) {
+  NND_REQUIRE(mask_layout >= 0 && mask_layout <= 2,
+              "convex_upsample: mask_layout %d is not 0 (fp32 NCHW), 1 (fp32 channels-last) or 2 (fp16 channels-last)", mask_layout);
+  if (mask_layout != 0) {
     NND_REQUIRE(rate == 8, "convex_upsample: the channels-last mask path is built for rate 8 (got %d)", rate);
     NND_REQUIRE(aligned16(mask) && aligned16(out) && (!mask_bias || aligned16(mask_bias)),
                 "convex_upsample: mask, bias and output must be 16-byte aligned");
     const long long n_pix = hw * N;
     const long long want = (n_pix + 15) / 16, cap = static_cast<long long>(sm_count()) * 8;
-    convex_upsample_nhwc8_kernel<<<static_cast<unsigned>(want < cap ? want : cap), 256, 0, stream>>>(flow, mask, mask_bias, H, W,
-                                                                                              n_pix, mask_scale, out);
+    const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
+    if (mask_layout == 2) {
+      convex_upsample_nhwc8_kernel<1><<<grid, 256, 0, stream>>>(flow, mask, mask_bias, H, W, n_pix, mask_scale, out);
+    } else {
+      convex_upsample_nhwc8_kernel<0><<<grid, 256, 0, stream>>>(flow, mask, mask_bias, H, W, n_pix, mask_scale, out);
+    }
     return check_launch("convex_upsample_nhwc8_kernel");
   }
   dim3 grid(static_cast<unsigned>((hw + 31) / 32), N);
+  const float* fmask = reinterpret_cast<const float*>(mask);
   if (rate == 8) {
-    convex_upsample_kernel<8><<<grid, dim3(32, 8), 0, stream>>>(flow, mask, mask_bias, H, W, mask_scale, out);
+    convex_upsample_kernel<8><<<grid, dim3(32, 8), 0, stream>>>(flow, fmask, mask_bias, H, W, mask_scale, out);
   } else if (rate == 4) {
-    convex_upsample_kernel<4><<<grid, dim3(32, 4), 0, stream>>>(flow, mask, mask_bias, H, W, mask_scale, out);
+    convex_upsample_kernel<4><<<grid, dim3(32, 4), 0, stream>>>(flow, fmask, mask_bias, H, W, mask_scale, out);
   } else {
-    convex_upsample_kernel<2><<<grid, dim3(32, 2), 0, stream>>>(flow, mask, mask_bias, H, W, mask_scale, out);
+    convex_upsample_kernel<2><<<grid, dim3(32, 2), 0, stream>>>(flow, fmask, mask_bias, H, W, mask_scale, out);
   }
   return check_launch("convex_upsample_kernel");
 }

@@ -81,8 +81,27 @@ def _is_nhwc(t):
     return t.dim() == 4 and t.permute(0, 2, 3, 1).is_contiguous()
 
 
-def _small_kernels_ok(t):
-    return t.is_cuda and t.dtype == torch.float32 and not torch.is_grad_enabled()
+def _small_kernels_ok(t, half_ok=False):
+    return t.is_cuda and (t.dtype == torch.float32 or (half_ok and t.dtype == torch.float16)) and not torch.is_grad_enabled()
+
+
+def half_conv_params(conv):
+    """``(weight, bias)`` of a convolution as channels-last fp16 (cached per weight version): fp16 carries TF32's
+    10-bit mantissa, so this is the precision the TF32 path gives the weights, at twice the tensor-core rate."""
+    key = (conv.weight._version, None if conv.bias is None else conv.bias._version, conv.weight.device)
+    cache = getattr(conv, "_f16_params", None)
+    if cache is None or cache[0] != key:
+        w = conv.weight.detach().clamp(-65504.0, 65504.0).half().contiguous(memory_format=torch.channels_last)
+        b = None if conv.bias is None else conv.bias.detach().clamp(-65504.0, 65504.0).half().contiguous()
+        cache = (key, (w, b))
+        conv._f16_params = cache
+    return cache[1]
+
+
+def conv_relu_f16(conv, x16):
+    """``relu(conv(x))`` as cuDNN's fused fp16 convolution (fp32 accumulation) on a channels-last fp16 ``x``."""
+    w, b = half_conv_params(conv)
+    return torch.cudnn_convolution_relu(x16, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
 
 
 def flow_conv7x7_relu(conv, flow):
@@ -113,7 +132,7 @@ def flow_head_tail(conv, x, coords=None, org=None):
     channels-last ``x``, as one fp32 kernel.  With ``coords`` / ``org`` it also performs the loop's update
     (raft_stereo/model.py:132-134) and returns ``(coords + delta, coords + delta - org)``; otherwise ``delta``.
     Returns ``None`` when the shape is not the kernel's (the caller then uses cuDNN)."""
-    if not (_small_kernels_ok(x) and conv.out_channels == 1 and conv.in_channels in (128, 256, 512) and _is_nhwc(x)
+    if not (_small_kernels_ok(x, half_ok=True) and conv.out_channels == 1 and conv.in_channels in (128, 256, 512) and _is_nhwc(x)
             and conv.kernel_size == (3, 3) and conv.padding == (1, 1) and conv.stride == (1, 1)
             and conv.dilation == (1, 1) and conv.groups == 1):
         return None
@@ -129,13 +148,15 @@ def flow_head_tail(conv, x, coords=None, org=None):
     with torch.cuda.device(x.device):
         if coords is None:
             delta = torch.empty(N, 1, H, W, dtype=torch.float32, device=x.device)
-            _lib.check(lib.nnd_flow_head_tail(_lib.ptr(x), _lib.ptr(weight), _lib.ptr(bias) if bias is not None else None, N, C,
+            _lib.check(lib.nnd_flow_head_tail(_lib.ptr(x), int(x.dtype == torch.float16), _lib.ptr(weight),
+                                              _lib.ptr(bias) if bias is not None else None, N, C,
                                               H, W, _lib.ptr(delta), None, None, None, None, _lib.stream_ptr(x)),
                        "nnd_flow_head_tail")
             return delta
         coords, org = coords.contiguous(), org.contiguous()
         new_coords, new_flow = torch.empty_like(coords), torch.empty_like(coords)
-        _lib.check(lib.nnd_flow_head_tail(_lib.ptr(x), _lib.ptr(weight), _lib.ptr(bias) if bias is not None else None, N, C, H,
+        _lib.check(lib.nnd_flow_head_tail(_lib.ptr(x), int(x.dtype == torch.float16), _lib.ptr(weight),
+                                          _lib.ptr(bias) if bias is not None else None, N, C, H,
                                           W, None, _lib.ptr(coords), _lib.ptr(org), _lib.ptr(new_coords), _lib.ptr(new_flow),
                                           _lib.stream_ptr(x)), "nnd_flow_head_tail")
     return new_coords, new_flow
@@ -367,6 +388,7 @@ class FusedGRURun:
         self._lib = _lib
         self.gru = gru
         self.half = bool(half)      # fp16 staging buffer / weights / pre-activations (csrc/gru_fused.cu, fp16 variant)
+        self.fp16_heads = bool(getattr(gru, "fp16_heads", True))
         h0, inp = h0.float(), inp.float()
         N, ch, H, W = h0.shape
         self.N, self.ch, self.H, self.W = N, ch, H, W
@@ -378,6 +400,9 @@ class FusedGRURun:
                              device=h0.device).contiguous(memory_format=cl)
         self.h = torch.empty(N, ch, H, W, dtype=torch.float32, device=h0.device).contiguous(memory_format=cl)
         self.z = torch.empty_like(self.h)
+        # dense channels-last fp16 copy of the hidden state for the heads (fp16 form only), refreshed by every step
+        self.h16 = (torch.empty(N, ch, H, W, dtype=torch.float16, device=h0.device).contiguous(memory_format=cl)
+                    if self.half and self.fp16_heads else None)
         self.h.copy_(h0)
         self._stage(h0, 0)
         self._stage(inp, ch)
@@ -437,8 +462,9 @@ class FusedGRURun:
                 lib.check(lib.load().nnd_gru_gate_r_f16(zr.data_ptr(), lib.ptr(bzr), lib.ptr(self.h), pixels, self.ch,
                                                         lib.ptr(self.z), self.S.data_ptr(), self.ctot, st), "nnd_gru_gate_r_f16")
                 q = F.conv2d(self.S, wq, None, padding=pad).contiguous(memory_format=cl)
+                h16 = self.h16.data_ptr() if (self.h16 is not None and tag == "2") else None
                 lib.check(lib.load().nnd_gru_gate_h_f16(q.data_ptr(), lib.ptr(bq), lib.ptr(self.z), pixels, self.ch,
-                                                        lib.ptr(self.h), self.S.data_ptr(), self.ctot, None, st),
+                                                        lib.ptr(self.h), self.S.data_ptr(), self.ctot, h16, st),
                           "nnd_gru_gate_h_f16")
         return self.h
 
@@ -497,11 +523,11 @@ class FlowHead(nn.Module):
 
     def forward(self, x, coords=None, org=None):
         """``delta``; with ``coords`` / ``org`` and the fused tail available: ``(coords + delta, coords + delta - org)``."""
-        hidden = conv_relu(self.conv1, x)
+        hidden = conv_relu_f16(self.conv1, x) if x.dtype == torch.float16 else conv_relu(self.conv1, x)
         fused = flow_head_tail(self.conv2, hidden, coords, org)
         if fused is not None:
             return fused
-        delta = conv_plain(self.conv2, hidden)
+        delta = conv_plain(self.conv2, hidden.float())
         return delta if coords is None else (coords + delta, coords + delta - org)
 
 
@@ -532,6 +558,13 @@ class BasicUpdateBlock(nn.Module):
         else:
             motion = self.encoder(flow, corr, cor1=cor1)
             net = self.gru(net, torch.cat((inp, motion), dim=1))
+        net16 = getattr(gru_run, "h16", None) if (gru_run is not None and raw_mask and coords is not None) else None
+        if net16 is not None:
+            # fp16 recurrence: the heads read the fp16 copy of the new hidden state and run as fp16 convolutions too
+            # (same operand mantissa as TF32, twice the rate); the logits stay fp16 for the fused upsampling kernel
+            hidden = conv_relu_f16(self.mask[0], net16)
+            mask = F.conv2d(hidden, half_conv_params(self.mask[2])[0], None, self.mask[2].stride, self.mask[2].padding)
+            return net, mask, self.flow_head(net16, coords, org)
         hidden = conv_relu(self.mask[0], net)
         if raw_mask:
             # bias-free logits: the fused upsampling kernel adds self.mask[2].bias and applies the 0.25 itself

@@ -17,7 +17,9 @@ def convex_upsample(flow, mask, rate=8, mask_scale=1.0, mask_bias=None):
     """
     flow = _lib.as_cuda_f32(flow, "flow")
     # a channels-last mask (what cuDNN returns for a channels-last hidden state) is consumed as it lies
-    nhwc = (rate == 8 and isinstance(mask, torch.Tensor) and mask.is_cuda and mask.dtype == torch.float32 and mask.dim() == 4
+    # (fp32, or fp16 when the mask head ran as fp16 convolutions)
+    nhwc = (rate == 8 and isinstance(mask, torch.Tensor) and mask.is_cuda and mask.dtype in (torch.float32, torch.float16)
+            and mask.dim() == 4
             and mask.shape[1] > 1 and not mask.is_contiguous() and mask.is_contiguous(memory_format=torch.channels_last)
             and not (torch.is_grad_enabled() and mask.requires_grad))
     mask = mask.detach() if nhwc else _lib.as_cuda_f32(mask, "mask")
@@ -35,7 +37,8 @@ def convex_upsample(flow, mask, rate=8, mask_scale=1.0, mask_bias=None):
         _lib.check(
             _lib.load().nnd_convex_upsample(_lib.ptr(flow), _lib.ptr(mask), _lib.ptr(mask_bias) if mask_bias is not None else None,
                                             N, H, W, int(rate), float(mask_scale),
-                                            1 if nhwc else 0, _lib.ptr(out), _lib.stream_ptr(flow)),
+                                            (2 if mask.dtype == torch.float16 else 1) if nhwc else 0, _lib.ptr(out),
+                                            _lib.stream_ptr(flow)),
             "nnd_convex_upsample",
         )
     return out

@@ -50,6 +50,21 @@ def test_flow_head_tail(shape, bias):
     assert torch.equal(new_flow, (coords + delta) - org)
 
 
+@pytest.mark.parametrize("C", [128, 256])
+def test_flow_head_tail_fp16_input(C):
+    """fp16 channels-last input (the flow head's first convolution run in fp16): exact conversion, fp32 arithmetic."""
+    from nndepth_b200.raft_stereo import flow_head_tail
+    torch.manual_seed(2)
+    conv = torch.nn.Conv2d(C, 1, 3, padding=1).cuda()
+    x16 = torch.randn(2, C, 7, 19, device="cuda").half().contiguous(memory_format=torch.channels_last)
+    with torch.no_grad(), torch.backends.cudnn.flags(allow_tf32=False):
+        ref = conv(x16.float())
+        delta = flow_head_tail(conv, x16)
+        same = flow_head_tail(conv, x16.float())
+    assert torch.equal(delta, same)
+    torch.testing.assert_close(delta, ref, rtol=1e-5, atol=1e-5 * ref.abs().max().item())
+
+
 def test_flow_head_tail_declines_other_shapes():
     from nndepth_b200.raft_stereo import flow_head_tail
     x = torch.randn(1, 128, 4, 4, device="cuda").contiguous(memory_format=torch.channels_last)

@@ -43,6 +43,23 @@ def test_matches_reference_chain(shape, rate):
     assert torch.equal(nb.convex_upsample(flow, mask, rate, mask_scale=0.25), nb.convex_upsample(flow, 0.25 * mask, rate))
 
 
+@pytest.mark.parametrize("shape", [(2, 6, 10), (1, 48, 156), (1, 1, 1)])
+def test_fp16_channels_last_mask(shape):
+    """fp16 logits (mask head run as fp16 convolutions): the kernel converts exactly, so the result equals the
+    fp32 path on the same (fp16-representable) logits."""
+    import nndepth_b200 as nb
+    N, H, W = shape
+    torch.manual_seed(3)
+    flow = torch.randn(N, 1, H, W, device="cuda") * 20
+    mask16 = (torch.randn(N, 576, H, W, device="cuda") * 3).half().contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(576, device="cuda")
+    got = nb.convex_upsample(flow, mask16, 8, mask_scale=0.25, mask_bias=bias)
+    same = nb.convex_upsample(flow, mask16.float(), 8, mask_scale=0.25, mask_bias=bias)
+    assert torch.equal(got, same)
+    ref = reference_chain(flow.double(), 0.25 * (mask16.double() + bias.double().view(1, -1, 1, 1)), 8).float()
+    assert (got - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item())
+
+
 def test_convexity_and_constant_field():
     """A convex combination of a constant field is that constant (times rate), whatever the mask."""
     import nndepth_b200 as nb
