@@ -220,14 +220,18 @@ nnd_status nnd_convex_upsample(const float* flow, const void* mask, const float*
 /* Single-flow-channel convolutions of the update block (stereo: flow_channel = 1), fp32 FFMA.
  *   nnd_flow_conv7x7_relu: relu(convf1(flow)), BasicMotionEncoder blocks/update_block.py:53,60.
  *     flow (N,1,H,W); weight_t (49, c_out) = the (c_out,1,7,7) filter bank transposed (tap-major); bias (c_out);
- *     out channels-last (N,H,W,c_out); padding 3.
+ *     out channels-last (N,H,W,c_out), fp32 or (out_f16 != 0) IEEE fp16; padding 3.
  *   nnd_flow_head_tail: FlowHead.conv2 blocks/update_block.py:23,36 on a channels-last x (N,H,W,C) (fp32, or IEEE fp16
  *     when x_f16), C in
  *     {128, 256, 512}; weight (1,C,3,3); bias 1 float or NULL; delta (N,1,H,W) or NULL.  With coords_in the
  *     refinement-loop update raft_stereo/model.py:132-134 is fused: coords_out = coords_in + delta and, if
  *     flow_out, flow_out = coords_out - org (all (N,1,H,W); coords_out may alias coords_in). */
 nnd_status nnd_flow_conv7x7_relu(const float* flow, const float* weight_t, const float* bias, int N, int H, int W,
-                                 int c_out, float* out, nnd_stream_t stream);
+                                 int c_out, void* out, int out_f16, nnd_stream_t stream);
+/* torch.cat([a, b], dim=1) of two channels-last maps (blocks/update_block.py:62) converted to IEEE fp16 on the way:
+ * a (pixels, c_a), b (pixels, c_b), each fp32 or (x_f16 != 0) fp16 -> out (pixels, c_a + c_b) fp16; c_a, c_b % 4 == 0. */
+nnd_status nnd_nhwc_cat_f16(const void* a, int a_f16, int c_a, const void* b, int b_f16, int c_b, long long pixels,
+                            void* out, nnd_stream_t stream);
 nnd_status nnd_flow_head_tail(const void* x, int x_f16, const float* weight, const float* bias, int N, int C, int H,
                               int W, float* delta, const float* coords_in, const float* org, float* coords_out,
                               float* flow_out, nnd_stream_t stream);

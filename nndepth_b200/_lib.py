@@ -41,7 +41,8 @@ SIGNATURES = {
     "nnd_gev_squeeze_soft_argmin": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "nnd_agcl_offset": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "nnd_agcl_iter": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
-    "nnd_flow_conv7x7_relu": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "nnd_flow_conv7x7_relu": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _I, _P]),
+    "nnd_nhwc_cat_f16": (_I, [_P, _I, _I, _P, _I, _I, ctypes.c_longlong, _P, _P]),
     "nnd_flow_head_tail": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "nnd_gru_stage_f16": (_I, [_P, _I, _I, _I, ctypes.c_longlong, _P, _I, _I, _P]),
     "nnd_gru_gate_r_f16": (_I, [_P, _P, _P, ctypes.c_longlong, _I, _P, _P, _I, _P]),

@@ -16,9 +16,10 @@ namespace nnd {
 constexpr int F7_PX = 8;  // consecutive x positions per thread (share every weight load)
 
 // block = (Cout/4 lanes-of-4-channels, rows of 8-pixel strips); weight_t = the filter bank as [tap][Cout]
+template <int OUT_F16>
 __global__ void __launch_bounds__(256)
 flow_conv7x7_relu_kernel(const float* __restrict__ flow, const float* __restrict__ weight_t, const float* __restrict__ bias,
-                         int H, int W, int cout, long long n_strips, int strips_per_row, float* __restrict__ out) {
+                         int H, int W, int cout, long long n_strips, int strips_per_row, void* __restrict__ out) {
   extern __shared__ float4 w_sm[];  // [49][cout / 4]
   const int c4n = cout >> 2;
   for (int i = threadIdx.x; i < 49 * c4n; i += blockDim.x) w_sm[i] = __ldg(reinterpret_cast<const float4*>(weight_t) + i);
@@ -57,12 +58,16 @@ flow_conv7x7_relu_kernel(const float* __restrict__ flow, const float* __restrict
         }
       }
     }
-    float4* dst = reinterpret_cast<float4*>(out) + (row * W + x0) * c4n + c4;
+    const long long q0 = (row * W + x0) * c4n + c4;   // index in units of 4 channels
 #pragma unroll
     for (int p = 0; p < F7_PX; ++p) {
       if (x0 + p < W) {
-        dst[static_cast<long long>(p) * c4n] = make_float4(fmaxf(acc[p].x, 0.f), fmaxf(acc[p].y, 0.f),
-                                                           fmaxf(acc[p].z, 0.f), fmaxf(acc[p].w, 0.f));
+        const float4 v = make_float4(fmaxf(acc[p].x, 0.f), fmaxf(acc[p].y, 0.f), fmaxf(acc[p].z, 0.f), fmaxf(acc[p].w, 0.f));
+        if (OUT_F16) {
+          reinterpret_cast<uint2*>(out)[q0 + static_cast<long long>(p) * c4n] = pack_h4(v);
+        } else {
+          reinterpret_cast<float4*>(out)[q0 + static_cast<long long>(p) * c4n] = v;
+        }
       }
     }
   }
@@ -147,12 +152,44 @@ flow_head_tail_kernel(const void* __restrict__ x_, const float* __restrict__ wei
   }
 }
 
+// channels-last concatenation with conversion to fp16: out[p] = [a[p] (Ca) | b[p] (Cb)], each source fp32 or fp16.
+// One thread = 4 channels of one pixel.
+__global__ void __launch_bounds__(256)
+nhwc_cat_f16_kernel(const void* __restrict__ a, int a_f16, int ca4, const void* __restrict__ b, int b_f16, int cb4,
+                    long long total4, uint2* __restrict__ out) {
+  const int ct4 = ca4 + cb4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = i / ct4;
+    const int c4 = static_cast<int>(i - p * ct4);
+    const bool from_a = c4 < ca4;
+    const void* src = from_a ? a : b;
+    const long long idx = from_a ? p * ca4 + c4 : p * cb4 + (c4 - ca4);
+    const int f16 = from_a ? a_f16 : b_f16;
+    out[i] = f16 ? __ldg(reinterpret_cast<const uint2*>(src) + idx) : pack_h4(__ldg(reinterpret_cast<const float4*>(src) + idx));
+  }
+}
+
 }  // namespace nnd
 
 extern "C" {
 
+nnd_status nnd_nhwc_cat_f16(const void* a, int a_f16, int c_a, const void* b, int b_f16, int c_b, long long pixels, void* out,
+                            nnd_stream_t stream) {
+  using namespace nnd;
+  NND_REQUIRE(a && b && out, "nhwc_cat_f16: null pointer");
+  NND_REQUIRE(pixels > 0 && c_a > 0 && c_b > 0 && c_a % 4 == 0 && c_b % 4 == 0,
+              "nhwc_cat_f16: channel counts must be positive multiples of 4");
+  NND_REQUIRE(aligned16(a) && aligned16(b) && aligned16(out), "nhwc_cat_f16: tensors must be 16-byte aligned");
+  const long long total4 = pixels * ((c_a + c_b) / 4);
+  const long long want = (total4 + 255) / 256, cap = static_cast<long long>(sm_count()) * 16;
+  nhwc_cat_f16_kernel<<<static_cast<unsigned>(want < cap ? want : cap), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      a, a_f16, c_a / 4, b, b_f16, c_b / 4, total4, reinterpret_cast<uint2*>(out));
+  return check_launch("nhwc_cat_f16_kernel");
+}
+
 nnd_status nnd_flow_conv7x7_relu(const float* flow, const float* weight_t, const float* bias, int N, int H, int W,
-                                 int c_out, float* out, nnd_stream_t stream) {
+                                 int c_out, void* out, int out_f16, nnd_stream_t stream) {
   using namespace nnd;
   NND_REQUIRE(flow && weight_t && bias && out, "flow_conv7x7_relu: null pointer");
   NND_REQUIRE(N > 0 && H > 0 && W > 0, "flow_conv7x7_relu: N, H, W must be positive");
@@ -167,8 +204,12 @@ nnd_status nnd_flow_conv7x7_relu(const float* flow, const float* weight_t, const
   const long long cap = static_cast<long long>(sm_count()) * 2;  // persistent: the 49 x c_out weights are staged per block
   const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
   const size_t smem = static_cast<size_t>(49) * c_out * sizeof(float);
-  flow_conv7x7_relu_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(flow, weight_t, bias, H, W, c_out,
-                                                                                        n_strips, strips_per_row, out);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (out_f16) {
+    flow_conv7x7_relu_kernel<1><<<grid, 256, smem, st>>>(flow, weight_t, bias, H, W, c_out, n_strips, strips_per_row, out);
+  } else {
+    flow_conv7x7_relu_kernel<0><<<grid, 256, smem, st>>>(flow, weight_t, bias, H, W, c_out, n_strips, strips_per_row, out);
+  }
   return check_launch("flow_conv7x7_relu_kernel");
 }
 

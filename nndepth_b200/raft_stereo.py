@@ -104,13 +104,14 @@ def conv_relu_f16(conv, x16):
     return torch.cudnn_convolution_relu(x16, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
 
 
-def flow_conv7x7_relu(conv, flow):
+def flow_conv7x7_relu(conv, flow, half=False):
     """``relu(conv(flow))`` for the one-channel 7x7 ``convf1`` (reference blocks/update_block.py:53,60) as one fp32
-    kernel writing channels-last; anything else goes to cuDNN."""
+    kernel writing channels-last (``half``: rounded to fp16 on the way out); anything else goes to cuDNN."""
     if not (_small_kernels_ok(flow) and flow.shape[1] == 1 and conv.kernel_size == (7, 7) and conv.padding == (3, 3)
             and conv.stride == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1 and conv.bias is not None
             and conv.out_channels % 4 == 0 and 256 % (conv.out_channels // 4) == 0):
-        return conv_relu(conv, flow)
+        out = conv_relu(conv, flow)
+        return out.half().contiguous(memory_format=torch.channels_last) if half else out
     from . import _lib
     N, _, H, W = flow.shape
     flow = flow.contiguous()
@@ -119,11 +120,26 @@ def flow_conv7x7_relu(conv, flow):
         cache = (conv.weight._version, conv.weight.detach().reshape(conv.out_channels, 49).t().contiguous())
         conv._tap_major_weight = cache
     weight = cache[1]                                # (49, Cout)
-    out = torch.empty(N, H, W, conv.out_channels, dtype=torch.float32, device=flow.device)
+    out = torch.empty(N, H, W, conv.out_channels, dtype=torch.float16 if half else torch.float32, device=flow.device)
     with torch.cuda.device(flow.device):
         _lib.check(_lib.load().nnd_flow_conv7x7_relu(_lib.ptr(flow), _lib.ptr(weight), _lib.ptr(conv.bias.detach()), N, H, W,
-                                                     conv.out_channels, _lib.ptr(out), _lib.stream_ptr(flow)),
+                                                     conv.out_channels, _lib.ptr(out), int(half), _lib.stream_ptr(flow)),
                    "nnd_flow_conv7x7_relu")
+    return out.permute(0, 3, 1, 2)
+
+
+def nhwc_cat_f16(a, b):
+    """``torch.cat([a, b], 1)`` of two channels-last maps (fp32 or fp16 each) as one channels-last fp16 tensor."""
+    from . import _lib
+    N, Ca, H, W = a.shape
+    Cb = b.shape[1]
+    if not (_is_nhwc(a) and _is_nhwc(b) and Ca % 4 == 0 and Cb % 4 == 0 and a.is_cuda):
+        return torch.cat([a.half(), b.half()], 1).contiguous(memory_format=torch.channels_last)
+    out = torch.empty(N, H, W, Ca + Cb, dtype=torch.float16, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.load().nnd_nhwc_cat_f16(_lib.ptr(a), int(a.dtype == torch.float16), Ca, _lib.ptr(b),
+                                                int(b.dtype == torch.float16), Cb, N * H * W, _lib.ptr(out), _lib.stream_ptr(a)),
+                   "nnd_nhwc_cat_f16")
     return out.permute(0, 3, 1, 2)
 
 
@@ -481,12 +497,20 @@ class BasicMotionEncoder(nn.Module):
         self.conv = nn.Conv2d(64 + 192, hidden_dim - flow_channel, 3, padding=1)
         self.channels_last = False      # set by the engine together with channels-last weights
 
-    def forward(self, flow, corr, cor1=None, split_flow=False):
-        """``cor1``: ``relu(convc1(corr))`` already computed by the fused lookup kernel (then ``corr`` is unused)."""
+    def forward(self, flow, corr, cor1=None, split_flow=False, half=False):
+        """``cor1``: ``relu(convc1(corr))`` already computed by the fused lookup kernel (then ``corr`` is unused).
+        ``half`` (with ``split_flow``): the flow branch and the last convolution run as fp16 convolutions and the
+        motion features come back fp16 (they are rounded to fp16 for the recurrence anyway); ``convc2`` stays TF32
+        (tools/exp_epe_fp16_dense.py: it is the one convolution here whose fp16 form moves the disparity)."""
         if cor1 is not None and self.channels_last:
             # the rest of the encoder then stays channels-last: cuDNN's tensor-core kernels need no layout conversion
             cor1 = cor1.contiguous(memory_format=torch.channels_last)
         cor = conv_relu(self.convc2, cor1 if cor1 is not None else conv_relu(self.convc1, corr))
+        if half and split_flow and self.channels_last:
+            flo = conv_relu_f16(self.convf2, flow_conv7x7_relu(self.convf1, flow, half=True))
+            w, b = self._padded_conv(half=True)
+            return torch.cudnn_convolution_relu(nhwc_cat_f16(cor, flo), w, b, self.conv.stride, self.conv.padding,
+                                                self.conv.dilation, 1), flow
         flo = conv_relu(self.convf2, flow_conv7x7_relu(self.convf1, flow) if self.channels_last
                         else conv_relu(self.convf1, flow))
         x = torch.cat([cor, flo], dim=1)
@@ -499,10 +523,19 @@ class BasicMotionEncoder(nn.Module):
         out = conv_relu(self.conv, x)
         return torch.cat([out, flow], dim=1)
 
-    def _padded_conv(self):
+    def _padded_conv(self, half=False):
         """``self.conv`` with zero filters appended up to ``hidden_dim`` output channels (cached per weight version)."""
         conv = self.conv
         key = (conv.weight._version, conv.bias._version, conv.weight.device, torch.backends.cudnn.allow_tf32)
+        if half:
+            cache = getattr(self, "_pad_cache16", None)
+            if cache is None or cache[0] != key:
+                w, b = half_conv_params(conv)
+                extra = self.convf1.weight.shape[1]
+                w = torch.cat([w, w.new_zeros(extra, *w.shape[1:])], 0).contiguous(memory_format=torch.channels_last)
+                cache = (key, (w, torch.cat([b, b.new_zeros(extra)], 0).contiguous()))
+                self._pad_cache16 = cache
+            return cache[1]
         cache = getattr(self, "_pad_cache", None)
         if cache is None or cache[0] != key:
             w = inference_weight(conv).detach()
@@ -552,7 +585,7 @@ class BasicUpdateBlock(nn.Module):
         (the loop's update, fused into the flow head's last convolution) instead of ``delta``."""
         if gru_run is not None:
             split = flow.is_cuda and not torch.is_grad_enabled() and hasattr(torch, "cudnn_convolution_relu")
-            motion = self.encoder(flow, corr, cor1=cor1, split_flow=split)
+            motion = self.encoder(flow, corr, cor1=cor1, split_flow=split, half=split and getattr(gru_run, "half", False))
             # fused channels-last weight-split recurrence; `net` lives in the runner
             net = gru_run.step(*motion) if split else gru_run.step(motion)
         else:

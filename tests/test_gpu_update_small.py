@@ -21,6 +21,23 @@ def test_flow_conv7x7_relu(shape, cout):
     assert (got == 0).any() and (got > 0).any()
 
 
+def test_flow_conv7x7_fp16_output_and_cat():
+    from nndepth_b200.raft_stereo import flow_conv7x7_relu, nhwc_cat_f16
+    torch.manual_seed(4)
+    conv = torch.nn.Conv2d(1, 128, 7, padding=3).cuda()
+    flow = torch.randn(2, 1, 9, 21, device="cuda") * 5
+    with torch.no_grad():
+        f32 = flow_conv7x7_relu(conv, flow)
+        f16 = flow_conv7x7_relu(conv, flow, half=True)
+        assert f16.dtype == torch.float16 and torch.equal(f16, f32.half())
+        a = torch.randn(2, 192, 9, 21, device="cuda").contiguous(memory_format=torch.channels_last)
+        b = torch.randn(2, 64, 9, 21, device="cuda").half().contiguous(memory_format=torch.channels_last)
+        cat = nhwc_cat_f16(a, b)
+        assert cat.dtype == torch.float16 and cat.permute(0, 2, 3, 1).is_contiguous()
+        assert torch.equal(cat, torch.cat([a.half(), b], 1))
+        assert torch.equal(nhwc_cat_f16(b, a), torch.cat([b, a.half()], 1))
+
+
 def test_flow_conv7x7_falls_back_for_two_flow_channels():
     from nndepth_b200.raft_stereo import flow_conv7x7_relu
     conv = torch.nn.Conv2d(2, 128, 7, padding=3).cuda()
