@@ -94,12 +94,13 @@ nnd_status nnd_corr1d_lookup(const float* const* level, const int* width, const 
  *   weight (L*9, c_out) row-major (= convc1.weight[:, :, 0, 0] transposed), bias (c_out) or NULL, relu 0/1;
  *   out (B, c_out, H, W).  radius 4, 4 levels.  precision NND_PREC_FP32: fp32 FFMA; NND_PREC_TF32
  *   (c_out <= 256): mma.sync TF32 with both operands rounded to nearest, weights resident in registers --
- *   the precision class cuDNN gives this layer under allow_tf32.  out_channels_last != 0 (tensor-core path
- *   only): out is written (B, H, W, c_out), the layout cuDNN's tensor-core convolutions consume directly. */
+ *   the precision class cuDNN gives this layer under allow_tf32.  out_layout (tensor-core path only for
+ *   1 and 2): 0 = fp32 (B, c_out, H, W); 1 = fp32 written (B, H, W, c_out), the layout cuDNN's tensor-core
+ *   convolutions consume directly; 2 = that layout rounded to IEEE fp16 (the consumer runs as an fp16 convolution). */
 nnd_status nnd_corr1d_lookup_conv1x1(const float* const* level, const int* width, const int* pitch,
                                      const float* coords, int B, int H, int W1, int num_levels, int radius,
                                      const float* weight, const float* bias, int c_out, int relu, int precision,
-                                     int out_channels_last, float* out, nnd_stream_t stream);
+                                     int out_layout, void* out, nnd_stream_t stream);
 
 /* Backward passes for training (the reference path is differentiable; trainers: raft_trainer.py:242-259).
  *   nnd_corr1d_lookup_backward: gradient of the lookup w.r.t. the pyramid.  grad_out (B, L*(2r+1), H, W1);

@@ -264,7 +264,8 @@ class CorrBlock1D:
         weight = _lib.as_cuda_f32(weight, "weight")
         return weight.reshape(weight.shape[0], -1).t().contiguous()
 
-    def lookup_conv1x1(self, coords, weight, bias=None, relu=True, weight_t=None, precision="fp32", channels_last=False):
+    def lookup_conv1x1(self, coords, weight, bias=None, relu=True, weight_t=None, precision="fp32", channels_last=False,
+                       half=False):
         """``relu(conv1x1(self(coords)))`` in one launch; the ``(B, L*(2r+1), H, W)`` lookup never reaches HBM.
 
         Fuses the lookup with the motion encoder's first layer (reference ``blocks/update_block.py:51,58``:
@@ -278,6 +279,8 @@ class CorrBlock1D:
             raise ValueError(f"precision must be 'fp32' or 'tf32', got {precision!r}")
         if channels_last and precision != "tf32":
             raise ValueError("channels_last output is provided by the tensor-core ('tf32') path only")
+        if half and not channels_last:
+            raise ValueError("half=True (fp16 output) needs channels_last=True")
         B, H, W1, _ = self._shape
         coords = _check_coords(coords, B, H, W1)
         T = 2 * self.radius + 1
@@ -291,8 +294,11 @@ class CorrBlock1D:
         c_out = weight.shape[1]
         if channels_last and c_out <= 256:
             # (B, H, W, c_out) in memory, returned with NCHW shape and channels-last strides
-            out = torch.empty(B, H, W1, c_out, dtype=torch.float32, device=coords.device).permute(0, 3, 1, 2)
+            out = torch.empty(B, H, W1, c_out, dtype=torch.float16 if half else torch.float32,
+                              device=coords.device).permute(0, 3, 1, 2)
         else:
+            if half:
+                raise ValueError("fp16 output needs c_out <= 256 (tensor-core path)")
             channels_last = False
             out = torch.empty(B, c_out, H, W1, dtype=torch.float32, device=coords.device)
         with torch.cuda.device(coords.device):
@@ -302,7 +308,8 @@ class CorrBlock1D:
                                                       _lib.ptr(weight), _lib.ptr(bias) if bias is not None else None,
                                                       c_out, 1 if relu else 0,
                                                       _lib.PREC_TF32 if precision == "tf32" else _lib.PREC_FP32,
-                                                      1 if channels_last else 0, _lib.ptr(out), _lib.stream_ptr(coords)),
+                                                      (2 if half else 1) if channels_last else 0, _lib.ptr(out),
+                                                      _lib.stream_ptr(coords)),
                 "nnd_corr1d_lookup_conv1x1",
             )
         return out

@@ -627,6 +627,19 @@ corr1d_lookup_conv1x1_tc_kernel(const __grid_constant__ LookupArgs a, const floa
         const int r0 = 64 * lvl + 16 * mt + gid, r1 = r0 + 8;
         if (out_nhwc) {
           // channels-last output (B, H*W, c_out): eight lanes (gid) write 32 contiguous bytes of one pixel
+          if (out_nhwc == 2) {
+            // the same, rounded to IEEE fp16 (the consumer runs as an fp16 convolution): 16 bytes per pixel per store
+            uint16_t* o16 = reinterpret_cast<uint16_t*>(a.out) + (static_cast<long long>(b) * a.hw + rem0 + px) * c_out;
+            if (rem0 + px < a.hw) {
+              if (r0 < c_out) o16[r0] = static_cast<uint16_t>(pack_h2(d[0], 0.f));
+              if (r1 < c_out) o16[r1] = static_cast<uint16_t>(pack_h2(d[2], 0.f));
+            }
+            if (rem0 + px + 1 < a.hw) {
+              if (r0 < c_out) o16[c_out + r0] = static_cast<uint16_t>(pack_h2(d[1], 0.f));
+              if (r1 < c_out) o16[c_out + r1] = static_cast<uint16_t>(pack_h2(d[3], 0.f));
+            }
+            continue;
+          }
           float* o = a.out + (static_cast<long long>(b) * a.hw + rem0 + px) * c_out;
           if (rem0 + px < a.hw) {
             if (r0 < c_out) o[r0] = d[0];
@@ -1007,8 +1020,8 @@ nnd_status nnd_gev_lookup(const float* const* level_feat, const float* const* le
 
 nnd_status nnd_corr1d_lookup_conv1x1(const float* const* level, const int* width, const int* pitch, const float* coords,
                                      int B, int H, int W1, int num_levels, int radius, const float* weight,
-                                     const float* bias, int c_out, int relu, int precision, int out_channels_last,
-                                     float* out, nnd_stream_t stream) {
+                                     const float* bias, int c_out, int relu, int precision, int out_layout,
+                                     void* out, nnd_stream_t stream) {
   using namespace nnd;
   NND_REQUIRE(level && width && pitch && coords && weight && out, "lookup_conv1x1: null pointer argument");
   NND_REQUIRE(B > 0 && H > 0 && W1 > 0 && c_out > 0, "lookup_conv1x1: B, H, W1, c_out must be positive");
@@ -1028,7 +1041,7 @@ nnd_status nnd_corr1d_lookup_conv1x1(const float* const* level, const int* width
     vec = vec && (pitch[l] % 4 == 0) && aligned16(level[l]);
   }
   a.coords = coords;
-  a.out = out;
+  a.out = reinterpret_cast<float*>(out);
   a.hw = H * W1;
   a.G = 1;
   a.n_src = 1;
@@ -1036,6 +1049,8 @@ nnd_status nnd_corr1d_lookup_conv1x1(const float* const* level, const int* width
   a.radius = radius;
   a.vec = vec ? 1 : 0;
   NND_REQUIRE(precision == NND_PREC_FP32 || precision == NND_PREC_TF32, "lookup_conv1x1: unknown precision %d", precision);
+  NND_REQUIRE(out_layout >= 0 && out_layout <= 2,
+              "lookup_conv1x1: out_layout %d is not 0 (fp32 NCHW), 1 (fp32 channels-last) or 2 (fp16 channels-last)", out_layout);
   const long long n_groups_all = static_cast<long long>(B) * ((a.hw + 31) / 32);
   if (precision == NND_PREC_TF32 && c_out <= 256) {
     // tensor-core path: weights live in registers, shared memory holds only the lookup tiles
@@ -1043,10 +1058,10 @@ nnd_status nnd_corr1d_lookup_conv1x1(const float* const* level, const int* width
     const long long resident = static_cast<long long>(sm_count()) * 3;   // 128 threads x ~150 registers
     dim3 grid_tc(static_cast<unsigned>(n_groups_all < resident ? n_groups_all : resident));
     corr1d_lookup_conv1x1_tc_kernel<9><<<grid_tc, dim3(32, 4), smem_tc, reinterpret_cast<cudaStream_t>(stream)>>>(
-        a, weight, bias, c_out, relu ? 1 : 0, out_channels_last ? 1 : 0, n_groups_all);
+        a, weight, bias, c_out, relu ? 1 : 0, out_layout, n_groups_all);
     return check_launch("corr1d_lookup_conv1x1_tc_kernel");
   }
-  NND_REQUIRE(!out_channels_last, "lookup_conv1x1: the channels-last output is provided by the tensor-core path only");
+  NND_REQUIRE(out_layout == 0, "lookup_conv1x1: the channels-last outputs are provided by the tensor-core path only");
   const int K = num_levels * 9;
   const size_t c_pad = (static_cast<size_t>(c_out) + 3) & ~static_cast<size_t>(3);
   const size_t smem = (c_pad * K + c_pad + static_cast<size_t>(K) * 32 + static_cast<size_t>(num_levels) * 32 * 17) *

@@ -500,12 +500,15 @@ class BasicMotionEncoder(nn.Module):
     def forward(self, flow, corr, cor1=None, split_flow=False, half=False):
         """``cor1``: ``relu(convc1(corr))`` already computed by the fused lookup kernel (then ``corr`` is unused).
         ``half`` (with ``split_flow``): the flow branch and the last convolution run as fp16 convolutions and the
-        motion features come back fp16 (they are rounded to fp16 for the recurrence anyway); ``convc2`` stays TF32
-        (tools/exp_epe_fp16_dense.py: it is the one convolution here whose fp16 form moves the disparity)."""
+        motion features come back fp16 (they are rounded to fp16 for the recurrence anyway); ``convc2`` follows the
+        dtype of ``cor1``."""
         if cor1 is not None and self.channels_last:
             # the rest of the encoder then stays channels-last: cuDNN's tensor-core kernels need no layout conversion
             cor1 = cor1.contiguous(memory_format=torch.channels_last)
-        cor = conv_relu(self.convc2, cor1 if cor1 is not None else conv_relu(self.convc1, corr))
+        if cor1 is not None and cor1.dtype == torch.float16:
+            cor = conv_relu_f16(self.convc2, cor1)      # the fused lookup kernel wrote fp16 for the fp16 iteration
+        else:
+            cor = conv_relu(self.convc2, cor1 if cor1 is not None else conv_relu(self.convc1, corr))
         if half and split_flow and self.channels_last:
             flo = conv_relu_f16(self.convf2, flow_conv7x7_relu(self.convf1, flow, half=True))
             w, b = self._padded_conv(half=True)
@@ -714,9 +717,10 @@ class RAFTStereo(nn.Module):
                 if it == 0:
                     conv1_wt = corr.prepare_conv1x1_weight(conv1.weight)    # k-major copy, once per forward
                 tf32 = bool(torch.backends.cudnn.allow_tf32)
+                cl_out = tf32 and self.update_block.encoder.channels_last
                 sampled, cor1 = None, corr.lookup_conv1x1(coords1, None, conv1.bias, relu=True, weight_t=conv1_wt,
-                                                          precision="tf32" if tf32 else "fp32",
-                                                          channels_last=tf32 and self.update_block.encoder.channels_last)
+                                                          precision="tf32" if tf32 else "fp32", channels_last=cl_out,
+                                                          half=cl_out and getattr(gru_run, "half", False))
             else:
                 sampled, cor1 = corr(coords1), None
             # on the GPU the convex upsampling is one fused kernel (softmax + unfold + weighted sum + pixel

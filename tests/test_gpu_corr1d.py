@@ -386,6 +386,11 @@ def test_lookup_conv1x1_fusion(shape, c_out):
     assert (tc - ref).abs().max().item() <= 1e-3 * scale
     assert tc_cl.shape == tc.shape and tc_cl.is_contiguous(memory_format=torch.channels_last)
     assert torch.equal(tc_cl, tc)                       # same numbers, channels-last memory
+    if c_out <= 256:
+        with torch.no_grad():
+            tc_h = blk.lookup_conv1x1(coords, conv.weight, conv.bias, relu=True, precision="tf32", channels_last=True, half=True)
+        assert tc_h.dtype == torch.float16 and tc_h.permute(0, 2, 3, 1).is_contiguous()
+        assert torch.equal(tc_h, tc.half())             # the same values rounded to nearest fp16
 
 
 def test_randomised_lookup_sweep_bit_exact():
