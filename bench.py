@@ -202,7 +202,8 @@ def time_lookup_kernel(device, reps=40):
 
 def time_step_kernels(device, peak):
     """Isolated CUDA-event timings (L2 flushed) of this repo's other kernels at the bench shape, with their
-    algorithmic bytes: the per-step launch mix is 1 build, 32 fused lookups, 32 upsamplings, 34 stagings, 64 + 64 gates."""
+    algorithmic bytes: the per-step launch mix is 1 build, 32 fused lookups, 32 upsamplings, 34 + 32 stagings, 64 + 64
+    gates, 32 one-channel 7x7 convolutions, 32 flow-head tails and (fp16 iteration) 32 concatenations."""
     import nndepth_b200 as nb
     from nndepth_b200 import _lib
     B, H, W, ch, cx = PAIRS_PER_GPU, 48, 156, 128, 256
@@ -255,6 +256,29 @@ def time_step_kernels(device, peak):
         lambda: _lib.check(lib.nnd_gru_stage(_lib.ptr(motion), 1, B, ch, H * W, _lib.ptr(S), ctot, ch + ch, sp), "stage"))
     add("convex_upsample_nhwc8_kernel", 32, px * 576 * 4 + px * 64 * 4 + px * 4,
         lambda: nb.convex_upsample(flow, mask, 8, 0.25, mbias))
+    # ---- the fp16 iteration (dense_precision mixed16, the default): same kernels on fp16 staging / pre-activations ----
+    from nndepth_b200.raft_stereo import flow_conv7x7_relu, flow_head_tail, nhwc_cat_f16
+    S16 = torch.empty(B, ctot, H, W, device=device, dtype=torch.float16).contiguous(memory_format=cl)
+    zr16, q16, motion16, mask16 = zr.half(), q.half(), motion.half(), mask.half()
+    h16 = torch.empty(B, ch, H, W, device=device, dtype=torch.float16).contiguous(memory_format=cl)
+    add("gru_gate_r_f16_kernel", 64, px * (2 * ch * 2 + ch * 4 + ch * 4 + 2 * ch * 2),
+        lambda: _lib.check(lib.nnd_gru_gate_r_f16(_lib.ptr(zr16), _lib.ptr(bias), _lib.ptr(h), px, ch, _lib.ptr(z), _lib.ptr(S16), ctot, sp), "gate_r16"))
+    add("gru_gate_h_f16_kernel", 64, px * (ch * 2 + ch * 4 + ch * 4 + ch * 4 + 2 * ch * 2 + ch * 2),
+        lambda: _lib.check(lib.nnd_gru_gate_h_f16(_lib.ptr(q16), _lib.ptr(bias), _lib.ptr(z), px, ch, _lib.ptr(h), _lib.ptr(S16), ctot,
+                                                  _lib.ptr(h16), sp), "gate_h16"))
+    add("gru_stage_cl_f16_kernel (fp16 motion features)", 32, px * (ch * 2 + 2 * ch * 2),
+        lambda: _lib.check(lib.nnd_gru_stage_f16(_lib.ptr(motion16), 2, B, ch, H * W, _lib.ptr(S16), ctot, ch + ch, sp), "stage16"))
+    add("convex_upsample_nhwc8_kernel<fp16 mask>", 32, px * 576 * 2 + px * 64 * 4 + px * 4,
+        lambda: nb.convex_upsample(flow, mask16, 8, 0.25, mbias))
+    conv7 = torch.nn.Conv2d(1, 128, 7, padding=3).to(device)
+    head2 = torch.nn.Conv2d(128, 1, 3, padding=1).to(device)
+    coords = torch.randn(B, 1, H, W, device=device)
+    cor = torch.randn(B, 192, H, W, device=device).contiguous(memory_format=cl)
+    flo16 = torch.randn(B, 64, H, W, device=device).half().contiguous(memory_format=cl)
+    with torch.no_grad():
+        add("flow_conv7x7_relu_kernel<fp16 out>", 32, px * 4 + px * 128 * 2, lambda: flow_conv7x7_relu(conv7, flow, half=True))
+        add("flow_head_tail_kernel<4, fp16 in>", 32, px * 128 * 2 + px * 16, lambda: flow_head_tail(head2, h16, coords, coords))
+        add("nhwc_cat_f16_kernel", 32, px * (192 * 4 + 64 * 2 + 256 * 2), lambda: nhwc_cat_f16(cor, flo16))
     return rows
 
 
@@ -374,6 +398,9 @@ def run_ours(args):
     step_device()
     launches_per_step = _lib.launch_count() - before
     engine.model.corr_fn = TimedCorr
+    # queue ~60 ms of GPU spin first: the host then runs ahead of the device for the whole eager step, so the event
+    # pairs bracket the kernels back to back on the stream instead of the host's launch gaps
+    torch.cuda._sleep(int(1.2e8))
     step_device()
     torch.cuda.synchronize(device)
     in_step_us = sorted(e0.elapsed_time(e1) * 1e3 for e0, e1 in lookup_events)
@@ -400,8 +427,10 @@ def run_ours(args):
         kern = time_lookup_kernel(device)
         in_step_med = in_step_us[len(in_step_us) // 2]
         fused_front = bool(getattr(engine.model, "fuse_motion_front", False))
-        # fused kernel: windows + coords in, 256 fp32 channels out (the 36-channel lookup tensor stays on chip)
-        step_bytes = kern["pixels"] * ((4 * 10 * 4 + 4) + 256 * 4) if fused_front else kern["lookup_bytes"]
+        # fused kernel: windows + coords in, 256 channels out (the 36-channel lookup tensor stays on chip); the output
+        # is fp16 when the rest of the iteration runs as fp16 convolutions (mixed16), fp32 otherwise
+        out_elem = 2 if args.dense_precision == "mixed16" else 4
+        step_bytes = kern["pixels"] * ((4 * 10 * 4 + 4) + 256 * out_elem) if fused_front else kern["lookup_bytes"]
         achieved = step_bytes / (in_step_med * 1e-6) / 1e9
         cpu = None
         if world == 1 and not args.skip_cpu_baseline:
@@ -418,10 +447,14 @@ def run_ours(args):
                                             "mixed": "ConvGRU cuDNN fp32, other convolutions cuDNN TF32",
                                             "mixed2x": "ConvGRU TF32 activations x split fp32 weights [w_hi; w_lo] on tensor cores, "
                                                        "other convolutions cuDNN TF32",
-                                            "mixed16": "ConvGRU fp16 activations x split weights [w_hi16; w_lo16] on tensor cores "
-                                                       "(fp32 accumulate, fp32 gates and state), other convolutions cuDNN TF32"}[args.dense_precision]),
-            "parity": {"final_epe_px_vs_reference": {"fp32": 0.00016, "mixed": 0.0021, "mixed2x": 0.0031, "mixed16": 0.0031, "tf32": 0.0147}[args.dense_precision],
-                       "bar_px": 0.01, "source": "tests/test_gpu_raft_model.py::test_kitti_32_iterations, tools/exp_epe_modules.py"},
+                                            "mixed16": "refinement iteration on fp16 tensor-core products with fp32 accumulation "
+                                                       "(same 10-bit operand mantissa as TF32): ConvGRU fp16 activations x split weights "
+                                                       "[w_hi16; w_lo16], fp32 gates and state; motion encoder and heads fp16; "
+                                                       "encoders cuDNN TF32; one-channel flow convolutions fp32"}[args.dense_precision]),
+            "parity": {"final_epe_px_vs_reference": {"fp32": 0.00016, "mixed": 0.0021, "mixed2x": 0.0031, "mixed16": 0.0024, "tf32": 0.0147}[args.dense_precision],
+                       "bar_px": 0.01, "source": "tests/test_gpu_raft_model.py::test_engine_bench_configuration_stays_inside_the_bar, tools/exp_epe_modules.py",
+                       "other_weight_seeds": "0.003 - 0.009 px against the same model run in fp32, for every mode that keeps "
+                                             "the encoders in TF32 (DESIGN.md 4b)"},
             "data": "synthetic", "config": workload_config(world), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": 2 * host_l.numel() * 4, "d2h_bytes_per_step": PAIRS_PER_GPU * IMAGE_HW[0] * IMAGE_HW[1] * 4,
@@ -432,9 +465,10 @@ def run_ours(args):
                                    + ", 32 launches per step",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(fused_front), "peak_source": peak_src,
-                         "how": "CUDA events around each of the 32 per-iteration lookups of one eager step (median); "
-                                "algorithmic bytes = (164 B window+coords in + 1024 B out) x 59904 pixels for the fused "
-                                "kernel, 308 B/pixel for the stand-alone lookup",
+                         "how": "CUDA events around each of the 32 per-iteration lookups of one eager step that runs behind a "
+                                "queued GPU spin, so the host's launch gaps stay out of the brackets (median); "
+                                "algorithmic bytes = (164 B window+coords in + 256 x %d B out) x 59904 pixels for the fused "
+                                "kernel, 308 B/pixel for the stand-alone lookup" % (out_elem if fused_front else 4),
                          "us_per_launch_in_step": in_step_med,
                          "algorithmic_bytes_per_launch": step_bytes,
                          "standalone_lookup": {"us_per_launch_l2_flushed": kern["lookup_ms_l2_flushed"] * 1e3,

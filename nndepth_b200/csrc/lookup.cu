@@ -628,15 +628,27 @@ corr1d_lookup_conv1x1_tc_kernel(const __grid_constant__ LookupArgs a, const floa
         if (out_nhwc) {
           // channels-last output (B, H*W, c_out): eight lanes (gid) write 32 contiguous bytes of one pixel
           if (out_nhwc == 2) {
-            // the same, rounded to IEEE fp16 (the consumer runs as an fp16 convolution): 16 bytes per pixel per store
-            uint16_t* o16 = reinterpret_cast<uint16_t*>(a.out) + (static_cast<long long>(b) * a.hw + rem0 + px) * c_out;
-            if (rem0 + px < a.hw) {
-              if (r0 < c_out) o16[r0] = static_cast<uint16_t>(pack_h2(d[0], 0.f));
-              if (r1 < c_out) o16[r1] = static_cast<uint16_t>(pack_h2(d[2], 0.f));
-            }
-            if (rem0 + px + 1 < a.hw) {
-              if (r0 < c_out) o16[c_out + r0] = static_cast<uint16_t>(pack_h2(d[1], 0.f));
-              if (r1 < c_out) o16[c_out + r1] = static_cast<uint16_t>(pack_h2(d[3], 0.f));
+            // the same, rounded to IEEE fp16 (the consumer runs as an fp16 convolution).  Lanes gid and gid^1 hold
+            // adjacent channels of the same two pixels: one exchange each way and the even lane owns channel pairs
+            // (r, r+1) of pixel px, the odd lane those of pixel px+1 -> 4-byte stores, 16 contiguous bytes per pixel
+            const bool odd = gid & 1;
+            const float s0 = __shfl_xor_sync(0xffffffffu, odd ? d[0] : d[1], 4);
+            const float s1 = __shfl_xor_sync(0xffffffffu, odd ? d[2] : d[3], 4);
+            const uint32_t lo = odd ? pack_h2(s0, d[1]) : pack_h2(d[0], s0);   // channels (r0e, r0e + 1)
+            const uint32_t hi = odd ? pack_h2(s1, d[3]) : pack_h2(d[2], s1);   // channels (r0e + 8, r0e + 9)
+            const int re = r0 - (odd ? 1 : 0);                                  // even channel of the pair
+            const long long pix = rem0 + px + (odd ? 1 : 0);
+            if (pix < a.hw) {
+              uint16_t* o16 = reinterpret_cast<uint16_t*>(a.out) + (static_cast<long long>(b) * a.hw + pix) * c_out;
+              if ((c_out & 1) == 0) {
+                if (re < c_out) *reinterpret_cast<uint32_t*>(o16 + re) = lo;
+                if (re + 8 < c_out) *reinterpret_cast<uint32_t*>(o16 + re + 8) = hi;
+              } else {
+                if (re < c_out) o16[re] = static_cast<uint16_t>(lo);
+                if (re + 1 < c_out) o16[re + 1] = static_cast<uint16_t>(lo >> 16);
+                if (re + 8 < c_out) o16[re + 8] = static_cast<uint16_t>(hi);
+                if (re + 9 < c_out) o16[re + 9] = static_cast<uint16_t>(hi >> 16);
+              }
             }
             continue;
           }
