@@ -312,15 +312,18 @@ static int soft_argmin_slices(long long units, int D) {
 // cv_squeezer (Conv3d(8 -> 1, 3x3x3, padding 1), igev_stereo/model.py:65,144-145) fused with the soft-argmin
 // (model.py:92-95,146) on the interleaved level-0 geometry volume [b][h][w][d][g].
 //
-// Thread = one input disparity plane d' with its 8 groups in registers (two 16-byte loads per neighbour
-// pixel, lanes run along d' = contiguous memory).  Instead of gathering the three d-taps of an output, every
-// thread SCATTERS: it accumulates, per output pixel of its SQ_TH x SQ_TW register tile, the three partial
-// sums A_kd[d'] = sum_{g,kh,kw} W[g,kd,kh,kw] * x[g,d',h+kh-1,w+kw-1]; the 216 weights are immediate
-// constant-bank operands of the FFMAs (static indices after unrolling), so a neighbour pixel costs 2 loads
-// for up to 96 FFMAs.  out[d] = bias + A_0[d-1] + A_1[d] + A_2[d+1] is assembled through shared memory in
-// a fixed order (deterministic) and one warp per pixel runs the online softmax-expectation over d.
+// Thread = one input disparity plane d' with its 8 groups in registers (one 32-byte load per pixel, lanes run
+// along d' = contiguous memory).  Instead of gathering, every thread SCATTERS its plane: along d into the three
+// partial sums A_kd[d'] = sum_{g,kh,kw} W[g,kd,kh,kw] * x[g,d',..] (combined across lanes only once per output
+// row, through shared memory: out[d] = bias + A_0[d-1] + A_1[d] + A_2[d+1], fixed order, deterministic), and
+// along h into the three output rows an input row touches.  A warp-set (ceil(D/32) warps) marches down a
+// strip of SQ_TW pixel columns: each input row is loaded ONCE (halo only in w: SQ_TW + 2 pixels), feeds
+// 3 rows x SQ_TW pixels x 3 d-taps = 36 register accumulators with 864 FFMAs, then the finished row's cost is
+// assembled and one warp per pixel runs the softmax-expectation.  The 216 weights are uniform constant-bank
+// operands (two LDCU.128 per tap serve SQ_TW pixels).  SQ_NS strips per CTA keep the warp count a multiple
+// of four at D = 160 (20 warps) and share the halo pixels through L1.
 // ---------------------------------------------------------------------------------------------------
-constexpr int SQ_TH = 2, SQ_TW = 4, SQ_PX = SQ_TH * SQ_TW;
+constexpr int SQ_TW = 4;
 // Conv3d weight (1, 8, 3, 3, 3) repacked [kd][kh][kw][g] (the eight group weights of a tap = two uniform
 // 16-byte constant loads), bias in [54].x.  Filled stream-ordered from g_squeeze_stage by the ABI call.
 __constant__ float4 c_squeeze[56];
@@ -332,43 +335,65 @@ __global__ void squeeze_pack_kernel(const float* __restrict__ weight, const floa
   if (i >= 216 && i < 224) g_squeeze_stage[i] = (i == 216 && bias) ? bias[0] : 0.f;
 }
 
-template <int MAX_THREADS>
-__global__ void __launch_bounds__(MAX_THREADS)
-gev_squeeze_soft_argmin_kernel(const float* __restrict__ geo, int D, int H, int W, float* __restrict__ out,
-                               float* __restrict__ cost_out) {
-  extern __shared__ float sq_part[];  // [3][SQ_PX][D + 2], index d' + 1; [0] and [D + 1] stay zero
+struct F8 {
+  float v[8];
+};
+__device__ __forceinline__ F8 ldg_f8(const float* p) {  // 32-byte aligned, read-only path, one LDG.256
+  F8 r;
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+               : "l"(p));
+  return r;
+}
+
+// grid = (w-tiles, h-segments, B); block = n_strips * n_chunks warps; seg_rows output rows per CTA
+__global__ void __launch_bounds__(640)
+gev_squeeze_soft_argmin_kernel(const float* __restrict__ geo, int D, int H, int W, int n_chunks, int seg_rows,
+                               float* __restrict__ out, float* __restrict__ cost_out) {
+  extern __shared__ float sq_part[];  // [2 buffers][strip][3 kd][SQ_TW][D + 2], index d' + 1; [0] and [D + 1] stay zero
   const int Dp = D + 2;
-  const int w0 = blockIdx.x * SQ_TW, h0 = blockIdx.y * SQ_TH, b = blockIdx.z;
-  const int dq = threadIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int strip = warp / n_chunks, chunk = warp - strip * n_chunks;
+  const int n_strips = (blockDim.x >> 5) / n_chunks;
+  const int dq = chunk * 32 + lane;
+  const int w0 = (blockIdx.x * n_strips + strip) * SQ_TW;
+  const int b = blockIdx.z;
+  const int hs = blockIdx.y * seg_rows, he = min(H, hs + seg_rows);
+  const bool live = dq < D && w0 < W;
+  const int strip_floats = 3 * SQ_TW * Dp;
+  float* my = sq_part + strip * strip_floats;           // buffer 0 of this strip; buffer 1 at + n_strips * strip_floats
+  const int buf_stride = n_strips * strip_floats;
 
-  float acc[SQ_PX][3];
-#pragma unroll
-  for (int p = 0; p < SQ_PX; ++p) acc[p][0] = acc[p][1] = acc[p][2] = 0.f;
+  for (int i = threadIdx.x; i < 2 * n_strips * 3 * SQ_TW; i += blockDim.x) {
+    sq_part[i * Dp] = 0.f;
+    sq_part[i * Dp + D + 1] = 0.f;
+  }
 
-  if (dq < D) {
+  // accumulators of the output rows h' - 1 (prev), h' (cur), h' + 1 (next) while input row h' is processed
+  float acc[3][SQ_TW][3];
 #pragma unroll
-    for (int nh = 0; nh < SQ_TH + 2; ++nh) {
-      // one row of neighbour pixels in registers: every weight vector then feeds SQ_TW output pixels
-      const int hh = h0 + nh - 1;
-      const bool row_ok = hh >= 0 && hh < H;
-      const float4* row = reinterpret_cast<const float4*>(
-          geo + (((static_cast<long long>(b) * H + (row_ok ? hh : 0)) * W) * D + dq) * 8);
-      float4 v0[SQ_TW + 2], v1[SQ_TW + 2];
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int p = 0; p < SQ_TW; ++p) acc[r][p][0] = acc[r][p][1] = acc[r][p][2] = 0.f;
+
+  const float bias = c_squeeze[54].x;
+  for (int hh = hs - 1; hh <= he; ++hh) {     // input rows; rows outside the image are zero padding
+    if (live && hh >= 0 && hh < H) {
+      const float* row = geo + (((static_cast<long long>(b) * H + hh) * W) * D + dq) * 8;
+      F8 x[SQ_TW + 2];
 #pragma unroll
       for (int nw = 0; nw < SQ_TW + 2; ++nw) {
         const int ww = w0 + nw - 1;
-        v0[nw] = v1[nw] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row_ok && ww >= 0 && ww < W) {
-          const float4* src = row + static_cast<long long>(ww) * D * 2;
-          v0[nw] = __ldg(src);
-          v1[nw] = __ldg(src + 1);
+        if (ww >= 0 && ww < W) {
+          x[nw] = ldg_f8(row + static_cast<long long>(ww) * D * 8);
+        } else {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) x[nw].v[g] = 0.f;
         }
       }
+      // input row hh reaches output row hh + 1 - kh: acc[2 - kh]  (kh = 0 -> next, 1 -> cur, 2 -> prev)
 #pragma unroll
-      for (int oh = 0; oh < SQ_TH; ++oh) {
-        const int kh = nh - oh;
-        if (kh < 0 || kh > 2) continue;
+      for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
 #pragma unroll
@@ -376,63 +401,72 @@ gev_squeeze_soft_argmin_kernel(const float* __restrict__ geo, int D, int H, int 
             const float4 wa = c_squeeze[((kd * 3 + kh) * 3 + kw) * 2], wb = c_squeeze[((kd * 3 + kh) * 3 + kw) * 2 + 1];
 #pragma unroll
             for (int ow = 0; ow < SQ_TW; ++ow) {
-              const int nw = ow + kw;
-              float a = acc[oh * SQ_TW + ow][kd];
-              a = fmaf(v0[nw].x, wa.x, a);
-              a = fmaf(v0[nw].y, wa.y, a);
-              a = fmaf(v0[nw].z, wa.z, a);
-              a = fmaf(v0[nw].w, wa.w, a);
-              a = fmaf(v1[nw].x, wb.x, a);
-              a = fmaf(v1[nw].y, wb.y, a);
-              a = fmaf(v1[nw].z, wb.z, a);
-              a = fmaf(v1[nw].w, wb.w, a);
-              acc[oh * SQ_TW + ow][kd] = a;
+              const F8& v = x[ow + kw];
+              float a = acc[2 - kh][ow][kd];
+              a = fmaf(v.v[0], wa.x, a);
+              a = fmaf(v.v[1], wa.y, a);
+              a = fmaf(v.v[2], wa.z, a);
+              a = fmaf(v.v[3], wa.w, a);
+              a = fmaf(v.v[4], wb.x, a);
+              a = fmaf(v.v[5], wb.y, a);
+              a = fmaf(v.v[6], wb.z, a);
+              a = fmaf(v.v[7], wb.w, a);
+              acc[2 - kh][ow][kd] = a;
             }
           }
         }
       }
     }
+    // output row ho = hh - 1 is complete
+    const int ho = hh - 1;
+    float* buf = my + (ho & 1) * buf_stride;
+    if (ho >= hs) {   // block-uniform
+      if (live) {
 #pragma unroll
-    for (int p = 0; p < SQ_PX; ++p) {
+        for (int p = 0; p < SQ_TW; ++p)
 #pragma unroll
-      for (int kd = 0; kd < 3; ++kd) sq_part[(kd * SQ_PX + p) * Dp + dq + 1] = acc[p][kd];
-    }
-  }
-  if (threadIdx.x < 3 * SQ_PX) {
-    sq_part[threadIdx.x * Dp] = 0.f;
-    sq_part[threadIdx.x * Dp + D + 1] = 0.f;
-  }
-  __syncthreads();
-
-  const float bias = c_squeeze[54].x;
-  for (int p = warp; p < SQ_PX; p += n_warps) {
-    const int hh = h0 + p / SQ_TW, ww = w0 + p % SQ_TW;
-    if (hh >= H || ww >= W) continue;  // warp-uniform
-    const float* a0 = sq_part + (0 * SQ_PX + p) * Dp;
-    const float* a1 = sq_part + (1 * SQ_PX + p) * Dp;
-    const float* a2 = sq_part + (2 * SQ_PX + p) * Dp;
-    // out[d] = bias + A_0[d' = d - 1] + A_1[d' = d] + A_2[d' = d + 1]  (kd = 0 reads d - 1, ... as Conv3d does)
-    float mx = -FLT_MAX;
-    for (int d = lane; d < D; d += 32) {
-      const float c = ((bias + a0[d]) + a1[d + 1]) + a2[d + 2];
-      if (cost_out) cost_out[((static_cast<long long>(b) * D + d) * H + hh) * W + ww] = c;
-      mx = fmaxf(mx, c * LOG2E);
-    }
+          for (int kd = 0; kd < 3; ++kd) buf[(kd * SQ_TW + p) * Dp + dq + 1] = acc[0][p][kd];
+      }
+      __syncthreads();   // one barrier per row: the buffers alternate, row ho + 2 is written after the next barrier
+      for (int p = chunk; p < SQ_TW; p += n_chunks) {
+        const int ww = w0 + p;
+        if (ww >= W) continue;  // warp-uniform
+        const float* a0 = buf + (0 * SQ_TW + p) * Dp;
+        const float* a1 = buf + (1 * SQ_TW + p) * Dp;
+        const float* a2 = buf + (2 * SQ_TW + p) * Dp;
+        // out[d] = bias + A_0[d' = d - 1] + A_1[d' = d] + A_2[d' = d + 1]  (tap kd reads plane d + kd - 1, as Conv3d does)
+        float mx = -FLT_MAX;
+        for (int d = lane; d < D; d += 32) {
+          const float c = ((bias + a0[d]) + a1[d + 1]) + a2[d + 2];
+          if (cost_out) cost_out[((static_cast<long long>(b) * D + d) * H + ho) * W + ww] = c;
+          mx = fmaxf(mx, c * LOG2E);
+        }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float s = 0.f, ws = 0.f;
-    for (int d = lane; d < D; d += 32) {
-      const float c = ((bias + a0[d]) + a1[d + 1]) + a2[d + 2];
-      const float e = ex2_fast(fmaf(c, LOG2E, -mx));
-      s += e;
-      ws = fmaf(static_cast<float>(d), e, ws);
-    }
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f, ws = 0.f;
+        for (int d = lane; d < D; d += 32) {
+          const float c = ((bias + a0[d]) + a1[d + 1]) + a2[d + 2];
+          const float e = ex2_fast(fmaf(c, LOG2E, -mx));
+          sum += e;
+          ws = fmaf(static_cast<float>(d), e, ws);
+        }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      s += __shfl_xor_sync(0xffffffffu, s, o);
-      ws += __shfl_xor_sync(0xffffffffu, ws, o);
+        for (int o = 16; o > 0; o >>= 1) {
+          sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          ws += __shfl_xor_sync(0xffffffffu, ws, o);
+        }
+        if (lane == 0) out[(static_cast<long long>(b) * H + ho) * W + ww] = -(ws / sum);
+      }
     }
-    if (lane == 0) out[(static_cast<long long>(b) * H + hh) * W + ww] = -(ws / s);
+    // rotate: prev <- cur, cur <- next, next <- 0
+#pragma unroll
+    for (int p = 0; p < SQ_TW; ++p)
+#pragma unroll
+      for (int kd = 0; kd < 3; ++kd) {
+        acc[0][p][kd] = acc[1][p][kd];
+        acc[1][p][kd] = acc[2][p][kd];
+        acc[2][p][kd] = 0.f;
+      }
   }
 }
 
@@ -529,9 +563,9 @@ nnd_status nnd_gev_squeeze_soft_argmin(const float* geo_level0, const float* wei
   NND_REQUIRE(geo_level0 && weight && out, "gev_squeeze_soft_argmin: null pointer");
   NND_REQUIRE(G == 8, "gev_squeeze_soft_argmin: the interleaved layout holds 8 groups (got %d)", G);
   NND_REQUIRE(B > 0 && D > 0 && H > 0 && W1 > 0, "gev_squeeze_soft_argmin: B, D, H, W1 must be positive");
-  NND_REQUIRE(B <= 65535 && (H + SQ_TH - 1) / SQ_TH <= 65535, "gev_squeeze_soft_argmin: B or H exceeds the grid limit");
-  NND_REQUIRE(D <= 512, "gev_squeeze_soft_argmin: D = %d exceeds 512 (one thread per disparity plane)", D);
-  NND_REQUIRE(aligned16(geo_level0), "gev_squeeze_soft_argmin: volume must be 16-byte aligned");
+  NND_REQUIRE(B <= 65535, "gev_squeeze_soft_argmin: B exceeds the grid limit");
+  NND_REQUIRE(D <= 640, "gev_squeeze_soft_argmin: D = %d exceeds 640 (one thread per disparity plane, 20 warps)", D);
+  NND_REQUIRE((reinterpret_cast<uintptr_t>(geo_level0) & 31u) == 0, "gev_squeeze_soft_argmin: volume must be 32-byte aligned");
   // weights -> constant bank, stream-ordered (no host synchronisation; capturable).  Launches on different
   // streams with DIFFERENT weights would race on the symbol; one model per process uses one squeezer.
   squeeze_pack_kernel<<<1, 224, 0, stream>>>(weight, bias);
@@ -542,14 +576,31 @@ nnd_status nnd_gev_squeeze_soft_argmin(const float* geo_level0, const float* wei
   if (e != cudaSuccess) return cuda_fail(e, "gev_squeeze_soft_argmin: staging symbol");
   e = cudaMemcpyToSymbolAsync(c_squeeze, stage, 224 * sizeof(float), 0, cudaMemcpyDeviceToDevice, stream);
   if (e != cudaSuccess) return cuda_fail(e, "gev_squeeze_soft_argmin: weight upload");
-  const int threads = ((D + 31) / 32) * 32;
-  const size_t smem = static_cast<size_t>(3) * SQ_PX * (D + 2) * sizeof(float);
-  dim3 grid((W1 + SQ_TW - 1) / SQ_TW, (H + SQ_TH - 1) / SQ_TH, B);
-  if (threads <= 256) {
-    gev_squeeze_soft_argmin_kernel<256><<<grid, threads, smem, stream>>>(geo_level0, D, H, W1, out, cost_out);
-  } else {
-    gev_squeeze_soft_argmin_kernel<512><<<grid, threads, smem, stream>>>(geo_level0, D, H, W1, out, cost_out);
+  const int n_chunks = (D + 31) / 32;
+  const int w_strips = (W1 + SQ_TW - 1) / SQ_TW;
+  int n_strips = 20 / n_chunks;                       // up to 20 warps per CTA (a multiple of four at D = 160)
+  if (n_strips < 1) n_strips = 1;
+  if (n_strips > w_strips) n_strips = w_strips;
+  const int w_tiles = (w_strips + n_strips - 1) / n_strips;
+  // h-segments: about four CTAs per SM in total; every segment re-reads two halo rows
+  const long long cols = static_cast<long long>(B) * w_tiles;
+  long long segs = (4LL * sm_count() + cols - 1) / cols;
+  if (segs < 1) segs = 1;
+  int seg_rows = static_cast<int>((H + segs - 1) / segs);
+  if (seg_rows < 8) seg_rows = H < 8 ? H : 8;
+  const int h_segs = (H + seg_rows - 1) / seg_rows;
+  NND_REQUIRE(h_segs <= 65535, "gev_squeeze_soft_argmin: H = %d exceeds the grid limit", H);
+  const int threads = n_strips * n_chunks * 32;
+  const size_t smem = static_cast<size_t>(2) * n_strips * 3 * SQ_TW * (D + 2) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t ae = cudaFuncSetAttribute(gev_squeeze_soft_argmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (ae != cudaSuccess) return cuda_fail(ae, "gev_squeeze_soft_argmin: shared-memory attribute");
+    attr_set = true;
   }
+  NND_REQUIRE(smem <= 200 * 1024, "gev_squeeze_soft_argmin: D = %d needs %zu bytes of shared memory", D, smem);
+  dim3 grid(w_tiles, h_segs, B);
+  gev_squeeze_soft_argmin_kernel<<<grid, threads, smem, stream>>>(geo_level0, D, H, W1, n_chunks, seg_rows, out, cost_out);
   return check_launch("gev_squeeze_soft_argmin_kernel");
 }
 
