@@ -368,6 +368,7 @@ gev_squeeze_soft_argmin_kernel(const float* __restrict__ geo, int D, int H, int 
     sq_part[i * Dp] = 0.f;
     sq_part[i * Dp + D + 1] = 0.f;
   }
+  __syncthreads();
 
   // accumulators of the output rows h' - 1 (prev), h' (cur), h' + 1 (next) while input row h' is processed
   float acc[3][SQ_TW][3];
@@ -427,7 +428,9 @@ gev_squeeze_soft_argmin_kernel(const float* __restrict__ geo, int D, int H, int 
 #pragma unroll
           for (int kd = 0; kd < 3; ++kd) buf[(kd * SQ_TW + p) * Dp + dq + 1] = acc[0][p][kd];
       }
-      __syncthreads();   // one barrier per row: the buffers alternate, row ho + 2 is written after the next barrier
+      // one barrier per row and per strip (the strips of a CTA are independent): the buffers alternate, row
+      // ho + 2 is written after the next barrier
+      asm volatile("bar.sync %0, %1;" ::"r"(strip + 1), "r"(n_chunks * 32) : "memory");
       for (int p = chunk; p < SQ_TW; p += n_chunks) {
         const int ww = w0 + p;
         if (ww >= W) continue;  // warp-uniform
@@ -584,7 +587,7 @@ nnd_status nnd_gev_squeeze_soft_argmin(const float* geo_level0, const float* wei
   const int w_tiles = (w_strips + n_strips - 1) / n_strips;
   // h-segments: about four CTAs per SM in total; every segment re-reads two halo rows
   const long long cols = static_cast<long long>(B) * w_tiles;
-  long long segs = (4LL * sm_count() + cols - 1) / cols;
+  long long segs = (6LL * sm_count() + cols - 1) / cols;
   if (segs < 1) segs = 1;
   int seg_rows = static_cast<int>((H + segs - 1) / segs);
   if (seg_rows < 8) seg_rows = H < 8 ? H : 8;

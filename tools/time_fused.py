@@ -22,6 +22,10 @@ print("lookup alone", timed(lambda: blk(coords)))
 wt = blk.prepare_conv1x1_weight(w)
 print("fused lookup+conv1x1+relu fp32", timed(lambda: blk.lookup_conv1x1(coords, None, b, True, weight_t=wt)))
 print("fused lookup+conv1x1+relu tf32", timed(lambda: blk.lookup_conv1x1(coords, None, b, True, weight_t=wt, precision="tf32")))
+print("fused tf32, channels-last fp32 out", timed(lambda: blk.lookup_conv1x1(coords, None, b, True, weight_t=wt, precision="tf32", channels_last=True)))
+print("fused tf32, channels-last fp16 out", timed(lambda: blk.lookup_conv1x1(coords, None, b, True, weight_t=wt, precision="tf32", channels_last=True, half=True)))
+if "--fused-only" in sys.argv:
+    sys.exit(0)
 with torch.no_grad():
     x = blk(coords)
     for tf32 in (False, True):
