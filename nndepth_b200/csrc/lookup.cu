@@ -484,7 +484,8 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
 }
 
 __device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+  // not volatile: the scheduler may interleave independent accumulation chains
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -605,6 +606,7 @@ corr1d_lookup_conv1x1_tc_kernel(const __grid_constant__ LookupArgs a, const floa
 
     // D[co][px] = sum_k W[co][k] * corr[px][k]: 4 m-tiles x 4 n-tiles (8 pixels each) per warp
     float* out_img = a.out + static_cast<long long>(b) * c_out * a.hw + rem0;
+    const bool full_tile = rem0 + 32 <= a.hw && 64 * lvl + 64 <= c_out && (c_out & 1) == 0 && (a.hw & 1) == 0;
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
       uint32_t bf[KSTEPS][2];   // b0:(k = tig, n = gid)  b1:(k = tig + 4, n = gid)
@@ -615,11 +617,69 @@ corr1d_lookup_conv1x1_tc_kernel(const __grid_constant__ LookupArgs a, const floa
         bf[ks][1] = __float_as_uint(cp[8 * ks + 4]);
       }
       const int px = 8 * nt + 2 * tig;   // my two output pixels (c0/c1 and c2/c3 columns)
+      // the four m-tiles are independent accumulation chains: k-step outermost, so consecutive MMAs never depend
+      float dd[4][4];
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt) {
-        float d[4] = {bv[mt][0], bv[mt][0], bv[mt][1], bv[mt][1]};
+        dd[mt][0] = dd[mt][1] = bv[mt][0];
+        dd[mt][2] = dd[mt][3] = bv[mt][1];
+      }
 #pragma unroll
-        for (int ks = 0; ks < KSTEPS; ++ks) mma_tf32_16x8x8(d, af[mt][ks], bf[ks][0], bf[ks][1]);
+      for (int ks = 0; ks < KSTEPS; ++ks)
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) mma_tf32_16x8x8(dd[mt], af[mt][ks], bf[ks][0], bf[ks][1]);
+      if (full_tile) {
+        // whole group inside the image and all 64 channels of this warp exist: one base pointer per n-tile, constant
+        // offsets per m-tile, no predicates
+        const long long pix0 = static_cast<long long>(b) * a.hw + rem0 + px;
+        if (out_nhwc == 2) {
+          const bool odd = gid & 1;
+          uint16_t* ob = reinterpret_cast<uint16_t*>(a.out) + (pix0 + (odd ? 1 : 0)) * c_out + 64 * lvl + (gid & ~1);
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) {
+            float (&d)[4] = dd[mt];
+            if (relu) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) d[i] = fmaxf(d[i], 0.f);
+            }
+            const float s0 = __shfl_xor_sync(0xffffffffu, odd ? d[0] : d[1], 4);
+            const float s1 = __shfl_xor_sync(0xffffffffu, odd ? d[2] : d[3], 4);
+            *reinterpret_cast<uint32_t*>(ob + 16 * mt) = odd ? pack_h2(s0, d[1]) : pack_h2(d[0], s0);
+            *reinterpret_cast<uint32_t*>(ob + 16 * mt + 8) = odd ? pack_h2(s1, d[3]) : pack_h2(d[2], s1);
+          }
+        } else if (out_nhwc == 1) {
+          float* ob = a.out + pix0 * c_out + 64 * lvl + gid;
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) {
+            float (&d)[4] = dd[mt];
+            if (relu) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) d[i] = fmaxf(d[i], 0.f);
+            }
+            ob[16 * mt] = d[0];
+            ob[16 * mt + 8] = d[2];
+            ob[c_out + 16 * mt] = d[1];
+            ob[c_out + 16 * mt + 8] = d[3];
+          }
+        } else {
+          float* ob = out_img + static_cast<long long>(64 * lvl + gid) * a.hw + px;
+          const long long hw8 = 8LL * a.hw;
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) {
+            float (&d)[4] = dd[mt];
+            if (relu) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) d[i] = fmaxf(d[i], 0.f);
+            }
+            *reinterpret_cast<float2*>(ob + (2 * mt) * hw8) = make_float2(d[0], d[1]);
+            *reinterpret_cast<float2*>(ob + (2 * mt + 1) * hw8) = make_float2(d[2], d[3]);
+          }
+        }
+        continue;
+      }
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        float (&d)[4] = dd[mt];
         if (relu) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) d[i] = fmaxf(d[i], 0.f);
