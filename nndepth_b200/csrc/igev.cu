@@ -595,13 +595,10 @@ nnd_status nnd_gev_squeeze_soft_argmin(const float* geo_level0, const float* wei
   NND_REQUIRE(h_segs <= 65535, "gev_squeeze_soft_argmin: H = %d exceeds the grid limit", H);
   const int threads = n_strips * n_chunks * 32;
   const size_t smem = static_cast<size_t>(2) * n_strips * 3 * SQ_TW * (D + 2) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t ae = cudaFuncSetAttribute(gev_squeeze_soft_argmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (ae != cudaSuccess) return cuda_fail(ae, "gev_squeeze_soft_argmin: shared-memory attribute");
-    attr_set = true;
-  }
   NND_REQUIRE(smem <= 200 * 1024, "gev_squeeze_soft_argmin: D = %d needs %zu bytes of shared memory", D, smem);
+  // per call (once per forward) rather than cached in a static: the attribute is per device
+  e = cudaFuncSetAttribute(gev_squeeze_soft_argmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return cuda_fail(e, "gev_squeeze_soft_argmin: shared-memory attribute");
   dim3 grid(w_tiles, h_segs, B);
   gev_squeeze_soft_argmin_kernel<<<grid, threads, smem, stream>>>(geo_level0, D, H, W1, n_chunks, seg_rows, out, cost_out);
   return check_launch("gev_squeeze_soft_argmin_kernel");

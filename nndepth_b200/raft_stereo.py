@@ -189,6 +189,13 @@ def fold_bn(conv, bn, tf32=False):
     return (rn_tf32(w) if tf32 else w), b.contiguous()
 
 
+def _fold_f16(conv, bn):
+    """``fold_bn`` with the folded weight / bias as channels-last fp16 (fp16 carries TF32's mantissa)."""
+    w, b = fold_bn(conv, bn, False)
+    return (w.clamp(-65504.0, 65504.0).half().contiguous(memory_format=torch.channels_last),
+            b.clamp(-65504.0, 65504.0).half().contiguous())
+
+
 def _fused_ok(x, *norms):
     """Inference on the GPU with eval-mode BatchNorm: the conv + BN (+ add) + ReLU chains run as single cuDNN calls."""
     return (x.is_cuda and not torch.is_grad_enabled() and hasattr(torch, "cudnn_convolution_relu")
@@ -218,13 +225,17 @@ class ResidualBlock(nn.Module):
         self.norm1, self.norm2, self.norm3 = (_norm(norm_fn, planes) for _ in range(3))
         self.downsample = nn.Sequential(nn.Conv2d(in_planes, planes, 1, stride=stride), self.norm3)
 
-    def _folded(self):
+    def _folded(self, half=False):
         """(w, b) of conv1+norm1, conv2+norm2, shortcut+norm3, folded once (inference)."""
-        tf32 = bool(torch.backends.cudnn.allow_tf32)
+        tf32 = "f16" if half else bool(torch.backends.cudnn.allow_tf32)
         cache = getattr(self, "_fold_cache", None)
         if cache is None or cache[0] != tf32:
-            cache = (tf32, (fold_bn(self.conv1, self.norm1, tf32), fold_bn(self.conv2, self.norm2, tf32),
-                            fold_bn(self.downsample[0], self.norm3, tf32)))
+            if half:
+                cache = (tf32, (_fold_f16(self.conv1, self.norm1), _fold_f16(self.conv2, self.norm2),
+                                _fold_f16(self.downsample[0], self.norm3)))
+            else:
+                cache = (tf32, (fold_bn(self.conv1, self.norm1, tf32), fold_bn(self.conv2, self.norm2, tf32),
+                                fold_bn(self.downsample[0], self.norm3, tf32)))
             self._fold_cache = cache
         return cache[1]
 
@@ -232,7 +243,7 @@ class ResidualBlock(nn.Module):
         if _fused_ok(x, self.norm1, self.norm2, self.norm3):
             # BatchNorm folded into the convolutions; conv + bias + ReLU and conv + bias + add + ReLU are single
             # cuDNN calls (the reference chain is conv, bias add, batch norm, clamp: four passes per layer)
-            (w1, b1), (w2, b2), (w3, b3) = self._folded()
+            (w1, b1), (w2, b2), (w3, b3) = self._folded(half=x.dtype == torch.float16)
             c1, c3 = self.conv1, self.downsample[0]
             y = torch.cudnn_convolution_relu(x, w1, b1, c1.stride, c1.padding, c1.dilation, 1)
             y = torch.cudnn_convolution_relu(y, w2, b2, self.conv2.stride, self.conv2.padding, self.conv2.dilation, 1)
@@ -271,10 +282,13 @@ class BasicEncoder(nn.Module):
         pair = isinstance(x, (tuple, list))
         if pair:
             x = torch.cat(x, dim=0)
+        half = bool(getattr(self, "half_convs", False)) and _fused_ok(x, self.norm1)
+        if half:
+            x = x.half()
         if _fused_ok(x, self.norm1):
-            tf32 = bool(torch.backends.cudnn.allow_tf32)
+            tf32 = "f16" if half else bool(torch.backends.cudnn.allow_tf32)
             if getattr(self, "_fold_cache", None) is None or self._fold_cache[0] != tf32:
-                w, b = fold_bn(self.conv1, self.norm1, tf32)
+                w, b = _fold_f16(self.conv1, self.norm1) if half else fold_bn(self.conv1, self.norm1, tf32)
                 # a fourth, all-zero input channel: with 3 channels cuDNN has no Blackwell kernel for this layer and
                 # falls back to an sm80 one (763 us at KITTI x 16 images); 4 channels are TMA-addressable
                 w = F.pad(w, (0, 0, 0, 0, 0, (-w.shape[1]) % 4))
@@ -290,7 +304,11 @@ class BasicEncoder(nn.Module):
         else:
             x = self.relu1(self.norm1(self.conv1(x)))
         x = self.layer3(self.layer2(self.layer1(x)))
-        x = conv_plain(self.conv2, x)
+        if x.dtype == torch.float16:
+            w16, b16 = half_conv_params(self.conv2)
+            x = F.conv2d(x, w16, b16, self.conv2.stride, self.conv2.padding)
+        else:
+            x = conv_plain(self.conv2, x)
         if self.dropout is not None:
             x = self.dropout(x)
         return torch.split(x, x.shape[0] // 2, dim=0) if pair else x
@@ -698,6 +716,10 @@ class RAFTStereo(nn.Module):
         gru = getattr(self.update_block, "gru", None)
         if gru is not None:
             gru.recurrence = {"mixed": "fp32", "mixed2x": "wsplit", "mixed16": "wsplit16"}.get(self.dense_precision)
+        if hasattr(self.fnet, "half_convs") or isinstance(self.fnet, BasicEncoder):
+            # mixed16 runs the (BatchNorm-folded) feature encoder as fp16 convolutions as well: the feature maps are
+            # rounded to 10 mantissa bits for the correlation volume anyway (RN_tf32(RN_fp16(x)) == RN_fp16(x))
+            self.fnet.half_convs = self.dense_precision == "mixed16" and getattr(self, "fp16_encoder", True)
         with cudnn_tf32(self.dense_precision != "fp32"):
             return self._forward(frame1, frame2, **kwargs)
 
@@ -706,7 +728,7 @@ class RAFTStereo(nn.Module):
         fnet_ds = frame1.shape[-1] // fmap1.shape[-1]
         fmap1, fmap2 = fmap1.float(), fmap2.float()
         net, inp = torch.split(cnet1, [self.hidden_dim, self.context_dim], dim=1)
-        net, inp = torch.tanh(net), F.relu(inp)
+        net, inp = torch.tanh(net.float()), F.relu(inp)
 
         corr = self.corr_fn(fmap1, fmap2, self.corr_levels, self.corr_radius)
         gru = getattr(self.update_block, "gru", None)
@@ -801,4 +823,5 @@ class BaseRAFTStereo(RAFTStereo):
 
     def forward_fnet(self, frame1, frame2):
         fmap1, fmap2 = self.fnet([frame1, frame2])
-        return fmap1, fmap2, conv_relu(self.cnet_proj[0], fmap1)
+        cnet = conv_relu_f16(self.cnet_proj[0], fmap1) if fmap1.dtype == torch.float16 else conv_relu(self.cnet_proj[0], fmap1)
+        return fmap1, fmap2, cnet
