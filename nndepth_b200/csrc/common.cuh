@@ -133,4 +133,15 @@ __device__ __forceinline__ float4 unpack_h4(const uint2 v) {
   return make_float4(a.x, a.y, b.x, b.y);
 }
 
+// ---- packed fp32 FMA (sm_100: FFMA2, two fused multiply-adds per issued instruction) -------------------
+// acc.{x,y} = fma(a.{x,y}, b.{x,y}, acc.{x,y}), each lane of the pair rounded exactly like a scalar fmaf.
+__device__ __forceinline__ void ffma2(float2& acc, const float2 a, const float2 b) {
+  unsigned long long A, B, C;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(B) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(C) : "f"(acc.x), "f"(acc.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(C) : "l"(A), "l"(B));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(C));
+}
+
 }  // namespace nnd

@@ -33,28 +33,37 @@ flow_conv7x7_relu_kernel(const float* __restrict__ flow, const float* __restrict
     const int x0 = static_cast<int>(s - row * strips_per_row) * F7_PX;
     const int y = static_cast<int>(row % H);
     const float* img = flow + (row - y) * W;   // image n
-    float4 acc[F7_PX];
+    float2 acc[F7_PX][2];   // channels (x, y) and (z, w) of each pixel: packed FFMA2 accumulators
 #pragma unroll
-    for (int p = 0; p < F7_PX; ++p) acc[p] = b4;
+    for (int p = 0; p < F7_PX; ++p) {
+      acc[p][0] = make_float2(b4.x, b4.y);
+      acc[p][1] = make_float2(b4.z, b4.w);
+    }
 #pragma unroll
     for (int ky = 0; ky < 7; ++ky) {
       const int yy = y + ky - 3;
       if (yy < 0 || yy >= H) continue;
       float f[F7_PX + 6];
+      const float* line = img + static_cast<long long>(yy) * W + x0 - 3;
+      if (x0 >= 3 && x0 + F7_PX + 3 <= W) {   // interior strip (warp-uniform): immediate offsets, no predicates
 #pragma unroll
-      for (int i = 0; i < F7_PX + 6; ++i) {
-        const int xx = x0 + i - 3;
-        f[i] = (xx >= 0 && xx < W) ? __ldg(img + static_cast<long long>(yy) * W + xx) : 0.f;
+        for (int i = 0; i < F7_PX + 6; ++i) f[i] = __ldg(line + i);
+      } else {
+#pragma unroll
+        for (int i = 0; i < F7_PX + 6; ++i) {
+          const int xx = x0 + i - 3;
+          f[i] = (xx >= 0 && xx < W) ? __ldg(line + i) : 0.f;
+        }
       }
 #pragma unroll
       for (int kx = 0; kx < 7; ++kx) {
         const float4 w4 = w_sm[(ky * 7 + kx) * c4n + c4];
+        const float2 wlo = make_float2(w4.x, w4.y), whi = make_float2(w4.z, w4.w);
 #pragma unroll
         for (int p = 0; p < F7_PX; ++p) {
-          acc[p].x = fmaf(w4.x, f[p + kx], acc[p].x);
-          acc[p].y = fmaf(w4.y, f[p + kx], acc[p].y);
-          acc[p].z = fmaf(w4.z, f[p + kx], acc[p].z);
-          acc[p].w = fmaf(w4.w, f[p + kx], acc[p].w);
+          const float2 ff = make_float2(f[p + kx], f[p + kx]);
+          ffma2(acc[p][0], wlo, ff);
+          ffma2(acc[p][1], whi, ff);
         }
       }
     }
@@ -62,7 +71,8 @@ flow_conv7x7_relu_kernel(const float* __restrict__ flow, const float* __restrict
 #pragma unroll
     for (int p = 0; p < F7_PX; ++p) {
       if (x0 + p < W) {
-        const float4 v = make_float4(fmaxf(acc[p].x, 0.f), fmaxf(acc[p].y, 0.f), fmaxf(acc[p].z, 0.f), fmaxf(acc[p].w, 0.f));
+        const float4 v = make_float4(fmaxf(acc[p][0].x, 0.f), fmaxf(acc[p][0].y, 0.f), fmaxf(acc[p][1].x, 0.f),
+                                     fmaxf(acc[p][1].y, 0.f));
         if (OUT_F16) {
           reinterpret_cast<uint2*>(out)[q0 + static_cast<long long>(p) * c4n] = pack_h4(v);
         } else {

@@ -131,6 +131,7 @@ class StereoEngine:
         self.divis_by = divis_by
         self._dev_in = {}
         self._host_out = {}
+        self._pipe, self._pipe_next, self._copy_stream, self._h2d_stream = {}, {}, None, None
 
     @torch.no_grad()
     def infer_device(self, left, right):
@@ -145,6 +146,61 @@ class StereoEngine:
         else:
             outputs = self.model(left_p, right_p)
         return padder.unpad(outputs[-1]["up_disp"])
+
+    # ---- pipelined host-to-host inference: the next pair's H2D and the previous pair's D2H overlap the forward ----
+    def _slots(self, key):
+        slots = self._pipe.get(key)
+        if slots is None:
+            slots = []
+            for _ in range(2):
+                slots.append({
+                    "dev_l": torch.empty(key, dtype=torch.float32, device=self.device),
+                    "dev_r": torch.empty(key, dtype=torch.float32, device=self.device),
+                    "dev_out": torch.empty((key[0], 1, key[2], key[3]), dtype=torch.float32, device=self.device),
+                    "host_out": torch.empty((key[0], 1, key[2], key[3]), dtype=torch.float32).pin_memory(),
+                    "h2d": torch.cuda.Event(), "consumed": torch.cuda.Event(), "out_ready": torch.cuda.Event(),
+                    "d2h": torch.cuda.Event(), "used": False})
+            self._pipe[key] = slots
+            self._pipe_next[key] = 0
+        return slots
+
+    @torch.no_grad()
+    def submit(self, left, right):
+        """Enqueue one batch of (pinned) host images; returns a ticket for ``collect``.  Copies run on their own
+        streams: with two batches in flight the H2D of batch i+1 and the D2H of batch i-1 hide behind forward i."""
+        key = tuple(left.shape)
+        slots = self._slots(key)
+        i = self._pipe_next[key]
+        self._pipe_next[key] = (i + 1) % len(slots)
+        slot = slots[i]
+        if self._copy_stream is None:
+            # one stream per direction: a D2H queued behind forward i must not hold back the H2D of batch i+1
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._h2d_stream = torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream(self.device)
+        if slot["used"]:
+            slot["d2h"].synchronize()                    # the host buffer of this slot has been read out
+            self._h2d_stream.wait_event(slot["consumed"])    # and its device inputs are no longer being read
+        with torch.cuda.stream(self._h2d_stream):
+            slot["dev_l"].copy_(left, non_blocking=True)
+            slot["dev_r"].copy_(right, non_blocking=True)
+            slot["h2d"].record(self._h2d_stream)
+        main.wait_event(slot["h2d"])
+        disp = self.infer_device(slot["dev_l"], slot["dev_r"])
+        slot["consumed"].record(main)
+        slot["dev_out"].copy_(disp)                      # the graph's static output is overwritten by the next replay
+        slot["out_ready"].record(main)
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(slot["out_ready"])
+            slot["host_out"].copy_(slot["dev_out"], non_blocking=True)
+            slot["d2h"].record(self._copy_stream)
+        slot["used"] = True
+        return slot
+
+    def collect(self, ticket):
+        """Wait for a submitted batch; the returned pinned tensor is reused two submissions later."""
+        ticket["d2h"].synchronize()
+        return ticket["host_out"]
 
     @torch.no_grad()
     def infer(self, left, right):

@@ -154,6 +154,16 @@ def test_engine_bench_configuration_stays_inside_the_bar(golden):
         assert epe(out, ref) < EPE_BAR, epe(out, ref)
     host = engine.infer(left.cpu().pin_memory(), right.cpu().pin_memory())
     assert epe(host.cuda(), ref) < EPE_BAR
+    # pipelined host-to-host path (two batches in flight on a copy stream): same numbers as the synchronous call, and
+    # a different batch in the other slot does not disturb them
+    hl, hr = left.cpu().pin_memory(), right.cpu().pin_memory()
+    t1 = engine.submit(hl, hr)
+    t2 = engine.submit(hr, hl)
+    first = engine.collect(t1).clone()
+    t3 = engine.submit(hl, hr)
+    engine.collect(t2)
+    third = engine.collect(t3).clone()
+    assert torch.equal(first, host) and torch.equal(third, host)
 
 
 @pytest.mark.parametrize("mode", ["mixed2x", "mixed16"])
