@@ -85,6 +85,17 @@ flow_conv7x7_relu_kernel(const float* __restrict__ flow, const float* __restrict
 
 constexpr int FH_PX = 8;  // output pixels per warp (a strip along x)
 
+template <int F16>
+struct QuadOf {
+  using type = float4;
+};
+template <>
+struct QuadOf<1> {
+  using type = uint2;
+};
+__device__ __forceinline__ float4 quad_to_float4(const float4 v) { return v; }
+__device__ __forceinline__ float4 quad_to_float4(const uint2 v) { return unpack_h4(v); }
+
 // x (N,H,W,C) channels-last with C = 32 * CPL: lane owns channels [lane*CPL, lane*CPL + CPL).  weight (1, C, 3, 3).
 // One warp per strip of FH_PX output pixels: the 3 x (FH_PX + 2) input pixels are read once each.
 template <int CPL, int X_F16>
@@ -93,14 +104,24 @@ flow_head_tail_kernel(const void* __restrict__ x_, const float* __restrict__ wei
                       int H, int W, long long n_strips, int strips_per_row, float* __restrict__ delta,
                       const float* __restrict__ coords_in, const float* __restrict__ org, float* __restrict__ coords_out,
                       float* __restrict__ flow_out) {
+  using RawQuad = typename QuadOf<X_F16>::type;
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   constexpr int C = 32 * CPL;
+  // weights: read coalesced once per block, handed to the lanes through shared memory laid out [tap][j][lane]
+  // (a lane's 9 * CPL values straight from global memory are 9 * CPL scattered 4-byte reads per warp: 283 MB of
+  // L2 traffic per launch at KITTI shapes for 16 MB of activations)
+  __shared__ float w_s[9 * CPL * 32];
+  for (int idx = threadIdx.x; idx < 9 * C; idx += blockDim.x) {
+    const int c = idx / 9, t = idx - 9 * c;
+    w_s[(t * CPL + (c % CPL)) * 32 + c / CPL] = __ldg(weight + idx);
+  }
+  __syncthreads();
   float w[9][CPL];
 #pragma unroll
   for (int t = 0; t < 9; ++t)
 #pragma unroll
-    for (int j = 0; j < CPL; ++j) w[t][j] = __ldg(weight + (lane * CPL + j) * 9 + t);
+    for (int j = 0; j < CPL; ++j) w[t][j] = w_s[(t * CPL + j) * 32 + lane];
   const float b = bias ? __ldg(bias) : 0.f;
   for (long long s = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); s < n_strips;
        s += static_cast<long long>(gridDim.x) * warps_per_block) {
@@ -110,33 +131,51 @@ flow_head_tail_kernel(const void* __restrict__ x_, const float* __restrict__ wei
     float acc[FH_PX];
 #pragma unroll
     for (int p = 0; p < FH_PX; ++p) acc[p] = 0.f;
+    // loads are predicated, not branched around, and batched: with 4 channels per lane all 3 x (FH_PX + 2) of a strip
+    // are issued back to back before the first FMA (one DRAM latency per strip); wider lanes batch one row at a time
+    constexpr int KYB = CPL == 4 ? 3 : 1;
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int yy = y + ky - 1;
-      if (yy < 0 || yy >= H) continue;  // warp-uniform
-      const long long line = ((row - y + yy) * W) * C + lane * CPL;   // element index of this lane's channels
+    for (int ky0 = 0; ky0 < 3; ky0 += KYB) {
+      RawQuad v4[KYB][FH_PX + 2][CPL / 4];   // raw bits: an fp16 quad stays 8 bytes until the FMAs need it
 #pragma unroll
-      for (int i = 0; i < FH_PX + 2; ++i) {
-        const int xx = x0 + i - 1;
-        float v[CPL];
+      for (int kb = 0; kb < KYB; ++kb) {
+        const int yy = y + ky0 + kb - 1;
+        const bool row_ok = yy >= 0 && yy < H;
+        const long long line = ((row - y + (row_ok ? yy : y)) * W) * C + lane * CPL;   // element index of this lane's channels
 #pragma unroll
-        for (int q = 0; q < CPL / 4; ++q) {
-          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (xx >= 0 && xx < W) {
-            const long long e4 = (line + static_cast<long long>(xx) * C) / 4 + q;
-            a = X_F16 ? unpack_h4(__ldg(reinterpret_cast<const uint2*>(x_) + e4)) : __ldg(reinterpret_cast<const float4*>(x_) + e4);
+        for (int i = 0; i < FH_PX + 2; ++i) {
+          const int xx = x0 + i - 1;
+          const bool ok = row_ok && xx >= 0 && xx < W;
+#pragma unroll
+          for (int q = 0; q < CPL / 4; ++q) {
+            RawQuad a;
+            memset(&a, 0, sizeof(a));
+            if (ok) a = __ldg(reinterpret_cast<const RawQuad*>(x_) + (line + static_cast<long long>(xx) * C) / 4 + q);
+            v4[kb][i][q] = a;
           }
-          v[4 * q] = a.x;
-          v[4 * q + 1] = a.y;
-          v[4 * q + 2] = a.z;
-          v[4 * q + 3] = a.w;
         }
+      }
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const int p = i - kx;  // output pixel that sees input i through tap kx
-          if (p < 0 || p >= FH_PX) continue;
+      for (int kb = 0; kb < KYB; ++kb) {
+        const int ky = ky0 + kb;
 #pragma unroll
-          for (int j = 0; j < CPL; ++j) acc[p] = fmaf(v[j], w[ky * 3 + kx][j], acc[p]);
+        for (int i = 0; i < FH_PX + 2; ++i) {
+          float v[CPL];
+#pragma unroll
+          for (int q = 0; q < CPL / 4; ++q) {
+            const float4 f = quad_to_float4(v4[kb][i][q]);
+            v[4 * q] = f.x;
+            v[4 * q + 1] = f.y;
+            v[4 * q + 2] = f.z;
+            v[4 * q + 3] = f.w;
+          }
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const int p = i - kx;  // output pixel that sees input i through tap kx
+            if (p < 0 || p >= FH_PX) continue;
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) acc[p] = fmaf(v[j], w[ky * 3 + kx][j], acc[p]);
+          }
         }
       }
     }
