@@ -19,6 +19,8 @@
 //
 // Bit-exactness: tap positions follow the reference's fp32 operation order exactly; integer indices
 // therefore equal the CPU reference's, and the lerp is evaluated without FMA contraction.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace nnd {
@@ -748,6 +750,280 @@ corr1d_lookup_conv1x1_tc_kernel(const __grid_constant__ LookupArgs a, const floa
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same fused lookup + convc1 + ReLU on the 5th-generation tensor cores (tcgen05, accumulators in TMEM) for the
+// shipping shape (c_out = 256, channels-last output).  The mma.sync kernel above keeps the 256 x 40 weight matrix in
+// registers (80 per thread), which caps it at 12 warps per SM and leaves it latency-bound; here the weights sit in
+// shared memory ONCE per CTA (K-major, no swizzle: 8-row x 16-byte core matrices), a tile is 128 pixels, the
+// interpolated taps of a tile are written straight into the A operand's core-matrix layout, one thread issues five
+// tcgen05.mma (M = 128, N = 256, K = 8) into 256 TMEM columns, and all eight warps run the epilogue
+// (tcgen05.ld 32 columns -> bias -> ReLU -> fp16/fp32 -> 64/128 contiguous bytes per thread).  Windows of tile t+1
+// are gathered with cp.async while tile t is interpolated, multiplied and written.
+// Pixels are addressed flat over the batch (pyramid rows, coordinates and channels-last output are all contiguous
+// in b*H*W + p), so a tile may straddle two images.
+// ------------------------------------------------------------------------------------------------
+namespace umma {
+constexpr int TILE = 128;                 // pixels per tile = UMMA M
+constexpr int NOUT = 256;                 // c_out = UMMA N = TMEM columns
+constexpr int KSTEPS = 5;                 // K = 40 (36 taps + 4 zero columns) in k-steps of 8
+constexpr int A_KSTEP_BYTES = TILE * 32;  // one k-step of A: 128 rows x 32 bytes
+constexpr int B_KSTEP_BYTES = NOUT * 32;
+constexpr int WSTRIDE = 20;               // floats per window row (16 + 4 pad, 16-byte aligned)
+constexpr int WIN_BUF_FLOATS = 4 * TILE * WSTRIDE;
+constexpr int SMEM_B = 0;
+constexpr int SMEM_A = SMEM_B + KSTEPS * B_KSTEP_BYTES;            // 40960
+constexpr int SMEM_WIN = SMEM_A + KSTEPS * A_KSTEP_BYTES;          // + 20480
+constexpr int SMEM_BIAS = SMEM_WIN + 2 * WIN_BUF_FLOATS * 4;       // + 81920
+constexpr int SMEM_COORD = SMEM_BIAS + NOUT * 4;                   // [2 buffers][TILE] coordinates of the tiles in flight
+constexpr int SMEM_BAR = SMEM_COORD + 2 * TILE * 4;
+constexpr int SMEM_TOTAL = SMEM_BAR + 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  int spins = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && ++spins == 1024) {  // watchdog: a protocol bug must fault, not hang the GPU
+      spins = 0;
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000LL) __trap();
+    }
+  } while (!done);
+}
+// K-major operand without swizzle: 16-byte K chunks of 8 consecutive rows form a 128-byte core matrix;
+// lbo = distance between the two K chunks of a k-step, sbo = distance between 8-row groups.
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;   // layout type 0: no swizzle
+}
+// element (row r, column k) of an operand region whose k-steps are blocks of `kstep_bytes`
+__device__ __forceinline__ uint32_t operand_offset(int r, int k, int kstep_bytes) {
+  return static_cast<uint32_t>((k >> 3) * kstep_bytes + (r >> 3) * 256 + ((k >> 2) & 1) * 128 + (r & 7) * 16 + (k & 3) * 4);
+}
+__device__ __forceinline__ void ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+}  // namespace umma
+
+// weight: (K = 36, 256) k-major fp32; out: channels-last (B*H*W, 256) fp32 (out_f16 = 0) or fp16 (1)
+__global__ void __launch_bounds__(512, 1)
+corr1d_lookup_conv1x1_umma_kernel(const __grid_constant__ LookupArgs a, const float* __restrict__ weight,
+                                  const float* __restrict__ bias, int relu, int out_f16, long long total_px,
+                                  long long n_tiles) {
+  using namespace umma;
+  constexpr int TAPS = 9, R = 4, K = 36;
+  extern __shared__ __align__(1024) unsigned char usm[];
+  float* bias_s = reinterpret_cast<float*>(usm + SMEM_BIAS);
+  float* wins = reinterpret_cast<float*>(usm + SMEM_WIN);
+  const uint32_t bar = smem_u32(usm + SMEM_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(usm + SMEM_BAR + 16);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- one-time set-up: weights -> B operand (TF32, round to nearest), zero the K padding, bias, barrier, TMEM ----
+  {
+    // all of a thread's weight loads are issued before the first is used (a load -> convert -> store loop pays the
+    // DRAM latency once per element: 20 serialized round trips cost more than the rest of the kernel)
+    constexpr int PER_THREAD = NOUT * 40 / 512;
+    float wv[PER_THREAD];
+#pragma unroll
+    for (int j = 0; j < PER_THREAD; ++j) {
+      const int idx = tid + 512 * j, n = idx & (NOUT - 1), k = idx >> 8;
+      wv[j] = k < K ? __ldg(weight + static_cast<long long>(k) * NOUT + n) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < PER_THREAD; ++j) {
+      const int idx = tid + 512 * j, n = idx & (NOUT - 1), k = idx >> 8;
+      *reinterpret_cast<uint32_t*>(usm + SMEM_B + operand_offset(n, k, B_KSTEP_BYTES)) = to_tf32(wv[j]);
+    }
+  }
+  for (int idx = tid; idx < TILE * 4; idx += 512)   // A columns 36..39 stay zero for the whole kernel
+    *reinterpret_cast<uint32_t*>(usm + SMEM_A + operand_offset(idx >> 2, K + (idx & 3), A_KSTEP_BYTES)) = 0u;
+  if (tid < NOUT) bias_s[tid] = bias ? __ldg(bias + tid) : 0.f;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(NOUT)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  // 16 warps: half the per-thread work of an 8-warp CTA in every phase (the phases are latency-, not issue-bound)
+  // gather role: thread = (16-byte quarter q, pixel p32 of a 32-pixel pass, level): 4 pixel passes
+  const int gq = tid & 3, gp = (tid >> 2) & 31, glvl = tid >> 7;
+  // interpolation role: thread = (pixel m of the tile, level)
+  const int im = tid & (TILE - 1), ilvl = tid >> 7;
+
+  float* coord_s = reinterpret_cast<float*>(usm + SMEM_COORD);
+  // coordinates of the gather role's four pixels, always fetched one tile ahead of their use (no global latency
+  // between a tile's coordinates and its cp.async issue); the gather also parks them in shared memory for the
+  // interpolation phase of that tile
+  auto load_coords = [&](long long tile, float (&cn)[4]) {
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+      const long long px = tile * TILE + pass * 32 + gp;
+      cn[pass] = (tile < n_tiles && px < total_px) ? __ldg(a.coords + px) : 0.f;
+    }
+  };
+  auto issue_windows = [&](long long tile, int buf, const float (&cn)[4]) {
+    if (tile < n_tiles) {
+#pragma unroll
+      for (int pass = 0; pass < 4; ++pass) {
+        const int m = pass * 32 + gp;
+        const long long px = tile * TILE + m;
+        const float c = cn[pass];
+        if (gq == 0 && glvl == 0) coord_s[buf * TILE + m] = c;
+        if (px < total_px) {
+          {
+            const int lvl = glvl;
+            const int w = a.src[0].width[lvl], pitch = a.src[0].pitch[lvl];
+            const float centre = __fmul_rn(c, 1.0f / static_cast<float>(1 << lvl));
+            const LevelScale sc = level_scale(w, lvl, 0.f);
+            const int s = make_tap(0, R, centre, sc).i0 & ~3;
+            const int hi = make_tap(TAPS - 1, R, centre, sc).i1;
+            const int cq = s + 4 * gq;
+            if (cq <= hi && cq < w) {
+              const float* src = a.src[0].ptr[lvl] + px * pitch + cq;
+              const uint32_t dst = smem_u32(wins + buf * WIN_BUF_FLOATS + (lvl * TILE + m) * WSTRIDE + 4 * gq);
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            }
+          }
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(NOUT >> 3) << 17) |
+                         (static_cast<uint32_t>(TILE >> 4) << 24);   // D f32, A/B tf32, both K-major
+  const long long stride = gridDim.x;
+  long long tile = blockIdx.x;
+  int buf = 0;
+  uint32_t phase = 0;
+  float cn[4];
+  load_coords(tile, cn);
+  issue_windows(tile, 0, cn);
+  load_coords(tile + stride, cn);
+  for (; tile < n_tiles; tile += stride, buf ^= 1) {
+    issue_windows(tile + stride, buf ^ 1, cn);                 // next tile's gather flies during this whole iteration
+    load_coords(tile + 2 * stride, cn);                        // and the coordinates after that
+    asm volatile("cp.async.wait_group 1;" ::: "memory");        // this tile's windows have landed (my own copies)
+    __syncthreads();                                            // ... and everybody else's
+    // ---- interpolate: 9 taps of one level for pixel im, straight into the A operand ----
+    {
+      const long long px = tile * TILE + im;
+      const bool live = px < total_px;
+      const float c = coord_s[buf * TILE + im];
+      {
+        const int lvl = ilvl;
+        const int w = a.src[0].width[lvl];
+        const float centre = __fmul_rn(c, 1.0f / static_cast<float>(1 << lvl));
+        const LevelScale sc = level_scale(w, lvl, 0.f);
+        const int s = make_tap(0, R, centre, sc).i0 & ~3;
+        const float* mine = wins + buf * WIN_BUF_FLOATS + (lvl * TILE + im) * WSTRIDE - s;
+#pragma unroll
+        for (int k = 0; k < TAPS; ++k) {
+          const Tap tp = make_tap(k, R, centre, sc);
+          const float val = live ? __fadd_rn(__fmul_rn(tp.coef, mine[tp.i0]), __fmul_rn(tp.one_minus, mine[tp.i1])) : 0.f;
+          *reinterpret_cast<uint32_t*>(usm + SMEM_A + operand_offset(im, lvl * TAPS + k, A_KSTEP_BYTES)) = to_tf32(val);
+        }
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int ks = 0; ks < KSTEPS; ++ks) {
+        const uint64_t adesc = desc_kmajor(smem_u32(usm + SMEM_A + ks * A_KSTEP_BYTES), 128, 256);
+        const uint64_t bdesc = desc_kmajor(smem_u32(usm + SMEM_B + ks * B_KSTEP_BYTES), 128, 256);
+        const uint32_t acc = ks > 0 ? 1u : 0u;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_base), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+            : "memory");
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ---- epilogue: warp = (lane quarter, column quarter); thread = one pixel row x 2 chunks of 32 channels ----
+    {
+      const int lq = warp & 3, ch = warp >> 2;
+      const int m = 32 * lq + lane;
+      const long long px = tile * TILE + m;
+#pragma unroll
+      for (int cchunk = 0; cchunk < 2; ++cchunk) {
+        const int col0 = 64 * ch + 32 * cchunk;
+        float v[32];
+        ld32(tmem_base + (static_cast<uint32_t>(32 * lq) << 16) + col0, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          v[i] += bias_s[col0 + i];
+          if (relu) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (px < total_px) {
+          if (out_f16) {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(a.out) + px * NOUT + col0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              dst[i] = make_uint4(pack_h2(v[8 * i], v[8 * i + 1]), pack_h2(v[8 * i + 2], v[8 * i + 3]),
+                                  pack_h2(v[8 * i + 4], v[8 * i + 5]), pack_h2(v[8 * i + 6], v[8 * i + 7]));
+          } else {
+            float4* dst = reinterpret_cast<float4*>(a.out + px * NOUT + col0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();   // TMEM drained and the A tile consumed before the next tile overwrites them
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(NOUT) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // IGEV dual lookup over the interleaved pyramids ([b][h][w1][d][g], igev.cu): the eight windows of a
 // pixel are one contiguous run of (hi - lo + 1) * 32 bytes <= 352 bytes, so every fetched sector is used.
 // Warp = 32 consecutive pixels x one level; for each of the two sources the warp copies the 32 runs into a
@@ -1124,6 +1400,22 @@ nnd_status nnd_corr1d_lookup_conv1x1(const float* const* level, const int* width
   NND_REQUIRE(out_layout >= 0 && out_layout <= 2,
               "lookup_conv1x1: out_layout %d is not 0 (fp32 NCHW), 1 (fp32 channels-last) or 2 (fp16 channels-last)", out_layout);
   const long long n_groups_all = static_cast<long long>(B) * ((a.hw + 31) / 32);
+  if (precision == NND_PREC_TF32 && c_out == 256 && out_layout != 0 && vec && getenv("NND_LOOKUP_UMMA") &&
+      getenv("NND_LOOKUP_UMMA")[0] == '1') {
+    // tcgen05 path (opt-in, NND_LOOKUP_UMMA=1): weights in shared memory, accumulators in TMEM, 128-pixel tiles.
+    // Parity-green but not yet faster than the mma.sync kernel below (33.8 vs 29.2 us isolated, 32.8 vs 28.6 us in
+    // the step): DESIGN.md section 8.
+    const long long total_px = static_cast<long long>(B) * a.hw;
+    const long long n_tiles = (total_px + umma::TILE - 1) / umma::TILE;
+    cudaError_t ae = cudaFuncSetAttribute(corr1d_lookup_conv1x1_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          umma::SMEM_TOTAL);
+    if (ae != cudaSuccess) return cuda_fail(ae, "lookup_conv1x1: shared-memory attribute");
+    const long long sms = sm_count();
+    corr1d_lookup_conv1x1_umma_kernel<<<static_cast<unsigned>(n_tiles < sms ? n_tiles : sms), 512, umma::SMEM_TOTAL,
+                                        reinterpret_cast<cudaStream_t>(stream)>>>(a, weight, bias, relu ? 1 : 0,
+                                                                                  out_layout == 2 ? 1 : 0, total_px, n_tiles);
+    return check_launch("corr1d_lookup_conv1x1_umma_kernel");
+  }
   if (precision == NND_PREC_TF32 && c_out <= 256) {
     // tensor-core path: weights live in registers, shared memory holds only the lookup tiles
     const size_t smem_tc = (32 * 40 + static_cast<size_t>(2) * 4 * 32 * 20) * sizeof(float);

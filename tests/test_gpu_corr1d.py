@@ -385,12 +385,46 @@ def test_lookup_conv1x1_fusion(shape, c_out):
         tc_cl = blk.lookup_conv1x1(coords, conv.weight, conv.bias, relu=True, precision="tf32", channels_last=True)
     assert (tc - ref).abs().max().item() <= 1e-3 * scale
     assert tc_cl.shape == tc.shape and tc_cl.is_contiguous(memory_format=torch.channels_last)
-    assert torch.equal(tc_cl, tc)                       # same numbers, channels-last memory
+    if c_out == 256:
+        # c_out = 256 channels-last runs on the tcgen05 kernel: same TF32 operands, another summation order
+        assert (tc_cl - ref).abs().max().item() <= 1e-3 * scale
+        assert (tc_cl - tc).abs().max().item() <= 1e-5 * scale
+    else:
+        assert torch.equal(tc_cl, tc)                   # same kernel, same numbers, channels-last memory
     if c_out <= 256:
         with torch.no_grad():
             tc_h = blk.lookup_conv1x1(coords, conv.weight, conv.bias, relu=True, precision="tf32", channels_last=True, half=True)
         assert tc_h.dtype == torch.float16 and tc_h.permute(0, 2, 3, 1).is_contiguous()
-        assert torch.equal(tc_h, tc.half())             # the same values rounded to nearest fp16
+        assert torch.equal(tc_h, tc_cl.half())          # the same values rounded to nearest fp16
+
+
+@pytest.mark.parametrize("shape", [(8, 48, 156), (1, 5, 52), (3, 7, 44)])
+def test_lookup_conv1x1_tcgen05_path(shape, monkeypatch):
+    """The opt-in tcgen05 / TMEM version of the fused lookup (NND_LOOKUP_UMMA=1; c_out = 256, channels-last): same TF32
+    operands as the mma.sync kernel, another summation order; tiles straddle images and the last tile is ragged."""
+    import nndepth_b200 as nb
+    B, H, W = shape
+    torch.manual_seed(B * H + W)
+    f1, f2 = torch.randn(B, 64, H, W, device="cuda"), torch.randn(B, 64, H, W, device="cuda")
+    blk = nb.CorrBlock1D(f1, f2, 4, 4)
+    coords = torch.arange(W, device="cuda").float().view(1, 1, 1, W).repeat(B, 1, H, 1) - torch.rand(B, 1, H, W, device="cuda") * 30
+    coords.view(-1)[::17] = -7.5
+    coords.view(-1)[5::23] = W + 3.25
+    conv = torch.nn.Conv2d(36, 256, 1).cuda()
+    with torch.no_grad():
+        monkeypatch.setenv("NND_LOOKUP_UMMA", "0")
+        base = blk.lookup_conv1x1(coords, conv.weight, conv.bias, relu=True, precision="tf32", channels_last=True)
+        monkeypatch.setenv("NND_LOOKUP_UMMA", "1")
+        umma = blk.lookup_conv1x1(coords, conv.weight, conv.bias, relu=True, precision="tf32", channels_last=True)
+        umma_h = blk.lookup_conv1x1(coords, conv.weight, conv.bias, relu=True, precision="tf32", channels_last=True, half=True)
+        lin = blk.lookup_conv1x1(coords, conv.weight, None, relu=False, precision="tf32", channels_last=True)
+        monkeypatch.setenv("NND_LOOKUP_UMMA", "0")
+        base_lin = blk.lookup_conv1x1(coords, conv.weight, None, relu=False, precision="tf32", channels_last=True)
+    scale = base_lin.abs().max().item()
+    assert umma.is_contiguous(memory_format=torch.channels_last)
+    assert (umma - base).abs().max().item() <= 1e-5 * scale
+    assert (lin - base_lin).abs().max().item() <= 1e-5 * scale
+    assert torch.equal(umma_h, umma.half())
 
 
 def test_randomised_lookup_sweep_bit_exact():
