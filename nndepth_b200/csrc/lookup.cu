@@ -775,7 +775,8 @@ constexpr int SMEM_WIN = SMEM_A + KSTEPS * A_KSTEP_BYTES;          // + 20480
 constexpr int SMEM_BIAS = SMEM_WIN + 2 * WIN_BUF_FLOATS * 4;       // + 81920
 constexpr int SMEM_COORD = SMEM_BIAS + NOUT * 4;                   // [2 buffers][TILE] coordinates of the tiles in flight
 constexpr int SMEM_BAR = SMEM_COORD + 2 * TILE * 4;
-constexpr int SMEM_TOTAL = SMEM_BAR + 64;
+constexpr int SMEM_STAGE = SMEM_BAR + 64;                          // fp16 output tile [TILE][NOUT], 16-byte chunks XOR-swizzled
+constexpr int SMEM_TOTAL = SMEM_STAGE + TILE * NOUT * 2;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -998,19 +999,32 @@ corr1d_lookup_conv1x1_umma_kernel(const __grid_constant__ LookupArgs a, const fl
           v[i] += bias_s[col0 + i];
           if (relu) v[i] = fmaxf(v[i], 0.f);
         }
-        if (px < total_px) {
-          if (out_f16) {
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(a.out) + px * NOUT + col0);
+        if (out_f16) {
+          // a thread owns a pixel ROW: stored directly, a warp instruction would touch 32 rows x 16 bytes.  Stage the
+          // tile in shared memory (16-byte chunk c of row m at chunk c ^ (m & 31): conflict-free both ways) ...
+          uint4* stage = reinterpret_cast<uint4*>(usm + SMEM_STAGE);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              dst[i] = make_uint4(pack_h2(v[8 * i], v[8 * i + 1]), pack_h2(v[8 * i + 2], v[8 * i + 3]),
-                                  pack_h2(v[8 * i + 4], v[8 * i + 5]), pack_h2(v[8 * i + 6], v[8 * i + 7]));
-          } else {
-            float4* dst = reinterpret_cast<float4*>(a.out + px * NOUT + col0);
+          for (int i = 0; i < 4; ++i)
+            stage[m * 32 + (((col0 >> 3) + i) ^ (m & 31))] =
+                make_uint4(pack_h2(v[8 * i], v[8 * i + 1]), pack_h2(v[8 * i + 2], v[8 * i + 3]),
+                           pack_h2(v[8 * i + 4], v[8 * i + 5]), pack_h2(v[8 * i + 6], v[8 * i + 7]));
+        } else if (px < total_px) {
+          float4* dst = reinterpret_cast<float4*>(a.out + px * NOUT + col0);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          }
+          for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         }
+      }
+    }
+    if (out_f16) {
+      // ... and write it out 512 contiguous bytes per pixel: warp = 8 pixel rows, lane = one 16-byte chunk
+      __syncthreads();
+      const uint4* stage = reinterpret_cast<const uint4*>(usm + SMEM_STAGE);
+      uint4* out16 = reinterpret_cast<uint4*>(a.out);
+#pragma unroll
+      for (int r = 0; r < TILE / 16; ++r) {
+        const int row = warp * (TILE / 16) + r;
+        const long long px = tile * TILE + row;
+        if (px < total_px) out16[px * 32 + lane] = stage[row * 32 + (lane ^ (row & 31))];
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
