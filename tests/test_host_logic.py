@@ -74,3 +74,61 @@ def test_model_shell_parameter_names_follow_the_reference_layout():
         outs = model(torch.rand(1, 3, 64, 160) * 2 - 1, torch.rand(1, 3, 64, 160) * 2 - 1)
     assert len(outs) == 2 and outs[-1]["up_disp"].shape == (1, 1, 64, 160) and torch.isfinite(outs[-1]["up_disp"]).all()
     assert np.isfinite(outs[0]["up_disp"].numpy()).all()
+
+
+def test_gru_split_weights_reconstruct_fp32_weights():
+    """[w_hi; w_lo] of the weight-split ConvGRU: hi + lo reproduces the fp32 weight to 2^-22 (TF32 split) and to about
+    2^-17 relative (fp16 split, where w_lo runs into fp16's subnormal spacing) -- versus 2^-11 for a plain rounding."""
+    import torch
+    from nndepth_b200.raft_stereo import SepConvGRU
+    torch.manual_seed(0)
+    gru = SepConvGRU(hidden_dim=16, input_dim=24).eval()
+    for tag in "12":
+        wz, wr, wq = (getattr(gru, f"conv{g}{tag}").weight.detach() for g in "zrq")
+        for half, tol in ((False, 2.0 ** -21), (True, 2.0 ** -15)):
+            (wzr, bzr), (wq2, bq), pad = gru._split_weights(tag, half=half)
+            cin = wz.shape[1]
+            assert wzr.shape[1] == 2 * cin and wq2.shape[1] == 2 * cin and pad == getattr(gru, f"convz{tag}").padding
+            assert wzr.dtype == (torch.float16 if half else torch.float32)
+            rec_zr = wzr[:, :cin].float() + wzr[:, cin:].float()
+            rec_q = wq2[:, :cin].float() + wq2[:, cin:].float()
+            ref_zr = torch.cat([wz, wr], 0)
+            scale = ref_zr.abs().max().item()
+            assert (rec_zr - ref_zr).abs().max().item() <= tol * scale
+            assert (rec_q - wq).abs().max().item() <= tol * scale
+            # the plain rounding alone is 2^-12 .. 2^-11 off: the low part matters
+            assert (wzr[:, :cin].float() - ref_zr).abs().max().item() > 2.0 ** -14 * scale
+            assert bzr.dtype == torch.float32 and bq.dtype == torch.float32
+
+
+def test_fold_bn_equals_conv_then_batchnorm():
+    """BatchNorm folded into the convolution (inference): same function as conv -> bn in eval mode."""
+    import torch
+    from nndepth_b200.raft_stereo import fold_bn
+    torch.manual_seed(1)
+    conv = torch.nn.Conv2d(5, 7, 3, padding=1)
+    bn = torch.nn.BatchNorm2d(7).eval()
+    bn.running_mean.normal_()
+    bn.running_var.uniform_(0.5, 2.0)
+    bn.weight.data.normal_()
+    bn.bias.data.normal_()
+    x = torch.randn(2, 5, 6, 9)
+    with torch.no_grad():
+        w, b = fold_bn(conv, bn)
+        ref = bn(conv(x))
+        got = torch.nn.functional.conv2d(x, w, b, padding=1)
+    assert torch.allclose(got, ref, rtol=1e-5, atol=1e-5)
+
+
+def test_rn_tf32_is_round_to_nearest_on_10_mantissa_bits():
+    import torch
+    from nndepth_b200.raft_stereo import rn_tf32
+    x = torch.tensor([1.0, 1.0 + 2.0 ** -11, 1.0 + 2.0 ** -10, 1.0 + 3 * 2.0 ** -12, -3.1415927, 1e-30, 65504.0])
+    y = rn_tf32(x)
+    assert torch.equal(y.view(torch.int32) & 0x1FFF, torch.zeros_like(y, dtype=torch.int32))     # low 13 bits cleared
+    assert (y - x).abs().max().item() <= (x.abs() * 2.0 ** -11).max().item()
+    assert y[0] == 1.0 and y[2] == 1.0 + 2.0 ** -10
+    # fp16 carries the same mantissa: inside fp16's normal range the two roundings agree (ties aside)
+    z = torch.randn(4096) * 3
+    same = (rn_tf32(z) == z.half().float()).float().mean().item()
+    assert same > 0.999
