@@ -101,26 +101,7 @@ def test_gru_split_weights_reconstruct_fp32_weights():
             assert bzr.dtype == torch.float32 and bq.dtype == torch.float32
 
 
-def test_fold_bn_equals_conv_then_batchnorm():
-    """BatchNorm folded into the convolution (inference): same function as conv -> bn in eval mode."""
-    import torch
-    from nndepth_b200.raft_stereo import fold_bn
-    torch.manual_seed(1)
-    conv = torch.nn.Conv2d(5, 7, 3, padding=1)
-    bn = torch.nn.BatchNorm2d(7).eval()
-    bn.running_mean.normal_()
-    bn.running_var.uniform_(0.5, 2.0)
-    bn.weight.data.normal_()
-    bn.bias.data.normal_()
-    x = torch.randn(2, 5, 6, 9)
-    with torch.no_grad():
-        w, b = fold_bn(conv, bn)
-        ref = bn(conv(x))
-        got = torch.nn.functional.conv2d(x, w, b, padding=1)
-    assert torch.allclose(got, ref, rtol=1e-5, atol=1e-5)
-
-
-def test_rn_tf32_is_round_to_nearest_on_10_mantissa_bits():
+def test_fp16_rounding_agrees_with_rn_tf32():
     import torch
     from nndepth_b200.raft_stereo import rn_tf32
     x = torch.tensor([1.0, 1.0 + 2.0 ** -11, 1.0 + 2.0 ** -10, 1.0 + 3 * 2.0 ** -12, -3.1415927, 1e-30, 65504.0])
