@@ -196,6 +196,15 @@ def _fold_f16(conv, bn):
             b.clamp(-65504.0, 65504.0).half().contiguous())
 
 
+def _fold_key(mode, *pairs):
+    """Cache key of a folded conv + BatchNorm chain: in-place weight updates (load_state_dict, .to()) bump ``_version``."""
+    key = [mode]
+    for conv, bn in pairs:
+        key += [conv.weight._version, conv.weight.device, None if conv.bias is None else conv.bias._version,
+                bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version]
+    return tuple(key)
+
+
 def _fused_ok(x, *norms):
     """Inference on the GPU with eval-mode BatchNorm: the conv + BN (+ add) + ReLU chains run as single cuDNN calls."""
     return (x.is_cuda and not torch.is_grad_enabled() and hasattr(torch, "cudnn_convolution_relu")
@@ -228,14 +237,15 @@ class ResidualBlock(nn.Module):
     def _folded(self, half=False):
         """(w, b) of conv1+norm1, conv2+norm2, shortcut+norm3, folded once (inference)."""
         tf32 = "f16" if half else bool(torch.backends.cudnn.allow_tf32)
+        key = _fold_key(tf32, (self.conv1, self.norm1), (self.conv2, self.norm2), (self.downsample[0], self.norm3))
         cache = getattr(self, "_fold_cache", None)
-        if cache is None or cache[0] != tf32:
+        if cache is None or cache[0] != key:
             if half:
-                cache = (tf32, (_fold_f16(self.conv1, self.norm1), _fold_f16(self.conv2, self.norm2),
-                                _fold_f16(self.downsample[0], self.norm3)))
+                cache = (key, (_fold_f16(self.conv1, self.norm1), _fold_f16(self.conv2, self.norm2),
+                               _fold_f16(self.downsample[0], self.norm3)))
             else:
-                cache = (tf32, (fold_bn(self.conv1, self.norm1, tf32), fold_bn(self.conv2, self.norm2, tf32),
-                                fold_bn(self.downsample[0], self.norm3, tf32)))
+                cache = (key, (fold_bn(self.conv1, self.norm1, tf32), fold_bn(self.conv2, self.norm2, tf32),
+                               fold_bn(self.downsample[0], self.norm3, tf32)))
             self._fold_cache = cache
         return cache[1]
 
@@ -287,14 +297,15 @@ class BasicEncoder(nn.Module):
             x = x.half()
         if _fused_ok(x, self.norm1):
             tf32 = "f16" if half else bool(torch.backends.cudnn.allow_tf32)
-            if getattr(self, "_fold_cache", None) is None or self._fold_cache[0] != tf32:
+            key = _fold_key(tf32, (self.conv1, self.norm1))
+            if getattr(self, "_fold_cache", None) is None or self._fold_cache[0] != key:
                 w, b = _fold_f16(self.conv1, self.norm1) if half else fold_bn(self.conv1, self.norm1, tf32)
                 # a fourth, all-zero input channel: with 3 channels cuDNN has no Blackwell kernel for this layer and
                 # falls back to an sm80 one (763 us at KITTI x 16 images); 4 channels are TMA-addressable
                 w = F.pad(w, (0, 0, 0, 0, 0, (-w.shape[1]) % 4))
                 if self.conv1.weight.is_contiguous(memory_format=torch.channels_last) and not self.conv1.weight.is_contiguous():
                     w = w.contiguous(memory_format=torch.channels_last)
-                self._fold_cache = (tf32, (w, b))
+                self._fold_cache = (key, (w, b))
             w, b = self._fold_cache[1]
             if w.shape[1] != x.shape[1]:
                 fmt = torch.channels_last if (x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()) \
@@ -363,9 +374,11 @@ class SepConvGRU(nn.Module):
         """``[w_hi ; w_lo]`` along the INPUT-channel axis for the (z|r) and q convolutions of one half-step (the
         activations are presented twice, ``[RN(x) ; RN(x)]``).  ``half``: both parts as fp16 (same 10-bit mantissa
         as TF32; ``w_lo`` keeps ~5 more bits before fp16's subnormal spacing cuts it, i.e. weights good to 2**-17)."""
+        cz, cr, cq = (getattr(self, f"conv{g}{tag}") for g in "zrq")
+        # in-place weight updates (load_state_dict, .to()) bump ``_version``: a stale split is never served
+        stamp = tuple(p._version for c in (cz, cr, cq) for p in (c.weight, c.bias)) + (cz.weight.device,)
         key = (tag, channels_last, half)
-        if key not in self._split_w:
-            cz, cr, cq = (getattr(self, f"conv{g}{tag}") for g in "zrq")
+        if key not in self._split_w or self._split_w[key][3] != stamp:
             packed = []
             for w, b in ((torch.cat([cz.weight, cr.weight], 0), torch.cat([cz.bias, cr.bias], 0)), (cq.weight, cq.bias)):
                 w = w.detach().float()
@@ -378,8 +391,8 @@ class SepConvGRU(nn.Module):
                 if channels_last:
                     w2 = w2.contiguous(memory_format=torch.channels_last)
                 packed.append((w2, b.detach().float().contiguous()))
-            self._split_w[key] = (packed[0], packed[1], cz.padding)
-        return self._split_w[key]
+            self._split_w[key] = (packed[0], packed[1], cz.padding, stamp)
+        return self._split_w[key][:3]
 
     def _half_step_wsplit(self, h, x, tag):
         """The same recurrence through torch ops (the fused runner's reference and its fallback)."""

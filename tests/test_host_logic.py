@@ -113,3 +113,26 @@ def test_fp16_rounding_agrees_with_rn_tf32():
     z = torch.randn(4096) * 3
     same = (rn_tf32(z) == z.half().float()).float().mean().item()
     assert same > 0.999
+
+
+def test_weight_caches_follow_in_place_updates():
+    """Split / folded weight caches are keyed on the parameters' versions: loading a checkpoint after a first forward
+    must not leave stale tensors behind."""
+    import torch
+    from nndepth_b200.raft_stereo import ResidualBlock, SepConvGRU
+    torch.manual_seed(2)
+    gru = SepConvGRU(hidden_dim=8, input_dim=8).eval()
+    (w_a, _), _, _ = gru._split_weights("1")
+    assert gru._split_weights("1")[0][0] is w_a                      # cached while nothing changes
+    with torch.no_grad():
+        gru.convz1.weight.mul_(2.0)
+    (w_b, _), _, _ = gru._split_weights("1")
+    cin = gru.convz1.weight.shape[1]
+    assert torch.allclose(w_b[:8, :cin] + w_b[:8, cin:], gru.convz1.weight.detach(), atol=1e-7)
+    assert not torch.equal(w_a, w_b)
+    block = ResidualBlock(4, 4, norm_fn="batch").eval()
+    f_a = block._folded()[0][0]
+    with torch.no_grad():
+        block.norm1.running_var.fill_(4.0)
+    f_b = block._folded()[0][0]
+    assert not torch.equal(f_a, f_b)
