@@ -14,6 +14,7 @@ backward are kernels of this package, the two volume-gradient contractions are c
 AGCL and the IGEV volume are inference only.
 """
 import math
+import warnings
 
 import torch
 
@@ -23,9 +24,11 @@ _VOLUME_PRECISION = "tf32"
 
 
 def set_volume_precision(precision):
-    """``"tf32"`` (default: tcgen05 tensor cores, operands rounded to nearest TF32, 1e-3 bar) or
-    ``"fp32"`` (CUDA-core FFMA, 1e-5 parity bar).  Shapes the tensor-core path cannot take (feature
-    widths not divisible by 4) run on the fp32 kernel when the precision is left at its default."""
+    """``"tf32"`` (inference default: tcgen05 tensor cores, operands rounded to nearest TF32, 1e-3 bar) or
+    ``"fp32"`` (CUDA-core FFMA, 1e-5 parity bar).  Two cases run on the fp32 kernel while the precision is left at
+    its default: a differentiable build (feature maps that require grad, under grad mode -- the reference trains in
+    fp32 unless the caller opts into autocast) and shapes the tensor-core path cannot take (feature widths not
+    divisible by 4; warned once)."""
     global _VOLUME_PRECISION
     if precision not in ("fp32", "tf32"):
         raise ValueError(f"precision must be 'fp32' or 'tf32', got {precision!r}")
@@ -36,11 +39,29 @@ def get_volume_precision():
     return _VOLUME_PRECISION
 
 
-def _prec_code(precision, W1=4, W2=4):
+_warned = set()
+
+
+def _warn_once(key, message):
+    """One line per process and cause: a re-routed call must not be silent (there is no multi-backend dispatch)."""
+    if key not in _warned:
+        _warned.add(key)
+        warnings.warn(message, RuntimeWarning, stacklevel=3)
+
+
+def _prec_code(precision, W1=4, W2=4, train=False):
     if precision is None:
         precision = _VOLUME_PRECISION
+        if precision == "tf32" and train:
+            # the reference's training forward contracts in fp32 unless the caller opts into autocast: a drop-in
+            # must not change the numerics of a training run behind the caller's back
+            precision = "fp32"
         if precision == "tf32" and (W1 % 4 or W2 % 4):
-            precision = "fp32"      # 16-byte TMA rows need widths divisible by 4: same result on the fp32 kernel
+            # 16-byte TMA rows need widths divisible by 4: same result (to 1e-5) on the slower fp32 FFMA kernel
+            _warn_once(("width", W1, W2),
+                       f"nndepth_b200: feature widths ({W1}, {W2}) are not multiples of 4; the correlation volume is "
+                       "built by the fp32 CUDA-core kernel instead of the tcgen05 TF32 kernel (about 5x slower)")
+            precision = "fp32"
     if precision not in ("fp32", "tf32"):
         raise ValueError(f"precision must be 'fp32' or 'tf32', got {precision!r}")
     return _lib.PREC_TF32 if precision == "tf32" else _lib.PREC_FP32
@@ -210,7 +231,7 @@ class CorrBlock1D:
         W2 = f2.shape[3]
         self._shape = (B, H, W1, W2)
         if train:
-            self._graph_buffer = _BuildPyramid.apply(f1, f2, num_levels, _prec_code(precision, W1, W2))
+            self._graph_buffer = _BuildPyramid.apply(f1, f2, num_levels, _prec_code(precision, W1, W2, train=True))
             self._pyr = PyramidStorage(B * H * W1, W2, num_levels, f1.device, buffer=self._graph_buffer.detach())
             return
         self._pyr = PyramidStorage(B * H * W1, W2, num_levels, f1.device)

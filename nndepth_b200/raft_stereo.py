@@ -15,11 +15,13 @@ plain ``torch.nn`` modules.  This file only re-states their module tree so that
 ``corr_fn`` is a class-valued attribute exactly as in the reference (model.py:58), so the same shell
 runs the CPU oracle in tests / the CPU baseline (``model.corr_fn = <oracle class>``).
 """
+import itertools
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .corr import CorrBlock1D
+from .corr import CorrBlock1D, _warn_once
 from .upsample import convex_upsample as fused_convex_upsample
 
 
@@ -110,6 +112,9 @@ def flow_conv7x7_relu(conv, flow, half=False):
     if not (_small_kernels_ok(flow) and flow.shape[1] == 1 and conv.kernel_size == (7, 7) and conv.padding == (3, 3)
             and conv.stride == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1 and conv.bias is not None
             and conv.out_channels % 4 == 0 and 256 % (conv.out_channels // 4) == 0):
+        if flow.is_cuda and not torch.is_grad_enabled():
+            _warn_once("flow_conv7x7", "nndepth_b200: flow_conv7x7_relu shape outside the fused kernel's (1 -> C, 7x7, "
+                       f"pad 3, C % 4 == 0): conv {tuple(conv.weight.shape)} runs on cuDNN instead")
         out = conv_relu(conv, flow)
         return out.half().contiguous(memory_format=torch.channels_last) if half else out
     from . import _lib
@@ -151,6 +156,9 @@ def flow_head_tail(conv, x, coords=None, org=None):
     if not (_small_kernels_ok(x, half_ok=True) and conv.out_channels == 1 and conv.in_channels in (128, 256, 512) and _is_nhwc(x)
             and conv.kernel_size == (3, 3) and conv.padding == (1, 1) and conv.stride == (1, 1)
             and conv.dilation == (1, 1) and conv.groups == 1):
+        if x.is_cuda and not torch.is_grad_enabled() and conv.out_channels == 1:
+            _warn_once("flow_head_tail", "nndepth_b200: flow_head_tail shape outside the fused kernel's (channels-last "
+                       f"128/256/512 -> 1, 3x3): conv {tuple(conv.weight.shape)} runs on cuDNN instead")
         return None
     from . import _lib
     N, C, H, W = x.shape
@@ -345,17 +353,27 @@ class SepConvGRU(nn.Module):
         self._split_w = {}
 
     def fuse_gates(self):
-        """Pre-concatenate the z|r gate weights (call after loading weights, in eval mode)."""
+        """Enable the concatenated z|r gate convolution for inference (call any time; weights may still change)."""
+        self._fuse_zr = True
         self._fused = {}
-        for tag in "12":
-            cz, cr = getattr(self, f"convz{tag}"), getattr(self, f"convr{tag}")
-            self._fused[tag] = (torch.cat([cz.weight, cr.weight], 0).detach().contiguous(),
-                                torch.cat([cz.bias, cr.bias], 0).detach().contiguous(), cz.padding)
+
+    def _fused_zr(self, tag):
+        """Concatenated z|r weights of one half-step, keyed on the parameters' versions and device: in-place updates
+        (``load_state_dict``, ``.to()``, an optimiser step) bump ``_version``, so a stale snapshot is never served."""
+        cz, cr = getattr(self, f"convz{tag}"), getattr(self, f"convr{tag}")
+        stamp = tuple(p._version for c in (cz, cr) for p in (c.weight, c.bias)) + (cz.weight.device, cz.weight.dtype)
+        hit = self._fused.get(tag)
+        if hit is None or hit[3] != stamp:
+            hit = (torch.cat([cz.weight, cr.weight], 0).detach().contiguous(),
+                   torch.cat([cz.bias, cr.bias], 0).detach().contiguous(), cz.padding, stamp)
+            self._fused[tag] = hit
+        return hit[:3]
 
     def _half_step(self, h, x, tag):
         hx = torch.cat([h, x], dim=1)
-        if tag in self._fused:
-            w, b, pad = self._fused[tag]
+        if getattr(self, "_fuse_zr", False) and not torch.is_grad_enabled():
+            # inference only: under grad mode the per-gate convolutions below keep convz / convr in the autograd graph
+            w, b, pad = self._fused_zr(tag)
             z, r = torch.sigmoid(F.conv2d(hx, w, b, padding=pad)).chunk(2, dim=1)
         else:
             z = torch.sigmoid(getattr(self, f"convz{tag}")(hx))
@@ -726,15 +744,25 @@ class RAFTStereo(nn.Module):
         if self.dense_precision not in ("fp32", "mixed", "mixed2x", "mixed16", "tf32"):
             raise ValueError("dense_precision must be None, 'fp32', 'mixed', 'mixed2x', 'mixed16' or 'tf32', "
                              f"got {self.dense_precision!r}")
+        # the mode is applied for the duration of this call only: the submodule switches it drives are restored on
+        # the way out, so a later call with ``dense_precision = None`` really runs on the caller's own flags
         gru = getattr(self.update_block, "gru", None)
+        has_half = hasattr(self.fnet, "half_convs") or isinstance(self.fnet, BasicEncoder)
+        saved = (getattr(gru, "recurrence", None), getattr(self.fnet, "half_convs", False))
         if gru is not None:
             gru.recurrence = {"mixed": "fp32", "mixed2x": "wsplit", "mixed16": "wsplit16"}.get(self.dense_precision)
-        if hasattr(self.fnet, "half_convs") or isinstance(self.fnet, BasicEncoder):
+        if has_half:
             # mixed16 runs the (BatchNorm-folded) feature encoder as fp16 convolutions as well: the feature maps are
             # rounded to 10 mantissa bits for the correlation volume anyway (RN_tf32(RN_fp16(x)) == RN_fp16(x))
             self.fnet.half_convs = self.dense_precision == "mixed16" and getattr(self, "fp16_encoder", True)
-        with cudnn_tf32(self.dense_precision != "fp32"):
-            return self._forward(frame1, frame2, **kwargs)
+        try:
+            with cudnn_tf32(self.dense_precision != "fp32"):
+                return self._forward(frame1, frame2, **kwargs)
+        finally:
+            if gru is not None:
+                gru.recurrence = saved[0]
+            if has_half:
+                self.fnet.half_convs = saved[1]
 
     def _forward(self, frame1, frame2, **kwargs):
         fmap1, fmap2, cnet1 = self.forward_fnet(frame1, frame2)
@@ -792,6 +820,34 @@ class RAFTStereo(nn.Module):
         return outputs
 
     # ---- CUDA-graph replay of the whole forward (inference) ---------------------------------------
+    def _graph_key(self, frame1):
+        """Everything a captured graph bakes in.  Python does not run on replay, and the derived weights built during
+        warm-up (TF32-rounded, BatchNorm-folded, split, padded copies) are captured by ADDRESS: the key therefore
+        carries a stamp of every parameter's / buffer's in-place version and storage, next to the shape and every
+        switch that changes which kernels run.  ``load_state_dict`` / ``.to()`` / ``.half()`` also drop the cache
+        outright (hooks below) so stale graphs do not pile up."""
+        from . import corr as _corr
+        stamp = 0
+        for t in itertools.chain(self.parameters(), self.buffers()):
+            stamp = (stamp * 1000003 + t._version * 31 + (t.data_ptr() >> 4)) & 0xFFFFFFFFFFFF
+        gru = getattr(self.update_block, "gru", None)
+        enc = getattr(self.update_block, "encoder", None)
+        return (tuple(frame1.shape), tuple(frame1.stride()), frame1.device.index, frame1.dtype, self.iters, self.final_only,
+                self.dense_precision, stamp, self.corr_fn, _corr.get_volume_precision(), self.fuse_motion_front,
+                self.fuse_gru, getattr(self, "fp16_encoder", True), getattr(gru, "recurrence", None),
+                getattr(gru, "_fuse_zr", False), getattr(self.fnet, "half_convs", False),
+                getattr(enc, "channels_last", False), self.corr_levels, self.corr_radius,
+                bool(torch.backends.cudnn.allow_tf32) if self.dense_precision is None else None,
+                bool(torch.backends.cudnn.benchmark))
+
+    def _apply(self, fn, *args, **kwargs):
+        self._graphs = {}           # .to() / .cuda() / .half(): every captured address is stale
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._graphs = {}
+        return super().load_state_dict(*args, **kwargs)
+
     @torch.no_grad()
     def forward_graphed(self, frame1, frame2):
         """Replay ``forward`` as one CUDA graph per input shape; returns the static output list.
@@ -800,7 +856,7 @@ class RAFTStereo(nn.Module):
         host synchronisation, so the 32-iteration loop captures cleanly.  Outputs are overwritten by
         the next replay of the same shape.
         """
-        key = (tuple(frame1.shape), frame1.device.index, self.iters, self.final_only, self.dense_precision)
+        key = self._graph_key(frame1)
         entry = self._graphs.get(key)
         if entry is None:
             static1, static2 = torch.empty_like(frame1), torch.empty_like(frame2)

@@ -1,0 +1,257 @@
+"""Drop-in parity THROUGH THE REFERENCE'S OWN FORWARDS: the unmodified reference models, imported
+from the vendored ``oracle/_ref`` copy, run once with their own correlation classes and once with this package's
+classes swapped in exactly as ``INTEGRATION.md`` tells a maintainer to do it:
+
+* RAFT-Stereo   ``model.corr_fn = nndepth_b200.CorrBlock1D``            (raft_stereo/model.py:58,124,132)
+* CREStereo     ``cre_stereo.model.AGCL = nndepth_b200.AGCL``           (cre_stereo/model.py:198-200,219-283)
+                -- BASELINE configs[2]: the full 1/32 -> 1/16 -> 1/8 cascade at 720x1280, batch 4
+* IGEV-Stereo   ``model.corr_fn = nndepth_b200.GeometryAwareCostVolume`` (igev_stereo/model.py:64,133-146,154) on an
+                ``IGEVStereoBase`` subclass with a small conv stand-in for the timm backbone
+
+plus BASELINE configs[3] at its full size (batch 16, 120x160) against the reference classes on ``torch.cuda``.
+Both runs of a pair use the same weights, the same inputs and strict fp32 cuDNN / cuBLAS, so the only difference
+is the correlation path.  Bar: final disparity end-point error <= 0.01 px (north_star); measured values are printed.
+"""
+import contextlib
+import time
+
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+EPE_BAR = 0.01
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("oracle/_ref is not staged: run __graft_entry__.build() in the build container first")
+    ref_shim.install()
+    return ref_shim
+
+
+@contextlib.contextmanager
+def strict_fp32():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = False
+    try:
+        with torch.no_grad():
+            yield
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+
+
+def epe(a, b):
+    """reference raft_stereo/loss.py:40-43: sqrt(sum_c (a - b)^2), mean over pixels."""
+    return torch.sum((a.float() - b.float()) ** 2, dim=1).sqrt().mean().item()
+
+
+def seeded_images(shape, seed):
+    gen = torch.Generator().manual_seed(seed)
+    left = torch.rand(shape, generator=gen) * 2 - 1
+    right = torch.rand(shape, generator=gen) * 2 - 1
+    return left, right
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# RAFT-Stereo
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision,bar", [("fp32", 1e-3), ("tf32", EPE_BAR)])
+def test_reference_raft_forward_with_swapped_corr_fn(ref, precision, bar):
+    """KITTI geometry, 32 iterations, the shipped KITTI pair + one noise pair in the batch."""
+    import nndepth_b200 as nb
+    from nndepth.models.raft_stereo.model import BaseRAFTStereo
+    from nndepth.data.dataloaders.utils import Padder
+    torch.manual_seed(0)
+    model = BaseRAFTStereo(iters=32).eval().cuda()
+    kl, kr = ref.kitti_sample_pair()
+    nl, nr = seeded_images((1, 3, 375, 1242), 1)
+    left, right = torch.cat([kl, nl]).cuda(), torch.cat([kr, nr]).cuda()
+    padder = Padder(left.shape, divis_by=32)
+    left, right = padder.pad(left, right)
+    assert tuple(left.shape) == (2, 3, 384, 1248)
+    old = nb.get_volume_precision()
+    try:
+        with strict_fp32():
+            want = model(left, right)
+            nb.set_volume_precision(precision)
+            model.corr_fn = nb.CorrBlock1D              # <- the whole integration patch
+            got = model(left, right)
+    finally:
+        nb.set_volume_precision(old)
+    assert len(got) == len(want) == 32
+    errs = [epe(g["up_disp"], w["up_disp"]) for g, w in zip(got, want)]
+    print(f"\nreference RAFT forward, corr_fn swapped ({precision} volume): final EPE {errs[-1]:.2e} px, "
+          f"worst iteration {max(errs):.2e} px, mean |disp| {want[-1]['up_disp'].abs().mean().item():.1f} px")
+    assert got[-1]["up_disp"].shape == want[-1]["up_disp"].shape == (2, 1, 384, 1248)
+    assert max(errs) < bar, errs
+
+
+def test_reference_raft_cpu_vs_swapped_gpu(ref):
+    """The CPU run of the reference (the index oracle of SURVEY fact 6) against the swapped model on the GPU."""
+    import nndepth_b200 as nb
+    from nndepth.models.raft_stereo.model import BaseRAFTStereo
+    torch.manual_seed(0)
+    model = BaseRAFTStereo(iters=12).eval()
+    left, right = seeded_images((1, 3, 192, 416), 5)
+    with torch.no_grad():
+        want = model(left, right)[-1]["up_disp"]
+    model = model.cuda()
+    model.corr_fn = nb.CorrBlock1D
+    old = nb.get_volume_precision()
+    try:
+        nb.set_volume_precision("fp32")
+        with strict_fp32():
+            got = model(left.cuda(), right.cuda())[-1]["up_disp"].cpu()
+    finally:
+        nb.set_volume_precision(old)
+    print(f"\nreference RAFT on CPU vs swapped model on GPU: final EPE {epe(got, want):.2e} px")
+    assert epe(got, want) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CREStereo: BASELINE configs[2], the whole cascade
+# ------------------------------------------------------------------------------------------------------------------
+def test_reference_crestereo_cascade_with_swapped_agcl(ref, monkeypatch):
+    import nndepth_b200 as nb
+    import nndepth.models.cre_stereo.model as cre
+    torch.manual_seed(0)
+    model = cre.CREStereoBase(iters=12).eval().cuda()
+    left, right = (t.cuda() for t in seeded_images((4, 3, 720, 1280), 1))
+    calls = {"n": 0}
+
+    class CountingAGCL(nb.AGCL):
+        def __call__(self, *a, **k):
+            calls["n"] += 1
+            return super().__call__(*a, **k)
+
+    with strict_fp32():
+        t0 = time.perf_counter()
+        want = model(left, right)
+        torch.cuda.synchronize()
+        t_ref = time.perf_counter() - t0
+        monkeypatch.setattr(cre, "AGCL", CountingAGCL)   # <- the whole integration patch
+        t0 = time.perf_counter()
+        got = model(left, right)
+        torch.cuda.synchronize()
+        t_new = time.perf_counter() - t0
+    assert len(got) == len(want) == 6 + 6 + 12
+    assert calls["n"] == 24                               # 6 + 6 offset-mode calls, 12 iter-mode calls
+    errs = [epe(g["up_disp"], w["up_disp"]) for g, w in zip(got, want)]
+    mag = torch.sum(want[-1]["up_disp"] ** 2, dim=1).sqrt().mean().item()
+    print(f"\nreference CREStereo cascade 720x1280 N=4, AGCL swapped: final EPE {errs[-1]:.2e} px, worst stage output "
+          f"{max(errs):.2e} px (mean |flow| {mag:.1f} px); forward {t_ref * 1e3:.0f} ms -> {t_new * 1e3:.0f} ms")
+    assert got[-1]["up_disp"].shape == (4, 2, 720, 1280)
+    assert max(errs) < EPE_BAR, errs
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# IGEV-Stereo
+# ------------------------------------------------------------------------------------------------------------------
+def make_igev(ref_module):
+    """``IGEVStereoBase`` with a conv stand-in for the (offline-unavailable) timm MobileNetV3: the reference's
+    ``forward`` (igev_stereo/model.py:121-160) and its ``CostVolumeFilterNetwork`` run unchanged."""
+    from nndepth.models.igev_stereo.cost_volume import CostVolumeFilterNetwork
+
+    class StandInBackbone(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.s4 = nn.Sequential(nn.Conv2d(3, 24, 7, 4, 3), nn.ReLU(), nn.Conv2d(24, 24, 3, 1, 1), nn.ReLU())
+            self.s8 = nn.Sequential(nn.Conv2d(24, 40, 3, 2, 1), nn.ReLU())
+            self.s16 = nn.Sequential(nn.Conv2d(40, 80, 3, 2, 1), nn.ReLU())
+            self.s32 = nn.Sequential(nn.Conv2d(80, 160, 3, 2, 1), nn.ReLU())
+
+        def forward(self, x):
+            f4 = self.s4(x)
+            f8 = self.s8(f4)
+            f16 = self.s16(f8)
+            return f4, f8, f16, self.s32(f16)
+
+    class IGEVStandIn(ref_module.IGEVStereoBase):
+        def __init__(self, **kw):
+            super().__init__(**kw)
+            self.fnet_proj = nn.Sequential(nn.Conv2d(24, self.hidden_dim * 2, 3, 1, 1), nn.ReLU(False))
+            self.cnet_proj = nn.Sequential(nn.Conv2d(24, self.context_dim * 2, 3, 1, 1), nn.ReLU(False))
+
+        def _init_fnet(self):
+            return StandInBackbone()
+
+        def _init_cost_volume_filter(self):
+            return CostVolumeFilterNetwork(self.cv_groups, [40, 80, 160])
+
+        def forward_fnet(self, frame1, frame2):
+            B = frame1.shape[0]
+            f4, f8, f16, f32 = self.fnet(torch.cat([frame1, frame2], dim=0))
+            cnet1 = self.cnet_proj(f4[:B])
+            fmap1, fmap2 = torch.split(self.fnet_proj(f4), B, dim=0)
+            return fmap1, fmap2, cnet1, [f8[:B], f16[:B], f32[:B]]
+
+    return IGEVStandIn
+
+
+def test_reference_igev_forward_with_swapped_corr_fn(ref):
+    import nndepth_b200 as nb
+    import nndepth.models.igev_stereo.model as igev
+    torch.manual_seed(0)
+    model = make_igev(igev)(iters=12).eval().cuda()
+    left, right = (t.cuda() for t in seeded_images((2, 3, 480, 640), 1))
+    with strict_fp32():
+        want = model(left, right)
+        model.corr_fn = nb.GeometryAwareCostVolume      # <- the whole integration patch
+        got = model(left, right)
+    assert len(got) == len(want) == 12
+    errs = [epe(g["up_disp"], w["up_disp"]) for g, w in zip(got, want)]
+    print(f"\nreference IGEV forward 480x640 N=2, corr_fn swapped: final EPE {errs[-1]:.2e} px, worst iteration "
+          f"{max(errs):.2e} px (outputs are absolute coordinates, mean {want[-1]['up_disp'].abs().mean().item():.0f})")
+    assert got[-1]["up_disp"].shape == (2, 1, 480, 640)
+    assert max(errs) < EPE_BAR, errs
+
+
+def test_config4_full_size_against_reference_classes_on_cuda(ref):
+    """BASELINE configs[3] at its full size -- batch 16, 120x160 features, 8 groups, D = 160 -- against the
+    reference's own classes on torch.cuda: group-wise volume, both pyramids, the 576-channel dual lookup, and the
+    soft-argmin initial disparity (cv_squeezer Conv3d + softmax + regress_disparity)."""
+    import nndepth_b200 as nb
+    from nndepth.models.igev_stereo.cost_volume import GeometryAwareCostVolume, CostVolumeFilterNetwork
+    B, C, H, W, G = 16, 256, 120, 160, 8
+    torch.manual_seed(0)
+    reg = CostVolumeFilterNetwork(G, [40, 80, 160]).eval().cuda()
+    squeezer = nn.Conv3d(G, 1, 3, 1, 1).cuda()
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    f1 = torch.randn(B, C, H, W, device="cuda", generator=gen)
+    f2 = torch.randn(B, C, H, W, device="cuda", generator=gen)
+    feats = [torch.randn(B, c, H // s, W // s, device="cuda", generator=gen) for c, s in ((40, 2), (80, 4), (160, 8))]
+    coords = (torch.arange(W, device="cuda").float().view(1, 1, 1, W).repeat(B, 1, H, 1)
+              - torch.rand(B, 1, H, W, device="cuda", generator=gen) * 40)
+    coords[:, :, ::7, ::11] -= 200.0                      # some pixels out of range on the left ...
+    coords[:, :, 3::7, 5::11] += 200.0                    # ... and on the right (clamped-border reads)
+    with strict_fp32():
+        want_cv = GeometryAwareCostVolume(f1, f2, feats, reg, 4, 4, G)
+        want = want_cv(coords)
+        geo0 = want_cv.geo_aware_cv[0].reshape(B, G, H, W, W).permute(0, 1, 4, 2, 3)
+        want_init = -torch.sum(torch.arange(W, device="cuda", dtype=torch.float32).view(1, -1, 1, 1)
+                               * F.softmax(squeezer(geo0).squeeze(1), dim=1), dim=1, keepdim=True)
+        scale_f = want_cv.feat_corr_cv[0].abs().max().item()
+        scale_g = want_cv.geo_aware_cv[0].abs().max().item()
+        del want_cv, geo0
+        torch.cuda.empty_cache()
+        got_cv = nb.GeometryAwareCostVolume(f1, f2, feats, reg, 4, 4, G)
+        got = got_cv(coords)
+        got_init = got_cv.init_disparity(squeezer)
+    assert got.shape == want.shape == (B, 576, H, W)
+    # channel = l*144 + src*72 + g*9 + k: feature-correlation planes (src 0) and geometry planes (src 1)
+    diff = (got - want).abs().view(B, 4, 2, 72, H, W)
+    err_f = diff[:, :, 0].max().item() / scale_f
+    err_g = diff[:, :, 1].max().item() / scale_g
+    err_i = (got_init - want_init).abs().max().item()
+    print(f"\ncfg4 full size vs reference classes on cuda: lookup feature planes {err_f:.2e}, geometry planes "
+          f"{err_g:.2e} (relative to the volume scale); init disparity max |diff| {err_i:.2e} px")
+    # fp32 everywhere: 1e-5 relative to the volume scale for the directly computed planes (north_star); the geometry
+    # planes pass through the 3-D hourglass (cuDNN fp32, different summation order on a different input rounding)
+    assert err_f < 1e-5 and err_g < 1e-4
+    assert err_i < 5e-3

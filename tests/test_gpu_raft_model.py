@@ -186,3 +186,49 @@ def test_small_all_iterations_bench_mode(golden, graph, mode):
     for i, o in enumerate(outs):
         assert o["up_disp"].shape == ref[i].shape
         assert epe(o["up_disp"], ref[i]) < EPE_BAR, (i, epe(o["up_disp"], ref[i]))
+
+
+def test_graph_replay_after_weight_reload_uses_the_new_weights():
+    """derived weights (rounded / folded / split copies) are captured by address; after load_state_dict a
+    replay must not mix fresh parameters with stale derived tensors."""
+    from nndepth_b200.raft_stereo import BaseRAFTStereo
+    torch.manual_seed(0)
+    model = BaseRAFTStereo(iters=4).eval().cuda()
+    model.dense_precision = "mixed16"
+    model.update_block.gru.fuse_gates()
+    torch.manual_seed(11)
+    other = BaseRAFTStereo(iters=4).eval().cuda()
+    other.dense_precision = "mixed16"
+    left, right = (t.cuda() for t in seeded_pair((1, 3, 128, 256)))
+    with torch.no_grad():
+        first = model.forward_graphed(left, right)[-1]["up_disp"].clone()
+        model.forward_graphed(left, right)                          # a replay
+        model.load_state_dict(other.state_dict())
+        reloaded = model.forward_graphed(left, right)[-1]["up_disp"].clone()
+        want = other(left, right)[-1]["up_disp"]
+    assert not torch.equal(first, reloaded)
+    assert epe(reloaded, want) < 1e-4, epe(reloaded, want)
+
+
+def test_dense_precision_does_not_leak_into_later_calls():
+    """after a mixed16 run, ``dense_precision = None`` runs on the caller's own flags again (fp32 recurrence,
+    fp32 encoder), eagerly and in a freshly captured graph."""
+    from nndepth_b200.raft_stereo import BaseRAFTStereo
+    torch.manual_seed(0)
+    model = BaseRAFTStereo(iters=4).eval().cuda()
+    left, right = (t.cuda() for t in seeded_pair((1, 3, 128, 256)))
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            before = model(left, right)[-1]["up_disp"].clone()
+            model.dense_precision = "mixed16"
+            model(left, right)
+            assert model.update_block.gru.recurrence is None and not getattr(model.fnet, "half_convs", False)
+            model.dense_precision = None
+            after = model(left, right)[-1]["up_disp"].clone()
+            graphed = model.forward_graphed(left, right)[-1]["up_disp"].clone()
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert torch.equal(before, after)
+    assert epe(graphed, before) < 1e-5

@@ -136,3 +136,48 @@ def test_weight_caches_follow_in_place_updates():
         block.norm1.running_var.fill_(4.0)
     f_b = block._folded()[0][0]
     assert not torch.equal(f_a, f_b)
+
+
+def test_fused_gate_weights_follow_parameter_updates_and_keep_autograd():
+    """the concatenated z|r gate weights are keyed on the parameters' versions (no stale snapshot after
+    load_state_dict / in-place updates) and are bypassed under grad mode (convz / convr keep their gradients)."""
+    import torch
+    from nndepth_b200.raft_stereo import SepConvGRU
+    torch.manual_seed(0)
+    gru = SepConvGRU(hidden_dim=8, input_dim=12).eval()
+    plain = SepConvGRU(hidden_dim=8, input_dim=12).eval()
+    h, x = torch.tanh(torch.randn(1, 8, 5, 7)), torch.randn(1, 12, 5, 7)
+    gru.fuse_gates()
+    with torch.no_grad():
+        gru(h, x)                                           # populates the fused cache with the OLD weights
+        gru.load_state_dict(plain.state_dict())             # in-place update
+        torch.testing.assert_close(gru(h, x), plain(h, x), rtol=1e-5, atol=1e-6)
+        gru.convz1.weight.mul_(0.5)
+        plain.convz1.weight.mul_(0.5)
+        torch.testing.assert_close(gru(h, x), plain(h, x), rtol=1e-5, atol=1e-6)
+    gru.train()
+    gru(h, x).sum().backward()
+    assert gru.convz1.weight.grad is not None and gru.convr2.weight.grad is not None
+
+
+def test_graph_key_changes_with_weights_and_switches():
+    """everything a captured graph bakes in is part of its cache key."""
+    import torch
+    from nndepth_b200.raft_stereo import BaseRAFTStereo
+    model = BaseRAFTStereo(iters=2).eval()
+    x = torch.zeros(1, 3, 64, 64)
+    k0 = model._graph_key(x)
+    assert model._graph_key(x) == k0
+    model._graphs["sentinel"] = 1
+    model.load_state_dict(model.state_dict())
+    assert model._graphs == {} and model._graph_key(x) != k0          # versions bumped, cache dropped
+    k1 = model._graph_key(x)
+    for attr, value in (("fuse_gru", False), ("fuse_motion_front", False), ("fp16_encoder", False), ("final_only", True),
+                        ("dense_precision", "mixed16")):
+        old = getattr(model, attr, None)
+        setattr(model, attr, value)
+        assert model._graph_key(x) != k1, attr
+        setattr(model, attr, old)
+    model._graphs["sentinel"] = 1
+    model.float()
+    assert model._graphs == {}
