@@ -22,77 +22,9 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "lookup_common.cuh"
 
 namespace nnd {
-
-struct LookupArgs {
-  ConstPyramid src[2];  // [0] = feature correlation, [1] = geometry volume (IGEV only)
-  const float* coords;
-  float* out;
-  int hw;           // H * W1 (pixels per image)
-  int G;            // planes (groups) per pixel and source
-  int n_src;        // 1 or 2
-  int num_levels;
-  int radius;
-  int mode;              // 0: channel = l*(S*G*T) + s*(G*T) + g*T + k ; 1: GroupCorrBlock1D view quirk
-  int planes_per_block;  // chunk of the S*G planes handled by one block (blockIdx.y selects it)
-  int vec;               // 1: pitches % 4 == 0 and bases 16-byte aligned -> float4 loads
-};
-
-// One tap of linear_sampler: position t (fp32, reference op order), neighbours i0 <= i1, lerp weights.
-struct Tap {
-  int i0, i1;
-  float coef, one_minus;
-};
-
-struct LevelScale {
-  float span;      // w2 - 1
-  float inv_span;  // RN(1 / span)
-  float inv_pow2;  // 1 / 2**level (exact)
-};
-
-// x / span, correctly rounded, for x in [-1, span + 1]:  q = RN(x*y), r = x - q*span (exact, FMA),
-// q' = RN(q + r*y) with y = RN(1/span) is the IEEE quotient (Markstein's theorem; span is a small
-// positive integer, so y is never the all-ones-significand exception).  Inputs outside [-1, span+1]
-// are clamped first, which cannot change clamp(x/span, 0, 1); NaN becomes -1 (-> t = 0).
-// The theorem needs the residual r free of underflow, i.e. |x| >= ~2^-100.  For smaller non-zero |x|
-// the interpolated VALUE is unaffected (t is then 0 or a denormal: either way the result is row[0]
-// exactly), but ceil(t) could differ; EXACT_TINY (the index-reporting kernel) therefore routes those
-// inputs through the generic IEEE division.
-template <bool EXACT_TINY>
-__device__ __forceinline__ float sampler_quotient(float x, const LevelScale& s) {
-  x = fminf(fmaxf(x, -1.0f), s.span + 1.0f);
-  if (EXACT_TINY && fabsf(x) < 1e-30f) return __fdiv_rn(x, s.span);
-  const float q = __fmul_rn(x, s.inv_span);
-  const float r = __fmaf_rn(-q, s.span, x);
-  return __fmaf_rn(r, s.inv_span, q);
-}
-
-__device__ __forceinline__ LevelScale level_scale(int width, int lvl, float centre) {
-  LevelScale s;
-  s.span = static_cast<float>(width - 1);
-  s.inv_span = __frcp_rn(s.span);
-  s.inv_pow2 = 1.0f / static_cast<float>(1 << lvl);
-  (void)centre;
-  return s;
-}
-
-template <bool EXACT_TINY = false>
-__device__ __forceinline__ Tap make_tap(int k, int r, float centre, const LevelScale& s) {
-  // dx + coords / 2**i (cost_volume.py:44-46): dx = k - r is an exact small integer
-  const float x = __fadd_rn(static_cast<float>(k - r), centre);
-  // clamp(x / (w2-1), 0, 1) * (w2-1)   (utils.py:16-18); __saturatef maps NaN to 0
-  const float t = __fmul_rn(__saturatef(sampler_quotient<EXACT_TINY>(x, s)), s.span);
-  const float f0 = floorf(t);
-  Tap tap;
-  tap.i0 = static_cast<int>(f0);
-  const bool whole = (t == f0);
-  tap.i1 = tap.i0 + (whole ? 0 : 1);                        // ceil(t)
-  const float f1 = whole ? f0 : __fadd_rn(f0, 1.0f);        // float(idx1), exact
-  tap.coef = __fsub_rn(f1, t);                              // coef = idx1 - t      (utils.py:26)
-  tap.one_minus = __fsub_rn(1.0f, tap.coef);                // (1 - coef)           (utils.py:27)
-  return tap;
-}
 
 // WINQ : 16-byte quads per staged window (window = 4*WINQ floats >= 2r+6)
 // TAPS : compile-time tap count (2r+1) -> per-tap state lives in registers across planes; 0 = dynamic
@@ -479,12 +411,6 @@ corr1d_lookup_conv1x1_kernel(const __grid_constant__ LookupArgs a, const float* 
 // the lookup itself, 80 MMAs per warp fed from the 36 x 32 tile the lookup left in shared memory, and the
 // output stores.  The GEMM all but vanishes; the kernel costs a lookup plus a 61 MB write.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t y;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(y) : "f"(x));
-  return y;
-}
-
 __device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   // not volatile: the scheduler may interleave independent accumulation chains
   asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
@@ -746,294 +672,6 @@ corr1d_lookup_conv1x1_tc_kernel(const __grid_constant__ LookupArgs a, const floa
     c = c1; b = b1; rem0 = rem01;
     c1 = c2; b1 = b2; rem01 = rem02;
     buf ^= 1;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// The same fused lookup + convc1 + ReLU on the 5th-generation tensor cores (tcgen05, accumulators in TMEM) for the
-// shipping shape (c_out = 256, channels-last output).  The mma.sync kernel above keeps the 256 x 40 weight matrix in
-// registers (80 per thread), which caps it at 12 warps per SM and leaves it latency-bound; here the weights sit in
-// shared memory ONCE per CTA (K-major, no swizzle: 8-row x 16-byte core matrices), a tile is 128 pixels, the
-// interpolated taps of a tile are written straight into the A operand's core-matrix layout, one thread issues five
-// tcgen05.mma (M = 128, N = 256, K = 8) into 256 TMEM columns, and all eight warps run the epilogue
-// (tcgen05.ld 32 columns -> bias -> ReLU -> fp16/fp32 -> 64/128 contiguous bytes per thread).  Windows of tile t+1
-// are gathered with cp.async while tile t is interpolated, multiplied and written.
-// Pixels are addressed flat over the batch (pyramid rows, coordinates and channels-last output are all contiguous
-// in b*H*W + p), so a tile may straddle two images.
-// ------------------------------------------------------------------------------------------------
-namespace umma {
-constexpr int TILE = 128;                 // pixels per tile = UMMA M
-constexpr int NOUT = 256;                 // c_out = UMMA N = TMEM columns
-constexpr int KSTEPS = 5;                 // K = 40 (36 taps + 4 zero columns) in k-steps of 8
-constexpr int A_KSTEP_BYTES = TILE * 32;  // one k-step of A: 128 rows x 32 bytes
-constexpr int B_KSTEP_BYTES = NOUT * 32;
-constexpr int WSTRIDE = 20;               // floats per window row (16 + 4 pad, 16-byte aligned)
-constexpr int WIN_BUF_FLOATS = 4 * TILE * WSTRIDE;
-constexpr int SMEM_B = 0;
-constexpr int SMEM_A = SMEM_B + KSTEPS * B_KSTEP_BYTES;            // 40960
-constexpr int SMEM_WIN = SMEM_A + KSTEPS * A_KSTEP_BYTES;          // + 20480
-constexpr int SMEM_BIAS = SMEM_WIN + 2 * WIN_BUF_FLOATS * 4;       // + 81920
-constexpr int SMEM_COORD = SMEM_BIAS + NOUT * 4;                   // [2 buffers][TILE] coordinates of the tiles in flight
-constexpr int SMEM_BAR = SMEM_COORD + 2 * TILE * 4;
-constexpr int SMEM_STAGE = SMEM_BAR + 64;                          // fp16 output tile [TILE][NOUT], 16-byte chunks XOR-swizzled
-constexpr int SMEM_TOTAL = SMEM_STAGE + TILE * NOUT * 2;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  long long t0 = 0;
-  int spins = 0;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (!done && ++spins == 1024) {  // watchdog: a protocol bug must fault, not hang the GPU
-      spins = 0;
-      const long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 2000000000LL) __trap();
-    }
-  } while (!done);
-}
-// K-major operand without swizzle: 16-byte K chunks of 8 consecutive rows form a 128-byte core matrix;
-// lbo = distance between the two K chunks of a k-step, sbo = distance between 8-row groups.
-__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  return d;   // layout type 0: no swizzle
-}
-// element (row r, column k) of an operand region whose k-steps are blocks of `kstep_bytes`
-__device__ __forceinline__ uint32_t operand_offset(int r, int k, int kstep_bytes) {
-  return static_cast<uint32_t>((k >> 3) * kstep_bytes + (r >> 3) * 256 + ((k >> 2) & 1) * 128 + (r & 7) * 16 + (k & 3) * 4);
-}
-__device__ __forceinline__ void ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-}  // namespace umma
-
-// weight: (K = 36, 256) k-major fp32; out: channels-last (B*H*W, 256) fp32 (out_f16 = 0) or fp16 (1)
-__global__ void __launch_bounds__(512, 1)
-corr1d_lookup_conv1x1_umma_kernel(const __grid_constant__ LookupArgs a, const float* __restrict__ weight,
-                                  const float* __restrict__ bias, int relu, int out_f16, long long total_px,
-                                  long long n_tiles) {
-  using namespace umma;
-  constexpr int TAPS = 9, R = 4, K = 36;
-  extern __shared__ __align__(1024) unsigned char usm[];
-  float* bias_s = reinterpret_cast<float*>(usm + SMEM_BIAS);
-  float* wins = reinterpret_cast<float*>(usm + SMEM_WIN);
-  const uint32_t bar = smem_u32(usm + SMEM_BAR);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(usm + SMEM_BAR + 16);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-  // ---- one-time set-up: weights -> B operand (TF32, round to nearest), zero the K padding, bias, barrier, TMEM ----
-  {
-    // all of a thread's weight loads are issued before the first is used (a load -> convert -> store loop pays the
-    // DRAM latency once per element: 20 serialized round trips cost more than the rest of the kernel)
-    constexpr int PER_THREAD = NOUT * 40 / 512;
-    float wv[PER_THREAD];
-#pragma unroll
-    for (int j = 0; j < PER_THREAD; ++j) {
-      const int idx = tid + 512 * j, n = idx & (NOUT - 1), k = idx >> 8;
-      wv[j] = k < K ? __ldg(weight + static_cast<long long>(k) * NOUT + n) : 0.f;
-    }
-#pragma unroll
-    for (int j = 0; j < PER_THREAD; ++j) {
-      const int idx = tid + 512 * j, n = idx & (NOUT - 1), k = idx >> 8;
-      *reinterpret_cast<uint32_t*>(usm + SMEM_B + operand_offset(n, k, B_KSTEP_BYTES)) = to_tf32(wv[j]);
-    }
-  }
-  for (int idx = tid; idx < TILE * 4; idx += 512)   // A columns 36..39 stay zero for the whole kernel
-    *reinterpret_cast<uint32_t*>(usm + SMEM_A + operand_offset(idx >> 2, K + (idx & 3), A_KSTEP_BYTES)) = 0u;
-  if (tid < NOUT) bias_s[tid] = bias ? __ldg(bias + tid) : 0.f;
-  if (tid == 0) {
-    mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(NOUT)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
-
-  // 16 warps: half the per-thread work of an 8-warp CTA in every phase (the phases are latency-, not issue-bound)
-  // gather role: thread = (16-byte quarter q, pixel p32 of a 32-pixel pass, level): 4 pixel passes
-  const int gq = tid & 3, gp = (tid >> 2) & 31, glvl = tid >> 7;
-  // interpolation role: thread = (pixel m of the tile, level)
-  const int im = tid & (TILE - 1), ilvl = tid >> 7;
-
-  float* coord_s = reinterpret_cast<float*>(usm + SMEM_COORD);
-  // coordinates of the gather role's four pixels, always fetched one tile ahead of their use (no global latency
-  // between a tile's coordinates and its cp.async issue); the gather also parks them in shared memory for the
-  // interpolation phase of that tile
-  auto load_coords = [&](long long tile, float (&cn)[4]) {
-#pragma unroll
-    for (int pass = 0; pass < 4; ++pass) {
-      const long long px = tile * TILE + pass * 32 + gp;
-      cn[pass] = (tile < n_tiles && px < total_px) ? __ldg(a.coords + px) : 0.f;
-    }
-  };
-  auto issue_windows = [&](long long tile, int buf, const float (&cn)[4]) {
-    if (tile < n_tiles) {
-#pragma unroll
-      for (int pass = 0; pass < 4; ++pass) {
-        const int m = pass * 32 + gp;
-        const long long px = tile * TILE + m;
-        const float c = cn[pass];
-        if (gq == 0 && glvl == 0) coord_s[buf * TILE + m] = c;
-        if (px < total_px) {
-          {
-            const int lvl = glvl;
-            const int w = a.src[0].width[lvl], pitch = a.src[0].pitch[lvl];
-            const float centre = __fmul_rn(c, 1.0f / static_cast<float>(1 << lvl));
-            const LevelScale sc = level_scale(w, lvl, 0.f);
-            const int s = make_tap(0, R, centre, sc).i0 & ~3;
-            const int hi = make_tap(TAPS - 1, R, centre, sc).i1;
-            const int cq = s + 4 * gq;
-            if (cq <= hi && cq < w) {
-              const float* src = a.src[0].ptr[lvl] + px * pitch + cq;
-              const uint32_t dst = smem_u32(wins + buf * WIN_BUF_FLOATS + (lvl * TILE + m) * WSTRIDE + 4 * gq);
-              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-            }
-          }
-        }
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-
-  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(NOUT >> 3) << 17) |
-                         (static_cast<uint32_t>(TILE >> 4) << 24);   // D f32, A/B tf32, both K-major
-  const long long stride = gridDim.x;
-  long long tile = blockIdx.x;
-  int buf = 0;
-  uint32_t phase = 0;
-  float cn[4];
-  load_coords(tile, cn);
-  issue_windows(tile, 0, cn);
-  load_coords(tile + stride, cn);
-  for (; tile < n_tiles; tile += stride, buf ^= 1) {
-    issue_windows(tile + stride, buf ^ 1, cn);                 // next tile's gather flies during this whole iteration
-    load_coords(tile + 2 * stride, cn);                        // and the coordinates after that
-    asm volatile("cp.async.wait_group 1;" ::: "memory");        // this tile's windows have landed (my own copies)
-    __syncthreads();                                            // ... and everybody else's
-    // ---- interpolate: 9 taps of one level for pixel im, straight into the A operand ----
-    {
-      const long long px = tile * TILE + im;
-      const bool live = px < total_px;
-      const float c = coord_s[buf * TILE + im];
-      {
-        const int lvl = ilvl;
-        const int w = a.src[0].width[lvl];
-        const float centre = __fmul_rn(c, 1.0f / static_cast<float>(1 << lvl));
-        const LevelScale sc = level_scale(w, lvl, 0.f);
-        const int s = make_tap(0, R, centre, sc).i0 & ~3;
-        const float* mine = wins + buf * WIN_BUF_FLOATS + (lvl * TILE + im) * WSTRIDE - s;
-#pragma unroll
-        for (int k = 0; k < TAPS; ++k) {
-          const Tap tp = make_tap(k, R, centre, sc);
-          const float val = live ? __fadd_rn(__fmul_rn(tp.coef, mine[tp.i0]), __fmul_rn(tp.one_minus, mine[tp.i1])) : 0.f;
-          *reinterpret_cast<uint32_t*>(usm + SMEM_A + operand_offset(im, lvl * TAPS + k, A_KSTEP_BYTES)) = to_tf32(val);
-        }
-      }
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-    __syncthreads();
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-      for (int ks = 0; ks < KSTEPS; ++ks) {
-        const uint64_t adesc = desc_kmajor(smem_u32(usm + SMEM_A + ks * A_KSTEP_BYTES), 128, 256);
-        const uint64_t bdesc = desc_kmajor(smem_u32(usm + SMEM_B + ks * B_KSTEP_BYTES), 128, 256);
-        const uint32_t acc = ks > 0 ? 1u : 0u;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-            ::"r"(tmem_base), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-            : "memory");
-      }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-    }
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // ---- epilogue: warp = (lane quarter, column quarter); thread = one pixel row x 2 chunks of 32 channels ----
-    {
-      const int lq = warp & 3, ch = warp >> 2;
-      const int m = 32 * lq + lane;
-      const long long px = tile * TILE + m;
-#pragma unroll
-      for (int cchunk = 0; cchunk < 2; ++cchunk) {
-        const int col0 = 64 * ch + 32 * cchunk;
-        float v[32];
-        ld32(tmem_base + (static_cast<uint32_t>(32 * lq) << 16) + col0, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          v[i] += bias_s[col0 + i];
-          if (relu) v[i] = fmaxf(v[i], 0.f);
-        }
-        if (out_f16) {
-          // a thread owns a pixel ROW: stored directly, a warp instruction would touch 32 rows x 16 bytes.  Stage the
-          // tile in shared memory (16-byte chunk c of row m at chunk c ^ (m & 31): conflict-free both ways) ...
-          uint4* stage = reinterpret_cast<uint4*>(usm + SMEM_STAGE);
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            stage[m * 32 + (((col0 >> 3) + i) ^ (m & 31))] =
-                make_uint4(pack_h2(v[8 * i], v[8 * i + 1]), pack_h2(v[8 * i + 2], v[8 * i + 3]),
-                           pack_h2(v[8 * i + 4], v[8 * i + 5]), pack_h2(v[8 * i + 6], v[8 * i + 7]));
-        } else if (px < total_px) {
-          float4* dst = reinterpret_cast<float4*>(a.out + px * NOUT + col0);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        }
-      }
-    }
-    if (out_f16) {
-      // ... and write it out 512 contiguous bytes per pixel: warp = 8 pixel rows, lane = one 16-byte chunk
-      __syncthreads();
-      const uint4* stage = reinterpret_cast<const uint4*>(usm + SMEM_STAGE);
-      uint4* out16 = reinterpret_cast<uint4*>(a.out);
-#pragma unroll
-      for (int r = 0; r < TILE / 16; ++r) {
-        const int row = warp * (TILE / 16) + r;
-        const long long px = tile * TILE + row;
-        if (px < total_px) out16[px * 32 + lane] = stage[row * 32 + (lane ^ (row & 31))];
-      }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();   // TMEM drained and the A tile consumed before the next tile overwrites them
-  }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
-  if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(NOUT) : "memory");
   }
 }
 
@@ -1304,6 +942,11 @@ static nnd_status launch_lookup(const float* const* level_a, const float* const*
 
 }  // namespace nnd
 
+namespace nnd {
+nnd_status launch_lookup_conv1x1_ws(const LookupArgs& a, const float* weight, const float* bias, int relu, int out_f16,
+                                    long long total_px, cudaStream_t stream);
+}
+
 extern "C" {
 
 nnd_status nnd_corr1d_lookup(const float* const* level, const int* width, const int* pitch, const float* coords,
@@ -1414,21 +1057,11 @@ nnd_status nnd_corr1d_lookup_conv1x1(const float* const* level, const int* width
   NND_REQUIRE(out_layout >= 0 && out_layout <= 2,
               "lookup_conv1x1: out_layout %d is not 0 (fp32 NCHW), 1 (fp32 channels-last) or 2 (fp16 channels-last)", out_layout);
   const long long n_groups_all = static_cast<long long>(B) * ((a.hw + 31) / 32);
-  if (precision == NND_PREC_TF32 && c_out == 256 && out_layout != 0 && vec && getenv("NND_LOOKUP_UMMA") &&
-      getenv("NND_LOOKUP_UMMA")[0] == '1') {
-    // tcgen05 path (opt-in, NND_LOOKUP_UMMA=1): weights in shared memory, accumulators in TMEM, 128-pixel tiles.
-    // Parity-green but not yet faster than the mma.sync kernel below (33.8 vs 29.2 us isolated, 32.8 vs 28.6 us in
-    // the step): DESIGN.md section 8.
-    const long long total_px = static_cast<long long>(B) * a.hw;
-    const long long n_tiles = (total_px + umma::TILE - 1) / umma::TILE;
-    cudaError_t ae = cudaFuncSetAttribute(corr1d_lookup_conv1x1_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          umma::SMEM_TOTAL);
-    if (ae != cudaSuccess) return cuda_fail(ae, "lookup_conv1x1: shared-memory attribute");
-    const long long sms = sm_count();
-    corr1d_lookup_conv1x1_umma_kernel<<<static_cast<unsigned>(n_tiles < sms ? n_tiles : sms), 512, umma::SMEM_TOTAL,
-                                        reinterpret_cast<cudaStream_t>(stream)>>>(a, weight, bias, relu ? 1 : 0,
-                                                                                  out_layout == 2 ? 1 : 0, total_px, n_tiles);
-    return check_launch("corr1d_lookup_conv1x1_umma_kernel");
+  if (precision == NND_PREC_TF32 && c_out == 256 && out_layout != 0 && vec) {
+    // the shipping shape: warp-specialised tcgen05 kernel (lookup_ws.cu) -- weights in shared memory, accumulators in
+    // TMEM, producer / MMA / epilogue warps decoupled by mbarrier pipelines
+    return launch_lookup_conv1x1_ws(a, weight, bias, relu ? 1 : 0, out_layout == 2 ? 1 : 0,
+                                    static_cast<long long>(B) * a.hw, reinterpret_cast<cudaStream_t>(stream));
   }
   if (precision == NND_PREC_TF32 && c_out <= 256) {
     // tensor-core path: weights live in registers, shared memory holds only the lookup tiles

@@ -1,0 +1,353 @@
+// Warp-specialised tcgen05 form of the fused per-iteration kernel of RAFT-Stereo (sm_100a):
+//
+//     out[px, :] = relu(W . lookup(coords[px]) + b)          W = convc1's 1x1 weights, 36 -> 256
+//
+//   CorrBlock1D.__call__     raft_stereo/cost_volume.py:36-53   (4 levels x 9 taps, linear_sampler utils.py:4-27)
+//   BasicMotionEncoder       blocks/update_block.py:51,58       cor = F.relu(self.convc1(corr))
+//
+// The (B, 36, H, W) lookup tensor never exists in HBM, and no warp ever waits for another role:
+//
+//   warps  0-15  PRODUCERS   warp = (32-pixel group of the 128-pixel tile, pyramid level).  cp.async gathers the 32
+//                            windows of the NEXT tile into a private double buffer (4 lanes x 16 bytes per window,
+//                            coordinates prefetched two tiles ahead), interpolates the 9 taps of the current tile with
+//                            the reference's exact fp32 operation order (bit-exact indices) and writes them, rounded
+//                            to nearest TF32, straight into the A operand's core-matrix layout: K is laid out as
+//                            4 levels x 12 columns (9 taps + 3 zeros), so a thread's taps are three 16-byte stores.
+//   warp   20    MMA         one thread: 6 x tcgen05.mma kind::tf32 (M 128 pixels, N 256 channels, K 8) per tile into
+//                            one of two 256-column TMEM accumulators; tcgen05.commit releases the A slot to the
+//                            producers and hands the accumulator to the epilogue.
+//   warps 16-19  EPILOGUE    stage the weights (once, while the producers already gather), then per tile:
+//                            tcgen05.ld 32 columns -> + bias -> ReLU -> fp16 / fp32 -> XOR-swizzled per-warp staging
+//                            -> 256-byte contiguous row segments of the channels-last output.
+//
+// mbarrier pipelines: a_full / a_empty (producers <-> MMA, ring of NA operand slots), tmem_full / tmem_empty (MMA <->
+// epilogue, 2 accumulators), b_ready (weights staged).  Work is split in CONTIGUOUS pixel ranges of equal length
+// (one per SM, flat over the batch), so every CTA gathers and stores the same number of pixels: at the KITTI shape
+// 405 pixels = 3.16 tiles each instead of 3 tiles on most SMs and 4 on 24 of them.
+#include "common.cuh"
+#include "lookup_common.cuh"
+
+namespace nnd {
+namespace ws {
+
+constexpr int TILE = 128;                   // pixels per tile = UMMA M
+constexpr int NOUT = 256;                   // output channels = UMMA N = TMEM columns per accumulator
+constexpr int KCOLS = 12;                   // operand columns per level: 9 taps + 3 zeros
+constexpr int KSTEPS = 6;                   // K = 48 in k-steps of 8
+constexpr int A_KSTEP_BYTES = TILE * 32;
+constexpr int B_KSTEP_BYTES = NOUT * 32;
+constexpr int A_SLOT_BYTES = KSTEPS * A_KSTEP_BYTES;   // 24 KB
+constexpr int NA = 2;                       // A-operand ring
+constexpr int PROD_WARPS = 16;
+constexpr int EPI_WARP0 = 16;
+constexpr int EPI_WARPS = 4;
+constexpr int MMA_WARP = 20;
+constexpr int THREADS = 32 * (MMA_WARP + 1);
+constexpr int WSTRIDE = 20;                 // floats per staged window (16 + 4: 16-byte aligned rows)
+constexpr int WIN_BUF_FLOATS = 32 * WSTRIDE;
+constexpr int STAGE_ROW_BYTES = 256;        // one pass of the epilogue writes 256 bytes of every pixel row
+constexpr int STAGE_WARP_BYTES = 32 * STAGE_ROW_BYTES;
+
+constexpr int SMEM_B = 0;
+constexpr int SMEM_A = SMEM_B + KSTEPS * B_KSTEP_BYTES;                       // 48 KB
+constexpr int SMEM_WIN = SMEM_A + NA * A_SLOT_BYTES;                          // + 48 KB
+constexpr int SMEM_STAGE = SMEM_WIN + PROD_WARPS * 2 * WIN_BUF_FLOATS * 4;    // + 80 KB
+constexpr int SMEM_BIAS = SMEM_STAGE + EPI_WARPS * STAGE_WARP_BYTES;          // + 32 KB
+constexpr int SMEM_BAR = SMEM_BIAS + NOUT * 4;
+constexpr int SMEM_TOTAL = SMEM_BAR + 128;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// byte offset of the 16-byte chunk `ch` (4 consecutive K columns) of operand row `r`
+__device__ __forceinline__ uint32_t chunk_offset(int r, int ch, int kstep_bytes) {
+  return static_cast<uint32_t>((ch >> 1) * kstep_bytes + (r >> 3) * 256 + (ch & 1) * 128 + (r & 7) * 16);
+}
+
+}  // namespace ws
+
+// out: channels-last (B*H*W, 256), fp16 (OUT_F16) or fp32.  weight: (36, 256) k-major fp32.
+template <bool OUT_F16>
+__global__ void __launch_bounds__(ws::THREADS, 1)
+corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const float* __restrict__ weight,
+                                const float* __restrict__ bias, int relu, long long total_px, long long px_per_cta) {
+  using namespace ws;
+  using umma::smem_u32;
+  using umma::mbar_init;
+  using umma::mbar_wait;
+  constexpr int TAPS = 9, R = 4;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  const uint32_t bar0 = smem_u32(smem + SMEM_BAR);
+  auto a_full = [&](int s) { return bar0 + 8u * s; };
+  auto a_empty = [&](int s) { return bar0 + 8u * (NA + s); };
+  auto tmem_full = [&](int s) { return bar0 + 8u * (2 * NA + s); };
+  auto tmem_empty = [&](int s) { return bar0 + 8u * (2 * NA + 2 + s); };
+  const uint32_t b_ready = bar0 + 8u * (2 * NA + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SMEM_BAR + 8 * (2 * NA + 5));
+
+  const long long px0 = static_cast<long long>(blockIdx.x) * px_per_cta;
+  const long long px_end = px0 + px_per_cta < total_px ? px0 + px_per_cta : total_px;
+  const int nt = px_end > px0 ? static_cast<int>((px_end - px0 + TILE - 1) / TILE) : 0;
+
+  if (warp == MMA_WARP) {
+    if (lane == 0) {
+      for (int s = 0; s < NA; ++s) {
+        mbar_init(a_full(s), PROD_WARPS);
+        mbar_init(a_empty(s), 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(tmem_full(s), 1);
+        mbar_init(tmem_empty(s), 32 * EPI_WARPS);
+      }
+      mbar_init(b_ready, EPI_WARPS);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < PROD_WARPS) {
+    // =========================================== producers ===========================================
+    const int pg = warp & 3, lvl = warp >> 2;
+    const int m = 32 * pg + lane;                       // my pixel's row of the tile
+    const int w = a.src[0].width[lvl], pitch = a.src[0].pitch[lvl];
+    const float* __restrict__ lbase = a.src[0].ptr[lvl];
+    const LevelScale sc = level_scale(w, lvl, 0.f);
+    const float inv_pow2 = 1.0f / static_cast<float>(1 << lvl);
+    float* const wins = reinterpret_cast<float*>(smem + SMEM_WIN) + warp * (2 * WIN_BUF_FLOATS);
+    const int q = lane & 3;
+    constexpr unsigned FULL = 0xffffffffu;
+
+    auto coord_of = [&](int t) -> float {
+      const long long px = px0 + static_cast<long long>(t) * TILE + m;
+      return (t < nt && px < px_end) ? __ldg(a.coords + px) : 0.0f;
+    };
+    auto issue_windows = [&](int t, float c, float* win) {
+      if (t < nt) {
+        const float centre = __fmul_rn(c, inv_pow2);
+        const int s = make_tap(0, R, centre, sc).i0 & ~3;
+        const int hi = make_tap(TAPS - 1, R, centre, sc).i1;
+        const long long grp0 = px0 + static_cast<long long>(t) * TILE + 32 * pg;   // first pixel of my group
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int p = j * 8 + (lane >> 2);
+          const int sp = __shfl_sync(FULL, s, p);
+          const int hp = __shfl_sync(FULL, hi, p);
+          const int cq = sp + 4 * q;
+          if (grp0 + p < px_end && cq <= hp && cq < w) {
+            const float* src = lbase + (grp0 + p) * pitch + cq;
+            const uint32_t dst = smem_u32(win + p * WSTRIDE + 4 * q);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+          }
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    float c0 = coord_of(0), c1 = coord_of(1);
+    issue_windows(0, c0, wins);
+    for (int t = 0; t < nt; ++t) {
+      const float c2 = coord_of(t + 2);                          // in flight during this whole iteration
+      issue_windows(t + 1, c1, wins + ((t + 1) & 1) * WIN_BUF_FLOATS);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");         // tile t's windows (my copies) have landed
+      __syncwarp();                                               // ... and the other lanes' copies
+      const int slot = t % NA;
+      mbar_wait(a_empty(slot), ((t / NA) & 1) ^ 1);               // the MMAs that read this slot have completed
+      {
+        const long long px = px0 + static_cast<long long>(t) * TILE + m;
+        const bool live = px < px_end;
+        const float centre = __fmul_rn(c0, inv_pow2);
+        const int s = make_tap(0, R, centre, sc).i0 & ~3;
+        const float* mine = wins + (t & 1) * WIN_BUF_FLOATS + lane * WSTRIDE - s;
+        uint32_t v[12];
+#pragma unroll
+        for (int k = 0; k < TAPS; ++k) {
+          const Tap tp = make_tap(k, R, centre, sc);
+          // coef * val0 + (1 - coef) * val1, each operation rounded (utils.py:27); then RN to TF32 for the MMA
+          const float val = live ? __fadd_rn(__fmul_rn(tp.coef, mine[tp.i0]), __fmul_rn(tp.one_minus, mine[tp.i1])) : 0.f;
+          v[k] = to_tf32(val);
+        }
+        v[9] = v[10] = v[11] = 0u;
+        unsigned char* slot_base = smem + SMEM_A + slot * A_SLOT_BYTES;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          *reinterpret_cast<uint4*>(slot_base + chunk_offset(m, 3 * lvl + i, A_KSTEP_BYTES)) =
+              make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
+      fence_proxy_async();                                        // generic-proxy writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full(slot));
+      c0 = c1;
+      c1 = c2;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else if (warp == MMA_WARP) {
+    // =========================================== MMA issuer ===========================================
+    if (lane == 0 && nt > 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(NOUT >> 3) << 17) |
+                             (static_cast<uint32_t>(TILE >> 4) << 24);   // D f32, A/B tf32, both K-major
+      mbar_wait(b_ready, 0);
+      for (int t = 0; t < nt; ++t) {
+        const int slot = t % NA, acc = t & 1;
+        mbar_wait(tmem_empty(acc), ((t >> 1) & 1) ^ 1);           // the epilogue has drained this accumulator
+        mbar_wait(a_full(slot), (t / NA) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+          const uint64_t adesc = umma::desc_kmajor(smem_u32(smem + SMEM_A + slot * A_SLOT_BYTES + ks * A_KSTEP_BYTES), 128, 256);
+          const uint64_t bdesc = umma::desc_kmajor(smem_u32(smem + SMEM_B + ks * B_KSTEP_BYTES), 128, 256);
+          const uint32_t accum = ks > 0 ? 1u : 0u;
+          asm volatile(
+              "{\n\t.reg .pred p;\n\t"
+              "setp.ne.b32 p, %4, 0;\n\t"
+              "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+              ::"r"(tmem_base + static_cast<uint32_t>(acc * NOUT)), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+              : "memory");
+        }
+        tc_commit(a_empty(slot));        // implicit tcgen05.fence::before_thread_sync
+        tc_commit(tmem_full(acc));
+      }
+    }
+  } else {
+    // =========================================== epilogue ===========================================
+    const int eq = warp - EPI_WARP0;                    // TMEM lane quarter this warp may read (warp % 4)
+    const int et = tid - 32 * EPI_WARP0;                // 0..127
+    float* bias_s = reinterpret_cast<float*>(smem + SMEM_BIAS);
+    {
+      // weights -> B operand (TF32, round to nearest), K laid out as 4 levels x (9 taps + 3 zero columns).  All of a
+      // thread's loads are issued before the first is used; the producers are already gathering meanwhile.
+      constexpr int TOTAL = NOUT * KSTEPS * 8, PER_THREAD = TOTAL / (32 * EPI_WARPS), BATCH = 24;
+      static_assert(PER_THREAD % BATCH == 0, "weight staging batches");
+      for (int j0 = 0; j0 < PER_THREAD; j0 += BATCH) {
+        float wv[BATCH];
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j) {
+          const int idx = et + 128 * (j0 + j), n = idx & (NOUT - 1), col = idx >> 8;
+          const int l = col / KCOLS, k = col - l * KCOLS;
+          wv[j] = k < TAPS ? __ldg(weight + static_cast<long long>(l * TAPS + k) * NOUT + n) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j) {
+          const int idx = et + 128 * (j0 + j), n = idx & (NOUT - 1), col = idx >> 8;
+          *reinterpret_cast<uint32_t*>(smem + SMEM_B + chunk_offset(n, col >> 2, B_KSTEP_BYTES) + (col & 3) * 4) = to_tf32(wv[j]);
+        }
+      }
+      for (int i = et; i < NOUT; i += 32 * EPI_WARPS) bias_s[i] = bias ? __ldg(bias + i) : 0.f;
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_ready);
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // bias_s visible to the four epilogue warps
+    }
+    constexpr int ELEM = OUT_F16 ? 2 : 4;
+    constexpr int ROW_BYTES = NOUT * ELEM;                       // bytes per pixel of the output
+    constexpr int PASSES = ROW_BYTES / STAGE_ROW_BYTES;          // 2 (fp16) or 4 (fp32)
+    constexpr int CHUNKS_PER_PASS = NOUT / PASSES / 32;          // tcgen05.ld x32 chunks per pass: 4 or 2
+    uint4* stage = reinterpret_cast<uint4*>(smem + SMEM_STAGE + eq * STAGE_WARP_BYTES);   // [32 rows][16 chunks of 16 B]
+    unsigned char* out_bytes = reinterpret_cast<unsigned char*>(a.out);
+    for (int t = 0; t < nt; ++t) {
+      const int acc = t & 1;
+      mbar_wait(tmem_full(acc), (t >> 1) & 1);
+      tc_fence_after();
+      const long long row0 = px0 + static_cast<long long>(t) * TILE + 32 * eq;   // pixel of staging row 0
+#pragma unroll 1
+      for (int pass = 0; pass < PASSES; ++pass) {
+#pragma unroll
+        for (int cq = 0; cq < CHUNKS_PER_PASS; ++cq) {
+          const int col0 = (pass * CHUNKS_PER_PASS + cq) * 32;
+          float v[32];
+          umma::ld32(tmem_base + (static_cast<uint32_t>(32 * eq) << 16) + static_cast<uint32_t>(acc * NOUT + col0), v);
+          if (pass == PASSES - 1 && cq == CHUNKS_PER_PASS - 1) {
+            tc_fence_before();
+            mbar_arrive(tmem_empty(acc));                        // my last TMEM read of this tile
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 bq = *reinterpret_cast<const float4*>(bias_s + col0 + i);
+            v[i] += bq.x; v[i + 1] += bq.y; v[i + 2] += bq.z; v[i + 3] += bq.w;
+          }
+          if (relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          // 16-byte chunk c of staging row `lane` lives at chunk (c ^ (lane & 15)): conflict-free for these row-wise
+          // writes and for the chunk-wise reads below
+          if (OUT_F16) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              stage[lane * 16 + ((cq * 4 + i) ^ (lane & 15))] =
+                  make_uint4(pack_h2(v[8 * i], v[8 * i + 1]), pack_h2(v[8 * i + 2], v[8 * i + 3]),
+                             pack_h2(v[8 * i + 4], v[8 * i + 5]), pack_h2(v[8 * i + 6], v[8 * i + 7]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              stage[lane * 16 + ((cq * 8 + i) ^ (lane & 15))] =
+                  make_uint4(__float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]), __float_as_uint(v[4 * i + 2]),
+                             __float_as_uint(v[4 * i + 3]));
+          }
+        }
+        __syncwarp();
+        // write the pass out: one instruction = two pixel rows x 256 contiguous bytes
+        {
+          const int c = lane & 15, rh = lane >> 4;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int r = 2 * i + rh;
+            const long long px = row0 + r;
+            const uint4 val = stage[r * 16 + (c ^ (r & 15))];
+            if (px < px_end)
+              *reinterpret_cast<uint4*>(out_bytes + px * ROW_BYTES + pass * STAGE_ROW_BYTES + c * 16) = val;
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+// host-side launcher, called by nnd_corr1d_lookup_conv1x1 (lookup.cu) for the shipping shape:
+// 4 levels, radius 4, c_out = 256, channels-last output, 16-byte aligned pyramid rows
+nnd_status launch_lookup_conv1x1_ws(const LookupArgs& a, const float* weight, const float* bias, int relu, int out_f16,
+                                    long long total_px, cudaStream_t stream) {
+  const long long sms = sm_count();
+  const long long tiles = (total_px + ws::TILE - 1) / ws::TILE;
+  const long long grid = tiles < sms ? tiles : sms;
+  long long per = (total_px + grid - 1) / grid;
+  per = (per + 31) & ~31LL;                                  // whole 32-pixel groups per CTA
+  cudaError_t e;
+  if (out_f16) {
+    e = cudaFuncSetAttribute(corr1d_lookup_conv1x1_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws::SMEM_TOTAL);
+    if (e != cudaSuccess) return cuda_fail(e, "lookup_conv1x1: shared-memory attribute");
+    corr1d_lookup_conv1x1_ws_kernel<true><<<static_cast<unsigned>(grid), ws::THREADS, ws::SMEM_TOTAL, stream>>>(
+        a, weight, bias, relu, total_px, per);
+  } else {
+    e = cudaFuncSetAttribute(corr1d_lookup_conv1x1_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws::SMEM_TOTAL);
+    if (e != cudaSuccess) return cuda_fail(e, "lookup_conv1x1: shared-memory attribute");
+    corr1d_lookup_conv1x1_ws_kernel<false><<<static_cast<unsigned>(grid), ws::THREADS, ws::SMEM_TOTAL, stream>>>(
+        a, weight, bias, relu, total_px, per);
+  }
+  return check_launch("corr1d_lookup_conv1x1_ws_kernel");
+}
+
+}  // namespace nnd

@@ -398,10 +398,11 @@ def test_lookup_conv1x1_fusion(shape, c_out):
         assert torch.equal(tc_h, tc_cl.half())          # the same values rounded to nearest fp16
 
 
-@pytest.mark.parametrize("shape", [(8, 48, 156), (1, 5, 52), (3, 7, 44)])
-def test_lookup_conv1x1_tcgen05_path(shape, monkeypatch):
-    """The opt-in tcgen05 / TMEM version of the fused lookup (NND_LOOKUP_UMMA=1; c_out = 256, channels-last): same TF32
-    operands as the mma.sync kernel, another summation order; tiles straddle images and the last tile is ragged."""
+@pytest.mark.parametrize("shape", [(8, 48, 156), (1, 5, 52), (3, 7, 44), (1, 1, 8), (20, 48, 156)])
+def test_lookup_conv1x1_tcgen05_path(shape):
+    """The warp-specialised tcgen05 / TMEM kernel (c_out = 256, channels-last: the shipping path) against the mma.sync
+    kernel (NCHW output): same TF32 operands, another summation order.  CTAs own contiguous pixel ranges that straddle
+    images, the last tile of a range is ragged, and the largest shape runs 8 tiles per CTA (every mbarrier phase wraps)."""
     import nndepth_b200 as nb
     B, H, W = shape
     torch.manual_seed(B * H + W)
@@ -412,16 +413,14 @@ def test_lookup_conv1x1_tcgen05_path(shape, monkeypatch):
     coords.view(-1)[5::23] = W + 3.25
     conv = torch.nn.Conv2d(36, 256, 1).cuda()
     with torch.no_grad():
-        monkeypatch.setenv("NND_LOOKUP_UMMA", "0")
-        base = blk.lookup_conv1x1(coords, conv.weight, conv.bias, relu=True, precision="tf32", channels_last=True)
-        monkeypatch.setenv("NND_LOOKUP_UMMA", "1")
-        umma = blk.lookup_conv1x1(coords, conv.weight, conv.bias, relu=True, precision="tf32", channels_last=True)
+        base = blk.lookup_conv1x1(coords, conv.weight, conv.bias, relu=True, precision="tf32")
+        base_lin = blk.lookup_conv1x1(coords, conv.weight, None, relu=False, precision="tf32")
+        for _ in range(2):                  # twice: barriers / TMEM are re-initialised per launch
+            umma = blk.lookup_conv1x1(coords, conv.weight, conv.bias, relu=True, precision="tf32", channels_last=True)
         umma_h = blk.lookup_conv1x1(coords, conv.weight, conv.bias, relu=True, precision="tf32", channels_last=True, half=True)
         lin = blk.lookup_conv1x1(coords, conv.weight, None, relu=False, precision="tf32", channels_last=True)
-        monkeypatch.setenv("NND_LOOKUP_UMMA", "0")
-        base_lin = blk.lookup_conv1x1(coords, conv.weight, None, relu=False, precision="tf32", channels_last=True)
     scale = base_lin.abs().max().item()
-    assert umma.is_contiguous(memory_format=torch.channels_last)
+    assert umma.is_contiguous(memory_format=torch.channels_last) and umma.shape == base.shape
     assert (umma - base).abs().max().item() <= 1e-5 * scale
     assert (lin - base_lin).abs().max().item() <= 1e-5 * scale
     assert torch.equal(umma_h, umma.half())

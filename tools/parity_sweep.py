@@ -46,7 +46,7 @@ def main():
         torch.backends.cuda.matmul.allow_tf32 = False
         for name, (l, r) in inputs.items():
             l, r = l.cuda(), r.cuda()
-            padder = Padder(l.shape, divis_by=32)
+            padder = Padder(l.shape[-2:], divis_by=32)
             lp, rp = padder.pad(l, r)
             with torch.no_grad():
                 torch.cuda.synchronize()
