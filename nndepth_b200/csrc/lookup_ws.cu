@@ -108,7 +108,7 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const floa
         mbar_init(tmem_full(s), 1);
         mbar_init(tmem_empty(s), 32 * EPI_WARPS);
       }
-      mbar_init(b_ready, EPI_WARPS);
+      mbar_init(b_ready, THREADS / 32);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -120,6 +120,28 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const floa
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+  // weights -> B operand (TF32, round to nearest), K laid out as 4 levels x (9 taps + 3 zero columns): staged by EVERY
+  // thread (19 loads each, all issued before the first is used); the producers put their first gather in flight first.
+  auto stage_weights = [&]() {
+    constexpr int TOTAL = NOUT * KSTEPS * 8, PER_THREAD = (TOTAL + THREADS - 1) / THREADS;
+    float wv[PER_THREAD];
+#pragma unroll
+    for (int j = 0; j < PER_THREAD; ++j) {
+      const int idx = tid + THREADS * j, n = idx & (NOUT - 1), col = idx >> 8;
+      const int l = col / KCOLS, k = col - l * KCOLS;
+      wv[j] = (idx < TOTAL && k < TAPS) ? __ldg(weight + static_cast<long long>(l * TAPS + k) * NOUT + n) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < PER_THREAD; ++j) {
+      const int idx = tid + THREADS * j, n = idx & (NOUT - 1), col = idx >> 8;
+      if (idx < TOTAL)
+        *reinterpret_cast<uint32_t*>(smem + SMEM_B + chunk_offset(n, col >> 2, B_KSTEP_BYTES) + (col & 3) * 4) = to_tf32(wv[j]);
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(b_ready);
+  };
 
   if (warp < PROD_WARPS) {
     // =========================================== producers ===========================================
@@ -149,7 +171,11 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const floa
           const int sp = __shfl_sync(FULL, s, p);
           const int hp = __shfl_sync(FULL, hi, p);
           const int cq = sp + 4 * q;
+#ifdef NND_WS_SKIP_GATHER
+          if (false) {
+#else
           if (grp0 + p < px_end && cq <= hp && cq < w) {
+#endif
             const float* src = lbase + (grp0 + p) * pitch + cq;
             const uint32_t dst = smem_u32(win + p * WSTRIDE + 4 * q);
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -161,6 +187,7 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const floa
 
     float c0 = coord_of(0), c1 = coord_of(1);
     issue_windows(0, c0, wins);
+    stage_weights();
     for (int t = 0; t < nt; ++t) {
       const float c2 = coord_of(t + 2);                          // in flight during this whole iteration
       issue_windows(t + 1, c1, wins + ((t + 1) & 1) * WIN_BUF_FLOATS);
@@ -198,6 +225,7 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const floa
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else if (warp == MMA_WARP) {
     // =========================================== MMA issuer ===========================================
+    stage_weights();
     if (lane == 0 && nt > 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(NOUT >> 3) << 17) |
                              (static_cast<uint32_t>(TILE >> 4) << 24);   // D f32, A/B tf32, both K-major
@@ -228,31 +256,9 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const floa
     const int eq = warp - EPI_WARP0;                    // TMEM lane quarter this warp may read (warp % 4)
     const int et = tid - 32 * EPI_WARP0;                // 0..127
     float* bias_s = reinterpret_cast<float*>(smem + SMEM_BIAS);
-    {
-      // weights -> B operand (TF32, round to nearest), K laid out as 4 levels x (9 taps + 3 zero columns).  All of a
-      // thread's loads are issued before the first is used; the producers are already gathering meanwhile.
-      constexpr int TOTAL = NOUT * KSTEPS * 8, PER_THREAD = TOTAL / (32 * EPI_WARPS), BATCH = 24;
-      static_assert(PER_THREAD % BATCH == 0, "weight staging batches");
-      for (int j0 = 0; j0 < PER_THREAD; j0 += BATCH) {
-        float wv[BATCH];
-#pragma unroll
-        for (int j = 0; j < BATCH; ++j) {
-          const int idx = et + 128 * (j0 + j), n = idx & (NOUT - 1), col = idx >> 8;
-          const int l = col / KCOLS, k = col - l * KCOLS;
-          wv[j] = k < TAPS ? __ldg(weight + static_cast<long long>(l * TAPS + k) * NOUT + n) : 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < BATCH; ++j) {
-          const int idx = et + 128 * (j0 + j), n = idx & (NOUT - 1), col = idx >> 8;
-          *reinterpret_cast<uint32_t*>(smem + SMEM_B + chunk_offset(n, col >> 2, B_KSTEP_BYTES) + (col & 3) * 4) = to_tf32(wv[j]);
-        }
-      }
-      for (int i = et; i < NOUT; i += 32 * EPI_WARPS) bias_s[i] = bias ? __ldg(bias + i) : 0.f;
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(b_ready);
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // bias_s visible to the four epilogue warps
-    }
+    for (int i = et; i < NOUT; i += 32 * EPI_WARPS) bias_s[i] = bias ? __ldg(bias + i) : 0.f;
+    stage_weights();
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // bias_s (staged below by these warps) is visible
     constexpr int ELEM = OUT_F16 ? 2 : 4;
     constexpr int ROW_BYTES = NOUT * ELEM;                       // bytes per pixel of the output
     constexpr int PASSES = ROW_BYTES / STAGE_ROW_BYTES;          // 2 (fp16) or 4 (fp32)
@@ -309,7 +315,11 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const floa
             const int r = 2 * i + rh;
             const long long px = row0 + r;
             const uint4 val = stage[r * 16 + (c ^ (r & 15))];
+#ifdef NND_WS_SKIP_STORE
+            if (px < px_end && val.x == 0x12345678u)
+#else
             if (px < px_end)
+#endif
               *reinterpret_cast<uint4*>(out_bytes + px * ROW_BYTES + pass * STAGE_ROW_BYTES + c * 16) = val;
           }
         }

@@ -100,8 +100,46 @@ def half_conv_params(conv):
     return cache[1]
 
 
+def _split16(w, b):
+    """``(w_hi, w_lo, b_hi, b_lo)``: fp16 value + fp16 remainder of an fp32 weight / bias (weights good to 2**-22
+    relative, down to fp16's subnormal spacing) -- the two-term form the tensor cores can consume exactly."""
+    w = w.detach().float().clamp(-65504.0, 65504.0)
+    w_hi = w.half()
+    w_lo = (w - w_hi.float()).half()
+    cl = torch.channels_last
+    if b is None:
+        return w_hi.contiguous(memory_format=cl), w_lo.contiguous(memory_format=cl), None, None
+    b = b.detach().float().clamp(-65504.0, 65504.0)
+    b_hi = b.half()
+    return (w_hi.contiguous(memory_format=cl), w_lo.contiguous(memory_format=cl), b_hi.contiguous(),
+            (b - b_hi.float()).half().contiguous())
+
+
+def half_split_conv_params(conv):
+    """``_split16`` of a convolution's parameters, cached per parameter version / device."""
+    key = (conv.weight._version, None if conv.bias is None else conv.bias._version, conv.weight.device)
+    cache = getattr(conv, "_f16_split", None)
+    if cache is None or cache[0] != key:
+        cache = (key, _split16(conv.weight, conv.bias))
+        conv._f16_split = cache
+    return cache[1]
+
+
+def conv_add_relu_split16(x16, params, stride, padding, dilation=(1, 1), groups=1):
+    """``relu(conv(x, w_hi + w_lo) + b)`` on fp16 tensor cores with fp32 accumulation: the remainder product is a plain
+    fp16 convolution (its output is ~2**-11 of the result, so its own fp16 rounding is ~2**-22), the main product is
+    cuDNN's fused convolution + add + bias + ReLU reading it.  A rounded WEIGHT perturbs every GRU iteration the same
+    way (the error accumulates coherently over 32 iterations); rounded ACTIVATIONS are fresh noise each iteration."""
+    w_hi, w_lo, b_hi, b_lo = params
+    z = F.conv2d(x16, w_lo, b_lo, stride, padding, dilation, groups)
+    return torch.cudnn_convolution_add_relu(x16, w_hi, z, 1.0, b_hi, stride, padding, dilation, groups)
+
+
 def conv_relu_f16(conv, x16):
-    """``relu(conv(x))`` as cuDNN's fused fp16 convolution (fp32 accumulation) on a channels-last fp16 ``x``."""
+    """``relu(conv(x))`` as cuDNN's fused fp16 convolution (fp32 accumulation) on a channels-last fp16 ``x``; with
+    ``conv.exact16`` set (RAFTStereo.exact_weights) the weights enter as ``w_hi + w_lo`` (two products)."""
+    if getattr(conv, "exact16", False):
+        return conv_add_relu_split16(x16, half_split_conv_params(conv), conv.stride, conv.padding, conv.dilation, conv.groups)
     w, b = half_conv_params(conv)
     return torch.cudnn_convolution_relu(x16, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
 
@@ -257,12 +295,27 @@ class ResidualBlock(nn.Module):
             self._fold_cache = cache
         return cache[1]
 
+    def _folded_split16(self):
+        key = _fold_key("f16s", (self.conv1, self.norm1), (self.conv2, self.norm2), (self.downsample[0], self.norm3))
+        cache = getattr(self, "_fold_cache16s", None)
+        if cache is None or cache[0] != key:
+            cache = (key, tuple(_split16(*fold_bn(c, n, False))
+                                for c, n in ((self.conv1, self.norm1), (self.conv2, self.norm2), (self.downsample[0], self.norm3))))
+            self._fold_cache16s = cache
+        return cache[1]
+
     def forward(self, x):
         if _fused_ok(x, self.norm1, self.norm2, self.norm3):
             # BatchNorm folded into the convolutions; conv + bias + ReLU and conv + bias + add + ReLU are single
             # cuDNN calls (the reference chain is conv, bias add, batch norm, clamp: four passes per layer)
-            (w1, b1), (w2, b2), (w3, b3) = self._folded(half=x.dtype == torch.float16)
             c1, c3 = self.conv1, self.downsample[0]
+            if x.dtype == torch.float16 and getattr(self, "exact16", False):
+                p1, p2, p3 = self._folded_split16()
+                y = conv_add_relu_split16(x, p1, c1.stride, c1.padding, c1.dilation)
+                y = conv_add_relu_split16(y, p2, self.conv2.stride, self.conv2.padding, self.conv2.dilation)
+                y = y + F.conv2d(x, p3[1], p3[3], c3.stride, c3.padding, c3.dilation)
+                return torch.cudnn_convolution_add_relu(x, p3[0], y, 1.0, p3[2], c3.stride, c3.padding, c3.dilation, 1)
+            (w1, b1), (w2, b2), (w3, b3) = self._folded(half=x.dtype == torch.float16)
             y = torch.cudnn_convolution_relu(x, w1, b1, c1.stride, c1.padding, c1.dilation, 1)
             y = torch.cudnn_convolution_relu(y, w2, b2, self.conv2.stride, self.conv2.padding, self.conv2.dilation, 1)
             return torch.cudnn_convolution_add_relu(x, w3, y, 1.0, b3, c3.stride, c3.padding, c3.dilation, 1)
@@ -319,11 +372,21 @@ class BasicEncoder(nn.Module):
                 fmt = torch.channels_last if (x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()) \
                     else torch.contiguous_format
                 x = F.pad(x, (0, 0, 0, 0, 0, w.shape[1] - x.shape[1])).contiguous(memory_format=fmt)
-            x = torch.cudnn_convolution_relu(x, w, b, self.conv1.stride, self.conv1.padding, self.conv1.dilation, 1)
+            if half and getattr(self, "exact16", False):
+                key = _fold_key("f16s", (self.conv1, self.norm1))
+                if getattr(self, "_fold_cache16s", None) is None or self._fold_cache16s[0] != key:
+                    wf, bf = fold_bn(self.conv1, self.norm1, False)
+                    self._fold_cache16s = (key, _split16(F.pad(wf, (0, 0, 0, 0, 0, (-wf.shape[1]) % 4)), bf))
+                x = conv_add_relu_split16(x, self._fold_cache16s[1], self.conv1.stride, self.conv1.padding, self.conv1.dilation)
+            else:
+                x = torch.cudnn_convolution_relu(x, w, b, self.conv1.stride, self.conv1.padding, self.conv1.dilation, 1)
         else:
             x = self.relu1(self.norm1(self.conv1(x)))
         x = self.layer3(self.layer2(self.layer1(x)))
-        if x.dtype == torch.float16:
+        if x.dtype == torch.float16 and getattr(self, "exact16", False):
+            w_hi, w_lo, b_hi, b_lo = half_split_conv_params(self.conv2)
+            x = F.conv2d(x, w_hi, b_hi, self.conv2.stride, self.conv2.padding) + F.conv2d(x, w_lo, b_lo, self.conv2.stride, self.conv2.padding)
+        elif x.dtype == torch.float16:
             w16, b16 = half_conv_params(self.conv2)
             x = F.conv2d(x, w16, b16, self.conv2.stride, self.conv2.padding)
         else:
@@ -570,6 +633,9 @@ class BasicMotionEncoder(nn.Module):
             cor = conv_relu(self.convc2, cor1 if cor1 is not None else conv_relu(self.convc1, corr))
         if half and split_flow and self.channels_last:
             flo = conv_relu_f16(self.convf2, flow_conv7x7_relu(self.convf1, flow, half=True))
+            if getattr(self.conv, "exact16", False):
+                return conv_add_relu_split16(nhwc_cat_f16(cor, flo), self._padded_conv_split16(), self.conv.stride,
+                                             self.conv.padding, self.conv.dilation), flow
             w, b = self._padded_conv(half=True)
             return torch.cudnn_convolution_relu(nhwc_cat_f16(cor, flo), w, b, self.conv.stride, self.conv.padding,
                                                 self.conv.dilation, 1), flow
@@ -584,6 +650,19 @@ class BasicMotionEncoder(nn.Module):
             return torch.cudnn_convolution_relu(x, w, b, self.conv.stride, self.conv.padding, self.conv.dilation, 1), flow
         out = conv_relu(self.conv, x)
         return torch.cat([out, flow], dim=1)
+
+    def _padded_conv_split16(self):
+        """``_padded_conv`` as the two-term fp16 split ``(w_hi, w_lo, b_hi, b_lo)`` (cached per weight version)."""
+        conv = self.conv
+        key = (conv.weight._version, conv.bias._version, conv.weight.device)
+        cache = getattr(self, "_pad_cache16s", None)
+        if cache is None or cache[0] != key:
+            extra = self.convf1.weight.shape[1]
+            w = torch.cat([conv.weight.detach(), conv.weight.new_zeros(extra, *conv.weight.shape[1:])], 0)
+            b = torch.cat([conv.bias.detach(), conv.bias.new_zeros(extra)], 0)
+            cache = (key, _split16(w, b))
+            self._pad_cache16s = cache
+        return cache[1]
 
     def _padded_conv(self, half=False):
         """``self.conv`` with zero filters appended up to ``hidden_dim`` output channels (cached per weight version)."""
@@ -710,6 +789,13 @@ class RAFTStereo(nn.Module):
         #   "tf32"  everything TF32 (PyTorch's CUDA default)                           0.0147 px  -> outside the bar
         # None leaves torch.backends.cudnn.allow_tf32 as the caller set it.
         self.dense_precision = None
+        # mixed16 only.  exact_weights: the convolutions INSIDE the refinement loop take their weights as the two-term
+        # fp16 split w_hi + w_lo (a rounded weight is the same perturbation in all 32 iterations and accumulates
+        # coherently; gpurun_out/r2_exp_modules.log: with weight seeds 1 / 2 on the shipped KITTI pair single-term
+        # weights put the final disparity 0.013 - 0.018 px from the fp32 reference, outside the 0.01 px bar).
+        # exact_encoder: the same for the feature encoder (run once per forward).
+        self.exact_weights = True
+        self.exact_encoder = False
         self._graphs = {}
         if weights is not None:
             state = torch.load(weights, map_location="cpu") if not str(weights).endswith(".safetensors") else None
@@ -755,14 +841,31 @@ class RAFTStereo(nn.Module):
             # mixed16 runs the (BatchNorm-folded) feature encoder as fp16 convolutions as well: the feature maps are
             # rounded to 10 mantissa bits for the correlation volume anyway (RN_tf32(RN_fp16(x)) == RN_fp16(x))
             self.fnet.half_convs = self.dense_precision == "mixed16" and getattr(self, "fp16_encoder", True)
+        self._set_exact16(self.dense_precision == "mixed16" and self.exact_weights,
+                          self.dense_precision == "mixed16" and self.exact_encoder)
         try:
             with cudnn_tf32(self.dense_precision != "fp32"):
                 return self._forward(frame1, frame2, **kwargs)
         finally:
+            self._set_exact16(False, False)
             if gru is not None:
                 gru.recurrence = saved[0]
             if has_half:
                 self.fnet.half_convs = saved[1]
+
+    def _set_exact16(self, iteration, encoder):
+        """Switch the two-term fp16 weights (``w_hi + w_lo``, see ``conv_add_relu_split16``) of the convolutions inside
+        the refinement loop (motion encoder, flow head; the ConvGRU has its own split) and of the feature encoder."""
+        ub = self.update_block
+        enc, head = getattr(ub, "encoder", None), getattr(ub, "flow_head", None)
+        for conv in (getattr(enc, "convc2", None), getattr(enc, "convf2", None), getattr(enc, "conv", None),
+                     getattr(head, "conv1", None)):
+            if conv is not None:
+                conv.exact16 = bool(iteration)
+        for m in self.fnet.modules():
+            if isinstance(m, (BasicEncoder, ResidualBlock)):
+                m.exact16 = bool(encoder)
+        self.cnet_proj[0].exact16 = bool(encoder)
 
     def _forward(self, frame1, frame2, **kwargs):
         fmap1, fmap2, cnet1 = self.forward_fnet(frame1, frame2)
@@ -834,7 +937,8 @@ class RAFTStereo(nn.Module):
         enc = getattr(self.update_block, "encoder", None)
         return (tuple(frame1.shape), tuple(frame1.stride()), frame1.device.index, frame1.dtype, self.iters, self.final_only,
                 self.dense_precision, stamp, self.corr_fn, _corr.get_volume_precision(), self.fuse_motion_front,
-                self.fuse_gru, getattr(self, "fp16_encoder", True), getattr(gru, "recurrence", None),
+                self.fuse_gru, getattr(self, "fp16_encoder", True), self.exact_weights, self.exact_encoder,
+                getattr(gru, "recurrence", None),
                 getattr(gru, "_fuse_zr", False), getattr(self.fnet, "half_convs", False),
                 getattr(enc, "channels_last", False), self.corr_levels, self.corr_radius,
                 bool(torch.backends.cudnn.allow_tf32) if self.dense_precision is None else None,

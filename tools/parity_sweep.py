@@ -59,16 +59,27 @@ def main():
         for mode in args.modes:
             model = BaseRAFTStereo(iters=32).eval()
             model.load_state_dict(state)
-            model.dense_precision = mode
+            base, _, overrides = mode.partition(":")       # e.g. mixed16:exact_encoder=1,fp16_encoder=0
+            model.dense_precision = base
+            for item in filter(None, overrides.split(",")):
+                k, v = item.split("=")
+                setattr(model, k, bool(int(v)))
             engine = StereoEngine(model, device="cuda", use_cuda_graph=True)
             for name, (l, r) in inputs.items():
                 l, r = l.cuda(), r.cuda()
                 got = engine.infer_device(l, r).clone()
+                engine.infer_device(l, r)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    engine.infer_device(l, r)
+                torch.cuda.synchronize()
+                ms = (time.perf_counter() - t0) / 3 * 1e3
                 ref_out, t_ref = want[name]
                 per_pair = (got - ref_out).abs().flatten(1).mean(1)
                 row = {"seed": seed, "mode": mode, "input": name, "epe_px": (got - ref_out).abs().mean().item(),
                        "worst_pair_epe_px": per_pair.max().item(), "mean_abs_disp_px": ref_out.abs().mean().item(),
-                       "reference_cuda_fp32_forward_s": t_ref}
+                       "reference_cuda_fp32_forward_s": t_ref, "ms_per_forward": ms}
                 rows.append(row)
                 print(json.dumps(row), flush=True)
             del engine, model
