@@ -1,8 +1,14 @@
-"""ctypes binding of ``libnndepth_b200.so`` -- the C ABI declared in ``include/nndepth_b200.h``.
+"""Bindings of the C ABI declared in ``include/nndepth_b200.h`` (``libnndepth_b200.so``).
 
-The Python mirror classes in this package are the only callers.  There is deliberately no CPU or
-PyTorch fallback: if the shared library is missing, or a tensor is not a contiguous fp32 CUDA
-tensor, the call raises.  PyTorch is used for device memory and the current CUDA stream only.
+* ``ops()`` -- the product binding: ``libnndepth_b200_torch.so``, a thin PyTorch C++ extension (``csrc/torch_ext.cpp``,
+  ``TORCH_LIBRARY(nndepth_b200, ...)``) whose operators check device / dtype / contiguity / shapes, take the current
+  CUDA stream and call the C ABI.  The mirror classes of this package (``corr.py``, ``igev.py``, ``agcl.py``,
+  ``upsample.py``) call ``torch.ops.nndepth_b200.*`` through it.
+* ``load()`` -- a ``ctypes`` view of the same C ABI, used by ``tests/test_abi.py`` (symbol / signature checks), by the
+  timing tools, and by the model shell's out-of-scope glue kernels (ConvGRU gates, one-channel convolutions).
+
+There is deliberately no CPU or PyTorch fallback: if a shared library is missing, or a tensor is not a contiguous
+CUDA tensor of the expected dtype, the call raises.  PyTorch is used for device memory and the current stream only.
 """
 import ctypes
 import os
@@ -13,6 +19,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnndepth_b200.so")
+TORCH_EXT_PATH = os.path.join(_HERE, "libnndepth_b200_torch.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 NND_OK = 0
@@ -60,6 +67,7 @@ SIGNATURES = {
 
 _lock = threading.Lock()
 _lib = None
+_launches = 0
 
 
 class NNDepthError(RuntimeError):
@@ -68,7 +76,9 @@ class NNDepthError(RuntimeError):
 
 def build_library(verbose=False):
     """Compile ``csrc/*.cu`` into ``libnndepth_b200.so`` for sm_100a (nvcc cross-compiles without a GPU)."""
-    cmd = ["make", "-C", CSRC_DIR, "-j", str(min(8, os.cpu_count() or 1))]
+    torch_dir = os.path.dirname(torch.__file__)
+    cmd = ["make", "-C", CSRC_DIR, "-j", str(min(8, os.cpu_count() or 1)), f"TORCH_DIR={torch_dir}",
+           f"CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}"]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or res.returncode != 0:
         print(res.stdout)
@@ -99,12 +109,46 @@ def load():
     return _lib
 
 
+class _Ops:
+    """``torch.ops.nndepth_b200`` with a launch counter in front (``launch_count()``)."""
+
+    def __getattr__(self, name):
+        fn = getattr(torch.ops.nndepth_b200, name)
+
+        def call(*args):
+            global _launches
+            out = fn(*args)
+            _launches += 1
+            return out
+
+        setattr(self, name, call)
+        return call
+
+
+_ops = None
+
+
+def ops():
+    """The PyTorch operator library over the C ABI (loaded once).  Raises if it is not built."""
+    global _ops
+    if _ops is None:
+        with _lock:
+            if _ops is None:
+                if not os.path.exists(TORCH_EXT_PATH):
+                    raise ImportError(
+                        f"{TORCH_EXT_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        f"or `make -C {CSRC_DIR}`.  nndepth_b200 has no CPU / PyTorch fallback."
+                    )
+                torch.ops.load_library(TORCH_EXT_PATH)
+                if torch.ops.nndepth_b200.abi_version() != 1:
+                    raise ImportError("libnndepth_b200_torch.so was built against another C ABI version")
+                _ops = _Ops()
+    return _ops
+
+
 def last_error():
     msg = load().nnd_last_error_string()
     return msg.decode("utf-8", "replace") if msg else ""
-
-
-_launches = 0
 
 
 def check(status, what):

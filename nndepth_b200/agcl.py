@@ -36,11 +36,7 @@ class AGCL:
         hit = self._staged.get(id(t))
         if hit is not None and hit[0] is t:
             return hit[1]
-        N, C, H, W = t.shape
-        out = torch.empty(N, H, W, C, dtype=torch.float32, device=t.device)
-        with torch.cuda.device(t.device):
-            _lib.check(_lib.load().nnd_nchw_to_nhwc(_lib.ptr(t), N, C, H, W, _lib.ptr(out), _lib.stream_ptr(t)),
-                       "nnd_nchw_to_nhwc")
+        out = _lib.ops().nchw_to_nhwc(t)
         if len(self._staged) >= 4:          # fmap1, fmap2 and their attended versions; transient maps rotate out
             self._staged.pop(next(iter(self._staged)))
         self._staged[id(t)] = (t, out)
@@ -63,25 +59,11 @@ class AGCL:
         right = right_feature if right_feature is self.fmap2 else _lib.as_cuda_f32(right_feature, "right_feature")
         N, C, H, W = left.shape
         flow = self._check_flow(flow, N, H, W)
-        out = torch.empty(N, 36, H, W, dtype=torch.float32, device=left.device)
         if self._fast(C) and H >= 2 and W >= 2:
             if self._warp_ws is None or self._warp_ws.shape != (N, H, W, C) or self._warp_ws.device != left.device:
                 self._warp_ws = torch.empty(N, H, W, C, dtype=torch.float32, device=left.device)
-            with torch.cuda.device(left.device):
-                _lib.check(
-                    _lib.load().nnd_agcl_iter_nhwc(_lib.ptr(self._nhwc(left)), _lib.ptr(self._nhwc(right)),
-                                                   _lib.ptr(flow), N, C, H, W, 1 if small_patch else 0,
-                                                   _lib.ptr(self._warp_ws), _lib.ptr(out), _lib.stream_ptr(left)),
-                    "nnd_agcl_iter_nhwc",
-                )
-            return out
-        with torch.cuda.device(left.device):
-            _lib.check(
-                _lib.load().nnd_agcl_iter(_lib.ptr(left), _lib.ptr(right), _lib.ptr(flow), N, C, H, W,
-                                          1 if small_patch else 0, _lib.ptr(out), _lib.stream_ptr(left)),
-                "nnd_agcl_iter",
-            )
-        return out
+            return _lib.ops().agcl_iter(self._nhwc(left), self._nhwc(right), flow, bool(small_patch), True, self._warp_ws)
+        return _lib.ops().agcl_iter(left, right, flow, bool(small_patch), False, None)
 
     def _attend(self, left, right):
         """Cross-attention on ``(N, H*W, C)`` token layout and back (reference :91-99), cached."""
@@ -104,23 +86,9 @@ class AGCL:
         extra = _lib.as_cuda_f32(extra_offset, "extra_offset")
         if tuple(extra.shape) != (N, 18, H, W):
             raise RuntimeError(f"extra_offset must be (N, 18, H, W) = {(N, 18, H, W)}, got {tuple(extra.shape)}")
-        out = torch.empty(N, 36, H, W, dtype=torch.float32, device=left.device)
         if self._fast(C) and H >= 2 and W >= 2:
-            with torch.cuda.device(left.device):
-                _lib.check(
-                    _lib.load().nnd_agcl_offset_nhwc(_lib.ptr(self._nhwc(left)), _lib.ptr(self._nhwc(right)),
-                                                     _lib.ptr(flow), _lib.ptr(extra), N, C, H, W,
-                                                     1 if small_patch else 0, _lib.ptr(out), _lib.stream_ptr(left)),
-                    "nnd_agcl_offset_nhwc",
-                )
-            return out
-        with torch.cuda.device(left.device):
-            _lib.check(
-                _lib.load().nnd_agcl_offset(_lib.ptr(left), _lib.ptr(right), _lib.ptr(flow), _lib.ptr(extra), N, C, H,
-                                            W, 1 if small_patch else 0, _lib.ptr(out), _lib.stream_ptr(left)),
-                "nnd_agcl_offset",
-            )
-        return out
+            return _lib.ops().agcl_offset(self._nhwc(left), self._nhwc(right), flow, extra, bool(small_patch), True)
+        return _lib.ops().agcl_offset(left, right, flow, extra, bool(small_patch), False)
 
     def get_correlation(self, left_feature, right_feature, psize=(3, 3), dilate=(1, 1)):
         """Replicate-padded local correlation of ONE channel group -> ``(N, 9, H, W)`` (reference :28-52).

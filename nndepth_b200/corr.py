@@ -90,9 +90,20 @@ class PyramidStorage:
             self.levels.append(self.buffer[start:start + self.rows * p].view(self.rows, p))
             start += self.rows * p
         self._extra = None
-        self._level_ptrs = _lib.ptr_array(self.levels)
-        self._width_arr = _lib.int_array(self.widths)
-        self._pitch_arr = _lib.int_array(self.pitches)
+        self.width0 = int(width0)
+
+    # ctypes views of the level table, for callers that drive the C ABI directly (tests/test_abi.py, tools/)
+    @property
+    def _level_ptrs(self):
+        return _lib.ptr_array(self.levels)
+
+    @property
+    def _width_arr(self):
+        return _lib.int_array(self.widths)
+
+    @property
+    def _pitch_arr(self):
+        return _lib.int_array(self.pitches)
 
     @property
     def num_levels(self):
@@ -117,15 +128,7 @@ class PyramidStorage:
             w_last = self.widths[-1]
             if w_last < 2:
                 raise RuntimeError("avg_pool1d(kernel 2) of a 1-wide level: output size would be 0")
-            pitch = _lib.row_pitch(w_last // 2)
-            extra = torch.empty(self.rows, pitch, dtype=torch.float32, device=self.buffer.device)
-            with torch.cuda.device(self.buffer.device):
-                _lib.check(
-                    _lib.load().nnd_avgpool_pairs(_lib.ptr(self.levels[-1]), w_last, self.pitches[-1], _lib.ptr(extra),
-                                                  pitch, self.rows, _lib.stream_ptr(extra)),
-                    "nnd_avgpool_pairs",
-                )
-            self._extra = extra
+            self._extra = _lib.ops().avgpool_pairs(self.levels[-1], w_last)
         views.append(self._extra[:, None, :self.widths[-1] // 2])
         return views
 
@@ -139,12 +142,7 @@ class _BuildPyramid(torch.autograd.Function):
         B, C, H, W1 = f1.shape
         W2 = f2.shape[3]
         pyr = PyramidStorage(B * H * W1, W2, num_levels, f1.device)
-        with torch.cuda.device(f1.device):
-            _lib.check(
-                _lib.load().nnd_corr1d_build(_lib.ptr(f1), _lib.ptr(f2), B, C, H, W1, W2, num_levels, prec_code,
-                                             pyr._level_ptrs, pyr._pitch_arr, _lib.stream_ptr(f1)),
-                "nnd_corr1d_build",
-            )
+        _lib.ops().corr1d_build(f1, f2, pyr.buffer, num_levels, prec_code)
         ctx.save_for_backward(f1, f2)
         ctx.geom = (B, C, H, W1, W2, num_levels)
         return pyr.buffer
@@ -154,14 +152,7 @@ class _BuildPyramid(torch.autograd.Function):
         f1, f2 = ctx.saved_tensors
         B, C, H, W1, W2, L = ctx.geom
         d = PyramidStorage(B * H * W1, W2, L, f1.device, buffer=d_buffer.contiguous().clone())
-        with torch.cuda.device(f1.device):
-            for l in range(L - 1, 0, -1):       # avg_pool1d backward, coarsest level first
-                _lib.check(
-                    _lib.load().nnd_avgpool_pairs_backward(_lib.ptr(d.levels[l]), d.widths[l], d.pitches[l],
-                                                           _lib.ptr(d.levels[l - 1]), d.pitches[l - 1], d.rows,
-                                                           _lib.stream_ptr(f1)),
-                    "nnd_avgpool_pairs_backward",
-                )
+        _lib.ops().pyramid_unpool_(d.buffer, d.rows, W2, L)     # avg_pool1d backward, coarsest level first
         d_vol = d.levels[0][:, :W2].reshape(B, H, W1, W2) / math.sqrt(C)
         d_f1 = torch.einsum("bhij,bchj->bchi", d_vol, f2) if ctx.needs_input_grad[0] else None
         d_f2 = torch.einsum("bhij,bchi->bchj", d_vol, f1) if ctx.needs_input_grad[1] else None
@@ -182,17 +173,9 @@ class _LookupPyramid(torch.autograd.Function):
         (coords,) = ctx.saved_tensors
         block = ctx.block
         B, H, W1, W2 = block._shape
-        d = PyramidStorage(B * H * W1, W2, block.num_levels, coords.device,
-                           buffer=torch.zeros_like(block._pyr.buffer))
-        grad_out = grad_out.contiguous().float()
-        with torch.cuda.device(coords.device):
-            _lib.check(
-                _lib.load().nnd_corr1d_lookup_backward(_lib.ptr(grad_out), _lib.ptr(coords), d._width_arr, d._pitch_arr, B, H,
-                                                       W1, block.num_levels, block.radius, d._level_ptrs,
-                                                       _lib.stream_ptr(coords)),
-                "nnd_corr1d_lookup_backward",
-            )
-        return d.buffer, None, None
+        d_buffer = _lib.ops().corr1d_lookup_backward(grad_out.contiguous().float(), coords, W2, block.num_levels,
+                                                     block.radius)
+        return d_buffer, None, None
 
 
 def _check_coords(coords, B, H, W1):
@@ -235,13 +218,7 @@ class CorrBlock1D:
             self._pyr = PyramidStorage(B * H * W1, W2, num_levels, f1.device, buffer=self._graph_buffer.detach())
             return
         self._pyr = PyramidStorage(B * H * W1, W2, num_levels, f1.device)
-        with torch.cuda.device(f1.device):
-            _lib.check(
-                _lib.load().nnd_corr1d_build(_lib.ptr(f1), _lib.ptr(f2), B, C, H, W1, W2, num_levels,
-                                             _prec_code(precision, W1, W2), self._pyr._level_ptrs, self._pyr._pitch_arr,
-                                             _lib.stream_ptr(f1)),
-                "nnd_corr1d_build",
-            )
+        _lib.ops().corr1d_build(f1, f2, self._pyr.buffer, num_levels, _prec_code(precision, W1, W2))
 
     @classmethod
     def from_pyramid(cls, levels, batch, height, num_levels=4, radius=4, device="cuda"):
@@ -267,17 +244,7 @@ class CorrBlock1D:
         return self._lookup_raw(_check_coords(coords, B, H, W1))
 
     def _lookup_raw(self, coords):
-        B, H, W1, _ = self._shape
-        T = 2 * self.radius + 1
-        out = torch.empty(B, self.num_levels * T, H, W1, dtype=torch.float32, device=coords.device)
-        with torch.cuda.device(coords.device):
-            _lib.check(
-                _lib.load().nnd_corr1d_lookup(self._pyr._level_ptrs, self._pyr._width_arr, self._pyr._pitch_arr,
-                                              _lib.ptr(coords), B, H, W1, self.num_levels, self.radius, _lib.ptr(out),
-                                              _lib.stream_ptr(coords)),
-                "nnd_corr1d_lookup",
-            )
-        return out
+        return _lib.ops().corr1d_lookup(self._pyr.buffer, self._shape[3], coords, self.num_levels, self.radius)
 
     @staticmethod
     def prepare_conv1x1_weight(weight):
@@ -313,27 +280,15 @@ class CorrBlock1D:
         if bias is not None:
             bias = _lib.as_cuda_f32(bias, "bias")
         c_out = weight.shape[1]
-        if channels_last and c_out <= 256:
-            # (B, H, W, c_out) in memory, returned with NCHW shape and channels-last strides
-            out = torch.empty(B, H, W1, c_out, dtype=torch.float16 if half else torch.float32,
-                              device=coords.device).permute(0, 3, 1, 2)
-        else:
+        if not (channels_last and c_out <= 256):
             if half:
                 raise ValueError("fp16 output needs c_out <= 256 (tensor-core path)")
             channels_last = False
-            out = torch.empty(B, c_out, H, W1, dtype=torch.float32, device=coords.device)
-        with torch.cuda.device(coords.device):
-            _lib.check(
-                _lib.load().nnd_corr1d_lookup_conv1x1(self._pyr._level_ptrs, self._pyr._width_arr, self._pyr._pitch_arr,
-                                                      _lib.ptr(coords), B, H, W1, self.num_levels, self.radius,
-                                                      _lib.ptr(weight), _lib.ptr(bias) if bias is not None else None,
-                                                      c_out, 1 if relu else 0,
-                                                      _lib.PREC_TF32 if precision == "tf32" else _lib.PREC_FP32,
-                                                      (2 if half else 1) if channels_last else 0, _lib.ptr(out),
-                                                      _lib.stream_ptr(coords)),
-                "nnd_corr1d_lookup_conv1x1",
-            )
-        return out
+        # channels-last results come back with NCHW shape and channels-last strides ((B, H, W, c_out) in memory)
+        return _lib.ops().corr1d_lookup_conv1x1(self._pyr.buffer, self._shape[3], coords, self.num_levels, self.radius,
+                                                weight, bias, bool(relu),
+                                                _lib.PREC_TF32 if precision == "tf32" else _lib.PREC_FP32,
+                                                (2 if half else 1) if channels_last else 0)
 
     def lookup_indices(self, coords):
         """Debug/parity helper: the int32 ``(idx0, idx1)`` of every tap, each ``(L, B*H*W1, 2r+1)``."""
@@ -349,30 +304,14 @@ class CorrBlock1D:
         B, C, H, W1 = f1.shape
         W2 = f2.shape[3]
         pyr = PyramidStorage(B * H * W1, W2, 1, f1.device)
-        with torch.cuda.device(f1.device):
-            _lib.check(
-                _lib.load().nnd_corr1d_build(_lib.ptr(f1), _lib.ptr(f2), B, C, H, W1, W2, 1, _prec_code(precision, W1, W2),
-                                             pyr._level_ptrs, pyr._pitch_arr, _lib.stream_ptr(f1)),
-                "nnd_corr1d_build",
-            )
+        _lib.ops().corr1d_build(f1, f2, pyr.buffer, 1, _prec_code(precision, W1, W2))
         return pyr.levels[0][:, :W2].reshape(B, H, W1, W2)
 
 
 def lookup_indices(widths, coords, num_levels=4, radius=4):
     """Integer window indices of ``linear_sampler`` (raft_stereo/utils.py:16-21) for every level/tap."""
     coords = _lib.require_cuda_f32(coords, "coords")
-    B, _, H, W1 = coords.shape
-    T = 2 * radius + 1
-    idx0 = torch.empty(num_levels, B * H * W1, T, dtype=torch.int32, device=coords.device)
-    idx1 = torch.empty_like(idx0)
-    with torch.cuda.device(coords.device):
-        _lib.check(
-            _lib.load().nnd_corr1d_lookup_indices(_lib.int_array(list(widths)[:num_levels]), _lib.ptr(coords), B, H, W1,
-                                                  num_levels, radius, _lib.ptr(idx0), _lib.ptr(idx1),
-                                                  _lib.stream_ptr(coords)),
-            "nnd_corr1d_lookup_indices",
-        )
-    return idx0, idx1
+    return _lib.ops().corr1d_lookup_indices([int(w) for w in list(widths)[:num_levels]], coords, num_levels, radius)
 
 
 def linear_sampler(corr, coords_lvl):
@@ -393,17 +332,10 @@ def linear_sampler(corr, coords_lvl):
         rows = torch.zeros(N, pitch, dtype=torch.float32, device=corr.device)
         rows[:, :w2] = corr
     out = torch.empty(N, T, dtype=torch.float32, device=corr.device)
-    lib = _lib.load()
-    with torch.cuda.device(corr.device):
-        for t in range(T):
-            col = coords_lvl[:, t].contiguous()
-            res = torch.empty(N, dtype=torch.float32, device=corr.device)
-            _lib.check(
-                lib.nnd_corr1d_lookup(_lib.ptr_array([rows]), _lib.int_array([w2]), _lib.int_array([pitch]),
-                                      _lib.ptr(col), 1, 1, N, 1, 0, _lib.ptr(res), _lib.stream_ptr(corr)),
-                "nnd_corr1d_lookup",
-            )
-            out[:, t] = res
+    flat = rows.reshape(-1)
+    for t in range(T):
+        col = coords_lvl[:, t].contiguous().view(1, 1, 1, N)
+        out[:, t] = _lib.ops().corr1d_lookup(flat, w2, col, 1, 0).view(N)
     return out
 
 
@@ -431,13 +363,7 @@ class GroupCorrBlock1D:
             raise IndexError("tuple index out of range")  # the reference indexes chunk i < G of size G
         self._shape = (B, H, W1, W2)
         self._pyr = PyramidStorage(B * G * H * W1, W2, num_levels, f1.device)
-        with torch.cuda.device(f1.device):
-            _lib.check(
-                _lib.load().nnd_groupcorr_build(_lib.ptr(f1), _lib.ptr(f2), B, C, H, W1, W2, G, G,
-                                                float(math.sqrt(C)), num_levels, self._pyr._level_ptrs,
-                                                self._pyr._pitch_arr, _lib.stream_ptr(f1)),
-                "nnd_groupcorr_build",
-            )
+        _lib.ops().groupcorr_build(f1, f2, self._pyr.buffer, G, G, float(math.sqrt(C)), num_levels)
 
     @classmethod
     def from_pyramid(cls, levels, batch, height, num_levels=4, radius=4, num_groups=4, device="cuda"):
@@ -456,13 +382,5 @@ class GroupCorrBlock1D:
     def __call__(self, coords):
         B, H, W1, _ = self._shape
         coords = _check_coords(coords, B, H, W1)
-        T = 2 * self.radius + 1
-        out = torch.empty(B, self.num_levels * self.num_groups * T, H, W1, dtype=torch.float32, device=coords.device)
-        with torch.cuda.device(coords.device):
-            _lib.check(
-                _lib.load().nnd_group_lookup(self._pyr._level_ptrs, None, self._pyr._width_arr, self._pyr._pitch_arr,
-                                             _lib.ptr(coords), B, self.num_groups, H, W1, self.num_levels, self.radius,
-                                             1, _lib.ptr(out), _lib.stream_ptr(coords)),
-                "nnd_group_lookup",
-            )
-        return out
+        return _lib.ops().group_lookup(self._pyr.buffer, None, self._shape[3], coords, self.num_groups, self.num_levels,
+                                       self.radius, 1)

@@ -31,15 +31,13 @@ class InterleavedPyramid:
         for n in sizes:
             self.levels.append(self.buffer[start:start + n])
             start += n
-        self._level_ptrs = _lib.ptr_array(self.levels)
+
+    @property
+    def _level_ptrs(self):
+        return _lib.ptr_array(self.levels)
 
     def fill(self, src, layout, src_pitch, B, D, H, W1):
-        with torch.cuda.device(src.device):
-            _lib.check(
-                _lib.load().nnd_gev_interleave_pool(_lib.ptr(src), layout, src_pitch, B, 8, D, H, W1, len(self.levels),
-                                                    self._level_ptrs, _lib.stream_ptr(src)),
-                "nnd_gev_interleave_pool",
-            )
+        _lib.ops().gev_interleave_pool(src, layout, src_pitch, B, D, H, W1, self.buffer, len(self.levels))
         return self
 
     def load_reference(self, levels, B, H, W1):
@@ -94,12 +92,7 @@ class GeometryAwareCostVolume(nn.Module):
             self._geo = None
             return
         self._geo = PyramidStorage(B * G * H * W1, D, num_levels, f1.device)
-        with torch.cuda.device(f1.device):
-            _lib.check(
-                _lib.load().nnd_geo_transpose_pool(_lib.ptr(geo), B, G, D, H, W1, num_levels, self._geo._level_ptrs,
-                                                   self._geo._pitch_arr, _lib.stream_ptr(geo)),
-                "nnd_geo_transpose_pool",
-            )
+        _lib.ops().geo_transpose_pool(geo, self._geo.buffer, num_levels)
 
     @classmethod
     def from_pyramids(cls, feat_levels, geo_levels, batch, height, num_levels=4, radius=4, num_groups=8,
@@ -134,13 +127,7 @@ class GeometryAwareCostVolume(nn.Module):
             "Number of channels of fmap1 and fmap2 must be the factor of num_groups"
         if G * G > C:
             raise IndexError("tuple index out of range")  # reference reads chunk i < G of size G (:90)
-        with torch.cuda.device(f1.device):
-            _lib.check(
-                _lib.load().nnd_groupcorr_build(_lib.ptr(f1), _lib.ptr(f2), B, C, H, W1, W2, G, G,
-                                                float(math.sqrt(G)), pyr.num_levels, pyr._level_ptrs, pyr._pitch_arr,
-                                                _lib.stream_ptr(f1)),
-                "nnd_groupcorr_build",
-            )
+        _lib.ops().groupcorr_build(f1, f2, pyr.buffer, G, G, float(math.sqrt(G)), pyr.num_levels)
 
     def _reference_list(self, il):
         """The reference's ``num_levels + 1`` list from an interleaved pyramid (de-interleaved copies)."""
@@ -189,42 +176,18 @@ class GeometryAwareCostVolume(nn.Module):
             cost = torch.nn.functional.conv3d(geo, weight, bias, 1, 1).squeeze(1).contiguous()
             disp = soft_argmin(cost)
             return (disp, cost) if return_cost else disp
-        out = torch.empty(B, 1, H, W1, dtype=torch.float32, device=weight.device)
-        cost = torch.empty(B, D, H, W1, dtype=torch.float32, device=weight.device) if return_cost else None
-        with torch.cuda.device(weight.device):
-            _lib.check(
-                _lib.load().nnd_gev_squeeze_soft_argmin(_lib.ptr(self._geo_il.levels[0]), _lib.ptr(weight),
-                                                        _lib.ptr(bias) if bias is not None else None, B,
-                                                        self.num_groups, D, H, W1, _lib.ptr(out),
-                                                        _lib.ptr(cost) if cost is not None else None,
-                                                        _lib.stream_ptr(weight)),
-                "nnd_gev_squeeze_soft_argmin",
-            )
+        out, cost = _lib.ops().gev_squeeze_soft_argmin(self._geo_il.levels[0], weight, bias, B, self.num_groups, D, H, W1,
+                                                       bool(return_cost))
         return (out, cost) if return_cost else out
 
     def forward(self, coords):
         B, H, W1, _ = self._shape
         coords = _check_coords(coords, B, H, W1)
-        T = 2 * self.radius + 1
-        out = torch.empty(B, self.num_levels * 2 * self.num_groups * T, H, W1, dtype=torch.float32,
-                          device=coords.device)
         if self._interleaved:
-            with torch.cuda.device(coords.device):
-                _lib.check(
-                    _lib.load().nnd_gev_lookup(self._feat_il._level_ptrs, self._geo_il._level_ptrs, _lib.ptr(coords), B,
-                                               self.num_groups, self._shape[3], H, W1, self.num_levels, self.radius,
-                                               _lib.ptr(out), _lib.stream_ptr(coords)),
-                    "nnd_gev_lookup",
-                )
-            return out
-        with torch.cuda.device(coords.device):
-            _lib.check(
-                _lib.load().nnd_group_lookup(self._feat._level_ptrs, self._geo._level_ptrs, self._feat._width_arr,
-                                             self._feat._pitch_arr, _lib.ptr(coords), B, self.num_groups, H, W1,
-                                             self.num_levels, self.radius, 0, _lib.ptr(out), _lib.stream_ptr(coords)),
-                "nnd_group_lookup",
-            )
-        return out
+            return _lib.ops().gev_lookup(self._feat_il.buffer, self._geo_il.buffer, coords, self._shape[3], self.num_levels,
+                                         self.radius)
+        return _lib.ops().group_lookup(self._feat.buffer, self._geo.buffer, self._shape[3], coords, self.num_groups,
+                                       self.num_levels, self.radius, 0)
 
 
 def soft_argmin(cost):
@@ -235,9 +198,4 @@ def soft_argmin(cost):
     cost = _lib.as_cuda_f32(cost, "cost")
     if cost.dim() != 4:
         raise RuntimeError(f"cost must be (B, D, H, W), got {tuple(cost.shape)}")
-    B, D, H, W = cost.shape
-    out = torch.empty(B, 1, H, W, dtype=torch.float32, device=cost.device)
-    with torch.cuda.device(cost.device):
-        _lib.check(_lib.load().nnd_soft_argmin(_lib.ptr(cost), B, D, H, W, _lib.ptr(out), _lib.stream_ptr(cost)),
-                   "nnd_soft_argmin")
-    return out
+    return _lib.ops().soft_argmin(cost)

@@ -795,7 +795,7 @@ class RAFTStereo(nn.Module):
         # weights put the final disparity 0.013 - 0.018 px from the fp32 reference, outside the 0.01 px bar).
         # exact_encoder: the same for the feature encoder (run once per forward).
         self.exact_weights = True
-        self.exact_encoder = False
+        self.exact_encoder = True
         self._graphs = {}
         if weights is not None:
             state = torch.load(weights, map_location="cpu") if not str(weights).endswith(".safetensors") else None

@@ -32,13 +32,5 @@ def convex_upsample(flow, mask, rate=8, mask_scale=1.0, mask_bias=None):
         mask_bias = _lib.as_cuda_f32(mask_bias, "mask_bias")
         if mask_bias.numel() != 9 * rate * rate:
             raise RuntimeError(f"mask_bias must have {9 * rate * rate} elements, got {mask_bias.numel()}")
-    out = torch.empty(N, 1, rate * H, rate * W, dtype=torch.float32, device=flow.device)
-    with torch.cuda.device(flow.device):
-        _lib.check(
-            _lib.load().nnd_convex_upsample(_lib.ptr(flow), _lib.ptr(mask), _lib.ptr(mask_bias) if mask_bias is not None else None,
-                                            N, H, W, int(rate), float(mask_scale),
-                                            (2 if mask.dtype == torch.float16 else 1) if nhwc else 0, _lib.ptr(out),
-                                            _lib.stream_ptr(flow)),
-            "nnd_convex_upsample",
-        )
-    return out
+    return _lib.ops().convex_upsample(flow, mask, mask_bias, int(rate), float(mask_scale),
+                                      (2 if mask.dtype == torch.float16 else 1) if nhwc else 0)

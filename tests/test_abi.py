@@ -105,3 +105,36 @@ def test_product_package_does_not_import_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), fn
+
+
+TORCH_OPS = ["abi_version", "corr1d_build", "groupcorr_build", "avgpool_pairs", "corr1d_lookup", "corr1d_lookup_conv1x1",
+             "corr1d_lookup_backward", "pyramid_unpool_", "corr1d_lookup_indices", "group_lookup", "geo_transpose_pool",
+             "gev_interleave_pool", "gev_lookup", "soft_argmin", "gev_squeeze_soft_argmin", "nchw_to_nhwc", "agcl_offset",
+             "agcl_iter", "convex_upsample"]
+
+
+def test_torch_extension_registers_every_operator_and_refuses_cpu_tensors():
+    """The thin PyTorch C++ extension over the C ABI (csrc/torch_ext.cpp): every operator the mirror classes call is
+    registered under torch.ops.nndepth_b200, reports the C ABI's version, and raises (no compute, no fallback) on CPU
+    tensors, wrong dtypes and non-contiguous tensors."""
+    import torch
+    from nndepth_b200 import _lib
+    ops = _lib.ops()
+    assert ops.abi_version() == _lib.load().nnd_abi_version() == 1
+    for name in TORCH_OPS:
+        assert hasattr(torch.ops.nndepth_b200, name), name
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ops.soft_argmin(torch.zeros(1, 4, 2, 2))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ops.corr1d_lookup(torch.zeros(64), 8, torch.zeros(1, 1, 1, 8), 1, 4)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ops.agcl_iter(torch.zeros(1, 16, 2, 2), torch.zeros(1, 16, 2, 2), torch.zeros(1, 2, 2, 2), False, False, None)
+    # the mirror classes go through the operator library, not ctypes
+    import inspect
+    import nndepth_b200.corr as corr
+    import nndepth_b200.igev as igev
+    import nndepth_b200.agcl as agcl
+    import nndepth_b200.upsample as upsample
+    for mod in (corr, igev, agcl, upsample):
+        src = inspect.getsource(mod)
+        assert "_lib.ops()" in src and "_lib.load()" not in src, mod.__name__

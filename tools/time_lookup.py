@@ -53,7 +53,7 @@ def main():
             disp = torch.rand(B, 1, H, W, device=dev) * 40
         coords = (base - disp).contiguous()
         conv = torch.nn.Conv2d(36, 256, 1).to(dev)
-        wt = blk.prepare_conv1x1_weight(conv.weight)
+        wt = blk.prepare_conv1x1_weight(conv.weight.detach())
         bias = conv.bias.detach()
         px = B * H * W
         for layout, elem in ((2, 2), (1, 4)):
