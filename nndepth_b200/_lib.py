@@ -117,7 +117,12 @@ class _Ops:
 
         def call(*args):
             global _launches
-            out = fn(*args)
+            try:
+                out = fn(*args)
+            except RuntimeError as e:
+                if " failed (status " in str(e):        # a non-zero status of the C ABI (TORCH_CHECK in torch_ext.cpp)
+                    raise NNDepthError(str(e).split("\n")[0]) from None
+                raise
             _launches += 1
             return out
 

@@ -13,17 +13,20 @@
 //                            the reference's exact fp32 operation order (bit-exact indices) and writes them, rounded
 //                            to nearest TF32, straight into the A operand's core-matrix layout: K is laid out as
 //                            4 levels x 12 columns (9 taps + 3 zeros), so a thread's taps are three 16-byte stores.
-//   warp   20    MMA         one thread: 6 x tcgen05.mma kind::tf32 (M 128 pixels, N 256 channels, K 8) per tile into
+//   warp   24    MMA         one thread: 6 x tcgen05.mma kind::tf32 (M 128 pixels, N 256 channels, K 8) per tile into
 //                            one of two 256-column TMEM accumulators; tcgen05.commit releases the A slot to the
 //                            producers and hands the accumulator to the epilogue.
-//   warps 16-19  EPILOGUE    stage the weights (once, while the producers already gather), then per tile:
-//                            tcgen05.ld 32 columns -> + bias -> ReLU -> fp16 / fp32 -> XOR-swizzled per-warp staging
-//                            -> 256-byte contiguous row segments of the channels-last output.
+//   warps 16-23  EPILOGUE    warp = (TMEM lane quarter, half of the 256 channels).  Per tile: tcgen05.ld 32 columns ->
+//                            + bias -> ReLU -> fp16 / fp32 -> a 32-row x 128-byte box in the 128B-swizzle layout ->
+//                            one TMA store (cp.async.bulk.tensor.2d) per box into the channels-last output: no
+//                            read-back of the staging tile, no per-thread global stores.
 //
 // mbarrier pipelines: a_full / a_empty (producers <-> MMA, ring of NA operand slots), tmem_full / tmem_empty (MMA <->
 // epilogue, 2 accumulators), b_ready (weights staged).  Work is split in CONTIGUOUS pixel ranges of equal length
 // (one per SM, flat over the batch), so every CTA gathers and stores the same number of pixels: at the KITTI shape
 // 405 pixels = 3.16 tiles each instead of 3 tiles on most SMs and 4 on 24 of them.
+#include <cuda.h>
+
 #include "common.cuh"
 #include "lookup_common.cuh"
 
@@ -40,19 +43,19 @@ constexpr int A_SLOT_BYTES = KSTEPS * A_KSTEP_BYTES;   // 24 KB
 constexpr int NA = 2;                       // A-operand ring
 constexpr int PROD_WARPS = 16;
 constexpr int EPI_WARP0 = 16;
-constexpr int EPI_WARPS = 4;
-constexpr int MMA_WARP = 20;
+constexpr int EPI_WARPS = 8;
+constexpr int MMA_WARP = 24;
 constexpr int THREADS = 32 * (MMA_WARP + 1);
 constexpr int WSTRIDE = 20;                 // floats per staged window (16 + 4: 16-byte aligned rows)
 constexpr int WIN_BUF_FLOATS = 32 * WSTRIDE;
-constexpr int STAGE_ROW_BYTES = 256;        // one pass of the epilogue writes 256 bytes of every pixel row
-constexpr int STAGE_WARP_BYTES = 32 * STAGE_ROW_BYTES;
+constexpr int BOX_ROW_BYTES = 128;          // one TMA store box: 32 pixel rows x 128 bytes (SWIZZLE_128B atom width)
+constexpr int STAGE_WARP_BYTES = 32 * BOX_ROW_BYTES;
 
 constexpr int SMEM_B = 0;
 constexpr int SMEM_A = SMEM_B + KSTEPS * B_KSTEP_BYTES;                       // 48 KB
 constexpr int SMEM_WIN = SMEM_A + NA * A_SLOT_BYTES;                          // + 48 KB
 constexpr int SMEM_STAGE = SMEM_WIN + PROD_WARPS * 2 * WIN_BUF_FLOATS * 4;    // + 80 KB
-constexpr int SMEM_BIAS = SMEM_STAGE + EPI_WARPS * STAGE_WARP_BYTES;          // + 32 KB
+constexpr int SMEM_BIAS = SMEM_STAGE + EPI_WARPS * STAGE_WARP_BYTES;          // + 32 KB (1024-byte aligned boxes)
 constexpr int SMEM_BAR = SMEM_BIAS + NOUT * 4;
 constexpr int SMEM_TOTAL = SMEM_BAR + 128;
 
@@ -65,6 +68,14 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // byte offset of the 16-byte chunk `ch` (4 consecutive K columns) of operand row `r`
 __device__ __forceinline__ uint32_t chunk_offset(int r, int ch, int kstep_bytes) {
@@ -76,8 +87,9 @@ __device__ __forceinline__ uint32_t chunk_offset(int r, int ch, int kstep_bytes)
 // out: channels-last (B*H*W, 256), fp16 (OUT_F16) or fp32.  weight: (36, 256) k-major fp32.
 template <bool OUT_F16>
 __global__ void __launch_bounds__(ws::THREADS, 1)
-corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const float* __restrict__ weight,
-                                const float* __restrict__ bias, int relu, long long total_px, long long px_per_cta) {
+corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const __grid_constant__ CUtensorMap out_map,
+                                const float* __restrict__ weight, const float* __restrict__ bias, int relu,
+                                long long total_px, long long px_per_cta) {
   using namespace ws;
   using umma::smem_u32;
   using umma::mbar_init;
@@ -253,31 +265,47 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const floa
     }
   } else {
     // =========================================== epilogue ===========================================
-    const int eq = warp - EPI_WARP0;                    // TMEM lane quarter this warp may read (warp % 4)
-    const int et = tid - 32 * EPI_WARP0;                // 0..127
+    const int e = warp - EPI_WARP0;
+    const int eq = e & 3;                               // TMEM lane quarter this warp may read (warp % 4)
+    const int half = e >> 2;                            // channels [128 * half, 128 * half + 128)
+    const int et = tid - 32 * EPI_WARP0;
     float* bias_s = reinterpret_cast<float*>(smem + SMEM_BIAS);
     for (int i = et; i < NOUT; i += 32 * EPI_WARPS) bias_s[i] = bias ? __ldg(bias + i) : 0.f;
+    if (e == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&out_map) : "memory");
     stage_weights();
-    asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // bias_s (staged below by these warps) is visible
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // bias_s is visible to every epilogue warp
     constexpr int ELEM = OUT_F16 ? 2 : 4;
     constexpr int ROW_BYTES = NOUT * ELEM;                       // bytes per pixel of the output
-    constexpr int PASSES = ROW_BYTES / STAGE_ROW_BYTES;          // 2 (fp16) or 4 (fp32)
-    constexpr int CHUNKS_PER_PASS = NOUT / PASSES / 32;          // tcgen05.ld x32 chunks per pass: 4 or 2
-    uint4* stage = reinterpret_cast<uint4*>(smem + SMEM_STAGE + eq * STAGE_WARP_BYTES);   // [32 rows][16 chunks of 16 B]
+    constexpr int COLS_PER_BOX = BOX_ROW_BYTES / ELEM;           // 64 (fp16) or 32 (fp32) channels per TMA box
+    constexpr int CHUNKS_PER_BOX = COLS_PER_BOX / 32;            // tcgen05.ld x32 chunks per box: 2 or 1
+    constexpr int BOXES = (NOUT / 2) / COLS_PER_BOX;             // boxes per warp and tile: 2 or 4
+    unsigned char* box = smem + SMEM_STAGE + e * STAGE_WARP_BYTES;          // [32 rows][128 B], 16-byte chunk c of row r at c ^ (r & 7)
+    const uint32_t box_addr = smem_u32(box);
     unsigned char* out_bytes = reinterpret_cast<unsigned char*>(a.out);
     for (int t = 0; t < nt; ++t) {
       const int acc = t & 1;
       mbar_wait(tmem_full(acc), (t >> 1) & 1);
       tc_fence_after();
-      const long long row0 = px0 + static_cast<long long>(t) * TILE + 32 * eq;   // pixel of staging row 0
+      const long long row0 = px0 + static_cast<long long>(t) * TILE + 32 * eq;   // pixel of my TMEM lane 0
+      const bool whole = row0 + 32 <= px_end;            // all 32 rows are mine: TMA store; else (the global tail) plain stores
+#ifdef NND_WS_SKIP_EPI
+      tc_fence_before();
+      mbar_arrive(tmem_empty(acc));
+      continue;
+#endif
 #pragma unroll 1
-      for (int pass = 0; pass < PASSES; ++pass) {
+      for (int b = 0; b < BOXES; ++b) {
+        const int colb = half * (NOUT / 2) + b * COLS_PER_BOX;   // first channel of the box
+        if (whole) {
+          if (lane == 0) tma_store_wait_read();          // the TMA store that last read this staging box has drained it
+          __syncwarp();
+        }
 #pragma unroll
-        for (int cq = 0; cq < CHUNKS_PER_PASS; ++cq) {
-          const int col0 = (pass * CHUNKS_PER_PASS + cq) * 32;
+        for (int cq = 0; cq < CHUNKS_PER_BOX; ++cq) {
+          const int col0 = colb + 32 * cq;
           float v[32];
           umma::ld32(tmem_base + (static_cast<uint32_t>(32 * eq) << 16) + static_cast<uint32_t>(acc * NOUT + col0), v);
-          if (pass == PASSES - 1 && cq == CHUNKS_PER_PASS - 1) {
+          if (b == BOXES - 1 && cq == CHUNKS_PER_BOX - 1) {
             tc_fence_before();
             mbar_arrive(tmem_empty(acc));                        // my last TMEM read of this tile
           }
@@ -290,42 +318,42 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const floa
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
           }
-          // 16-byte chunk c of staging row `lane` lives at chunk (c ^ (lane & 15)): conflict-free for these row-wise
-          // writes and for the chunk-wise reads below
+          uint4 pk[OUT_F16 ? 4 : 8];
           if (OUT_F16) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-              stage[lane * 16 + ((cq * 4 + i) ^ (lane & 15))] =
-                  make_uint4(pack_h2(v[8 * i], v[8 * i + 1]), pack_h2(v[8 * i + 2], v[8 * i + 3]),
-                             pack_h2(v[8 * i + 4], v[8 * i + 5]), pack_h2(v[8 * i + 6], v[8 * i + 7]));
+              pk[i] = make_uint4(pack_h2(v[8 * i], v[8 * i + 1]), pack_h2(v[8 * i + 2], v[8 * i + 3]),
+                                 pack_h2(v[8 * i + 4], v[8 * i + 5]), pack_h2(v[8 * i + 6], v[8 * i + 7]));
           } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              stage[lane * 16 + ((cq * 8 + i) ^ (lane & 15))] =
-                  make_uint4(__float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]), __float_as_uint(v[4 * i + 2]),
-                             __float_as_uint(v[4 * i + 3]));
+              pk[i] = make_uint4(__float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]), __float_as_uint(v[4 * i + 2]),
+                                 __float_as_uint(v[4 * i + 3]));
           }
-        }
-        __syncwarp();
-        // write the pass out: one instruction = two pixel rows x 256 contiguous bytes
-        {
-          const int c = lane & 15, rh = lane >> 4;
+          constexpr int NPK = OUT_F16 ? 4 : 8;
+          if (whole) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int r = 2 * i + rh;
-            const long long px = row0 + r;
-            const uint4 val = stage[r * 16 + (c ^ (r & 15))];
-#ifdef NND_WS_SKIP_STORE
-            if (px < px_end && val.x == 0x12345678u)
-#else
-            if (px < px_end)
-#endif
-              *reinterpret_cast<uint4*>(out_bytes + px * ROW_BYTES + pass * STAGE_ROW_BYTES + c * 16) = val;
+            for (int i = 0; i < NPK; ++i)
+              *reinterpret_cast<uint4*>(box + lane * BOX_ROW_BYTES + (((cq * NPK + i) ^ (lane & 7)) << 4)) = pk[i];
+          } else if (row0 + lane < px_end) {
+            uint4* dst = reinterpret_cast<uint4*>(out_bytes + (row0 + lane) * ROW_BYTES + static_cast<long long>(col0) * ELEM);
+#pragma unroll
+            for (int i = 0; i < NPK; ++i) dst[i] = pk[i];
           }
         }
-        __syncwarp();
+        if (whole) {
+          fence_proxy_async();                          // generic-proxy writes of the box -> visible to the TMA engine
+          __syncwarp();
+#ifndef NND_WS_SKIP_STORE
+          if (lane == 0) {
+            tma_store_2d(&out_map, box_addr, colb * ELEM / 4, static_cast<int>(row0));   // coordinates in 32-bit words, rows
+            tma_store_commit();
+          }
+#endif
+        }
       }
     }
+    if (lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -336,6 +364,25 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const floa
   }
 }
 
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || !sym) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(sym);
+  return fn;
+}
+}  // namespace
+
 // host-side launcher, called by nnd_corr1d_lookup_conv1x1 (lookup.cu) for the shipping shape:
 // 4 levels, radius 4, c_out = 256, channels-last output, 16-byte aligned pyramid rows
 nnd_status launch_lookup_conv1x1_ws(const LookupArgs& a, const float* weight, const float* bias, int relu, int out_f16,
@@ -345,17 +392,41 @@ nnd_status launch_lookup_conv1x1_ws(const LookupArgs& a, const float* weight, co
   const long long grid = tiles < sms ? tiles : sms;
   long long per = (total_px + grid - 1) / grid;
   per = (per + 31) & ~31LL;                                  // whole 32-pixel groups per CTA
+  if (total_px >= (1LL << 31)) {
+    set_error("lookup_conv1x1: %lld pixels exceed the TMA store's 32-bit row coordinate", total_px);
+    return NND_ERR_INVALID_ARGUMENT;
+  }
+  // the channels-last output as a 2-D tensor of 32-bit words: (total_px rows) x (row_bytes / 4 words), stored in boxes of
+  // 32 rows x 32 words (128 bytes) whose shared-memory image uses the 128-byte swizzle
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) {
+    set_error("lookup_conv1x1: cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+    return NND_ERR_CUDA;
+  }
+  alignas(64) CUtensorMap out_map;
+  const cuuint64_t row_bytes = static_cast<cuuint64_t>(ws::NOUT) * (out_f16 ? 2 : 4);
+  const cuuint64_t dims[2] = {row_bytes / 4, static_cast<cuuint64_t>(total_px)};
+  const cuuint64_t strides[1] = {row_bytes};
+  const cuuint32_t box[2] = {32, 32};
+  const cuuint32_t elem_strides[2] = {1, 1};
+  const CUresult r = enc(&out_map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, a.out, dims, strides, box, elem_strides,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("lookup_conv1x1: cuTensorMapEncodeTiled(output) failed with CUresult %d", static_cast<int>(r));
+    return NND_ERR_CUDA;
+  }
   cudaError_t e;
   if (out_f16) {
     e = cudaFuncSetAttribute(corr1d_lookup_conv1x1_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws::SMEM_TOTAL);
     if (e != cudaSuccess) return cuda_fail(e, "lookup_conv1x1: shared-memory attribute");
     corr1d_lookup_conv1x1_ws_kernel<true><<<static_cast<unsigned>(grid), ws::THREADS, ws::SMEM_TOTAL, stream>>>(
-        a, weight, bias, relu, total_px, per);
+        a, out_map, weight, bias, relu, total_px, per);
   } else {
     e = cudaFuncSetAttribute(corr1d_lookup_conv1x1_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws::SMEM_TOTAL);
     if (e != cudaSuccess) return cuda_fail(e, "lookup_conv1x1: shared-memory attribute");
     corr1d_lookup_conv1x1_ws_kernel<false><<<static_cast<unsigned>(grid), ws::THREADS, ws::SMEM_TOTAL, stream>>>(
-        a, weight, bias, relu, total_px, per);
+        a, out_map, weight, bias, relu, total_px, per);
   }
   return check_launch("corr1d_lookup_conv1x1_ws_kernel");
 }
