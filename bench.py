@@ -10,10 +10,14 @@ each with a fused 4-level radius-4 lookup, convex upsampling of every iteration 
 reference's ``evaluate.py``), random-init weights of the reference architecture (seed 0).
 
 Prints ONE JSON line (rank 0).  ``value`` = pairs/s with inputs resident in HBM; ``e2e`` = pairs/s
-through ``StereoEngine.infer`` with pinned HOST buffers (H2D + D2H inside the timed region);
-``roofline`` = the per-iteration lookup kernel against measured HBM bandwidth; ``cpu_baseline`` = the
-oracle port (torch CPU ops, all host threads) on a bounded sample.  Multi-GPU: one process per GPU
-(torchrun), batch-sharded, no data-path collective; the only NCCL call gathers the output maps.
+through ``StereoEngine.submit/collect`` with pinned HOST buffers (H2D + D2H inside the timed region);
+``roofline`` = the per-iteration lookup kernel against measured HBM bandwidth; ``parity`` = final EPE of
+the timed configuration against the reference model, measured in the run; ``value_fp32`` = the same step
+with every dense layer in fp32; ``gpu_baseline`` = the unmodified reference on torch.cuda; ``cpu_baseline`` =
+the unmodified reference (oracle/_ref) on all host threads, bounded sample; ``hotpath`` = BASELINE configs
+0 / 2 / 3 / 4 kernel by kernel; ``strong`` = the same 8 pairs split across the GPUs.  Multi-GPU: one process
+per GPU (torchrun), batch-sharded, no data-path collective; the only NCCL call gathers the output maps
+(on its own stream, overlapped with the next step).
 """
 import argparse
 import json
@@ -103,22 +107,36 @@ def physical_gpu_index(local_rank):
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU reference / baseline leg (oracle port; the only place bench.py executes oracle/)
+# reference legs: the UNMODIFIED reference (oracle/_ref, staged by __graft_entry__.build()) on the host CPU and on
+# torch.cuda; the oracle port only when the staged copy is missing.  The only places bench.py executes oracle/.
 # ------------------------------------------------------------------------------------------------
-def cpu_forward_seconds(steps, warmup, pairs=1):
-    """Seconds per step of the reference algorithm on the host: model shell + oracle correlation."""
+def reference_model(seed=0):
+    """(model, Padder class, kind): the reference's own BaseRAFTStereo (stock code path, kind "reference"), else the
+    repo's model shell with the oracle's torch-op correlation (kind "port")."""
+    from oracle import ref_shim
+    torch.manual_seed(seed)
+    if ref_shim.available():
+        ref_shim.install()
+        from nndepth.models.raft_stereo.model import BaseRAFTStereo as RefModel
+        from nndepth.data.dataloaders.utils import Padder as RefPadder
+        return RefModel(iters=ITERS).eval(), (lambda shape: RefPadder(shape[-2:], divis_by=32)), "reference"
     from nndepth_b200.raft_stereo import BaseRAFTStereo
     from nndepth_b200.engine import Padder
     from oracle import torch_port
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    torch.manual_seed(0)
     model = BaseRAFTStereo(iters=ITERS).eval()
     model.corr_fn = torch_port.CorrBlock1D
+    return model, (lambda shape: Padder(shape, 32)), "port"
+
+
+def cpu_forward_seconds(steps, warmup, pairs=1):
+    """Seconds per step of the reference on the host cores: pad -> forward -> unpad (evaluate.py:146-156)."""
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    model, make_padder, kind = reference_model()
     gen = torch.Generator().manual_seed(1)
     left = torch.rand((pairs, 3) + IMAGE_HW, generator=gen) * 2 - 1
     right = torch.rand((pairs, 3) + IMAGE_HW, generator=gen) * 2 - 1
-    padder = Padder(left.shape, 32)
+    padder = make_padder(left.shape)
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
@@ -128,25 +146,56 @@ def cpu_forward_seconds(steps, warmup, pairs=1):
             float(out.sum())
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
-    return sum(times) / len(times), torch.get_num_threads()
+    return sum(times) / len(times), torch.get_num_threads(), kind
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sec, threads = cpu_forward_seconds(args.steps, args.warmup, pairs=1)
+    sec, threads, kind = cpu_forward_seconds(args.steps, args.warmup, pairs=1)
     value = 1.0 / sec
-    sample = f"1 pair of {IMAGE_HW[0]}x{IMAGE_HW[1]} per step ({ITERS} iterations), {args.steps} timed steps"
+    sample = (f"1 pair of {IMAGE_HW[0]}x{IMAGE_HW[1]} per step ({ITERS} iterations), {args.steps} timed steps, "
+              + ("the reference's BaseRAFTStereo as is (oracle/_ref)" if kind == "reference"
+                 else "model shell in torch CPU ops + oracle/torch_port.py correlation"))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def reference_on_cuda(device, left, right, steps=3):
+    """The reference model on torch.cuda, same weights (seed 0) and inputs: (disparity in strict fp32, ms per forward in
+    strict fp32, ms per forward with PyTorch's stock flags).  The like-for-like GPU baseline and the parity reference."""
+    model, make_padder, kind = reference_model()
+    model = model.to(device)
+    padder = make_padder(left.shape)
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    out, ms = None, {}
+    try:
+        for label, tf32 in (("stock_flags", None), ("strict_fp32", False)):
+            torch.backends.cudnn.benchmark = False
+            if tf32 is None:
+                torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = True, False   # PyTorch defaults
+            else:
+                torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = tf32
+            with torch.no_grad():
+                for i in range(steps + 1):
+                    if i == 1:
+                        torch.cuda.synchronize(device)
+                        t0 = time.perf_counter()
+                    lp, rp = padder.pad(left, right)
+                    out = padder.unpad(model(lp, rp)[-1]["up_disp"])
+                torch.cuda.synchronize(device)
+            ms[label] = (time.perf_counter() - t0) / steps * 1e3
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = saved
+    return out, ms, kind
 
 
 # ------------------------------------------------------------------------------------------------
@@ -282,6 +331,66 @@ def time_step_kernels(device, peak):
     return rows
 
 
+def time_fused_lookup(device, B, out_elem, peak, reps=10):
+    """The per-iteration kernel (lookup + convc1 + ReLU) stand-alone at batch ``B`` of the KITTI feature shape, L2 flushed."""
+    import nndepth_b200 as nb
+    C, H, W = 256, 48, 156
+    torch.manual_seed(3)
+    f1, f2 = torch.randn(B, C, H, W, device=device), torch.randn(B, C, H, W, device=device)
+    blk = nb.CorrBlock1D(f1, f2, 4, 4)
+    del f1, f2
+    coords = (torch.arange(W, device=device).float().view(1, 1, 1, W).repeat(B, 1, H, 1)
+              - torch.rand(B, 1, H, W, device=device) * 40)
+    conv = torch.nn.Conv2d(36, 256, 1).to(device)
+    wt = blk.prepare_conv1x1_weight(conv.weight.detach())
+    bias = conv.bias.detach()
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=device)
+    stream = torch.cuda.current_stream(device)
+
+    def launch():
+        return blk.lookup_conv1x1(coords, None, bias, relu=True, weight_t=wt, precision="tf32", channels_last=True,
+                                  half=out_elem == 2)
+    for _ in range(3):
+        launch()
+    ts = []
+    for _ in range(reps):
+        flush.fill_(1.0)
+        torch.cuda._sleep(200000)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        launch()
+        e1.record(stream)
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    us = statistics.median(ts)
+    nbytes = B * H * W * (164 + 256 * out_elem)
+    del blk, flush
+    torch.cuda.empty_cache()
+    return {"batch": B, "pixels": B * H * W, "us_per_launch_l2_flushed": us, "algorithmic_bytes_per_launch": nbytes,
+            "achieved_gbs": nbytes / us / 1e3, "frac": nbytes / us / 1e3 / peak}
+
+
+def hotpath_configs(skip_cpu=False):
+    """The other BASELINE configs (0, 2, 3, 4) through bench_hotpath.py, condensed: kernel microseconds with their
+    fraction of the HBM roofline, the reference's ATen chain on torch.cuda beside them, the reference on the host cores."""
+    import bench_hotpath as hp
+    out = {}
+    for name, fn in (("cfg1", hp.cfg1), ("cfg3", hp.cfg3), ("cfg4", hp.cfg4), ("cfg5", hp.cfg5)):
+        try:
+            line = fn(skip_cpu)
+        except Exception as e:          # a failed side leg must not lose the headline line
+            out[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            torch.cuda.empty_cache()
+            continue
+        roofs = [line.get("roofline")] + [line.get("lookup_roofline")] + list(line.get("other_rooflines", []))
+        out[name] = {"workload": line["config"]["workload"], "gpu_us": line["gpu_us"],
+                     "rooflines": [{"kernel": r["kernel"], "us": r["us_per_launch"], "algorithmic_bytes": r["algorithmic_bytes_per_launch"],
+                                    "achieved_gbs": r["achieved"], "frac": r["frac"]} for r in roofs if r],
+                     "gpu_baseline": line.get("gpu_baseline"), "cpu_baseline": line.get("cpu_baseline")}
+        torch.cuda.empty_cache()
+    return out
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -307,7 +416,7 @@ def run_ours(args):
     import torch.distributed as dist
     import nndepth_b200 as nb
     from nndepth_b200 import _lib
-    from nndepth_b200.engine import StereoEngine, gather_disparities
+    from nndepth_b200.engine import OverlappedGather, StereoEngine
     from nndepth_b200.raft_stereo import BaseRAFTStereo
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -324,14 +433,12 @@ def run_ours(args):
     nb.load_library()
     if args.volume_precision:
         nb.set_volume_precision(args.volume_precision)
-    # Parity first: the reference computes in fp32 (CPU) and the bar is 0.01 px of final end-point error.
-    # Measured on the KITTI / 32-iteration golden (tools/exp_epe_modules.py, tests/test_gpu_raft_model.py):
-    # all cuDNN convolutions in TF32 drift 0.0147 px (outside the bar); the drift comes from the ConvGRU
-    # recurrence.  "mixed" keeps the ConvGRU in fp32 and lets the encoder, motion encoder, flow and mask heads
-    # use TF32 tensor cores: 0.0021 px.  "mixed2x" (default) keeps the ConvGRU's WEIGHTS exact on the tensor cores
-    # (conv(RN(x), [w_hi; w_lo]), the halves added in the fused channels-last glue kernels -- the recurrence is
-    # sensitive to weight rounding only, tools/exp_epe_2term.py): 0.0031 px at 4x the speed of "mixed".  "fp32" (0.0002 px) and "tf32" are selectable; `value` is never measured in the
-    # out-of-tolerance "tf32" mode unless asked for explicitly.
+    # Parity first: the reference computes in fp32 and the bar is 0.01 px of final end-point error.  The default
+    # "mixed16" runs every dense layer on fp16 tensor-core products with fp32 accumulation and gives the convolutions
+    # whose rounding would repeat identically in all 32 iterations (ConvGRU, motion encoder, flow head) and the feature
+    # encoder two-term weights w_hi + w_lo; tests/test_gpu_dropin.py gates it on weight seeds 0-3 x two inputs, and
+    # the EPE of THIS run against the reference model on torch.cuda is measured below (key "parity").  `value` is
+    # never measured in the out-of-tolerance "tf32" mode unless asked for explicitly.
 
     torch.manual_seed(0)
     model = BaseRAFTStereo(iters=ITERS).eval()
@@ -348,9 +455,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(device)
 
+    # the only collective: the all-gather of the ranks' disparity maps.  It runs on its own stream behind a snapshot of
+    # the maps, overlapped with the next step's forward; the last one is waited for inside the timed region.
+    gather = OverlappedGather(world, device=device)
+
     def step_device():
         disp = engine.infer_device(dev_l, dev_r)
-        return gather_disparities(disp, world) if world > 1 else disp
+        gather.submit(disp)
+        return disp
 
     pending = []
 
@@ -365,6 +477,9 @@ def run_ours(args):
     def drain_host():
         while pending:
             engine.collect(pending.pop(0))
+
+    def finish_device():
+        gather.result()
 
     def timed(fn, steps, warmup, finish=None):
         for _ in range(warmup):
@@ -428,13 +543,31 @@ def run_ours(args):
         step_device()
     barrier()
     sampler.start()
-    dev_ms, _ = timed(step_device, args.steps, 0)
+    dev_ms, _ = timed(step_device, args.steps, 0, finish=finish_device)
     clocks = sampler.stop()
     _, host_wall_ms = timed(step_host, args.steps, 2, finish=drain_host)
 
     total_pairs = PAIRS_PER_GPU * world * args.steps
     value = total_pairs / (dev_ms / 1e3)
     e2e_value = total_pairs / (host_wall_ms / 1e3)
+
+    # strong scaling (B/n pairs per GPU): the SAME 8 pairs split over the ranks
+    strong = None
+    if PAIRS_PER_GPU % world == 0:
+        per_rank = PAIRS_PER_GPU // world
+        if world == 1:
+            strong = {"global_pairs": PAIRS_PER_GPU, "pairs_per_gpu": per_rank, "value": value, "unit": UNIT,
+                      "ms_per_step": dev_ms / args.steps}
+        else:
+            sl, sr = dev_l[:per_rank].contiguous(), dev_r[:per_rank].contiguous()
+            sgather = OverlappedGather(world, device=device)
+
+            def step_strong():
+                sgather.submit(engine.infer_device(sl, sr))
+
+            strong_ms, _ = timed(step_strong, args.steps, 3, finish=sgather.result)
+            strong = {"global_pairs": PAIRS_PER_GPU, "pairs_per_gpu": per_rank, "unit": UNIT,
+                      "value": PAIRS_PER_GPU * args.steps / (strong_ms / 1e3), "ms_per_step": strong_ms / args.steps}
 
     line = None
     if rank == 0:
@@ -449,34 +582,85 @@ def run_ours(args):
         achieved = step_bytes / (in_step_med * 1e-6) / 1e9
         cpu = None
         if world == 1 and not args.skip_cpu_baseline:
-            sec, threads = cpu_forward_seconds(steps=2, warmup=1, pairs=1)
-            cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"1 pair of {IMAGE_HW[0]}x{IMAGE_HW[1]}, {ITERS} iterations, 2 timed forwards "
-                             f"(model shell in torch CPU ops + oracle/torch_port.py correlation)"}
+            sec, threads, kind = cpu_forward_seconds(steps=2, warmup=1, pairs=1)
+            cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": threads, "kind": kind,
+                   "sample": f"1 pair of {IMAGE_HW[0]}x{IMAGE_HW[1]}, {ITERS} iterations, 2 timed forwards, "
+                             + ("the reference's BaseRAFTStereo as is (oracle/_ref)" if kind == "reference"
+                                else "model shell in torch CPU ops + oracle/torch_port.py correlation")}
+        # ---- parity, measured in this run: the timed configuration against the reference model on torch.cuda (strict
+        # fp32, same seed-0 weights, this rank's 8 pairs); the same reference run is the like-for-like GPU baseline ----
+        parity, gpu_baseline = None, None
+        if not args.skip_parity:
+            want, ref_ms, ref_kind = reference_on_cuda(device, dev_l, dev_r)
+            got = engine.infer_device(dev_l, dev_r)
+            per_pair = (got - want).abs().flatten(1).mean(1)
+            parity = {"final_epe_px_vs_reference": (got - want).abs().mean().item(), "worst_pair_epe_px": per_pair.max().item(),
+                      "bar_px": 0.01, "measured_in_this_run": True, "pairs": int(got.shape[0]),
+                      "reference": ("the unmodified reference BaseRAFTStereo (oracle/_ref) on torch.cuda, strict fp32, same weights "
+                                    "and inputs" if ref_kind == "reference" else "oracle port on torch.cuda (oracle/_ref missing)"),
+                      "mean_abs_disparity_px": want.abs().mean().item(),
+                      "other_weight_seeds": "tests/test_gpu_dropin.py::test_headline_mode_against_reference_across_weight_seeds "
+                                            "gates seeds 0-3 x (noise, shipped KITTI pair) x batch 8 on the same bar"}
+            gpu_baseline = {"what": "the reference model itself (its ATen correlation chain, cuDNN convolutions) on torch.cuda, "
+                                    "one B200, batch 8, eager as the reference runs it",
+                            "kind": ref_kind, "ms_per_step_strict_fp32": ref_ms["strict_fp32"],
+                            "ms_per_step_stock_flags": ref_ms["stock_flags"], "unit": UNIT,
+                            "value_strict_fp32": PAIRS_PER_GPU / (ref_ms["strict_fp32"] / 1e3),
+                            "value_stock_flags": PAIRS_PER_GPU / (ref_ms["stock_flags"] / 1e3)}
+            del want, got
+        # ---- the precision-matched number: every dense layer in fp32 like the reference's eval (correlation volume fp32) ----
+        value_fp32 = None
+        if world == 1 and not args.skip_fp32:
+            torch.manual_seed(0)
+            m32 = BaseRAFTStereo(iters=ITERS).eval()
+            m32.dense_precision = "fp32"
+            old_prec = nb.get_volume_precision()
+            nb.set_volume_precision("fp32")
+            try:
+                e32 = StereoEngine(m32, device=device, use_cuda_graph=not args.no_graph)
+                for _ in range(2):
+                    e32.infer_device(dev_l, dev_r)
+                torch.cuda.synchronize(device)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(3):
+                    e32.infer_device(dev_l, dev_r)
+                e1.record(stream)
+                torch.cuda.synchronize(device)
+                value_fp32 = {"value": PAIRS_PER_GPU * 3 / (e0.elapsed_time(e1) / 1e3), "unit": UNIT,
+                              "ms_per_step": e0.elapsed_time(e1) / 3, "steps": 3,
+                              "dtype": "f32 everywhere: cuDNN fp32 convolutions, fp32 FFMA correlation volume"}
+            finally:
+                nb.set_volume_precision(old_prec)
+            del e32, m32
+            torch.cuda.empty_cache()
+        fnet_half = bool(args.dense_precision == "mixed16" and getattr(engine.model, "fp16_encoder", True))
+        dense = {"fp32": "cuDNN fp32", "tf32": "cuDNN TF32",
+                 "mixed": "ConvGRU cuDNN fp32, other convolutions cuDNN TF32",
+                 "mixed2x": "ConvGRU TF32 activations x split fp32 weights [w_hi; w_lo] on tensor cores, other convolutions cuDNN TF32",
+                 "mixed16": "fp16 tensor-core products with fp32 accumulation (TF32's 10-bit operand mantissa): ConvGRU fp16 "
+                            "activations x two-term weights [w_hi16; w_lo16], fp32 gates and state; motion encoder / flow head "
+                            + ("with two-term fp16 weights (w_hi + w_lo); " if getattr(engine.model, "exact_weights", False)
+                               else "fp16; ")
+                            + "mask head fp16; feature encoder "
+                            + (("fp16" + (" with two-term weights" if getattr(engine.model, "exact_encoder", False) else ""))
+                               if fnet_half else "cuDNN TF32")
+                            + "; one-channel flow convolutions fp32"}[args.dense_precision]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": warm, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None,
             "dtype": "f32 (correlation volume: %s operands rounded to nearest, fp32 accumulate; dense layers: %s)" % (
-                nb.get_volume_precision(), {"fp32": "cuDNN fp32", "tf32": "cuDNN TF32",
-                                            "mixed": "ConvGRU cuDNN fp32, other convolutions cuDNN TF32",
-                                            "mixed2x": "ConvGRU TF32 activations x split fp32 weights [w_hi; w_lo] on tensor cores, "
-                                                       "other convolutions cuDNN TF32",
-                                            "mixed16": "refinement iteration on fp16 tensor-core products with fp32 accumulation "
-                                                       "(same 10-bit operand mantissa as TF32): ConvGRU fp16 activations x split weights "
-                                                       "[w_hi16; w_lo16], fp32 gates and state; motion encoder and heads fp16; "
-                                                       "encoders cuDNN TF32; one-channel flow convolutions fp32"}[args.dense_precision]),
-            "parity": {"final_epe_px_vs_reference": {"fp32": 0.00016, "mixed": 0.0021, "mixed2x": 0.0031, "mixed16": 0.0024, "tf32": 0.0147}[args.dense_precision],
-                       "bar_px": 0.01, "source": "tests/test_gpu_raft_model.py::test_engine_bench_configuration_stays_inside_the_bar, tools/exp_epe_modules.py",
-                       "other_weight_seeds": "0.003 - 0.009 px against the same model run in fp32, for every mode that keeps "
-                                             "the encoders in TF32 (DESIGN.md 4b)"},
+                nb.get_volume_precision(), dense),
+            "dense_precision": args.dense_precision,
+            "parity": parity,
             "data": "synthetic", "config": workload_config(world), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": 2 * host_l.numel() * 4, "d2h_bytes_per_step": PAIRS_PER_GPU * IMAGE_HW[0] * IMAGE_HW[1] * 4,
                     "ms_per_step": host_wall_ms / args.steps},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": {"kernel": ("corr1d_lookup_conv1x1_kernel<9> (nnd_corr1d_lookup_conv1x1: lookup + convc1 + ReLU)"
-                                    if fused_front else "corr1d_lookup_lean_kernel<9> (nnd_corr1d_lookup)")
+            "roofline": {"kernel": ("corr1d_lookup_conv1x1_ws_kernel (nnd_corr1d_lookup_conv1x1: lookup + convc1 + ReLU, "
+                                    "warp-specialised tcgen05)" if fused_front else "corr1d_lookup_lean_kernel<9> (nnd_corr1d_lookup)")
                                    + ", 32 launches per step",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(fused_front), "peak_source": peak_src,
@@ -489,18 +673,26 @@ def run_ours(args):
                          "standalone_lookup": {"us_per_launch_l2_flushed": kern["lookup_ms_l2_flushed"] * 1e3,
                                                "us_per_launch_l2_warm": kern["lookup_ms_l2_warm"] * 1e3,
                                                "algorithmic_bytes_per_launch": kern["lookup_bytes"]},
-                         "note": "latency-bound launch: a torch copy of the same 18.4 MB takes 13.3 us flushed / "
-                                 "9.2 us warm in the same harness (profiles/README.md); the bandwidth-sized lookup "
-                                 "(IGEV config 4, 1.5 GB/launch) reaches 87.5 % of this peak"},
+                         "large_batch": time_fused_lookup(device, 64, out_elem, peak) if fused_front else None,
+                         "note": "the KITTI batch is a latency-sized launch (405 pixels per SM); large_batch times the same "
+                                 "kernel at batch 64, where it is bound by DRAM traffic"},
             "build": {"kernel": "nnd_corr1d_build (%s)" % nb.get_volume_precision(),
                       "us_per_launch_l2_flushed": kern["build_ms_l2_flushed"] * 1e3,
                       "hbm_gbs": kern["build_bytes"] / (kern["build_ms_l2_flushed"] * 1e-3) / 1e9,
+                      "frac_of_hbm_peak": kern["build_bytes"] / (kern["build_ms_l2_flushed"] * 1e-3) / 1e9 / peak,
                       "tflops": kern["build_flops"] / (kern["build_ms_l2_flushed"] * 1e-3) / 1e12},
             "other_kernels": time_step_kernels(device, peak),
             "cuda_graph": engine.use_cuda_graph,
+            "strong": strong,
         }
+        if value_fp32 is not None:
+            line["value_fp32"] = value_fp32
+        if gpu_baseline is not None:
+            line["gpu_baseline"] = gpu_baseline
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if world == 1 and not args.skip_hotpath:
+            line["hotpath"] = hotpath_configs(skip_cpu=args.skip_cpu_baseline)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -517,10 +709,14 @@ def main():
     ap.add_argument("--volume-precision", default=None, choices=["fp32", "tf32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--dense-precision", default="mixed16", choices=["fp32", "mixed", "mixed2x", "mixed16", "tf32"],
-                    help="cuDNN layers: fp32 everywhere (0.0002 px EPE); ConvGRU fp32 + TF32 elsewhere (0.0021 px); "
-                         "ConvGRU with split fp32 weights on tensor cores + TF32 elsewhere (default, 0.0031 px); TF32 everywhere "
-                         "(0.0147 px: outside the 0.01 px bar)")
+                    help="dense layers: 'mixed16' (default) fp16 tensor-core products, fp32 accumulation, two-term weights; "
+                         "'mixed2x' ConvGRU with split fp32 weights on TF32 tensor cores + TF32 elsewhere; 'mixed' ConvGRU fp32 + "
+                         "TF32 elsewhere; 'fp32' everything fp32; 'tf32' everything TF32 (outside the 0.01 px bar).  The final "
+                         "EPE against the reference is measured in the run (key 'parity')")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-parity", action="store_true", help="do not run the reference model on torch.cuda (parity + gpu_baseline)")
+    ap.add_argument("--skip-fp32", action="store_true", help="do not time the all-fp32 configuration (value_fp32)")
+    ap.add_argument("--skip-hotpath", action="store_true", help="do not time BASELINE configs 0 / 2 / 3 / 4 (hotpath)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -61,6 +61,20 @@ def roof(kernel, nbytes, us):
             "traffic": None, "peak_source": PEAK_SRC, "algorithmic_bytes_per_launch": nbytes, "us_per_launch": us}
 
 
+def reference_available():
+    """The unmodified reference staged under oracle/_ref (or /root/reference in the build container)."""
+    from oracle import ref_shim
+    if not ref_shim.available():
+        return False
+    ref_shim.install()
+    return True
+
+
+def strict_fp32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
 def cpu_seconds(fn, reps=2):
     fn()
     ts = []
@@ -95,16 +109,36 @@ def cfg1(skip_cpu):
             "gpu_us": {"build": build, "lookup": lookup, "build_plus_32_lookups": total},
             "roofline": roof("corr1d_build_tf32_kernel", 2 * B * C * H * W * 4 + B * H * W * 300 * 4, build),
             "lookup_roofline": roof("corr1d_lookup_lean_kernel<9>", B * H * W * 308, lookup)}
+    have_ref = reference_available()
+    if have_ref:
+        from nndepth.models.raft_stereo.cost_volume import CorrBlock1D as RefCorr
+        strict_fp32()
+
+        def ref_gpu():
+            b = RefCorr(f1, f2, 4, 4)
+            for c in coords:
+                b(c)
+        with torch.no_grad():
+            us_ref = gpu_us(ref_gpu, reps=4)
+            rb = RefCorr(f1, f2, 4, 4)
+            us_ref_lookup = gpu_us(lambda: rb(coords[5]), reps=4)
+        line["gpu_baseline"] = {"what": "the reference's own CorrBlock1D (ATen chain) on torch.cuda, same inputs, fp32",
+                                "build_plus_32_lookups_us": us_ref, "lookup_us": us_ref_lookup,
+                                "speedup_whole": us_ref / total, "speedup_lookup": us_ref_lookup / lookup}
     if not skip_cpu:
         torch.set_num_threads(os.cpu_count() or 1)
+        cls = RefCorr if have_ref else torch_port.CorrBlock1D
 
         def cpu():
-            b = torch_port.CorrBlock1D(f1c, f2c, 4, 4)
+            b = cls(f1c, f2c, 4, 4)
             for c in coords_c:
                 b(c)
-        sec = cpu_seconds(cpu)
-        line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "passes/s", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": "the full config (1 build + 32 lookups), oracle/torch_port.py"}
+        with torch.no_grad():
+            sec = cpu_seconds(cpu, reps=1)
+        line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "passes/s", "cores": torch.get_num_threads(),
+                                "kind": "reference" if have_ref else "port",
+                                "sample": "the full config (1 build + 32 lookups), " +
+                                          ("the reference's CorrBlock1D as is (oracle/_ref)" if have_ref else "oracle/torch_port.py")}
     return line
 
 
@@ -138,7 +172,32 @@ def cfg3(skip_cpu):
     out["roofline"] = roof("agcl_cl_kernel<0> (offset mode, 90x160)", N * 90 * 160 * 2272, us)
     out["roofline"]["note"] = ("gather-bound, not HBM-bound: 36 KB of corner vectors are gathered per pixel (2.2 GB through "
                                "L1, 1.6 GB from L2) for 2.3 KB of compulsory traffic; DRAM moves only 123 MB (ncu)")
-    if not skip_cpu:
+    have_ref = reference_available()
+    if have_ref:
+        from nndepth.models.cre_stereo.cost_volume import AGCL as RefAGCL
+        strict_fp32()
+        H, W = 90, 160
+        torch.manual_seed(3)
+        f1, f2 = torch.randn(N, C, H, W, device="cuda"), torch.randn(N, C, H, W, device="cuda")
+        flow = torch.randn(N, 2, H, W, device="cuda") * 3
+        offs = torch.rand(N, 18, H, W, device="cuda") * 2 - 1
+        ra = RefAGCL(f1, f2)
+        with torch.no_grad():
+            ref_us = {"offset_1x9_90x160": gpu_us(lambda: ra(flow, offs, False, False), reps=3),
+                      "offset_3x3_90x160": gpu_us(lambda: ra(flow, offs, True, False), reps=3),
+                      "iter_1x9_90x160": gpu_us(lambda: ra(flow, None, False, True), reps=3),
+                      "iter_3x3_90x160": gpu_us(lambda: ra(flow, None, True, True), reps=3)}
+        out["gpu_baseline"] = {"what": "the reference's own AGCL (ATen chain) on torch.cuda, same inputs, fp32", "us": ref_us,
+                               "speedup": {k: v / out["gpu_us"][k] for k, v in ref_us.items()}}
+        if not skip_cpu:
+            torch.set_num_threads(os.cpu_count() or 1)
+            rc = RefAGCL(f1.cpu(), f2.cpu())
+            fc, oc = flow.cpu(), offs.cpu()
+            with torch.no_grad():
+                sec = cpu_seconds(lambda: rc(fc, oc, False, False), reps=1)
+            out["cpu_baseline"] = {"value": 1.0 / sec, "unit": "calls/s", "cores": torch.get_num_threads(), "kind": "reference",
+                                   "sample": "offset mode 1x9 at the full config (N4 C256 90x160), the reference's AGCL as is"}
+    elif not skip_cpu:
         rng = np.random.default_rng(3)
         H, W = 22, 40
         f1, f2 = rng.standard_normal((1, C, H, W), dtype=np.float32), rng.standard_normal((1, C, H, W), dtype=np.float32)
@@ -204,7 +263,37 @@ def cfg4(skip_cpu):
                                     fp32_gflop=2 * 216 * B * W * H * W / 1e9,
                                     ffma_tflops=2 * 216 * B * W * H * W / us["squeeze_soft_argmin_fused"] / 1e6,
                                     max_abs_diff_vs_torch_fp32_px=diff)]}
-    if not skip_cpu:
+    have_ref = reference_available()
+    if have_ref:
+        from nndepth.models.igev_stereo.cost_volume import GeometryAwareCostVolume as RefGEV
+        strict_fp32()
+        torch.manual_seed(0)
+        f1, f2 = torch.randn(B, C, H, W, device="cuda"), torch.randn(B, C, H, W, device="cuda")
+        with torch.no_grad():
+            rcv = RefGEV(f1, f2, [], lambda vol, feats: vol, 4, 4, G)
+            ref_lookup = gpu_us(lambda: rcv(coords), reps=3)
+            del rcv
+            torch.cuda.empty_cache()
+            z = torch.randn(B, W, H, W, device="cuda")
+            disp_values = torch.arange(W, device="cuda").float().view(1, -1, 1, 1)
+            ref_soft = gpu_us(lambda: -torch.sum(disp_values * torch.softmax(z, dim=1), dim=1, keepdim=True), reps=3)
+            del z
+        out["gpu_baseline"] = {"what": "the reference's own GeometryAwareCostVolume.forward / softmax + regress_disparity "
+                                       "(ATen chains) on torch.cuda, same shapes, fp32",
+                               "dual_lookup_us": ref_lookup, "soft_argmin_us": ref_soft,
+                               "speedup_lookup": ref_lookup / us["dual_lookup"], "speedup_soft_argmin": ref_soft / us["soft_argmin"]}
+        if not skip_cpu:
+            torch.set_num_threads(os.cpu_count() or 1)
+            bs = 4                                          # bounded sample: a quarter of the batch (the CPU build alone is ~10 s at 16)
+            with torch.no_grad():
+                rc = RefGEV(f1[:bs].cpu(), f2[:bs].cpu(), [], lambda vol, feats: vol, 4, 4, G)
+                cc = coords[:bs].cpu()
+                sec = cpu_seconds(lambda: rc(cc), reps=1)
+            out["cpu_baseline"] = {"value": 1.0 / (sec * B / bs), "unit": "lookups/s", "cores": torch.get_num_threads(),
+                                   "kind": "reference",
+                                   "sample": f"the reference's dual lookup on {bs} of the 16 pairs ({sec:.2f} s), scaled x{B // bs}"}
+        del f1, f2
+    elif not skip_cpu:
         rng = np.random.default_rng(0)
         b, h = 1, 8
         g1, g2 = rng.standard_normal((b, C, h, W), dtype=np.float32), rng.standard_normal((b, C, h, W), dtype=np.float32)
@@ -232,10 +321,34 @@ def cfg5(skip_cpu):
     band = nb.CorrBlock1D(b1, b2, 4, 4)
     us["lookup_band17"] = gpu_us(lambda: band(bc))
     nbytes = 2 * B * C * H * W * 4 + B * H * W * 450 * 4
-    return {"config": {"workload": "BASELINE configs[4]: RAFT-Stereo 1080x1920 pair, features 136x240, 8 row bands of 17 rows"},
+    line = {"config": {"workload": "BASELINE configs[4]: RAFT-Stereo 1080x1920 pair, features 136x240, 8 row bands of 17 rows"},
             "metric": "pyramid build", "unit": "builds/s", "value": 1e6 / us["build_full"], "dtype": "f32 (TF32 operands, RN)",
             "gpu_us": us, "roofline": roof("corr1d_build_tf32_kernel", nbytes, us["build_full"]),
+            "lookup_roofline": roof("corr1d_lookup_lean_kernel<9>", B * H * W * 308, us["lookup_full"]),
             "note": "a 17-row band is 17 row jobs on 148 SMs: the sharded run is launch-latency bound per GPU"}
+    if reference_available():
+        from nndepth.models.raft_stereo.cost_volume import CorrBlock1D as RefCorr
+        strict_fp32()
+        with torch.no_grad():
+            ref_build = gpu_us(lambda: RefCorr(f1, f2, 4, 4), reps=4)
+            rb = RefCorr(f1, f2, 4, 4)
+            ref_lookup = gpu_us(lambda: rb(coords), reps=4)
+        line["gpu_baseline"] = {"what": "the reference's own CorrBlock1D (ATen chain) on torch.cuda, same inputs, fp32",
+                                "build_us": ref_build, "lookup_us": ref_lookup,
+                                "speedup_build": ref_build / us["build_full"], "speedup_lookup": ref_lookup / us["lookup_full"]}
+        if not skip_cpu:
+            torch.set_num_threads(os.cpu_count() or 1)
+            c1, c2, cc = f1.cpu(), f2.cpu(), coords.cpu()
+
+            def cpu():
+                b = RefCorr(c1, c2, 4, 4)
+                for _ in range(4):
+                    b(cc)
+            with torch.no_grad():
+                sec = cpu_seconds(cpu, reps=1)
+            line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "passes/s", "cores": torch.get_num_threads(), "kind": "reference",
+                                    "sample": "1 build + 4 lookups of the full 136x240 map, the reference's CorrBlock1D as is"}
+    return line
 
 
 def cfg5_sharded():

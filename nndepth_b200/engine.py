@@ -55,6 +55,49 @@ def gather_disparities(local, world_size=None, group=None):
     return out
 
 
+class OverlappedGather:
+    """``gather_disparities`` off the critical path: the all-gather of step ``i`` runs on its own stream while step
+    ``i + 1`` computes.  ``submit(local)`` snapshots the rank's maps (the engine's graph output is overwritten by the next
+    replay) and enqueues the collective behind that copy; ``result()`` makes the current stream wait for the latest one."""
+
+    def __init__(self, world_size, group=None, device=None, depth=2):
+        self.world_size, self.group = int(world_size), group
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.depth, self._slots, self._next, self._last = depth, [], 0, None
+
+    def submit(self, local):
+        import torch.distributed as dist
+        if self.world_size == 1:
+            self._last = (local, None)
+            return
+        if not self._slots:
+            for _ in range(self.depth):
+                self._slots.append({"src": torch.empty_like(local),
+                                    "dst": torch.empty((self.world_size * local.shape[0],) + tuple(local.shape[1:]),
+                                                       dtype=local.dtype, device=local.device),
+                                    "copied": torch.cuda.Event(), "done": torch.cuda.Event(), "used": False})
+        slot = self._slots[self._next]
+        self._next = (self._next + 1) % self.depth
+        main = torch.cuda.current_stream(self.device)
+        if slot["used"]:
+            main.wait_event(slot["done"])          # the collective that last read this slot's snapshot has finished
+        slot["src"].copy_(local)
+        slot["copied"].record(main)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(slot["copied"])
+            dist.all_gather_into_tensor(slot["dst"], slot["src"], group=self.group)
+            slot["done"].record(self.stream)
+        slot["used"] = True
+        self._last = (slot["dst"], slot["done"])
+
+    def result(self):
+        out, done = self._last
+        if done is not None:
+            torch.cuda.current_stream(self.device).wait_event(done)
+        return out
+
+
 def row_band(tensor, rank, world_size):
     """Rows ``[h0, h1)`` of a ``(B, C, H, W)`` tensor owned by ``rank`` (contiguous copy) and the range.
 
