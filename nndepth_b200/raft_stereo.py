@@ -135,12 +135,37 @@ def conv_add_relu_split16(x16, params, stride, padding, dilation=(1, 1), groups=
     return torch.cudnn_convolution_add_relu(x16, w_hi, z, 1.0, b_hi, stride, padding, dilation, groups)
 
 
+def _dither16(t, k, K):
+    """fp16 rounding of ``t + ((k + 1/2) / K - 1/2) * ulp16(t)``: K roundings of the same fp32 tensor whose mean is within
+    ulp / (2K) of it.  Used for weights inside the refinement loop: iteration ``i`` takes variant ``i mod K``, so the
+    rounding error of a weight is no longer the same perturbation in all 32 iterations (which accumulates coherently,
+    see ``conv_add_relu_split16``) but changes sign from one iteration to the next -- at the cost of ONE product."""
+    t = t.detach().float().clamp(-65504.0, 65504.0)
+    ulp = torch.exp2(torch.floor(torch.log2(t.abs().clamp_min(2.0 ** -14))) - 10.0)
+    return (t + ((k + 0.5) / K - 0.5) * ulp).clamp(-65504.0, 65504.0).half()
+
+
+def half_dither_conv_params(conv, k, K, weight=None, bias=None, tag="_f16_dither"):
+    """Variant ``k`` of ``K`` of a convolution's (channels-last fp16 weight, fp16 bias), cached per parameter version."""
+    key = (conv.weight._version, None if conv.bias is None else conv.bias._version, conv.weight.device, K)
+    cache = getattr(conv, tag, None)
+    if cache is None or cache[0] != key:
+        w = conv.weight if weight is None else weight
+        b = conv.bias if bias is None else bias
+        cache = (key, [(_dither16(w, j, K).contiguous(memory_format=torch.channels_last),
+                        None if b is None else _dither16(b, j, K).contiguous()) for j in range(K)])
+        setattr(conv, tag, cache)
+    return cache[1][k % K]
+
+
 def conv_relu_f16(conv, x16):
-    """``relu(conv(x))`` as cuDNN's fused fp16 convolution (fp32 accumulation) on a channels-last fp16 ``x``; with
-    ``conv.exact16`` set (RAFTStereo.exact_weights) the weights enter as ``w_hi + w_lo`` (two products)."""
+    """``relu(conv(x))`` as cuDNN's fused fp16 convolution (fp32 accumulation) on a channels-last fp16 ``x``.  Weight
+    form (set by ``RAFTStereo._set_exact16``): ``conv.exact16`` -- two-term ``w_hi + w_lo`` (two products);
+    ``conv.dither16 = (k, K)`` -- variant ``k`` of ``K`` dithered roundings (one product); else plain fp16."""
     if getattr(conv, "exact16", False):
         return conv_add_relu_split16(x16, half_split_conv_params(conv), conv.stride, conv.padding, conv.dilation, conv.groups)
-    w, b = half_conv_params(conv)
+    dither = getattr(conv, "dither16", None)
+    w, b = half_dither_conv_params(conv, *dither) if dither else half_conv_params(conv)
     return torch.cudnn_convolution_relu(x16, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
 
 
@@ -636,7 +661,16 @@ class BasicMotionEncoder(nn.Module):
             if getattr(self.conv, "exact16", False):
                 return conv_add_relu_split16(nhwc_cat_f16(cor, flo), self._padded_conv_split16(), self.conv.stride,
                                              self.conv.padding, self.conv.dilation), flow
-            w, b = self._padded_conv(half=True)
+            dither = getattr(self.conv, "dither16", None)
+            if dither:
+                extra = self.convf1.weight.shape[1]
+                conv = self.conv
+                w, b = half_dither_conv_params(
+                    conv, *dither, tag="_f16_dither_padded",
+                    weight=torch.cat([conv.weight.detach(), conv.weight.new_zeros(extra, *conv.weight.shape[1:])], 0),
+                    bias=torch.cat([conv.bias.detach(), conv.bias.new_zeros(extra)], 0))
+            else:
+                w, b = self._padded_conv(half=True)
             return torch.cudnn_convolution_relu(nhwc_cat_f16(cor, flo), w, b, self.conv.stride, self.conv.padding,
                                                 self.conv.dilation, 1), flow
         flo = conv_relu(self.convf2, flow_conv7x7_relu(self.convf1, flow) if self.channels_last
@@ -796,6 +830,9 @@ class RAFTStereo(nn.Module):
         # exact_encoder: the same for the feature encoder (run once per forward).
         self.exact_weights = True
         self.exact_encoder = True
+        # dither_weights = K > 0 (instead of exact_weights): the loop's convolutions take ONE fp16 product with variant
+        # (iteration mod K) of K dithered roundings of their weights -- see _dither16
+        self.dither_weights = 0
         self._graphs = {}
         if weights is not None:
             state = torch.load(weights, map_location="cpu") if not str(weights).endswith(".safetensors") else None
@@ -841,7 +878,7 @@ class RAFTStereo(nn.Module):
             # mixed16 runs the (BatchNorm-folded) feature encoder as fp16 convolutions as well: the feature maps are
             # rounded to 10 mantissa bits for the correlation volume anyway (RN_tf32(RN_fp16(x)) == RN_fp16(x))
             self.fnet.half_convs = self.dense_precision == "mixed16" and getattr(self, "fp16_encoder", True)
-        self._set_exact16(self.dense_precision == "mixed16" and self.exact_weights,
+        self._set_exact16(self.dense_precision == "mixed16" and self.exact_weights and not self.dither_weights,
                           self.dense_precision == "mixed16" and self.exact_encoder)
         try:
             with cudnn_tf32(self.dense_precision != "fp32"):
@@ -853,15 +890,18 @@ class RAFTStereo(nn.Module):
             if has_half:
                 self.fnet.half_convs = saved[1]
 
+    def _loop_convs(self):
+        ub = self.update_block
+        enc, head = getattr(ub, "encoder", None), getattr(ub, "flow_head", None)
+        return [c for c in (getattr(enc, "convc2", None), getattr(enc, "convf2", None), getattr(enc, "conv", None),
+                            getattr(head, "conv1", None)) if c is not None]
+
     def _set_exact16(self, iteration, encoder):
         """Switch the two-term fp16 weights (``w_hi + w_lo``, see ``conv_add_relu_split16``) of the convolutions inside
         the refinement loop (motion encoder, flow head; the ConvGRU has its own split) and of the feature encoder."""
-        ub = self.update_block
-        enc, head = getattr(ub, "encoder", None), getattr(ub, "flow_head", None)
-        for conv in (getattr(enc, "convc2", None), getattr(enc, "convf2", None), getattr(enc, "conv", None),
-                     getattr(head, "conv1", None)):
-            if conv is not None:
-                conv.exact16 = bool(iteration)
+        for conv in self._loop_convs():
+            conv.exact16 = bool(iteration)
+            conv.dither16 = None
         for m in self.fnet.modules():
             if isinstance(m, (BasicEncoder, ResidualBlock)):
                 m.exact16 = bool(encoder)
@@ -883,8 +923,12 @@ class RAFTStereo(nn.Module):
         org_coords = self.initialize_coords(fmap1)
         coords1 = org_coords.clone()
         outputs = []
+        dither = self.dither_weights if (self.dense_precision == "mixed16" and not torch.is_grad_enabled()) else 0
         for it in range(self.iters):
             coords1 = coords1.detach()
+            if dither:
+                for conv in self._loop_convs():
+                    conv.dither16 = (it % dither, dither)
             fuse_front = (self.fuse_motion_front and coords1.is_cuda and not torch.is_grad_enabled()
                           and hasattr(corr, "lookup_conv1x1") and self.corr_levels == 4 and self.corr_radius == 4)
             if fuse_front:
@@ -937,7 +981,7 @@ class RAFTStereo(nn.Module):
         enc = getattr(self.update_block, "encoder", None)
         return (tuple(frame1.shape), tuple(frame1.stride()), frame1.device.index, frame1.dtype, self.iters, self.final_only,
                 self.dense_precision, stamp, self.corr_fn, _corr.get_volume_precision(), self.fuse_motion_front,
-                self.fuse_gru, getattr(self, "fp16_encoder", True), self.exact_weights, self.exact_encoder,
+                self.fuse_gru, getattr(self, "fp16_encoder", True), self.exact_weights, self.exact_encoder, self.dither_weights,
                 getattr(gru, "recurrence", None),
                 getattr(gru, "_fuse_zr", False), getattr(self.fnet, "half_convs", False),
                 getattr(enc, "channels_last", False), self.corr_levels, self.corr_radius,

@@ -63,7 +63,7 @@ def main():
             model.dense_precision = base
             for item in filter(None, overrides.split(",")):
                 k, v = item.split("=")
-                setattr(model, k, bool(int(v)))
+                setattr(model, k, int(v) if k == "dither_weights" else bool(int(v)))
             engine = StereoEngine(model, device="cuda", use_cuda_graph=True)
             for name, (l, r) in inputs.items():
                 l, r = l.cuda(), r.cuda()
