@@ -533,6 +533,143 @@ agcl_warp_cl_kernel(const float* __restrict__ R, const float* __restrict__ flow,
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Iter mode in ONE pass (cost_volume.py:54-79): the flow-warped right map is never written to HBM.  A block owns a
+// tile of TH x TW output pixels.  Phase 1 computes the warped map Rw[q] = bilinear(R, q + flow(q)) (zero padding,
+// utils.py:34-107, every step rounded like the reference's materialised intermediate) for the tile PLUS the halo its
+// nine replicate-clamped taps can reach -- +-4 columns for the 1x9 window, +-1 row / column for 3x3 -- into shared
+// memory: each warped pixel is produced once per tile (1.1x / 1.9x the tile's own pixels) instead of being gathered
+// nine times from L2.  Phase 2: warp = pixel, lane = C/32 consecutive channels (8 lanes per channel group); the left
+// vector comes straight from global memory (1 KB coalesced), each tap is a conflict-free read of the staged tile, an
+// 8-lane butterfly finishes the group dot.  Phase 3 writes the [36][TH*TW] result tile as coalesced NCHW row segments.
+// Compulsory traffic: each map once (2*C*4 B/px) + flow + output = 2 200 B/px at C = 256.
+// ------------------------------------------------------------------------------------------------
+template <bool SMALL>
+struct IterTile {
+  static constexpr int TH = SMALL ? 3 : 1;
+  static constexpr int TW = SMALL ? 16 : 80;
+  static constexpr int HX = SMALL ? 1 : 4;
+  static constexpr int HY = SMALL ? 1 : 0;
+  static constexpr int SW = TW + 2 * HX;
+  static constexpr int SH = TH + 2 * HY;
+  static constexpr int THREADS = 512;
+};
+
+template <bool SMALL, int V>   // V float4 per lane: C = 128 * V
+__global__ void __launch_bounds__(IterTile<SMALL>::THREADS)
+agcl_iter_fused_kernel(const float* __restrict__ L, const float* __restrict__ R, const float* __restrict__ flow, int H, int W,
+                       float* __restrict__ out) {
+  using T = IterTile<SMALL>;
+  constexpr int C = 128 * V;
+  constexpr int NW = T::THREADS / 32;
+  constexpr int NS = T::SH * T::SW;          // staged (warped) pixels
+  constexpr int NP = T::TH * T::TW;          // output pixels
+  extern __shared__ __align__(16) float ism[];
+  float* rw = ism;                                                        // [NS][C]
+  float* res = rw + NS * C;                                               // [36][NP + 1]
+  WarpFootprint* fp = reinterpret_cast<WarpFootprint*>(res + AGCL_GROUPS * AGCL_TAPS * (NP + 1));   // [NS]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = blockIdx.z;
+  const int x0 = blockIdx.x * T::TW, y0 = blockIdx.y * T::TH;
+  const long long hw = static_cast<long long>(H) * W;
+  const float* fl = flow + static_cast<long long>(n) * 2 * hw;
+
+  // phase 0: footprints of the staged pixels that lie inside the image
+  for (int s = tid; s < NS; s += T::THREADS) {
+    const int sy = s / T::SW, sx = s - sy * T::SW;
+    const int qx = x0 - T::HX + sx, qy = y0 - T::HY + sy;
+    WarpFootprint f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { f.off[q] = -1; f.wt[q] = 0.f; }
+    if (qx >= 0 && qx < W && qy >= 0 && qy < H) {
+      const int p = qy * W + qx;
+      const Footprint ff = make_footprint(__fadd_rn(static_cast<float>(qx), __ldg(fl + p)),
+                                          __fadd_rn(static_cast<float>(qy), __ldg(fl + hw + p)), H, W);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { f.off[q] = ff.off[q]; f.wt[q] = ff.wt[q]; }
+      if (f.off[0] < 0 && f.off[1] < 0 && f.off[2] < 0 && f.off[3] < 0) f.off[0] = -2;   // inside, but samples only padding
+    }
+    fp[s] = f;
+  }
+  __syncthreads();
+
+  // phase 1: warp per staged pixel, two pixels in flight (8 V independent 16-byte loads per lane)
+  const float* rb = R + static_cast<long long>(n) * hw * C + 4 * V * lane;
+  for (int s = warp; s < NS; s += NW) {
+    const WarpFootprint f = fp[s];
+    const bool inside = f.off[0] != -1 || f.off[1] >= 0 || f.off[2] >= 0 || f.off[3] >= 0;
+    if (!inside) continue;                                  // outside the image: never read (taps are clamped into it)
+    float4 v[4][V];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int j = 0; j < V; ++j)
+        v[q][j] = f.off[q] >= 0 ? ldg_f4(rb + static_cast<long long>(f.off[q]) * C + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      // Ia*wa + Ib*wb + Ic*wc + Id*wd, left to right, every step rounded (utils.py:107)
+      const float vx[4] = {v[0][j].x, v[1][j].x, v[2][j].x, v[3][j].x}, vy[4] = {v[0][j].y, v[1][j].y, v[2][j].y, v[3][j].y};
+      const float vz[4] = {v[0][j].z, v[1][j].z, v[2][j].z, v[3][j].z}, vw[4] = {v[0][j].w, v[1][j].w, v[2][j].w, v[3][j].w};
+      float4 r;
+      r.x = blend(vx, f.wt); r.y = blend(vy, f.wt); r.z = blend(vz, f.wt); r.w = blend(vw, f.wt);
+      *reinterpret_cast<float4*>(rw + s * C + 4 * V * lane + 4 * j) = r;
+    }
+  }
+  __syncthreads();
+
+  // phase 2: warp per output pixel
+  const float cnt = static_cast<float>(C / AGCL_GROUPS);
+  const int g = lane >> 3;
+  for (int i = warp; i < NP; i += NW) {
+    const int ty = i / T::TW, tx = i - ty * T::TW;
+    const int x = x0 + tx, y = y0 + ty;
+    if (x >= W || y >= H) continue;                          // warp-uniform
+    const float* lp = L + (static_cast<long long>(n) * hw + static_cast<long long>(y) * W + x) * C + 4 * V * lane;
+    float4 lv[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) lv[j] = ldg_f4(lp + 4 * j);
+#pragma unroll
+    for (int k = 0; k < AGCL_TAPS; ++k) {
+      const int dx = SMALL ? (k % 3 - 1) : (k - 4), dy = SMALL ? (k / 3 - 1) : 0;
+      // replicate padding of the warped map (cost_volume.py:40, utils.py:29-31): clamp the tap into the image
+      const int qx = min(max(x + dx, 0), W - 1), qy = min(max(y + dy, 0), H - 1);
+      const float* rp = rw + ((qy - (y0 - T::HY)) * T::SW + (qx - (x0 - T::HX))) * C + 4 * V * lane;
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc = dot4(lv[j], *reinterpret_cast<const float4*>(rp + 4 * j), acc);
+      acc = group_reduce8(acc);
+      if ((lane & 7) == 0) res[(g * AGCL_TAPS + k) * (NP + 1) + i] = __fdiv_rn(acc, cnt);   // torch.mean over C/4
+    }
+  }
+  __syncthreads();
+
+  // phase 3: NCHW output, channel = g*9 + k: TW-wide row segments
+  float* ob = out + static_cast<long long>(n) * AGCL_GROUPS * AGCL_TAPS * hw;
+  for (int idx = tid; idx < AGCL_GROUPS * AGCL_TAPS * NP; idx += T::THREADS) {
+    const int ch = idx / NP, i = idx - ch * NP;
+    const int ty = i / T::TW, tx = i - ty * T::TW;
+    const int x = x0 + tx, y = y0 + ty;
+    if (x < W && y < H) ob[ch * hw + static_cast<long long>(y) * W + x] = res[ch * (NP + 1) + i];
+  }
+}
+
+template <bool SMALL, int V>
+static nnd_status launch_iter_fused(const float* L, const float* R, const float* flow, int N, int H, int W, float* out,
+                                    cudaStream_t stream) {
+  using T = IterTile<SMALL>;
+  constexpr int C = 128 * V;
+  constexpr size_t smem = (static_cast<size_t>(T::SH * T::SW) * C + AGCL_GROUPS * AGCL_TAPS * (T::TH * T::TW + 1)) * sizeof(float) +
+                          static_cast<size_t>(T::SH * T::SW) * sizeof(WarpFootprint);
+  static_assert(smem <= 227 * 1024, "iter tile does not fit shared memory");
+  cudaError_t e = cudaFuncSetAttribute(agcl_iter_fused_kernel<SMALL, V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e != cudaSuccess) return cuda_fail(e, "agcl_iter_nhwc: shared-memory attribute");
+  dim3 grid((W + T::TW - 1) / T::TW, (H + T::TH - 1) / T::TH, N);
+  NND_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "agcl_iter_nhwc: grid too large");
+  agcl_iter_fused_kernel<SMALL, V><<<grid, T::THREADS, smem, stream>>>(L, R, flow, H, W, out);
+  return check_launch("agcl_iter_fused_kernel");
+}
+
 static nnd_status check_agcl(const float* f1, const float* f2, const float* flow, const float* out, int N, int C,
                              int H, int W, const char* who) {
   NND_REQUIRE(f1 && f2 && flow && out, "%s: null pointer argument", who);
@@ -640,6 +777,13 @@ nnd_status nnd_agcl_iter_nhwc(const float* fmap1_nhwc, const float* fmap2_nhwc, 
   NND_REQUIRE(warped_ws, "agcl_iter_nhwc: the N*H*W*C workspace for the warped right map is null");
   NND_REQUIRE(aligned16(fmap1_nhwc) && aligned16(fmap2_nhwc) && aligned16(warped_ws),
               "agcl_iter_nhwc: maps and workspace must be 16-byte aligned");
+  if (C == 256 || C == 128) {
+    // the model's configurations: one fused pass, the warped map lives in shared memory (the workspace stays unused)
+    if (small_patch) return C == 256 ? launch_iter_fused<true, 2>(fmap1_nhwc, fmap2_nhwc, flow, N, H, W, out, stream)
+                                     : launch_iter_fused<true, 1>(fmap1_nhwc, fmap2_nhwc, flow, N, H, W, out, stream);
+    return C == 256 ? launch_iter_fused<false, 2>(fmap1_nhwc, fmap2_nhwc, flow, N, H, W, out, stream)
+                    : launch_iter_fused<false, 1>(fmap1_nhwc, fmap2_nhwc, flow, N, H, W, out, stream);
+  }
   const long long n_pix = static_cast<long long>(N) * H * W;
   const long long wblocks = (n_pix + CL_WARPS - 1) / CL_WARPS;
   const long long blocks = (n_pix + CL_PIX - 1) / CL_PIX;
