@@ -574,7 +574,22 @@ agcl_iter_fused_kernel(const float* __restrict__ L, const float* __restrict__ R,
   const long long hw = static_cast<long long>(H) * W;
   const float* fl = flow + static_cast<long long>(n) * 2 * hw;
 
-  // phase 0: footprints of the staged pixels that lie inside the image
+  // the left vectors of this warp's output pixels do not depend on anything: put their loads in flight first
+  constexpr int PPW = (NP + NW - 1) / NW;    // output pixels per warp
+  float4 lv[PPW][V];
+#pragma unroll
+  for (int r = 0; r < PPW; ++r) {
+    const int i = warp + r * NW;
+    const int ty = i / T::TW, tx = i - ty * T::TW;
+    const int x = x0 + tx, y = y0 + ty;
+    const bool ok = i < NP && x < W && y < H;
+    const float* lp = L + (static_cast<long long>(n) * hw + static_cast<long long>(ok ? y : 0) * W + (ok ? x : 0)) * C + 4 * V * lane;
+#pragma unroll
+    for (int j = 0; j < V; ++j) lv[r][j] = ok ? ldg_f4(lp + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+
+  // phase 0: footprints of the staged pixels that lie inside the image.  An out-of-image corner contributes exactly
+  // zero (zero padding): it gets weight 0 and points at pixel 0, so the gather below is predicate-free.
   for (int s = tid; s < NS; s += T::THREADS) {
     const int sy = s / T::SW, sx = s - sy * T::SW;
     const int qx = x0 - T::HX + sx, qy = y0 - T::HY + sy;
@@ -586,48 +601,58 @@ agcl_iter_fused_kernel(const float* __restrict__ L, const float* __restrict__ R,
       const Footprint ff = make_footprint(__fadd_rn(static_cast<float>(qx), __ldg(fl + p)),
                                           __fadd_rn(static_cast<float>(qy), __ldg(fl + hw + p)), H, W);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { f.off[q] = ff.off[q]; f.wt[q] = ff.wt[q]; }
-      if (f.off[0] < 0 && f.off[1] < 0 && f.off[2] < 0 && f.off[3] < 0) f.off[0] = -2;   // inside, but samples only padding
+      for (int q = 0; q < 4; ++q) {
+        f.off[q] = ff.off[q] >= 0 ? ff.off[q] : 0;
+        f.wt[q] = ff.off[q] >= 0 ? ff.wt[q] : 0.f;
+      }
     }
     fp[s] = f;
   }
   __syncthreads();
 
-  // phase 1: warp per staged pixel, two pixels in flight (8 V independent 16-byte loads per lane)
+  // phase 1: warp per staged pixel, TWO pixels per round: 8 V independent 16-byte gathers per lane in flight
   const float* rb = R + static_cast<long long>(n) * hw * C + 4 * V * lane;
-  for (int s = warp; s < NS; s += NW) {
-    const WarpFootprint f = fp[s];
-    const bool inside = f.off[0] != -1 || f.off[1] >= 0 || f.off[2] >= 0 || f.off[3] >= 0;
-    if (!inside) continue;                                  // outside the image: never read (taps are clamped into it)
-    float4 v[4][V];
+  for (int s0 = warp; s0 < NS; s0 += 2 * NW) {
+    const int s1 = s0 + NW;
+    const WarpFootprint fa = fp[s0];
+    const WarpFootprint fb = fp[s1 < NS ? s1 : s0];
+    const bool in_a = fa.off[0] >= 0, in_b = s1 < NS && fb.off[0] >= 0;    // outside the image: never read (taps are clamped)
+    float4 va[4][V], vb[4][V];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
 #pragma unroll
-      for (int j = 0; j < V; ++j)
-        v[q][j] = f.off[q] >= 0 ? ldg_f4(rb + static_cast<long long>(f.off[q]) * C + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < V; ++j) {
+        va[q][j] = in_a ? ldg_f4(rb + static_cast<long long>(fa.off[q]) * C + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        vb[q][j] = in_b ? ldg_f4(rb + static_cast<long long>(fb.off[q]) * C + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       // Ia*wa + Ib*wb + Ic*wc + Id*wd, left to right, every step rounded (utils.py:107)
-      const float vx[4] = {v[0][j].x, v[1][j].x, v[2][j].x, v[3][j].x}, vy[4] = {v[0][j].y, v[1][j].y, v[2][j].y, v[3][j].y};
-      const float vz[4] = {v[0][j].z, v[1][j].z, v[2][j].z, v[3][j].z}, vw[4] = {v[0][j].w, v[1][j].w, v[2][j].w, v[3][j].w};
-      float4 r;
-      r.x = blend(vx, f.wt); r.y = blend(vy, f.wt); r.z = blend(vz, f.wt); r.w = blend(vw, f.wt);
-      *reinterpret_cast<float4*>(rw + s * C + 4 * V * lane + 4 * j) = r;
+      if (in_a) {
+        const float vx[4] = {va[0][j].x, va[1][j].x, va[2][j].x, va[3][j].x}, vy[4] = {va[0][j].y, va[1][j].y, va[2][j].y, va[3][j].y};
+        const float vz[4] = {va[0][j].z, va[1][j].z, va[2][j].z, va[3][j].z}, vw[4] = {va[0][j].w, va[1][j].w, va[2][j].w, va[3][j].w};
+        *reinterpret_cast<float4*>(rw + s0 * C + 4 * V * lane + 4 * j) =
+            make_float4(blend(vx, fa.wt), blend(vy, fa.wt), blend(vz, fa.wt), blend(vw, fa.wt));
+      }
+      if (in_b) {
+        const float vx[4] = {vb[0][j].x, vb[1][j].x, vb[2][j].x, vb[3][j].x}, vy[4] = {vb[0][j].y, vb[1][j].y, vb[2][j].y, vb[3][j].y};
+        const float vz[4] = {vb[0][j].z, vb[1][j].z, vb[2][j].z, vb[3][j].z}, vw[4] = {vb[0][j].w, vb[1][j].w, vb[2][j].w, vb[3][j].w};
+        *reinterpret_cast<float4*>(rw + s1 * C + 4 * V * lane + 4 * j) =
+            make_float4(blend(vx, fb.wt), blend(vy, fb.wt), blend(vz, fb.wt), blend(vw, fb.wt));
+      }
     }
   }
   __syncthreads();
 
-  // phase 2: warp per output pixel
+  // phase 2: warp per output pixel, taps from the staged tile
   const float cnt = static_cast<float>(C / AGCL_GROUPS);
   const int g = lane >> 3;
-  for (int i = warp; i < NP; i += NW) {
+#pragma unroll
+  for (int r = 0; r < PPW; ++r) {
+    const int i = warp + r * NW;
     const int ty = i / T::TW, tx = i - ty * T::TW;
     const int x = x0 + tx, y = y0 + ty;
-    if (x >= W || y >= H) continue;                          // warp-uniform
-    const float* lp = L + (static_cast<long long>(n) * hw + static_cast<long long>(y) * W + x) * C + 4 * V * lane;
-    float4 lv[V];
-#pragma unroll
-    for (int j = 0; j < V; ++j) lv[j] = ldg_f4(lp + 4 * j);
+    if (i >= NP || x >= W || y >= H) continue;               // warp-uniform
 #pragma unroll
     for (int k = 0; k < AGCL_TAPS; ++k) {
       const int dx = SMALL ? (k % 3 - 1) : (k - 4), dy = SMALL ? (k / 3 - 1) : 0;
@@ -636,7 +661,7 @@ agcl_iter_fused_kernel(const float* __restrict__ L, const float* __restrict__ R,
       const float* rp = rw + ((qy - (y0 - T::HY)) * T::SW + (qx - (x0 - T::HX))) * C + 4 * V * lane;
       float acc = 0.f;
 #pragma unroll
-      for (int j = 0; j < V; ++j) acc = dot4(lv[j], *reinterpret_cast<const float4*>(rp + 4 * j), acc);
+      for (int j = 0; j < V; ++j) acc = dot4(lv[r][j], *reinterpret_cast<const float4*>(rp + 4 * j), acc);
       acc = group_reduce8(acc);
       if ((lane & 7) == 0) res[(g * AGCL_TAPS + k) * (NP + 1) + i] = __fdiv_rn(acc, cnt);   // torch.mean over C/4
     }
