@@ -556,7 +556,7 @@ struct IterTile {
 };
 
 template <bool SMALL, int V>   // V float4 per lane: C = 128 * V
-__global__ void __launch_bounds__(IterTile<SMALL>::THREADS)
+__global__ void __launch_bounds__(IterTile<SMALL>::THREADS, 2)
 agcl_iter_fused_kernel(const float* __restrict__ L, const float* __restrict__ R, const float* __restrict__ flow, int H, int W,
                        float* __restrict__ out) {
   using T = IterTile<SMALL>;
@@ -574,20 +574,6 @@ agcl_iter_fused_kernel(const float* __restrict__ L, const float* __restrict__ R,
   const long long hw = static_cast<long long>(H) * W;
   const float* fl = flow + static_cast<long long>(n) * 2 * hw;
 
-  // the left vectors of this warp's output pixels do not depend on anything: put their loads in flight first
-  constexpr int PPW = (NP + NW - 1) / NW;    // output pixels per warp
-  float4 lv[PPW][V];
-#pragma unroll
-  for (int r = 0; r < PPW; ++r) {
-    const int i = warp + r * NW;
-    const int ty = i / T::TW, tx = i - ty * T::TW;
-    const int x = x0 + tx, y = y0 + ty;
-    const bool ok = i < NP && x < W && y < H;
-    const float* lp = L + (static_cast<long long>(n) * hw + static_cast<long long>(ok ? y : 0) * W + (ok ? x : 0)) * C + 4 * V * lane;
-#pragma unroll
-    for (int j = 0; j < V; ++j) lv[r][j] = ok ? ldg_f4(lp + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-
   // phase 0: footprints of the staged pixels that lie inside the image.  An out-of-image corner contributes exactly
   // zero (zero padding): it gets weight 0 and points at pixel 0, so the gather below is predicate-free.
   for (int s = tid; s < NS; s += T::THREADS) {
@@ -602,7 +588,7 @@ agcl_iter_fused_kernel(const float* __restrict__ L, const float* __restrict__ R,
                                           __fadd_rn(static_cast<float>(qy), __ldg(fl + hw + p)), H, W);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        f.off[q] = ff.off[q] >= 0 ? ff.off[q] : 0;
+        f.off[q] = ff.off[q] >= 0 ? ff.off[q] * C : 0;       // float offset inside the image (H*W*C < 2^31)
         f.wt[q] = ff.off[q] >= 0 ? ff.wt[q] : 0.f;
       }
     }
@@ -610,61 +596,71 @@ agcl_iter_fused_kernel(const float* __restrict__ L, const float* __restrict__ R,
   }
   __syncthreads();
 
-  // phase 1: warp per staged pixel, TWO pixels per round: 8 V independent 16-byte gathers per lane in flight
+  // phase 1: warp per staged pixel: 4 V independent 16-byte gathers per lane, blended in the reference's order
   const float* rb = R + static_cast<long long>(n) * hw * C + 4 * V * lane;
-  for (int s0 = warp; s0 < NS; s0 += 2 * NW) {
-    const int s1 = s0 + NW;
-    const WarpFootprint fa = fp[s0];
-    const WarpFootprint fb = fp[s1 < NS ? s1 : s0];
-    const bool in_a = fa.off[0] >= 0, in_b = s1 < NS && fb.off[0] >= 0;    // outside the image: never read (taps are clamped)
-    float4 va[4][V], vb[4][V];
+  for (int s = warp; s < NS; s += NW) {
+    const WarpFootprint f = fp[s];
+    if (f.off[0] < 0) continue;                               // outside the image: never read (taps are clamped into it)
+    float4 v[4][V];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
 #pragma unroll
-      for (int j = 0; j < V; ++j) {
-        va[q][j] = in_a ? ldg_f4(rb + static_cast<long long>(fa.off[q]) * C + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-        vb[q][j] = in_b ? ldg_f4(rb + static_cast<long long>(fb.off[q]) * C + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      for (int j = 0; j < V; ++j) v[q][j] = ldg_f4(rb + f.off[q] + 4 * j);
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       // Ia*wa + Ib*wb + Ic*wc + Id*wd, left to right, every step rounded (utils.py:107)
-      if (in_a) {
-        const float vx[4] = {va[0][j].x, va[1][j].x, va[2][j].x, va[3][j].x}, vy[4] = {va[0][j].y, va[1][j].y, va[2][j].y, va[3][j].y};
-        const float vz[4] = {va[0][j].z, va[1][j].z, va[2][j].z, va[3][j].z}, vw[4] = {va[0][j].w, va[1][j].w, va[2][j].w, va[3][j].w};
-        *reinterpret_cast<float4*>(rw + s0 * C + 4 * V * lane + 4 * j) =
-            make_float4(blend(vx, fa.wt), blend(vy, fa.wt), blend(vz, fa.wt), blend(vw, fa.wt));
-      }
-      if (in_b) {
-        const float vx[4] = {vb[0][j].x, vb[1][j].x, vb[2][j].x, vb[3][j].x}, vy[4] = {vb[0][j].y, vb[1][j].y, vb[2][j].y, vb[3][j].y};
-        const float vz[4] = {vb[0][j].z, vb[1][j].z, vb[2][j].z, vb[3][j].z}, vw[4] = {vb[0][j].w, vb[1][j].w, vb[2][j].w, vb[3][j].w};
-        *reinterpret_cast<float4*>(rw + s1 * C + 4 * V * lane + 4 * j) =
-            make_float4(blend(vx, fb.wt), blend(vy, fb.wt), blend(vz, fb.wt), blend(vw, fb.wt));
-      }
+      const float vx[4] = {v[0][j].x, v[1][j].x, v[2][j].x, v[3][j].x}, vy[4] = {v[0][j].y, v[1][j].y, v[2][j].y, v[3][j].y};
+      const float vz[4] = {v[0][j].z, v[1][j].z, v[2][j].z, v[3][j].z}, vw[4] = {v[0][j].w, v[1][j].w, v[2][j].w, v[3][j].w};
+      *reinterpret_cast<float4*>(rw + s * C + 4 * V * lane + 4 * j) =
+          make_float4(blend(vx, f.wt), blend(vy, f.wt), blend(vz, f.wt), blend(vw, f.wt));
     }
   }
   __syncthreads();
 
-  // phase 2: warp per output pixel, taps from the staged tile
-  const float cnt = static_cast<float>(C / AGCL_GROUPS);
+  // phase 2: warp per output pixel, taps from the staged tile.  Every lane accumulates its C/32 channels for all nine
+  // taps; the 8 lanes of a channel group then reduce taps 0..7 with a transposing butterfly (7 exchanges: lane l ends up
+  // owning tap l & 7) and tap 8 with a plain one.  torch.mean over C/4 = 64 or 32 channels: an exact scaling.
+  const float inv_cnt = 1.0f / static_cast<float>(C / AGCL_GROUPS);
   const int g = lane >> 3;
-#pragma unroll
-  for (int r = 0; r < PPW; ++r) {
-    const int i = warp + r * NW;
+  constexpr unsigned FULL = 0xffffffffu;
+  for (int i = warp; i < NP; i += NW) {
     const int ty = i / T::TW, tx = i - ty * T::TW;
     const int x = x0 + tx, y = y0 + ty;
-    if (i >= NP || x >= W || y >= H) continue;               // warp-uniform
+    if (x >= W || y >= H) continue;                          // warp-uniform
+    const float* lp = L + (static_cast<long long>(n) * hw + y * W + x) * C + 4 * V * lane;
+    float4 lv[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) lv[j] = ldg_f4(lp + 4 * j);
+    float acc[AGCL_TAPS];
 #pragma unroll
     for (int k = 0; k < AGCL_TAPS; ++k) {
       const int dx = SMALL ? (k % 3 - 1) : (k - 4), dy = SMALL ? (k / 3 - 1) : 0;
       // replicate padding of the warped map (cost_volume.py:40, utils.py:29-31): clamp the tap into the image
       const int qx = min(max(x + dx, 0), W - 1), qy = min(max(y + dy, 0), H - 1);
       const float* rp = rw + ((qy - (y0 - T::HY)) * T::SW + (qx - (x0 - T::HX))) * C + 4 * V * lane;
-      float acc = 0.f;
+      float a = 0.f;
 #pragma unroll
-      for (int j = 0; j < V; ++j) acc = dot4(lv[r][j], *reinterpret_cast<const float4*>(rp + 4 * j), acc);
-      acc = group_reduce8(acc);
-      if ((lane & 7) == 0) res[(g * AGCL_TAPS + k) * (NP + 1) + i] = __fdiv_rn(acc, cnt);   // torch.mean over C/4
+      for (int j = 0; j < V; ++j) a = dot4(lv[j], *reinterpret_cast<const float4*>(rp + 4 * j), a);
+      acc[k] = a;
     }
+    float b4[4], c2[2];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const bool hi = lane & 1;
+      const float send = hi ? acc[2 * t] : acc[2 * t + 1], keep = hi ? acc[2 * t + 1] : acc[2 * t];
+      b4[t] = keep + __shfl_xor_sync(FULL, send, 1);
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const bool hi = lane & 2;
+      const float send = hi ? b4[2 * t] : b4[2 * t + 1], keep = hi ? b4[2 * t + 1] : b4[2 * t];
+      c2[t] = keep + __shfl_xor_sync(FULL, send, 2);
+    }
+    const bool hi4 = lane & 4;
+    const float mine = (hi4 ? c2[1] : c2[0]) + __shfl_xor_sync(FULL, hi4 ? c2[0] : c2[1], 4);   // tap lane & 7
+    const float last = group_reduce8(acc[8]);
+    res[(g * AGCL_TAPS + (lane & 7)) * (NP + 1) + i] = mine * inv_cnt;
+    if ((lane & 7) == 0) res[(g * AGCL_TAPS + 8) * (NP + 1) + i] = last * inv_cnt;
   }
   __syncthreads();
 
