@@ -544,19 +544,45 @@ agcl_warp_cl_kernel(const float* __restrict__ R, const float* __restrict__ flow,
 // 8-lane butterfly finishes the group dot.  Phase 3 writes the [36][TH*TW] result tile as coalesced NCHW row segments.
 // Compulsory traffic: each map once (2*C*4 B/px) + flow + output = 2 200 B/px at C = 256.
 // ------------------------------------------------------------------------------------------------
+// Sum N values over the N consecutive lanes of a group with N - 1 exchanges instead of N * log2(N): at the step with
+// distance m every lane passes on the half of its values its partner is responsible for.  Afterwards v[0] of lane l is
+// the group's sum of value (l & (N - 1)).
+template <int N>
+__device__ __forceinline__ float transpose_reduce(float (&v)[N], int lane) {
+#pragma unroll
+  for (int m = 1, cnt = N / 2; cnt >= 1; m <<= 1, cnt >>= 1) {
+    const bool hi = lane & m;
+#pragma unroll
+    for (int t = 0; t < cnt; ++t) {
+      const float send = hi ? v[2 * t] : v[2 * t + 1], keep = hi ? v[2 * t + 1] : v[2 * t];
+      v[t] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+    }
+  }
+  return v[0];
+}
+
 template <bool SMALL>
 struct IterTile {
   static constexpr int TH = SMALL ? 3 : 1;
-  static constexpr int TW = SMALL ? 16 : 80;
+#ifndef NND_AGCL_TW
+#define NND_AGCL_TW 80
+#endif
+#ifndef NND_AGCL_THREADS
+#define NND_AGCL_THREADS 512
+#endif
+#ifndef NND_AGCL_MINB
+#define NND_AGCL_MINB 2
+#endif
+  static constexpr int TW = SMALL ? 16 : NND_AGCL_TW;
   static constexpr int HX = SMALL ? 1 : 4;
   static constexpr int HY = SMALL ? 1 : 0;
   static constexpr int SW = TW + 2 * HX;
   static constexpr int SH = TH + 2 * HY;
-  static constexpr int THREADS = 512;
+  static constexpr int THREADS = NND_AGCL_THREADS;
 };
 
 template <bool SMALL, int V>   // V float4 per lane: C = 128 * V
-__global__ void __launch_bounds__(IterTile<SMALL>::THREADS, 2)
+__global__ void __launch_bounds__(IterTile<SMALL>::THREADS, NND_AGCL_MINB)
 agcl_iter_fused_kernel(const float* __restrict__ L, const float* __restrict__ R, const float* __restrict__ flow, int H, int W,
                        float* __restrict__ out) {
   using T = IterTile<SMALL>;
@@ -597,7 +623,8 @@ agcl_iter_fused_kernel(const float* __restrict__ L, const float* __restrict__ R,
   __syncthreads();
 
   // phase 1: warp per staged pixel: 4 V independent 16-byte gathers per lane, blended in the reference's order
-  const float* rb = R + static_cast<long long>(n) * hw * C + 4 * V * lane;
+  // lane -> float4 number lane + 32 j of a pixel's channel vector: every warp instruction moves 512 contiguous bytes
+  const float* rb = R + static_cast<long long>(n) * hw * C + 4 * lane;
   for (int s = warp; s < NS; s += NW) {
     const WarpFootprint f = fp[s];
     if (f.off[0] < 0) continue;                               // outside the image: never read (taps are clamped into it)
@@ -605,62 +632,65 @@ agcl_iter_fused_kernel(const float* __restrict__ L, const float* __restrict__ R,
 #pragma unroll
     for (int q = 0; q < 4; ++q)
 #pragma unroll
-      for (int j = 0; j < V; ++j) v[q][j] = ldg_f4(rb + f.off[q] + 4 * j);
+      for (int j = 0; j < V; ++j) v[q][j] = ldg_f4(rb + f.off[q] + 128 * j);
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       // Ia*wa + Ib*wb + Ic*wc + Id*wd, left to right, every step rounded (utils.py:107)
       const float vx[4] = {v[0][j].x, v[1][j].x, v[2][j].x, v[3][j].x}, vy[4] = {v[0][j].y, v[1][j].y, v[2][j].y, v[3][j].y};
       const float vz[4] = {v[0][j].z, v[1][j].z, v[2][j].z, v[3][j].z}, vw[4] = {v[0][j].w, v[1][j].w, v[2][j].w, v[3][j].w};
-      *reinterpret_cast<float4*>(rw + s * C + 4 * V * lane + 4 * j) =
+      *reinterpret_cast<float4*>(rw + s * C + 4 * lane + 128 * j) =
           make_float4(blend(vx, f.wt), blend(vy, f.wt), blend(vz, f.wt), blend(vw, f.wt));
     }
   }
   __syncthreads();
 
-  // phase 2: warp per output pixel, taps from the staged tile.  Every lane accumulates its C/32 channels for all nine
-  // taps; the 8 lanes of a channel group then reduce taps 0..7 with a transposing butterfly (7 exchanges: lane l ends up
-  // owning tap l & 7) and tap 8 with a plain one.  torch.mean over C/4 = 64 or 32 channels: an exact scaling.
+  // phase 2: warp per output pixel, taps from the staged tile.  Float4 number lane + 32 j belongs to channel group
+  // (lane >> 4) + 2 j at C = 256 (16 lanes per group and j) and to group lane >> 3 at C = 128; every lane accumulates
+  // its channels for all nine taps, then the lanes of a group reduce taps 0..7 with the transposing butterfly and tap 8
+  // with a plain one.  torch.mean over C/4 = 64 or 32 channels is an exact scaling.
   const float inv_cnt = 1.0f / static_cast<float>(C / AGCL_GROUPS);
-  const int g = lane >> 3;
   constexpr unsigned FULL = 0xffffffffu;
   for (int i = warp; i < NP; i += NW) {
     const int ty = i / T::TW, tx = i - ty * T::TW;
     const int x = x0 + tx, y = y0 + ty;
     if (x >= W || y >= H) continue;                          // warp-uniform
-    const float* lp = L + (static_cast<long long>(n) * hw + y * W + x) * C + 4 * V * lane;
+    const float* lp = L + (static_cast<long long>(n) * hw + y * W + x) * C + 4 * lane;
     float4 lv[V];
 #pragma unroll
-    for (int j = 0; j < V; ++j) lv[j] = ldg_f4(lp + 4 * j);
-    float acc[AGCL_TAPS];
+    for (int j = 0; j < V; ++j) lv[j] = ldg_f4(lp + 128 * j);
+    float acc[V][AGCL_TAPS];
 #pragma unroll
     for (int k = 0; k < AGCL_TAPS; ++k) {
       const int dx = SMALL ? (k % 3 - 1) : (k - 4), dy = SMALL ? (k / 3 - 1) : 0;
       // replicate padding of the warped map (cost_volume.py:40, utils.py:29-31): clamp the tap into the image
       const int qx = min(max(x + dx, 0), W - 1), qy = min(max(y + dy, 0), H - 1);
-      const float* rp = rw + ((qy - (y0 - T::HY)) * T::SW + (qx - (x0 - T::HX))) * C + 4 * V * lane;
-      float a = 0.f;
+      const float* rp = rw + ((qy - (y0 - T::HY)) * T::SW + (qx - (x0 - T::HX))) * C + 4 * lane;
 #pragma unroll
-      for (int j = 0; j < V; ++j) a = dot4(lv[j], *reinterpret_cast<const float4*>(rp + 4 * j), a);
-      acc[k] = a;
+      for (int j = 0; j < V; ++j) acc[j][k] = dot4(lv[j], *reinterpret_cast<const float4*>(rp + 128 * j), 0.f);
     }
-    float b4[4], c2[2];
+    if (V == 2) {
+      float v16[16];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const bool hi = lane & 1;
-      const float send = hi ? acc[2 * t] : acc[2 * t + 1], keep = hi ? acc[2 * t + 1] : acc[2 * t];
-      b4[t] = keep + __shfl_xor_sync(FULL, send, 1);
-    }
+      for (int k = 0; k < 8; ++k) { v16[k] = acc[0][k]; v16[8 + k] = acc[V - 1][k]; }
+      const float mine = transpose_reduce<16>(v16, lane);                 // value (lane & 15): j = bit 3, tap = low 3 bits
+      const int j = (lane >> 3) & 1, k = lane & 7, grp = (lane >> 4) + 2 * j;
+      res[(grp * AGCL_TAPS + k) * (NP + 1) + i] = mine * inv_cnt;
+      // tap 8: lane bit 0 picks j, then a plain reduction over the other three lane bits
+      const bool odd = lane & 1;
+      float last = (odd ? acc[V - 1][8] : acc[0][8]) + __shfl_xor_sync(FULL, odd ? acc[0][8] : acc[V - 1][8], 1);
+      last += __shfl_xor_sync(FULL, last, 2);
+      last += __shfl_xor_sync(FULL, last, 4);
+      last += __shfl_xor_sync(FULL, last, 8);
+      if ((lane & 14) == 0) res[(((lane >> 4) + 2 * (lane & 1)) * AGCL_TAPS + 8) * (NP + 1) + i] = last * inv_cnt;
+    } else {
+      float v8[8];
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      const bool hi = lane & 2;
-      const float send = hi ? b4[2 * t] : b4[2 * t + 1], keep = hi ? b4[2 * t + 1] : b4[2 * t];
-      c2[t] = keep + __shfl_xor_sync(FULL, send, 2);
+      for (int k = 0; k < 8; ++k) v8[k] = acc[0][k];
+      const float mine = transpose_reduce<8>(v8, lane);                   // tap lane & 7 of group lane >> 3
+      const float last = group_reduce8(acc[0][8]);
+      res[((lane >> 3) * AGCL_TAPS + (lane & 7)) * (NP + 1) + i] = mine * inv_cnt;
+      if ((lane & 7) == 0) res[((lane >> 3) * AGCL_TAPS + 8) * (NP + 1) + i] = last * inv_cnt;
     }
-    const bool hi4 = lane & 4;
-    const float mine = (hi4 ? c2[1] : c2[0]) + __shfl_xor_sync(FULL, hi4 ? c2[0] : c2[1], 4);   // tap lane & 7
-    const float last = group_reduce8(acc[8]);
-    res[(g * AGCL_TAPS + (lane & 7)) * (NP + 1) + i] = mine * inv_cnt;
-    if ((lane & 7) == 0) res[(g * AGCL_TAPS + 8) * (NP + 1) + i] = last * inv_cnt;
   }
   __syncthreads();
 
