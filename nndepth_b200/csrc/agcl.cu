@@ -642,6 +642,18 @@ agcl_iter_fused_kernel(const float* __restrict__ L, const float* __restrict__ R,
           make_float4(blend(vx, f.wt), blend(vy, f.wt), blend(vz, f.wt), blend(vw, f.wt));
     }
   }
+  // the left vector of this warp's first output pixel is put in flight before the barrier, every later one while its
+  // predecessor is being correlated: their DRAM latency never sits between two pixels
+  auto load_left = [&](int i, float4 (&dst)[V]) {
+    const int ty = i / T::TW, tx = i - ty * T::TW;
+    const int x = x0 + tx, y = y0 + ty;
+    const bool ok = i < NP && x < W && y < H;
+    const float* lp = L + (static_cast<long long>(n) * hw + (ok ? y * W + x : 0)) * C + 4 * lane;
+#pragma unroll
+    for (int j = 0; j < V; ++j) dst[j] = ok ? ldg_f4(lp + 128 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  float4 lv[V], lnext[V];
+  load_left(warp, lnext);
   __syncthreads();
 
   // phase 2: warp per output pixel, taps from the staged tile.  Float4 number lane + 32 j belongs to channel group
@@ -653,11 +665,10 @@ agcl_iter_fused_kernel(const float* __restrict__ L, const float* __restrict__ R,
   for (int i = warp; i < NP; i += NW) {
     const int ty = i / T::TW, tx = i - ty * T::TW;
     const int x = x0 + tx, y = y0 + ty;
-    if (x >= W || y >= H) continue;                          // warp-uniform
-    const float* lp = L + (static_cast<long long>(n) * hw + y * W + x) * C + 4 * lane;
-    float4 lv[V];
 #pragma unroll
-    for (int j = 0; j < V; ++j) lv[j] = ldg_f4(lp + 128 * j);
+    for (int j = 0; j < V; ++j) lv[j] = lnext[j];
+    load_left(i + NW, lnext);
+    if (x >= W || y >= H) continue;                          // warp-uniform
     float acc[V][AGCL_TAPS];
 #pragma unroll
     for (int k = 0; k < AGCL_TAPS; ++k) {
