@@ -130,8 +130,11 @@ def conv_add_relu_split16(x16, params, stride, padding, dilation=(1, 1), groups=
     fp16 convolution (its output is ~2**-11 of the result, so its own fp16 rounding is ~2**-22), the main product is
     cuDNN's fused convolution + add + bias + ReLU reading it.  A rounded WEIGHT perturbs every GRU iteration the same
     way (the error accumulates coherently over 32 iterations); rounded ACTIVATIONS are fresh noise each iteration."""
-    w_hi, w_lo, b_hi, b_lo = params
-    z = F.conv2d(x16, w_lo, b_lo, stride, padding, dilation, groups)
+    w_hi, w_lo, b_hi, _ = params
+    # no bias on the remainder product: PyTorch would add it with a separate elementwise kernel, and the fp16 rounding
+    # of the BIAS (one value per channel, ~2**-11 of a number ~1/sqrt(fan_in)) is two orders of magnitude below the
+    # accumulated weight rounding this split removes
+    z = F.conv2d(x16, w_lo, None, stride, padding, dilation, groups)
     return torch.cudnn_convolution_add_relu(x16, w_hi, z, 1.0, b_hi, stride, padding, dilation, groups)
 
 
@@ -338,7 +341,7 @@ class ResidualBlock(nn.Module):
                 p1, p2, p3 = self._folded_split16()
                 y = conv_add_relu_split16(x, p1, c1.stride, c1.padding, c1.dilation)
                 y = conv_add_relu_split16(y, p2, self.conv2.stride, self.conv2.padding, self.conv2.dilation)
-                y = y + F.conv2d(x, p3[1], p3[3], c3.stride, c3.padding, c3.dilation)
+                y = y + F.conv2d(x, p3[1], None, c3.stride, c3.padding, c3.dilation)
                 return torch.cudnn_convolution_add_relu(x, p3[0], y, 1.0, p3[2], c3.stride, c3.padding, c3.dilation, 1)
             (w1, b1), (w2, b2), (w3, b3) = self._folded(half=x.dtype == torch.float16)
             y = torch.cudnn_convolution_relu(x, w1, b1, c1.stride, c1.padding, c1.dilation, 1)
@@ -410,7 +413,7 @@ class BasicEncoder(nn.Module):
         x = self.layer3(self.layer2(self.layer1(x)))
         if x.dtype == torch.float16 and getattr(self, "exact16", False):
             w_hi, w_lo, b_hi, b_lo = half_split_conv_params(self.conv2)
-            x = F.conv2d(x, w_hi, b_hi, self.conv2.stride, self.conv2.padding) + F.conv2d(x, w_lo, b_lo, self.conv2.stride, self.conv2.padding)
+            x = F.conv2d(x, w_hi, b_hi, self.conv2.stride, self.conv2.padding) + F.conv2d(x, w_lo, None, self.conv2.stride, self.conv2.padding)
         elif x.dtype == torch.float16:
             w16, b16 = half_conv_params(self.conv2)
             x = F.conv2d(x, w16, b16, self.conv2.stride, self.conv2.padding)
