@@ -715,233 +715,6 @@ agcl_iter_fused_kernel(const float* __restrict__ L, const float* __restrict__ R,
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// The same computation as a persistent, software-pipelined kernel: one block per SM walks over the tiles; warps
-// 0..STG-1 ("stagers") run phases 0-1 of tile k+1 (footprints, gather + blend of the warped tile into shared-memory
-// buffer (k+1) & 1) while warps STG.. ("correlators") run phases 2-3 of tile k out of buffer k & 1.  full / empty
-// mbarriers hand the two buffers back and forth, named barriers synchronise each role internally, so the gather
-// latency of one tile hides behind the arithmetic of the previous one instead of adding to it.
-// ------------------------------------------------------------------------------------------------
-namespace pipe {
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  long long t0 = 0;
-  int spins = 0;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (!done && ++spins == 1024) {  // watchdog: a protocol bug must fault, not hang the GPU
-      spins = 0;
-      const long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 2000000000LL) __trap();
-    }
-  } while (!done);
-}
-constexpr int THREADS = 1024;
-constexpr int STG_WARPS = 12;                    // stagers
-constexpr int COR_WARPS = THREADS / 32 - STG_WARPS;   // correlators
-}  // namespace pipe
-
-template <bool SMALL, int V>   // V float4 per lane: C = 128 * V
-__global__ void __launch_bounds__(pipe::THREADS, 1)
-agcl_iter_pipe_kernel(const float* __restrict__ L, const float* __restrict__ R, const float* __restrict__ flow, int H, int W,
-                      int tiles_x, int tiles_y, int total_tiles, float* __restrict__ out) {
-  using T = IterTile<SMALL>;
-  using namespace pipe;
-  constexpr int C = 128 * V;
-  constexpr int NS = T::SH * T::SW;          // staged (warped) pixels
-  constexpr int NP = T::TH * T::TW;          // output pixels
-  constexpr int RES = AGCL_GROUPS * AGCL_TAPS * (NP + 1);
-  extern __shared__ __align__(16) float ism[];
-  float* rw0 = ism;                                                       // [2][NS][C]
-  float* res0 = rw0 + 2 * NS * C;                                         // [2][36][NP + 1]
-  WarpFootprint* fp0 = reinterpret_cast<WarpFootprint*>(res0 + 2 * RES);  // [2][NS]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(fp0 + 2 * NS);             // full[2], empty[2]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long hw = static_cast<long long>(H) * W;
-  const uint32_t bar0 = smem_u32(bars);
-  if (tid == 0) {
-    mbar_init(bar0, STG_WARPS);
-    mbar_init(bar0 + 8, STG_WARPS);
-    mbar_init(bar0 + 16, COR_WARPS);
-    mbar_init(bar0 + 24, COR_WARPS);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  auto decode = [&](int t, int& n, int& x0, int& y0) {
-    const int per_img = tiles_x * tiles_y;
-    n = t / per_img;
-    const int r = t - n * per_img;
-    const int ty = r / tiles_x;
-    y0 = ty * T::TH;
-    x0 = (r - ty * tiles_x) * T::TW;
-  };
-
-  if (warp < STG_WARPS) {
-    // ===================================== stagers: phases 0 and 1 =====================================
-    int k = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++k) {
-      const int b = k & 1;
-      int n, x0, y0;
-      decode(t, n, x0, y0);
-      float* rw = rw0 + b * NS * C;
-      WarpFootprint* fp = fp0 + b * NS;
-      const float* fl = flow + static_cast<long long>(n) * 2 * hw;
-      // phase 0 (no shared data of the correlators is touched: it may run before the buffer is released)
-      for (int s = tid; s < NS; s += 32 * STG_WARPS) {
-        const int sy = s / T::SW, sx = s - sy * T::SW;
-        const int qx = x0 - T::HX + sx, qy = y0 - T::HY + sy;
-        WarpFootprint f;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { f.off[q] = -1; f.wt[q] = 0.f; }
-        if (qx >= 0 && qx < W && qy >= 0 && qy < H) {
-          const int p = qy * W + qx;
-          const Footprint ff = make_footprint(__fadd_rn(static_cast<float>(qx), __ldg(fl + p)),
-                                              __fadd_rn(static_cast<float>(qy), __ldg(fl + hw + p)), H, W);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            f.off[q] = ff.off[q] >= 0 ? ff.off[q] * C : 0;   // zero padding: weight 0, any valid address
-            f.wt[q] = ff.off[q] >= 0 ? ff.wt[q] : 0.f;
-          }
-        }
-        fp[s] = f;
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * STG_WARPS) : "memory");
-      mbar_wait(bar0 + 16 + 8 * b, ((k >> 1) & 1) ^ 1);       // the correlators have finished with this buffer
-      // phase 1
-      const float* rb = R + static_cast<long long>(n) * hw * C + 4 * lane;
-      for (int s = warp; s < NS; s += STG_WARPS) {
-        const WarpFootprint f = fp[s];
-        if (f.off[0] < 0) continue;                           // outside the image: never read (taps are clamped into it)
-        float4 v[4][V];
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-          for (int j = 0; j < V; ++j) v[q][j] = ldg_f4(rb + f.off[q] + 128 * j);
-#pragma unroll
-        for (int j = 0; j < V; ++j) {
-          // Ia*wa + Ib*wb + Ic*wc + Id*wd, left to right, every step rounded (utils.py:107)
-          const float vx[4] = {v[0][j].x, v[1][j].x, v[2][j].x, v[3][j].x}, vy[4] = {v[0][j].y, v[1][j].y, v[2][j].y, v[3][j].y};
-          const float vz[4] = {v[0][j].z, v[1][j].z, v[2][j].z, v[3][j].z}, vw[4] = {v[0][j].w, v[1][j].w, v[2][j].w, v[3][j].w};
-          *reinterpret_cast<float4*>(rw + s * C + 4 * lane + 128 * j) =
-              make_float4(blend(vx, f.wt), blend(vy, f.wt), blend(vz, f.wt), blend(vw, f.wt));
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar0 + 8 * b);              // full[b]
-    }
-  } else {
-    // ===================================== correlators: phases 2 and 3 =====================================
-    const int cw = warp - STG_WARPS, ctid = tid - 32 * STG_WARPS;
-    const float inv_cnt = 1.0f / static_cast<float>(C / AGCL_GROUPS);
-    constexpr unsigned FULL = 0xffffffffu;
-    int k = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++k) {
-      const int b = k & 1;
-      int n, x0, y0;
-      decode(t, n, x0, y0);
-      const float* rw = rw0 + b * NS * C;
-      float* res = res0 + b * RES;
-      auto load_left = [&](int i, float4 (&dst)[V]) {
-        const int ty = i / T::TW, tx = i - ty * T::TW;
-        const int x = x0 + tx, y = y0 + ty;
-        const bool ok = i < NP && x < W && y < H;
-        const float* lp = L + (static_cast<long long>(n) * hw + (ok ? y * W + x : 0)) * C + 4 * lane;
-#pragma unroll
-        for (int j = 0; j < V; ++j) dst[j] = ok ? ldg_f4(lp + 128 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-      };
-      float4 lv[V], lnext[V];
-      load_left(cw, lnext);
-      mbar_wait(bar0 + 8 * b, (k >> 1) & 1);                  // the staged tile is complete
-      for (int i = cw; i < NP; i += COR_WARPS) {
-        const int ty = i / T::TW, tx = i - ty * T::TW;
-        const int x = x0 + tx, y = y0 + ty;
-#pragma unroll
-        for (int j = 0; j < V; ++j) lv[j] = lnext[j];
-        load_left(i + COR_WARPS, lnext);
-        if (x >= W || y >= H) continue;                        // warp-uniform
-        float acc[V][AGCL_TAPS];
-#pragma unroll
-        for (int kk = 0; kk < AGCL_TAPS; ++kk) {
-          const int dx = SMALL ? (kk % 3 - 1) : (kk - 4), dy = SMALL ? (kk / 3 - 1) : 0;
-          // replicate padding of the warped map (cost_volume.py:40, utils.py:29-31): clamp the tap into the image
-          const int qx = min(max(x + dx, 0), W - 1), qy = min(max(y + dy, 0), H - 1);
-          const float* rp = rw + ((qy - (y0 - T::HY)) * T::SW + (qx - (x0 - T::HX))) * C + 4 * lane;
-#pragma unroll
-          for (int j = 0; j < V; ++j) acc[j][kk] = dot4(lv[j], *reinterpret_cast<const float4*>(rp + 128 * j), 0.f);
-        }
-        if (V == 2) {
-          float v16[16];
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk) { v16[kk] = acc[0][kk]; v16[8 + kk] = acc[V - 1][kk]; }
-          const float mine = transpose_reduce<16>(v16, lane);               // value (lane & 15): j = bit 3, tap = low 3 bits
-          const int j = (lane >> 3) & 1, kk = lane & 7, grp = (lane >> 4) + 2 * j;
-          res[(grp * AGCL_TAPS + kk) * (NP + 1) + i] = mine * inv_cnt;
-          const bool odd = lane & 1;
-          float last = (odd ? acc[V - 1][8] : acc[0][8]) + __shfl_xor_sync(FULL, odd ? acc[0][8] : acc[V - 1][8], 1);
-          last += __shfl_xor_sync(FULL, last, 2);
-          last += __shfl_xor_sync(FULL, last, 4);
-          last += __shfl_xor_sync(FULL, last, 8);
-          if ((lane & 14) == 0) res[(((lane >> 4) + 2 * (lane & 1)) * AGCL_TAPS + 8) * (NP + 1) + i] = last * inv_cnt;
-        } else {
-          float v8[8];
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk) v8[kk] = acc[0][kk];
-          const float mine = transpose_reduce<8>(v8, lane);                 // tap lane & 7 of group lane >> 3
-          const float last = group_reduce8(acc[0][8]);
-          res[((lane >> 3) * AGCL_TAPS + (lane & 7)) * (NP + 1) + i] = mine * inv_cnt;
-          if ((lane & 7) == 0) res[((lane >> 3) * AGCL_TAPS + 8) * (NP + 1) + i] = last * inv_cnt;
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar0 + 16 + 8 * b);          // empty[b]: my reads of the staged tile are done
-      asm volatile("bar.sync 2, %0;" ::"n"(32 * COR_WARPS) : "memory");
-      // phase 3: NCHW output, channel = g*9 + k: TW-wide row segments
-      float* ob = out + static_cast<long long>(n) * AGCL_GROUPS * AGCL_TAPS * hw;
-      for (int idx = ctid; idx < AGCL_GROUPS * AGCL_TAPS * NP; idx += 32 * COR_WARPS) {
-        const int ch = idx / NP, i = idx - ch * NP;
-        const int ty = i / T::TW, tx = i - ty * T::TW;
-        const int x = x0 + tx, y = y0 + ty;
-        if (x < W && y < H) ob[ch * hw + static_cast<long long>(y) * W + x] = res[ch * (NP + 1) + i];
-      }
-    }
-  }
-}
-
-template <bool SMALL, int V>
-static nnd_status launch_iter_pipe(const float* L, const float* R, const float* flow, int N, int H, int W, float* out,
-                                   cudaStream_t stream) {
-  using T = IterTile<SMALL>;
-  constexpr int C = 128 * V;
-  constexpr int NS = T::SH * T::SW, NP = T::TH * T::TW;
-  constexpr size_t smem = (static_cast<size_t>(2) * NS * C + 2 * AGCL_GROUPS * AGCL_TAPS * (NP + 1)) * sizeof(float) +
-                          static_cast<size_t>(2) * NS * sizeof(WarpFootprint) + 64;
-  static_assert(smem <= 227 * 1024, "pipelined iter tiles do not fit shared memory");
-  cudaError_t e = cudaFuncSetAttribute(agcl_iter_pipe_kernel<SMALL, V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem));
-  if (e != cudaSuccess) return cuda_fail(e, "agcl_iter_nhwc: shared-memory attribute");
-  const int tiles_x = (W + T::TW - 1) / T::TW, tiles_y = (H + T::TH - 1) / T::TH;
-  const long long total = static_cast<long long>(N) * tiles_x * tiles_y;
-  NND_REQUIRE(total < (1LL << 31), "agcl_iter_nhwc: too many tiles");
-  const long long sms = sm_count();
-  agcl_iter_pipe_kernel<SMALL, V><<<static_cast<unsigned>(total < sms ? total : sms), pipe::THREADS, smem, stream>>>(
-      L, R, flow, H, W, tiles_x, tiles_y, static_cast<int>(total), out);
-  return check_launch("agcl_iter_pipe_kernel");
-}
-
 template <bool SMALL, int V>
 static nnd_status launch_iter_fused(const float* L, const float* R, const float* flow, int N, int H, int W, float* out,
                                     cudaStream_t stream) {
@@ -1068,17 +841,10 @@ nnd_status nnd_agcl_iter_nhwc(const float* fmap1_nhwc, const float* fmap2_nhwc, 
               "agcl_iter_nhwc: maps and workspace must be 16-byte aligned");
   if (C == 256 || C == 128) {
     // the model's configurations: one fused pass, the warped map lives in shared memory (the workspace stays unused)
-#ifdef NND_AGCL_NO_PIPE
     if (small_patch) return C == 256 ? launch_iter_fused<true, 2>(fmap1_nhwc, fmap2_nhwc, flow, N, H, W, out, stream)
                                      : launch_iter_fused<true, 1>(fmap1_nhwc, fmap2_nhwc, flow, N, H, W, out, stream);
     return C == 256 ? launch_iter_fused<false, 2>(fmap1_nhwc, fmap2_nhwc, flow, N, H, W, out, stream)
                     : launch_iter_fused<false, 1>(fmap1_nhwc, fmap2_nhwc, flow, N, H, W, out, stream);
-#else
-    if (small_patch) return C == 256 ? launch_iter_pipe<true, 2>(fmap1_nhwc, fmap2_nhwc, flow, N, H, W, out, stream)
-                                     : launch_iter_pipe<true, 1>(fmap1_nhwc, fmap2_nhwc, flow, N, H, W, out, stream);
-    return C == 256 ? launch_iter_pipe<false, 2>(fmap1_nhwc, fmap2_nhwc, flow, N, H, W, out, stream)
-                    : launch_iter_pipe<false, 1>(fmap1_nhwc, fmap2_nhwc, flow, N, H, W, out, stream);
-#endif
   }
   const long long n_pix = static_cast<long long>(N) * H * W;
   const long long wblocks = (n_pix + CL_WARPS - 1) / CL_WARPS;
