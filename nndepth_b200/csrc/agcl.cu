@@ -590,14 +590,9 @@ agcl_iter_fused_kernel(const float* __restrict__ L, const float* __restrict__ R,
   constexpr int NW = T::THREADS / 32;
   constexpr int NS = T::SH * T::SW;          // staged (warped) pixels
   constexpr int NP = T::TH * T::TW;          // output pixels
-  // staged pixel row: float4 number f of the channel vector sits at float4 position (f % FPL) * 17 + f / FPL, FPL = C / 64:
-  // phase 2 gives every pixel HALF a warp, lane l16 owning the FPL consecutive float4 FPL*l16 .. (= 4 lanes per channel
-  // group), and reads segment j of all 16 lanes as 256 contiguous bytes; the 17 keeps phase 1's stores conflict-free
-  constexpr int FPL = C / 64;
-  constexpr int ROWF = FPL * 17 * 4;         // floats per staged pixel row
   extern __shared__ __align__(16) float ism[];
-  float* rw = ism;                                                        // [NS][ROWF]
-  float* res = rw + NS * ROWF;                                            // [36][NP + 1]
+  float* rw = ism;                                                        // [NS][C]
+  float* res = rw + NS * C;                                               // [36][NP + 1]
   WarpFootprint* fp = reinterpret_cast<WarpFootprint*>(res + AGCL_GROUPS * AGCL_TAPS * (NP + 1));   // [NS]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = blockIdx.z;
@@ -643,87 +638,69 @@ agcl_iter_fused_kernel(const float* __restrict__ L, const float* __restrict__ R,
       // Ia*wa + Ib*wb + Ic*wc + Id*wd, left to right, every step rounded (utils.py:107)
       const float vx[4] = {v[0][j].x, v[1][j].x, v[2][j].x, v[3][j].x}, vy[4] = {v[0][j].y, v[1][j].y, v[2][j].y, v[3][j].y};
       const float vz[4] = {v[0][j].z, v[1][j].z, v[2][j].z, v[3][j].z}, vw[4] = {v[0][j].w, v[1][j].w, v[2][j].w, v[3][j].w};
-      const int fnum = lane + 32 * j;
-      *reinterpret_cast<float4*>(rw + s * ROWF + ((fnum % FPL) * 17 + fnum / FPL) * 4) =
+      *reinterpret_cast<float4*>(rw + s * C + 4 * lane + 128 * j) =
           make_float4(blend(vx, f.wt), blend(vy, f.wt), blend(vz, f.wt), blend(vw, f.wt));
     }
   }
-  // phase 2: HALF a warp per output pixel (two pixels per warp instruction stream).  Lane l16 owns float4 FPL*l16 ..
-  // FPL*l16 + FPL - 1 of the channel vector, i.e. 4 lanes per channel group; per tap it accumulates its channels with
-  // packed FMAs, then the 4 lanes reduce taps 0..7 with a two-step transposing butterfly (6 exchanges; lane q ends up
-  // owning taps q and 4 + q) and tap 8 with a plain one.  The left vectors are software-pipelined: the first pair is in
-  // flight before the barrier, every later one while its predecessor is being correlated.  torch.mean over C/4 = 64 or
-  // 32 channels is an exact scaling.
-  const int hf = lane >> 4, l16 = lane & 15;
-  constexpr int PAIRS = (NP + 1) / 2;
-  auto load_left = [&](int pr, float4 (&dst)[FPL]) {
-    const int i = 2 * pr + hf;
+  // the left vector of this warp's first output pixel is put in flight before the barrier, every later one while its
+  // predecessor is being correlated: their DRAM latency never sits between two pixels
+  auto load_left = [&](int i, float4 (&dst)[V]) {
     const int ty = i / T::TW, tx = i - ty * T::TW;
     const int x = x0 + tx, y = y0 + ty;
-    const bool ok = pr < PAIRS && i < NP && x < W && y < H;
-    const float* lp = L + (static_cast<long long>(n) * hw + (ok ? y * W + x : 0)) * C + 4 * FPL * l16;
+    const bool ok = i < NP && x < W && y < H;
+    const float* lp = L + (static_cast<long long>(n) * hw + (ok ? y * W + x : 0)) * C + 4 * lane;
 #pragma unroll
-    for (int j = 0; j < FPL; ++j) dst[j] = ok ? ldg_f4(lp + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < V; ++j) dst[j] = ok ? ldg_f4(lp + 128 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
   };
-  float4 lv[FPL], lnext[FPL];
+  float4 lv[V], lnext[V];
   load_left(warp, lnext);
   __syncthreads();
 
+  // phase 2: warp per output pixel, taps from the staged tile.  Float4 number lane + 32 j belongs to channel group
+  // (lane >> 4) + 2 j at C = 256 (16 lanes per group and j) and to group lane >> 3 at C = 128; every lane accumulates
+  // its channels for all nine taps, then the lanes of a group reduce taps 0..7 with the transposing butterfly and tap 8
+  // with a plain one.  torch.mean over C/4 = 64 or 32 channels is an exact scaling.
   const float inv_cnt = 1.0f / static_cast<float>(C / AGCL_GROUPS);
   constexpr unsigned FULL = 0xffffffffu;
-  for (int pr = warp; pr < PAIRS; pr += NW) {
-    const int i = 2 * pr + hf;
+  for (int i = warp; i < NP; i += NW) {
     const int ty = i / T::TW, tx = i - ty * T::TW;
     const int x = x0 + tx, y = y0 + ty;
-    const bool live = i < NP && x < W && y < H;
 #pragma unroll
-    for (int j = 0; j < FPL; ++j) lv[j] = lnext[j];
-    load_left(pr + NW, lnext);
-    // taps whose window stays inside the image need no clamping: constant offsets from one base pointer
-    const bool interior = live && (SMALL ? (x >= 1 && x + 1 < W && y >= 1 && y + 1 < H) : (x >= 4 && x + 4 < W));
-    float acc[AGCL_TAPS];
-    if (__all_sync(FULL, interior)) {
-      const float* base = rw + ((ty + T::HY) * T::SW + (tx + T::HX)) * ROWF + 4 * l16;
+    for (int j = 0; j < V; ++j) lv[j] = lnext[j];
+    load_left(i + NW, lnext);
+    if (x >= W || y >= H) continue;                          // warp-uniform
+    float acc[V][AGCL_TAPS];
 #pragma unroll
-      for (int k = 0; k < AGCL_TAPS; ++k) {
-        const int dx = SMALL ? (k % 3 - 1) : (k - 4), dy = SMALL ? (k / 3 - 1) : 0;
-        const float* rp = base + (dy * T::SW + dx) * ROWF;
-        float2 a2 = make_float2(0.f, 0.f);
+    for (int k = 0; k < AGCL_TAPS; ++k) {
+      const int dx = SMALL ? (k % 3 - 1) : (k - 4), dy = SMALL ? (k / 3 - 1) : 0;
+      // replicate padding of the warped map (cost_volume.py:40, utils.py:29-31): clamp the tap into the image
+      const int qx = min(max(x + dx, 0), W - 1), qy = min(max(y + dy, 0), H - 1);
+      const float* rp = rw + ((qy - (y0 - T::HY)) * T::SW + (qx - (x0 - T::HX))) * C + 4 * lane;
 #pragma unroll
-        for (int j = 0; j < FPL; ++j) {
-          const float4 r = *reinterpret_cast<const float4*>(rp + 68 * j);
-          ffma2(a2, make_float2(lv[j].x, lv[j].y), make_float2(r.x, r.y));
-          ffma2(a2, make_float2(lv[j].z, lv[j].w), make_float2(r.z, r.w));
-        }
-        acc[k] = a2.x + a2.y;
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < AGCL_TAPS; ++k) {
-        const int dx = SMALL ? (k % 3 - 1) : (k - 4), dy = SMALL ? (k / 3 - 1) : 0;
-        // replicate padding of the warped map (cost_volume.py:40, utils.py:29-31): clamp the tap into the image
-        const int qx = live ? min(max(x + dx, 0), W - 1) : x0, qy = live ? min(max(y + dy, 0), H - 1) : y0;
-        const float* rp = rw + ((qy - (y0 - T::HY)) * T::SW + (qx - (x0 - T::HX))) * ROWF + 4 * l16;
-        float a = 0.f;
-#pragma unroll
-        for (int j = 0; j < FPL; ++j) a = dot4(lv[j], *reinterpret_cast<const float4*>(rp + 68 * j), a);
-        acc[k] = a;
-      }
+      for (int j = 0; j < V; ++j) acc[j][k] = dot4(lv[j], *reinterpret_cast<const float4*>(rp + 128 * j), 0.f);
     }
-    // 8 values over the 4 lanes of a channel group: exchange at distance 1, then 2
-    float b4[4], c2[2];
-    const bool o1 = lane & 1, o2 = lane & 2;
+    if (V == 2) {
+      float v16[16];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) b4[t] = (o1 ? acc[2 * t + 1] : acc[2 * t]) + __shfl_xor_sync(FULL, o1 ? acc[2 * t] : acc[2 * t + 1], 1);
+      for (int k = 0; k < 8; ++k) { v16[k] = acc[0][k]; v16[8 + k] = acc[V - 1][k]; }
+      const float mine = transpose_reduce<16>(v16, lane);                 // value (lane & 15): j = bit 3, tap = low 3 bits
+      const int j = (lane >> 3) & 1, k = lane & 7, grp = (lane >> 4) + 2 * j;
+      res[(grp * AGCL_TAPS + k) * (NP + 1) + i] = mine * inv_cnt;
+      // tap 8: lane bit 0 picks j, then a plain reduction over the other three lane bits
+      const bool odd = lane & 1;
+      float last = (odd ? acc[V - 1][8] : acc[0][8]) + __shfl_xor_sync(FULL, odd ? acc[0][8] : acc[V - 1][8], 1);
+      last += __shfl_xor_sync(FULL, last, 2);
+      last += __shfl_xor_sync(FULL, last, 4);
+      last += __shfl_xor_sync(FULL, last, 8);
+      if ((lane & 14) == 0) res[(((lane >> 4) + 2 * (lane & 1)) * AGCL_TAPS + 8) * (NP + 1) + i] = last * inv_cnt;
+    } else {
+      float v8[8];
 #pragma unroll
-    for (int t = 0; t < 2; ++t) c2[t] = (o2 ? b4[2 * t + 1] : b4[2 * t]) + __shfl_xor_sync(FULL, o2 ? b4[2 * t] : b4[2 * t + 1], 2);
-    float last = acc[8] + __shfl_xor_sync(FULL, acc[8], 1);
-    last += __shfl_xor_sync(FULL, last, 2);
-    if (live) {
-      const int g = l16 >> 2, q = lane & 3;
-      res[(g * AGCL_TAPS + q) * (NP + 1) + i] = c2[0] * inv_cnt;          // tap q
-      res[(g * AGCL_TAPS + 4 + q) * (NP + 1) + i] = c2[1] * inv_cnt;      // tap 4 + q
-      if (q == 0) res[(g * AGCL_TAPS + 8) * (NP + 1) + i] = last * inv_cnt;
+      for (int k = 0; k < 8; ++k) v8[k] = acc[0][k];
+      const float mine = transpose_reduce<8>(v8, lane);                   // tap lane & 7 of group lane >> 3
+      const float last = group_reduce8(acc[0][8]);
+      res[((lane >> 3) * AGCL_TAPS + (lane & 7)) * (NP + 1) + i] = mine * inv_cnt;
+      if ((lane & 7) == 0) res[((lane >> 3) * AGCL_TAPS + 8) * (NP + 1) + i] = last * inv_cnt;
     }
   }
   __syncthreads();
@@ -743,8 +720,8 @@ static nnd_status launch_iter_fused(const float* L, const float* R, const float*
                                     cudaStream_t stream) {
   using T = IterTile<SMALL>;
   constexpr int C = 128 * V;
-  constexpr size_t smem = (static_cast<size_t>(T::SH * T::SW) * (C / 64 * 17 * 4) + AGCL_GROUPS * AGCL_TAPS * (T::TH * T::TW + 1)) *
-                              sizeof(float) + static_cast<size_t>(T::SH * T::SW) * sizeof(WarpFootprint);
+  constexpr size_t smem = (static_cast<size_t>(T::SH * T::SW) * C + AGCL_GROUPS * AGCL_TAPS * (T::TH * T::TW + 1)) * sizeof(float) +
+                          static_cast<size_t>(T::SH * T::SW) * sizeof(WarpFootprint);
   static_assert(smem <= 227 * 1024, "iter tile does not fit shared memory");
   cudaError_t e = cudaFuncSetAttribute(agcl_iter_fused_kernel<SMALL, V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem));
