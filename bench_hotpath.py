@@ -426,10 +426,34 @@ def cfg5_sharded():
         full = forward_graphed()
     e1.record()
     torch.cuda.synchronize(device)
-    ms = torch.tensor([e0.elapsed_time(e1) / steps, eager_ms], device=device, dtype=torch.float64)
+    graph_ms = e0.elapsed_time(e1) / steps
+
+    # SURVEY 8(e), second option: the update block runs REPLICATED on every rank, so each iteration's band lookup
+    # (1, 36, h, 240) is all-gathered right away (32 collectives per forward, 0.6 MB each) instead of one gather at the end
+    def forward_gather_every_iteration():
+        blk = nb.CorrBlock1D(b1, b2, 4, 4)
+        out = None
+        for c in bc:
+            out = blk(c)
+            out = gather_row_bands(out, H, world) if world > 1 else out
+        return out
+
+    for _ in range(2):
+        every = forward_gather_every_iteration()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        every = forward_gather_every_iteration()
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms = torch.tensor([graph_ms, eager_ms, e0.elapsed_time(e1) / steps], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    eager_ms = ms[1].item()
+    eager_ms, every_ms = ms[1].item(), ms[2].item()
+    same_every = bool(torch.equal(every, full))
     ms = ms[:1]
     ok = True
     if rank == 0:
@@ -441,6 +465,7 @@ def cfg5_sharded():
                                        f"row-band-sharded x{world} (bands of {h1 - h0} rows on rank 0), build + 32 lookups + 1 gather"},
                 "metric": "pyramid build + 32 lookups of one 1080x1920 pair", "unit": "pairs/s", "value": 1e3 / ms.item(),
                 "ms_per_step": ms.item(), "ms_per_step_eager": eager_ms, "cuda_graph": True,
+                "ms_per_step_gather_every_iteration": every_ms, "gather_every_iteration_equals_final_gather": same_every,
                 "dtype": "f32 (TF32 operands, RN)", "gathered_equals_unsharded": ok,
                 "note": "the band's build + 32 lookups are replayed as one CUDA graph (eager, the 33 launches of 0.3-2 MB each "
                         "are host-launch bound: ms_per_step_eager); the all-gather of the last lookup follows on the stream"}
