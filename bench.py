@@ -569,6 +569,16 @@ def run_ours(args):
             strong = {"global_pairs": PAIRS_PER_GPU, "pairs_per_gpu": per_rank, "unit": UNIT,
                       "value": PAIRS_PER_GPU * args.steps / (strong_ms / 1e3), "ms_per_step": strong_ms / args.steps}
 
+    # BASELINE configs[4] as it is meant to run: ONE 1080x1920 pair, its epipolar rows split into row bands across the
+    # ranks (no halo, no data-path collective; build + 32 lookups per band as one CUDA graph, one all-gather)
+    row_band = None
+    if not args.skip_hotpath:
+        import bench_hotpath as hp
+        try:
+            row_band = hp.cfg5_sharded(standalone=False)
+        except BaseException as e:      # a failed side leg must not lose the headline line
+            row_band = {"error": f"{type(e).__name__}: {e}"[:300]} if rank == 0 else None
+
     line = None
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -684,6 +694,7 @@ def run_ours(args):
             "other_kernels": time_step_kernels(device, peak),
             "cuda_graph": engine.use_cuda_graph,
             "strong": strong,
+            "row_band": row_band,
         }
         if value_fp32 is not None:
             line["value_fp32"] = value_fp32

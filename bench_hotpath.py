@@ -351,7 +351,7 @@ def cfg5(skip_cpu):
     return line
 
 
-def cfg5_sharded():
+def cfg5_sharded(standalone=True):
     """BASELINE configs[4] as it is meant to run: ONE 1080x1920 pair, its 136 epipolar feature rows split into
     row bands across the ranks of a torchrun job (one process per GPU).  Every rank builds the pyramid of its
     band and runs the 32 lookups on it -- no halo, no collective in the data path -- and one NCCL all-gather per
@@ -364,7 +364,7 @@ def cfg5_sharded():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
-    if world > 1:
+    if world > 1 and standalone:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
     B, C, H, W = 1, 256, 136, 240
@@ -455,7 +455,7 @@ def cfg5_sharded():
     eager_ms, every_ms = ms[1].item(), ms[2].item()
     same_every = bool(torch.equal(every, full))
     ms = ms[:1]
-    ok = True
+    ok, line = True, None
     if rank == 0:
         # the gathered lookup equals the unsharded one bit for bit (rows are independent)
         whole = nb.CorrBlock1D(f1.to(device), f2.to(device), 4, 4)(coords[-1].to(device))
@@ -468,13 +468,16 @@ def cfg5_sharded():
                 "ms_per_step_gather_every_iteration": every_ms, "gather_every_iteration_equals_final_gather": same_every,
                 "dtype": "f32 (TF32 operands, RN)", "gathered_equals_unsharded": ok,
                 "note": "the band's build + 32 lookups are replayed as one CUDA graph (eager, the 33 launches of 0.3-2 MB each "
-                        "are host-launch bound: ms_per_step_eager); the all-gather of the last lookup follows on the stream"}
-        print(json.dumps(line), flush=True)
-    if world > 1:
+                        "are host-launch bound: ms_per_step_eager); the all-gather of the last lookup follows on the stream; "
+                        "gather_every_iteration = SURVEY 8(e)'s replicated-GRU variant (32 collectives per forward)"}
+        if standalone:
+            print(json.dumps(line), flush=True)
+    if world > 1 and standalone:
         dist.barrier()
         dist.destroy_process_group()
     if not ok:
         raise SystemExit("row-band gather differs from the unsharded lookup")
+    return line
 
 
 def main():
