@@ -172,6 +172,9 @@ def cfg3(skip_cpu):
     out["roofline"] = roof("agcl_cl_kernel<0> (offset mode, 90x160)", N * 90 * 160 * 2272, us)
     out["roofline"]["note"] = ("gather-bound, not HBM-bound: 36 KB of corner vectors are gathered per pixel (2.2 GB through "
                                "L1, 1.6 GB from L2) for 2.3 KB of compulsory traffic; DRAM moves only 123 MB (ncu)")
+    out["other_rooflines"] = [roof("agcl_iter_fused_kernel<1x9> (iter mode, 90x160)", N * 90 * 160 * 2200, out["gpu_us"]["iter_1x9_90x160"]),
+                              roof("agcl_iter_fused_kernel<3x3> (iter mode, 90x160)", N * 90 * 160 * 2200, out["gpu_us"]["iter_3x3_90x160"]),
+                              roof("agcl_cl4_kernel<0> (offset mode 3x3, 90x160)", N * 90 * 160 * 2272, out["gpu_us"]["offset_3x3_90x160"])]
     have_ref = reference_available()
     if have_ref:
         from nndepth.models.cre_stereo.cost_volume import AGCL as RefAGCL
