@@ -201,6 +201,22 @@ nnd_status nnd_agcl_iter_nhwc(const float* fmap1_nhwc, const float* fmap2_nhwc, 
                               int C, int H, int W, int small_patch, float* warped_ws, float* out,
                               nnd_stream_t stream);
 
+/* Backward of the channels-last AGCL entry points for the reference's trainers (the forward they differentiate:
+ * cre_stereo/cost_volume.py:54-154; bilinear sampling utils.py:34-107).  grad_out is (N,36,H,W).  d_fmap1 (N,H,W,C) is
+ * written; d_fmap2 (N,H,W,C) -- and d_warped_ws for iter mode -- are ACCUMULATED with atomics: the caller zero-fills
+ * them.  d_flow (N,2,H,W) and d_extra (N,18,H,W) may be NULL.  nnd_agcl_warp_nhwc materialises the flow-warped right
+ * map (cost_volume.py:57-59) that iter mode's backward re-reads. */
+nnd_status nnd_agcl_warp_nhwc(const float* fmap2_nhwc, const float* flow, int N, int C, int H, int W, float* warped,
+                              nnd_stream_t stream);
+nnd_status nnd_agcl_offset_backward_nhwc(const float* fmap1_nhwc, const float* fmap2_nhwc, const float* flow,
+                                         const float* extra_offset, const float* grad_out, int N, int C, int H, int W,
+                                         int small_patch, float* d_fmap1, float* d_fmap2, float* d_flow, float* d_extra,
+                                         nnd_stream_t stream);
+nnd_status nnd_agcl_iter_backward_nhwc(const float* fmap1_nhwc, const float* fmap2_nhwc, const float* flow,
+                                       const float* warped, const float* grad_out, int N, int C, int H, int W,
+                                       int small_patch, float* d_fmap1, float* d_fmap2, float* d_flow, float* d_warped_ws,
+                                       nnd_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Convex upsampling of the coarse disparity by the learned 9-neighbour mask, one pass.
  * Replaces RAFTStereo.convex_upsample nndepth/models/raft_stereo/model.py:93-105 (identical code in

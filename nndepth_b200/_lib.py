@@ -63,6 +63,9 @@ SIGNATURES = {
     "nnd_nchw_to_nhwc": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "nnd_agcl_offset_nhwc": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "nnd_agcl_iter_nhwc": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "nnd_agcl_warp_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
+    "nnd_agcl_offset_backward_nhwc": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "nnd_agcl_iter_backward_nhwc": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
 }
 
 _lock = threading.Lock()

@@ -14,12 +14,55 @@ two maps are staged ONCE per object as channels-last ``(N, H, W, C)`` copies (``
 import torch
 
 from . import _lib
+from .corr import _train_f32, _wants_grad
+
+
+class _AGCLOffset(torch.autograd.Function):
+    """Differentiable offset mode on channels-last maps: forward ``nnd_agcl_offset_nhwc``, backward
+    ``nnd_agcl_offset_backward_nhwc`` (gradients for both maps, the flow and the learned offsets)."""
+
+    @staticmethod
+    def forward(ctx, left, right, flow, extra, small_patch):
+        ctx.save_for_backward(left, right, flow, extra)
+        ctx.small = bool(small_patch)
+        return _lib.ops().agcl_offset(left, right, flow, extra, ctx.small, True)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        left, right, flow, extra = ctx.saved_tensors
+        d1, d2, dflow, dextra = _lib.ops().agcl_offset_backward(left, right, flow, extra, grad_out.contiguous().float(), ctx.small)
+        need = ctx.needs_input_grad
+        return (d1 if need[0] else None, d2 if need[1] else None, dflow if need[2] else None, dextra if need[3] else None, None)
+
+
+class _AGCLIter(torch.autograd.Function):
+    """Differentiable iter mode on channels-last maps: forward ``nnd_agcl_iter_nhwc`` (one fused pass); backward
+    re-materialises the flow-warped right map (``nnd_agcl_warp_nhwc``) and runs ``nnd_agcl_iter_backward_nhwc``."""
+
+    @staticmethod
+    def forward(ctx, left, right, flow, small_patch):
+        ctx.save_for_backward(left, right, flow)
+        ctx.small = bool(small_patch)
+        ws = torch.empty_like(right)
+        return _lib.ops().agcl_iter(left, right, flow, ctx.small, True, ws)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        left, right, flow = ctx.saved_tensors
+        warped = _lib.ops().agcl_warp(right, flow)
+        d1, d2, dflow = _lib.ops().agcl_iter_backward(left, right, flow, warped, grad_out.contiguous().float(), ctx.small)
+        need = ctx.needs_input_grad
+        return (d1 if need[0] else None, d2 if need[1] else None, dflow if need[2] else None, None)
 
 
 class AGCL:
     def __init__(self, fmap1, fmap2, att=None):
-        self.fmap1 = _lib.as_cuda_f32(fmap1, "fmap1")
-        self.fmap2 = _lib.as_cuda_f32(fmap2, "fmap2")
+        # training (feature maps, or the attention module's parameters, require grad): the maps stay attached to the
+        # autograd graph and the calls go through _AGCLOffset / _AGCLIter; otherwise inference on detached copies
+        self._train = _wants_grad(fmap1, fmap2) or (
+            torch.is_grad_enabled() and isinstance(att, torch.nn.Module) and any(p.requires_grad for p in att.parameters()))
+        self.fmap1 = _train_f32(fmap1, "fmap1") if self._train else _lib.as_cuda_f32(fmap1, "fmap1")
+        self.fmap2 = _train_f32(fmap2, "fmap2") if self._train else _lib.as_cuda_f32(fmap2, "fmap2")
         if self.fmap1.dim() != 4 or self.fmap1.shape != self.fmap2.shape:
             raise RuntimeError("fmap1 and fmap2 must be (N, C, H, W) of identical shape")
         self.att = att
@@ -42,6 +85,28 @@ class AGCL:
         self._staged[id(t)] = (t, out)
         return out
 
+    def _training_call(self, *tensors):
+        """Differentiable path: grad mode on and something upstream requires grad (maps with C % 16 == 0 only)."""
+        if not (torch.is_grad_enabled() and (self._train or any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors))):
+            return False
+        C = tensors[0].shape[1]
+        if C % 16 != 0:
+            raise RuntimeError(f"the differentiable AGCL path needs C % 16 == 0 (got {C})")
+        return True
+
+    @staticmethod
+    def _nhwc_grad(t):
+        """Channels-last copy that stays in the autograd graph (the staging kernel of the inference path does not)."""
+        return t.float().permute(0, 2, 3, 1).contiguous()
+
+    @staticmethod
+    def _flow_grad(flow, N, H, W):
+        if not (isinstance(flow, torch.Tensor) and flow.is_cuda):
+            raise RuntimeError("flow must be a CUDA tensor: nndepth_b200 has no CPU path")
+        if tuple(flow.shape) != (N, 2, H, W):
+            raise RuntimeError(f"flow must be (N, 2, H, W) = {(N, 2, H, W)}, got {tuple(flow.shape)}")
+        return flow.float().contiguous()
+
     def __call__(self, flow, extra_offset, small_patch=False, iter_mode=False):
         if iter_mode:
             return self.corr_iter(self.fmap1, self.fmap2, flow, small_patch)
@@ -58,6 +123,8 @@ class AGCL:
         left = left_feature if left_feature is self.fmap1 else _lib.as_cuda_f32(left_feature, "left_feature")
         right = right_feature if right_feature is self.fmap2 else _lib.as_cuda_f32(right_feature, "right_feature")
         N, C, H, W = left.shape
+        if self._training_call(left, right, flow):
+            return _AGCLIter.apply(self._nhwc_grad(left), self._nhwc_grad(right), self._flow_grad(flow, N, H, W), bool(small_patch))
         flow = self._check_flow(flow, N, H, W)
         if self._fast(C) and H >= 2 and W >= 2:
             if self._warp_ws is None or self._warp_ws.shape != (N, H, W, C) or self._warp_ws.device != left.device:
@@ -73,7 +140,10 @@ class AGCL:
             rt = right.permute(0, 2, 3, 1).reshape(N, H * W, C)
             lt, rt = self.att(lt, rt)
             la, ra = [x.reshape(N, H, W, C).permute(0, 3, 1, 2) for x in (lt, rt)]
-            self._attended = (left, right, _lib.as_cuda_f32(la, "att(left)"), _lib.as_cuda_f32(ra, "att(right)"))
+            if self._train and torch.is_grad_enabled():
+                self._attended = (left, right, _train_f32(la, "att(left)"), _train_f32(ra, "att(right)"))
+            else:
+                self._attended = (left, right, _lib.as_cuda_f32(la, "att(left)"), _lib.as_cuda_f32(ra, "att(right)"))
         return self._attended[2], self._attended[3]
 
     def corr_att_offset(self, left_feature, right_feature, flow, extra_offset, small_patch):
@@ -82,6 +152,12 @@ class AGCL:
         N, C, H, W = left.shape
         if self.att is not None:
             left, right = self._attend(left, right)
+        if self._training_call(left, right, flow, extra_offset):
+            extra = _train_f32(extra_offset, "extra_offset")
+            if tuple(extra.shape) != (N, 18, H, W):
+                raise RuntimeError(f"extra_offset must be (N, 18, H, W) = {(N, 18, H, W)}, got {tuple(extra.shape)}")
+            return _AGCLOffset.apply(self._nhwc_grad(left), self._nhwc_grad(right), self._flow_grad(flow, N, H, W), extra,
+                                     bool(small_patch))
         flow = self._check_flow(flow, N, H, W)
         extra = _lib.as_cuda_f32(extra_offset, "extra_offset")
         if tuple(extra.shape) != (N, 18, H, W):

@@ -10,8 +10,8 @@ Differences by design: one launch builds the volume *and* its pooled levels; one
 iteration does the whole 4-level lookup; rows of the pyramid are padded to 16 bytes (``corr_pyramid``
 hides the padding).  ``CorrBlock1D`` is differentiable with respect to the feature maps (the coordinates are
 detached by the reference before every lookup, ``raft_stereo/model.py:131``): the lookup backward and the pooling
-backward are kernels of this package, the two volume-gradient contractions are cuBLAS GEMMs.  The grouped blocks,
-AGCL and the IGEV volume are inference only.
+backward are kernels of this package, the two volume-gradient contractions are cuBLAS GEMMs.  ``GroupCorrBlock1D`` and
+the IGEV volume (``igev.py``) are differentiable the same way (grouped contraction, lookup backward per group).
 """
 import math
 import warnings
@@ -118,6 +118,15 @@ class PyramidStorage:
             dst[:, :w] = src.to(device=dst.device, dtype=torch.float32)
         return self
 
+    def graph_view(self, graph_buffer):
+        """The same list as views of an autograd-tracked copy of the buffer (training: gradients flow through them)."""
+        views, start = [], 0
+        for p, w in zip(self.pitches, self.widths):
+            views.append(graph_buffer[start:start + self.rows * p].view(self.rows, p)[:, None, :w])
+            start += self.rows * p
+        views.append(torch.nn.functional.avg_pool1d(views[-1], 2))
+        return views
+
     def reference_view(self):
         """The reference's list: ``num_levels + 1`` tensors ``(rows, 1, w_l)`` (cost_volume.py:29-34).
 
@@ -176,6 +185,83 @@ class _LookupPyramid(torch.autograd.Function):
         d_buffer = _lib.ops().corr1d_lookup_backward(grad_out.contiguous().float(), coords, W2, block.num_levels,
                                                      block.radius)
         return d_buffer, None, None
+
+
+def _wants_grad(*tensors):
+    return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
+
+
+def _train_f32(t, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise RuntimeError(f"{name} must be a CUDA tensor: nndepth_b200 has no CPU path")
+    return t.float().contiguous()
+
+
+class _GroupedBuild(torch.autograd.Function):
+    """Differentiable group-wise pyramid build (rows ``[b][g][h][w1]``): forward = ``nnd_groupcorr_build``; backward =
+    un-pool the level gradients (``nnd_avgpool_pairs_backward``) and contract ``d_volume`` group by group with the
+    other feature map.  Only the first ``G * group_size`` channels take part (the reference's ``torch.split`` quirk)."""
+
+    @staticmethod
+    def forward(ctx, f1, f2, G, group_size, scale_div, num_levels):
+        B, C, H, W1 = f1.shape
+        W2 = f2.shape[3]
+        pyr = PyramidStorage(B * G * H * W1, W2, num_levels, f1.device)
+        _lib.ops().groupcorr_build(f1, f2, pyr.buffer, G, group_size, float(scale_div), num_levels)
+        ctx.save_for_backward(f1, f2)
+        ctx.geom = (B, C, H, W1, W2, G, group_size, float(scale_div), num_levels)
+        return pyr.buffer
+
+    @staticmethod
+    def backward(ctx, d_buffer):
+        f1, f2 = ctx.saved_tensors
+        B, C, H, W1, W2, G, gs, scale_div, L = ctx.geom
+        d = PyramidStorage(B * G * H * W1, W2, L, f1.device, buffer=d_buffer.contiguous().clone())
+        _lib.ops().pyramid_unpool_(d.buffer, d.rows, W2, L)
+        d_vol = d.levels[0][:, :W2].reshape(B, G, H, W1, W2) / scale_div
+        used = G * gs
+        f1g = f1[:, :used].reshape(B, G, gs, H, W1)
+        f2g = f2[:, :used].reshape(B, G, gs, H, W2)
+        d_f1 = d_f2 = None
+        if ctx.needs_input_grad[0]:
+            d_f1 = torch.zeros_like(f1)
+            d_f1[:, :used] = torch.einsum("bghij,bgchj->bgchi", d_vol, f2g).reshape(B, used, H, W1)
+        if ctx.needs_input_grad[1]:
+            d_f2 = torch.zeros_like(f2)
+            d_f2[:, :used] = torch.einsum("bghij,bgchi->bgchj", d_vol, f1g).reshape(B, used, H, W2)
+        return d_f1, d_f2, None, None, None, None
+
+
+class _GroupedLookup(torch.autograd.Function):
+    """Differentiable grouped lookup over one or two row-layout pyramids (``nnd_group_lookup``).  The gradient flows to
+    the pyramids only: per source it is the plain lookup backward (``nnd_corr1d_lookup_backward``) on ``B * G``
+    "images" whose coordinates repeat per group, after undoing the output channel order of the mode
+    (0: ``l*(S*G*T) + s*(G*T) + g*T + k``; 1: the ``GroupCorrBlock1D`` view quirk, reference cost_volume.py:108)."""
+
+    @staticmethod
+    def forward(ctx, buf_a, buf_b, coords, W2, G, num_levels, radius, mode):
+        ctx.save_for_backward(coords)
+        ctx.meta = (W2, G, num_levels, radius, mode, buf_b is not None)
+        return _lib.ops().group_lookup(buf_a, buf_b, W2, coords, G, num_levels, radius, mode)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (coords,) = ctx.saved_tensors
+        W2, G, L, r, mode, two = ctx.meta
+        B, _, H, W1 = coords.shape
+        T, S, hw = 2 * r + 1, 2 if two else 1, H * W1
+        grad_out = grad_out.contiguous().float()
+        coords_g = coords.repeat_interleave(G, dim=0).contiguous()          # (B*G, 1, H, W1): image b*G + g
+        grads = []
+        for s in range(S):
+            if mode == 0:
+                g = grad_out.view(B, L, S, G, T, H, W1)[:, :, s].permute(0, 2, 1, 3, 4, 5)      # (B, G, L, T, H, W1)
+            else:
+                # level block (GT, hw) is the transpose of the flat [g][rem][k] result, see lookup.cu mode 1
+                g = grad_out.view(B, L, G * T, hw).transpose(2, 3).reshape(B, L, G, hw, T).permute(0, 2, 1, 4, 3)
+            g = g.reshape(B * G, L * T, H, W1).contiguous()
+            grads.append(_lib.ops().corr1d_lookup_backward(g, coords_g, W2, L, r))
+        return grads[0], (grads[1] if two else None), None, None, None, None, None, None
 
 
 def _check_coords(coords, B, H, W1):
@@ -352,8 +438,10 @@ class GroupCorrBlock1D:
         self.num_levels = num_levels
         self.radius = radius
         self.num_groups = num_groups
-        f1 = _lib.as_cuda_f32(fmap1, "fmap1")
-        f2 = _lib.as_cuda_f32(fmap2, "fmap2")
+        self._graph_buffer = None
+        train = _wants_grad(fmap1, fmap2)
+        f1 = _train_f32(fmap1, "fmap1") if train else _lib.as_cuda_f32(fmap1, "fmap1")
+        f2 = _train_f32(fmap2, "fmap2") if train else _lib.as_cuda_f32(fmap2, "fmap2")
         if f1.dim() != 4 or f1.shape[:3] != f2.shape[:3]:
             raise RuntimeError("fmap1 and fmap2 must be (B, C, H, W) with equal batch, channels and height")
         B, C, H, W1 = f1.shape
@@ -362,6 +450,11 @@ class GroupCorrBlock1D:
         if G * G > C:
             raise IndexError("tuple index out of range")  # the reference indexes chunk i < G of size G
         self._shape = (B, H, W1, W2)
+        if train:
+            # training: the pyramid buffer stays in the autograd graph (the feature maps receive gradients)
+            self._graph_buffer = _GroupedBuild.apply(f1, f2, G, G, math.sqrt(C), num_levels)
+            self._pyr = PyramidStorage(B * G * H * W1, W2, num_levels, f1.device, buffer=self._graph_buffer.detach())
+            return
         self._pyr = PyramidStorage(B * G * H * W1, W2, num_levels, f1.device)
         _lib.ops().groupcorr_build(f1, f2, self._pyr.buffer, G, G, float(math.sqrt(C)), num_levels)
 
@@ -369,6 +462,7 @@ class GroupCorrBlock1D:
     def from_pyramid(cls, levels, batch, height, num_levels=4, radius=4, num_groups=4, device="cuda"):
         self = cls.__new__(cls)
         self.num_levels, self.radius, self.num_groups = num_levels, radius, num_groups
+        self._graph_buffer = None
         first = torch.as_tensor(levels[0])
         rows, W2 = first.reshape(first.shape[0], -1).shape
         self._shape = (batch, height, rows // (batch * height * num_groups), W2)
@@ -377,10 +471,16 @@ class GroupCorrBlock1D:
 
     @property
     def corr_pyramid(self):
+        if self._graph_buffer is not None and torch.is_grad_enabled():
+            return self._pyr.graph_view(self._graph_buffer)
         return self._pyr.reference_view()
 
     def __call__(self, coords):
         B, H, W1, _ = self._shape
+        if self._graph_buffer is not None and torch.is_grad_enabled():
+            coords = _check_coords(coords.detach(), B, H, W1)     # the reference detaches them too (model.py:302)
+            return _GroupedLookup.apply(self._graph_buffer, None, coords, self._shape[3], self.num_groups, self.num_levels,
+                                        self.radius, 1)
         coords = _check_coords(coords, B, H, W1)
         return _lib.ops().group_lookup(self._pyr.buffer, None, self._shape[3], coords, self.num_groups, self.num_levels,
                                        self.radius, 1)

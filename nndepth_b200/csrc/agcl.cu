@@ -732,6 +732,185 @@ static nnd_status launch_iter_fused(const float* L, const float* R, const float*
   return check_launch("agcl_iter_fused_kernel");
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward of AGCL for the reference's trainers (cre_stereo/cre_trainer.py; the forward path above is what they
+// differentiate through: cre_stereo/cost_volume.py:54-154, utils.py:34-107).  Channels-last maps, warp per pixel, lane =
+// 16-byte channel chunks; correctness first (float4 atomics for the scattered map gradients), not tuned.
+//
+//   sample_backward<OFFSET>  per (pixel p, tap k): position (p + flow(p)) + (d_k + extra_k(p)); the upstream gradient
+//                            of channel c is u_c = dout[g(c)*9+k, p] / (C/4) * L[p, c]:
+//                              dL[p, c]          += dout/(C/4) * Rs_c          (Rs = the bilinear sample)
+//                              dR[corner_q, c]   += w_q * u_c                  (atomic)
+//                              d position        += sum_c u_c * dRs_c/d(x, y)  -> d extra_k and d flow
+//   sample_backward<WARP>    the same arithmetic with ONE tap at p + flow(p) and u_c = dRw[p, c]: the backward of the
+//                            flow-warp that precedes iter mode's window (cost_volume.py:57-59)
+//   window_backward          iter mode's replicate-clamped window: dL[p] += dout/(C/4) * Rw[q_k], dRw[q_k] += dout/(C/4) * L[p]
+//
+// The weights of out-of-image corners come from the UNCLAMPED corner coordinates and multiply a zero image value
+// (utils.py:79-93), so they contribute to d position but not to dR.  floor() carries no gradient, the normalise /
+// denormalise round trip (utils.py:9-10, 59-60) has derivative 1.
+// ------------------------------------------------------------------------------------------------
+struct GradFootprint {
+  int off[4];        // pixel offsets y*W + x of a, b, c, d or -1
+  float fx, fy;      // x - x0, y - y0
+};
+
+__device__ __forceinline__ GradFootprint make_grad_footprint(float px, float py, int H, int W) {
+  const float x = pixel_round_trip(px, static_cast<float>(W - 1));
+  const float y = pixel_round_trip(py, static_cast<float>(H - 1));
+  const float x0f = floorf(x), y0f = floorf(y);
+  GradFootprint f;
+  f.fx = x - x0f;
+  f.fy = y - y0f;
+  const int x0 = static_cast<int>(fminf(fmaxf(x0f, -2.0f), static_cast<float>(W + 1)));
+  const int y0 = static_cast<int>(fminf(fmaxf(y0f, -2.0f), static_cast<float>(H + 1)));
+  const int x1 = x0 + 1, y1 = y0 + 1;
+  const bool vx0 = x0 >= 0 && x0 < W, vx1 = x1 >= 0 && x1 < W;
+  const bool vy0 = y0 >= 0 && y0 < H, vy1 = y1 >= 0 && y1 < H;
+  f.off[0] = (vx0 && vy0) ? y0 * W + x0 : -1;
+  f.off[1] = (vx0 && vy1) ? y1 * W + x0 : -1;
+  f.off[2] = (vx1 && vy0) ? y0 * W + x1 : -1;
+  f.off[3] = (vx1 && vy1) ? y1 * W + x1 : -1;
+  return f;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  return v;
+}
+
+__device__ __forceinline__ void atomic_add4(float* dst, float4 v) {
+  atomicAdd(reinterpret_cast<float4*>(dst), v);   // vector red.global.add (sm_90+)
+}
+
+// MODE 0: offset mode (9 taps, upstream = dout * L);  MODE 1: flow-warp backward (1 tap, upstream = dRw)
+template <int MODE>
+__global__ void __launch_bounds__(256)
+agcl_sample_backward_kernel(const float* __restrict__ L, const float* __restrict__ R, const float* __restrict__ flow,
+                            const float* __restrict__ extra, const float* __restrict__ up, int C, int H, int W, long long n_pix,
+                            int small_patch, float* __restrict__ dL, float* __restrict__ dR, float* __restrict__ dflow,
+                            float* __restrict__ dextra) {
+  const int lane = threadIdx.x & 31;
+  const long long pix = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pix >= n_pix) return;
+  const long long hw = static_cast<long long>(H) * W;
+  const long long n = pix / hw;
+  const int p = static_cast<int>(pix - n * hw);
+  const int y = p / W, x = p - y * W;
+  const int cg = C / AGCL_GROUPS;
+  const float inv_cg = 1.0f / static_cast<float>(cg);
+  const float* fl = flow + n * 2 * hw + p;
+  const float fxw = __ldg(fl), fyw = __ldg(fl + hw);
+  const float* rb = R + n * hw * C;
+  float* drb = dR + n * hw * C;
+  const float* lp = L ? L + pix * C : nullptr;
+  float dfx = 0.f, dfy = 0.f;
+  constexpr int NT = MODE == 0 ? AGCL_TAPS : 1;
+  for (int k = 0; k < NT; ++k) {
+    float px, py;
+    if (MODE == 0) {
+      int dx, dy;
+      tap_delta(k, small_patch != 0, dx, dy);
+      const float* ex = extra + (n * 2 * AGCL_TAPS + 2 * k) * hw + p;
+      px = __fadd_rn(__fadd_rn(static_cast<float>(x), fxw), __fadd_rn(static_cast<float>(dx), __ldg(ex)));
+      py = __fadd_rn(__fadd_rn(static_cast<float>(y), fyw), __fadd_rn(static_cast<float>(dy), __ldg(ex + hw)));
+    } else {
+      px = __fadd_rn(static_cast<float>(x), fxw);
+      py = __fadd_rn(static_cast<float>(y), fyw);
+    }
+    const GradFootprint f = make_grad_footprint(px, py, H, W);
+    const float wa = (1.f - f.fx) * (1.f - f.fy), wb = (1.f - f.fx) * f.fy, wc = f.fx * (1.f - f.fy), wd = f.fx * f.fy;
+    float gx = 0.f, gy = 0.f;
+    for (int c4 = lane; c4 < C / 4; c4 += 32) {
+      const int ch = 4 * c4;
+      float4 u;   // upstream gradient of the sampled vector, channels ch .. ch+3
+      float go = 0.f;
+      float4 l = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (MODE == 0) {
+        go = __ldg(up + (n * AGCL_GROUPS * AGCL_TAPS + (ch / cg) * AGCL_TAPS + k) * hw + p) * inv_cg;
+        l = ldg_f4(lp + ch);
+        u = make_float4(go * l.x, go * l.y, go * l.z, go * l.w);
+      } else {
+        u = ldg_f4(up + pix * C + ch);
+      }
+      float4 r[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) r[q] = f.off[q] >= 0 ? ldg_f4(rb + static_cast<long long>(f.off[q]) * C + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (MODE == 0) {
+        float4 rs;   // the sample itself: dL = go * Rs
+        rs.x = wa * r[0].x + wb * r[1].x + wc * r[2].x + wd * r[3].x;
+        rs.y = wa * r[0].y + wb * r[1].y + wc * r[2].y + wd * r[3].y;
+        rs.z = wa * r[0].z + wb * r[1].z + wc * r[2].z + wd * r[3].z;
+        rs.w = wa * r[0].w + wb * r[1].w + wc * r[2].w + wd * r[3].w;
+        float* dl = dL + pix * C + ch;          // a pixel's dL row belongs to this warp: plain read-modify-write
+        float4 acc = k == 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<float4*>(dl);
+        acc.x += go * rs.x; acc.y += go * rs.y; acc.z += go * rs.z; acc.w += go * rs.w;
+        *reinterpret_cast<float4*>(dl) = acc;
+      }
+      const float wq[4] = {wa, wb, wc, wd};
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (f.off[q] >= 0)
+          atomic_add4(drb + static_cast<long long>(f.off[q]) * C + ch, make_float4(wq[q] * u.x, wq[q] * u.y, wq[q] * u.z, wq[q] * u.w));
+      // dRs/dx = (1-fy) (c - a) + fy (d - b);  dRs/dy = (1-fx) (b - a) + fx (d - c)
+      const float ddx_x = (1.f - f.fy) * (r[2].x - r[0].x) + f.fy * (r[3].x - r[1].x);
+      const float ddx_y = (1.f - f.fy) * (r[2].y - r[0].y) + f.fy * (r[3].y - r[1].y);
+      const float ddx_z = (1.f - f.fy) * (r[2].z - r[0].z) + f.fy * (r[3].z - r[1].z);
+      const float ddx_w = (1.f - f.fy) * (r[2].w - r[0].w) + f.fy * (r[3].w - r[1].w);
+      const float ddy_x = (1.f - f.fx) * (r[1].x - r[0].x) + f.fx * (r[3].x - r[2].x);
+      const float ddy_y = (1.f - f.fx) * (r[1].y - r[0].y) + f.fx * (r[3].y - r[2].y);
+      const float ddy_z = (1.f - f.fx) * (r[1].z - r[0].z) + f.fx * (r[3].z - r[2].z);
+      const float ddy_w = (1.f - f.fx) * (r[1].w - r[0].w) + f.fx * (r[3].w - r[2].w);
+      gx += u.x * ddx_x + u.y * ddx_y + u.z * ddx_z + u.w * ddx_w;
+      gy += u.x * ddy_x + u.y * ddy_y + u.z * ddy_z + u.w * ddy_w;
+    }
+    gx = warp_sum(gx);
+    gy = warp_sum(gy);
+    if (MODE == 0 && lane == 0 && dextra) {
+      dextra[(n * 2 * AGCL_TAPS + 2 * k) * hw + p] = gx;
+      dextra[(n * 2 * AGCL_TAPS + 2 * k + 1) * hw + p] = gy;
+    }
+    dfx += gx;
+    dfy += gy;
+    __syncwarp();   // the dL row is re-read by the next tap
+  }
+  if (lane == 0 && dflow) {
+    dflow[n * 2 * hw + p] = dfx;
+    dflow[n * 2 * hw + hw + p] = dfy;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+agcl_window_backward_kernel(const float* __restrict__ L, const float* __restrict__ Rw, const float* __restrict__ dout, int C,
+                            int H, int W, long long n_pix, int small_patch, float* __restrict__ dL, float* __restrict__ dRw) {
+  const int lane = threadIdx.x & 31;
+  const long long pix = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pix >= n_pix) return;
+  const long long hw = static_cast<long long>(H) * W;
+  const long long n = pix / hw;
+  const int p = static_cast<int>(pix - n * hw);
+  const int y = p / W, x = p - y * W;
+  const int cg = C / AGCL_GROUPS;
+  const float inv_cg = 1.0f / static_cast<float>(cg);
+  for (int c4 = lane; c4 < C / 4; c4 += 32) {
+    const int ch = 4 * c4;
+    const float4 l = ldg_f4(L + pix * C + ch);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < AGCL_TAPS; ++k) {
+      int dx, dy;
+      tap_delta(k, small_patch != 0, dx, dy);
+      const int xx = min(max(x + dx, 0), W - 1), yy = min(max(y + dy, 0), H - 1);
+      const long long q = (n * hw + static_cast<long long>(yy) * W + xx) * C + ch;
+      const float go = __ldg(dout + (n * AGCL_GROUPS * AGCL_TAPS + (ch / cg) * AGCL_TAPS + k) * hw + p) * inv_cg;
+      const float4 r = ldg_f4(Rw + q);
+      acc.x += go * r.x; acc.y += go * r.y; acc.z += go * r.z; acc.w += go * r.w;
+      atomic_add4(dRw + q, make_float4(go * l.x, go * l.y, go * l.z, go * l.w));
+    }
+    *reinterpret_cast<float4*>(dL + pix * C + ch) = acc;
+  }
+}
+
 static nnd_status check_agcl(const float* f1, const float* f2, const float* flow, const float* out, int N, int C,
                              int H, int W, const char* who) {
   NND_REQUIRE(f1 && f2 && flow && out, "%s: null pointer argument", who);
@@ -865,6 +1044,66 @@ nnd_status nnd_agcl_iter_nhwc(const float* fmap1_nhwc, const float* fmap2_nhwc, 
                                                                                n_pix, small_patch ? 1 : 0, out);
   }
   return check_launch("agcl_cl_kernel<iter>");
+}
+
+nnd_status nnd_agcl_warp_nhwc(const float* fmap2_nhwc, const float* flow, int N, int C, int H, int W, float* warped,
+                              nnd_stream_t stream) {
+  using namespace nnd;
+  nnd_status st = check_agcl(fmap2_nhwc, fmap2_nhwc, flow, warped, N, C, H, W, "agcl_warp_nhwc");
+  if (st != NND_OK) return st;
+  NND_REQUIRE(C % 4 == 0 && aligned16(fmap2_nhwc) && aligned16(warped), "agcl_warp_nhwc: needs C %% 4 == 0 and 16-byte aligned maps");
+  const long long n_pix = static_cast<long long>(N) * H * W;
+  const long long blocks = (n_pix + CL_WARPS - 1) / CL_WARPS;
+  NND_REQUIRE(blocks <= 0x7fffffffLL, "agcl_warp_nhwc: too many pixels");
+  agcl_warp_cl_kernel<<<static_cast<unsigned>(blocks), 32 * CL_WARPS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      fmap2_nhwc, flow, C, H, W, n_pix, warped);
+  return check_launch("agcl_warp_cl_kernel");
+}
+
+nnd_status nnd_agcl_offset_backward_nhwc(const float* fmap1_nhwc, const float* fmap2_nhwc, const float* flow,
+                                         const float* extra_offset, const float* grad_out, int N, int C, int H, int W,
+                                         int small_patch, float* d_fmap1, float* d_fmap2, float* d_flow, float* d_extra,
+                                         nnd_stream_t stream) {
+  using namespace nnd;
+  nnd_status st = check_agcl(fmap1_nhwc, fmap2_nhwc, flow, d_fmap1, N, C, H, W, "agcl_offset_backward_nhwc");
+  if (st != NND_OK) return st;
+  NND_REQUIRE(extra_offset && grad_out && d_fmap2, "agcl_offset_backward_nhwc: null pointer argument");
+  NND_REQUIRE(C % 16 == 0, "agcl_offset_backward_nhwc: needs C %% 16 == 0 (got %d)", C);
+  NND_REQUIRE(aligned16(fmap1_nhwc) && aligned16(fmap2_nhwc) && aligned16(d_fmap1) && aligned16(d_fmap2),
+              "agcl_offset_backward_nhwc: maps must be 16-byte aligned");
+  const long long n_pix = static_cast<long long>(N) * H * W;
+  const long long blocks = (n_pix + 7) / 8;
+  NND_REQUIRE(blocks <= 0x7fffffffLL, "agcl_offset_backward_nhwc: too many pixels");
+  // d_fmap2 is accumulated with atomics: the caller zero-fills it
+  agcl_sample_backward_kernel<0><<<static_cast<unsigned>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      fmap1_nhwc, fmap2_nhwc, flow, extra_offset, grad_out, C, H, W, n_pix, small_patch ? 1 : 0, d_fmap1, d_fmap2, d_flow, d_extra);
+  return check_launch("agcl_sample_backward_kernel<offset>");
+}
+
+nnd_status nnd_agcl_iter_backward_nhwc(const float* fmap1_nhwc, const float* fmap2_nhwc, const float* flow,
+                                       const float* warped, const float* grad_out, int N, int C, int H, int W,
+                                       int small_patch, float* d_fmap1, float* d_fmap2, float* d_flow, float* d_warped_ws,
+                                       nnd_stream_t stream_) {
+  using namespace nnd;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  nnd_status st = check_agcl(fmap1_nhwc, fmap2_nhwc, flow, d_fmap1, N, C, H, W, "agcl_iter_backward_nhwc");
+  if (st != NND_OK) return st;
+  NND_REQUIRE(warped && grad_out && d_fmap2 && d_warped_ws, "agcl_iter_backward_nhwc: null pointer argument");
+  NND_REQUIRE(C % 16 == 0, "agcl_iter_backward_nhwc: needs C %% 16 == 0 (got %d)", C);
+  NND_REQUIRE(aligned16(fmap1_nhwc) && aligned16(fmap2_nhwc) && aligned16(warped) && aligned16(d_fmap1) && aligned16(d_fmap2) &&
+                  aligned16(d_warped_ws),
+              "agcl_iter_backward_nhwc: maps must be 16-byte aligned");
+  const long long n_pix = static_cast<long long>(N) * H * W;
+  const long long blocks = (n_pix + 7) / 8;
+  NND_REQUIRE(blocks <= 0x7fffffffLL, "agcl_iter_backward_nhwc: too many pixels");
+  // d_fmap2 and d_warped_ws are accumulated with atomics: the caller zero-fills both
+  agcl_window_backward_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(fmap1_nhwc, warped, grad_out, C, H, W, n_pix,
+                                                                                 small_patch ? 1 : 0, d_fmap1, d_warped_ws);
+  st = check_launch("agcl_window_backward_kernel");
+  if (st != NND_OK) return st;
+  agcl_sample_backward_kernel<1><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+      nullptr, fmap2_nhwc, flow, nullptr, d_warped_ws, C, H, W, n_pix, 0, nullptr, d_fmap2, d_flow, nullptr);
+  return check_launch("agcl_sample_backward_kernel<warp>");
 }
 
 }  // extern "C"

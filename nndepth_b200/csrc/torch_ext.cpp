@@ -378,6 +378,67 @@ Tensor agcl_iter(const Tensor& f1, const Tensor& f2, const Tensor& flow, bool sm
   return out;
 }
 
+
+// ---- backward of the channels-last AGCL (training) ----
+Tensor agcl_warp(const Tensor& f2, const Tensor& flow) {
+  check_cuda(f2, "fmap2"); check_cuda(flow, "flow");
+  same_device(f2, flow, "agcl_warp");
+  auto sf = nchw(flow, "flow");
+  TORCH_CHECK(f2.dim() == 4 && f2.size(0) == sf[0] && f2.size(1) == sf[2] && f2.size(2) == sf[3] && sf[1] == 2,
+              "agcl_warp: fmap2 must be (N, H, W, C) and flow (N, 2, H, W)");
+  c10::cuda::CUDAGuard guard(f2.device());
+  Tensor out = at::empty_like(f2);
+  check_status(nnd_agcl_warp_nhwc(f2.data_ptr<float>(), flow.data_ptr<float>(), sf[0], f2.size(3), sf[2], sf[3],
+                                  out.data_ptr<float>(), current_stream(f2)),
+               "nnd_agcl_warp_nhwc");
+  return out;
+}
+
+// returns (d_fmap1, d_fmap2, d_flow, d_extra), maps channels-last (N, H, W, C)
+std::tuple<Tensor, Tensor, Tensor, Tensor> agcl_offset_backward(const Tensor& f1, const Tensor& f2, const Tensor& flow,
+                                                                const Tensor& extra_offset, const Tensor& grad_out,
+                                                                bool small_patch) {
+  check_cuda(f1, "fmap1"); check_cuda(f2, "fmap2"); check_cuda(flow, "flow"); check_cuda(extra_offset, "extra_offset");
+  check_cuda(grad_out, "grad_out");
+  auto sf = nchw(flow, "flow");
+  const int64_t N = sf[0], H = sf[2], W = sf[3];
+  TORCH_CHECK(f1.dim() == 4 && f1.sizes() == f2.sizes() && f1.size(0) == N && f1.size(1) == H && f1.size(2) == W && sf[1] == 2,
+              "agcl_offset_backward: maps must be (N, H, W, C) matching flow (N, 2, H, W)");
+  TORCH_CHECK(grad_out.dim() == 4 && grad_out.size(0) == N && grad_out.size(1) == 36 && grad_out.size(2) == H && grad_out.size(3) == W,
+              "agcl_offset_backward: grad_out must be (N, 36, H, W), got ", grad_out.sizes());
+  TORCH_CHECK(extra_offset.numel() == N * 18 * H * W, "agcl_offset_backward: extra_offset must be (N, 18, H, W)");
+  c10::cuda::CUDAGuard guard(f1.device());
+  Tensor d1 = at::empty_like(f1), d2 = at::zeros_like(f2), dflow = at::empty_like(flow), dextra = at::empty_like(extra_offset);
+  check_status(nnd_agcl_offset_backward_nhwc(f1.data_ptr<float>(), f2.data_ptr<float>(), flow.data_ptr<float>(),
+                                             extra_offset.data_ptr<float>(), grad_out.data_ptr<float>(), N, f1.size(3), H, W,
+                                             small_patch ? 1 : 0, d1.data_ptr<float>(), d2.data_ptr<float>(),
+                                             dflow.data_ptr<float>(), dextra.data_ptr<float>(), current_stream(f1)),
+               "nnd_agcl_offset_backward_nhwc");
+  return {d1, d2, dflow, dextra};
+}
+
+// returns (d_fmap1, d_fmap2, d_flow); `warped` = agcl_warp(fmap2, flow)
+std::tuple<Tensor, Tensor, Tensor> agcl_iter_backward(const Tensor& f1, const Tensor& f2, const Tensor& flow, const Tensor& warped,
+                                                      const Tensor& grad_out, bool small_patch) {
+  check_cuda(f1, "fmap1"); check_cuda(f2, "fmap2"); check_cuda(flow, "flow"); check_cuda(warped, "warped");
+  check_cuda(grad_out, "grad_out");
+  auto sf = nchw(flow, "flow");
+  const int64_t N = sf[0], H = sf[2], W = sf[3];
+  TORCH_CHECK(f1.dim() == 4 && f1.sizes() == f2.sizes() && f1.sizes() == warped.sizes() && f1.size(0) == N && f1.size(1) == H &&
+                  f1.size(2) == W && sf[1] == 2,
+              "agcl_iter_backward: maps must be (N, H, W, C) matching flow (N, 2, H, W)");
+  TORCH_CHECK(grad_out.dim() == 4 && grad_out.size(0) == N && grad_out.size(1) == 36 && grad_out.size(2) == H && grad_out.size(3) == W,
+              "agcl_iter_backward: grad_out must be (N, 36, H, W), got ", grad_out.sizes());
+  c10::cuda::CUDAGuard guard(f1.device());
+  Tensor d1 = at::empty_like(f1), d2 = at::zeros_like(f2), dflow = at::empty_like(flow), dws = at::zeros_like(f2);
+  check_status(nnd_agcl_iter_backward_nhwc(f1.data_ptr<float>(), f2.data_ptr<float>(), flow.data_ptr<float>(),
+                                           warped.data_ptr<float>(), grad_out.data_ptr<float>(), N, f1.size(3), H, W,
+                                           small_patch ? 1 : 0, d1.data_ptr<float>(), d2.data_ptr<float>(),
+                                           dflow.data_ptr<float>(), dws.data_ptr<float>(), current_stream(f1)),
+               "nnd_agcl_iter_backward_nhwc");
+  return {d1, d2, dflow};
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // convex upsampling  (raft_stereo/model.py:93-105)
 // ---------------------------------------------------------------------------------------------------------------
@@ -442,6 +503,11 @@ TORCH_LIBRARY(nndepth_b200, m) {
   m.def("agcl_offset(Tensor fmap1, Tensor fmap2, Tensor flow, Tensor extra_offset, bool small_patch, bool nhwc) -> Tensor",
         &agcl_offset);
   m.def("agcl_iter(Tensor fmap1, Tensor fmap2, Tensor flow, bool small_patch, bool nhwc, Tensor? warped_ws) -> Tensor", &agcl_iter);
+  m.def("agcl_warp(Tensor fmap2, Tensor flow) -> Tensor", &agcl_warp);
+  m.def("agcl_offset_backward(Tensor fmap1, Tensor fmap2, Tensor flow, Tensor extra_offset, Tensor grad_out, bool small_patch) "
+        "-> (Tensor, Tensor, Tensor, Tensor)", &agcl_offset_backward);
+  m.def("agcl_iter_backward(Tensor fmap1, Tensor fmap2, Tensor flow, Tensor warped, Tensor grad_out, bool small_patch) "
+        "-> (Tensor, Tensor, Tensor)", &agcl_iter_backward);
   m.def("convex_upsample(Tensor flow, Tensor mask, Tensor? mask_bias, int rate, float mask_scale, int mask_layout) -> Tensor",
         &convex_upsample);
 }

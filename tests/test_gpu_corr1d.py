@@ -324,10 +324,10 @@ def test_edge_cases_and_errors():
     out = ok(torch.full((1, 1, 2, 12), float("nan"), device="cuda"))
     assert out.shape == (1, 18, 2, 12)
     torch.cuda.synchronize()
-    # CorrBlock1D is differentiable (tests/test_gpu_backward.py); the grouped block refuses gradients loudly
-    # instead of silently dropping them
-    with pytest.raises(RuntimeError, match="inference-only"):
-        nb.GroupCorrBlock1D(f.clone().requires_grad_(True), f, 2, 4, 2)
+    # CorrBlock1D and GroupCorrBlock1D are differentiable (tests/test_gpu_backward.py); a tensor that requires grad is
+    # refused loudly only where no backward exists (the fused convolution front of the model shell)
+    grp = nb.GroupCorrBlock1D(f.clone().requires_grad_(True), f, 2, 4, 2)
+    assert grp._graph_buffer is not None and grp(torch.zeros(1, 1, 2, 12, device="cuda")).requires_grad
 
 
 def test_config5_row_bands_equal_full_volume():
