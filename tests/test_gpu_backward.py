@@ -66,8 +66,8 @@ def test_inference_path_is_unchanged_and_grad_free():
     with torch.no_grad():
         blk = nb.CorrBlock1D(f, f, 2, 4)
         out = blk(torch.zeros(1, 1, 2, 16, device="cuda"))
-    assert not out.requires_grad and blk._graph_buffer is None
         grp = nb.GroupCorrBlock1D(f, f, 2, 4, 2)
+    assert not out.requires_grad and blk._graph_buffer is None
     assert grp._graph_buffer is None
 
 
