@@ -138,9 +138,14 @@ def test_igev_volume_gradients(ref):
     w_out = torch.randn(B, 576, H, W, device="cuda")
     w_geo = torch.randn(B * G * H * W, 1, W, device="cuda")
 
-    cv = nb.GeometryAwareCostVolume(f1, f2, [], reg, 4, 4, G)
-    loss = (cv(coords) * w_out).sum() + (cv.geo_aware_cv[0] * w_geo).sum()
-    loss.backward()
+    old_flags = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False     # the regulariser is cuDNN: keep it fp32
+    try:
+        cv = nb.GeometryAwareCostVolume(f1, f2, [], reg, 4, 4, G)
+        loss = (cv(coords) * w_out).sum() + (cv.geo_aware_cv[0] * w_geo).sum()
+        loss.backward()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old_flags
 
     d1, d2 = f1.detach().double().requires_grad_(True), f2.detach().double().requires_grad_(True)
     rcv = RefGEV(d1, d2, [], reg64, 4, 4, G)
