@@ -96,7 +96,8 @@ class GeometryAwareCostVolume(nn.Module):
         if train:
             self._init_differentiable(f1, f2, features, regularizer_3d, train_f)
             return
-        self._interleaved        # feature volume in the reference row layout: level 0 only on the interleaved path (it feeds the
+        self._interleaved = (G == 8 and W2 % 8 == 0 and W1 % 4 == 0 and num_levels <= 4 and radius == 4)
+        # feature volume in the reference row layout: level 0 only on the interleaved path (it feeds the
         # regulariser), all levels otherwise
         self._feat = PyramidStorage(B * G * H * W1, W2, 1 if self._interleaved else num_levels, f1.device)
         self._build_feature_volume(f1, f2, self._feat)
