@@ -205,7 +205,9 @@ nnd_status nnd_agcl_iter_nhwc(const float* fmap1_nhwc, const float* fmap2_nhwc, 
  * cre_stereo/cost_volume.py:54-154; bilinear sampling utils.py:34-107).  grad_out is (N,36,H,W).  d_fmap1 (N,H,W,C) is
  * written; d_fmap2 (N,H,W,C) -- and d_warped_ws for iter mode -- are ACCUMULATED with atomics: the caller zero-fills
  * them.  d_flow (N,2,H,W) and d_extra (N,18,H,W) may be NULL.  nnd_agcl_warp_nhwc materialises the flow-warped right
- * map (cost_volume.py:57-59) that iter mode's backward re-reads. */
+ * map (cost_volume.py:57-59) that iter mode's backward re-reads.  nnd_agcl_iter_backward_nhwc with d_fmap2 == NULL
+ * computes d_fmap1 only: the reference detaches the warped map (manual_pad, cre_stereo/utils.py:29-31), so its iter
+ * mode trains the left features alone. */
 nnd_status nnd_agcl_warp_nhwc(const float* fmap2_nhwc, const float* flow, int N, int C, int H, int W, float* warped,
                               nnd_stream_t stream);
 nnd_status nnd_agcl_offset_backward_nhwc(const float* fmap1_nhwc, const float* fmap2_nhwc, const float* flow,

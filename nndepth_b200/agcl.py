@@ -40,9 +40,9 @@ class _AGCLIter(torch.autograd.Function):
     re-materialises the flow-warped right map (``nnd_agcl_warp_nhwc``) and runs ``nnd_agcl_iter_backward_nhwc``."""
 
     @staticmethod
-    def forward(ctx, left, right, flow, small_patch):
+    def forward(ctx, left, right, flow, small_patch, detach_warped):
         ctx.save_for_backward(left, right, flow)
-        ctx.small = bool(small_patch)
+        ctx.small, ctx.left_only = bool(small_patch), bool(detach_warped)
         ws = torch.empty_like(right)
         return _lib.ops().agcl_iter(left, right, flow, ctx.small, True, ws)
 
@@ -50,9 +50,12 @@ class _AGCLIter(torch.autograd.Function):
     def backward(ctx, grad_out):
         left, right, flow = ctx.saved_tensors
         warped = _lib.ops().agcl_warp(right, flow)
-        d1, d2, dflow = _lib.ops().agcl_iter_backward(left, right, flow, warped, grad_out.contiguous().float(), ctx.small)
+        d1, d2, dflow = _lib.ops().agcl_iter_backward(left, right, flow, warped, grad_out.contiguous().float(), ctx.small,
+                                                      ctx.left_only)
         need = ctx.needs_input_grad
-        return (d1 if need[0] else None, d2 if need[1] else None, dflow if need[2] else None, None)
+        if ctx.left_only:
+            return (d1 if need[0] else None, None, None, None, None)
+        return (d1 if need[0] else None, d2 if need[1] else None, dflow if need[2] else None, None, None)
 
 
 class AGCL:
@@ -66,6 +69,9 @@ class AGCL:
         if self.fmap1.dim() != 4 or self.fmap1.shape != self.fmap2.shape:
             raise RuntimeError("fmap1 and fmap2 must be (N, C, H, W) of identical shape")
         self.att = att
+        # iter mode: the reference replicate-pads a DETACHED clone of the warped right map (manual_pad, cre_stereo/utils.py:
+        # 29-31), so its gradient reaches the left features only; False differentiates through the warp as well
+        self.detach_warped = True
         self._attended = None
         self._staged = {}       # id(nchw tensor) -> (nchw tensor kept alive, channels-last copy)
         self._warp_ws = None    # workspace of the flow-warped right map (iter mode)
@@ -124,7 +130,8 @@ class AGCL:
         right = right_feature if right_feature is self.fmap2 else _lib.as_cuda_f32(right_feature, "right_feature")
         N, C, H, W = left.shape
         if self._training_call(left, right, flow):
-            return _AGCLIter.apply(self._nhwc_grad(left), self._nhwc_grad(right), self._flow_grad(flow, N, H, W), bool(small_patch))
+            return _AGCLIter.apply(self._nhwc_grad(left), self._nhwc_grad(right), self._flow_grad(flow, N, H, W), bool(small_patch),
+                                   self.detach_warped)
         flow = self._check_flow(flow, N, H, W)
         if self._fast(C) and H >= 2 and W >= 2:
             if self._warp_ws is None or self._warp_ws.shape != (N, H, W, C) or self._warp_ws.device != left.device:

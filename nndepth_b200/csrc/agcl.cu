@@ -905,7 +905,7 @@ agcl_window_backward_kernel(const float* __restrict__ L, const float* __restrict
       const float go = __ldg(dout + (n * AGCL_GROUPS * AGCL_TAPS + (ch / cg) * AGCL_TAPS + k) * hw + p) * inv_cg;
       const float4 r = ldg_f4(Rw + q);
       acc.x += go * r.x; acc.y += go * r.y; acc.z += go * r.z; acc.w += go * r.w;
-      atomic_add4(dRw + q, make_float4(go * l.x, go * l.y, go * l.z, go * l.w));
+      if (dRw) atomic_add4(dRw + q, make_float4(go * l.x, go * l.y, go * l.z, go * l.w));
     }
     *reinterpret_cast<float4*>(dL + pix * C + ch) = acc;
   }
@@ -1088,19 +1088,23 @@ nnd_status nnd_agcl_iter_backward_nhwc(const float* fmap1_nhwc, const float* fma
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   nnd_status st = check_agcl(fmap1_nhwc, fmap2_nhwc, flow, d_fmap1, N, C, H, W, "agcl_iter_backward_nhwc");
   if (st != NND_OK) return st;
-  NND_REQUIRE(warped && grad_out && d_fmap2 && d_warped_ws, "agcl_iter_backward_nhwc: null pointer argument");
+  // d_fmap2 == NULL (then d_warped_ws and d_flow are ignored): the reference's own behaviour -- manual_pad detaches the
+  // warped right map (cre_stereo/utils.py:29-31), so iter mode trains the LEFT features only
+  const bool left_only = d_fmap2 == nullptr;
+  NND_REQUIRE(warped && grad_out && (left_only || d_warped_ws), "agcl_iter_backward_nhwc: null pointer argument");
   NND_REQUIRE(C % 16 == 0, "agcl_iter_backward_nhwc: needs C %% 16 == 0 (got %d)", C);
-  NND_REQUIRE(aligned16(fmap1_nhwc) && aligned16(fmap2_nhwc) && aligned16(warped) && aligned16(d_fmap1) && aligned16(d_fmap2) &&
-                  aligned16(d_warped_ws),
+  NND_REQUIRE(aligned16(fmap1_nhwc) && aligned16(fmap2_nhwc) && aligned16(warped) && aligned16(d_fmap1) &&
+                  (left_only || (aligned16(d_fmap2) && aligned16(d_warped_ws))),
               "agcl_iter_backward_nhwc: maps must be 16-byte aligned");
   const long long n_pix = static_cast<long long>(N) * H * W;
   const long long blocks = (n_pix + 7) / 8;
   NND_REQUIRE(blocks <= 0x7fffffffLL, "agcl_iter_backward_nhwc: too many pixels");
   // d_fmap2 and d_warped_ws are accumulated with atomics: the caller zero-fills both
   agcl_window_backward_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(fmap1_nhwc, warped, grad_out, C, H, W, n_pix,
-                                                                                 small_patch ? 1 : 0, d_fmap1, d_warped_ws);
+                                                                                 small_patch ? 1 : 0, d_fmap1,
+                                                                                 left_only ? nullptr : d_warped_ws);
   st = check_launch("agcl_window_backward_kernel");
-  if (st != NND_OK) return st;
+  if (st != NND_OK || left_only) return st;
   agcl_sample_backward_kernel<1><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
       nullptr, fmap2_nhwc, flow, nullptr, d_warped_ws, C, H, W, n_pix, 0, nullptr, d_fmap2, d_flow, nullptr);
   return check_launch("agcl_sample_backward_kernel<warp>");

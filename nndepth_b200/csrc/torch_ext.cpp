@@ -419,7 +419,7 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> agcl_offset_backward(const Tensor& f1
 
 // returns (d_fmap1, d_fmap2, d_flow); `warped` = agcl_warp(fmap2, flow)
 std::tuple<Tensor, Tensor, Tensor> agcl_iter_backward(const Tensor& f1, const Tensor& f2, const Tensor& flow, const Tensor& warped,
-                                                      const Tensor& grad_out, bool small_patch) {
+                                                      const Tensor& grad_out, bool small_patch, bool left_only) {
   check_cuda(f1, "fmap1"); check_cuda(f2, "fmap2"); check_cuda(flow, "flow"); check_cuda(warped, "warped");
   check_cuda(grad_out, "grad_out");
   auto sf = nchw(flow, "flow");
@@ -430,7 +430,16 @@ std::tuple<Tensor, Tensor, Tensor> agcl_iter_backward(const Tensor& f1, const Te
   TORCH_CHECK(grad_out.dim() == 4 && grad_out.size(0) == N && grad_out.size(1) == 36 && grad_out.size(2) == H && grad_out.size(3) == W,
               "agcl_iter_backward: grad_out must be (N, 36, H, W), got ", grad_out.sizes());
   c10::cuda::CUDAGuard guard(f1.device());
-  Tensor d1 = at::empty_like(f1), d2 = at::zeros_like(f2), dflow = at::empty_like(flow), dws = at::zeros_like(f2);
+  Tensor d1 = at::empty_like(f1);
+  if (left_only) {   // the reference detaches the warped right map: only the left features receive a gradient
+    check_status(nnd_agcl_iter_backward_nhwc(f1.data_ptr<float>(), f2.data_ptr<float>(), flow.data_ptr<float>(),
+                                             warped.data_ptr<float>(), grad_out.data_ptr<float>(), N, f1.size(3), H, W,
+                                             small_patch ? 1 : 0, d1.data_ptr<float>(), nullptr, nullptr, nullptr,
+                                             current_stream(f1)),
+                 "nnd_agcl_iter_backward_nhwc");
+    return {d1, at::empty({0}, f1.options()), at::empty({0}, f1.options())};
+  }
+  Tensor d2 = at::zeros_like(f2), dflow = at::empty_like(flow), dws = at::zeros_like(f2);
   check_status(nnd_agcl_iter_backward_nhwc(f1.data_ptr<float>(), f2.data_ptr<float>(), flow.data_ptr<float>(),
                                            warped.data_ptr<float>(), grad_out.data_ptr<float>(), N, f1.size(3), H, W,
                                            small_patch ? 1 : 0, d1.data_ptr<float>(), d2.data_ptr<float>(),
@@ -506,8 +515,8 @@ TORCH_LIBRARY(nndepth_b200, m) {
   m.def("agcl_warp(Tensor fmap2, Tensor flow) -> Tensor", &agcl_warp);
   m.def("agcl_offset_backward(Tensor fmap1, Tensor fmap2, Tensor flow, Tensor extra_offset, Tensor grad_out, bool small_patch) "
         "-> (Tensor, Tensor, Tensor, Tensor)", &agcl_offset_backward);
-  m.def("agcl_iter_backward(Tensor fmap1, Tensor fmap2, Tensor flow, Tensor warped, Tensor grad_out, bool small_patch) "
-        "-> (Tensor, Tensor, Tensor)", &agcl_iter_backward);
+  m.def("agcl_iter_backward(Tensor fmap1, Tensor fmap2, Tensor flow, Tensor warped, Tensor grad_out, bool small_patch, "
+        "bool left_only) -> (Tensor, Tensor, Tensor)", &agcl_iter_backward);
   m.def("convex_upsample(Tensor flow, Tensor mask, Tensor? mask_bias, int rate, float mask_scale, int mask_layout) -> Tensor",
         &convex_upsample);
 }

@@ -159,12 +159,19 @@ def test_igev_volume_gradients(ref):
 
 
 @pytest.mark.parametrize("small_patch", [False, True])
-@pytest.mark.parametrize("iter_mode", [False, True])
-def test_agcl_gradients(ref, small_patch, iter_mode):
+@pytest.mark.parametrize("iter_mode", [False, True, "through_warp"])
+def test_agcl_gradients(ref, small_patch, iter_mode, monkeypatch):
     """AGCL under grad (both modes, both windows): gradients for both feature maps, the flow and (offset mode) the learned
-    offsets vs autograd through the reference's AGCL / bilinear_grid_sample in float64."""
+    offsets vs autograd through the reference's AGCL / bilinear_grid_sample in float64.  In iter mode the reference pads
+    a DETACHED clone of the warped right map (manual_pad, cre_stereo/utils.py:29-31): only the left features receive a
+    gradient, and so it is here; "through_warp" checks the full backward against the reference with that detach removed."""
     import nndepth_b200 as nb
+    import nndepth.models.cre_stereo.cost_volume as ref_cv
     from nndepth.models.cre_stereo.cost_volume import AGCL as RefAGCL
+    through_warp = iter_mode == "through_warp"
+    iter_mode = bool(iter_mode)
+    if through_warp:
+        monkeypatch.setattr(ref_cv, "manual_pad", lambda x, pady, padx: F.pad(x, (padx, padx, pady, pady), "replicate"))
     N, C, H, W = 2, 32, 7, 11
     torch.manual_seed(3 + int(small_patch) + 2 * int(iter_mode))
     f1 = torch.randn(N, C, H, W, device="cuda", requires_grad=True)
@@ -172,7 +179,9 @@ def test_agcl_gradients(ref, small_patch, iter_mode):
     flow = (torch.randn(N, 2, H, W, device="cuda") * 2).requires_grad_(True)
     extra = (torch.rand(N, 18, H, W, device="cuda") * 2 - 1).requires_grad_(True)
     w_out = torch.randn(N, 36, H, W, device="cuda")
-    out = nb.AGCL(f1, f2)(flow, None if iter_mode else extra, small_patch, iter_mode)
+    blk = nb.AGCL(f1, f2)
+    blk.detach_warped = not through_warp
+    out = blk(flow, None if iter_mode else extra, small_patch, iter_mode)
     loss = (out * w_out).sum()
     loss.backward()
     dd = [t.detach().double().requires_grad_(True) for t in (f1, f2, flow, extra)]
@@ -181,6 +190,10 @@ def test_agcl_gradients(ref, small_patch, iter_mode):
     rloss.backward()
     assert abs(loss.item() - rloss.item()) <= 1e-4 * max(1.0, abs(rloss.item()))
     _close(f1.grad, dd[0].grad)
+    if iter_mode and not through_warp:
+        assert dd[1].grad is None and dd[2].grad is None          # the reference's detach
+        assert f2.grad is None and flow.grad is None
+        return
     _close(f2.grad, dd[1].grad)
     _close(flow.grad, dd[2].grad, tol=1e-3)
     if not iter_mode:
