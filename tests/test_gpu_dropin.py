@@ -325,3 +325,70 @@ def test_headline_mode_against_reference_across_weight_seeds(ref, seed):
               f"mean |disp| {want.abs().mean().item():.1f} px")
         assert got.shape == want.shape == (8, 1, 375, 1242)
         assert per_pair.max().item() < EPE_BAR, (name, per_pair.tolist())
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# training through the reference's forwards: parameter gradients with the swapped classes
+# ------------------------------------------------------------------------------------------------------------------
+def _grad_snapshot(model, loss):
+    model.zero_grad(set_to_none=True)
+    loss.backward()
+    return {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+
+
+def _compare_grads(got, want, tol):
+    assert set(got) == set(want) and len(want) > 10
+    worst = 0.0
+    for name, w in want.items():
+        scale = w.abs().max().item()
+        if scale == 0.0:
+            continue
+        worst = max(worst, (got[name] - w).abs().max().item() / scale)
+    return worst
+
+
+@contextlib.contextmanager
+def strict_fp32_grad():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = False
+    try:
+        yield
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+
+
+def test_training_gradients_through_reference_forwards(ref, monkeypatch):
+    """The trainers differentiate through these forwards (raft_trainer.py:242-259 and its siblings): every parameter's
+    gradient of a sequence-style loss with the swapped correlation classes against the reference's own classes, fp32."""
+    import nndepth_b200 as nb
+    from nndepth.models.raft_stereo.model import BaseRAFTStereo
+    import nndepth.models.cre_stereo.model as cre
+    import nndepth.models.igev_stereo.model as igev
+    left, right = (t.cuda() for t in seeded_images((1, 3, 96, 160), 2))
+
+    def loss_of(outputs):
+        return sum((0.8 ** (len(outputs) - 1 - i)) * o["up_disp"].abs().mean() for i, o in enumerate(outputs))
+
+    report = {}
+    with strict_fp32_grad():
+        torch.manual_seed(0)
+        raft = BaseRAFTStereo(iters=3).eval().cuda()
+        want = _grad_snapshot(raft, loss_of(raft(left, right)))
+        raft.corr_fn = nb.CorrBlock1D
+        report["raft"] = _compare_grads(_grad_snapshot(raft, loss_of(raft(left, right))), want, 1e-3)
+
+        torch.manual_seed(0)
+        model = cre.CREStereoBase(iters=2).eval().cuda()
+        want = _grad_snapshot(model, loss_of(model(left, right)))
+        monkeypatch.setattr(cre, "AGCL", nb.AGCL)
+        report["crestereo"] = _compare_grads(_grad_snapshot(model, loss_of(model(left, right))), want, 1e-3)
+
+        torch.manual_seed(0)
+        model = make_igev(igev)(iters=2).eval().cuda()
+        want = _grad_snapshot(model, loss_of(model(left, right)))
+        model.corr_fn = nb.GeometryAwareCostVolume
+        report["igev"] = _compare_grads(_grad_snapshot(model, loss_of(model(left, right))), want, 1e-3)
+    print("\nworst relative parameter-gradient difference, swapped vs reference classes:",
+          {k: f"{v:.1e}" for k, v in report.items()})
+    assert all(v < 1e-3 for v in report.values()), report
