@@ -338,12 +338,16 @@ def _grad_snapshot(model, loss):
 
 def _compare_grads(got, want, tol):
     assert set(got) == set(want) and len(want) > 10
-    worst = 0.0
+    # relative to the parameter's own gradient scale, floored at 1e-4 of the largest gradient in the model (a parameter
+    # whose true gradient is rounding noise has no meaningful relative error)
+    floor = 1e-4 * max(w.abs().max().item() for w in want.values())
+    worst, worst_name = 0.0, None
     for name, w in want.items():
-        scale = w.abs().max().item()
-        if scale == 0.0:
-            continue
-        worst = max(worst, (got[name] - w).abs().max().item() / scale)
+        err = (got[name] - w).abs().max().item() / max(w.abs().max().item(), floor)
+        if err > worst:
+            worst, worst_name = err, name
+    if worst >= tol:
+        print(f"worst parameter: {worst_name} ({worst:.2e}); scale {want[worst_name].abs().max().item():.2e}, floor {floor:.2e}")
     return worst
 
 
