@@ -115,6 +115,16 @@ nnd_status nnd_corr1d_lookup_backward(const float* grad_out, const float* coords
 nnd_status nnd_avgpool_pairs_backward(const float* d_dst, int dst_width, int dst_pitch, float* d_src, int src_pitch,
                                       int64_t rows, nnd_stream_t stream);
 
+/* Backward of the volume builds for the trainers (raft_trainer.py:242-259): the gradient of pyramid level 0 (rows
+ * (b, g, h, w1) of `pitch` floats; g = 0 only for CorrBlock1D) contracted with the other feature map,
+ *   which 0: d_fmap1[b,c,h,i] = 1/scale_div * sum_j dV[(b,g,h,i), j] * fmap2[b,c,h,j]      (f_other = fmap2)
+ *   which 1: d_fmap2[b,c,h,j] = 1/scale_div * sum_i dV[(b,g,h,i), j] * fmap1[b,c,h,i]      (f_other = fmap1)
+ * for c in group g = c / group_size -- the transpose of CorrBlock1D.corr / build_cost_volume
+ * (raft_stereo/cost_volume.py:55-61, :113-128; igev_stereo/cost_volume.py:81-98).  Channels beyond
+ * num_groups * group_size are not written (zero-fill d_fmap when they exist). */
+nnd_status nnd_volume_grad(const float* d_level0, int pitch, const float* f_other, int B, int C, int H, int W1, int W2,
+                           int num_groups, int group_size, float scale_div, int which, float* d_fmap, nnd_stream_t stream);
+
 /* Debug/parity twin of the lookup: writes the int32 window indices instead of values.
  *   idx0, idx1: (num_levels, B*H*W1, 2r+1) int32. */
 nnd_status nnd_corr1d_lookup_indices(const int* width, const float* coords, int B, int H, int W1,

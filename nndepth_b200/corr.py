@@ -9,8 +9,8 @@ kernels (``raft_stereo/model.py:58,124,132``).
 Differences by design: one launch builds the volume *and* its pooled levels; one launch per GRU
 iteration does the whole 4-level lookup; rows of the pyramid are padded to 16 bytes (``corr_pyramid``
 hides the padding).  ``CorrBlock1D`` is differentiable with respect to the feature maps (the coordinates are
-detached by the reference before every lookup, ``raft_stereo/model.py:131``): the lookup backward and the pooling
-backward are kernels of this package, the two volume-gradient contractions are cuBLAS GEMMs.  ``GroupCorrBlock1D`` and
+detached by the reference before every lookup, ``raft_stereo/model.py:131``): the lookup backward, the pooling
+backward and the two volume-gradient contractions (``nnd_volume_grad``) are kernels of this package.  ``GroupCorrBlock1D`` and
 the IGEV volume (``igev.py``) are differentiable the same way (grouped contraction, lookup backward per group).
 """
 import math
@@ -144,7 +144,7 @@ class PyramidStorage:
 
 class _BuildPyramid(torch.autograd.Function):
     """Differentiable pyramid build: forward = ``nnd_corr1d_build``; backward = un-pool the level gradients
-    (``nnd_avgpool_pairs_backward``) and contract ``d_volume`` with the other feature map (cuBLAS)."""
+    (``nnd_avgpool_pairs_backward``) and contract ``d_volume`` with the other feature map (``nnd_volume_grad``)."""
 
     @staticmethod
     def forward(ctx, f1, f2, num_levels, prec_code):
@@ -162,9 +162,8 @@ class _BuildPyramid(torch.autograd.Function):
         B, C, H, W1, W2, L = ctx.geom
         d = PyramidStorage(B * H * W1, W2, L, f1.device, buffer=d_buffer.contiguous().clone())
         _lib.ops().pyramid_unpool_(d.buffer, d.rows, W2, L)     # avg_pool1d backward, coarsest level first
-        d_vol = d.levels[0][:, :W2].reshape(B, H, W1, W2) / math.sqrt(C)
-        d_f1 = torch.einsum("bhij,bchj->bchi", d_vol, f2) if ctx.needs_input_grad[0] else None
-        d_f2 = torch.einsum("bhij,bchi->bchj", d_vol, f1) if ctx.needs_input_grad[1] else None
+        d_f1 = _lib.ops().volume_grad(d.buffer, f2, W1, W2, 1, C, math.sqrt(C), 0) if ctx.needs_input_grad[0] else None
+        d_f2 = _lib.ops().volume_grad(d.buffer, f1, W1, W2, 1, C, math.sqrt(C), 1) if ctx.needs_input_grad[1] else None
         return d_f1, d_f2, None, None
 
 
@@ -218,17 +217,8 @@ class _GroupedBuild(torch.autograd.Function):
         B, C, H, W1, W2, G, gs, scale_div, L = ctx.geom
         d = PyramidStorage(B * G * H * W1, W2, L, f1.device, buffer=d_buffer.contiguous().clone())
         _lib.ops().pyramid_unpool_(d.buffer, d.rows, W2, L)
-        d_vol = d.levels[0][:, :W2].reshape(B, G, H, W1, W2) / scale_div
-        used = G * gs
-        f1g = f1[:, :used].reshape(B, G, gs, H, W1)
-        f2g = f2[:, :used].reshape(B, G, gs, H, W2)
-        d_f1 = d_f2 = None
-        if ctx.needs_input_grad[0]:
-            d_f1 = torch.zeros_like(f1)
-            d_f1[:, :used] = torch.einsum("bghij,bgchj->bgchi", d_vol, f2g).reshape(B, used, H, W1)
-        if ctx.needs_input_grad[1]:
-            d_f2 = torch.zeros_like(f2)
-            d_f2[:, :used] = torch.einsum("bghij,bgchi->bgchj", d_vol, f1g).reshape(B, used, H, W2)
+        d_f1 = _lib.ops().volume_grad(d.buffer, f2, W1, W2, G, gs, scale_div, 0) if ctx.needs_input_grad[0] else None
+        d_f2 = _lib.ops().volume_grad(d.buffer, f1, W1, W2, G, gs, scale_div, 1) if ctx.needs_input_grad[1] else None
         return d_f1, d_f2, None, None, None, None
 
 

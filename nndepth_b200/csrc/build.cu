@@ -305,6 +305,72 @@ nnd_status pool_tail(const Pyramid& pyr, int num_levels, long long rows, cudaStr
   return NND_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward of the volume builds (training): the gradient of level 0, contracted with the OTHER feature map.
+//   which = 0:  d_f1[b, c, h, i] = 1/scale * sum_j dV[(b, g, h, i), j] * f2[b, c, h, j]
+//   which = 1:  d_f2[b, c, h, j] = 1/scale * sum_i dV[(b, g, h, i), j] * f1[b, c, h, i]
+// for c in group g = c / group_size (CorrBlock1D: one group of C channels).  Volume rows are (b, g, h, i) with `pitch`
+// floats each.  Plain fp32 FFMA GEMM tiles (64 channels x 64 positions, k-step 16) through shared memory: the forward's
+// precision class in fp32 mode, and exact enough (1e-6) to serve the tensor-core forward's backward as well.
+// ------------------------------------------------------------------------------------------------
+template <int WHICH>
+__global__ void __launch_bounds__(256)
+volume_grad_kernel(const float* __restrict__ dvol, int pitch, const float* __restrict__ fother, int C, int H, int W1, int W2,
+                   int G, int group_size, float inv_scale, float* __restrict__ dout) {
+  constexpr int TM = 64, TN = 64, TK = 16;
+  __shared__ float As[TK][TM + 1];   // [k][channel]
+  __shared__ float Bs[TK][TN + 1];   // [k][position]
+  const int bgh = blockIdx.z;                 // (b * G + g) * H + h
+  const int h = bgh % H, bg = bgh / H, g = bg % G, b = bg / G;
+  const int c0 = blockIdx.y * TM;             // channel within the group
+  const int n0 = blockIdx.x * TN;             // output position (i for WHICH 0, j for WHICH 1)
+  const int Wout = WHICH == 0 ? W1 : W2, Wk = WHICH == 0 ? W2 : W1;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;   // 16 x 16 threads, 4 x 4 outputs each
+  const long long fo_base = ((static_cast<long long>(b) * C + g * group_size) * H + h) * Wk;        // + c * H * Wk + k
+  const long long dv_base = (static_cast<long long>(bg) * H + h) * W1 * static_cast<long long>(pitch);  // + i * pitch + j
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < Wk; k0 += TK) {
+    // A tile: fother[c0 + m][k0 + k]  (k contiguous)
+    for (int e = tid; e < TM * TK; e += 256) {
+      const int m = e / TK, k = e % TK;
+      const int c = c0 + m, kk = k0 + k;
+      As[k][m] = (c < group_size && kk < Wk) ? __ldg(fother + fo_base + static_cast<long long>(c) * H * Wk + kk) : 0.f;
+    }
+    // B tile: WHICH 0: dV[i = n0 + n][j = k0 + k] (k contiguous);  WHICH 1: dV[i = k0 + k][j = n0 + n] (n contiguous)
+    for (int e = tid; e < TN * TK; e += 256) {
+      int n, k;
+      if (WHICH == 0) { n = e / TK; k = e % TK; } else { k = e / TN; n = e % TN; }
+      const int nn = n0 + n, kk = k0 + k;
+      const int i = WHICH == 0 ? nn : kk, j = WHICH == 0 ? kk : nn;
+      Bs[k][n] = (nn < Wout && kk < Wk) ? __ldg(dvol + dv_base + static_cast<long long>(i) * pitch + j) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      float a[4], bb[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) { a[r] = As[k][ty * 4 + r]; bb[r] = Bs[k][tx * 4 + r]; }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[r][q] = fmaf(a[r], bb[q], acc[r][q]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int c = c0 + ty * 4 + r;
+    if (c >= group_size) continue;
+    float* orow = dout + ((static_cast<long long>(b) * C + g * group_size + c) * H + h) * Wout;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int nn = n0 + tx * 4 + q;
+      if (nn < Wout) orow[nn] = acc[r][q] * inv_scale;
+    }
+  }
+}
+
+
 }  // namespace nnd
 
 extern "C" {
@@ -409,6 +475,28 @@ nnd_status nnd_avgpool_pairs(const float* src, int src_width, int src_pitch, flo
   avgpool_pairs_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, src_pitch, dst, dst_width,
                                                                                    dst_pitch, rows);
   return check_launch("avgpool_pairs_kernel");
+}
+
+nnd_status nnd_volume_grad(const float* d_level0, int pitch, const float* f_other, int B, int C, int H, int W1, int W2,
+                           int num_groups, int group_size, float scale_div, int which, float* d_fmap, nnd_stream_t stream) {
+  using namespace nnd;
+  NND_REQUIRE(d_level0 && f_other && d_fmap, "volume_grad: null pointer argument");
+  NND_REQUIRE(B > 0 && C > 0 && H > 0 && W1 > 0 && W2 > 0, "volume_grad: B, C, H, W1, W2 must be positive");
+  NND_REQUIRE(num_groups > 0 && group_size > 0 && static_cast<long long>(num_groups) * group_size <= C,
+              "volume_grad: num_groups * group_size exceeds C");
+  NND_REQUIRE(pitch >= W2, "volume_grad: pitch %d smaller than W2 %d", pitch, W2);
+  NND_REQUIRE(scale_div > 0.f && (which == 0 || which == 1), "volume_grad: scale_div must be positive, which 0 or 1");
+  const long long z = static_cast<long long>(B) * num_groups * H;
+  NND_REQUIRE(z <= 65535, "volume_grad: B * G * H = %lld exceeds the grid limit (65535)", z);
+  const int Wout = which == 0 ? W1 : W2;
+  dim3 grid((Wout + 63) / 64, (group_size + 63) / 64, static_cast<unsigned>(z));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // channels beyond num_groups * group_size receive no gradient: the caller zero-fills d_fmap when they exist
+  if (which == 0)
+    volume_grad_kernel<0><<<grid, 256, 0, st>>>(d_level0, pitch, f_other, C, H, W1, W2, num_groups, group_size, 1.0f / scale_div, d_fmap);
+  else
+    volume_grad_kernel<1><<<grid, 256, 0, st>>>(d_level0, pitch, f_other, C, H, W1, W2, num_groups, group_size, 1.0f / scale_div, d_fmap);
+  return check_launch("volume_grad_kernel");
 }
 
 }  // extern "C"

@@ -202,6 +202,26 @@ void pyramid_unpool_(Tensor d_pyramid, int64_t rows, int64_t width0, int64_t num
                  "nnd_avgpool_pairs_backward");
 }
 
+// d_fmap of one side of the build (which 0: fmap1, 1: fmap2) from the un-pooled pyramid-gradient buffer (its level 0)
+Tensor volume_grad(const Tensor& d_pyramid, const Tensor& f_other, int64_t W1, int64_t W2, int64_t num_groups, int64_t group_size,
+                   double scale_div, int64_t which) {
+  check_cuda(d_pyramid, "d_pyramid"); check_cuda(f_other, "f_other");
+  same_device(d_pyramid, f_other, "volume_grad");
+  auto s = nchw(f_other, "f_other");
+  const int64_t B = s[0], C = s[1], H = s[2];
+  TORCH_CHECK(s[3] == (which == 0 ? W2 : W1), "volume_grad: f_other has width ", s[3], ", expected ", (which == 0 ? W2 : W1));
+  const int pitch = nnd_row_pitch(static_cast<int>(W2));
+  TORCH_CHECK(d_pyramid.numel() >= B * num_groups * H * W1 * pitch, "volume_grad: gradient buffer smaller than level 0");
+  c10::cuda::CUDAGuard guard(f_other.device());
+  const bool partial = num_groups * group_size < C;
+  Tensor out = partial ? at::zeros({B, C, H, which == 0 ? W1 : W2}, f_other.options())
+                       : at::empty({B, C, H, which == 0 ? W1 : W2}, f_other.options());
+  check_status(nnd_volume_grad(d_pyramid.data_ptr<float>(), pitch, f_other.data_ptr<float>(), B, C, H, W1, W2, num_groups,
+                               group_size, static_cast<float>(scale_div), which, out.data_ptr<float>(), current_stream(f_other)),
+               "nnd_volume_grad");
+  return out;
+}
+
 std::tuple<Tensor, Tensor> corr1d_lookup_indices(at::IntArrayRef widths, const Tensor& coords, int64_t num_levels,
                                                  int64_t radius) {
   check_cuda(coords, "coords");
@@ -497,6 +517,8 @@ TORCH_LIBRARY(nndepth_b200, m) {
   m.def("corr1d_lookup_backward(Tensor grad_out, Tensor coords, int width0, int num_levels, int radius) -> Tensor",
         &corr1d_lookup_backward);
   m.def("pyramid_unpool_(Tensor(a!) d_pyramid, int rows, int width0, int num_levels) -> ()", &pyramid_unpool_);
+  m.def("volume_grad(Tensor d_pyramid, Tensor f_other, int W1, int W2, int num_groups, int group_size, float scale_div, int which) "
+        "-> Tensor", &volume_grad);
   m.def("corr1d_lookup_indices(int[] widths, Tensor coords, int num_levels, int radius) -> (Tensor, Tensor)",
         &corr1d_lookup_indices);
   m.def("group_lookup(Tensor pyramid_a, Tensor? pyramid_b, int width0, Tensor coords, int num_groups, int num_levels, int radius, "
