@@ -474,7 +474,7 @@ class SepConvGRU(nn.Module):
 
     # ---- weight-split TF32: conv(x, w) ~ conv(RN(x), w_hi) + conv(RN(x), w_lo) as ONE conv with doubled outputs ----
     # The recurrence tolerates TF32-rounded ACTIVATIONS (fresh rounding noise every iteration) but not TF32
-    # WEIGHTS (the same perturbation 32 times): tools/exp_epe_2term.py, csrc/gru_fused.cu.
+    # WEIGHTS (the same perturbation 32 times): csrc/gru_fused.cu.
     @staticmethod
     def _rn_tf32(t):
         return ((t.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
@@ -818,7 +818,7 @@ class RAFTStereo(nn.Module):
         self.final_only = False     # True: upsample only the last iteration (what evaluate.py:155 consumes)
         self.fuse_motion_front = True   # lookup + convc1 + ReLU as one kernel when corr_fn provides it
         self.fuse_gru = True            # weight-split ConvGRU on the fused channels-last kernels (mode "mixed2x")
-        # Precision of the dense (cuDNN) layers, measured on the KITTI/32-iteration golden (tools/exp_epe_modules.py):
+        # Precision of the dense (cuDNN) layers, measured on the KITTI/32-iteration golden (profiles/r2_exp_modules.jsonl):
         #   "fp32"  every convolution in fp32                           final EPE vs reference 0.0002 px
         #   "mixed" ConvGRU in fp32, everything else on TF32 tensor cores              0.0021 px  (bar: 0.01 px)
         #   "mixed2x" as "mixed", the ConvGRU with TF32 activations x split fp32 weights [w_hi; w_lo] on tensor
