@@ -123,6 +123,25 @@ def test_reference_raft_cpu_vs_swapped_gpu(ref):
     assert epe(got, want) < 1e-3
 
 
+def test_reference_repvit_raft_forward_with_swapped_group_corr_fn(ref):
+    """``Coarse2FineGroupRepViTRAFTStereo`` (raft_stereo/model.py:166-320): three coarse-to-fine stages, each with its own
+    ``GroupCorrBlock1D`` (num_groups 4, one level) -- the reference's own test shape, 384x512."""
+    import nndepth_b200 as nb
+    from nndepth.models.raft_stereo.model import Coarse2FineGroupRepViTRAFTStereo
+    torch.manual_seed(0)
+    model = Coarse2FineGroupRepViTRAFTStereo(corr_levels=1, iters=4).eval().cuda()
+    left, right = (t.cuda() for t in seeded_images((2, 3, 384, 512), 4))
+    with strict_fp32():
+        want = model(left, right)
+        model.corr_fn = nb.GroupCorrBlock1D             # <- the whole integration patch (model.py:219)
+        got = model(left, right)
+    assert len(got) == len(want)
+    errs = [epe(g["up_disp"], w["up_disp"]) for g, w in zip(got, want)]
+    print(f"\nreference RepViT coarse-to-fine RAFT forward, corr_fn swapped: {len(got)} outputs, final EPE {errs[-1]:.2e} px, "
+          f"worst {max(errs):.2e} px")
+    assert max(errs) < EPE_BAR, errs
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # CREStereo: BASELINE configs[2], the whole cascade
 # ------------------------------------------------------------------------------------------------------------------
