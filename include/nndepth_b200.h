@@ -102,6 +102,21 @@ nnd_status nnd_corr1d_lookup_conv1x1(const float* const* level, const int* width
                                      const float* weight, const float* bias, int c_out, int relu, int precision,
                                      int out_layout, void* out, nnd_stream_t stream);
 
+/* Skewed copy of a CorrBlock1D pyramid and the fused lookup on it (private layout of this library; the reference's
+ * volume is all-pairs (B,H,W1,W2), raft_stereo/cost_volume.py:55-61).  For every epipolar row (b, h), level l is stored
+ * as a (W2_l x skew_pitch) matrix S[j][w1] = V_l[(b,h,w1)][w2] with j = ((w1 >> l) - w2) mod W2_l: the windows of
+ * neighbouring pixels with similar disparity then share cache lines (a warp's 32 windows are ~12 rows of 128 contiguous
+ * bytes), which removes the 64-byte-granule read amplification of one 40-byte window per 624-byte volume row.
+ * skewed[l] needs B*H*width[l]*skew_pitch floats, skew_pitch >= W1 and a multiple of 4.
+ * nnd_corr1d_lookup_conv1x1_skewed == nnd_corr1d_lookup_conv1x1 (TF32 operands, 4 levels, radius 4, c_out 256,
+ * channels-last output: out_layout 1 = fp32, 2 = fp16) reading the skewed copy; results are bit-identical. */
+nnd_status nnd_corr1d_skew(const float* const* level, const int* width, const int* pitch, int B, int H, int W1,
+                           int num_levels, float* const* skewed, int skew_pitch, nnd_stream_t stream);
+nnd_status nnd_corr1d_lookup_conv1x1_skewed(const float* const* skewed, const int* width, int skew_pitch,
+                                            const float* coords, int B, int H, int W1, int num_levels, int radius,
+                                            const float* weight, const float* bias, int c_out, int relu, int out_layout,
+                                            void* out, nnd_stream_t stream);
+
 /* Backward passes for training (the reference path is differentiable; trainers: raft_trainer.py:242-259).
  *   nnd_corr1d_lookup_backward: gradient of the lookup w.r.t. the pyramid.  grad_out (B, L*(2r+1), H, W1);
  *     d_level[l] (rows = B*H*W1, pitch[l]) must be zero-initialised: each row receives its <= 2r+3 window

@@ -328,8 +328,17 @@ class CorrBlock1D:
         weight = _lib.as_cuda_f32(weight, "weight")
         return weight.reshape(weight.shape[0], -1).t().contiguous()
 
+    def skewed_pyramid(self):
+        """The skewed copy of the pyramid (``nnd_corr1d_skew``), built on first use: level ``l`` of an epipolar row is
+        stored as ``S[j][w1]`` with ``j = ((w1 >> l) - w2) mod W2_l``, so the windows of neighbouring pixels with similar
+        disparity share cache lines.  Read by ``lookup_conv1x1(..., skewed=True)``."""
+        if getattr(self, "_skew", None) is None:
+            B, H, W1, W2 = self._shape
+            self._skew = _lib.ops().corr1d_skew(self._pyr.buffer, B, H, W1, W2, self.num_levels)
+        return self._skew
+
     def lookup_conv1x1(self, coords, weight, bias=None, relu=True, weight_t=None, precision="fp32", channels_last=False,
-                       half=False):
+                       half=False, skewed=False):
         """``relu(conv1x1(self(coords)))`` in one launch; the ``(B, L*(2r+1), H, W)`` lookup never reaches HBM.
 
         Fuses the lookup with the motion encoder's first layer (reference ``blocks/update_block.py:51,58``:
@@ -360,6 +369,10 @@ class CorrBlock1D:
             if half:
                 raise ValueError("fp16 output needs c_out <= 256 (tensor-core path)")
             channels_last = False
+        if skewed and channels_last and c_out == 256 and precision == "tf32" and self.num_levels == 4 and self.radius == 4:
+            # same kernel, same bits, windows gathered from the skewed copy (smooth disparity fields: ~3x fewer DRAM bytes)
+            return _lib.ops().corr1d_lookup_conv1x1_skewed(self.skewed_pyramid(), self._shape[3], coords, self.num_levels,
+                                                           self.radius, weight, bias, bool(relu), 2 if half else 1)
         # channels-last results come back with NCHW shape and channels-last strides ((B, H, W, c_out) in memory)
         return _lib.ops().corr1d_lookup_conv1x1(self._pyr.buffer, self._shape[3], coords, self.num_levels, self.radius,
                                                 weight, bias, bool(relu),

@@ -944,7 +944,9 @@ static nnd_status launch_lookup(const float* const* level_a, const float* const*
 
 namespace nnd {
 nnd_status launch_lookup_conv1x1_ws(const LookupArgs& a, const float* weight, const float* bias, int relu, int out_f16,
-                                    long long total_px, cudaStream_t stream);
+                                    long long total_px, int skew_w1, cudaStream_t stream);
+nnd_status launch_corr1d_skew(const ConstPyramid& src, int num_levels, int B, int H, int W1, float* const* dst, int P1,
+                              cudaStream_t stream);
 }
 
 extern "C" {
@@ -1061,7 +1063,7 @@ nnd_status nnd_corr1d_lookup_conv1x1(const float* const* level, const int* width
     // the shipping shape: warp-specialised tcgen05 kernel (lookup_ws.cu) -- weights in shared memory, accumulators in
     // TMEM, producer / MMA / epilogue warps decoupled by mbarrier pipelines
     return launch_lookup_conv1x1_ws(a, weight, bias, relu ? 1 : 0, out_layout == 2 ? 1 : 0,
-                                    static_cast<long long>(B) * a.hw, reinterpret_cast<cudaStream_t>(stream));
+                                    static_cast<long long>(B) * a.hw, 0, reinterpret_cast<cudaStream_t>(stream));
   }
   if (precision == NND_PREC_TF32 && c_out <= 256) {
     // tensor-core path: weights live in registers, shared memory holds only the lookup tiles
@@ -1130,6 +1132,55 @@ nnd_status nnd_avgpool_pairs_backward(const float* d_dst, int dst_width, int dst
   avgpool_pairs_backward_kernel<<<static_cast<unsigned>(want < cap ? want : cap), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       d_dst, dst_width, dst_pitch, d_src, src_pitch, rows);
   return check_launch("avgpool_pairs_backward_kernel");
+}
+
+nnd_status nnd_corr1d_skew(const float* const* level, const int* width, const int* pitch, int B, int H, int W1, int num_levels,
+                           float* const* skewed, int skew_pitch, nnd_stream_t stream) {
+  using namespace nnd;
+  NND_REQUIRE(level && width && pitch && skewed, "corr1d_skew: null pointer argument");
+  NND_REQUIRE(B > 0 && H > 0 && W1 > 0, "corr1d_skew: B, H, W1 must be positive");
+  NND_REQUIRE(num_levels >= 1 && num_levels <= NND_MAX_LEVELS, "corr1d_skew: num_levels %d outside [1, %d]", num_levels, NND_MAX_LEVELS);
+  NND_REQUIRE(skew_pitch >= W1, "corr1d_skew: skew_pitch %d smaller than W1 %d", skew_pitch, W1);
+  ConstPyramid src;
+  memset(&src, 0, sizeof(src));
+  for (int l = 0; l < num_levels; ++l) {
+    NND_REQUIRE(level[l] && skewed[l] && width[l] >= 1 && pitch[l] >= width[l], "corr1d_skew: level %d invalid", l);
+    src.ptr[l] = level[l];
+    src.width[l] = width[l];
+    src.pitch[l] = pitch[l];
+  }
+  return launch_corr1d_skew(src, num_levels, B, H, W1, skewed, skew_pitch, reinterpret_cast<cudaStream_t>(stream));
+}
+
+nnd_status nnd_corr1d_lookup_conv1x1_skewed(const float* const* skewed, const int* width, int skew_pitch, const float* coords,
+                                            int B, int H, int W1, int num_levels, int radius, const float* weight,
+                                            const float* bias, int c_out, int relu, int out_layout, void* out,
+                                            nnd_stream_t stream) {
+  using namespace nnd;
+  NND_REQUIRE(skewed && width && coords && weight && out, "lookup_conv1x1_skewed: null pointer argument");
+  NND_REQUIRE(B > 0 && H > 0 && W1 > 0, "lookup_conv1x1_skewed: B, H, W1 must be positive");
+  NND_REQUIRE(radius == 4 && num_levels == 4 && c_out == 256, "lookup_conv1x1_skewed: built for 4 levels, radius 4, 256 outputs");
+  NND_REQUIRE(out_layout == 1 || out_layout == 2, "lookup_conv1x1_skewed: out_layout must be 1 (fp32) or 2 (fp16), channels-last");
+  NND_REQUIRE(skew_pitch >= W1, "lookup_conv1x1_skewed: skew_pitch %d smaller than W1 %d", skew_pitch, W1);
+  NND_REQUIRE(static_cast<long long>(H) * W1 < (1LL << 30), "lookup_conv1x1_skewed: H*W1 too large");
+  LookupArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int l = 0; l < num_levels; ++l) {
+    NND_REQUIRE(width[l] >= 2 && skewed[l], "lookup_conv1x1_skewed: level %d invalid (linear_sampler needs width >= 2)", l);
+    a.src[0].ptr[l] = skewed[l];
+    a.src[0].width[l] = width[l];
+    a.src[0].pitch[l] = skew_pitch;
+  }
+  a.coords = coords;
+  a.out = reinterpret_cast<float*>(out);
+  a.hw = H * W1;
+  a.G = 1;
+  a.n_src = 1;
+  a.num_levels = num_levels;
+  a.radius = radius;
+  a.vec = 1;
+  return launch_lookup_conv1x1_ws(a, weight, bias, relu ? 1 : 0, out_layout == 2 ? 1 : 0, static_cast<long long>(B) * a.hw, W1,
+                                  reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

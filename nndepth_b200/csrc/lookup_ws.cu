@@ -85,11 +85,15 @@ __device__ __forceinline__ uint32_t chunk_offset(int r, int ch, int kstep_bytes)
 }  // namespace ws
 
 // out: channels-last (B*H*W, 256), fp16 (OUT_F16) or fp32.  weight: (36, 256) k-major fp32.
-template <bool OUT_F16>
+// SKEW: the pyramid is read from its SKEWED copy (corr1d_skew_kernel below): level l of an epipolar row (b, h) is stored
+// as S[j][w1] with j = ((w1 >> l) - w2) mod W2_l, so the windows of neighbouring pixels with similar disparity lie in the
+// SAME rows at neighbouring columns -- a warp's 32 windows are ~12 rows of 128 contiguous bytes instead of 32 separate
+// 40-byte pieces in 32 volume rows (a 64-byte DRAM granule or two each).  a.src[0].pitch[l] is then the w1 pitch.
+template <bool OUT_F16, bool SKEW>
 __global__ void __launch_bounds__(ws::THREADS, 1)
 corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const __grid_constant__ CUtensorMap out_map,
                                 const float* __restrict__ weight, const float* __restrict__ bias, int relu,
-                                long long total_px, long long px_per_cta) {
+                                long long total_px, long long px_per_cta, int row_w1) {
   using namespace ws;
   using umma::smem_u32;
   using umma::mbar_init;
@@ -171,8 +175,31 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const __gr
       const long long px = px0 + static_cast<long long>(t) * TILE + m;
       return (t < nt && px < px_end) ? __ldg(a.coords + px) : 0.0f;
     };
+    constexpr int SKSTRIDE = 13;                         // skewed mode: 11 window floats per pixel, odd stride
     auto issue_windows = [&](int t, float c, float* win) {
-      if (t < nt) {
+      if (t < nt && SKEW) {
+        const float centre = __fmul_rn(c, inv_pow2);
+        const int lo = make_tap(0, R, centre, sc).i0;
+        const int hi = make_tap(TAPS - 1, R, centre, sc).i1;
+        const long long px = px0 + static_cast<long long>(t) * TILE + m;
+        if (px < px_end) {
+          const long long bh = px / row_w1;
+          const int w1 = static_cast<int>(px - bh * row_w1);
+          const float* colp = lbase + bh * w * static_cast<long long>(pitch) + w1;   // row j = 0 of my epipolar row, my column
+          int jr = ((w1 >> lvl) - lo) % w;               // row of window element 0; element i sits i rows above (mod w)
+          if (jr < 0) jr += w;
+          const uint32_t dst = smem_u32(win + lane * SKSTRIDE);
+#pragma unroll
+          for (int i = 0; i < 11; ++i) {
+#ifndef NND_WS_SKIP_GATHER
+            if (lo + i <= hi && lo + i < w)
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * i), "l"(colp + static_cast<long long>(jr) * pitch)
+                           : "memory");
+#endif
+            jr = jr == 0 ? w - 1 : jr - 1;
+          }
+        }
+      } else if (t < nt) {
         const float centre = __fmul_rn(c, inv_pow2);
         const int s = make_tap(0, R, centre, sc).i0 & ~3;
         const int hi = make_tap(TAPS - 1, R, centre, sc).i1;
@@ -211,8 +238,8 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const __gr
         const long long px = px0 + static_cast<long long>(t) * TILE + m;
         const bool live = px < px_end;
         const float centre = __fmul_rn(c0, inv_pow2);
-        const int s = make_tap(0, R, centre, sc).i0 & ~3;
-        const float* mine = wins + (t & 1) * WIN_BUF_FLOATS + lane * WSTRIDE - s;
+        const int s = SKEW ? make_tap(0, R, centre, sc).i0 : (make_tap(0, R, centre, sc).i0 & ~3);
+        const float* mine = wins + (t & 1) * WIN_BUF_FLOATS + lane * (SKEW ? SKSTRIDE : WSTRIDE) - s;
         uint32_t v[12];
 #pragma unroll
         for (int k = 0; k < TAPS; ++k) {
@@ -383,10 +410,77 @@ EncodeTiledFn encode_tiled() {
 }
 }  // namespace
 
-// host-side launcher, called by nnd_corr1d_lookup_conv1x1 (lookup.cu) for the shipping shape:
+// ------------------------------------------------------------------------------------------------
+// Skewed copy of a CorrBlock1D pyramid for the kernel above.  Source: level l rows (b, h, w1) of `pitch_l` floats
+// (raft_stereo/cost_volume.py:29-34).  Destination: for every epipolar row (b, h) a (W2_l x P1) matrix
+//     S_l[(b, h)][j][w1] = V_l[(b, h, w1)][w2],   j = ((w1 >> l) - w2) mod W2_l,   P1 = roundup4(W1).
+// Block = 32 consecutive w1 of one (b, h) and level: their volume rows are staged in shared memory with coalesced
+// loads, then every warp writes rows j as 128-byte segments.
+// ------------------------------------------------------------------------------------------------
+struct SkewArgs {
+  ConstPyramid src;
+  float* dst[NND_MAX_LEVELS];
+  int W1, P1;
+};
+
+__global__ void __launch_bounds__(256)
+corr1d_skew_kernel(const __grid_constant__ SkewArgs a) {
+  extern __shared__ float rows[];                    // [32][WP]
+  const int l = blockIdx.z;
+  const int w = a.src.width[l], pitch = a.src.pitch[l];
+  const int WP = l == 0 ? ((w + 1) & ~1) : (w | 1);  // the read below strides WP + 2^-l banks per lane: keep that odd
+  const long long bh = blockIdx.y;
+  const int w1_0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* __restrict__ src = a.src.ptr[l] + (bh * a.W1 + w1_0) * pitch;
+  for (int r = warp; r < 32; r += 8) {
+    if (w1_0 + r >= a.W1) break;
+    for (int c = lane; c < w; c += 32) rows[r * WP + c] = __ldg(src + static_cast<long long>(r) * pitch + c);
+  }
+  __syncthreads();
+  const int w1 = w1_0 + lane;
+  if (w1 >= a.W1) return;
+  float* __restrict__ dst = a.dst[l] + bh * w * static_cast<long long>(a.P1) + w1;
+  const int top = w1 >> l;
+  for (int j = warp; j < w; j += 8) {
+    int w2 = (top - j) % w;
+    if (w2 < 0) w2 += w;
+    dst[static_cast<long long>(j) * a.P1] = rows[lane * WP + w2];
+  }
+}
+
+nnd_status launch_corr1d_skew(const ConstPyramid& src, int num_levels, int B, int H, int W1, float* const* dst, int P1,
+                              cudaStream_t stream) {
+  SkewArgs a;
+  memset(&a, 0, sizeof(a));
+  a.src = src;
+  a.W1 = W1;
+  a.P1 = P1;
+  int wmax = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    a.dst[l] = dst[l];
+    wmax = src.width[l] > wmax ? src.width[l] : wmax;
+  }
+  const size_t smem = static_cast<size_t>(32) * (wmax + 2) * sizeof(float);
+  if (smem > 200 * 1024) {
+    set_error("corr1d_skew: volume rows of %d floats do not fit shared memory", wmax);
+    return NND_ERR_UNSUPPORTED;
+  }
+  if (smem > 48 * 1024) cudaFuncSetAttribute(corr1d_skew_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  const long long bh = static_cast<long long>(B) * H;
+  if (bh > 65535) {
+    set_error("corr1d_skew: B*H = %lld exceeds the grid limit (65535)", bh);
+    return NND_ERR_INVALID_ARGUMENT;
+  }
+  dim3 grid((W1 + 31) / 32, static_cast<unsigned>(bh), num_levels);
+  corr1d_skew_kernel<<<grid, 256, smem, stream>>>(a);
+  return check_launch("corr1d_skew_kernel");
+}
+
+// host-side launcher, called by nnd_corr1d_lookup_conv1x1[_skewed] (lookup.cu) for the shipping shape:
 // 4 levels, radius 4, c_out = 256, channels-last output, 16-byte aligned pyramid rows
 nnd_status launch_lookup_conv1x1_ws(const LookupArgs& a, const float* weight, const float* bias, int relu, int out_f16,
-                                    long long total_px, cudaStream_t stream) {
+                                    long long total_px, int skew_w1, cudaStream_t stream) {
   const long long sms = sm_count();
   const long long tiles = (total_px + ws::TILE - 1) / ws::TILE;
   const long long grid = tiles < sms ? tiles : sms;
@@ -416,18 +510,20 @@ nnd_status launch_lookup_conv1x1_ws(const LookupArgs& a, const float* weight, co
     set_error("lookup_conv1x1: cuTensorMapEncodeTiled(output) failed with CUresult %d", static_cast<int>(r));
     return NND_ERR_CUDA;
   }
-  cudaError_t e;
-  if (out_f16) {
-    e = cudaFuncSetAttribute(corr1d_lookup_conv1x1_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws::SMEM_TOTAL);
-    if (e != cudaSuccess) return cuda_fail(e, "lookup_conv1x1: shared-memory attribute");
-    corr1d_lookup_conv1x1_ws_kernel<true><<<static_cast<unsigned>(grid), ws::THREADS, ws::SMEM_TOTAL, stream>>>(
-        a, out_map, weight, bias, relu, total_px, per);
+#define NND_WS_LAUNCH(F16, SK)                                                                                          \
+  do {                                                                                                                  \
+    cudaError_t e = cudaFuncSetAttribute(corr1d_lookup_conv1x1_ws_kernel<F16, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         ws::SMEM_TOTAL);                                                               \
+    if (e != cudaSuccess) return cuda_fail(e, "lookup_conv1x1: shared-memory attribute");                               \
+    corr1d_lookup_conv1x1_ws_kernel<F16, SK><<<static_cast<unsigned>(grid), ws::THREADS, ws::SMEM_TOTAL, stream>>>(     \
+        a, out_map, weight, bias, relu, total_px, per, skew_w1 > 0 ? skew_w1 : 1);                                      \
+  } while (0)
+  if (skew_w1 > 0) {
+    if (out_f16) NND_WS_LAUNCH(true, true); else NND_WS_LAUNCH(false, true);
   } else {
-    e = cudaFuncSetAttribute(corr1d_lookup_conv1x1_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws::SMEM_TOTAL);
-    if (e != cudaSuccess) return cuda_fail(e, "lookup_conv1x1: shared-memory attribute");
-    corr1d_lookup_conv1x1_ws_kernel<false><<<static_cast<unsigned>(grid), ws::THREADS, ws::SMEM_TOTAL, stream>>>(
-        a, out_map, weight, bias, relu, total_px, per);
+    if (out_f16) NND_WS_LAUNCH(true, false); else NND_WS_LAUNCH(false, false);
   }
+#undef NND_WS_LAUNCH
   return check_launch("corr1d_lookup_conv1x1_ws_kernel");
 }
 

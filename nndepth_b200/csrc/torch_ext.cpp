@@ -172,6 +172,62 @@ Tensor corr1d_lookup_conv1x1(const Tensor& pyramid, int64_t width0, const Tensor
   return out;
 }
 
+// skewed copy of a row-layout pyramid: one flat buffer, level l = B*H*(W2 >> l) rows of roundup4(W1) floats
+Tensor corr1d_skew(const Tensor& pyramid, int64_t B, int64_t H, int64_t W1, int64_t W2, int64_t num_levels) {
+  check_cuda(pyramid, "pyramid");
+  c10::cuda::CUDAGuard guard(pyramid.device());
+  LevelTable t = row_levels(pyramid, B * H * W1, W2, num_levels, "corr1d_skew");
+  const int P1 = nnd_row_pitch(static_cast<int>(W1));
+  int64_t floats = 0;
+  for (int l = 0; l < num_levels; ++l) floats += B * H * t.width[l] * P1;
+  Tensor skew = at::empty({floats}, pyramid.options());
+  std::array<float*, NND_MAX_LEVELS> dst{};
+  int64_t off = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    dst[l] = skew.data_ptr<float>() + off;
+    off += B * H * t.width[l] * P1;
+  }
+  check_status(nnd_corr1d_skew(t.ptr.data(), t.width.data(), t.pitch.data(), B, H, W1, num_levels, dst.data(), P1,
+                               current_stream(pyramid)),
+               "nnd_corr1d_skew");
+  return skew;
+}
+
+Tensor corr1d_lookup_conv1x1_skewed(const Tensor& skew, int64_t width0, const Tensor& coords, int64_t num_levels, int64_t radius,
+                                    const Tensor& weight_t, const optional<Tensor>& bias, bool relu, int64_t out_layout) {
+  check_cuda(skew, "skewed pyramid"); check_cuda(coords, "coords"); check_cuda(weight_t, "weight_t");
+  same_device(skew, coords, "corr1d_lookup_conv1x1_skewed"); same_device(weight_t, coords, "corr1d_lookup_conv1x1_skewed");
+  auto s = nchw(coords, "coords");
+  TORCH_CHECK(s[1] == 1, "coords must be (B, 1, H, W), got ", coords.sizes());
+  TORCH_CHECK(weight_t.dim() == 2 && weight_t.size(0) == num_levels * (2 * radius + 1) && weight_t.size(1) == 256,
+              "weight_t must be (", num_levels * (2 * radius + 1), ", 256), got ", weight_t.sizes());
+  TORCH_CHECK(out_layout == 1 || out_layout == 2, "out_layout must be 1 (NHWC fp32) or 2 (NHWC fp16)");
+  const float* bias_ptr = nullptr;
+  if (bias.has_value()) {
+    check_cuda(*bias, "bias");
+    TORCH_CHECK(bias->numel() == 256, "bias must have 256 elements");
+    bias_ptr = bias->data_ptr<float>();
+  }
+  c10::cuda::CUDAGuard guard(coords.device());
+  const int64_t B = s[0], H = s[2], W1 = s[3];
+  const int P1 = nnd_row_pitch(static_cast<int>(W1));
+  std::array<const float*, NND_MAX_LEVELS> lv{};
+  std::array<int, NND_MAX_LEVELS> width{};
+  int64_t off = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    width[l] = static_cast<int>(width0 >> l);
+    lv[l] = skew.data_ptr<float>() + off;
+    off += B * H * width[l] * P1;
+  }
+  TORCH_CHECK(skew.numel() >= off, "skewed pyramid holds ", skew.numel(), " floats, needs ", off);
+  Tensor out = at::empty({B, H, W1, 256}, coords.options().dtype(out_layout == 2 ? at::kHalf : at::kFloat)).permute({0, 3, 1, 2});
+  check_status(nnd_corr1d_lookup_conv1x1_skewed(lv.data(), width.data(), P1, coords.data_ptr<float>(), B, H, W1, num_levels,
+                                                radius, weight_t.data_ptr<float>(), bias_ptr, 256, relu ? 1 : 0, out_layout,
+                                                out.data_ptr(), current_stream(coords)),
+               "nnd_corr1d_lookup_conv1x1_skewed");
+  return out;
+}
+
 Tensor corr1d_lookup_backward(const Tensor& grad_out, const Tensor& coords, int64_t width0, int64_t num_levels, int64_t radius) {
   check_cuda(grad_out, "grad_out"); check_cuda(coords, "coords");
   same_device(grad_out, coords, "corr1d_lookup_backward");
@@ -514,6 +570,9 @@ TORCH_LIBRARY(nndepth_b200, m) {
   m.def("corr1d_lookup(Tensor pyramid, int width0, Tensor coords, int num_levels, int radius) -> Tensor", &corr1d_lookup);
   m.def("corr1d_lookup_conv1x1(Tensor pyramid, int width0, Tensor coords, int num_levels, int radius, Tensor weight_t, "
         "Tensor? bias, bool relu, int precision, int out_layout) -> Tensor", &corr1d_lookup_conv1x1);
+  m.def("corr1d_skew(Tensor pyramid, int B, int H, int W1, int W2, int num_levels) -> Tensor", &corr1d_skew);
+  m.def("corr1d_lookup_conv1x1_skewed(Tensor skewed, int width0, Tensor coords, int num_levels, int radius, Tensor weight_t, "
+        "Tensor? bias, bool relu, int out_layout) -> Tensor", &corr1d_lookup_conv1x1_skewed);
   m.def("corr1d_lookup_backward(Tensor grad_out, Tensor coords, int width0, int num_levels, int radius) -> Tensor",
         &corr1d_lookup_backward);
   m.def("pyramid_unpool_(Tensor(a!) d_pyramid, int rows, int width0, int num_levels) -> ()", &pyramid_unpool_);

@@ -426,6 +426,36 @@ def test_lookup_conv1x1_tcgen05_path(shape):
     assert torch.equal(umma_h, umma.half())
 
 
+@pytest.mark.parametrize("shape", [(8, 48, 156, 156), (1, 5, 52, 52), (3, 7, 44, 60), (2, 3, 60, 44), (1, 1, 16, 16), (20, 48, 156, 156)])
+@pytest.mark.parametrize("field", ["smooth", "noise"])
+def test_lookup_conv1x1_skewed_layout_is_bit_identical(shape, field):
+    """The fused kernel reading the SKEWED copy of the pyramid (S[j][w1], j = ((w1 >> l) - w2) mod W2_l) against the same
+    kernel on the row layout: identical bits for smooth and for white-noise coordinates, out-of-range coordinates,
+    rectangular volumes (W1 != W2), groups that straddle epipolar rows, ragged last tiles."""
+    import nndepth_b200 as nb
+    B, H, W1, W2 = shape
+    torch.manual_seed(B * H + W1 + W2)
+    f1, f2 = torch.randn(B, 64, H, W1, device="cuda"), torch.randn(B, 64, H, W2, device="cuda")
+    blk = nb.CorrBlock1D(f1, f2, 4, 4)
+    grid = torch.arange(W1, device="cuda").float().view(1, 1, 1, W1).repeat(B, 1, H, 1)
+    if field == "smooth":
+        bump = torch.nn.functional.interpolate(torch.rand(B, 1, 2, 3, device="cuda") * 12, size=(H, W1), mode="bilinear",
+                                               align_corners=True)
+        coords = grid - bump
+    else:
+        coords = grid - torch.rand(B, 1, H, W1, device="cuda") * 30
+    coords.view(-1)[::17] = -7.5
+    coords.view(-1)[5::23] = W2 + 3.25
+    conv = torch.nn.Conv2d(36, 256, 1).cuda()
+    with torch.no_grad():
+        for half in (False, True):
+            rows = blk.lookup_conv1x1(coords, conv.weight, conv.bias, relu=True, precision="tf32", channels_last=True, half=half)
+            skew = blk.lookup_conv1x1(coords, conv.weight, conv.bias, relu=True, precision="tf32", channels_last=True, half=half,
+                                      skewed=True)
+            assert skew.dtype == rows.dtype and skew.is_contiguous(memory_format=torch.channels_last)
+            assert torch.equal(skew, rows)
+
+
 def test_randomised_lookup_sweep_bit_exact():
     """40 random (shape, levels, radius, coordinate regime) draws: lookup on an identical pyramid and the integer
     window indices must equal the oracle bit for bit -- covers the generic kernel (radius != 4, ragged widths,

@@ -27,7 +27,7 @@ def main():
     import nndepth_b200 as nb
     from nndepth_b200 import _lib
     new = _lib.load()
-    libs = {"r2": new}
+    libs = {"r2": new, "r2_skewed": new}
     import glob
     for old_path in sorted(glob.glob(os.path.join(ROOT, "tools", "_old", "libnndepth_b200_*.so"))):
         if args.once:
@@ -48,7 +48,7 @@ def main():
         del f1, f2
         base = torch.arange(W, device=dev).float().view(1, 1, 1, W).repeat(B, 1, H, 1)
         if args.smooth:
-            disp = torch.nn.functional.interpolate(torch.rand(B, 1, 6, 20, device=dev) * 40, size=(H, W), mode="bilinear")
+            disp = torch.nn.functional.interpolate(torch.rand(B, 1, 6, 20, device=dev) * 12, size=(H, W), mode="bilinear")
         else:
             disp = torch.rand(B, 1, H, W, device=dev) * 40
         coords = (base - disp).contiguous()
@@ -62,6 +62,10 @@ def main():
             res = {}
             for name, lib in libs.items():
                 def launch():
+                    if name == "r2_skewed":
+                        res_t = blk.lookup_conv1x1(coords, None, bias, relu=True, weight_t=wt, precision="tf32", channels_last=True,
+                                                   half=layout == 2, skewed=True)
+                        return
                     st = lib.nnd_corr1d_lookup_conv1x1(blk._pyr._level_ptrs, blk._pyr._width_arr, blk._pyr._pitch_arr,
                                                        _lib.ptr(coords), B, H, W, 4, 4, _lib.ptr(wt), _lib.ptr(bias), 256, 1,
                                                        _lib.PREC_TF32, layout, _lib.ptr(out), _lib.stream_ptr(coords))
