@@ -224,25 +224,13 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const __gr
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    // window ring: the row layout keeps 2 buffers of 32 x 20 floats per warp (gather one tile ahead); the skewed layout's
-    // 32 x 13 floats fit THREE in the same space, so its gathers run two tiles ahead -- under load a DRAM round trip is
-    // longer than one tile's interpolation
-    constexpr int RING = SKEW ? 3 : 2;
-    constexpr int RING_FLOATS = SKEW ? 32 * SKSTRIDE : WIN_BUF_FLOATS;
-    static_assert(RING * RING_FLOATS <= 2 * WIN_BUF_FLOATS, "window ring exceeds the per-warp staging space");
-    float c0 = coord_of(0), c1 = coord_of(1), c2 = coord_of(2);
+    float c0 = coord_of(0), c1 = coord_of(1);
     issue_windows(0, c0, wins);
-    if (RING == 3) issue_windows(1, c1, wins + RING_FLOATS);
     stage_weights();
     for (int t = 0; t < nt; ++t) {
-      const float c3 = coord_of(t + 3);                          // in flight during this whole iteration
-      if (RING == 3) {
-        issue_windows(t + 2, c2, wins + ((t + 2) % 3) * RING_FLOATS);
-        asm volatile("cp.async.wait_group 2;" ::: "memory");       // tile t's windows (my copies) have landed
-      } else {
-        issue_windows(t + 1, c1, wins + ((t + 1) & 1) * RING_FLOATS);
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-      }
+      const float c2 = coord_of(t + 2);                          // in flight during this whole iteration
+      issue_windows(t + 1, c1, wins + ((t + 1) & 1) * WIN_BUF_FLOATS);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");         // tile t's windows (my copies) have landed
       __syncwarp();                                               // ... and the other lanes' copies
       const int slot = t % NA;
       mbar_wait(a_empty(slot), ((t / NA) & 1) ^ 1);               // the MMAs that read this slot have completed
@@ -251,7 +239,7 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const __gr
         const bool live = px < px_end;
         const float centre = __fmul_rn(c0, inv_pow2);
         const int s = SKEW ? make_tap(0, R, centre, sc).i0 : (make_tap(0, R, centre, sc).i0 & ~3);
-        const float* mine = wins + (t % RING) * RING_FLOATS + lane * (SKEW ? SKSTRIDE : WSTRIDE) - s;
+        const float* mine = wins + (t & 1) * WIN_BUF_FLOATS + lane * (SKEW ? SKSTRIDE : WSTRIDE) - s;
         uint32_t v[12];
 #pragma unroll
         for (int k = 0; k < TAPS; ++k) {
@@ -272,7 +260,6 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const __gr
       if (lane == 0) mbar_arrive(a_full(slot));
       c0 = c1;
       c1 = c2;
-      c2 = c3;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else if (warp == MMA_WARP) {
