@@ -68,6 +68,11 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint32_t pack_h2_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
                "r"(c1)
@@ -146,13 +151,20 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const __gr
     for (int j = 0; j < PER_THREAD; ++j) {
       const int idx = tid + THREADS * j, n = idx & (NOUT - 1), col = idx >> 8;
       const int l = col / KCOLS, k = col - l * KCOLS;
-      wv[j] = (idx < TOTAL && k < TAPS) ? __ldg(weight + static_cast<long long>(l * TAPS + k) * NOUT + n) : 0.f;
+      // level 0's spare columns 9 and 10 carry the BIAS as two TF32 terms (the A operand holds 1.0 there): the tensor
+      // core adds it, exact to 2**-22, and the epilogue needs neither the bias vector nor 256 additions per pixel
+      const bool is_bias = l == 0 && (k == TAPS || k == TAPS + 1) && bias != nullptr;
+      wv[j] = idx >= TOTAL ? 0.f : k < TAPS ? __ldg(weight + static_cast<long long>(l * TAPS + k) * NOUT + n)
+                                  : is_bias ? __ldg(bias + n) : 0.f;
     }
 #pragma unroll
     for (int j = 0; j < PER_THREAD; ++j) {
       const int idx = tid + THREADS * j, n = idx & (NOUT - 1), col = idx >> 8;
+      const int l = col / KCOLS, k = col - l * KCOLS;
+      uint32_t bits = to_tf32(wv[j]);
+      if (l == 0 && k == TAPS + 1) bits = to_tf32(wv[j] - __uint_as_float(to_tf32(wv[j])));   // the remainder term
       if (idx < TOTAL)
-        *reinterpret_cast<uint32_t*>(smem + SMEM_B + chunk_offset(n, col >> 2, B_KSTEP_BYTES) + (col & 3) * 4) = to_tf32(wv[j]);
+        *reinterpret_cast<uint32_t*>(smem + SMEM_B + chunk_offset(n, col >> 2, B_KSTEP_BYTES) + (col & 3) * 4) = bits;
     }
     fence_proxy_async();
     __syncwarp();
@@ -183,8 +195,9 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const __gr
         const int hi = make_tap(TAPS - 1, R, centre, sc).i1;
         const long long px = px0 + static_cast<long long>(t) * TILE + m;
         if (px < px_end) {
-          const long long bh = px / row_w1;
-          const int w1 = static_cast<int>(px - bh * row_w1);
+          const unsigned upx = static_cast<unsigned>(px);           // total_px < 2^31 (checked by the launcher)
+          const long long bh = upx / static_cast<unsigned>(row_w1);
+          const int w1 = static_cast<int>(upx - static_cast<unsigned>(bh) * static_cast<unsigned>(row_w1));
           const float* colp = lbase + bh * w * static_cast<long long>(pitch) + w1;   // row j = 0 of my epipolar row, my column
           int jr = ((w1 >> lvl) - lo) % w;               // row of window element 0; element i sits i rows above (mod w)
           if (jr < 0) jr += w;
@@ -248,7 +261,8 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const __gr
           const float val = live ? __fadd_rn(__fmul_rn(tp.coef, mine[tp.i0]), __fmul_rn(tp.one_minus, mine[tp.i1])) : 0.f;
           v[k] = to_tf32(val);
         }
-        v[9] = v[10] = v[11] = 0u;
+        v[9] = v[10] = lvl == 0 ? 0x3f800000u : 0u;            // 1.0 x (bias_hi, bias_lo) rows of the B operand
+        v[11] = 0u;
         unsigned char* slot_base = smem + SMEM_A + slot * A_SLOT_BYTES;
 #pragma unroll
         for (int i = 0; i < 3; ++i)
@@ -295,12 +309,8 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const __gr
     const int e = warp - EPI_WARP0;
     const int eq = e & 3;                               // TMEM lane quarter this warp may read (warp % 4)
     const int half = e >> 2;                            // channels [128 * half, 128 * half + 128)
-    const int et = tid - 32 * EPI_WARP0;
-    float* bias_s = reinterpret_cast<float*>(smem + SMEM_BIAS);
-    for (int i = et; i < NOUT; i += 32 * EPI_WARPS) bias_s[i] = bias ? __ldg(bias + i) : 0.f;
     if (e == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&out_map) : "memory");
     stage_weights();
-    asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // bias_s is visible to every epilogue warp
     constexpr int ELEM = OUT_F16 ? 2 : 4;
     constexpr int ROW_BYTES = NOUT * ELEM;                       // bytes per pixel of the output
     constexpr int COLS_PER_BOX = BOX_ROW_BYTES / ELEM;           // 64 (fp16) or 32 (fp32) channels per TMA box
@@ -336,22 +346,26 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const __gr
             tc_fence_before();
             mbar_arrive(tmem_empty(acc));                        // my last TMEM read of this tile
           }
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 bq = *reinterpret_cast<const float4*>(bias_s + col0 + i);
-            v[i] += bq.x; v[i + 1] += bq.y; v[i + 2] += bq.z; v[i + 3] += bq.w;
-          }
-          if (relu) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
+          // the bias is already in the accumulator (two extra K columns); fp16: ReLU rides on the conversion
+          // (cvt.rn.relu: max(x, 0) then round == round then max, 0 is exact); fp32: one FMNMX per value
           uint4 pk[OUT_F16 ? 4 : 8];
           if (OUT_F16) {
+            if (relu) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              pk[i] = make_uint4(pack_h2(v[8 * i], v[8 * i + 1]), pack_h2(v[8 * i + 2], v[8 * i + 3]),
-                                 pack_h2(v[8 * i + 4], v[8 * i + 5]), pack_h2(v[8 * i + 6], v[8 * i + 7]));
+              for (int i = 0; i < 4; ++i)
+                pk[i] = make_uint4(pack_h2_relu(v[8 * i], v[8 * i + 1]), pack_h2_relu(v[8 * i + 2], v[8 * i + 3]),
+                                   pack_h2_relu(v[8 * i + 4], v[8 * i + 5]), pack_h2_relu(v[8 * i + 6], v[8 * i + 7]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                pk[i] = make_uint4(pack_h2(v[8 * i], v[8 * i + 1]), pack_h2(v[8 * i + 2], v[8 * i + 3]),
+                                   pack_h2(v[8 * i + 4], v[8 * i + 5]), pack_h2(v[8 * i + 6], v[8 * i + 7]));
+            }
           } else {
+            if (relu) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i)
               pk[i] = make_uint4(__float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]), __float_as_uint(v[4 * i + 2]),
