@@ -68,6 +68,11 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// Round-to-nearest (ties away) TF32 operand in ONE integer instruction: tcgen05.mma kind::tf32 ignores the low 13
+// mantissa bits, so adding half an ulp of the 10-bit mantissa is all the rounding there is to do (cvt.rna.tf32.f32
+// expands to a five-instruction sequence here).  Same value the MMA would see after cvt.rna for every finite input.
+__device__ __forceinline__ uint32_t tf32_rna_bits(float x) { return __float_as_uint(x) + 0x1000u; }
+
 __device__ __forceinline__ uint32_t pack_h2_relu(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -161,8 +166,9 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const __gr
     for (int j = 0; j < PER_THREAD; ++j) {
       const int idx = tid + THREADS * j, n = idx & (NOUT - 1), col = idx >> 8;
       const int l = col / KCOLS, k = col - l * KCOLS;
-      uint32_t bits = to_tf32(wv[j]);
-      if (l == 0 && k == TAPS + 1) bits = to_tf32(wv[j] - __uint_as_float(to_tf32(wv[j])));   // the remainder term
+      uint32_t bits = tf32_rna_bits(wv[j]);
+      if (l == 0 && k == TAPS + 1)   // the remainder term of the bias
+        bits = tf32_rna_bits(wv[j] - __uint_as_float((__float_as_uint(wv[j]) + 0x1000u) & 0xffffe000u));
       if (idx < TOTAL)
         *reinterpret_cast<uint32_t*>(smem + SMEM_B + chunk_offset(n, col >> 2, B_KSTEP_BYTES) + (col & 3) * 4) = bits;
     }
@@ -201,14 +207,16 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const __gr
           const float* colp = lbase + bh * w * static_cast<long long>(pitch) + w1;   // row j = 0 of my epipolar row, my column
           int jr = ((w1 >> lvl) - lo) % w;               // row of window element 0; element i sits i rows above (mod w)
           if (jr < 0) jr += w;
+          const float* src = colp + static_cast<long long>(jr) * pitch;
+          const long long wrap = static_cast<long long>(w) * pitch;
           const uint32_t dst = smem_u32(win + lane * SKSTRIDE);
+          const int n_el = min(hi, w - 1) - lo;           // last window element
 #pragma unroll
           for (int i = 0; i < 11; ++i) {
 #ifndef NND_WS_SKIP_GATHER
-            if (lo + i <= hi && lo + i < w)
-              asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * i), "l"(colp + static_cast<long long>(jr) * pitch)
-                           : "memory");
+            if (i <= n_el) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * i), "l"(src) : "memory");
 #endif
+            src = jr == 0 ? src + wrap - pitch : src - pitch;
             jr = jr == 0 ? w - 1 : jr - 1;
           }
         }
@@ -259,7 +267,7 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const __gr
           const Tap tp = make_tap(k, R, centre, sc);
           // coef * val0 + (1 - coef) * val1, each operation rounded (utils.py:27); then RN to TF32 for the MMA
           const float val = live ? __fadd_rn(__fmul_rn(tp.coef, mine[tp.i0]), __fmul_rn(tp.one_minus, mine[tp.i1])) : 0.f;
-          v[k] = to_tf32(val);
+          v[k] = tf32_rna_bits(val);
         }
         v[9] = v[10] = lvl == 0 ? 0x3f800000u : 0u;            // 1.0 x (bias_hi, bias_lo) rows of the B operand
         v[11] = 0u;
