@@ -345,23 +345,15 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const __gr
           if (lane == 0) tma_store_wait_read();          // the TMA store that last read this staging box has drained it
           __syncwarp();
         }
-        // all of the box's TMEM loads are issued before the one wait: their latencies overlap
-        uint32_t raw[CHUNKS_PER_BOX][32];
-#pragma unroll
-        for (int cq = 0; cq < CHUNKS_PER_BOX; ++cq)
-          umma::ld32_issue(tmem_base + (static_cast<uint32_t>(32 * eq) << 16) + static_cast<uint32_t>(acc * NOUT + colb + 32 * cq),
-                           raw[cq]);
-        umma::tmem_ld_wait();
-        if (b == BOXES - 1) {
-          tc_fence_before();
-          mbar_arrive(tmem_empty(acc));                          // my last TMEM read of this tile
-        }
 #pragma unroll
         for (int cq = 0; cq < CHUNKS_PER_BOX; ++cq) {
           const int col0 = colb + 32 * cq;
           float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[cq][i]);
+          umma::ld32(tmem_base + (static_cast<uint32_t>(32 * eq) << 16) + static_cast<uint32_t>(acc * NOUT + col0), v);
+          if (b == BOXES - 1 && cq == CHUNKS_PER_BOX - 1) {
+            tc_fence_before();
+            mbar_arrive(tmem_empty(acc));                        // my last TMEM read of this tile
+          }
           // the bias is already in the accumulator (two extra K columns); fp16: ReLU rides on the conversion
           // (cvt.rn.relu: max(x, 0) then round == round then max, 0 is exact); fp32: one FMNMX per value
           uint4 pk[OUT_F16 ? 4 : 8];
