@@ -332,42 +332,56 @@ def time_step_kernels(device, peak):
 
 
 def time_fused_lookup(device, B, out_elem, peak, reps=10):
-    """The per-iteration kernel (lookup + convc1 + ReLU) stand-alone at batch ``B`` of the KITTI feature shape, L2 flushed."""
+    """The per-iteration kernel (lookup + convc1 + ReLU) stand-alone at batch ``B`` of the KITTI feature shape, L2 flushed:
+    on the row layout with white-noise coordinates (SURVEY 8(d)'s synthetic lookups) and with a smooth disparity field
+    like the one the model produces (tools/coords_smoothness.py: <= 4.6 px of disparity range inside any 32-pixel group
+    over all 32 iterations), and on the SKEWED copy of the pyramid with the smooth field."""
     import nndepth_b200 as nb
     C, H, W = 256, 48, 156
     torch.manual_seed(3)
     f1, f2 = torch.randn(B, C, H, W, device=device), torch.randn(B, C, H, W, device=device)
     blk = nb.CorrBlock1D(f1, f2, 4, 4)
     del f1, f2
-    coords = (torch.arange(W, device=device).float().view(1, 1, 1, W).repeat(B, 1, H, 1)
-              - torch.rand(B, 1, H, W, device=device) * 40)
+    grid = torch.arange(W, device=device).float().view(1, 1, 1, W).repeat(B, 1, H, 1)
+    noise = grid - torch.rand(B, 1, H, W, device=device) * 40
+    smooth = grid - torch.nn.functional.interpolate(torch.rand(B, 1, 6, 20, device=device) * 6, size=(H, W), mode="bilinear",
+                                                    align_corners=True)
     conv = torch.nn.Conv2d(36, 256, 1).to(device)
     wt = blk.prepare_conv1x1_weight(conv.weight.detach())
     bias = conv.bias.detach()
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=device)
     stream = torch.cuda.current_stream(device)
-
-    def launch():
-        return blk.lookup_conv1x1(coords, None, bias, relu=True, weight_t=wt, precision="tf32", channels_last=True,
-                                  half=out_elem == 2)
-    for _ in range(3):
-        launch()
-    ts = []
-    for _ in range(reps):
-        flush.fill_(1.0)
-        torch.cuda._sleep(200000)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        launch()
-        e1.record(stream)
-        e1.synchronize()
-        ts.append(e0.elapsed_time(e1) * 1e3)
-    us = statistics.median(ts)
     nbytes = B * H * W * (164 + 256 * out_elem)
+
+    def timed(coords, skewed):
+        def launch():
+            return blk.lookup_conv1x1(coords, None, bias, relu=True, weight_t=wt, precision="tf32", channels_last=True,
+                                      half=out_elem == 2, skewed=skewed)
+        for _ in range(3):
+            launch()
+        ts = []
+        for _ in range(reps):
+            flush.fill_(1.0)
+            torch.cuda._sleep(200000)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            launch()
+            e1.record(stream)
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        us = statistics.median(ts)
+        return {"us_per_launch_l2_flushed": us, "achieved_gbs": nbytes / us / 1e3, "frac": nbytes / us / 1e3 / peak}
+
+    rows_noise = timed(noise, False)
+    out = {"batch": B, "pixels": B * H * W, "algorithmic_bytes_per_launch": nbytes, **rows_noise,
+           "coords": "white noise: x - U(0, 40), row layout",
+           "smooth_field_row_layout": timed(smooth, False), "smooth_field_skewed_layout": timed(smooth, True),
+           "note": "skewed layout = nnd_corr1d_skew + nnd_corr1d_lookup_conv1x1_skewed (S[j][w1], j = ((w1 >> l) - w2) mod W2_l): "
+                   "ncu DRAM read 105 MB vs 268 MB on the row layout for 79 MB of window data (profiles/r2_lookup_ws_b64_summary.txt); "
+                   "bit-identical results; pays for smooth fields only"}
     del blk, flush
     torch.cuda.empty_cache()
-    return {"batch": B, "pixels": B * H * W, "us_per_launch_l2_flushed": us, "algorithmic_bytes_per_launch": nbytes,
-            "achieved_gbs": nbytes / us / 1e3, "frac": nbytes / us / 1e3 / peak}
+    return out
 
 
 def hotpath_configs(skip_cpu=False):
