@@ -463,11 +463,14 @@ corr1d_skew_kernel(const __grid_constant__ SkewArgs a) {
   const int w1 = w1_0 + lane;
   if (w1 >= a.W1) return;
   float* __restrict__ dst = a.dst[l] + bh * w * static_cast<long long>(a.P1) + w1;
-  const int top = w1 >> l;
+  int w2 = ((w1 >> l) - warp) % w;                   // row j = warp; every step of 8 rows moves w2 back by 8 (mod w)
+  if (w2 < 0) w2 += w;
+  const int step = 8 % w;
+  const float* mine = rows + lane * WP;
   for (int j = warp; j < w; j += 8) {
-    int w2 = (top - j) % w;
+    dst[static_cast<long long>(j) * a.P1] = mine[w2];
+    w2 -= step;
     if (w2 < 0) w2 += w;
-    dst[static_cast<long long>(j) * a.P1] = rows[lane * WP + w2];
   }
 }
 
