@@ -88,19 +88,30 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  // The wait itself is a two-instruction loop (try_wait suspends the warp in hardware for up to the time hint, so a
+  // waiting role does not take issue slots from the working ones); every 4096 misses the outer loop checks a watchdog:
+  // a protocol bug must fault, not hang the GPU.
   uint32_t done = 0;
   long long t0 = 0;
-  int spins = 0;
   do {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
+        "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
+        "mov.u32 n, 4096;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "@p bra LAB_DONE;\n\t"
+        "sub.u32 n, n, 1;\n\t"
+        "setp.ne.u32 p, n, 0;\n\t"
+        "@p bra LAB_WAIT;\n\t"
+        "mov.u32 %0, 0;\n\t"
+        "bra LAB_OUT;\n\t"
+        "LAB_DONE:\n\t"
+        "mov.u32 %0, 1;\n\t"
+        "LAB_OUT:\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(1000u)
         : "memory");
-    if (!done && ++spins == 1024) {  // watchdog: a protocol bug must fault, not hang the GPU
-      spins = 0;
+    if (!done) {
       const long long now = clock64();
       if (t0 == 0) t0 = now;
       else if (now - t0 > 2000000000LL) __trap();

@@ -103,7 +103,7 @@ template <bool OUT_F16, bool SKEW>
 __global__ void __launch_bounds__(ws::THREADS, 1)
 corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const __grid_constant__ CUtensorMap out_map,
                                 const float* __restrict__ weight, const float* __restrict__ bias, int relu,
-                                long long total_px, long long px_per_cta, int row_w1) {
+                                long long total_px, long long px_per_cta, int row_w1, unsigned magic_shl2) {
   using namespace ws;
   using umma::smem_u32;
   using umma::mbar_init;
@@ -179,27 +179,38 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const __gr
 
   if (warp < PROD_WARPS) {
     // =========================================== producers ===========================================
-    const int pg = warp & 3, lvl = warp >> 2;
+    // warp = 4 * (pixel group) + level: the four level-warps of one 32-pixel group sit on the four SM sub-partitions, so
+    // a ragged last tile (one or two live groups) costs a quarter or half of a full one
+    const int pg = warp >> 2, lvl = warp & 3;
     const int m = 32 * pg + lane;                       // my pixel's row of the tile
     const int w = a.src[0].width[lvl], pitch = a.src[0].pitch[lvl];
     const float* __restrict__ lbase = a.src[0].ptr[lvl];
     const LevelScale sc = level_scale(w, lvl, 0.f);
     const float inv_pow2 = 1.0f / static_cast<float>(1 << lvl);
     float* const wins = reinterpret_cast<float*>(smem + SMEM_WIN) + warp * (2 * WIN_BUF_FLOATS);
-    const int q = lane & 3;
+    const int q4 = 4 * (lane & 3), psub = lane >> 2;
     constexpr unsigned FULL = 0xffffffffu;
 
     auto coord_of = [&](int t) -> float {
       const long long px = px0 + static_cast<long long>(t) * TILE + m;
       return (t < nt && px < px_end) ? __ldg(a.coords + px) : 0.0f;
     };
+    // Row layout: the window is fetched from a CONSERVATIVE 4-aligned start -- floor(centre - 4 - 1/64), clamped to the
+    // row -- instead of the exact first tap index: never above it and at most one below (the taps' positions differ from
+    // centre + dx by a few ulps only, launcher: width <= 16384), so with the alignment slack every tap lies in
+    // [start, start + 14] of the 16 floats fetched, and the two exact taps the bounds used to cost are not computed.
+    auto window_start = [&](float centre) -> int {
+      return SKEW ? make_tap(0, R, centre, sc).i0
+                  : (__float2int_rd(fminf(fmaxf(__fadd_rn(centre, -4.015625f), 0.f), sc.span)) & ~3);
+    };
     constexpr int SKSTRIDE = 13;                         // skewed mode: 11 window floats per pixel, odd stride
-    auto issue_windows = [&](int t, float c, float* win) {
-      if (t < nt && SKEW) {
+    auto issue_windows = [&](int t, float c, int start, float* win) {
+      const long long grp0 = px0 + static_cast<long long>(t) * TILE + 32 * pg;   // first pixel of my group
+      if (t < nt && grp0 < px_end && SKEW) {
         const float centre = __fmul_rn(c, inv_pow2);
-        const int lo = make_tap(0, R, centre, sc).i0;
+        const int lo = start;
         const int hi = make_tap(TAPS - 1, R, centre, sc).i1;
-        const long long px = px0 + static_cast<long long>(t) * TILE + m;
+        const long long px = grp0 + lane;
         if (px < px_end) {
           const unsigned upx = static_cast<unsigned>(px);           // total_px < 2^31 (checked by the launcher)
           const long long bh = upx / static_cast<unsigned>(row_w1);
@@ -220,25 +231,24 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const __gr
             jr = jr == 0 ? w - 1 : jr - 1;
           }
         }
-      } else if (t < nt) {
+      } else if (t < nt && grp0 < px_end) {
         const float centre = __fmul_rn(c, inv_pow2);
-        const int s = make_tap(0, R, centre, sc).i0 & ~3;
-        const int hi = make_tap(TAPS - 1, R, centre, sc).i1;
-        const long long grp0 = px0 + static_cast<long long>(t) * TILE + 32 * pg;   // first pixel of my group
+        const int hi = __float2int_ru(fminf(fmaxf(__fadd_rn(centre, 4.015625f), 0.f), sc.span));   // >= the last tap's ceil
+        const int n_live = static_cast<int>(px_end - grp0 < 32 ? px_end - grp0 : 32);
+        const float* __restrict__ gbase = lbase + grp0 * pitch;
+        const uint32_t dst0 = smem_u32(win + psub * WSTRIDE) + 4u * q4;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int p = j * 8 + (lane >> 2);
-          const int sp = __shfl_sync(FULL, s, p);
+          const int p = j * 8 + psub;
+          const int cq = __shfl_sync(FULL, start, p) + q4;
           const int hp = __shfl_sync(FULL, hi, p);
-          const int cq = sp + 4 * q;
 #ifdef NND_WS_SKIP_GATHER
           if (false) {
 #else
-          if (grp0 + p < px_end && cq <= hp && cq < w) {
+          if (p < n_live && cq <= hp) {
 #endif
-            const float* src = lbase + (grp0 + p) * pitch + cq;
-            const uint32_t dst = smem_u32(win + p * WSTRIDE + 4 * q);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            const float* src = gbase + static_cast<unsigned>(p * pitch + cq);   // one IMAD.WIDE.U32
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + 4u * (j * 8 * WSTRIDE)), "l"(src) : "memory");
           }
         }
       }
@@ -246,28 +256,44 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const __gr
     };
 
     float c0 = coord_of(0), c1 = coord_of(1);
-    issue_windows(0, c0, wins);
+    int s0 = window_start(__fmul_rn(c0, inv_pow2)), s1 = window_start(__fmul_rn(c1, inv_pow2));
+    issue_windows(0, c0, s0, wins);
     stage_weights();
     for (int t = 0; t < nt; ++t) {
       const float c2 = coord_of(t + 2);                          // in flight during this whole iteration
-      issue_windows(t + 1, c1, wins + ((t + 1) & 1) * WIN_BUF_FLOATS);
+      issue_windows(t + 1, c1, s1, wins + ((t + 1) & 1) * WIN_BUF_FLOATS);
       asm volatile("cp.async.wait_group 1;" ::: "memory");         // tile t's windows (my copies) have landed
       __syncwarp();                                               // ... and the other lanes' copies
       const int slot = t % NA;
       mbar_wait(a_empty(slot), ((t / NA) & 1) ^ 1);               // the MMAs that read this slot have completed
-      {
-        const long long px = px0 + static_cast<long long>(t) * TILE + m;
-        const bool live = px < px_end;
-        const float centre = __fmul_rn(c0, inv_pow2);
-        const int s = SKEW ? make_tap(0, R, centre, sc).i0 : (make_tap(0, R, centre, sc).i0 & ~3);
-        const float* mine = wins + (t & 1) * WIN_BUF_FLOATS + lane * (SKEW ? SKSTRIDE : WSTRIDE) - s;
+      if (px0 + static_cast<long long>(t) * TILE + 32 * pg < px_end) {   // (rows past px_end are never stored)
+        // centre clamped ONCE to [-6, span + 6] instead of every tap's x to [-1, span + 1]: inside the range nothing
+        // changes, outside it every tap still lands on t = 0 or t = span through the saturation (NaN -> -6 -> t = 0)
+        const float centre = fminf(fmaxf(__fmul_rn(c0, inv_pow2), -6.0f), __fadd_rn(sc.span, 6.0f));
+        // byte address of window element 0, less the (2^23-as-float << 2) that the index trick below adds back
+        // (magic_shl2 = 0x4b000000 << 2 arrives as a kernel argument: as a literal, ptxas splits it off the base again and
+        // adds it back for every tap)
+        const uint32_t mine = smem_u32(wins + (t & 1) * WIN_BUF_FLOATS + lane * (SKEW ? SKSTRIDE : WSTRIDE)) -
+                              4u * static_cast<uint32_t>(s0) - magic_shl2;
         uint32_t v[12];
 #pragma unroll
         for (int k = 0; k < TAPS; ++k) {
-          const Tap tp = make_tap(k, R, centre, sc);
+          // linear_sampler (utils.py:16-27) with the reference's operation order; t in [0, span]
+          const float x = __fadd_rn(static_cast<float>(k - R), centre);
+          const float qn = __fmul_rn(x, sc.inv_span);
+          const float rr = __fmaf_rn(-qn, sc.span, x);
+          const float tt = __fmul_rn(__saturatef(__fmaf_rn(rr, sc.inv_span, qn)), sc.span);
+          const float u = __fadd_rz(tt, 8388608.0f);              // 2^23 + floor(t), exact: no F2I / FRND on the XU pipe
+          const float f0 = __fadd_rn(u, -8388608.0f);
+          const uint32_t addr = mine + (__float_as_uint(u) << 2);
+          float v0, v1;
+          asm volatile("ld.shared.f32 %0, [%2];\n\tld.shared.f32 %1, [%2+4];" : "=f"(v0), "=f"(v1) : "r"(addr));
+          const bool whole = (tt == f0);                          // ceil(t) == floor(t): both neighbours are element i0
+          const float coef = whole ? 0.0f : __fsub_rn(__fadd_rn(f0, 1.0f), tt);   // coef = idx1 - t      (utils.py:26)
+          const float one_minus = __fsub_rn(1.0f, coef);
+          v1 = whole ? v0 : v1;
           // coef * val0 + (1 - coef) * val1, each operation rounded (utils.py:27); then RN to TF32 for the MMA
-          const float val = live ? __fadd_rn(__fmul_rn(tp.coef, mine[tp.i0]), __fmul_rn(tp.one_minus, mine[tp.i1])) : 0.f;
-          v[k] = tf32_rna_bits(val);
+          v[k] = tf32_rna_bits(__fadd_rn(__fmul_rn(coef, v0), __fmul_rn(one_minus, v1)));
         }
         v[9] = v[10] = lvl == 0 ? 0x3f800000u : 0u;            // 1.0 x (bias_hi, bias_lo) rows of the B operand
         v[11] = 0u;
@@ -276,12 +302,14 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const __gr
         for (int i = 0; i < 3; ++i)
           *reinterpret_cast<uint4*>(slot_base + chunk_offset(m, 3 * lvl + i, A_KSTEP_BYTES)) =
               make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        fence_proxy_async();                                      // generic-proxy writes -> visible to the tensor core
       }
-      fence_proxy_async();                                        // generic-proxy writes -> visible to the tensor core
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full(slot));
       c0 = c1;
       c1 = c2;
+      s0 = s1;
+      s1 = window_start(__fmul_rn(c2, inv_pow2));
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else if (warp == MMA_WARP) {
@@ -333,6 +361,11 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const __gr
       tc_fence_after();
       const long long row0 = px0 + static_cast<long long>(t) * TILE + 32 * eq;   // pixel of my TMEM lane 0
       const bool whole = row0 + 32 <= px_end;            // all 32 rows are mine: TMA store; else (the global tail) plain stores
+      if (row0 >= px_end) {                              // ragged last tile: none of my rows exists
+        tc_fence_before();
+        mbar_arrive(tmem_empty(acc));
+        continue;
+      }
 #ifdef NND_WS_SKIP_EPI
       tc_fence_before();
       mbar_arrive(tmem_empty(acc));
@@ -515,6 +548,10 @@ nnd_status launch_lookup_conv1x1_ws(const LookupArgs& a, const float* weight, co
     set_error("lookup_conv1x1: %lld pixels exceed the TMA store's 32-bit row coordinate", total_px);
     return NND_ERR_INVALID_ARGUMENT;
   }
+  if (a.src[0].width[0] > 16384) {   // the conservative window start assumes positions exact to well below 1/64
+    set_error("lookup_conv1x1: level-0 width %d exceeds 16384", a.src[0].width[0]);
+    return NND_ERR_INVALID_ARGUMENT;
+  }
   // the channels-last output as a 2-D tensor of 32-bit words: (total_px rows) x (row_bytes / 4 words), stored in boxes of
   // 32 rows x 32 words (128 bytes) whose shared-memory image uses the 128-byte swizzle
   EncodeTiledFn enc = encode_tiled();
@@ -541,7 +578,7 @@ nnd_status launch_lookup_conv1x1_ws(const LookupArgs& a, const float* weight, co
                                          ws::SMEM_TOTAL);                                                               \
     if (e != cudaSuccess) return cuda_fail(e, "lookup_conv1x1: shared-memory attribute");                               \
     corr1d_lookup_conv1x1_ws_kernel<F16, SK><<<static_cast<unsigned>(grid), ws::THREADS, ws::SMEM_TOTAL, stream>>>(     \
-        a, out_map, weight, bias, relu, total_px, per, skew_w1 > 0 ? skew_w1 : 1);                                      \
+        a, out_map, weight, bias, relu, total_px, per, skew_w1 > 0 ? skew_w1 : 1, 0x4b000000u << 2);                                      \
   } while (0)
   if (skew_w1 > 0) {
     if (out_f16) NND_WS_LAUNCH(true, true); else NND_WS_LAUNCH(false, true);
