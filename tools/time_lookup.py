@@ -56,6 +56,22 @@ def main():
         wt = blk.prepare_conv1x1_weight(conv.weight.detach())
         bias = conv.bias.detach()
         px = B * H * W
+        if not args.once:
+            # the pass that writes the skewed copy (read the row pyramid once, write it once)
+            ts = []
+            Wl = [W >> l for l in range(4)]
+            for _ in range(args.reps):
+                blk._skew = None
+                flush.fill_(1.0)
+                torch.cuda._sleep(200000)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                blk.skewed_pyramid()
+                e1.record(stream)
+                e1.synchronize()
+                ts.append(e0.elapsed_time(e1) * 1e3)
+            print(json.dumps({"B": B, "kernel": "corr1d_skew", "us_l2_flushed": statistics.median(ts),
+                              "bytes_read_plus_written": 2 * 4 * px * sum(Wl)}), flush=True)
         for layout, elem in ((2, 2), (1, 4)):
             out = torch.empty(B, H, W, 256, dtype=torch.float16 if layout == 2 else torch.float32, device=dev)
             nbytes = px * (164 + 256 * elem)
