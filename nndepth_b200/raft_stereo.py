@@ -756,11 +756,13 @@ class BasicUpdateBlock(nn.Module):
         self.mask = nn.Sequential(nn.Conv2d(hidden_dim, hidden_dim * 2, 3, padding=1), nn.ReLU(inplace=True),
                                   nn.Conv2d(hidden_dim * 2, sps * 9, 1))
 
-    def forward(self, net, inp, corr, flow, raw_mask=False, cor1=None, gru_run=None, coords=None, org=None):
+    def forward(self, net, inp, corr, flow, raw_mask=False, cor1=None, gru_run=None, coords=None, org=None, need_mask=True):
         """``raw_mask=True`` returns the mask logits without the last convolution's bias and without the reference's
         ``0.25 *`` (update_block.py:110): the fused upsampling kernel applies both, saving two passes over the
         (N,576,H,W) tensor.  With ``coords`` / ``org`` the third result is ``(coords + delta, coords + delta - org)``
-        (the loop's update, fused into the flow head's last convolution) instead of ``delta``."""
+        (the loop's update, fused into the flow head's last convolution) instead of ``delta``.  ``need_mask=False``
+        (``final_only`` forwards, every iteration but the last) skips the mask head: the mask only feeds the upsampling
+        of that iteration's prediction, never the recurrence."""
         if gru_run is not None:
             split = flow.is_cuda and not torch.is_grad_enabled() and hasattr(torch, "cudnn_convolution_relu")
             motion = self.encoder(flow, corr, cor1=cor1, split_flow=split, half=split and getattr(gru_run, "half", False))
@@ -770,6 +772,8 @@ class BasicUpdateBlock(nn.Module):
             motion = self.encoder(flow, corr, cor1=cor1)
             net = self.gru(net, torch.cat((inp, motion), dim=1))
         net16 = getattr(gru_run, "h16", None) if (gru_run is not None and raw_mask and coords is not None) else None
+        if not need_mask:
+            return net, None, self.flow_head(net16 if net16 is not None else net, coords, org)
         if net16 is not None:
             # fp16 recurrence: the heads read the fp16 copy of the new hidden state and run as fp16 convolutions too
             # (same operand mantissa as TF32, twice the rate); the logits stay fp16 for the fused upsampling kernel
@@ -952,15 +956,18 @@ class RAFTStereo(nn.Module):
             fused = coords1.is_cuda and fnet_ds in (2, 4, 8) and not torch.is_grad_enabled()
             if it == 0:
                 flow = coords1 - org_coords
+            want_up = not self.final_only or it == self.iters - 1
             if fused:
                 # the flow head's last convolution also writes the new coordinates and the new flow
                 net, mask, (coords1, flow) = self.update_block(net, inp, sampled, flow, raw_mask=True, cor1=cor1,
-                                                               gru_run=gru_run, coords=coords1, org=org_coords)
+                                                               gru_run=gru_run, coords=coords1, org=org_coords,
+                                                               need_mask=want_up)
             else:
-                net, mask, delta = self.update_block(net, inp, sampled, flow, raw_mask=False, cor1=cor1, gru_run=gru_run)
+                net, mask, delta = self.update_block(net, inp, sampled, flow, raw_mask=False, cor1=cor1, gru_run=gru_run,
+                                                     need_mask=want_up)
                 coords1 = coords1 + delta
                 flow = coords1 - org_coords
-            if not self.final_only or it == self.iters - 1:
+            if want_up:
                 if fused:
                     up = fused_convex_upsample(flow, mask, rate=fnet_ds, mask_scale=0.25,
                                                mask_bias=self.update_block.mask[2].bias)

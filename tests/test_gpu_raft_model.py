@@ -66,6 +66,23 @@ def test_kitti_32_iterations(golden, precision):
     assert epe(graphed, ref) < EPE_BAR, epe(graphed, ref)
 
 
+@pytest.mark.parametrize("mode", ["mixed16", "fp32"])
+def test_final_only_gives_the_same_last_prediction(golden, mode):
+    """``final_only`` skips the mask head and the upsampling of every iteration but the last: the mask
+    never feeds the recurrence, so the last prediction must be BIT-identical to the full forward's."""
+    g = golden("raft_kitti")
+    left, right = (t.cuda() for t in seeded_pair(g["shape"]))
+    outs = []
+    for final_only in (False, True):
+        model = build(g, final_only=final_only)
+        model.dense_precision = mode
+        with torch.no_grad():
+            preds = model(left, right)
+        assert len(preds) == (1 if final_only else model.iters)
+        outs.append(preds[-1]["up_disp"])
+    assert torch.equal(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("mode,bar", [("fp32", 0.001), ("mixed", EPE_BAR), ("mixed2x", EPE_BAR), ("mixed16", EPE_BAR)])
 def test_kitti_dense_precision_modes(golden, mode, bar):
     """The bench's dense-layer precision modes against the reference disparity (KITTI geometry, 32 iterations):
