@@ -565,7 +565,7 @@ template <bool SMALL>
 struct IterTile {
   static constexpr int TH = SMALL ? 3 : 1;
 #ifndef NND_AGCL_TW
-#define NND_AGCL_TW 80
+#define NND_AGCL_TW 40        // 1x9 tiles: 4 per 160-pixel row, 1 440 CTAs = 4.9 waves of 296 (80: 2.4 waves, 62.5 vs 58.4 us)
 #endif
 #ifndef NND_AGCL_THREADS
 #define NND_AGCL_THREADS 512
@@ -573,6 +573,7 @@ struct IterTile {
 #ifndef NND_AGCL_MINB
 #define NND_AGCL_MINB 2
 #endif
+
   static constexpr int TW = SMALL ? 16 : NND_AGCL_TW;
   static constexpr int HX = SMALL ? 1 : 4;
   static constexpr int HY = SMALL ? 1 : 0;
@@ -599,7 +600,6 @@ agcl_iter_fused_kernel(const float* __restrict__ L, const float* __restrict__ R,
   const int x0 = blockIdx.x * T::TW, y0 = blockIdx.y * T::TH;
   const long long hw = static_cast<long long>(H) * W;
   const float* fl = flow + static_cast<long long>(n) * 2 * hw;
-
   // phase 0: footprints of the staged pixels that lie inside the image.  An out-of-image corner contributes exactly
   // zero (zero padding): it gets weight 0 and points at pixel 0, so the gather below is predicate-free.
   for (int s = tid; s < NS; s += T::THREADS) {
@@ -622,12 +622,26 @@ agcl_iter_fused_kernel(const float* __restrict__ L, const float* __restrict__ R,
   }
   __syncthreads();
 
+  // the left vector of this warp's first output pixel is put in flight before the barrier, every later one while its
+  // predecessor is being correlated: their DRAM latency never sits between two pixels
+  auto load_left = [&](int i, float4 (&dst)[V]) {
+    const int ty = i / T::TW, tx = i - ty * T::TW;
+    const int x = x0 + tx, y = y0 + ty;
+    const bool ok = i < NP && x < W && y < H;
+    const float* lp = L + (static_cast<long long>(n) * hw + (ok ? y * W + x : 0)) * C + 4 * lane;
+#pragma unroll
+    for (int j = 0; j < V; ++j) dst[j] = ok ? ldg_f4(lp + 128 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  float4 lv[V], lnext[V];
   // phase 1: warp per staged pixel: 4 V independent 16-byte gathers per lane, blended in the reference's order
   // lane -> float4 number lane + 32 j of a pixel's channel vector: every warp instruction moves 512 contiguous bytes
   const float* rb = R + static_cast<long long>(n) * hw * C + 4 * lane;
   for (int s = warp; s < NS; s += NW) {
     const WarpFootprint f = fp[s];
     if (f.off[0] < 0) continue;                               // outside the image: never read (taps are clamped into it)
+#ifdef NND_AGCL_SKIP_STAGE                                  // timing probe: no gathers of the right map
+    continue;
+#endif
     float4 v[4][V];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
@@ -642,17 +656,6 @@ agcl_iter_fused_kernel(const float* __restrict__ L, const float* __restrict__ R,
           make_float4(blend(vx, f.wt), blend(vy, f.wt), blend(vz, f.wt), blend(vw, f.wt));
     }
   }
-  // the left vector of this warp's first output pixel is put in flight before the barrier, every later one while its
-  // predecessor is being correlated: their DRAM latency never sits between two pixels
-  auto load_left = [&](int i, float4 (&dst)[V]) {
-    const int ty = i / T::TW, tx = i - ty * T::TW;
-    const int x = x0 + tx, y = y0 + ty;
-    const bool ok = i < NP && x < W && y < H;
-    const float* lp = L + (static_cast<long long>(n) * hw + (ok ? y * W + x : 0)) * C + 4 * lane;
-#pragma unroll
-    for (int j = 0; j < V; ++j) dst[j] = ok ? ldg_f4(lp + 128 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-  };
-  float4 lv[V], lnext[V];
   load_left(warp, lnext);
   __syncthreads();
 
@@ -669,6 +672,10 @@ agcl_iter_fused_kernel(const float* __restrict__ L, const float* __restrict__ R,
     for (int j = 0; j < V; ++j) lv[j] = lnext[j];
     load_left(i + NW, lnext);
     if (x >= W || y >= H) continue;                          // warp-uniform
+#ifdef NND_AGCL_SKIP_TAPS                                   // timing probe: staging + left loads + output only
+    if (lv[0].x == 123456.f) res[i] = lv[V - 1].y;
+    continue;
+#endif
     float acc[V][AGCL_TAPS];
 #pragma unroll
     for (int k = 0; k < AGCL_TAPS; ++k) {
