@@ -434,7 +434,8 @@ class GroupCorrBlock1D:
     Reproduces the reference's quirks: ``torch.split(fmap, num_groups)`` makes chunks *of size*
     ``num_groups`` and only the first ``num_groups`` chunks are read (:115-121); the scale is
     ``1/sqrt(C_total)`` (:125); the looked-up block ``[b][g][h][w][k]`` is reinterpreted as
-    ``(B, H, W, G*(2r+1))`` (:108).
+    ``(B, H, W, G*(2r+1))`` (:108).  Any ``num_groups`` from 1 to 16 (every value with ``G * G <= C`` at C <= 256) and
+    32 is built by its own instantiation of the kernel; other values raise ``NNDepthError`` (NND_ERR_UNSUPPORTED).
     """
 
     def __init__(self, fmap1, fmap2, num_levels=4, radius=4, num_groups=4):

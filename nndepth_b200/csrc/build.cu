@@ -125,7 +125,7 @@ corr1d_build_fp32_kernel(const float* __restrict__ f1, const float* __restrict__
 // and a warp store covers four full 128-byte row segments.  The pooled levels come out of the same
 // registers (levels 1-2 in-thread, level 3 with one shuffle).
 // ------------------------------------------------------------------------------------------------
-__host__ __device__ constexpr int gc_rows_per_thread(int k) { return k <= 8 ? 4 : k == 16 ? 2 : 1; }  // a[TR][K] must stay in registers
+__host__ __device__ constexpr int gc_rows_per_thread(int k) { return k <= 8 ? 4 : k <= 16 ? 2 : 1; }  // a[TR][K] must stay in registers
 
 template <int K>
 __global__ void __launch_bounds__(256)
@@ -445,15 +445,27 @@ nnd_status nnd_groupcorr_build(const float* fmap1, const float* fmap2, int B, in
     groupcorr_build_kernel<KK><<<static_cast<unsigned>(blocks), 32 * gc_warps, smem, stream>>>(                   \
         fmap1, fmap2, C, num_groups, H, W1, W2, scale_div, 1.0f / scale_div, num_levels, pyr, vec_ok ? 1 : 0);    \
   } while (0)
+  // every group size the reference's split quirk can produce with C <= 256 (G * G <= C: 1..16), and 32
   switch (group_size) {
     case 1: NND_LAUNCH_GROUP(1); break;
     case 2: NND_LAUNCH_GROUP(2); break;
+    case 3: NND_LAUNCH_GROUP(3); break;
     case 4: NND_LAUNCH_GROUP(4); break;
+    case 5: NND_LAUNCH_GROUP(5); break;
+    case 6: NND_LAUNCH_GROUP(6); break;
+    case 7: NND_LAUNCH_GROUP(7); break;
     case 8: NND_LAUNCH_GROUP(8); break;
+    case 9: NND_LAUNCH_GROUP(9); break;
+    case 10: NND_LAUNCH_GROUP(10); break;
+    case 11: NND_LAUNCH_GROUP(11); break;
+    case 12: NND_LAUNCH_GROUP(12); break;
+    case 13: NND_LAUNCH_GROUP(13); break;
+    case 14: NND_LAUNCH_GROUP(14); break;
+    case 15: NND_LAUNCH_GROUP(15); break;
     case 16: NND_LAUNCH_GROUP(16); break;
     case 32: NND_LAUNCH_GROUP(32); break;
     default:
-      set_error("groupcorr_build: group_size %d unsupported (1, 2, 4, 8, 16, 32)", group_size);
+      set_error("groupcorr_build: group_size %d unsupported (1..16, 32)", group_size);
       return NND_ERR_UNSUPPORTED;
   }
 #undef NND_LAUNCH_GROUP

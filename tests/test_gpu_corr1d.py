@@ -489,3 +489,30 @@ def test_randomised_lookup_sweep_bit_exact():
         for lvl, (o0, o1) in enumerate(oc.lookup_indices([W2 >> l for l in range(L)], coords, L, r)):
             np.testing.assert_array_equal(i0[lvl].cpu().numpy(), o0)
             np.testing.assert_array_equal(i1[lvl].cpu().numpy(), o1)
+
+
+@pytest.mark.parametrize("G", [3, 5, 6, 12])
+def test_group_block_any_group_count_against_reference(G):
+    """The reference accepts any ``num_groups`` with G * G <= C (its split quirk reads G chunks of G channels,
+    cost_volume.py:115-121); so does the kernel (group sizes 1..16 are instantiated)."""
+    ref_shim = pytest.importorskip("oracle.ref_shim")
+    if not ref_shim.available():
+        pytest.skip("the vendored reference (oracle/_ref) is not staged")
+    ref_shim.install()
+    import nndepth_b200 as nb
+    from nndepth.models.raft_stereo.cost_volume import GroupCorrBlock1D as RefGroup
+    B, C, H, W = 2, 160, 3, 40
+    torch.manual_seed(G)
+    f1, f2 = torch.randn(B, C, H, W, device="cuda"), torch.randn(B, C, H, W, device="cuda")
+    grid = torch.arange(W, device="cuda").float().view(1, 1, 1, W).repeat(B, 1, H, 1)
+    coords = grid - torch.rand(B, 1, H, W, device="cuda") * 12
+    old = nb.get_volume_precision()
+    nb.set_volume_precision("fp32")
+    try:
+        got = nb.GroupCorrBlock1D(f1, f2, 4, 4, G)(coords)
+    finally:
+        nb.set_volume_precision(old)
+    want = RefGroup(f1.double(), f2.double(), 4, 4, G)(coords.double())
+    assert got.shape == want.shape
+    scale = want.abs().max().item()
+    assert (got.double() - want).abs().max().item() <= 1e-5 * scale
