@@ -353,10 +353,12 @@ def time_fused_lookup(device, B, out_elem, peak, reps=10):
     stream = torch.cuda.current_stream(device)
     nbytes = B * H * W * (164 + 256 * out_elem)
 
-    def timed(coords, skewed):
+    def timed(coords, skewed, elem=out_elem):
+        nbytes = B * H * W * (164 + 256 * elem)
+
         def launch():
             return blk.lookup_conv1x1(coords, None, bias, relu=True, weight_t=wt, precision="tf32", channels_last=True,
-                                      half=out_elem == 2, skewed=skewed)
+                                      half=elem == 2, skewed=skewed)
         for _ in range(3):
             launch()
         ts = []
@@ -370,12 +372,17 @@ def time_fused_lookup(device, B, out_elem, peak, reps=10):
             e1.synchronize()
             ts.append(e0.elapsed_time(e1) * 1e3)
         us = statistics.median(ts)
-        return {"us_per_launch_l2_flushed": us, "achieved_gbs": nbytes / us / 1e3, "frac": nbytes / us / 1e3 / peak}
+        res = {"us_per_launch_l2_flushed": us, "achieved_gbs": nbytes / us / 1e3, "frac": nbytes / us / 1e3 / peak}
+        if elem != out_elem:
+            res["algorithmic_bytes_per_launch"] = nbytes
+        return res
 
     rows_noise = timed(noise, False)
     out = {"batch": B, "pixels": B * H * W, "algorithmic_bytes_per_launch": nbytes, **rows_noise,
            "coords": "white noise: x - U(0, 40), row layout",
            "smooth_field_row_layout": timed(smooth, False), "smooth_field_skewed_layout": timed(smooth, True),
+           # the reference's own output dtype (the fp16 output above belongs to the mixed16 step)
+           "fp32_output": {"white_noise_row_layout": timed(noise, False, 4), "smooth_field_skewed_layout": timed(smooth, True, 4)},
            "note": "skewed layout = nnd_corr1d_skew + nnd_corr1d_lookup_conv1x1_skewed (S[j][w1], j = ((w1 >> l) - w2) mod W2_l): "
                    "ncu DRAM read 105 MB vs 268 MB on the row layout for 79 MB of window data (profiles/r2_lookup_ws_b64_summary.txt); "
                    "bit-identical results; pays for smooth fields only"}
