@@ -17,6 +17,12 @@
 
 namespace nnd {
 
+__device__ __forceinline__ float ex2_approx(float x) {  // 2**x, MUFU.EX2 (what __expf uses after its multiply)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int RATE>
 __global__ void __launch_bounds__(32 * RATE)
 convex_upsample_kernel(const float* __restrict__ flow, const float* __restrict__ mask, const float* __restrict__ mask_bias,
@@ -69,70 +75,110 @@ convex_upsample_kernel(const float* __restrict__ flow, const float* __restrict__
 }
 
 // Channels-last mask (N, H, W, 9*RATE*RATE) -- what cuDNN hands back when the hidden state is channels-last.
-// Half a warp per coarse pixel: the pixel's 9*64 logits are 2304 contiguous bytes; lane = (pixel of the pair,
-// sub-row i, column quad) reads 16 bytes per neighbour k (a warp load covers 2 x 256 contiguous bytes) and
-// writes four outputs as one 16-byte store.
-// MASK_F16: the logits are IEEE fp16 (the mask head run as fp16 convolutions); a pixel's row is then 1152 bytes.
+// A pixel's 9*64 logits are contiguous (2304 bytes fp32, 1152 bytes fp16 when the mask head ran as fp16 convolutions).
+// lane = (pixel of the warp's 2 or 4, sub-row i, column group): 16 bytes per neighbour k and lane -- four fp32 or
+// eight fp16 logits -- so every warp load covers 512 contiguous bytes and a warp stores whole 64 / 128-byte output row
+// segments.  The kernel is ISSUE-bound (ncu: 27.6 M warp instructions, issue slots 73 % busy for 138 MB), so the
+// arithmetic per logit is kept to add-bias, max, one FMA into the exp2 argument, MUFU.EX2, add, FMA:
+//     softmax_k(s * t_k) = exp2(t_k * S - m * S) / sum,   t = logit + bias,  m = max_k t,  S = s * log2(e)  (s > 0)
+// and all index arithmetic is 32-bit (the launcher checks the sizes).
 template <int MASK_F16>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 convex_upsample_nhwc8_kernel(const float* __restrict__ flow, const void* __restrict__ mask_, const float* __restrict__ mask_bias,
-                             int H, int W, long long n_pix, float mask_scale, float* __restrict__ out) {
+                             int H, int W, unsigned n_pix, float mask_scale, float* __restrict__ out) {
   constexpr int RATE = 8;
-  const int lane = threadIdx.x & 31;
-  const int half = lane >> 4, i = (lane >> 1) & 7, jq = lane & 1;
-  const long long hw = static_cast<long long>(H) * W;
-  const long long warp0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-  const float4* bp = mask_bias ? reinterpret_cast<const float4*>(mask_bias + i * RATE + 4 * jq) : nullptr;  // L1-resident
-  for (long long pair = warp0; 2 * pair < n_pix; pair += n_warps) {
-    const long long pix = 2 * pair + half;
-    if (pix >= n_pix) continue;
-    const long long n = pix / hw;
-    const long long p = pix - n * hw;
-    const int h = static_cast<int>(p / W), w = static_cast<int>(p - static_cast<long long>(h) * W);
-    const float* fl = flow + n * hw;
-    const long long quad0 = (pix * (9 * RATE * RATE) + i * RATE + 4 * jq) / 4;   // index in units of 4 logits
-    float4 x[9];
+  constexpr int CPL = MASK_F16 ? 8 : 4;            // output columns per lane
+  constexpr int LPP = RATE * RATE / CPL;           // lanes per pixel: 8 (fp16) or 16 (fp32)
+  constexpr int PPW = 32 / LPP;                    // pixels per warp: 4 or 2
+  constexpr int LPR = RATE / CPL;                  // lanes per sub-row: 1 or 2
+  constexpr int UPP = 9 * RATE * RATE / (MASK_F16 ? 8 : 4);   // 16-byte units per pixel
+  constexpr int UPK = RATE * RATE / (MASK_F16 ? 8 : 4);       // ... per neighbour k
+  // The logits travel global -> shared with cp.async, one 16-byte unit per lane and neighbour, two pixel groups in
+  // flight per warp: the NEXT group's 4.6 KB are on their way while this one is computed, and they occupy no registers
+  // (every lane reads back only what it copied itself, so the stage needs no barrier, only cp.async.wait_group).
+  extern __shared__ uint4 up_stage[];              // [warp][2][9][32]
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  uint4* mine = up_stage + wib * (2 * 9 * 32) + lane;
+  const int sub = lane / LPP, r = lane % LPP, i = r / LPR, jq = r % LPR;
+  const unsigned hw = static_cast<unsigned>(H) * static_cast<unsigned>(W);
+  const unsigned warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
+  const float S = mask_scale * 1.4426950408889634f;
+  const float4* bp = mask_bias ? reinterpret_cast<const float4*>(mask_bias + i * RATE + CPL * jq) : nullptr;  // L1-resident
+  const uint4* units = reinterpret_cast<const uint4*>(mask_) + (MASK_F16 ? i : 2 * i + jq);
+
+  auto issue = [&](unsigned grp, int buf) {
+    const unsigned pix = grp * PPW + sub;
+    if (grp * PPW < n_pix && pix < n_pix) {
+      const uint4* src = units + static_cast<size_t>(pix) * UPP;
+      const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(mine + buf * (9 * 32)));
+#pragma unroll
+      for (int k = 0; k < 9; ++k)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + k * 512), "l"(src + k * UPK) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  issue(warp0, 0);
+  int buf = 0;
+  for (unsigned grp = warp0; grp * PPW < n_pix; grp += n_warps, buf ^= 1) {
+    issue(grp + n_warps, buf ^ 1);
+    const unsigned pix = grp * PPW + sub;
+    const bool live = pix < n_pix;
+    const unsigned n = live ? pix / hw : 0, p = live ? pix - n * hw : 0;
+    const int h = static_cast<int>(p / static_cast<unsigned>(W)), w = static_cast<int>(p - static_cast<unsigned>(h) * W);
+    const float* fl = flow + static_cast<size_t>(n) * hw;
     float nb[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-      if (MASK_F16) {
-        x[k] = unpack_h4(__ldcs(reinterpret_cast<const uint2*>(mask_) + quad0 + k * (RATE * RATE / 4)));
-      } else {
-        x[k] = __ldcs(reinterpret_cast<const float4*>(mask_) + quad0 + k * (RATE * RATE / 4));
-      }
       const int hh = h + k / 3 - 1, ww = w + k % 3 - 1;
-      nb[k] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __fmul_rn(8.0f, __ldg(fl + static_cast<long long>(hh) * W + ww)) : 0.f;
+      nb[k] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __fmul_rn(8.0f, __ldg(fl + hh * W + ww)) : 0.f;
     }
-    if (bp) {
+    asm volatile("cp.async.wait_group 1;" ::: "memory");       // this group's logits have landed
+    if (!live) continue;
+    const uint4* st = mine + buf * (9 * 32);
+    float* op = out + (static_cast<size_t>(n) * RATE * H + static_cast<size_t>(RATE) * h + i) * (static_cast<size_t>(RATE) * W) +
+                static_cast<size_t>(RATE) * w + CPL * jq;
+#pragma unroll
+    for (int g4 = 0; g4 < CPL / 4; ++g4) {
+      float4 t[9];
 #pragma unroll
       for (int k = 0; k < 9; ++k) {
-        const float4 bk = __ldg(bp + k * (RATE * RATE / 4));
-        x[k].x += bk.x; x[k].y += bk.y; x[k].z += bk.z; x[k].w += bk.w;
+        if (MASK_F16) {
+          const uint2 hq = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(st + k * 32) + 8 * g4);
+          t[k] = unpack_h4(hq);
+        } else {
+          const uint4 q = st[k * 32];
+          t[k] = make_float4(__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w));
+        }
+        if (bp) {
+          const float4 bk = __ldg(bp + k * (RATE * RATE / 4) + g4);
+          t[k].x += bk.x; t[k].y += bk.y; t[k].z += bk.z; t[k].w += bk.w;
+        }
       }
-    }
-    float res[4];
+      float res[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float v[9];
+      for (int e = 0; e < 4; ++e) {
+        float v[9];
 #pragma unroll
-      for (int k = 0; k < 9; ++k) v[k] = (e == 0 ? x[k].x : e == 1 ? x[k].y : e == 2 ? x[k].z : x[k].w) * mask_scale;
-      float m = v[0];
+        for (int k = 0; k < 9; ++k) v[k] = e == 0 ? t[k].x : e == 1 ? t[k].y : e == 2 ? t[k].z : t[k].w;
+        float m = v[0];
 #pragma unroll
-      for (int k = 1; k < 9; ++k) m = fmaxf(m, v[k]);
-      float s = 0.f, a = 0.f;
+        for (int k = 1; k < 9; ++k) m = fmaxf(m, v[k]);
+        const float mS = -m * S;
+        float sum = 0.f, a = 0.f;
 #pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        const float ex = __expf(v[k] - m);
-        s += ex;
-        a = fmaf(ex, nb[k], a);
+        for (int k = 0; k < 9; ++k) {
+          const float ex = ex2_approx(fmaf(v[k], S, mS));
+          sum += ex;
+          a = fmaf(ex, nb[k], a);
+        }
+        res[e] = a / sum;
       }
-      res[e] = a / s;
+      *reinterpret_cast<float4*>(op + 4 * g4) = make_float4(res[0], res[1], res[2], res[3]);
     }
-    float* op = out + (n * RATE * H + static_cast<long long>(RATE) * h + i) * (static_cast<long long>(RATE) * W) +
-                static_cast<long long>(RATE) * w + 4 * jq;
-    *reinterpret_cast<float4*>(op) = make_float4(res[0], res[1], res[2], res[3]);
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 }  // namespace nnd
@@ -156,12 +202,22 @@ nnd_status nnd_convex_upsample(const float* flow, const void* mask, const float*
     NND_REQUIRE(aligned16(mask) && aligned16(out) && (!mask_bias || aligned16(mask_bias)),
                 "convex_upsample: mask, bias and output must be 16-byte aligned");
     const long long n_pix = hw * N;
-    const long long want = (n_pix + 15) / 16, cap = static_cast<long long>(sm_count()) * 8;
+    NND_REQUIRE(n_pix < (1LL << 31) / 64, "convex_upsample: %lld pixels exceed the kernel's 32-bit pixel arithmetic", n_pix);
+    NND_REQUIRE(mask_scale > 0.f, "convex_upsample: the channels-last path folds mask_scale into the softmax and needs it positive");
+    const int per_block = mask_layout == 2 ? 32 : 16;     // pixels per block of 8 warps
+    // one wave of resident blocks (3 per SM by the launch bounds): every warp then loops over ~4 pixel groups and its
+    // cp.async pipeline has something to hide
+    const long long want = (n_pix + per_block - 1) / per_block, cap = static_cast<long long>(sm_count()) * 3;
     const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
+    constexpr int stage_bytes = 8 * 2 * 9 * 32 * 16;      // 8 warps x 2 groups x 9 neighbours x 512 bytes
     if (mask_layout == 2) {
-      convex_upsample_nhwc8_kernel<1><<<grid, 256, 0, stream>>>(flow, mask, mask_bias, H, W, n_pix, mask_scale, out);
+      cudaError_t e = cudaFuncSetAttribute(convex_upsample_nhwc8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage_bytes);
+      if (e != cudaSuccess) return cuda_fail(e, "convex_upsample: shared-memory attribute");
+      convex_upsample_nhwc8_kernel<1><<<grid, 256, stage_bytes, stream>>>(flow, mask, mask_bias, H, W, static_cast<unsigned>(n_pix), mask_scale, out);
     } else {
-      convex_upsample_nhwc8_kernel<0><<<grid, 256, 0, stream>>>(flow, mask, mask_bias, H, W, n_pix, mask_scale, out);
+      cudaError_t e = cudaFuncSetAttribute(convex_upsample_nhwc8_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage_bytes);
+      if (e != cudaSuccess) return cuda_fail(e, "convex_upsample: shared-memory attribute");
+      convex_upsample_nhwc8_kernel<0><<<grid, 256, stage_bytes, stream>>>(flow, mask, mask_bias, H, W, static_cast<unsigned>(n_pix), mask_scale, out);
     }
     return check_launch("convex_upsample_nhwc8_kernel");
   }
