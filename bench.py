@@ -377,12 +377,32 @@ def time_fused_lookup(device, B, out_elem, peak, reps=10):
             res["algorithmic_bytes_per_launch"] = nbytes
         return res
 
+    def timed_plain(coords):
+        # the drop-in CorrBlock1D.__call__ itself ((B, 36, H, W) fp32 out, 308 B / pixel)
+        nb_plain = B * H * W * LOOKUP_BYTES_PER_PIXEL
+        for _ in range(3):
+            blk(coords)
+        ts = []
+        for _ in range(reps):
+            flush.fill_(1.0)
+            torch.cuda._sleep(200000)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            blk(coords)
+            e1.record(stream)
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        us = statistics.median(ts)
+        return {"us_per_launch_l2_flushed": us, "algorithmic_bytes_per_launch": nb_plain, "achieved_gbs": nb_plain / us / 1e3,
+                "frac": nb_plain / us / 1e3 / peak}
+
     rows_noise = timed(noise, False)
     out = {"batch": B, "pixels": B * H * W, "algorithmic_bytes_per_launch": nbytes, **rows_noise,
            "coords": "white noise: x - U(0, 40), row layout",
            "smooth_field_row_layout": timed(smooth, False), "smooth_field_skewed_layout": timed(smooth, True),
            # the reference's own output dtype (the fp16 output above belongs to the mixed16 step)
            "fp32_output": {"white_noise_row_layout": timed(noise, False, 4), "smooth_field_skewed_layout": timed(smooth, True, 4)},
+           "plain_lookup_corr1d_lookup_lean_kernel": {"white_noise": timed_plain(noise), "smooth_field": timed_plain(smooth)},
            "note": "skewed layout = nnd_corr1d_skew + nnd_corr1d_lookup_conv1x1_skewed (S[j][w1], j = ((w1 >> l) - w2) mod W2_l): "
                    "ncu DRAM read 105 MB vs 268 MB on the row layout for 79 MB of window data (profiles/r2_lookup_ws_b64_summary.txt); "
                    "bit-identical results; pays for smooth fields only"}

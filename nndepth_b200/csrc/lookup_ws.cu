@@ -7,18 +7,21 @@
 //
 // The (B, 36, H, W) lookup tensor never exists in HBM, and no warp ever waits for another role:
 //
-//   warps  0-15  PRODUCERS   warp = (32-pixel group of the 128-pixel tile, pyramid level).  cp.async gathers the 32
-//                            windows of the NEXT tile into a private double buffer (4 lanes x 16 bytes per window,
-//                            coordinates prefetched two tiles ahead), interpolates the 9 taps of the current tile with
-//                            the reference's exact fp32 operation order (bit-exact indices) and writes them, rounded
-//                            to nearest TF32, straight into the A operand's core-matrix layout: K is laid out as
-//                            4 levels x 12 columns (9 taps + 3 zeros), so a thread's taps are three 16-byte stores.
+//   warps  0-15  PRODUCERS   warp = (32-pixel group of the 128-pixel tile, pyramid level); the four level-warps of a group
+//                            sit on the four SM sub-partitions.  cp.async gathers the 32 windows of the NEXT tile into a
+//                            private double buffer (4 lanes x 16 bytes per window, from a conservative 4-aligned start
+//                            that needs no exact tap; coordinates prefetched two tiles ahead), interpolates the 9 taps of
+//                            the current tile with the reference's exact fp32 operation order (bit-exact indices; one
+//                            clamp per pixel, floor through FADD.RZ) and writes them, rounded to nearest TF32, straight
+//                            into the A operand's core-matrix layout: K is laid out as 4 levels x 12 columns (9 taps +
+//                            3 spare; level 0's spare columns carry 1.0 against the bias rows of the weight operand),
+//                            so a thread's taps are three 16-byte stores.
 //   warp   24    MMA         one thread: 6 x tcgen05.mma kind::tf32 (M 128 pixels, N 256 channels, K 8) per tile into
 //                            one of two 256-column TMEM accumulators; tcgen05.commit releases the A slot to the
 //                            producers and hands the accumulator to the epilogue.
 //   warps 16-23  EPILOGUE    warp = (TMEM lane quarter, half of the 256 channels).  Per tile: tcgen05.ld 32 columns ->
-//                            + bias -> ReLU -> fp16 / fp32 -> a 32-row x 128-byte box in the 128B-swizzle layout ->
-//                            one TMA store (cp.async.bulk.tensor.2d) per box into the channels-last output: no
+//                            ReLU + fp16 in one conversion (or fp32) -> a 32-row x 128-byte box in the 128B-swizzle
+//                            layout -> one TMA store (cp.async.bulk.tensor.2d) per box into the channels-last output: no
 //                            read-back of the staging tile, no per-thread global stores.
 //
 // mbarrier pipelines: a_full / a_empty (producers <-> MMA, ring of NA operand slots), tmem_full / tmem_empty (MMA <->
@@ -55,8 +58,7 @@ constexpr int SMEM_B = 0;
 constexpr int SMEM_A = SMEM_B + KSTEPS * B_KSTEP_BYTES;                       // 48 KB
 constexpr int SMEM_WIN = SMEM_A + NA * A_SLOT_BYTES;                          // + 48 KB
 constexpr int SMEM_STAGE = SMEM_WIN + PROD_WARPS * 2 * WIN_BUF_FLOATS * 4;    // + 80 KB
-constexpr int SMEM_BIAS = SMEM_STAGE + EPI_WARPS * STAGE_WARP_BYTES;          // + 32 KB (1024-byte aligned boxes)
-constexpr int SMEM_BAR = SMEM_BIAS + NOUT * 4;
+constexpr int SMEM_BAR = SMEM_STAGE + EPI_WARPS * STAGE_WARP_BYTES;           // + 32 KB (1024-byte aligned boxes)
 constexpr int SMEM_TOTAL = SMEM_BAR + 128;
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
