@@ -377,18 +377,18 @@ def time_fused_lookup(device, B, out_elem, peak, reps=10):
             res["algorithmic_bytes_per_launch"] = nbytes
         return res
 
-    def timed_plain(coords):
+    def timed_plain(coords, skewed=False):
         # the drop-in CorrBlock1D.__call__ itself ((B, 36, H, W) fp32 out, 308 B / pixel)
         nb_plain = B * H * W * LOOKUP_BYTES_PER_PIXEL
         for _ in range(3):
-            blk(coords)
+            blk(coords, skewed=skewed)
         ts = []
         for _ in range(reps):
             flush.fill_(1.0)
             torch.cuda._sleep(200000)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            blk(coords)
+            blk(coords, skewed=skewed)
             e1.record(stream)
             e1.synchronize()
             ts.append(e0.elapsed_time(e1) * 1e3)
@@ -402,7 +402,10 @@ def time_fused_lookup(device, B, out_elem, peak, reps=10):
            "smooth_field_row_layout": timed(smooth, False), "smooth_field_skewed_layout": timed(smooth, True),
            # the reference's own output dtype (the fp16 output above belongs to the mixed16 step)
            "fp32_output": {"white_noise_row_layout": timed(noise, False, 4), "smooth_field_skewed_layout": timed(smooth, True, 4)},
-           "plain_lookup_corr1d_lookup_lean_kernel": {"white_noise": timed_plain(noise), "smooth_field": timed_plain(smooth)},
+           "plain_lookup": {"kernels": "corr1d_lookup_lean_kernel<9> (row layout) / corr1d_lookup_skewed_kernel<9>",
+                            "white_noise_row_layout": timed_plain(noise), "smooth_field_row_layout": timed_plain(smooth),
+                            "smooth_field_skewed_layout": timed_plain(smooth, True),
+                            "white_noise_skewed_layout": timed_plain(noise, True)},
            "note": "skewed layout = nnd_corr1d_skew + nnd_corr1d_lookup_conv1x1_skewed (S[j][w1], j = ((w1 >> l) - w2) mod W2_l): "
                    "ncu DRAM read 105 MB vs 268 MB on the row layout for 79 MB of window data (profiles/r2_lookup_ws_b64_summary.txt); "
                    "bit-identical results; pays for smooth fields only"}

@@ -112,6 +112,10 @@ nnd_status nnd_corr1d_lookup_conv1x1(const float* const* level, const int* width
  * channels-last output: out_layout 1 = fp32, 2 = fp16) reading the skewed copy; results are bit-identical. */
 nnd_status nnd_corr1d_skew(const float* const* level, const int* width, const int* pitch, int B, int H, int W1,
                            int num_levels, float* const* skewed, int skew_pitch, nnd_stream_t stream);
+/* nnd_corr1d_lookup_skewed == nnd_corr1d_lookup (RAFT-Stereo form: one plane, radius 4; CorrBlock1D.__call__,
+ * raft_stereo/cost_volume.py:36-53) reading the skewed copy: out (B, L*9, H, W1) fp32, bit-identical. */
+nnd_status nnd_corr1d_lookup_skewed(const float* const* skewed, const int* width, int skew_pitch, const float* coords, int B,
+                                    int H, int W1, int num_levels, int radius, float* out, nnd_stream_t stream);
 nnd_status nnd_corr1d_lookup_conv1x1_skewed(const float* const* skewed, const int* width, int skew_pitch,
                                             const float* coords, int B, int H, int W1, int num_levels, int radius,
                                             const float* weight, const float* bias, int c_out, int relu, int out_layout,

@@ -43,6 +43,7 @@ SIGNATURES = {
     "nnd_avgpool_pairs_backward": (_I, [_P, _I, _I, _P, _I, ctypes.c_int64, _P]),
     "nnd_corr1d_skew": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _I, _P]),
     "nnd_corr1d_lookup_conv1x1_skewed": (_I, [_P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _I, _P, _P]),
+    "nnd_corr1d_lookup_skewed": (_I, [_P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P]),
     "nnd_volume_grad": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _I, ctypes.c_float, _I, _P, _P]),
     "nnd_corr1d_lookup_indices": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "nnd_group_lookup": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),

@@ -312,11 +312,18 @@ class CorrBlock1D:
     def corr_pyramid(self):
         return self._pyr.reference_view()
 
-    def __call__(self, coords):
+    def __call__(self, coords, skewed=False):
+        """``skewed=True`` (inference, radius 4) reads the skewed copy of the pyramid instead (``skewed_pyramid()``): the
+        same values bit for bit, with a third of the DRAM traffic when the disparity field is smooth."""
         B, H, W1, _ = self._shape
         if self._graph_buffer is not None and torch.is_grad_enabled():
             coords = _check_coords(coords.detach(), B, H, W1)     # the reference detaches them too (model.py:131)
             return _LookupPyramid.apply(self._graph_buffer, coords, self)
+        if skewed:
+            if self.radius != 4:
+                raise ValueError("the skewed lookup is built for radius 4")
+            return _lib.ops().corr1d_lookup_skewed(self.skewed_pyramid(), self._shape[3], _check_coords(coords, B, H, W1),
+                                                   self.num_levels, self.radius)
         return self._lookup_raw(_check_coords(coords, B, H, W1))
 
     def _lookup_raw(self, coords):
@@ -331,7 +338,7 @@ class CorrBlock1D:
     def skewed_pyramid(self):
         """The skewed copy of the pyramid (``nnd_corr1d_skew``), built on first use: level ``l`` of an epipolar row is
         stored as ``S[j][w1]`` with ``j = ((w1 >> l) - w2) mod W2_l``, so the windows of neighbouring pixels with similar
-        disparity share cache lines.  Read by ``lookup_conv1x1(..., skewed=True)``."""
+        disparity share cache lines.  Read by ``__call__(coords, skewed=True)`` and ``lookup_conv1x1(..., skewed=True)``."""
         if getattr(self, "_skew", None) is None:
             B, H, W1, W2 = self._shape
             self._skew = _lib.ops().corr1d_skew(self._pyr.buffer, B, H, W1, W2, self.num_levels)

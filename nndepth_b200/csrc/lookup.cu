@@ -945,6 +945,7 @@ static nnd_status launch_lookup(const float* const* level_a, const float* const*
 namespace nnd {
 nnd_status launch_lookup_conv1x1_ws(const LookupArgs& a, const float* weight, const float* bias, int relu, int out_f16,
                                     long long total_px, int skew_w1, cudaStream_t stream);
+nnd_status launch_lookup_skewed(const LookupArgs& a, int B, int H, int W1, cudaStream_t stream);
 nnd_status launch_corr1d_skew(const ConstPyramid& src, int num_levels, int B, int H, int W1, float* const* dst, int P1,
                               cudaStream_t stream);
 }
@@ -1181,6 +1182,33 @@ nnd_status nnd_corr1d_lookup_conv1x1_skewed(const float* const* skewed, const in
   a.vec = 1;
   return launch_lookup_conv1x1_ws(a, weight, bias, relu ? 1 : 0, out_layout == 2 ? 1 : 0, static_cast<long long>(B) * a.hw, W1,
                                   reinterpret_cast<cudaStream_t>(stream));
+}
+
+nnd_status nnd_corr1d_lookup_skewed(const float* const* skewed, const int* width, int skew_pitch, const float* coords, int B,
+                                    int H, int W1, int num_levels, int radius, float* out, nnd_stream_t stream) {
+  using namespace nnd;
+  NND_REQUIRE(skewed && width && coords && out, "lookup_skewed: null pointer argument");
+  NND_REQUIRE(B > 0 && H > 0 && W1 > 0, "lookup_skewed: B, H, W1 must be positive");
+  NND_REQUIRE(radius == 4 && num_levels >= 1 && num_levels <= NND_MAX_LEVELS, "lookup_skewed: built for radius 4 and 1..%d levels",
+              NND_MAX_LEVELS);
+  NND_REQUIRE(skew_pitch >= W1, "lookup_skewed: skew_pitch %d smaller than W1 %d", skew_pitch, W1);
+  NND_REQUIRE(static_cast<long long>(H) * W1 < (1LL << 30) && B <= 65535, "lookup_skewed: H*W1 or B too large");
+  LookupArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int l = 0; l < num_levels; ++l) {
+    NND_REQUIRE(width[l] >= 2 && skewed[l], "lookup_skewed: level %d invalid (linear_sampler needs width >= 2)", l);
+    a.src[0].ptr[l] = skewed[l];
+    a.src[0].width[l] = width[l];
+    a.src[0].pitch[l] = skew_pitch;
+  }
+  a.coords = coords;
+  a.out = out;
+  a.hw = H * W1;
+  a.G = 1;
+  a.n_src = 1;
+  a.num_levels = num_levels;
+  a.radius = radius;
+  return launch_lookup_skewed(a, B, H, W1, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -206,6 +206,14 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const __gr
                   : (__float2int_rd(fminf(fmaxf(__fadd_rn(centre, -4.015625f), 0.f), sc.span)) & ~3);
     };
     constexpr int SKSTRIDE = 13;                         // skewed mode: 11 window floats per pixel, odd stride
+    float sk[SKEW ? 11 : 1];                             // skewed mode: the next tile's window of this lane, in flight
+    auto park_window = [&](float* win) {                 // skewed mode: registers -> my own window (no other lane reads it)
+      if (SKEW) {
+#pragma unroll
+        for (int i = 0; i < 11; ++i) win[lane * SKSTRIDE + i] = sk[i];
+        asm volatile("" ::: "memory");
+      }
+    };
     auto issue_windows = [&](int t, float c, int start, float* win) {
       const long long grp0 = px0 + static_cast<long long>(t) * TILE + 32 * pg;   // first pixel of my group
       if (t < nt && grp0 < px_end && SKEW) {
@@ -222,12 +230,13 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const __gr
           if (jr < 0) jr += w;
           const float* src = colp + static_cast<long long>(jr) * pitch;
           const long long wrap = static_cast<long long>(w) * pitch;
-          const uint32_t dst = smem_u32(win + lane * SKSTRIDE);
           const int n_el = min(hi, w - 1) - lo;           // last window element
+          // through REGISTERS (sk[], parked in the lane's window after this tile's taps): 4-byte cp.async copies of
+          // scattered windows run at a third of the rate of plain loads
 #pragma unroll
           for (int i = 0; i < 11; ++i) {
 #ifndef NND_WS_SKIP_GATHER
-            if (i <= n_el) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * i), "l"(src) : "memory");
+            if (i <= n_el) sk[i] = __ldg(src);
 #endif
             src = jr == 0 ? src + wrap - pitch : src - pitch;
             jr = jr == 0 ? w - 1 : jr - 1;
@@ -261,6 +270,7 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const __gr
     int s0 = window_start(__fmul_rn(c0, inv_pow2)), s1 = window_start(__fmul_rn(c1, inv_pow2));
     issue_windows(0, c0, s0, wins);
     stage_weights();
+    park_window(wins);
     for (int t = 0; t < nt; ++t) {
       const float c2 = coord_of(t + 2);                          // in flight during this whole iteration
       issue_windows(t + 1, c1, s1, wins + ((t + 1) & 1) * WIN_BUF_FLOATS);
@@ -289,7 +299,7 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const __gr
           const float f0 = __fadd_rn(u, -8388608.0f);
           const uint32_t addr = mine + (__float_as_uint(u) << 2);
           float v0, v1;
-          asm volatile("ld.shared.f32 %0, [%2];\n\tld.shared.f32 %1, [%2+4];" : "=f"(v0), "=f"(v1) : "r"(addr));
+          asm volatile("ld.shared.f32 %0, [%2];\n\tld.shared.f32 %1, [%2+4];" : "=f"(v0), "=f"(v1) : "r"(addr) : "memory");
           const bool whole = (tt == f0);                          // ceil(t) == floor(t): both neighbours are element i0
           const float coef = whole ? 0.0f : __fsub_rn(__fadd_rn(f0, 1.0f), tt);   // coef = idx1 - t      (utils.py:26)
           const float one_minus = __fsub_rn(1.0f, coef);
@@ -308,6 +318,7 @@ corr1d_lookup_conv1x1_ws_kernel(const __grid_constant__ LookupArgs a, const __gr
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full(slot));
+      park_window(wins + ((t + 1) & 1) * WIN_BUF_FLOATS);
       c0 = c1;
       c1 = c2;
       s0 = s1;
@@ -535,6 +546,93 @@ nnd_status launch_corr1d_skew(const ConstPyramid& src, int num_levels, int B, in
   dim3 grid((W1 + 31) / 32, static_cast<unsigned>(bh), num_levels);
   corr1d_skew_kernel<<<grid, 256, smem, stream>>>(a);
   return check_launch("corr1d_skew_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// CorrBlock1D.__call__ (raft_stereo/cost_volume.py:36-53) on the SKEWED copy: warp = 32 consecutive pixels x one level.
+// A lane fetches the <= 11 window elements of its pixel -- element e lies e rows above row j0 = ((w1 >> l) - i0) mod W2_l,
+// in column w1 -- so for a smooth disparity field a warp load is one 128-byte row segment.  Same tap arithmetic as the
+// row-layout kernel (bit-identical output), same (B, L*9, H, W) fp32 channel-plane stores.
+// ------------------------------------------------------------------------------------------------
+template <int TAPS>
+__global__ void __launch_bounds__(32 * NND_MAX_LEVELS, 8)
+corr1d_lookup_skewed_kernel(const __grid_constant__ LookupArgs a, int row_w1, int rows_h, unsigned magic_shl2) {
+  constexpr int R = (TAPS - 1) / 2, NEL = TAPS + 3, STRIDE = NEL + 1;   // 12 window floats + 1 spare; odd stride: conflict-free
+  extern __shared__ float lk_win[];
+  const int lane = threadIdx.x, lvl = threadIdx.y;
+  // block = 32 consecutive pixels of ONE epipolar row (b, h): blockIdx.y = b * H + h, so no per-thread division
+  const int w1 = blockIdx.x * 32 + lane;
+  if (w1 >= row_w1) return;                             // every lane works on its own window: no warp-wide step below
+  const long long bh = blockIdx.y;
+  const int b = blockIdx.y / rows_h, h = blockIdx.y - b * rows_h;
+  const int rem = h * row_w1 + w1;
+  float* win = lk_win + (lvl * 32 + lane) * STRIDE;
+  const int w = a.src[0].width[lvl], pitch = a.src[0].pitch[lvl];
+  const float c = __ldg(a.coords + bh * row_w1 + w1);
+  const LevelScale sc = level_scale(w, lvl, 0.f);
+  const float centre = __fmul_rn(c, 1.0f / static_cast<float>(1 << lvl));
+  // conservative window [lo, lo + 11]: lo = floor(centre - 4 - 1/64) clamped to the row is never above the first tap's
+  // index and at most one below it (see the fused kernel above; the launcher bounds the width)
+  const int lo = __float2int_rd(fminf(fmaxf(__fadd_rn(centre, -4.015625f), 0.f), sc.span));
+  const int hi = __float2int_ru(fminf(fmaxf(__fadd_rn(centre, 4.015625f), 0.f), sc.span));
+  int jr = (w1 >> lvl) - lo;                            // in (-W2, W1 >> l]: one add, and a modulo only when W1 > W2
+  if (jr < 0) jr += w;
+  if (jr >= w) jr %= w;
+  const float* colp = a.src[0].ptr[lvl] + bh * w * static_cast<long long>(pitch) + w1;   // row j = 0 of my epipolar row, my column
+  unsigned off = static_cast<unsigned>(jr) * static_cast<unsigned>(pitch);             // 32-bit offsets inside the (W2 x P1) slab
+  const unsigned top = static_cast<unsigned>(w - 1) * static_cast<unsigned>(pitch);
+  const int n_el = hi - lo;
+  // through registers: all twelve loads of a lane in flight at once (4-byte cp.async here was three times slower on
+  // scattered windows, and a persistent, software-pipelined form of this kernel lost to plain oversubscription: 49.6 vs
+  // 40.9 us at batch 64; ncu: issue slots 78 % busy -- the kernel is instruction-bound, 94 MB of DRAM reads)
+  float v[NEL];
+#pragma unroll
+  for (int i = 0; i < NEL; ++i) {
+    v[i] = i <= n_el ? __ldg(colp + off) : 0.f;
+    off = off == 0 ? top : off - pitch;                  // element i + 1 lies one row above (mod W2)
+  }
+#pragma unroll
+  for (int i = 0; i < NEL; ++i) win[i] = v[i];
+  // taps: the reference's operation order (utils.py:16-27) with one clamp per pixel and floor through FADD.RZ, exactly
+  // as in the fused kernel's producers
+  const float cc = fminf(fmaxf(centre, -6.0f), __fadd_rn(sc.span, 6.0f));
+  const uint32_t mine = static_cast<uint32_t>(__cvta_generic_to_shared(win)) - 4u * static_cast<uint32_t>(lo) - magic_shl2;
+  float* op = a.out + (static_cast<long long>(b) * a.num_levels + lvl) * TAPS * a.hw + rem;
+#pragma unroll
+  for (int k = 0; k < TAPS; ++k) {
+    const float x = __fadd_rn(static_cast<float>(k - R), cc);
+    const float qn = __fmul_rn(x, sc.inv_span);
+    const float rr = __fmaf_rn(-qn, sc.span, x);
+    const float tt = __fmul_rn(__saturatef(__fmaf_rn(rr, sc.inv_span, qn)), sc.span);
+    const float u = __fadd_rz(tt, 8388608.0f);
+    const float f0 = __fadd_rn(u, -8388608.0f);
+    const uint32_t addr = mine + (__float_as_uint(u) << 2);
+    float v0, v1;
+    asm volatile("ld.shared.f32 %0, [%2];\n\tld.shared.f32 %1, [%2+4];" : "=f"(v0), "=f"(v1) : "r"(addr) : "memory");
+    const bool whole = (tt == f0);
+    const float coef = whole ? 0.0f : __fsub_rn(__fadd_rn(f0, 1.0f), tt);
+    const float one_minus = __fsub_rn(1.0f, coef);
+    v1 = whole ? v0 : v1;
+    // coef * val0 + (1 - coef) * val1, each operation rounded (utils.py:27)
+    *op = __fadd_rn(__fmul_rn(coef, v0), __fmul_rn(one_minus, v1));
+    op += a.hw;
+  }
+}
+
+nnd_status launch_lookup_skewed(const LookupArgs& a, int B, int H, int W1, cudaStream_t stream) {
+  if (a.src[0].width[0] > 16384) {   // the conservative window start assumes positions exact to well below 1/64
+    set_error("lookup_skewed: level-0 width %d exceeds 16384", a.src[0].width[0]);
+    return NND_ERR_INVALID_ARGUMENT;
+  }
+  if (static_cast<long long>(B) * H > 65535) {
+    set_error("lookup_skewed: B*H = %lld exceeds the grid limit (65535)", static_cast<long long>(B) * H);
+    return NND_ERR_INVALID_ARGUMENT;
+  }
+  dim3 grid((W1 + 31) / 32, static_cast<unsigned>(B * H));
+  dim3 block(32, a.num_levels);
+  const size_t smem = static_cast<size_t>(a.num_levels) * 32 * 13 * sizeof(float);
+  corr1d_lookup_skewed_kernel<9><<<grid, block, smem, stream>>>(a, W1, H, 0x4b000000u << 2);
+  return check_launch("corr1d_lookup_skewed_kernel");
 }
 
 // host-side launcher, called by nnd_corr1d_lookup_conv1x1[_skewed] (lookup.cu) for the shipping shape:

@@ -228,6 +228,31 @@ Tensor corr1d_lookup_conv1x1_skewed(const Tensor& skew, int64_t width0, const Te
   return out;
 }
 
+Tensor corr1d_lookup_skewed(const Tensor& skew, int64_t width0, const Tensor& coords, int64_t num_levels, int64_t radius) {
+  check_cuda(skew, "skewed pyramid"); check_cuda(coords, "coords");
+  same_device(skew, coords, "corr1d_lookup_skewed");
+  auto s = nchw(coords, "coords");
+  TORCH_CHECK(s[1] == 1, "coords must be (B, 1, H, W), got ", coords.sizes());
+  TORCH_CHECK(num_levels >= 1 && num_levels <= NND_MAX_LEVELS, "num_levels out of range");
+  c10::cuda::CUDAGuard guard(coords.device());
+  const int64_t B = s[0], H = s[2], W1 = s[3];
+  const int P1 = nnd_row_pitch(static_cast<int>(W1));
+  std::array<const float*, NND_MAX_LEVELS> lv{};
+  std::array<int, NND_MAX_LEVELS> width{};
+  int64_t off = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    width[l] = static_cast<int>(width0 >> l);
+    lv[l] = skew.data_ptr<float>() + off;
+    off += B * H * width[l] * P1;
+  }
+  TORCH_CHECK(skew.numel() >= off, "skewed pyramid holds ", skew.numel(), " floats, needs ", off);
+  Tensor out = at::empty({B, num_levels * (2 * radius + 1), H, W1}, coords.options());
+  check_status(nnd_corr1d_lookup_skewed(lv.data(), width.data(), P1, coords.data_ptr<float>(), B, H, W1, num_levels, radius,
+                                        out.data_ptr<float>(), current_stream(coords)),
+               "nnd_corr1d_lookup_skewed");
+  return out;
+}
+
 Tensor corr1d_lookup_backward(const Tensor& grad_out, const Tensor& coords, int64_t width0, int64_t num_levels, int64_t radius) {
   check_cuda(grad_out, "grad_out"); check_cuda(coords, "coords");
   same_device(grad_out, coords, "corr1d_lookup_backward");
@@ -571,6 +596,7 @@ TORCH_LIBRARY(nndepth_b200, m) {
   m.def("corr1d_lookup_conv1x1(Tensor pyramid, int width0, Tensor coords, int num_levels, int radius, Tensor weight_t, "
         "Tensor? bias, bool relu, int precision, int out_layout) -> Tensor", &corr1d_lookup_conv1x1);
   m.def("corr1d_skew(Tensor pyramid, int B, int H, int W1, int W2, int num_levels) -> Tensor", &corr1d_skew);
+  m.def("corr1d_lookup_skewed(Tensor skewed, int width0, Tensor coords, int num_levels, int radius) -> Tensor", &corr1d_lookup_skewed);
   m.def("corr1d_lookup_conv1x1_skewed(Tensor skewed, int width0, Tensor coords, int num_levels, int radius, Tensor weight_t, "
         "Tensor? bias, bool relu, int out_layout) -> Tensor", &corr1d_lookup_conv1x1_skewed);
   m.def("corr1d_lookup_backward(Tensor grad_out, Tensor coords, int width0, int num_levels, int radius) -> Tensor",

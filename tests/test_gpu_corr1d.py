@@ -454,6 +454,10 @@ def test_lookup_conv1x1_skewed_layout_is_bit_identical(shape, field):
                                       skewed=True)
             assert skew.dtype == rows.dtype and skew.is_contiguous(memory_format=torch.channels_last)
             assert torch.equal(skew, rows)
+        # the plain lookup (CorrBlock1D.__call__) on the skewed copy: the same (B, 36, H, W) tensor bit for bit
+        plain, plain_skew = blk(coords), blk(coords, skewed=True)
+        assert plain_skew.shape == plain.shape and plain_skew.is_contiguous()
+        assert torch.equal(plain_skew, plain)
 
 
 def test_randomised_lookup_sweep_bit_exact():
