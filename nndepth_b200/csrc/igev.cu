@@ -258,12 +258,16 @@ soft_argmin_kernel(const float* __restrict__ z, int D, long long hwv, float* __r
     st[c].s = 0.f;
     st[c].ws = 0.f;
   }
-  // disparities slice, slice + S, slice + 2S, ... ; eight loads in flight per lane
-  for (int d = slice; d < D; d += 8 * S) {
-    float v[8][VEC];
+  // disparities slice, slice + S, slice + 2S, ... ; NF loads in flight per lane
+#ifndef NND_SA_INFLIGHT
+#define NND_SA_INFLIGHT 4      // loads in flight per lane and round; with four disparity slices per block at cfg4 this
+#endif                        // measured 41.0 us (8 loads, one slice: 45.1; 16 loads: 61; 2 loads, 8 slices: 47)
+  constexpr int NF = NND_SA_INFLIGHT;
+  for (int d = slice; d < D; d += NF * S) {
+    float v[NF][VEC];
     int n_valid = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < NF; ++i) {
 #pragma unroll
       for (int c = 0; c < VEC; ++c) v[i][c] = 0.f;
       if (d + i * S < D) {
@@ -273,8 +277,10 @@ soft_argmin_kernel(const float* __restrict__ z, int D, long long hwv, float* __r
     }
 #pragma unroll
     for (int c = 0; c < VEC; ++c) {
-      const float zc[8] = {v[0][c], v[1][c], v[2][c], v[3][c], v[4][c], v[5][c], v[6][c], v[7][c]};
-      soft_push<8>(st[c], zc, d, S, n_valid);
+      float zc[NF];
+#pragma unroll
+      for (int i = 0; i < NF; ++i) zc[i] = v[i][c];
+      soft_push<NF>(st[c], zc, d, S, n_valid);
     }
   }
 #pragma unroll
@@ -299,10 +305,13 @@ soft_argmin_kernel(const float* __restrict__ z, int D, long long hwv, float* __r
   }
 }
 
-// slices per block: 1 when one warp per 32 pixel groups already fills the machine (>= 12 warps per SM),
-// otherwise enough disparity slices to get there (merge cost grows with S, so at most 8).
+// slices per block: enough disparity slices for ~48 warps per SM (many warps with few loads each stream better here than
+// few warps with deep unrolling); the merge cost grows with S, so at most 8.
 static int soft_argmin_slices(long long units, int D) {
-  const long long want = static_cast<long long>(sm_count()) * 12;
+#ifndef NND_SA_WANT
+#define NND_SA_WANT 48
+#endif
+  const long long want = static_cast<long long>(sm_count()) * NND_SA_WANT;
   int S = 1;
   while (S < 8 && units * S < want && 2 * S <= D) S *= 2;
   return S;
