@@ -64,6 +64,14 @@ nnd_status nnd_corr1d_build(const float* fmap1, const float* fmap2, int B, int C
                             int num_levels, int precision, float* const* level, const int* pitch,
                             nnd_stream_t stream);
 
+/* nnd_corr1d_build for feature maps that are fp16 and channels-last, (B, H, W, C) in memory -- what a cuDNN fp16 encoder
+ * returns (raft_stereo/model.py:111-124 hands the encoder output to CorrBlock1D).  fp16 x fp16 products with fp32
+ * accumulation on tcgen05 (the products are exact, like TF32 products of the same values); C % 8 == 0, W1 % 4 == 0,
+ * W2 % 4 == 0.  Same pyramid as nnd_corr1d_build(NND_PREC_TF32) on the values converted to fp32 NCHW, to fp32
+ * accumulation order. */
+nnd_status nnd_corr1d_build_nhwc_f16(const void* fmap1, const void* fmap2, int B, int C, int H, int W1, int W2,
+                                     int num_levels, float* const* level, const int* pitch, nnd_stream_t stream);
+
 /* Grouped variant.  Replaces GroupCorrBlock1D.corr / GeometryAwareCostVolume.build_cost_volume,
  * raft_stereo/cost_volume.py:113-128 and igev_stereo/cost_volume.py:81-98: group g contracts
  * channels [g*group_size, (g+1)*group_size) and divides by `scale_div` (sqrt(C) resp. sqrt(G)).

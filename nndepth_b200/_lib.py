@@ -35,6 +35,7 @@ SIGNATURES = {
     "nnd_last_error_string": (ctypes.c_char_p, []),
     "nnd_row_pitch": (_I, [_I]),
     "nnd_corr1d_build": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "nnd_corr1d_build_nhwc_f16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "nnd_groupcorr_build": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, ctypes.c_float, _I, _P, _P, _P]),
     "nnd_avgpool_pairs": (_I, [_P, _I, _I, _P, _I, ctypes.c_int64, _P]),
     "nnd_corr1d_lookup": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),

@@ -263,6 +263,18 @@ def _check_coords(coords, B, H, W1):
     return coords
 
 
+def _half_channels_last(fmap1, fmap2, precision):
+    """True when both maps are dense fp16 channels-last CUDA tensors of a shape the tensor-core build takes and the
+    volume precision in force is "tf32" (the fp16 products are its exact equivalent; "fp32" asks for the FFMA build)."""
+    if (precision or _VOLUME_PRECISION) != "tf32":
+        return False
+    for t in (fmap1, fmap2):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float16 and t.dim() == 4
+                and t.shape[1] > 1 and t.is_contiguous(memory_format=torch.channels_last)):
+            return False
+    return fmap1.shape[1] % 8 == 0 and fmap1.shape[3] % 4 == 0 and fmap2.shape[3] % 4 == 0
+
+
 class CorrBlock1D:
     """All-pairs 1-D correlation pyramid + fused radius-r lookup (reference cost_volume.py:7-61)."""
 
@@ -277,6 +289,10 @@ class CorrBlock1D:
                 if not (isinstance(t, torch.Tensor) and t.is_cuda):
                     raise RuntimeError(f"{name} must be a CUDA tensor: nndepth_b200 has no CPU path")
             f1, f2 = fmap1.float().contiguous(), fmap2.float().contiguous()
+        elif _half_channels_last(fmap1, fmap2, precision):
+            # fp16 channels-last maps (a cuDNN fp16 encoder's output) are contracted where they lie: no fp32 copy, no
+            # NCHW copy, fp16 x fp16 products with fp32 accumulation (exactly the TF32 products of the same values)
+            f1, f2 = fmap1.detach(), fmap2.detach()
         else:
             f1 = _lib.as_cuda_f32(fmap1, "fmap1")
             f2 = _lib.as_cuda_f32(fmap2, "fmap2")
@@ -294,7 +310,10 @@ class CorrBlock1D:
             self._pyr = PyramidStorage(B * H * W1, W2, num_levels, f1.device, buffer=self._graph_buffer.detach())
             return
         self._pyr = PyramidStorage(B * H * W1, W2, num_levels, f1.device)
-        _lib.ops().corr1d_build(f1, f2, self._pyr.buffer, num_levels, _prec_code(precision, W1, W2))
+        if f1.dtype == torch.float16:
+            _lib.ops().corr1d_build_nhwc_f16(f1, f2, self._pyr.buffer, num_levels)
+        else:
+            _lib.ops().corr1d_build(f1, f2, self._pyr.buffer, num_levels, _prec_code(precision, W1, W2))
 
     @classmethod
     def from_pyramid(cls, levels, batch, height, num_levels=4, radius=4, device="cuda"):

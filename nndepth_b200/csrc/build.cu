@@ -20,6 +20,8 @@ namespace nnd {
 
 nnd_status corr1d_build_tf32(const float* fmap1, const float* fmap2, int B, int C, int H, int W1, int W2,
                              int num_levels, float* const* level, const int* pitch, cudaStream_t stream);
+nnd_status corr1d_build_f16_nhwc(const void* fmap1, const void* fmap2, int B, int C, int H, int W1, int W2,
+                                 int num_levels, float* const* level, const int* pitch, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------
 // fp32 all-pairs build: per (b,h) row, out[m][n] = sum_c f1[c][m] * f2[c][n] / scale_div.
@@ -402,6 +404,22 @@ nnd_status nnd_corr1d_build(const float* fmap1, const float* fmap2, int B, int C
   st = check_launch("corr1d_build_fp32_kernel");
   if (st != NND_OK) return st;
   return pool_tail(pyr, num_levels, bh * W1, stream);
+}
+
+nnd_status nnd_corr1d_build_nhwc_f16(const void* fmap1, const void* fmap2, int B, int C, int H, int W1, int W2,
+                                     int num_levels, float* const* level, const int* pitch, nnd_stream_t stream_) {
+  using namespace nnd;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  NND_REQUIRE(fmap1 && fmap2, "corr1d_build_nhwc_f16: null feature map");
+  NND_REQUIRE(B > 0 && C > 0 && H > 0 && W1 > 0 && W2 > 0, "corr1d_build_nhwc_f16: B, C, H, W1, W2 must be positive");
+  NND_REQUIRE(static_cast<long long>(B) * H <= 65535 * 1024LL, "corr1d_build_nhwc_f16: too many epipolar rows");
+  Pyramid pyr;
+  bool vec_ok;
+  nnd_status st = fill_pyramid(pyr, W2, num_levels, level, pitch, vec_ok, "corr1d_build_nhwc_f16");
+  if (st != NND_OK) return st;
+  st = corr1d_build_f16_nhwc(fmap1, fmap2, B, C, H, W1, W2, num_levels < 4 ? num_levels : 4, level, pitch, stream);
+  if (st != NND_OK) return st;
+  return pool_tail(pyr, num_levels, static_cast<long long>(B) * H * W1, stream);
 }
 
 nnd_status nnd_groupcorr_build(const float* fmap1, const float* fmap2, int B, int C, int H, int W1, int W2,

@@ -186,6 +186,33 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B: rows of 128 bytes (64 fp16 of K), 8-row atoms of 1024 bytes
+// stacked along M / N (stride byte offset 1024; the leading byte offset is not used by swizzled K-major layouts).
+// A k-step of 16 fp16 advances the start address by 32 bytes inside the swizzle span.
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;   // SWIZZLE_128B
+  return d;
+}
+// D = F32, A = B = F16, both K-major
+__device__ __forceinline__ uint32_t umma_idesc_f16(int n) {
+  return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(TILE_M >> 4) << 24);
+}
+
 // UMMA shared-memory descriptor, MN-major, SWIZZLE_128B_BASE32B (bit layout of cute::UMMA::SmemDescriptor):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (stride between 32-element MN atoms)
 //   [32,46) stride byte offset >> 4 (stride between 4-row K atoms) | [46,48) version = 1 | [61,64) layout = 1
@@ -236,6 +263,12 @@ __device__ __forceinline__ JobGeom job_geom(const BuildParams& p, long long job)
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
+// IN_F16: the feature maps are fp16 channels-last (N, H, W, C) -- what a cuDNN fp16 encoder hands over.  A pixel's channels
+// are contiguous, so both operands are K-major: TMA boxes {64 c, 32 w} land as 32 rows of 128 bytes in the plain
+// SWIZZLE_128B layout, an epipolar row is ONE contiguous run of W * C * 2 bytes in memory (the NCHW form reads 256
+// separate 624-byte segments per map and row), kind::f16 multiplies the fp16 values exactly (they are what TF32 would
+// keep of them) and nothing needs rounding: the rounder warps retire at once and the MMAs wait on the TMA barrier.
+template <bool IN_F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 corr1d_build_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                          const __grid_constant__ CUtensorMap map_l0, const __grid_constant__ CUtensorMap map_l1,
@@ -284,7 +317,8 @@ corr1d_build_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int k_blocks = (p.C + KB - 1) / KB;
+  constexpr int KBE = IN_F16 ? 64 : KB;             // channels per pipeline stage: 128 bytes of K either way
+  const int k_blocks = (p.C + KBE - 1) / KBE;
   const uint32_t b_region = static_cast<uint32_t>(p.a_region_boxes) * BOX_BYTES;
 
   if (warp == TMA_WARP) {
@@ -301,15 +335,21 @@ corr1d_build_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             mbar_wait(empty_bar(stage), phase ^ 1);
             const uint32_t sbase = smem_u32(smem + static_cast<size_t>(stage) * p.stage_bytes);
             mbar_expect_tx(full_bar(stage), static_cast<uint32_t>((a_boxes + g.b_boxes) * BOX_BYTES));
-            for (int i = 0; i < a_boxes; ++i)
-              tma_load_4d(sbase + i * BOX_BYTES, &map_a, full_bar(stage), m_start + i * BOX_W, g.h, kb * KB, g.b);
-            for (int i = 0; i < g.b_boxes; ++i)
-              tma_load_4d(sbase + b_region + i * BOX_BYTES, &map_b, full_bar(stage), g.n0 + i * BOX_W, g.h, kb * KB, g.b);
+            for (int i = 0; i < a_boxes; ++i) {
+              if (IN_F16) tma_load_4d(sbase + i * BOX_BYTES, &map_a, full_bar(stage), kb * KBE, m_start + i * BOX_W, g.h, g.b);
+              else tma_load_4d(sbase + i * BOX_BYTES, &map_a, full_bar(stage), m_start + i * BOX_W, g.h, kb * KB, g.b);
+            }
+            for (int i = 0; i < g.b_boxes; ++i) {
+              if (IN_F16) tma_load_4d(sbase + b_region + i * BOX_BYTES, &map_b, full_bar(stage), kb * KBE, g.n0 + i * BOX_W, g.h, g.b);
+              else tma_load_4d(sbase + b_region + i * BOX_BYTES, &map_b, full_bar(stage), g.n0 + i * BOX_W, g.h, kb * KB, g.b);
+            }
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
+  } else if (warp >= LOADER_WARP0 && IN_F16) {
+    // fp16 operands are exact: nothing to round
   } else if (warp >= LOADER_WARP0) {
     // ===================== rounders: TF32 round-to-nearest of the landed stage, in place =====================
     // The tensor core truncates fp32 operands to TF32; rounding them to nearest first removes the bias.
@@ -360,6 +400,16 @@ corr1d_build_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      // operand descriptor of k-step ks of the region at `base`; the stage is ready when the rounders (fp32) or the TMA
+      // itself (fp16) say so
+      auto opdesc = [&](uint32_t base, int ks) -> uint64_t {
+        return IN_F16 ? umma_desc_k_sw128(base + ks * 32) : umma_desc_mn_sw128_32b(base + ks * 1024, BOX_BYTES, 512);
+      };
+      auto stage_ready = [&](int st) -> uint32_t { return IN_F16 ? full_bar(st) : ready_bar(st); };
+      auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+        if (IN_F16) tc_mma_f16(d, a, b, idesc, acc); else tc_mma_tf32(d, a, b, idesc, acc);
+      };
+      auto make_idesc = [&](int n) -> uint32_t { return IN_F16 ? umma_idesc_f16(n) : umma_idesc_tf32(n); };
       if (p.lt_mode) {
         // Leftover-transposed layout (one job = one row, 128 < W1 <= 160, one pass):
         //   D0  [cols 0, n_cols)             rows m = 0..127        x all n        (A = f1 boxes 0-3, B = f2)
@@ -369,31 +419,31 @@ corr1d_build_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         // job needs n_cols + 64 columns and TWO jobs fit in TMEM: the epilogue of one row fully overlaps the
         // MMAs of the next.  Both operands are MN-major atoms of the same shape, so f2 boxes serve as the A operand
         // and the f1 box as B without any other change.
-        const uint32_t idesc32 = umma_idesc_tf32(32);
+        const uint32_t idesc32 = make_idesc(32);
         uint32_t job_seq = 0;
         for (long long job = blockIdx.x; job < p.jobs; job += gridDim.x, ++job_seq) {
           const JobGeom g = job_geom(p, job);
-          const uint32_t idesc = umma_idesc_tf32(g.n_mma);
+          const uint32_t idesc = make_idesc(g.n_mma);
           const uint32_t slot = job_seq & 1;
           const uint32_t d0 = tmem_base + slot * p.lt_cols, dla = d0 + g.n_cols, dlb = dla + 32;
           const bool has_b = g.n_ext > TILE_M;
           mbar_wait(tmem_empty_bar(slot), ((job_seq >> 1) & 1) ^ 1);
           tc_fence_after();
           for (int kb = 0; kb < k_blocks; ++kb) {
-            mbar_wait(ready_bar(stage), phase);
+            mbar_wait(stage_ready(stage), phase);
             tc_fence_after();
             const uint32_t sbase = smem_u32(smem + static_cast<size_t>(stage) * p.stage_bytes);
             const uint32_t bbase = sbase + b_region;
 #pragma unroll
             for (int ks = 0; ks < KB / 8; ++ks) {
               const uint32_t acc = (kb | ks) != 0 ? 1u : 0u;
-              const uint64_t f1_t0 = umma_desc_mn_sw128_32b(sbase + ks * 1024, BOX_BYTES, 512);
-              const uint64_t f1_b4 = umma_desc_mn_sw128_32b(sbase + 4 * BOX_BYTES + ks * 1024, BOX_BYTES, 512);
-              const uint64_t f2_t0 = umma_desc_mn_sw128_32b(bbase + ks * 1024, BOX_BYTES, 512);
-              const uint64_t f2_t1 = umma_desc_mn_sw128_32b(bbase + 4 * BOX_BYTES + ks * 1024, BOX_BYTES, 512);
-              tc_mma_tf32(d0, f1_t0, f2_t0, idesc, acc);
-              tc_mma_tf32(dla, f2_t0, f1_b4, idesc32, acc);
-              if (has_b) tc_mma_tf32(dlb, f2_t1, f1_b4, idesc32, acc);
+              const uint64_t f1_t0 = opdesc(sbase, ks);
+              const uint64_t f1_b4 = opdesc(sbase + 4 * BOX_BYTES, ks);
+              const uint64_t f2_t0 = opdesc(bbase, ks);
+              const uint64_t f2_t1 = opdesc(bbase + 4 * BOX_BYTES, ks);
+              mma(d0, f1_t0, f2_t0, idesc, acc);
+              mma(dla, f2_t0, f1_b4, idesc32, acc);
+              if (has_b) mma(dlb, f2_t1, f1_b4, idesc32, acc);
             }
             tc_commit(empty_bar(stage));
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -404,7 +454,7 @@ corr1d_build_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       uint32_t tile_seq = 0;  // every M tile takes the next TMEM tile slot of the ring
       for (long long job = p.lt_mode ? p.jobs : blockIdx.x; job < p.jobs; job += gridDim.x) {
         const JobGeom g = job_geom(p, job);
-        const uint32_t idesc = umma_idesc_tf32(g.n_mma);
+        const uint32_t idesc = make_idesc(g.n_mma);
         for (int pass = 0; pass < p.m_passes; ++pass) {
           const int m_start = pass * MAX_M;
           const int tiles = (min(p.W1 - m_start, MAX_M) + TILE_M - 1) / TILE_M;
@@ -414,21 +464,21 @@ corr1d_build_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             d_base[t] = tmem_base + slot[t] * p.slot_cols;
           }
           for (int kb = 0; kb < k_blocks; ++kb) {
-            mbar_wait(ready_bar(stage), phase);
+            mbar_wait(stage_ready(stage), phase);
             tc_fence_after();
             const uint32_t sbase = smem_u32(smem + static_cast<size_t>(stage) * p.stage_bytes);
             const uint32_t bbase = sbase + b_region;
 #pragma unroll
             for (int ks = 0; ks < KB / 8; ++ks) {
-              const uint64_t bdesc = umma_desc_mn_sw128_32b(bbase + ks * 1024, BOX_BYTES, 512);
+              const uint64_t bdesc = opdesc(bbase, ks);
               for (int t = 0; t < tiles; ++t) {
                 if ((kb | ks) == 0) {
                   // first write into this tile slot: the epilogue must have drained its previous tenant
                   mbar_wait(tmem_empty_bar(slot[t]), (((tile_seq + t) / p.n_tslots) & 1) ^ 1);
                   tc_fence_after();
                 }
-                const uint64_t adesc = umma_desc_mn_sw128_32b(sbase + t * 4 * BOX_BYTES + ks * 1024, BOX_BYTES, 512);
-                tc_mma_tf32(d_base[t], adesc, bdesc, idesc, (kb | ks) != 0 ? 1u : 0u);
+                const uint64_t adesc = opdesc(sbase + t * 4 * BOX_BYTES, ks);
+                mma(d_base[t], adesc, bdesc, idesc, (kb | ks) != 0 ? 1u : 0u);
               }
             }
             tc_commit(empty_bar(stage));  // frees this smem stage when the MMAs above retire
@@ -682,14 +732,15 @@ EncodeTiledFn encode_tiled_fn() {
 }
 
 nnd_status make_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                    const cuuint32_t* box, CUtensorMapSwizzle swizzle, const char* what) {
+                    const cuuint32_t* box, CUtensorMapSwizzle swizzle, const char* what,
+                    CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT32) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) {
     set_error("corr1d_build(tf32): cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
     return NND_ERR_CUDA;
   }
   cuuint32_t elem_strides[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, static_cast<cuuint32_t>(rank), const_cast<void*>(base), dims,
+  CUresult r = fn(map, dtype, static_cast<cuuint32_t>(rank), const_cast<void*>(base), dims,
                   strides_bytes, box, elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -701,12 +752,17 @@ nnd_status make_map(CUtensorMap* map, const void* base, int rank, const cuuint64
 
 }  // namespace
 
-nnd_status corr1d_build_tf32(const float* fmap1, const float* fmap2, int B, int C, int H, int W1, int W2,
-                             int num_levels, float* const* level, const int* pitch, cudaStream_t stream) {
+// in_f16 = 0: fp32 NCHW feature maps (TF32 products); 1: fp16 channels-last (N, H, W, C) feature maps (fp16 products)
+static nnd_status corr1d_build_tc(const void* fmap1, const void* fmap2, int in_f16, int B, int C, int H, int W1, int W2,
+                                  int num_levels, float* const* level, const int* pitch, cudaStream_t stream) {
   // TMA constraints: every global stride a multiple of 16 bytes, bases 16-byte aligned
   if (W1 % 4 != 0 || W2 % 4 != 0 || !aligned16(fmap1) || !aligned16(fmap2)) {
     set_error("corr1d_build(tf32): TMA needs W1 and W2 to be multiples of 4 and 16-byte aligned "
               "feature maps (W1=%d, W2=%d); use NND_PREC_FP32 for this shape", W1, W2);
+    return NND_ERR_UNSUPPORTED;
+  }
+  if (in_f16 && C % 8 != 0) {
+    set_error("corr1d_build(fp16 channels-last): TMA needs C to be a multiple of 8 (C=%d)", C);
     return NND_ERR_UNSUPPORTED;
   }
   for (int l = 0; l < num_levels; ++l) {
@@ -752,7 +808,24 @@ nnd_status corr1d_build_tf32(const float* fmap1, const float* fmap2, int B, int 
   const size_t smem_bytes = 1024 + static_cast<size_t>(p.stages) * p.stage_bytes + 2 * EPI_SET + BAR_BYTES;
 
   alignas(64) CUtensorMap map_a, map_b, map_l[4];
-  {
+  if (in_f16) {
+    // (N, H, W, C) fp16: dims innermost first {C, W, H, B}; a box is 64 channels (128 bytes) x 32 pixels of one row
+    const cuuint64_t dims1[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W1), static_cast<cuuint64_t>(H),
+                                 static_cast<cuuint64_t>(B)};
+    const cuuint64_t str1[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W1) * C * 2,
+                                static_cast<cuuint64_t>(H) * W1 * C * 2};
+    const cuuint64_t dims2[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W2), static_cast<cuuint64_t>(H),
+                                 static_cast<cuuint64_t>(B)};
+    const cuuint64_t str2[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W2) * C * 2,
+                                static_cast<cuuint64_t>(H) * W2 * C * 2};
+    const cuuint32_t box[4] = {64, BOX_W, 1, 1};
+    nnd_status st = make_map(&map_a, fmap1, 4, dims1, str1, box, CU_TENSOR_MAP_SWIZZLE_128B, "fmap1 (fp16 NHWC)",
+                             CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+    if (st != NND_OK) return st;
+    st = make_map(&map_b, fmap2, 4, dims2, str2, box, CU_TENSOR_MAP_SWIZZLE_128B, "fmap2 (fp16 NHWC)",
+                  CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+    if (st != NND_OK) return st;
+  } else {
     const cuuint64_t dims1[4] = {static_cast<cuuint64_t>(W1), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(C),
                                  static_cast<cuuint64_t>(B)};
     const cuuint64_t str1[3] = {static_cast<cuuint64_t>(W1) * 4, static_cast<cuuint64_t>(H) * W1 * 4,
@@ -780,16 +853,32 @@ nnd_status corr1d_build_tf32(const float* fmap1, const float* fmap2, int B, int 
     if (st != NND_OK) return st;
   }
 
-  {
-    cudaError_t e = cudaFuncSetAttribute(corr1d_build_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem_bytes));
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(corr1d_build_tf32_kernel)");
-  }
   const long long sms = sm_count();  // persistent: one CTA per SM, rows dealt round-robin
   const unsigned grid = static_cast<unsigned>(p.jobs < sms ? p.jobs : sms);
-  corr1d_build_tf32_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(map_a, map_b, map_l[0], map_l[1], map_l[2],
-                                                                      map_l[3], p);
+  if (in_f16) {
+    cudaError_t e = cudaFuncSetAttribute(corr1d_build_tf32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem_bytes));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(corr1d_build_tf32_kernel<fp16>)");
+    corr1d_build_tf32_kernel<true><<<grid, NUM_THREADS, smem_bytes, stream>>>(map_a, map_b, map_l[0], map_l[1], map_l[2],
+                                                                              map_l[3], p);
+  } else {
+    cudaError_t e = cudaFuncSetAttribute(corr1d_build_tf32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem_bytes));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(corr1d_build_tf32_kernel)");
+    corr1d_build_tf32_kernel<false><<<grid, NUM_THREADS, smem_bytes, stream>>>(map_a, map_b, map_l[0], map_l[1], map_l[2],
+                                                                               map_l[3], p);
+  }
   return check_launch("corr1d_build_tf32_kernel");
+}
+
+nnd_status corr1d_build_tf32(const float* fmap1, const float* fmap2, int B, int C, int H, int W1, int W2,
+                             int num_levels, float* const* level, const int* pitch, cudaStream_t stream) {
+  return corr1d_build_tc(fmap1, fmap2, 0, B, C, H, W1, W2, num_levels, level, pitch, stream);
+}
+
+nnd_status corr1d_build_f16_nhwc(const void* fmap1, const void* fmap2, int B, int C, int H, int W1, int W2,
+                                 int num_levels, float* const* level, const int* pitch, cudaStream_t stream) {
+  return corr1d_build_tc(fmap1, fmap2, 1, B, C, H, W1, W2, num_levels, level, pitch, stream);
 }
 
 }  // namespace nnd

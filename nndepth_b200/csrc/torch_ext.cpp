@@ -99,6 +99,25 @@ void corr1d_build(const Tensor& f1, const Tensor& f2, Tensor pyramid, int64_t nu
                "nnd_corr1d_build");
 }
 
+// the same build from fp16 channels-last feature maps (N, C, H, W logical; N, H, W, C in memory), read where they lie
+void corr1d_build_nhwc_f16(const Tensor& f1, const Tensor& f2, Tensor pyramid, int64_t num_levels) {
+  check_cuda(pyramid, "pyramid");
+  for (const Tensor* f : {&f1, &f2}) {
+    TORCH_CHECK(f->is_cuda() && f->scalar_type() == at::kHalf && f->dim() == 4 &&
+                    f->is_contiguous(at::MemoryFormat::ChannelsLast),
+                "corr1d_build_nhwc_f16: feature maps must be dense fp16 channels-last CUDA tensors");
+  }
+  same_device(f1, f2, "corr1d_build_nhwc_f16"); same_device(f1, pyramid, "corr1d_build_nhwc_f16");
+  auto s1 = nchw(f1, "fmap1"), s2 = nchw(f2, "fmap2");
+  TORCH_CHECK(s1[0] == s2[0] && s1[1] == s2[1] && s1[2] == s2[2], "fmap1 ", f1.sizes(), " and fmap2 ", f2.sizes(),
+              " must agree in batch, channels and height");
+  c10::cuda::CUDAGuard guard(f1.device());
+  LevelTable t = row_levels(pyramid, s1[0] * s1[2] * s1[3], s2[3], num_levels, "corr1d_build_nhwc_f16");
+  check_status(nnd_corr1d_build_nhwc_f16(f1.data_ptr(), f2.data_ptr(), s1[0], s1[1], s1[2], s1[3], s2[3], num_levels,
+                                         t.ptr.data(), t.pitch.data(), current_stream(f1)),
+               "nnd_corr1d_build_nhwc_f16");
+}
+
 void groupcorr_build(const Tensor& f1, const Tensor& f2, Tensor pyramid, int64_t num_groups, int64_t group_size,
                      double scale_div, int64_t num_levels) {
   check_cuda(f1, "fmap1"); check_cuda(f2, "fmap2"); check_cuda(pyramid, "pyramid");
@@ -589,6 +608,7 @@ int64_t abi_version() { return nnd_abi_version(); }
 TORCH_LIBRARY(nndepth_b200, m) {
   m.def("abi_version() -> int", &abi_version);
   m.def("corr1d_build(Tensor fmap1, Tensor fmap2, Tensor(a!) pyramid, int num_levels, int precision) -> ()", &corr1d_build);
+  m.def("corr1d_build_nhwc_f16(Tensor fmap1, Tensor fmap2, Tensor(a!) pyramid, int num_levels) -> ()", &corr1d_build_nhwc_f16);
   m.def("groupcorr_build(Tensor fmap1, Tensor fmap2, Tensor(a!) pyramid, int num_groups, int group_size, float scale_div, "
         "int num_levels) -> ()", &groupcorr_build);
   m.def("avgpool_pairs(Tensor src, int src_width) -> Tensor", &avgpool_pairs);

@@ -917,7 +917,11 @@ class RAFTStereo(nn.Module):
     def _forward(self, frame1, frame2, **kwargs):
         fmap1, fmap2, cnet1 = self.forward_fnet(frame1, frame2)
         fnet_ds = frame1.shape[-1] // fmap1.shape[-1]
-        fmap1, fmap2 = fmap1.float(), fmap2.float()
+        from . import corr as _corr
+        if not (isinstance(self.corr_fn, type) and issubclass(self.corr_fn, _corr.CorrBlock1D)
+                and not torch.is_grad_enabled() and _corr._half_channels_last(fmap1, fmap2, None)):
+            # (an fp16 channels-last pair from the fp16 encoder goes to CorrBlock1D as it is: the build reads it in place)
+            fmap1, fmap2 = fmap1.float(), fmap2.float()
         net, inp = torch.split(cnet1, [self.hidden_dim, self.context_dim], dim=1)
         net, inp = torch.tanh(net.float()), F.relu(inp)
 

@@ -110,7 +110,7 @@ def test_product_package_does_not_import_the_oracle():
 TORCH_OPS = ["abi_version", "corr1d_build", "groupcorr_build", "avgpool_pairs", "corr1d_lookup", "corr1d_lookup_conv1x1",
              "corr1d_lookup_backward", "pyramid_unpool_", "corr1d_lookup_indices", "group_lookup", "geo_transpose_pool",
              "gev_interleave_pool", "gev_lookup", "soft_argmin", "gev_squeeze_soft_argmin", "nchw_to_nhwc", "agcl_offset",
-             "agcl_iter", "convex_upsample", "agcl_warp", "agcl_offset_backward", "agcl_iter_backward", "volume_grad", "corr1d_skew", "corr1d_lookup_conv1x1_skewed", "corr1d_lookup_skewed"]
+             "agcl_iter", "convex_upsample", "agcl_warp", "agcl_offset_backward", "agcl_iter_backward", "volume_grad", "corr1d_skew", "corr1d_lookup_conv1x1_skewed", "corr1d_lookup_skewed", "corr1d_build_nhwc_f16"]
 
 
 def test_torch_extension_registers_every_operator_and_refuses_cpu_tensors():

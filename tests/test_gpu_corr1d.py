@@ -520,3 +520,32 @@ def test_group_block_any_group_count_against_reference(G):
     assert got.shape == want.shape
     scale = want.abs().max().item()
     assert (got.double() - want).abs().max().item() <= 1e-5 * scale
+
+
+@pytest.mark.parametrize("shape", [(8, 256, 48, 156, 156), (1, 256, 80, 160, 160), (2, 64, 5, 52, 44), (1, 96, 3, 260, 300), (3, 8, 2, 16, 16)])
+def test_build_from_fp16_channels_last_maps(shape):
+    """fp16 channels-last feature maps (a cuDNN fp16 encoder's output) are contracted where they lie: K-major fp16
+    operands on tcgen05.  Against the fp64 contraction of the same fp16 values (1e-5 of the volume's scale: the products
+    are exact, only the fp32 accumulation order differs) and against the TF32 build of the values converted to fp32
+    NCHW; the pooled levels are bit-exact poolings of level 0."""
+    import nndepth_b200 as nb
+    B, C, H, W1, W2 = shape
+    torch.manual_seed(W1 + C)
+    f1 = torch.randn(B, C, H, W1, device="cuda").half().contiguous(memory_format=torch.channels_last)
+    f2 = torch.randn(B, C, H, W2, device="cuda").half().contiguous(memory_format=torch.channels_last)
+    blk = nb.CorrBlock1D(f1, f2, 4, 4)
+    assert blk._pyr.levels[0].shape[0] == B * H * W1
+    want = torch.einsum("bchi,bchj->bhij", f1.double(), f2.double()) / C ** 0.5
+    got = blk.corr_pyramid[0].reshape(B, H, W1, W2)
+    scale = want.abs().max().item()
+    assert (got.double() - want).abs().max().item() <= 1e-5 * scale
+    ref = nb.CorrBlock1D(f1.float().contiguous(), f2.float().contiguous(), 4, 4)
+    for a, b in zip(blk.corr_pyramid[:4], ref.corr_pyramid[:4]):
+        assert a.shape == b.shape
+        assert (a - b).abs().max().item() <= 1e-5 * scale
+    for lo, hi in zip(blk.corr_pyramid[:3], blk.corr_pyramid[1:4]):
+        w = hi.shape[-1]
+        assert torch.equal(hi, (lo[..., 0:2 * w:2] + lo[..., 1:2 * w:2]) / 2)
+    # the lookup reads the same storage
+    coords = torch.arange(W1, device="cuda").float().view(1, 1, 1, W1).repeat(B, 1, H, 1) - 3.3
+    assert (blk(coords) - ref(coords)).abs().max().item() <= 1e-5 * scale
