@@ -98,6 +98,10 @@ def cfg1(skip_cpu):
     build = gpu_us(lambda: nb.CorrBlock1D(f1, f2, 4, 4))
     blk = nb.CorrBlock1D(f1, f2, 4, 4)
     lookup = gpu_us(lambda: blk(coords[5]))
+    # the same build from fp16 channels-last maps (what a cuDNN fp16 encoder hands over), read in place
+    h1, h2 = (t.half().contiguous(memory_format=torch.channels_last) for t in (f1, f2))
+    build16 = gpu_us(lambda: nb.CorrBlock1D(h1, h2, 4, 4))
+    lookup_skew = gpu_us(lambda: blk(coords[5], skewed=True))
 
     def whole():
         b = nb.CorrBlock1D(f1, f2, 4, 4)
@@ -106,9 +110,13 @@ def cfg1(skip_cpu):
     total = gpu_us(whole)
     line = {"config": {"workload": "BASELINE configs[0]: pyramid build + 32 lookups, B1 C256 80x160, L4 r4"},
             "metric": "pyramid build + 32 lookups", "unit": "passes/s", "value": 1e6 / total, "dtype": "f32 (TF32 operands, RN)",
-            "gpu_us": {"build": build, "lookup": lookup, "build_plus_32_lookups": total},
+            "gpu_us": {"build": build, "lookup": lookup, "build_plus_32_lookups": total,
+                       "build_from_fp16_channels_last_maps": build16, "lookup_on_skewed_copy": lookup_skew},
             "roofline": roof("corr1d_build_tf32_kernel", 2 * B * C * H * W * 4 + B * H * W * 300 * 4, build),
-            "lookup_roofline": roof("corr1d_lookup_lean_kernel<9>", B * H * W * 308, lookup)}
+            "lookup_roofline": roof("corr1d_lookup_lean_kernel<9>", B * H * W * 308, lookup),
+            "other_rooflines": [roof("corr1d_build_tf32_kernel<fp16 channels-last maps>",
+                                     2 * B * C * H * W * 2 + B * H * W * 300 * 4, build16),
+                                roof("corr1d_lookup_skewed_kernel<9>", B * H * W * 308, lookup_skew)]}
     have_ref = reference_available()
     if have_ref:
         from nndepth.models.raft_stereo.cost_volume import CorrBlock1D as RefCorr
