@@ -743,8 +743,10 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": warm, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None,
-            "dtype": "f32 (correlation volume: %s operands rounded to nearest, fp32 accumulate; dense layers: %s)" % (
-                nb.get_volume_precision(), dense),
+            "dtype": "f32 (correlation volume: %s, fp32 accumulate; dense layers: %s)" % (
+                ("fp16 x fp16 products of the fp16 encoder's feature maps (exact; what TF32 keeps of the same values)"
+                 if (fnet_half and nb.get_volume_precision() == "tf32")
+                 else "%s operands rounded to nearest" % nb.get_volume_precision()), dense),
             "dense_precision": args.dense_precision,
             "parity": parity,
             "data": "synthetic", "config": workload_config(world), "clocks": clocks,
