@@ -149,7 +149,6 @@ template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -699,7 +698,9 @@ corr1d_build_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         }
       }
     }
-    if (store_lane) tma_store_wait_all();
+    // (the stores must have read their staging tiles before the CTA retires; their writes complete asynchronously and
+    // are ordered by the end of the kernel)
+    if (store_lane) tma_store_wait_read<0>();
   }
 
   tc_fence_before();
