@@ -184,7 +184,7 @@ pyramid_lookup_kernel(const LookupArgs a) {
 // ------------------------------------------------------------------------------------------------
 template <int TAPS>
 __global__ void __launch_bounds__(32 * NND_MAX_LEVELS, 6)
-corr1d_lookup_lean_kernel(const __grid_constant__ LookupArgs a) {
+corr1d_lookup_lean_kernel(const __grid_constant__ LookupArgs a, unsigned magic_shl2) {
   constexpr int WINQ = 4, COLS = 4 * WINQ, STRIDE = COLS + 1;
   constexpr int R = (TAPS - 1) / 2;
   constexpr unsigned FULL = 0xffffffffu;
@@ -201,8 +201,11 @@ corr1d_lookup_lean_kernel(const __grid_constant__ LookupArgs a) {
   const float c = valid ? __ldg(a.coords + static_cast<long long>(b) * a.hw + rem) : 0.0f;
   const float centre = __fmul_rn(c, 1.0f / static_cast<float>(1 << lvl));
   const LevelScale sc = level_scale(w, lvl, centre);
-  const int s = make_tap(0, R, centre, sc).i0 & ~3;
-  const int hi = make_tap(TAPS - 1, R, centre, sc).i1;
+  // conservative window: a 4-aligned start never above the first tap's index and at most one below it, an end never
+  // below the last tap's (positions differ from centre + dx by a few ulps only; the launcher bounds the width), so the
+  // 16 floats fetched hold every tap and no exact tap has to be computed before the fetch
+  const int s = __float2int_rd(fminf(fmaxf(__fadd_rn(centre, -4.015625f), 0.f), sc.span)) & ~3;
+  const int hi = __float2int_ru(fminf(fmaxf(__fadd_rn(centre, 4.015625f), 0.f), sc.span));
 
   const int q = lane & 3;
   const float* __restrict__ rows = a.src[0].ptr[lvl] + (static_cast<long long>(b) * a.hw + rem0) * pitch;
@@ -237,13 +240,30 @@ corr1d_lookup_lean_kernel(const __grid_constant__ LookupArgs a) {
   }
   __syncwarp();
   if (!valid) return;
-  const float* mine = win + lane * STRIDE - s;
+  // taps: the reference's operation order (utils.py:16-27) with ONE clamp per pixel (outside [-6, span + 6] every tap
+  // saturates to t = 0 or t = span either way; NaN -> -6 -> t = 0) and floor through FADD.RZ with 2^23, whose bits also
+  // address the window (magic_shl2 = 0x4b000000 << 2 comes as an argument so that it stays folded into the base)
+  const float cc = fminf(fmaxf(centre, -6.0f), __fadd_rn(sc.span, 6.0f));
+  const uint32_t mine = static_cast<uint32_t>(__cvta_generic_to_shared(win + lane * STRIDE)) - 4u * static_cast<uint32_t>(s) - magic_shl2;
   float* op = a.out + (static_cast<long long>(b) * a.num_levels + lvl) * TAPS * a.hw + rem;
 #pragma unroll
   for (int k = 0; k < TAPS; ++k) {
-    const Tap tp = make_tap(k, R, centre, sc);
+    const float x = __fadd_rn(static_cast<float>(k - R), cc);
+    const float qn = __fmul_rn(x, sc.inv_span);
+    const float rr = __fmaf_rn(-qn, sc.span, x);
+    const float tt = __fmul_rn(__saturatef(__fmaf_rn(rr, sc.inv_span, qn)), sc.span);
+    const float u = __fadd_rz(tt, 8388608.0f);
+    const float f0 = __fadd_rn(u, -8388608.0f);
+    const uint32_t addr = mine + (__float_as_uint(u) << 2);
+    float v0, v1;
+    asm volatile("ld.shared.f32 %0, [%2];\n\tld.shared.f32 %1, [%2+4];" : "=f"(v0), "=f"(v1) : "r"(addr) : "memory");
+    const bool whole = (tt == f0);
+    const float coef = whole ? 0.0f : __fsub_rn(__fadd_rn(f0, 1.0f), tt);   // coef = idx1 - t (utils.py:26)
+    const float one_minus = __fsub_rn(1.0f, coef);
+    v1 = whole ? v0 : v1;
     // coef * val0 + (1 - coef) * val1, each operation rounded (utils.py:27)
-    op[static_cast<long long>(k) * a.hw] = __fadd_rn(__fmul_rn(tp.coef, mine[tp.i0]), __fmul_rn(tp.one_minus, mine[tp.i1]));
+    *op = __fadd_rn(__fmul_rn(coef, v0), __fmul_rn(one_minus, v1));
+    op += a.hw;
   }
 }
 
@@ -922,7 +942,8 @@ static nnd_status launch_lookup(const float* const* level_a, const float* const*
     dim3 grid((a.hw + 31) / 32, B);
     dim3 block(32, num_levels);
     const size_t smem = static_cast<size_t>(num_levels) * 32 * 17 * sizeof(float);
-    corr1d_lookup_lean_kernel<9><<<grid, block, smem, stream>>>(a);
+    NND_REQUIRE(width[0] <= 16384, "lookup: level-0 width %d exceeds 16384", width[0]);   // conservative window start
+    corr1d_lookup_lean_kernel<9><<<grid, block, smem, stream>>>(a, 0x4b000000u << 2);
     return check_launch("corr1d_lookup_lean_kernel");
   }
   dim3 grid((a.hw + 31) / 32, (n_planes + a.planes_per_block - 1) / a.planes_per_block, B);
