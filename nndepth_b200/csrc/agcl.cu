@@ -574,7 +574,10 @@ struct IterTile {
 #define NND_AGCL_MINB 2
 #endif
 
-  static constexpr int TW = SMALL ? 16 : NND_AGCL_TW;
+#ifndef NND_AGCL_TW3
+#define NND_AGCL_TW3 14       // 3x3 tiles: 3 x 14 (staged 5 x 16); 3 x 16 measured 74.8 us, 3 x 12 69.6, 3 x 14 65.5, 3 x 18 79.9
+#endif
+  static constexpr int TW = SMALL ? NND_AGCL_TW3 : NND_AGCL_TW;
   static constexpr int HX = SMALL ? 1 : 4;
   static constexpr int HY = SMALL ? 1 : 0;
   static constexpr int SW = TW + 2 * HX;
